@@ -1,0 +1,101 @@
+"""ctypes binding of libhymd_b200.so (C ABI in include/hymd_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or does not load, every
+entry point of hymd_b200.field fails with an explicit error.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libhymd_b200.so")
+
+HYMD_MAX_TYPES = 32
+NCCL_ID_BYTES = 128
+
+F32, F64 = 0, 1
+(FIELD_PHI, FIELD_PHI_FOURIER, FIELD_FORCE_MESH, FIELD_V_EXT, FIELD_PHI_Q, FIELD_PHI_Q_FOURIER,
+ FIELD_PSI, FIELD_ELEC_FIELD) = range(8)
+
+# every symbol include/hymd_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "hymd_last_error", "hymd_abi_version", "hymd_nccl_unique_id", "hymd_ctx_create",
+    "hymd_ctx_destroy", "hymd_ctx_set_box", "hymd_ctx_set_interaction", "hymd_sort_particles",
+    "hymd_set_charges", "hymd_paint", "hymd_field_cycle", "hymd_readout", "hymd_pme_cycle",
+    "hymd_materialize", "hymd_field_energy", "hymd_get_field", "hymd_ctx_status",
+    "hymd_launch_count", "hymd_migrate",
+]
+
+
+class HymdConfig(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_int32),
+        ("dtype", ctypes.c_int32),
+        ("mesh", ctypes.c_int32 * 3),
+        ("box", ctypes.c_double * 3),
+        ("n_types", ctypes.c_int32),
+        ("world_size", ctypes.c_int32),
+        ("rank", ctypes.c_int32),
+        ("pme", ctypes.c_int32),
+        ("sigma", ctypes.c_double),
+        ("elec_conversion", ctypes.c_double),
+        ("A", ctypes.c_double * (HYMD_MAX_TYPES * HYMD_MAX_TYPES)),
+        ("c", ctypes.c_double * HYMD_MAX_TYPES),
+        ("m", ctypes.c_double * HYMD_MAX_TYPES),
+    ]
+
+
+class HymdError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HymdError(
+            f"{LIB_PATH} is missing: build it with `python -m hymd_b200.build` "
+            "(hymd_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    P = ctypes.POINTER
+    lib.hymd_last_error.restype = ctypes.c_char_p
+    lib.hymd_last_error.argtypes = []
+    lib.hymd_abi_version.restype = ctypes.c_int
+    lib.hymd_nccl_unique_id.argtypes = [P(ctypes.c_uint8)]
+    lib.hymd_ctx_create.argtypes = [P(HymdConfig), P(ctypes.c_uint8), P(vp)]
+    lib.hymd_ctx_destroy.argtypes = [vp]
+    lib.hymd_ctx_set_box.argtypes = [vp, P(dbl)]
+    lib.hymd_ctx_set_interaction.argtypes = [vp, P(dbl), P(dbl), P(dbl), dbl, dbl]
+    lib.hymd_sort_particles.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.hymd_set_charges.argtypes = [vp, vp, vp]
+    lib.hymd_paint.argtypes = [vp, vp]
+    lib.hymd_field_cycle.argtypes = [vp, ctypes.c_int, vp]
+    lib.hymd_readout.argtypes = [vp, vp, vp]
+    lib.hymd_pme_cycle.argtypes = [vp, vp, ctypes.c_int, vp]
+    lib.hymd_materialize.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+    lib.hymd_field_energy.argtypes = [vp, P(dbl), dbl, dbl, dbl, P(dbl), vp]
+    lib.hymd_get_field.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, P(vp), P(i64), P(i64)]
+    lib.hymd_ctx_status.argtypes = [vp, P(i64)]
+    lib.hymd_launch_count.argtypes = [vp]
+    lib.hymd_launch_count.restype = i64
+    lib.hymd_migrate.argtypes = [vp, P(vp), P(i32), P(i32), ctypes.c_int, i64, P(i64), vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("hymd_last_error", "hymd_launch_count"):
+            fn.restype = ctypes.c_int
+    if lib.hymd_abi_version() != 1:
+        raise HymdError(f"libhymd_b200.so ABI {lib.hymd_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        msg = load().hymd_last_error().decode("utf-8", "replace")
+        raise HymdError(f"libhymd_b200 error {status}: {msg}")

@@ -1,0 +1,563 @@
+// C ABI of libhymd_b200.so: context life cycle, cuFFT plans, and the per-step entry points
+// (declared in include/hymd_b200.h, which cites the reference call sites each one replaces).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "ctx.cuh"
+
+namespace hymd {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int ceil_log2(long long v) {
+    int b = 0;
+    while ((1LL << b) < v) ++b;
+    return b;
+}
+
+static int dev_alloc(void** p, size_t bytes) {
+    if (*p != nullptr) return HYMD_OK;
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return HYMD_ERR_NOMEM;
+    }
+    return HYMD_OK;
+}
+
+template <typename real>
+static int upload(void* dst, const std::vector<double>& v) {
+    std::vector<real> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = (real)v[i];
+    HYMD_CUDA(cudaMemcpy(dst, h.data(), h.size() * sizeof(real), cudaMemcpyHostToDevice));
+    return HYMD_OK;
+}
+
+static int upload_real(hymd_ctx* c, void* dst, const std::vector<double>& v) {
+    return c->f64 ? upload<double>(dst, v) : upload<float>(dst, v);
+}
+
+// Gaussian factors and wave numbers (fftfreq convention), separable per axis.
+static int build_tables(hymd_ctx* c) {
+    const Geometry& g = c->g;
+    const double sigma = c->cfg.sigma;
+    std::vector<double> tab;
+    const int n[3] = {g.Nx, g.Ny, g.Nz};
+    const int len[3] = {g.Nx, g.Ny, g.Nzc};
+    std::vector<double> k[3];
+    for (int a = 0; a < 3; ++a) {
+        k[a].resize(len[a]);
+        for (int i = 0; i < len[a]; ++i) {
+            const int ni = (i < (n[a] + 1) / 2) ? i : i - n[a];   // numpy.fft.fftfreq ordering
+            k[a][i] = 2.0 * M_PI * ni / g.box[a];
+        }
+    }
+    for (int a = 0; a < 3; ++a)
+        for (int i = 0; i < len[a]; ++i) tab.push_back(exp(-0.5 * sigma * sigma * k[a][i] * k[a][i]));
+    for (int a = 0; a < 3; ++a)
+        for (int i = 0; i < len[a]; ++i) tab.push_back(k[a][i]);
+    HYMD_CHECK(dev_alloc(&c->tab, tab.size() * c->rsz));
+    return upload_real(c, c->tab, tab);
+}
+
+static int build_interaction(hymd_ctx* c) {
+    const int T = c->T;
+    // group types with identical rows of A (they share one potential / force mesh triple)
+    c->U = 0;
+    for (int t = 0; t < T; ++t) {
+        int found = -1;
+        for (int u = 0; u < c->U && found < 0; ++u) {
+            bool same = c->cfg.c[t] == c->cfg.c[c->rowrep[u]];
+            for (int j = 0; j < T && same; ++j)
+                same = c->cfg.A[t * T + j] == c->cfg.A[c->rowrep[u] * T + j];
+            if (same) found = u;
+        }
+        if (found < 0) { found = c->U; c->rowrep[c->U++] = t; }
+        c->urow[t] = found;
+    }
+    const Geometry& g = c->g;
+    const double m = (double)g.Nx * g.Ny * g.Nz;
+    std::vector<double> Au((size_t)c->U * T + 1), cu(c->U);
+    for (int u = 0; u < c->U; ++u) {
+        for (int j = 0; j < T; ++j) Au[u * T + j] = c->cfg.A[c->rowrep[u] * T + j] / m;
+        cu[u] = c->cfg.c[c->rowrep[u]];
+    }
+    Au[(size_t)c->U * T] = 1.0 / m;
+    HYMD_CHECK(dev_alloc(&c->Au, (size_t)(HYMD_MAX_TYPES * HYMD_MAX_TYPES + 1) * c->rsz));
+    HYMD_CHECK(dev_alloc(&c->cu, (size_t)HYMD_MAX_TYPES * c->rsz));
+    HYMD_CHECK(dev_alloc((void**)&c->d_urow, HYMD_MAX_TYPES * sizeof(int)));
+    HYMD_CHECK(dev_alloc(&c->outscale, (size_t)(HYMD_MAX_TYPES + 1) * c->rsz));
+    HYMD_CHECK(upload_real(c, c->Au, Au));
+    HYMD_CHECK(upload_real(c, c->cu, cu));
+    HYMD_CUDA(cudaMemcpy(c->d_urow, c->urow, T * sizeof(int), cudaMemcpyHostToDevice));
+    const double dv = g.box[0] * g.box[1] * g.box[2] / m;
+    std::vector<double> os(T + 1);
+    for (int t = 0; t < T; ++t) os[t] = c->cfg.m[t] / dv;
+    os[T] = 1.0 / dv;
+    return upload_real(c, c->outscale, os);
+}
+
+struct PlanSpec {
+    cufftHandle* h;
+    bool forward;
+    int batch;
+    bool ghost_out;   // c2r into the ghost-padded layout
+};
+
+static int build_plans(hymd_ctx* c) {
+    const Geometry& g = c->g;
+    if (g.P != 1) {
+        set_error("multi-GPU slab FFT plans are built in slabfft (not available in this build)");
+        return HYMD_ERR_INVALID;
+    }
+    int n[3] = {g.Nx, g.Ny, g.Nz};
+    int real_embed[3] = {g.Nx, g.Ny, g.Nz};
+    int ghost_embed[3] = {g.Nx + 1, g.Ny + 1, g.Nzp};
+    int k_embed[3] = {g.Nx, g.Ny, g.Nzcp};
+    std::vector<PlanSpec> specs = {
+        {&c->plan_r2c_T, true, c->T, false},  {&c->plan_c2r_3U, false, 3 * c->U, true},
+        {&c->plan_c2r_T, false, c->T, false}, {&c->plan_c2r_U, false, c->U, false}};
+    if (c->cfg.pme) {
+        specs.push_back({&c->plan_r2c_1, true, 1, false});
+        specs.push_back({&c->plan_c2r_3, false, 3, true});
+        specs.push_back({&c->plan_c2r_1, false, 1, false});
+    }
+    size_t work = 0;
+    for (auto& sp : specs) {
+        HYMD_CUFFT(cufftCreate(sp.h));
+        HYMD_CUFFT(cufftSetAutoAllocation(*sp.h, 0));
+        size_t ws = 0;
+        if (sp.forward) {
+            HYMD_CUFFT(cufftMakePlanMany(*sp.h, 3, n, real_embed, 1, (int)g.real_elems, k_embed, 1,
+                                         (int)g.k_elems, c->f64 ? CUFFT_D2Z : CUFFT_R2C, sp.batch,
+                                         &ws));
+        } else {
+            int* oe = sp.ghost_out ? ghost_embed : real_embed;
+            long long od = sp.ghost_out ? g.ghost_elems : g.real_elems;
+            HYMD_CUFFT(cufftMakePlanMany(*sp.h, 3, n, k_embed, 1, (int)g.k_elems, oe, 1, (int)od,
+                                         c->f64 ? CUFFT_Z2D : CUFFT_C2R, sp.batch, &ws));
+        }
+        if (ws > work) work = ws;
+    }
+    HYMD_CHECK(dev_alloc(&c->fft_work, work));
+    for (auto& sp : specs) HYMD_CUFFT(cufftSetWorkArea(*sp.h, c->fft_work));
+    c->plans_ready = true;
+    return HYMD_OK;
+}
+
+static int exec_r2c(hymd_ctx* c, cufftHandle h, void* in, void* out, cudaStream_t s) {
+    HYMD_CUFFT(cufftSetStream(h, s));
+    if (c->f64) HYMD_CUFFT(cufftExecD2Z(h, (cufftDoubleReal*)in, (cufftDoubleComplex*)out));
+    else HYMD_CUFFT(cufftExecR2C(h, (cufftReal*)in, (cufftComplex*)out));
+    c->launches += 2;   // cuFFT launches >= 2 kernels per 3-D transform (not ours; lower bound)
+    return HYMD_OK;
+}
+
+static int exec_c2r(hymd_ctx* c, cufftHandle h, void* in, void* out, cudaStream_t s) {
+    HYMD_CUFFT(cufftSetStream(h, s));
+    if (c->f64) HYMD_CUFFT(cufftExecZ2D(h, (cufftDoubleComplex*)in, (cufftDoubleReal*)out));
+    else HYMD_CUFFT(cufftExecC2R(h, (cufftComplex*)in, (cufftReal*)out));
+    c->launches += 2;
+    return HYMD_OK;
+}
+
+static int ensure_particle_capacity(hymd_ctx* c, int64_t n) {
+    if (n <= c->cap) return HYMD_OK;
+    int64_t cap = n + n / 8 + 1024;
+    void* bufs[] = {c->rec, c->key, c->rank_in_cell, c->q_sorted};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    c->rec = c->q_sorted = nullptr;
+    c->key = c->rank_in_cell = nullptr;
+    HYMD_CHECK(dev_alloc(&c->rec, (size_t)cap * (c->f64 ? sizeof(Rec64) : sizeof(Rec32))));
+    HYMD_CHECK(dev_alloc((void**)&c->key, (size_t)cap * 4));
+    HYMD_CHECK(dev_alloc((void**)&c->rank_in_cell, (size_t)cap * 4));
+    HYMD_CHECK(dev_alloc(&c->q_sorted, (size_t)cap * c->rsz));
+    c->cap = cap;
+    return HYMD_OK;
+}
+
+}  // namespace hymd
+
+using namespace hymd;
+
+extern "C" {
+
+const char* hymd_last_error(void) { return g_err; }
+int hymd_abi_version(void) { return HYMD_B200_ABI_VERSION; }
+
+int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** out) {
+    if (!cfg || !out) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (cfg->struct_size != (int32_t)sizeof(hymd_config)) {
+        set_error("hymd_config size mismatch: caller %d, library %zu", cfg->struct_size,
+                  sizeof(hymd_config));
+        return HYMD_ERR_INVALID;
+    }
+    if (cfg->n_types < 1 || cfg->n_types > HYMD_MAX_TYPES) {
+        set_error("n_types = %d outside [1, %d]", cfg->n_types, HYMD_MAX_TYPES);
+        return HYMD_ERR_INVALID;
+    }
+    for (int a = 0; a < 3; ++a)
+        if (cfg->mesh[a] < 2 || !(cfg->box[a] > 0.0)) {
+            set_error("invalid mesh/box on axis %d: %d, %g", a, cfg->mesh[a], cfg->box[a]);
+            return HYMD_ERR_INVALID;
+        }
+    const int P = cfg->world_size;
+    if (P < 1 || cfg->rank < 0 || cfg->rank >= P || cfg->mesh[0] % P || (P > 1 && cfg->mesh[1] % P)) {
+        set_error("mesh (%d,%d) not divisible into %d slabs (rank %d)", cfg->mesh[0], cfg->mesh[1],
+                  P, cfg->rank);
+        return HYMD_ERR_INVALID;
+    }
+    if (P > 1 && !nccl_id) { set_error("nccl_id required when world_size > 1"); return HYMD_ERR_INVALID; }
+
+    hymd_ctx* c = new hymd_ctx();
+    memset(c, 0, sizeof(*c));
+    c->cfg = *cfg;
+    c->f64 = cfg->dtype == HYMD_F64;
+    c->rsz = c->f64 ? 8 : 4;
+    c->T = cfg->n_types;
+    cudaGetDevice(&c->dev);
+    Geometry& g = c->g;
+    g.Nx = cfg->mesh[0]; g.Ny = cfg->mesh[1]; g.Nz = cfg->mesh[2];
+    g.P = P; g.rank = cfg->rank;
+    g.nxl = g.Nx / P; g.x0 = g.rank * g.nxl;
+    g.nyl = g.Ny / P; g.y0 = g.rank * g.nyl;
+    g.Nzc = g.Nz / 2 + 1;
+    g.Nzcp = g.Nzc + (g.Nzc & 1);
+    g.Nzp = (g.Nz + 1 + 3) / 4 * 4;
+    const int bits = c->f64 ? 64 : 32;
+    g.fbx = bits - ceil_log2(g.nxl > 2 ? g.nxl : 2);
+    g.fby = bits - ceil_log2(g.Ny);
+    g.fbz = bits - ceil_log2(g.Nz);
+    if (c->f64) {
+        if (g.fbx > 52) g.fbx = 52;
+        if (g.fby > 52) g.fby = 52;
+        if (g.fbz > 52) g.fbz = 52;
+    }
+    for (int a = 0; a < 3; ++a) g.box[a] = cfg->box[a];
+    g.ncell = (long long)g.nxl * g.Ny * g.Nz;
+    g.real_elems = (long long)(P == 1 ? g.nxl : g.nxl + 1) * g.Ny * g.Nz;
+    g.ghost_elems = (long long)(g.nxl + 1) * (g.Ny + 1) * g.Nzp;
+    g.k_elems = (long long)g.Nx * g.nyl * g.Nzcp;
+    if (g.ncell + 1 >= (1LL << 31) || g.ghost_elems >= (1LL << 31) || g.k_elems >= (1LL << 31)) {
+        set_error("local mesh too large for 32-bit cell keys / cuFFT int strides");
+        hymd_ctx_destroy(c);
+        return HYMD_ERR_INVALID;
+    }
+
+    int st = HYMD_OK;
+    auto fail = [&](int code) { hymd_ctx_destroy(c); return code; };
+    if ((st = dev_alloc((void**)&c->cell_count, (size_t)(g.ncell + 1) * 4))) return fail(st);
+    if ((st = dev_alloc((void**)&c->cell_start, (size_t)(g.ncell + 1) * 4))) return fail(st);
+    if ((st = dev_alloc((void**)&c->scalars, sizeof(DeviceScalars)))) return fail(st);
+    c->scan_tmp_bytes = scan_temp_bytes(g.ncell + 1);
+    if ((st = dev_alloc(&c->scan_tmp, c->scan_tmp_bytes))) return fail(st);
+    if ((st = build_tables(c))) return fail(st);
+    if ((st = build_interaction(c))) return fail(st);
+    const size_t rb = (size_t)g.real_elems * c->rsz, kb = (size_t)g.k_elems * 2 * c->rsz,
+                 gb = (size_t)g.ghost_elems * c->rsz;
+    if ((st = dev_alloc(&c->phi, c->T * rb))) return fail(st);
+    if ((st = dev_alloc(&c->phi_hat, c->T * kb))) return fail(st);
+    if ((st = dev_alloc(&c->f_hat, 3 * (size_t)c->T * kb))) return fail(st);   // sized for U == T
+    if ((st = dev_alloc(&c->gmesh, 3 * (size_t)c->T * gb))) return fail(st);
+    if (cudaMemset(c->gmesh, 0, 3 * (size_t)c->T * gb) != cudaSuccess) return fail(HYMD_ERR_CUDA);
+    if (cfg->pme) {
+        if ((st = dev_alloc(&c->phi_q, rb))) return fail(st);
+        if ((st = dev_alloc(&c->phiq_hat, kb))) return fail(st);
+        if ((st = dev_alloc(&c->e_hat, 4 * kb))) return fail(st);
+        if ((st = dev_alloc(&c->emesh, 3 * gb))) return fail(st);
+        if (cudaMemset(c->emesh, 0, 3 * gb) != cudaSuccess) return fail(HYMD_ERR_CUDA);
+    }
+    if ((st = build_plans(c))) return fail(st);
+    if ((st = readout_setup(c))) return fail(st);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(HYMD_ERR_CUDA);
+    *out = c;
+    return HYMD_OK;
+}
+
+int hymd_ctx_destroy(hymd_ctx* c) {
+    if (!c) return HYMD_OK;
+    cudaDeviceSynchronize();
+    if (c->plans_ready) {
+        cufftHandle hs[] = {c->plan_r2c_T, c->plan_c2r_3U, c->plan_c2r_T, c->plan_c2r_U};
+        for (cufftHandle h : hs) cufftDestroy(h);
+        if (c->cfg.pme) {
+            cufftDestroy(c->plan_r2c_1); cufftDestroy(c->plan_c2r_3); cufftDestroy(c->plan_c2r_1);
+        }
+    }
+    void* bufs[] = {c->rec, c->key, c->rank_in_cell, c->cell_count, c->cell_start, c->q_sorted,
+                    c->scalars, c->scan_tmp, c->tab, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
+                    c->phi_hat, c->f_hat, c->gmesh, c->v_hat, c->phif_hat, c->tmp_hat, c->v_ext,
+                    c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->emesh, c->psi, c->fft_work};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    delete c;
+    return HYMD_OK;
+}
+
+int hymd_ctx_set_box(hymd_ctx* c, const double box[3]) {
+    if (!c || !box) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    for (int a = 0; a < 3; ++a) { c->cfg.box[a] = box[a]; c->g.box[a] = box[a]; }
+    c->sorted = false;
+    HYMD_CHECK(build_tables(c));
+    return build_interaction(c);
+}
+
+int hymd_ctx_set_interaction(hymd_ctx* c, const double* A, const double* cc, const double* m,
+                             double sigma, double elec_conversion) {
+    if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    const int T = c->T;
+    if (A) memcpy(c->cfg.A, A, sizeof(double) * T * T);
+    if (cc) memcpy(c->cfg.c, cc, sizeof(double) * T);
+    if (m) memcpy(c->cfg.m, m, sizeof(double) * T);
+    c->cfg.sigma = sigma;
+    c->cfg.elec_conversion = elec_conversion;
+    const int oldU = c->U;
+    HYMD_CHECK(build_tables(c));
+    HYMD_CHECK(build_interaction(c));
+    if (c->U != oldU) {
+        // the number of distinct potential rows changed: batch sizes and the TMA box set change
+        cufftDestroy(c->plan_c2r_3U); cufftDestroy(c->plan_c2r_U);
+        cufftDestroy(c->plan_r2c_T); cufftDestroy(c->plan_c2r_T);
+        if (c->cfg.pme) { cufftDestroy(c->plan_r2c_1); cufftDestroy(c->plan_c2r_3); cufftDestroy(c->plan_c2r_1); }
+        c->plans_ready = false;
+        if (c->fft_work) { cudaFree(c->fft_work); c->fft_work = nullptr; }
+        HYMD_CHECK(build_plans(c));
+        HYMD_CHECK(readout_setup(c));
+    }
+    return HYMD_OK;
+}
+
+int hymd_sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types,
+                        const void* d_charges, int64_t n, void* stream) {
+    if (!c || (n > 0 && (!d_pos || !d_types))) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    const int64_t lim = c->f64 ? (1LL << 31) : (1LL << REC32_IDX_BITS);
+    if (n < 0 || n >= lim) {
+        set_error("n = %lld particles exceeds the per-GPU limit %lld", (long long)n, (long long)lim);
+        return HYMD_ERR_CAPACITY;
+    }
+    HYMD_CHECK(ensure_particle_capacity(c, n));
+    c->np = n;
+    c->has_charges = d_charges != nullptr;
+    HYMD_CHECK(sort_particles(c, d_pos, d_types, d_charges, n, (cudaStream_t)stream));
+    c->sorted = true;
+    return HYMD_OK;
+}
+
+int hymd_set_charges(hymd_ctx* c, const void* d_charges, void* stream) {
+    if (!c || !d_charges) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (!c->sorted) { set_error("hymd_set_charges before hymd_sort_particles"); return HYMD_ERR_STATE; }
+    HYMD_CHECK(gather_charges(c, d_charges, (cudaStream_t)stream));
+    c->has_charges = true;
+    return HYMD_OK;
+}
+
+int hymd_paint(hymd_ctx* c, void* stream) {
+    if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (!c->sorted) { set_error("hymd_paint before hymd_sort_particles"); return HYMD_ERR_STATE; }
+    HYMD_CHECK(paint_types(c, (cudaStream_t)stream));
+    c->phi_is_filtered = false;
+    c->have_phi_hat = false;
+    return HYMD_OK;
+}
+
+static int materialize_impl(hymd_ctx* c, bool want_phi, bool want_v, cudaStream_t s) {
+    const Geometry& g = c->g;
+    const size_t kb = (size_t)g.k_elems * 2 * c->rsz, rb = (size_t)g.real_elems * c->rsz;
+    if (want_v) {
+        HYMD_CHECK(dev_alloc(&c->v_ext, c->T * rb));
+        HYMD_CHECK(exec_c2r(c, c->plan_c2r_U, c->v_hat, c->v_ext, s));   // consumes v_hat
+    }
+    if (want_phi) {
+        HYMD_CHECK(dev_alloc(&c->tmp_hat, c->T * kb));
+        HYMD_CUDA(cudaMemcpyAsync(c->tmp_hat, c->phif_hat, c->T * kb, cudaMemcpyDeviceToDevice, s));
+        HYMD_CHECK(exec_c2r(c, c->plan_c2r_T, c->tmp_hat, c->phi, s));
+        c->phi_is_filtered = true;
+    }
+    return HYMD_OK;
+}
+
+int hymd_field_cycle(hymd_ctx* c, int compute_potential, void* stream) {
+    if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const Geometry& g = c->g;
+    const size_t kb = (size_t)g.k_elems * 2 * c->rsz;
+    if (c->phi_is_filtered) { set_error("hymd_field_cycle needs a fresh hymd_paint"); return HYMD_ERR_STATE; }
+    HYMD_CHECK(exec_r2c(c, c->plan_r2c_T, c->phi, c->phi_hat, s));
+    c->have_phi_hat = true;
+    const bool cp = compute_potential != 0;
+    if (cp) {
+        HYMD_CHECK(dev_alloc(&c->v_hat, c->T * kb));
+        HYMD_CHECK(dev_alloc(&c->phif_hat, c->T * kb));
+    }
+    HYMD_CHECK(kspace_forces(c, cp, cp, s));
+    HYMD_CHECK(exec_c2r(c, c->plan_c2r_3U, c->f_hat, c->gmesh, s));
+    HYMD_CHECK(fill_ghosts(c, c->gmesh, 3 * c->U, s));
+    c->have_forces = true;
+    c->have_phif = cp;
+    if (cp) HYMD_CHECK(materialize_impl(c, true, true, s));
+    return HYMD_OK;
+}
+
+int hymd_materialize(hymd_ctx* c, int want_phi, int want_phi_fourier, int want_v_ext,
+                     int want_psi, void* stream) {
+    if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t kb = (size_t)c->g.k_elems * 2 * c->rsz;
+    if (want_psi && !c->have_psi) {
+        if (!c->cfg.pme || !c->have_phiq_hat) {
+            set_error("hymd_materialize(psi) before hymd_pme_cycle");
+            return HYMD_ERR_STATE;
+        }
+        HYMD_CHECK(dev_alloc(&c->phiqf_hat, kb));
+        HYMD_CHECK(dev_alloc(&c->psi, (size_t)c->g.real_elems * c->rsz));
+        HYMD_CHECK(kspace_pme(c, true, s));   // e_hat is scratch between cycles
+        HYMD_CHECK(exec_c2r(c, c->plan_c2r_1, (char*)c->e_hat + 3 * kb, c->psi, s));
+        c->have_psi = true;
+    }
+    if (!(want_phi || want_phi_fourier || want_v_ext)) return HYMD_OK;
+    if (!c->have_phi_hat) { set_error("hymd_materialize before hymd_field_cycle"); return HYMD_ERR_STATE; }
+    const bool need_phi = want_phi && !c->phi_is_filtered;
+    const bool need_v = want_v_ext != 0;
+    const bool need_pf = (want_phi_fourier || need_phi) && !c->have_phif;
+    if (need_pf || need_v) {
+        HYMD_CHECK(dev_alloc(&c->v_hat, c->T * kb));
+        HYMD_CHECK(dev_alloc(&c->phif_hat, c->T * kb));
+        HYMD_CHECK(kspace_forces(c, true, true, s));   // f_hat is scratch between cycles
+        c->have_phif = true;
+    }
+    return materialize_impl(c, need_phi, need_v, s);
+}
+
+int hymd_readout(hymd_ctx* c, void* d_force, void* stream) {
+    if (!c || (c->np > 0 && !d_force)) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (!c->sorted || !c->have_forces) {
+        set_error("hymd_readout needs hymd_sort_particles and hymd_field_cycle first");
+        return HYMD_ERR_STATE;
+    }
+    if (c->np == 0) return HYMD_OK;
+    return readout_forces(c, d_force, (cudaStream_t)stream);
+}
+
+int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) {
+    if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (!c->cfg.pme) { set_error("context created without PME buffers"); return HYMD_ERR_STATE; }
+    if (!c->sorted || !c->has_charges) {
+        set_error("hymd_pme_cycle needs hymd_sort_particles with charges");
+        return HYMD_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const Geometry& g = c->g;
+    const size_t kb = (size_t)g.k_elems * 2 * c->rsz, rb = (size_t)g.real_elems * c->rsz;
+    HYMD_CHECK(paint_charges(c, s));
+    HYMD_CHECK(exec_r2c(c, c->plan_r2c_1, c->phi_q, c->phiq_hat, s));
+    c->have_phiq_hat = true;
+    if (want_psi) {
+        HYMD_CHECK(dev_alloc(&c->phiqf_hat, kb));
+        HYMD_CHECK(dev_alloc(&c->psi, rb));
+    }
+    HYMD_CHECK(kspace_pme(c, want_psi != 0, s));
+    HYMD_CHECK(exec_c2r(c, c->plan_c2r_3, c->e_hat, c->emesh, s));
+    HYMD_CHECK(fill_ghosts(c, c->emesh, 3, s));
+    if (want_psi)
+        HYMD_CHECK(exec_c2r(c, c->plan_c2r_1, (char*)c->e_hat + 3 * kb, c->psi, s));
+    c->have_psi = want_psi != 0;
+    if (c->np > 0 && d_elec_force) HYMD_CHECK(readout_pme(c, d_elec_force, s));
+    return HYMD_OK;
+}
+
+int hymd_field_energy(hymd_ctx* c, const double* chi, double kappa, double rho0, double a,
+                      double out[2], void* stream) {
+    if (!c || !chi || !out) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (!c->phi_is_filtered) {
+        set_error("hymd_field_energy needs the filtered densities (hymd_materialize / compute_potential)");
+        return HYMD_ERR_STATE;
+    }
+    if (c->cfg.pme && c->has_charges && !c->have_psi) {
+        set_error("hymd_field_energy needs psi (hymd_pme_cycle with want_psi)");
+        return HYMD_ERR_STATE;
+    }
+    return field_energy(c, chi, kappa, rho0, a, out, (cudaStream_t)stream);
+}
+
+int hymd_get_field(hymd_ctx* c, int field_id, int t, int d, void** d_ptr, int64_t dims[3],
+                   int64_t pitch[3]) {
+    if (!c || !d_ptr || !dims || !pitch) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    const Geometry& g = c->g;
+    const size_t rb = (size_t)g.real_elems * c->rsz, kb = (size_t)g.k_elems * 2 * c->rsz,
+                 gb = (size_t)g.ghost_elems * c->rsz;
+    auto real_geom = [&]() {
+        dims[0] = g.nxl; dims[1] = g.Ny; dims[2] = g.Nz;
+        pitch[0] = (int64_t)g.Ny * g.Nz; pitch[1] = g.Nz; pitch[2] = 1;
+    };
+    auto ghost_geom = [&]() {
+        dims[0] = g.nxl; dims[1] = g.Ny; dims[2] = g.Nz;
+        pitch[0] = (int64_t)(g.Ny + 1) * g.Nzp; pitch[1] = g.Nzp; pitch[2] = 1;
+    };
+    auto k_geom = [&]() {
+        dims[0] = g.Nx; dims[1] = g.nyl; dims[2] = g.Nzc;
+        pitch[0] = (int64_t)g.nyl * g.Nzcp; pitch[1] = g.Nzcp; pitch[2] = 1;
+    };
+    const bool t_ok = t >= 0 && t < c->T, d_ok = d >= 0 && d < 3;
+    char* p = nullptr;
+    switch (field_id) {
+        case HYMD_FIELD_PHI: if (!t_ok) break; p = (char*)c->phi + t * rb; real_geom(); break;
+        case HYMD_FIELD_PHI_FOURIER:
+            if (!t_ok || !c->phif_hat) break; p = (char*)c->phif_hat + t * kb; k_geom(); break;
+        case HYMD_FIELD_FORCE_MESH:
+            if (!t_ok || !d_ok) break; p = (char*)c->gmesh + (3 * c->urow[t] + d) * gb; ghost_geom(); break;
+        case HYMD_FIELD_V_EXT:
+            if (!t_ok || !c->v_ext) break; p = (char*)c->v_ext + c->urow[t] * rb; real_geom(); break;
+        case HYMD_FIELD_PHI_Q: if (!c->phi_q) break; p = (char*)c->phi_q; real_geom(); break;
+        case HYMD_FIELD_PHI_Q_FOURIER: if (!c->phiqf_hat) break; p = (char*)c->phiqf_hat; k_geom(); break;
+        case HYMD_FIELD_PSI: if (!c->psi) break; p = (char*)c->psi; real_geom(); break;
+        case HYMD_FIELD_ELEC_FIELD:
+            if (!d_ok || !c->emesh) break; p = (char*)c->emesh + d * gb; ghost_geom(); break;
+        default: break;
+    }
+    if (!p) {
+        set_error("field %d [t=%d, d=%d] is not available (not allocated / not materialized)",
+                  field_id, t, d);
+        return HYMD_ERR_STATE;
+    }
+    *d_ptr = p;
+    return HYMD_OK;
+}
+
+int64_t hymd_launch_count(hymd_ctx* c) { return c ? c->launches : 0; }
+
+int hymd_ctx_status(hymd_ctx* c, int64_t out[4]) {
+    if (!c || !out) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    DeviceScalars h;
+    HYMD_CUDA(cudaDeviceSynchronize());
+    HYMD_CUDA(cudaMemcpy(&h, c->scalars, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = h.max_cell_count; out[1] = h.out_of_slab; out[2] = c->np; out[3] = c->U;
+    return HYMD_OK;
+}
+
+int hymd_nccl_unique_id(uint8_t id[HYMD_NCCL_UNIQUE_ID_BYTES]) {
+    (void)id;
+    set_error("NCCL support is not compiled into this build yet");
+    return HYMD_ERR_NCCL;
+}
+
+int hymd_migrate(hymd_ctx* c, void** d_arrays, const int32_t* width, const int32_t* elem_size,
+                 int n_arrays, int64_t capacity, int64_t* n_inout, void* stream) {
+    (void)d_arrays; (void)width; (void)elem_size; (void)n_arrays; (void)capacity; (void)stream;
+    if (!c || !n_inout) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (c->g.P == 1) return HYMD_OK;   // one slab: nothing to exchange
+    set_error("hymd_migrate: multi-GPU exchange not available in this build");
+    return HYMD_ERR_NCCL;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// Internal context shared by the translation units of libhymd_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/hymd_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libhymd_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace hymd {
+
+void set_error(const char* fmt, ...);
+
+#define HYMD_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            hymd::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                 \
+                            cudaGetErrorString(e_));                                      \
+            return HYMD_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define HYMD_CUFFT(call)                                                                  \
+    do {                                                                                  \
+        cufftResult r_ = (call);                                                          \
+        if (r_ != CUFFT_SUCCESS) {                                                        \
+            hymd::set_error("%s:%d: %s -> cufft error %d", __FILE__, __LINE__, #call,     \
+                            (int)r_);                                                     \
+            return HYMD_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define HYMD_CHECK(call)                                                                  \
+    do {                                                                                  \
+        int s_ = (call);                                                                  \
+        if (s_ != HYMD_OK) return s_;                                                     \
+    } while (0)
+
+#define HYMD_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                                  \
+        (ctx)->launches++;                                                                \
+        cudaError_t e_ = cudaGetLastError();                                              \
+        if (e_ != cudaSuccess) {                                                          \
+            hymd::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,             \
+                            cudaGetErrorString(e_));                                      \
+            return HYMD_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+// Tile of mesh cells a paint CTA owns (vertices) / a readout CTA stages through TMA.
+constexpr int PAINT_TX = 8, PAINT_TY = 8, PAINT_TZ = 32;
+
+// Sorted particle record.  Coordinates are unsigned fixed point in local-slab grid units:
+// integer part = mesh cell, fraction = CIC offset d.  meta = original index | type << idx_bits.
+struct __align__(16) Rec32 {
+    uint32_t ux, uy, uz, meta;
+};
+struct __align__(16) Rec64 {
+    unsigned long long ux, uy, uz, meta;
+};
+constexpr int REC32_IDX_BITS = 27;  // <= 134M particles per GPU, <= 32 types
+constexpr int REC64_IDX_BITS = 40;
+
+struct DeviceScalars {
+    unsigned int max_cell_count;   // max particles in one cell (paint fixed-point scale)
+    unsigned int qmax_bits;        // max |charge| as float bits
+    unsigned int out_of_slab;      // particles outside the local slab (multi-GPU)
+    unsigned int pad;
+};
+
+struct Geometry {
+    int Nx, Ny, Nz;        // global mesh
+    int nxl, x0;           // local slab [x0, x0+nxl)
+    int P, rank;
+    int nyl, y0;           // k-space (transposed) local y range
+    int Nzc, Nzcp;         // complex z extent and padded pitch (even)
+    int Nzp;               // padded real z pitch of ghost meshes
+    int fbx, fby, fbz;     // fraction bits of the fixed-point coordinates
+    double box[3];
+    long long ncell;       // nxl*Ny*Nz
+    long long real_elems;  // nxl*Ny*Nz
+    long long ghost_elems; // (nxl+1)*(Ny+1)*Nzp
+    long long k_elems;     // Nx*nyl*Nzcp  (complex elements per spectrum)
+};
+
+}  // namespace hymd
+
+struct hymd_ctx {
+    hymd_config cfg;
+    hymd::Geometry g;
+    int dev;
+    bool f64;
+    int T, U;
+    int urow[HYMD_MAX_TYPES];     // type -> unique potential row
+    int rowrep[HYMD_MAX_TYPES];   // unique row -> representative type
+    size_t rsz;                   // sizeof(real)
+
+    // particles
+    int64_t np, cap;
+    bool sorted, has_charges;
+    void* rec;
+    uint32_t* key;
+    uint32_t* rank_in_cell;
+    uint32_t* cell_count;   // ncell + 1
+    uint32_t* cell_start;   // ncell + 1
+    void* q_sorted;
+    hymd::DeviceScalars* scalars;
+    void* scan_tmp;
+    size_t scan_tmp_bytes;
+
+    // k-space tables (real): hx,hy,hz Gaussian factors, kx,ky,kz wave numbers; Au (U x T) / M
+    void* tab;            // packed: hx[Nx] hy[Ny] hz[Nzc] kx[Nx] ky[Ny] kz[Nzc]
+    void* Au;             // U*T reals, already divided by M
+    void* cu;             // U offsets (added at k = 0 for v_ext)
+    int* d_urow;          // T ints
+    void* outscale;       // T reals: m_t / dV (paint output scale, without the fixed-point factor)
+
+    // fields
+    void* phi;            // T x real_elems
+    void* phi_hat;        // T x k_elems complex (raw spectra of phi, unnormalised)
+    void* f_hat;          // 3U x k_elems complex
+    void* gmesh;          // 3U x ghost_elems real
+    void* v_hat;          // U x k_elems (lazy)
+    void* phif_hat;       // T x k_elems (lazy, filtered & normalised = reference phi_fourier)
+    void* tmp_hat;        // max(T,U) x k_elems (lazy scratch for c2r of by-products)
+    void* v_ext;          // T x real_elems (lazy)
+    bool phi_is_filtered;   // phi holds the filtered densities (reference semantics after update_field)
+    bool have_phi_hat;      // raw density spectra of the last paint are valid
+    bool have_phif;         // phif_hat valid for the current spectra
+    bool have_forces;       // gmesh valid
+    bool have_psi;
+    bool have_phiq_hat;
+    // PME
+    void* phi_q;          // real_elems
+    void* phiq_hat;       // k_elems raw
+    void* phiqf_hat;      // k_elems filtered/normalised (reference phi_q_fourier)
+    void* e_hat;          // 4 x k_elems: E_x,E_y,E_z, psi
+    void* emesh;          // 3 x ghost_elems
+    void* psi;            // real_elems
+
+    // cuFFT
+    cufftHandle plan_r2c_T, plan_c2r_3U, plan_c2r_T, plan_c2r_U, plan_r2c_1, plan_c2r_3, plan_c2r_1;
+    bool plans_ready;
+    void* fft_work;         // one work area shared by all plans (they run on one stream)
+
+    // readout TMA
+    CUtensorMap tmap_gmesh, tmap_emesh;
+    int rtx, rty, rtz, rbz;       // readout tile and box z extent
+    size_t readout_smem, readout_smem_pme;
+
+    int64_t launches;
+};
+
+namespace hymd {
+// sort.cu
+int sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types, const void* d_q,
+                   int64_t n, cudaStream_t s);
+size_t scan_temp_bytes(long long n);
+int gather_charges(hymd_ctx* c, const void* d_q, cudaStream_t s);
+// paint.cu
+int paint_types(hymd_ctx* c, cudaStream_t s);
+int paint_charges(hymd_ctx* c, cudaStream_t s);
+// kspace.cu
+int kspace_forces(hymd_ctx* c, bool want_v, bool want_phif, cudaStream_t s);
+int kspace_pme(hymd_ctx* c, bool want_psi, cudaStream_t s);
+// readout.cu
+int readout_setup(hymd_ctx* c);
+int readout_forces(hymd_ctx* c, void* d_force, cudaStream_t s);
+int readout_pme(hymd_ctx* c, void* d_force, cudaStream_t s);
+int fill_ghosts(hymd_ctx* c, void* mesh, int nfields, cudaStream_t s);
+// energy.cu
+int field_energy(hymd_ctx* c, const double* chi, double kappa, double rho0, double a,
+                 double out[2], cudaStream_t s);
+}  // namespace hymd

@@ -1,0 +1,191 @@
+// Cell binning of the local particles: replaces pm.decompose (main.py:977-980, 1007).
+//
+// A counting sort keyed by the (local-slab, row-major) mesh cell of each particle:
+//   count   : one global atomicAdd per particle on the per-cell counter -> rank within cell
+//   scan    : exclusive prefix sum over the ncell+1 counters            -> cell_start[]
+//   scatter : record[cell_start[key] + rank] = fixed-point coordinates | index | type
+// The order of particles inside a cell depends on atomic arrival order; paint accumulates in
+// integer fixed point (order independent) and readout is a pure gather, so results are
+// bitwise reproducible anyway.
+#include <cub/device/device_scan.cuh>
+
+#include "ctx.cuh"
+
+namespace hymd {
+
+struct SortParams {
+    int Nx, Ny, Nz, nxl, x0;
+    int fbx, fby, fbz;
+    double sx, sy, sz;  // N/L per axis
+};
+
+__device__ __forceinline__ void split_coord(double x, int n, int& cell, double& frac) {
+    double f = floor(x);
+    double d = x - f;
+    long long c = (long long)f % n;
+    if (c < 0) c += n;
+    if (d >= 1.0) {  // x = -tiny rounds to d == 1
+        d = 0.0;
+        c = (c + 1 == n) ? 0 : c + 1;
+    }
+    cell = (int)c;
+    frac = d;
+}
+
+template <typename UT>
+__device__ __forceinline__ UT pack_coord(int cell, double frac, int fb) {
+    UT f = (UT)(frac * (double)((UT)1 << fb));
+    if (f >> fb) f = ((UT)1 << fb) - 1;  // frac*2^fb rounded up to 2^fb
+    return ((UT)cell << fb) | f;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos, long long n,
+                                                    SortParams p, uint32_t* __restrict__ cnt,
+                                                    uint32_t* __restrict__ key,
+                                                    uint32_t* __restrict__ rnk,
+                                                    DeviceScalars* __restrict__ sc) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    unsigned int r1 = 0, bad = 0;
+    if (i < n) {
+        int cx, cy, cz;
+        double d;
+        split_coord((double)pos[3 * i + 0] * p.sx, p.Nx, cx, d);
+        split_coord((double)pos[3 * i + 1] * p.sy, p.Ny, cy, d);
+        split_coord((double)pos[3 * i + 2] * p.sz, p.Nz, cz, d);
+        int lx = cx - p.x0;
+        if (lx < 0 || lx >= p.nxl) {
+            bad = 1;
+            lx = lx < 0 ? 0 : p.nxl - 1;
+        }
+        uint32_t k = (uint32_t)(((long long)lx * p.Ny + cy) * p.Nz + cz);
+        uint32_t r = atomicAdd(&cnt[k], 1u);
+        key[i] = k;
+        rnk[i] = r;
+        r1 = r + 1;
+    }
+    unsigned int m = __reduce_max_sync(0xffffffffu, r1);
+    unsigned int b = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (m > sc->max_cell_count) atomicMax(&sc->max_cell_count, m);
+        if (b) atomicAdd(&sc->out_of_slab, b);
+    }
+}
+
+template <typename real, typename RecT, typename UT, int IDX_BITS>
+__global__ void __launch_bounds__(256) scatter_kernel(
+    const real* __restrict__ pos, const int32_t* __restrict__ types, const real* __restrict__ q,
+    long long n, SortParams p, const uint32_t* __restrict__ start, const uint32_t* __restrict__ key,
+    const uint32_t* __restrict__ rnk, RecT* __restrict__ rec, real* __restrict__ q_sorted,
+    DeviceScalars* __restrict__ sc) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float aq = 0.f;
+    if (i < n) {
+        int cx, cy, cz;
+        double dx, dy, dz;
+        split_coord((double)pos[3 * i + 0] * p.sx, p.Nx, cx, dx);
+        split_coord((double)pos[3 * i + 1] * p.sy, p.Ny, cy, dy);
+        split_coord((double)pos[3 * i + 2] * p.sz, p.Nz, cz, dz);
+        int lx = cx - p.x0;
+        lx = lx < 0 ? 0 : (lx >= p.nxl ? p.nxl - 1 : lx);
+        size_t slot = (size_t)start[key[i]] + rnk[i];
+        RecT r;
+        r.ux = pack_coord<UT>(lx, dx, p.fbx);
+        r.uy = pack_coord<UT>(cy, dy, p.fby);
+        r.uz = pack_coord<UT>(cz, dz, p.fbz);
+        r.meta = (UT)i | ((UT)(uint32_t)types[i] << IDX_BITS);
+        rec[slot] = r;
+        if (q != nullptr) {
+            real qi = q[i];
+            q_sorted[slot] = qi;
+            aq = fabsf((float)qi);
+        }
+    }
+    if (q != nullptr) {
+        unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(aq));
+        if ((threadIdx.x & 31) == 0 && m > sc->qmax_bits) atomicMax(&sc->qmax_bits, m);
+    }
+}
+
+// Charges into sorted order for a sort that was made without them (update_field_force_q is
+// called after update_field on the same positions: main.py:1006-1058).
+template <typename real, typename RecT, typename UT, int IDX_BITS>
+__global__ void __launch_bounds__(256) gather_charges_kernel(const RecT* __restrict__ rec,
+                                                             const real* __restrict__ q, long long n,
+                                                             real* __restrict__ q_sorted,
+                                                             DeviceScalars* __restrict__ sc) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float aq = 0.f;
+    if (i < n) {
+        const UT idx = rec[i].meta & (((UT)1 << IDX_BITS) - 1);
+        const real qi = q[idx];
+        q_sorted[i] = qi;
+        aq = fabsf((float)qi);
+    }
+    unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(aq));
+    if ((threadIdx.x & 31) == 0 && m > sc->qmax_bits) atomicMax(&sc->qmax_bits, m);
+}
+
+int gather_charges(hymd_ctx* c, const void* d_q, cudaStream_t s) {
+    const long long n = c->np;
+    if (n == 0) return HYMD_OK;
+    const unsigned int blocks = (unsigned int)((n + 255) / 256);
+    if (c->f64)
+        gather_charges_kernel<double, Rec64, unsigned long long, REC64_IDX_BITS>
+            <<<blocks, 256, 0, s>>>((const Rec64*)c->rec, (const double*)d_q, n,
+                                    (double*)c->q_sorted, c->scalars);
+    else
+        gather_charges_kernel<float, Rec32, uint32_t, REC32_IDX_BITS>
+            <<<blocks, 256, 0, s>>>((const Rec32*)c->rec, (const float*)d_q, n,
+                                    (float*)c->q_sorted, c->scalars);
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
+}
+
+size_t scan_temp_bytes(long long n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    return bytes;
+}
+
+int sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types, const void* d_q,
+                   int64_t n, cudaStream_t s) {
+    const Geometry& g = c->g;
+    SortParams p;
+    p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nxl = g.nxl; p.x0 = g.x0;
+    p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
+    p.sx = g.Nx / g.box[0]; p.sy = g.Ny / g.box[1]; p.sz = g.Nz / g.box[2];
+    long long ncell = g.ncell;
+    HYMD_CUDA(cudaMemsetAsync(c->cell_count, 0, (size_t)(ncell + 1) * sizeof(uint32_t), s));
+    HYMD_CUDA(cudaMemsetAsync(c->scalars, 0, sizeof(DeviceScalars), s));
+    unsigned int blocks = (unsigned int)((n + 255) / 256);
+    if (n > 0) {
+        if (c->f64)
+            count_kernel<double><<<blocks, 256, 0, s>>>((const double*)d_pos, n, p, c->cell_count,
+                                                        c->key, c->rank_in_cell, c->scalars);
+        else
+            count_kernel<float><<<blocks, 256, 0, s>>>((const float*)d_pos, n, p, c->cell_count,
+                                                       c->key, c->rank_in_cell, c->scalars);
+        HYMD_LAUNCH_CHECK(c);
+    }
+    size_t tmp = c->scan_tmp_bytes;
+    HYMD_CUDA(cub::DeviceScan::ExclusiveSum(c->scan_tmp, tmp, c->cell_count, c->cell_start,
+                                            (int)(ncell + 1), s));
+    c->launches += 2;  // cub scan: init + scan kernels
+    if (n > 0) {
+        if (c->f64)
+            scatter_kernel<double, Rec64, unsigned long long, REC64_IDX_BITS>
+                <<<blocks, 256, 0, s>>>((const double*)d_pos, d_types, (const double*)d_q, n, p,
+                                        c->cell_start, c->key, c->rank_in_cell, (Rec64*)c->rec,
+                                        (double*)c->q_sorted, c->scalars);
+        else
+            scatter_kernel<float, Rec32, uint32_t, REC32_IDX_BITS>
+                <<<blocks, 256, 0, s>>>((const float*)d_pos, d_types, (const float*)d_q, n, p,
+                                        c->cell_start, c->key, c->rank_in_cell, (Rec32*)c->rec,
+                                        (float*)c->q_sorted, c->scalars);
+        HYMD_LAUNCH_CHECK(c);
+    }
+    return HYMD_OK;
+}
+
+}  // namespace hymd

@@ -1,0 +1,196 @@
+"""Drop-in replacement for the hot path of ``hymd/field.py`` on one or more B200 GPUs.
+
+Same function names, positional argument order and in-place output conventions as the
+reference, so ``main.py`` / ``integrator.py`` can call these unchanged:
+
+====================================  =========================
+this module                           reference
+====================================  =========================
+``initialize_pm``                     ``field.py:10-149``
+``update_field``                      ``field.py:428-616``
+``compute_field_force``               ``field.py:152-200``
+``update_field_force_q``              ``field.py:241-403``
+``compute_self_energy_q``             ``field.py:203-238``
+``compute_field_and_kinetic_energy``  ``field.py:619-703``
+``domain_decomposition``              ``field.py:1115-1178``
+====================================  =========================
+
+Particle arrays (``positions (N,3)``, ``types (N,)``, ``charges (N,)``, ``force (N,3)``) may be
+torch CUDA tensors (fast path, no copies) or numpy arrays in C or Fortran order (compatibility
+path: copied to the device and, for outputs, back).  All arithmetic happens in
+``libhymd_b200.so``; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .hamiltonian import energy_parameters
+from .pm import MeshField, ParticleMesh, UnusedField
+
+
+def initialize_pm(pmesh, config, comm=None):
+    """Create the particle-mesh context and the field handles (``field.py:10-149``).
+
+    ``pmesh`` (the pmesh module in the reference) is accepted for signature compatibility and
+    ignored.  Returns ``(pm, field_list, elec_common_list, coulomb_list)`` with the reference's
+    list layouts (``field.py:139-147, 66-75, 83-86``)."""
+    dtype = "f8" if np.dtype(config.dtype) == np.float64 else "f4"
+    coulombtype = getattr(config, "coulombtype", None)
+    if coulombtype == "PIC_Spectral_GPE":
+        raise NotImplementedError(
+            "coulombtype='PIC_Spectral_GPE' (field.py:764-1112) is outside the accelerated "
+            "field-force cycle; use 'PIC_Spectral'")
+    pm = ParticleMesh(config.mesh_size, BoxSize=config.box_size, dtype=dtype, comm=comm,
+                      config=config)
+    T = config.n_types
+    phi = [pm.field(_lib.FIELD_PHI, t) for t in range(T)]
+    phi_fourier = [pm.field(_lib.FIELD_PHI_FOURIER, t, kind="complex") for t in range(T)]
+    force_on_grid = [[pm.field(_lib.FIELD_FORCE_MESH, t, d) for d in range(3)] for t in range(T)]
+    v_ext_fourier = [UnusedField(f"v_ext_fourier[{i}]") for i in range(4)]
+    v_ext = [pm.field(_lib.FIELD_V_EXT, t) for t in range(T)]
+    phi_transfer = [UnusedField(f"phi_transfer[{i}]") for i in range(3)]
+    phi_laplacian = [[UnusedField(f"phi_laplacian[{t}][{d}]") for d in range(3)] for t in range(T)]
+    field_list = [phi, phi_fourier, force_on_grid, v_ext_fourier, v_ext, phi_transfer,
+                  phi_laplacian]
+    elec_common_list = [None, None, None, None]
+    coulomb_list = []
+    if coulombtype == "PIC_Spectral":
+        phi_q = pm.field(_lib.FIELD_PHI_Q)
+        phi_q_fourier = pm.field(_lib.FIELD_PHI_Q_FOURIER, kind="complex")
+        psi = pm.field(_lib.FIELD_PSI)
+        elec_field = [pm.field(_lib.FIELD_ELEC_FIELD, 0, d) for d in range(3)]
+        elec_common_list = [phi_q, phi_q_fourier, psi, elec_field]
+        coulomb_list = [[UnusedField(f"elec_field_fourier[{d}]") for d in range(3)],
+                        UnusedField("psi_fourier")]
+    return (pm, field_list, elec_common_list, coulomb_list)
+
+
+def update_field(phi, phi_laplacian, phi_transfer, layouts, force_mesh, hamiltonian, pm,
+                 positions, types, config, v_ext, phi_fourier, v_ext_fourier, m,
+                 compute_potential=False):
+    """Densities -> filter -> external potential -> force meshes (``field.py:428-616``).
+
+    One counting sort of all particles, one deterministic CIC paint of every type, T forward
+    FFTs, one fused k-space kernel and 3U inverse FFTs (U = distinct rows of the interaction
+    matrix).  With ``compute_potential`` the filtered densities ``phi`` and the potentials
+    ``v_ext`` are materialized as well (``field.py:578, 615-616``); otherwise they are computed
+    lazily when a handle's ``.value`` is read."""
+    pm.sync_interaction(hamiltonian, config, m)
+    pm.sort(positions, types)
+    _lib.check(pm.lib.hymd_paint(pm._ctx, pm.stream))
+    _lib.check(pm.lib.hymd_field_cycle(pm._ctx, 1 if compute_potential else 0, pm.stream))
+
+
+def _output_buffer(pm, out, n):
+    """Device tensor the kernel writes into, and a callback copying it back if needed."""
+    if isinstance(out, torch.Tensor) and out.device == pm.device and out.dtype == pm.dtype \
+            and out.is_contiguous() and tuple(out.shape) == (n, 3):
+        return out, None
+    buf = torch.empty((n, 3), dtype=pm.dtype, device=pm.device)
+    if isinstance(out, torch.Tensor):
+        return buf, lambda: out.copy_(buf)
+
+    def back():
+        out[...] = buf.cpu().numpy()
+    return buf, back
+
+
+def compute_field_force(layouts, r, force_mesh, force, types, n_types):
+    """CIC interpolation of the force meshes at the particle positions, written in place into
+    ``force`` in the caller's particle order (``field.py:152-200``)."""
+    pm = force_mesh[0][0].pm
+    pm.sort(r, types)
+    n = pm._n_local
+    buf, back = _output_buffer(pm, force, n)
+    _lib.check(pm.lib.hymd_readout(pm._ctx, ctypes.c_void_p(buf.data_ptr()), pm.stream))
+    if back is not None:
+        back()
+
+
+def compute_self_energy_q(config, charges, comm=None):
+    """Ewald self energy (``field.py:203-238``)."""
+    conv = config.coulomb_constant / config.dielectric_const
+    prefac = conv * np.sqrt(1.0 / (2.0 * np.pi * config.sigma * config.sigma))
+    if isinstance(charges, torch.Tensor):
+        s = (charges.double() ** 2).sum()
+    else:
+        s = torch.tensor(float(np.sum(np.asarray(charges, dtype=np.float64) ** 2)),
+                         dtype=torch.float64)
+    return float(prefac * _allreduce(s))
+
+
+def update_field_force_q(charges, phi_q, phi_q_fourier, psi, psi_fourier, elec_field_fourier,
+                         elec_field, elec_forces, layout_q, hamiltonian, pm, positions, config):
+    """PME electrostatics (``field.py:241-403``): charge density, Poisson solve with the
+    Gaussian filter, E = -grad psi, forces q*E written in place into ``elec_forces``."""
+    pm.sync_interaction(hamiltonian, config)
+    pm.sort(positions, None, charges)
+    n = pm._n_local
+    buf, back = _output_buffer(pm, elec_forces, n)
+    _lib.check(pm.lib.hymd_pme_cycle(pm._ctx, ctypes.c_void_p(buf.data_ptr()), 0, pm.stream))
+    if back is not None:
+        back()
+
+
+def compute_field_and_kinetic_energy(phi, phi_q, psi, velocity, hamiltonian, positions, types,
+                                     v_ext, config, layouts, comm=None):
+    """``(field_energy, kinetic_energy, field_q_energy)`` (``field.py:619-703``)."""
+    pm = phi[0].pm
+    pme = getattr(config, "coulombtype", None) == "PIC_Spectral" and pm._sorted_with_charges
+    pm._materialize(want_phi=True, want_psi=pme)
+    params = energy_parameters(hamiltonian)
+    if params is not None:
+        chi, kappa, rho0, a = params
+        out = (ctypes.c_double * 2)()
+        chi = np.ascontiguousarray(chi, dtype=np.float64)
+        _lib.check(pm.lib.hymd_field_energy(
+            pm._ctx, chi.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), kappa, rho0, a, out,
+            pm.stream))
+        loc = torch.tensor([out[0], out[1]], dtype=torch.float64)
+    else:  # user-defined affine functional: evaluate its own w_0 on the device tensors
+        dv = float(np.prod(pm.BoxSize) / np.prod(pm.Nmesh))
+        w = hamiltonian.w_0([f.value.double() for f in phi]).sum() * dv
+        wq = (0.5 * phi_q.value.double() * psi.value.double()).sum() * dv if pme else torch.zeros(())
+        loc = torch.stack([w.cpu(), wq.cpu().double()])
+    if isinstance(velocity, torch.Tensor):
+        kin = 0.5 * config.mass * (velocity.double() ** 2).sum().cpu()
+    else:
+        kin = torch.tensor(0.5 * config.mass * float(np.sum(np.asarray(velocity, dtype=np.float64) ** 2)),
+                           dtype=torch.float64)
+    tot = _allreduce(torch.stack([loc[0], loc[1], kin.reshape(())]))
+    field_energy, field_q, kinetic = float(tot[0]), float(tot[1]), float(tot[2])
+    if pme:
+        field_q_energy = field_q - float(getattr(config, "self_energy", 0.0) or 0.0)
+    else:
+        field_q_energy = 0.0
+    return field_energy, kinetic, field_q_energy
+
+
+def domain_decomposition(positions, pm, *args, molecules=None, bonds=None, topol=False, verbose=0,
+                         comm=None):
+    """Re-home particles on the rank owning their slab (``field.py:1115-1178``).  With one
+    GPU every particle is already home and the inputs are returned unchanged."""
+    if molecules is not None:
+        if not topol:
+            assert bonds is not None, "bonds must be provided with molecules"
+            args = (*args, bonds, molecules)
+        else:
+            args = (*args, molecules)
+    if pm.world_size == 1:
+        return (positions, *args)
+    return pm.migrate(positions, *args, molecules=molecules)
+
+
+def _allreduce(t):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = t.clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t)
+        t = t.cpu()
+    return t

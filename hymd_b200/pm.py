@@ -1,0 +1,371 @@
+"""Device-resident stand-ins for the pmesh objects HyMD threads through ``hymd/field.py``.
+
+``main.py`` only ever (a) creates these through ``initialize_pm``, (b) passes them back into
+the ``field.py`` functions and (c) calls a handful of methods on them directly:
+``pm.decompose(pos[, smoothing])`` -> layout with ``get_exchange_cost()`` / ``exchange()``
+(``main.py:332-334, 977-980, 1304``; ``field.py:1165-1178``), ``pm.np`` (``main.py:252``),
+``pm.create(...)`` (``main.py:488-498``) and ``field.csum()`` (``field.py:693``).  Mesh fields
+are therefore thin handles onto buffers owned by the CUDA context (``include/hymd_b200.h``);
+``.value`` exposes them as torch tensors without copying.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .hamiltonian import affine_parameters, get_hamiltonian
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist
+    return None
+
+
+class _CudaView:
+    """Minimal ``__cuda_array_interface__`` carrier for context-owned memory."""
+
+    def __init__(self, ptr, shape, strides_bytes, typestr, owner):
+        self._owner = owner  # keeps the context alive while a view exists
+        self.__cuda_array_interface__ = {
+            "shape": tuple(int(s) for s in shape),
+            "strides": tuple(int(s) for s in strides_bytes),
+            "typestr": typestr,
+            "data": (int(ptr), False),
+            "version": 2,
+        }
+
+
+class Layout:
+    """What ``pm.decompose`` returns.  Binning happens inside the field calls (one counting
+    sort for all types), so the layout itself carries no routing table."""
+
+    def __init__(self, pm, n, smoothing=None):
+        self.pm = pm
+        self.n = int(n)
+        self.smoothing = smoothing
+
+    def get_exchange_cost(self):
+        return np.zeros(max(self.pm.world_size, 1), dtype=np.int64)
+
+    def exchange(self, *arrays):
+        if self.pm.world_size == 1:
+            return arrays if len(arrays) != 1 else arrays[0]
+        return self.pm.migrate(*arrays)
+
+
+class MeshField:
+    """Handle onto one context-owned mesh buffer (real or complex)."""
+
+    def __init__(self, pm, field_id, t=0, d=0, kind="real"):
+        self.pm, self.field_id, self.t, self.d, self.kind = pm, field_id, t, d, kind
+
+    def _materialize(self):
+        fid = self.field_id
+        self.pm._materialize(
+            want_phi=fid == _lib.FIELD_PHI, want_phi_fourier=fid == _lib.FIELD_PHI_FOURIER,
+            want_v_ext=fid == _lib.FIELD_V_EXT,
+            want_psi=fid in (_lib.FIELD_PSI, _lib.FIELD_PHI_Q_FOURIER))
+
+    @property
+    def value(self) -> torch.Tensor:
+        """Zero-copy torch view of the logical (unpadded) extent of the field."""
+        self._materialize()
+        return self.pm._view(self.field_id, self.t, self.d, self.kind)
+
+    @property
+    def shape(self):
+        return tuple(self.value.shape)
+
+    @property
+    def dtype(self):
+        return self.value.dtype
+
+    def csum(self):
+        """Global sum (``RealField.csum``, ``field.py:693``)."""
+        s = self.value.sum(dtype=torch.complex128 if self.kind == "complex" else torch.float64)
+        return self.pm._allreduce_scalar(s)
+
+    def cnorm(self):
+        v = self.value
+        s = (v.real.double() ** 2 + v.imag.double() ** 2).sum() if self.kind == "complex" \
+            else (v.double() ** 2).sum()
+        return self.pm._allreduce_scalar(s)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.value.detach().cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def __repr__(self):
+        return f"MeshField(id={self.field_id}, t={self.t}, d={self.d}, kind={self.kind})"
+
+
+class UnusedField:
+    """Placeholder for pmesh buffers the reference allocates as scratch for its own algorithm
+    (``v_ext_fourier[4]``, ``phi_transfer[3]``: ``field.py:55-57``); the fused kernels need no
+    such scratch, so touching one is an error rather than a silent zero."""
+
+    def __init__(self, name):
+        self.name = name
+
+    @property
+    def value(self):
+        raise RuntimeError(f"{self.name} is reference-internal scratch and is not materialized "
+                           "by hymd_b200 (the fused k-space kernel does not use it)")
+
+
+class ParticleMesh:
+    """Stand-in for ``pmesh.pm.ParticleMesh(Nmesh, BoxSize, dtype, comm)`` (``field.py:45-47``)
+    that owns one CUDA context (one slab of the mesh) on the current device."""
+
+    def __init__(self, Nmesh, BoxSize, dtype="f4", comm=None, config=None, hamiltonian=None):
+        if not torch.cuda.is_available():
+            raise _lib.HymdError("hymd_b200 needs a CUDA device (there is no CPU fallback)")
+        if config is None:
+            raise ValueError("hymd_b200.pm.ParticleMesh needs config= (n_types, sigma, chi, ...)")
+        self.lib = _lib.load()
+        self.Nmesh = np.full(3, Nmesh).astype(np.int64)
+        self.BoxSize = np.asarray(BoxSize, dtype=np.float64).reshape(3).copy()
+        dt = np.dtype(dtype)
+        if dt not in (np.dtype("f4"), np.dtype("f8")):
+            raise ValueError(f"unsupported mesh dtype {dtype!r}")
+        self.np_dtype = dt
+        self.dtype = torch.float64 if dt == np.dtype("f8") else torch.float32
+        self.cdtype = torch.complex128 if dt == np.dtype("f8") else torch.complex64
+        self.comm = comm
+        dist = _dist()
+        self.world_size = dist.get_world_size() if dist else 1
+        self.rank = dist.get_rank() if dist else 0
+        self.np = (self.world_size, 1)          # processor mesh, logged at main.py:252
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_types = int(config.n_types)
+        self.pme = getattr(config, "coulombtype", None) == "PIC_Spectral"
+        self._config = config
+        self._ctx = ctypes.c_void_p()
+        self._interaction_key = None
+        self._sort_key = None
+        self._sort_types_key = None
+        self._keep = (None, None, None)
+        self._n_local = 0
+        self._sorted_with_charges = False
+        if hamiltonian is None:
+            hamiltonian = get_hamiltonian(config) if _has_density_params(config) else None
+        cfg = self._make_config(config, hamiltonian)
+        nccl_id = None
+        if self.world_size > 1:
+            nccl_id = self._broadcast_nccl_id()
+        _lib.check(self.lib.hymd_ctx_create(ctypes.byref(cfg), nccl_id, ctypes.byref(self._ctx)))
+
+    # ---- context configuration ---------------------------------------------------------
+    def _interaction(self, config, hamiltonian):
+        T = self.n_types
+        if hamiltonian is not None:
+            A, c = affine_parameters(hamiltonian, T)
+        else:  # parameters not known yet (set by the first update_field)
+            A, c = np.zeros((T, T)), np.zeros(T)
+        m = list(getattr(config, "m", None) or [1.0] * T)
+        conv = 0.0
+        if self.pme:
+            conv = float(config.coulomb_constant) / float(config.dielectric_const)
+        return A, c, np.asarray(m, dtype=np.float64), float(config.sigma), conv
+
+    def _make_config(self, config, hamiltonian):
+        A, c, m, sigma, conv = self._interaction(config, hamiltonian)
+        cfg = _lib.HymdConfig()
+        cfg.struct_size = ctypes.sizeof(_lib.HymdConfig)
+        cfg.dtype = _lib.F64 if self.np_dtype == np.dtype("f8") else _lib.F32
+        for a in range(3):
+            cfg.mesh[a] = int(self.Nmesh[a])
+            cfg.box[a] = float(self.BoxSize[a])
+        cfg.n_types = self.n_types
+        cfg.world_size, cfg.rank = self.world_size, self.rank
+        cfg.pme = 1 if self.pme else 0
+        cfg.sigma, cfg.elec_conversion = sigma, conv
+        T = self.n_types
+        for i in range(T):
+            cfg.c[i] = c[i]
+            cfg.m[i] = m[i]
+            for j in range(T):
+                cfg.A[i * T + j] = A[i, j]
+        self._interaction_key = (A.tobytes(), c.tobytes(), m.tobytes(), sigma, conv)
+        return cfg
+
+    def sync_interaction(self, hamiltonian, config, m=None):
+        """Push (A, c, m, sigma, k_e/eps) to the context if they changed since the last call
+        (barostat runs change rho0 / a; ``update_field`` receives ``m`` explicitly)."""
+        A, c, m_cfg, sigma, conv = self._interaction(config, hamiltonian)
+        if m is not None:
+            m_cfg = np.asarray(list(m), dtype=np.float64)
+        key = (A.tobytes(), c.tobytes(), m_cfg.tobytes(), sigma, conv)
+        if key == self._interaction_key:
+            return
+        dp = ctypes.POINTER(ctypes.c_double)
+        Ac = np.ascontiguousarray(A, dtype=np.float64)
+        _lib.check(self.lib.hymd_ctx_set_interaction(
+            self._ctx, Ac.ctypes.data_as(dp), c.ctypes.data_as(dp), m_cfg.ctypes.data_as(dp),
+            sigma, conv))
+        self._interaction_key = key
+
+    def set_box(self, box):
+        self.BoxSize = np.asarray(box, dtype=np.float64).reshape(3).copy()
+        dp = ctypes.POINTER(ctypes.c_double)
+        _lib.check(self.lib.hymd_ctx_set_box(self._ctx, self.BoxSize.ctypes.data_as(dp)))
+        self._sort_key = None
+
+    def _broadcast_nccl_id(self):
+        dist = _dist()
+        buf = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES)()
+        if self.rank == 0:
+            _lib.check(self.lib.hymd_nccl_unique_id(buf))
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.to(self.device)
+        dist.broadcast(t, src=0)
+        vals = t.cpu().tolist()
+        for i, v in enumerate(vals):
+            buf[i] = v
+        return buf
+
+    def close(self):
+        if self._ctx:
+            self.lib.hymd_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- pmesh-like surface --------------------------------------------------------------
+    def decompose(self, pos, smoothing=None):
+        return Layout(self, 0 if pos is None else len(pos), smoothing)
+
+    def create(self, kind="real", value=0.0):
+        """``pm.create`` (``main.py:488-498``): a free-standing zero mesh (torch tensor)."""
+        nxl = int(self.Nmesh[0]) // self.world_size
+        if kind == "real":
+            return torch.full((nxl, int(self.Nmesh[1]), int(self.Nmesh[2])), float(value),
+                              dtype=self.dtype, device=self.device)
+        return torch.full((int(self.Nmesh[0]), int(self.Nmesh[1]) // self.world_size,
+                           int(self.Nmesh[2]) // 2 + 1), value, dtype=self.cdtype,
+                          device=self.device)
+
+    def field(self, field_id, t=0, d=0, kind="real"):
+        return MeshField(self, field_id, t, d, kind)
+
+    # ---- device plumbing -----------------------------------------------------------------
+    @property
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def as_device(self, x, dtype=None, shape=None):
+        """C-contiguous device tensor of the mesh dtype (numpy in any memory order is copied)."""
+        dtype = dtype or self.dtype
+        if isinstance(x, torch.Tensor):
+            t = x
+            if t.device != self.device:
+                t = t.to(self.device, non_blocking=True)
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            t = t.contiguous()
+        else:
+            npd = {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32}[dtype]
+            t = torch.from_numpy(np.ascontiguousarray(x, dtype=npd)).to(self.device, non_blocking=True)
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    @staticmethod
+    def _fingerprint(x):
+        if isinstance(x, torch.Tensor):
+            return ("t", x.data_ptr(), x._version, tuple(x.shape), x.dtype)
+        a = np.asarray(x)
+        n = a.shape[0]
+        probe = (float(a[0, 0]), float(a[n // 2, 1]), float(a[-1, -1])) if a.ndim == 2 and n else ()
+        return ("n", id(x), a.ctypes.data, a.shape, probe)
+
+    def sort(self, positions, types, charges=None):
+        """Bin the local particles (all types at once).  Cached on the identity of the inputs:
+        ``compute_field_force`` / ``update_field_force_q`` called after ``update_field`` on the
+        same positions reuse its bins (``types=None`` means "whatever the bins hold")."""
+        pk = self._fingerprint(positions)
+        tk = None if types is None else self._fingerprint_types(types)
+        if pk == self._sort_key and (tk is None or tk == self._sort_types_key):
+            if charges is not None and not self._sorted_with_charges:
+                q = self.as_device(charges, shape=(self._n_local,))
+                _lib.check(self.lib.hymd_set_charges(self._ctx, ctypes.c_void_p(q.data_ptr()),
+                                                     self.stream))
+                self._sorted_with_charges = True
+                self._keep = (self._keep[0], self._keep[1], q)
+            return
+        pos = self.as_device(positions)
+        if pos.ndim != 2 or pos.shape[1] != 3:
+            raise ValueError(f"positions must be (N,3), got {tuple(pos.shape)}")
+        n = pos.shape[0]
+        if types is None:
+            ty = torch.zeros(n, dtype=torch.int32, device=self.device)
+        else:
+            ty = self.as_device(types, dtype=torch.int32, shape=(n,))
+        q = None if charges is None else self.as_device(charges, shape=(n,))
+        _lib.check(self.lib.hymd_sort_particles(
+            self._ctx, ctypes.c_void_p(pos.data_ptr()), ctypes.c_void_p(ty.data_ptr()),
+            ctypes.c_void_p(q.data_ptr()) if q is not None else None, n, self.stream))
+        self._keep = (pos, ty, q)   # inputs must outlive the asynchronous kernels
+        self._sort_key, self._sort_types_key = pk, tk
+        self._n_local = n
+        self._sorted_with_charges = charges is not None
+
+    def _fingerprint_types(self, types):
+        if isinstance(types, torch.Tensor):
+            return ("t", types.data_ptr(), types._version, tuple(types.shape))
+        a = np.asarray(types)
+        return ("n", id(types), a.ctypes.data, a.shape)
+
+    def _materialize(self, want_phi=False, want_phi_fourier=False, want_v_ext=False, want_psi=False):
+        if want_phi or want_phi_fourier or want_v_ext or want_psi:
+            _lib.check(self.lib.hymd_materialize(self._ctx, int(want_phi), int(want_phi_fourier),
+                                                 int(want_v_ext), int(want_psi), self.stream))
+
+    def _view(self, field_id, t, d, kind):
+        ptr = ctypes.c_void_p()
+        dims = (ctypes.c_int64 * 3)()
+        pitch = (ctypes.c_int64 * 3)()
+        _lib.check(self.lib.hymd_get_field(self._ctx, field_id, t, d, ctypes.byref(ptr), dims, pitch))
+        if kind == "complex":
+            esz = 16 if self.np_dtype == np.dtype("f8") else 8
+            typestr = "<c16" if esz == 16 else "<c8"
+        else:
+            esz = self.np_dtype.itemsize
+            typestr = "<f8" if esz == 8 else "<f4"
+        view = _CudaView(ptr.value, list(dims), [p * esz for p in pitch], typestr, self)
+        return torch.as_tensor(view, device=self.device)
+
+    def status(self):
+        out = (ctypes.c_int64 * 4)()
+        _lib.check(self.lib.hymd_ctx_status(self._ctx, out))
+        return {"max_cell_count": out[0], "out_of_slab": out[1], "n_local": out[2],
+                "potential_rows": out[3]}
+
+    def launch_count(self):
+        return int(self.lib.hymd_launch_count(self._ctx))
+
+    def _allreduce_scalar(self, s):
+        dist = _dist()
+        if dist and self.world_size > 1:
+            s = s.clone()
+            dist.all_reduce(s)
+        v = s.item()
+        return v
+
+    def migrate(self, *arrays):
+        raise _lib.HymdError("multi-GPU particle migration is not available in this build")
+
+
+def _has_density_params(config):
+    return getattr(config, "n_particles", None) is not None and \
+        getattr(config, "box_size", None) is not None and getattr(config, "hamiltonian", None)

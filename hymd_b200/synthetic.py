@@ -1,0 +1,123 @@
+"""Synthetic systems for the benchmark configurations of BASELINE.json.
+
+All systems: ``numpy.random.default_rng(seed)``, cubic box ``L = float32((N / 8.37)**(1/3))`` so
+the number density is ~8.37 nm^-3 (``utils/units.py:5`` of the reference), kappa = 0.05,
+``hamiltonian = "DefaultWithChi"``, ``m = [1.0] * T``, types assigned by fixed fractions.
+Polymer types are laid out as 20-bead random-walk chains (bond 0.47 nm) wrapped periodically;
+solvent is uniform.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .config import Chi, Config
+
+DENSITY = 8.37  # nm^-3
+
+# DPPC lipid + water chi table (docs/doc_pages/examples.rst:449-460 of the reference)
+DPPC_CHI = [("C", "W", 42.24), ("G", "C", 10.47), ("N", "W", -3.77), ("G", "W", 4.53),
+            ("N", "P", -9.34), ("P", "G", 8.04), ("N", "G", 1.97), ("P", "C", 14.72),
+            ("P", "W", -1.51), ("N", "C", 13.56)]
+
+
+@dataclass
+class System:
+    name: str
+    config: Config
+    positions: np.ndarray      # (N,3) config.dtype
+    types: np.ndarray          # (N,) int32
+    charges: Optional[np.ndarray]
+    velocities: np.ndarray
+
+
+SPECS: Dict[str, dict] = {
+    # ideal_chain-style 2-type homopolymer melt (examples.rst:371-373: chi_AB = 30)
+    "C1": dict(n=10_000, mesh=24, names=["A", "B"], frac=[0.5, 0.5], polymer=[True, True],
+               chi=[("A", "B", 30.0)], seed=1001),
+    # DPPC bilayer + water: N,P,G,C per lipid = 1,1,2,8 plus water
+    "C2": dict(n=100_000, mesh=64, names=["N", "P", "G", "C", "W"],
+               frac=[1 / 38.5, 1 / 38.5, 2 / 38.5, 8 / 38.5, 26.5 / 38.5],
+               polymer=[True, True, True, True, False], chi=DPPC_CHI, seed=1002),
+    # charged lipid membrane + counter ions, PME
+    "C3": dict(n=1_000_000, mesh=128, names=["N", "P", "G", "C", "W", "X"],
+               frac=[1 / 39.5, 1 / 39.5, 2 / 39.5, 8 / 39.5, 26.5 / 39.5, 1 / 39.5],
+               polymer=[True, True, True, True, False, False], chi=DPPC_CHI, seed=1003,
+               charges={"N": 1.0, "P": -1.0, "X": 0.0}, coulomb=True),
+    # multi-type polymer / water box
+    "C4": dict(n=10_000_000, mesh=256, names=["A", "B", "C", "W"], frac=[0.2, 0.2, 0.1, 0.5],
+               polymer=[True, True, True, False],
+               chi=[("A", "B", 20.0), ("A", "C", -5.0), ("B", "C", 10.0), ("A", "W", 30.0),
+                    ("B", "W", 5.0), ("C", "W", 0.0)], seed=1004),
+    "C5": dict(n=100_000_000, mesh=512, names=["A", "B", "C", "W"], frac=[0.2, 0.2, 0.1, 0.5],
+               polymer=[True, True, True, False],
+               chi=[("A", "B", 20.0), ("A", "C", -5.0), ("B", "C", 10.0), ("A", "W", 30.0),
+                    ("B", "W", 5.0), ("C", "W", 0.0)], seed=1005),
+}
+
+
+def box_length(n: int) -> float:
+    return float(np.float32((n / DENSITY) ** (1.0 / 3.0)))
+
+
+def make_system(name: str = "C2", dtype=np.float32, n: Optional[int] = None,
+                mesh: Optional[int] = None, sigma: float = 0.5, kappa: float = 0.05,
+                chains: bool = True) -> System:
+    """Build one of the C1..C5 systems (optionally at a reduced ``n`` / ``mesh``)."""
+    spec = SPECS[name]
+    n = int(n if n is not None else spec["n"])
+    mesh = int(mesh if mesh is not None else spec["mesh"])
+    rng = np.random.default_rng(spec["seed"])
+    names: List[str] = spec["names"]
+    L = box_length(n)
+    frac = np.asarray(spec["frac"], dtype=np.float64)
+    counts = np.floor(frac / frac.sum() * n).astype(np.int64)
+    counts[-1 if not spec.get("coulomb") else len(names) - 2] += n - counts.sum()
+    types = np.repeat(np.arange(len(names), dtype=np.int32), counts)
+    pos = rng.uniform(0.0, L, size=(n, 3))
+    if chains:
+        # 20-bead random walks for the polymer types (vectorised: one cumulative sum per chain)
+        for t, is_poly in enumerate(spec["polymer"]):
+            if not is_poly:
+                continue
+            idx = np.nonzero(types == t)[0]
+            nb = len(idx) // 20 * 20
+            if nb == 0:
+                continue
+            steps = rng.normal(size=(nb // 20, 20, 3))
+            steps *= 0.47 / np.linalg.norm(steps, axis=2, keepdims=True)
+            steps[:, 0, :] = 0.0
+            walk = np.cumsum(steps, axis=1) + pos[idx[:nb:20], None, :]
+            pos[idx[:nb]] = np.mod(walk.reshape(nb, 3), L)
+    perm = rng.permutation(n)          # caller order is arbitrary in HyMD (file order)
+    pos, types = pos[perm], types[perm]
+    charges = None
+    coulomb = bool(spec.get("coulomb"))
+    if coulomb:
+        charges = np.zeros(n, dtype=np.float64)
+        for nm, q in spec["charges"].items():
+            charges[types == names.index(nm)] = q
+        # counter ions neutralise exactly
+        ions = np.nonzero(types == names.index("X"))[0]
+        excess = charges.sum()
+        k = min(len(ions), int(round(abs(excess))))
+        charges[ions[:k]] = -np.sign(excess)
+    vel = rng.normal(size=(n, 3)) * np.sqrt(Config.gas_constant * 323.0 / 72.0)
+    cfg = Config(mesh_size=mesh, sigma=sigma, kappa=kappa, box_size=[L, L, L],
+                 hamiltonian="DefaultWithChi", chi=[Chi(*c) for c in spec["chi"]],
+                 dtype=np.dtype(dtype), mass=72.0, time_step=0.01, respa_inner=25,
+                 coulombtype="PIC_Spectral" if coulomb else None,
+                 dielectric_const=80.0 if coulomb else None)
+    cfg.finalize(names, n_particles=n)
+    if coulomb:
+        cfg.type_charges = [spec["charges"].get(nm, 0.0) for nm in cfg.unique_names]
+    # names sorted alphabetically define the type ids (input_parser.py:546-557): remap
+    remap = np.array([cfg.name_to_type_map[nm] for nm in names], dtype=np.int32)
+    types = remap[types]
+    pos = np.mod(pos, L).astype(dtype)
+    pos[pos >= np.asarray(L, dtype=dtype)] = 0.0
+    return System(name=name, config=cfg, positions=pos, types=types.astype(np.int32),
+                  charges=None if charges is None else charges.astype(dtype),
+                  velocities=vel.astype(dtype))

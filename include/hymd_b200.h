@@ -1,0 +1,162 @@
+/* hymd_b200.h — C ABI of the B200-native particle-mesh field-force cycle.
+ *
+ * This is the drop-in boundary for the hot path of HyMD's hymd/field.py.  The
+ * reference has no FFI of its own for this path (it calls the third-party
+ * pmesh/PFFT Python packages); each entry point below therefore cites the
+ * reference Python call sites it replaces (paths relative to the HyMD repo).
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative hymd_status code; the
+ *    message for the last failure on the calling thread is hymd_last_error().
+ *  - all pointers named d_* are DEVICE pointers on the context's GPU; plain
+ *    pointers are host memory.  No ownership is transferred.  Field buffers are
+ *    owned by the context and exposed through hymd_get_field().
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Calls are asynchronous with respect to the host unless stated otherwise.
+ *  - one context per GPU / rank; a context is not thread-safe.
+ *  - real fields are C-ordered (x slowest, z fastest).  With world_size > 1 the
+ *    mesh is split into contiguous slabs along x (the slowest storage axis):
+ *    rank r owns planes [r*Nx/P, (r+1)*Nx/P) and the particles inside it.
+ */
+#ifndef HYMD_B200_H
+#define HYMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYMD_B200_ABI_VERSION 1
+#define HYMD_MAX_TYPES 32
+#define HYMD_NCCL_UNIQUE_ID_BYTES 128
+
+typedef enum {
+    HYMD_OK = 0,
+    HYMD_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+    HYMD_ERR_CUDA = -2,      /* CUDA runtime or cuFFT failure */
+    HYMD_ERR_NCCL = -3,      /* NCCL failure or libnccl not loadable */
+    HYMD_ERR_STATE = -4,     /* call sequence violated (e.g. readout before sort) */
+    HYMD_ERR_CAPACITY = -5,  /* particle outside the local slab / capacity overflow */
+    HYMD_ERR_NOMEM = -6
+} hymd_status;
+
+typedef enum { HYMD_F32 = 0, HYMD_F64 = 1 } hymd_dtype;
+
+/* Which context-owned buffer hymd_get_field() returns.  Shapes are for the local slab
+ * (nxl = Nx / world_size planes); "pad" layouts are described in DESIGN.md. */
+typedef enum {
+    HYMD_FIELD_PHI = 0,          /* [t]      real  (nxl,Ny,Nz): raw painted density / dV after
+                                    hymd_paint; FILTERED density after hymd_materialize */
+    HYMD_FIELD_PHI_FOURIER = 1,  /* [t]      cplx  k-layout: H * r2c(phi)/M   (materialized) */
+    HYMD_FIELD_FORCE_MESH = 2,   /* [t][d]   real  ghost-padded (nxl+1,Ny+1,Nzp) */
+    HYMD_FIELD_V_EXT = 3,        /* [t]      real  (nxl,Ny,Nz)              (materialized) */
+    HYMD_FIELD_PHI_Q = 4,        /*          real  (nxl,Ny,Nz) unfiltered charge density */
+    HYMD_FIELD_PHI_Q_FOURIER = 5,/*          cplx  k-layout: H * r2c(phi_q)/M */
+    HYMD_FIELD_PSI = 6,          /*          real  (nxl,Ny,Nz) electrostatic potential */
+    HYMD_FIELD_ELEC_FIELD = 7    /* [d]      real  ghost-padded (nxl+1,Ny+1,Nzp) */
+} hymd_field_id;
+
+typedef struct {
+    int32_t struct_size;        /* = sizeof(hymd_config), for ABI checking */
+    int32_t dtype;              /* hymd_dtype: config.dtype, main.py:56-66 / field.py:32-35 */
+    int32_t mesh[3];            /* config.mesh_size via np.full(3, mesh_size), field.py:571 */
+    double box[3];              /* config.box_size [nm] */
+    int32_t n_types;            /* config.n_types */
+    int32_t world_size;         /* number of slabs (GPUs); 1 = single GPU */
+    int32_t rank;               /* this slab */
+    int32_t pme;                /* 1: allocate the PME buffers (config.coulombtype == "PIC_Spectral") */
+    double sigma;               /* config.sigma: H(k) = exp(-sigma^2 k^2/2), hamiltonian.py:57-66 */
+    double elec_conversion;     /* coulomb_constant / dielectric_const, field.py:360 */
+    /* Affine external potential  V_t = sum_j A[t][j]*phi~_j + c[t]  (hamiltonian.py:402-412,
+     * 470-473: A_tj = 1/(kappa rho0) + chi_tj/rho0, c_t = -a/(kappa rho0)).  Row-major T x T. */
+    double A[HYMD_MAX_TYPES * HYMD_MAX_TYPES];
+    double c[HYMD_MAX_TYPES];
+    double m[HYMD_MAX_TYPES];   /* config.m: per-type paint mass, field.py:574 */
+} hymd_config;
+
+typedef struct hymd_ctx hymd_ctx;
+
+/* Message describing the last error on this thread ("" if none). */
+const char* hymd_last_error(void);
+int hymd_abi_version(void);
+
+/* Rank 0 obtains an id, the host program broadcasts it (any transport), every rank passes it
+ * to hymd_ctx_create.  Replaces the MPI communicator handed to pmesh (field.py:45-47). */
+int hymd_nccl_unique_id(uint8_t id[HYMD_NCCL_UNIQUE_ID_BYTES]);
+
+/* initialize_pm (field.py:10-149): builds cuFFT plans and every mesh buffer for this slab.
+ * nccl_id may be NULL iff world_size == 1.  Synchronous. */
+int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** out);
+int hymd_ctx_destroy(hymd_ctx* ctx);
+
+/* Barostat box rescale (barostat.py:158-164 re-runs initialize_pm): cheap, keeps plans. */
+int hymd_ctx_set_box(hymd_ctx* ctx, const double box[3]);
+/* New Hamiltonian parameters without rebuilding the context. */
+int hymd_ctx_set_interaction(hymd_ctx* ctx, const double* A, const double* c, const double* m,
+                             double sigma, double elec_conversion);
+
+/* pm.decompose(positions[types==t]) for all t (main.py:977-980, 1007): bins the n local
+ * particles by mesh cell.  d_pos is (n,3) row-major in the context dtype, d_types int32 (n),
+ * d_charges (n) in the context dtype or NULL.  Positions may lie anywhere (they are wrapped
+ * periodically); with world_size > 1 every particle must lie inside this rank's slab
+ * (see hymd_migrate).  Keeps no reference to the inputs after the stream work completes. */
+int hymd_sort_particles(hymd_ctx* ctx, const void* d_pos, const int32_t* d_types,
+                        const void* d_charges, int64_t n, void* stream);
+
+/* Attach charges to an existing sort of the same positions (pm.decompose(positions) for the
+ * charge layout, main.py:1007, without re-binning). */
+int hymd_set_charges(hymd_ctx* ctx, const void* d_charges, void* stream);
+
+/* pm.paint(...)/volume_per_cell for every type (field.py:574-575): deterministic CIC deposit
+ * of the sorted particles into HYMD_FIELD_PHI[t]; includes the ghost-plane halo reduce. */
+int hymd_paint(hymd_ctx* ctx, void* stream);
+
+/* field.py:576-616: r2c, Gaussian filter, v_ext, second filter, -ik_d, c2r into
+ * HYMD_FIELD_FORCE_MESH (+ ghost fill / halo fetch).  compute_potential != 0 also
+ * materializes HYMD_FIELD_V_EXT (field.py:615-616) and the filtered HYMD_FIELD_PHI. */
+int hymd_field_cycle(hymd_ctx* ctx, int compute_potential, void* stream);
+
+/* compute_field_force (field.py:152-200): d_force (n,3) row-major, caller particle order. */
+int hymd_readout(hymd_ctx* ctx, void* d_force, void* stream);
+
+/* update_field_force_q (field.py:241-403): uses the charges given to hymd_sort_particles;
+ * writes d_elec_force (n,3).  want_psi != 0 also transforms psi back to real space. */
+int hymd_pme_cycle(hymd_ctx* ctx, void* d_elec_force, int want_psi, void* stream);
+
+/* Lazily materialize by-products the force path does not need every step:
+ * filtered phi~ (field.py:578), phi_fourier (field.py:577), v_ext (field.py:616), and the
+ * real-space electrostatic potential psi (field.py:377). */
+int hymd_materialize(hymd_ctx* ctx, int want_phi, int want_phi_fourier, int want_v_ext,
+                     int want_psi, void* stream);
+
+/* compute_field_and_kinetic_energy (field.py:688-703) field terms: writes 2 doubles to the
+ * HOST array out: {sum_cells w_0(phi~) dV, sum_cells 0.5 phi_q psi dV} for this slab (the
+ * caller all-reduces and subtracts the self energy).  chi_upper is the T x T chi table,
+ * kappa/rho0/a the Hamiltonian parameters, shift_a = 0 for SquaredPhi.  Synchronous. */
+int hymd_field_energy(hymd_ctx* ctx, const double* chi, double kappa, double rho0, double a,
+                      double out[2], void* stream);
+
+/* Pointer + geometry of a context-owned buffer.  dims[3] = logical extents, pitch[3] = element
+ * strides (in elements of the scalar or complex type). */
+int hymd_get_field(hymd_ctx* ctx, int field_id, int t, int d, void** d_ptr, int64_t dims[3],
+                   int64_t pitch[3]);
+
+/* Synchronizes and reports {max particles per cell, particles outside the local slab,
+ * local particle count, distinct potential rows} of the last hymd_sort_particles. */
+int hymd_ctx_status(hymd_ctx* ctx, int64_t out[4]);
+
+/* Number of CUDA kernels launched by this context since creation (bench bookkeeping). */
+int64_t hymd_launch_count(hymd_ctx* ctx);
+
+/* domain_decomposition / layout.exchange (field.py:1115-1178): GPU-side particle migration
+ * between slabs.  Packs particles whose wrapped x lies outside this slab, exchanges them with
+ * NCCL, and compacts.  d_arrays[i] is an (capacity, width[i]) array of 4- or 8-byte elements
+ * (elem_size[i]); array 0 must be the positions.  n_inout: local count in, new count out. */
+int hymd_migrate(hymd_ctx* ctx, void** d_arrays, const int32_t* width, const int32_t* elem_size,
+                 int n_arrays, int64_t capacity, int64_t* n_inout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYMD_B200_H */

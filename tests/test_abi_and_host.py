@@ -1,0 +1,133 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares,
+the host-side mirror of the reference interface behaves, synthetic systems are well formed."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_config
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "hymd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hymd_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hymd_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _header_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/hymd_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+    assert _lib.load().hymd_abi_version() == 1
+
+
+def test_config_struct_matches_header_layout():
+    from hymd_b200 import _lib
+    # 5 int32 (+4 pad) + 3 double + 4 int32 + 2 double + (32*32 + 32 + 32) double
+    assert ctypes.sizeof(_lib.HymdConfig) == 24 + 24 + 16 + 16 + 8 * (1024 + 64)
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hymd_b200 import _lib
+    from hymd_b200.field import initialize_pm
+    cfg = make_config(["A", "B"], 10, 8, [2.0, 2.0, 2.0])
+    with pytest.raises(_lib.HymdError):
+        initialize_pm(None, cfg)
+
+
+def test_signatures_mirror_reference():
+    """Positional argument names of the reference functions (field.py:10, 152, 203, 241-255,
+    428-444, 619-631, 1115-1117)."""
+    from hymd_b200 import field
+    expect = {
+        "initialize_pm": ["pmesh", "config", "comm"],
+        "compute_field_force": ["layouts", "r", "force_mesh", "force", "types", "n_types"],
+        "compute_self_energy_q": ["config", "charges", "comm"],
+        "update_field_force_q": ["charges", "phi_q", "phi_q_fourier", "psi", "psi_fourier",
+                                 "elec_field_fourier", "elec_field", "elec_forces", "layout_q",
+                                 "hamiltonian", "pm", "positions", "config"],
+        "update_field": ["phi", "phi_laplacian", "phi_transfer", "layouts", "force_mesh",
+                         "hamiltonian", "pm", "positions", "types", "config", "v_ext",
+                         "phi_fourier", "v_ext_fourier", "m", "compute_potential"],
+        "compute_field_and_kinetic_energy": ["phi", "phi_q", "psi", "velocity", "hamiltonian",
+                                             "positions", "types", "v_ext", "config", "layouts",
+                                             "comm"],
+    }
+    for name, args in expect.items():
+        got = list(inspect.signature(getattr(field, name)).parameters)
+        assert got == args, name
+    dd = inspect.signature(field.domain_decomposition)
+    assert list(dd.parameters)[:3] == ["positions", "pm", "args"]
+    for kw in ("molecules", "bonds", "topol", "verbose", "comm"):
+        assert kw in dd.parameters
+
+
+def test_affine_parameters_match_closed_form_and_reject_nonaffine():
+    from hymd_b200.hamiltonian import affine_parameters, get_hamiltonian
+    chi = [("A", "B", 9.6754032616815161), ("A", "C", -13.2596290315913623),
+           ("B", "C", 0.3852001771213374)]
+    cfg = make_config(["A", "B", "C"], 5, 16, [15.0, 15.0, 15.0], chi=chi)
+    h = get_hamiltonian(cfg)
+    A, c = affine_parameters(h, 3)
+    k, r = cfg.kappa, cfg.rho0
+    want = np.full((3, 3), 1.0 / (k * r)) + h.chi_matrix / r
+    np.testing.assert_allclose(A, want, rtol=1e-13)
+    np.testing.assert_allclose(c, -cfg.a / (k * r), rtol=1e-13)
+
+    class Quartic:
+        v_ext = [lambda phi: phi[0] ** 3]
+    with pytest.raises(ValueError):
+        affine_parameters(Quartic(), 1)
+
+
+def test_hamiltonian_mirror_matches_oracle_and_golden():
+    import json
+    from hymd_b200.config import Chi, Config
+    from hymd_b200.hamiltonian import get_hamiltonian
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "hamiltonian_golden.npz"))
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "hamiltonian_golden.json")))
+    for case in cases:
+        if case.get("f32_params"):
+            continue
+        cfg = Config(mesh_size=16, sigma=case["sigma"], kappa=case["kappa"], box_size=case["box"],
+                     hamiltonian=case["kind"], chi=[Chi(*c) for c in case["chi"]],
+                     coulombtype=case.get("coulombtype"),
+                     dielectric_const=case.get("dielectric_const"),
+                     self_energy=case.get("self_energy"))
+        cfg.finalize(case["names"], n_particles=case["n"])
+        cfg.box_size = np.asarray(cfg.box_size, dtype=np.float64)
+        h = get_hamiltonian(cfg)
+        pre = case["name"]
+        phi = list(gold[pre + "/phi"])
+        np.testing.assert_allclose(h.w_0(phi), gold[pre + "/w_0"], rtol=1e-11, atol=1e-9)
+        for t in range(cfg.n_types):
+            np.testing.assert_allclose(h.v_ext[t](phi), gold[pre + "/v_ext"][t], rtol=1e-11, atol=1e-9)
+        k = [gold[pre + "/k0"], gold[pre + "/k1"], gold[pre + "/k2"]]
+        np.testing.assert_allclose(h.H(k, gold[pre + "/v"]), gold[pre + "/H"], rtol=1e-13, atol=1e-300)
+
+
+@pytest.mark.parametrize("name,n,mesh", [("C1", 2000, 12), ("C2", 5000, 16), ("C3", 4000, 16),
+                                         ("C4", 3000, 16)])
+def test_synthetic_systems(name, n, mesh):
+    from hymd_b200.synthetic import make_system
+    s = make_system(name, np.float32, n=n, mesh=mesh)
+    L = float(s.config.box_size[0])
+    assert s.positions.shape == (n, 3) and s.positions.dtype == np.float32
+    assert (s.positions >= 0).all() and (s.positions < L).all()
+    assert s.types.min() >= 0 and s.types.max() < s.config.n_types
+    assert abs(n / L ** 3 - 8.37) < 0.05
+    if s.charges is not None:
+        assert abs(float(s.charges.sum())) < 1e-6
+        assert s.config.coulombtype == "PIC_Spectral"
+    s2 = make_system(name, np.float32, n=n, mesh=mesh)
+    assert np.array_equal(s.positions, s2.positions)

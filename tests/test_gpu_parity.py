@@ -1,0 +1,197 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): per-particle field forces and field energies agree
+within 1e-5 relative for the fp32 build and 1e-10 for the fp64 build; relative error is
+max|a-b| / max|b|.  fp32 results are compared against the fp64 oracle evaluated on the same
+(float32-valued) inputs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_config
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float32: 1e-5, np.float64: 1e-10}
+CHI3 = [("A", "B", 9.6754032616815161), ("A", "C", -13.2596290315913623),
+        ("B", "C", 0.3852001771213374)]
+
+
+def _system(n, mesh, box, dtype, seed=0, names=("A", "B", "C"), chi=CHI3, coulomb=False,
+            hamiltonian="DefaultWithChi", m=None):
+    rng = np.random.default_rng(seed)
+    box = np.asarray(box, dtype=np.float32)
+    pos = (rng.uniform(0, 1, size=(n, 3)) * box).astype(dtype)
+    pos = np.minimum(pos, np.nextafter(box.astype(dtype), 0).astype(dtype))
+    tnames = [names[i % len(names)] for i in range(n)]
+    cfg = make_config(tnames, n, mesh, box, chi=chi, dtype=dtype, hamiltonian=hamiltonian,
+                      coulombtype="PIC_Spectral" if coulomb else None,
+                      dielectric_const=80.0 if coulomb else None, m=m)
+    types = np.array([cfg.name_to_type_map[t] for t in tnames], dtype=np.int32)
+    q = None
+    if coulomb:
+        q = rng.choice([-1.0, 0.0, 1.0], size=n)
+        q -= q.mean()
+        q = q.astype(dtype)
+    return cfg, pos, types, q
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mesh", [[24, 24, 24], [16, 12, 10], [9, 12, 10], [40, 24, 72], [5, 5, 5]])
+def test_paint_matches_oracle(dtype, mesh):
+    """Raw CIC densities / dV (field.py:574-575) for every type, and mass conservation
+    (test_hamiltonian.py:105-109)."""
+    from gpu_common import GpuRun, rel_err
+    from hymd_b200 import _lib
+    from oracle import pm_oracle as pmo
+    from oracle.field_oracle import volume_per_cell
+    cfg, pos, types, _ = _system(3000, mesh, [4.0, 5.0, 6.0], dtype)
+    g = GpuRun(cfg, pos, types)
+    dv = volume_per_cell(cfg)
+    for t in range(cfg.n_types):
+        got = g.pm._view(_lib.FIELD_PHI, t, 0, "real").cpu().numpy()
+        want = pmo.cic_paint(pos[types == t].astype(np.float64), 1.0, mesh, cfg.box_size) / dv
+        assert rel_err(got, want) < (1e-6 if dtype == np.float32 else 1e-13)
+        assert got.sum(dtype=np.float64) * dv == pytest.approx((types == t).sum(), rel=1e-6 if dtype == np.float32 else 1e-13)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mesh,n", [([24, 24, 24], 10000), ([16, 12, 10], 700), ([9, 12, 10], 500),
+                                    ([32, 40, 64], 20000)])
+def test_field_forces_match_oracle(dtype, mesh, n):
+    from gpu_common import GpuRun, OracleRun, rel_err
+    cfg, pos, types, _ = _system(n, mesh, [4.0, 5.0, 6.0], dtype, seed=1)
+    g = GpuRun(cfg, pos, types)
+    o = OracleRun(cfg, pos, types)
+    assert rel_err(g.forces(), o.force) < TOL[dtype]
+    for t in range(cfg.n_types):
+        for d in range(3):
+            assert rel_err(g.force_mesh[t][d].value.cpu().numpy(), o.st.force_mesh[t][d]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kind", ["DefaultNoChi", "SquaredPhi", "DefaultWithChi"])
+def test_energies_and_potentials_match_oracle(dtype, kind):
+    """compute_potential=True path: filtered densities, v_ext and the field energy
+    (field.py:578, 615-616, 692-693)."""
+    from gpu_common import GpuRun, OracleRun, rel_err
+    cfg, pos, types, _ = _system(5000, [20, 24, 28], [4.0, 5.0, 6.0], dtype, seed=2,
+                                 hamiltonian=kind)
+    rng = np.random.default_rng(9)
+    vel = rng.normal(size=pos.shape).astype(dtype)
+    g = GpuRun(cfg, pos, types, compute_potential=True)
+    o = OracleRun(cfg, pos, types)
+    tol = TOL[dtype]
+    for t in range(cfg.n_types):
+        assert rel_err(g.phi[t].value.cpu().numpy(), o.st.phi[t]) < tol
+        assert rel_err(g.phi_fourier[t].value.cpu().numpy(), o.st.phi_fourier[t]) < tol
+        # v_ext ~ fluctuation around zero of terms of size A*rho0: compare on that scale
+        scale = np.abs(o.st.v_ext[t]).max() + 1.0 / cfg.kappa
+        assert np.abs(g.v_ext[t].value.cpu().numpy() - o.st.v_ext[t]).max() / scale < tol
+    e_g = g.energies(torch.as_tensor(vel, device="cuda"))
+    e_o = o.energies(vel)
+    # the field energy is a sum of squared fluctuations; compare on the scale N/(2 kappa)
+    escale = max(abs(e_o[0]), 0.5 * len(pos) / cfg.kappa * 1e-2)
+    assert abs(e_g[0] - e_o[0]) / escale < tol
+    assert e_g[1] == pytest.approx(e_o[1], rel=1e-6 if dtype == np.float32 else 1e-12)
+    assert e_g[2] == 0.0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pme_matches_oracle(dtype):
+    from gpu_common import GpuRun, OracleRun, rel_err
+    from hymd_b200.field import compute_self_energy_q
+    from oracle.field_oracle import compute_self_energy_q as self_o
+    cfg, pos, types, q = _system(6000, [24, 20, 28], [4.0, 5.0, 6.0], dtype, seed=3, coulomb=True)
+    cfg.self_energy = self_o(cfg, q)
+    assert compute_self_energy_q(cfg, torch.as_tensor(q, device="cuda")) == pytest.approx(cfg.self_energy, rel=1e-6)
+    g = GpuRun(cfg, pos, types, charges=q)
+    o = OracleRun(cfg, pos, types, charges=q)
+    tol = TOL[dtype]
+    assert rel_err(g.eforces(), o.elec_forces) < tol
+    assert rel_err(g.forces(), o.force) < tol
+    for d in range(3):
+        assert rel_err(g.elec_field[d].value.cpu().numpy(), o.st.elec_field[d]) < tol
+    vel = np.zeros_like(pos)
+    e_g = g.energies(vel)
+    e_o = o.energies(vel)
+    assert rel_err(g.psi.value.cpu().numpy(), o.st.psi) < tol
+    assert rel_err(g.phi_q.value.cpu().numpy(), o.st.phi_q) < (1e-6 if dtype == np.float32 else 1e-12)
+    assert rel_err(g.phi_q_fourier.value.cpu().numpy(), o.st.phi_q_fourier) < tol
+    assert abs(e_g[2] - e_o[2]) / max(abs(e_o[2]), abs(cfg.self_energy)) < tol
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bitwise_deterministic_and_order_independent(dtype):
+    """Same particles in a different caller order (and a second run): densities are bitwise
+    identical, per-particle forces are bitwise identical after un-permuting."""
+    from gpu_common import GpuRun
+    from hymd_b200 import _lib
+    cfg, pos, types, _ = _system(20000, [24, 24, 24], [3.0, 3.0, 3.0], dtype, seed=4)
+    # make some cells crowded
+    pos[:2000] = pos[0] + (np.random.default_rng(1).uniform(0, 0.05, size=(2000, 3))).astype(dtype)
+    pos = np.mod(pos, cfg.box_size.astype(dtype)).astype(dtype)
+    a = GpuRun(cfg, pos, types)
+    phi_a = [a.pm._view(_lib.FIELD_PHI, t, 0, "real").clone() for t in range(3)]
+    fa = a.forces()
+    b = GpuRun(cfg, pos, types)
+    assert np.array_equal(fa, b.forces())
+    perm = np.random.default_rng(7).permutation(len(pos))
+    c = GpuRun(cfg, pos[perm], types[perm])
+    for t in range(3):
+        assert torch.equal(phi_a[t], c.pm._view(_lib.FIELD_PHI, t, 0, "real"))
+    assert np.array_equal(fa[perm], c.forces())
+
+
+def test_numpy_fortran_order_inputs_and_inplace_outputs():
+    """main.py hands over host numpy arrays, Fortran-ordered when molecules exist
+    (main.py:500-506); outputs are written in place into the caller's array."""
+    from gpu_common import GpuRun
+    cfg, pos, types, q = _system(4000, [16, 16, 16], [3.0, 3.0, 3.0], np.float64, seed=5, coulomb=True)
+    ref = GpuRun(cfg, pos, types, charges=q)
+    posf = np.asfortranarray(pos)
+    g = GpuRun(cfg, posf, types.astype(np.int64), charges=q, as_numpy=True)
+    assert isinstance(g.force, np.ndarray)
+    assert np.array_equal(g.force, ref.forces())
+    assert np.array_equal(g.elec_forces, ref.eforces())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_edge_cases(dtype):
+    """Empty type, a single particle, particles on the box faces and outside [0, L)."""
+    from gpu_common import GpuRun, OracleRun, rel_err
+    box = np.array([3.0, 3.0, 3.0], dtype=np.float32)
+    mesh = [12, 12, 12]
+    # type "B" exists in the config but has no particles
+    rng = np.random.default_rng(6)
+    n = 300
+    pos = (rng.uniform(0, 1, size=(n, 3)) * box).astype(dtype)
+    pos[0] = [0.0, 0.0, 0.0]
+    pos[1] = [3.0, 3.0, 3.0]                 # == L: wraps onto vertex 0
+    pos[2] = [-0.25, 3.5, 7.0]               # outside the box: periodic wrap (CIC wraps mod N)
+    pos[3] = np.nextafter(np.asarray([3.0, 3.0, 3.0], dtype=dtype), 0)
+    names = ["A"] * n
+    cfg = make_config(names + ["B"], n, mesh, box, chi=[("A", "B", 5.0)], dtype=dtype)
+    types = np.zeros(n, dtype=np.int32)
+    g = GpuRun(cfg, pos, types)
+    o = OracleRun(cfg, pos, types)
+    assert rel_err(g.forces(), o.force) < TOL[dtype]
+    # single particle: forces ~ 0 by symmetry of its own filtered density, must be finite
+    cfg1 = make_config(["A"], 1, mesh, box, dtype=dtype, hamiltonian="DefaultNoChi")
+    g1 = GpuRun(cfg1, pos[5:6], np.zeros(1, dtype=np.int32))
+    o1 = OracleRun(cfg1, pos[5:6], np.zeros(1, dtype=np.int32))
+    assert np.isfinite(g1.forces()).all()
+    scale = np.abs(np.stack([np.stack(fm) for fm in o1.st.force_mesh])).max()
+    assert np.abs(g1.forces() - o1.force).max() / scale < TOL[dtype]
+
+
+def test_per_type_paint_mass_and_shared_potential_rows():
+    """config.m per-type paint masses (field.py:574) and types whose interaction rows coincide
+    (DefaultNoChi: all of them) share one force-mesh triple."""
+    from gpu_common import GpuRun, OracleRun, rel_err
+    cfg, pos, types, _ = _system(3000, [16, 16, 16], [3.0, 3.0, 3.0], np.float64, seed=8,
+                                 hamiltonian="DefaultNoChi", chi=(), m=[1.0, 2.5, 0.5])
+    g = GpuRun(cfg, pos, types)
+    o = OracleRun(cfg, pos, types)
+    assert g.pm.status()["potential_rows"] == 1
+    assert rel_err(g.forces(), o.force) < 1e-10

@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Benchmark of the particle-mesh field-force cycle (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload C4] [--dtype f32|f64] [--scaling strong|weak]
+
+One "step" = one field-force cycle on one batch of synthetic particles: cell binning
+(pm.decompose) + update_field (paint, FFTs, fused k-space) + compute_field_force (readout)
+[+ update_field_force_q for the PME workload C3], i.e. what HyMD's main.py:976-1058 runs every
+outer MD step.  Prints ONE JSON line (rank 0).
+
+* value      particle-steps/s with positions/types already resident in HBM (CUDA events,
+             max over ranks), through hymd_b200.field (the reference-shaped API over the C ABI)
+* e2e        same metric with HOST (pinned) positions/types in and HOST forces out every step
+* roofline   dominant hand-written kernel: algorithmic bytes / CUDA-event time vs measured HBM
+* phases     every phase of the cycle with its algorithmic bytes, time and GB/s
+* cpu_baseline  the CPU restatement of the reference path (oracle/, "port") timed on this
+             box's host cores on a bounded sample (N = 1 only)
+
+--impl reference times that CPU port instead (the reference's own pmesh/PFFT/mpi4py stack
+cannot be installed in this image), on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "field-force particle-steps/s"
+UNIT = "particle-steps/s"
+PS_PER_CYCLE = 0.01 * 25        # time_step 0.01 ps x respa_inner 25 (examples.rst:426-431)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--n", type=int, default=None, help="override particle count (debug)")
+    ap.add_argument("--mesh", type=int, default=None, help="override mesh size (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    """Measured roofline denominators (MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload, dtype):
+    """DRAM bytes per launch of each hand-written kernel from the committed ncu --set full
+    capture (profiles/traffic.json), or {} when there is none for this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)
+        return t.get(f"{workload}-{dtype}", {})
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 "200", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def build_system(args, world):
+    from hymd_b200.synthetic import SPECS, make_system
+    dtype = np.float32 if args.dtype == "f32" else np.float64
+    n, mesh = args.n, args.mesh
+    if args.scaling == "weak" and world > 1:
+        # per-GPU work fixed: N x world particles on a mesh with world x the cells
+        spec = SPECS[args.workload]
+        n = (n or spec["n"]) * world
+        mesh = int(round((mesh or spec["mesh"]) * world ** (1.0 / 3.0) / 8.0)) * 8
+    return make_system(args.workload, dtype=dtype, n=n, mesh=mesh)
+
+
+def algorithmic_bytes(N, T, U, mesh, b, pme):
+    """bytes each phase must move once (force-only cycle)."""
+    M = int(np.prod(mesh))
+    Mc = mesh[0] * mesh[1] * (mesh[2] // 2 + 1)
+    out = {
+        "paint": N * (3 * b + 4) + T * M * b,
+        "fft_fwd": T * (M * b + Mc * 2 * b),
+        "kspace": T * Mc * 2 * b + 3 * U * Mc * 2 * b,
+        "fft_inv": 3 * U * (Mc * 2 * b + M * b),
+        "readout": N * (3 * b + 4) + 3 * U * M * b + N * 3 * b,
+    }
+    if pme:
+        out["pme_paint"] = N * (4 * b + 4) + M * b
+        out["pme_kspace"] = Mc * 2 * b + 3 * Mc * 2 * b
+        out["pme_fft"] = (M * b + Mc * 2 * b) + 3 * (Mc * 2 * b + M * b)
+        out["pme_readout"] = N * (4 * b + 4) + 3 * M * b + N * 3 * b
+    return out
+
+
+def run_reference(args, rank, world):
+    """CPU port of the reference path (oracle/), all host threads; rank 0 only."""
+    if rank != 0:
+        return
+    import copy
+    from hymd_b200.synthetic import SPECS, make_system
+    from oracle import field_oracle as fo
+    from oracle.hamiltonian_oracle import OracleHamiltonian
+    dtype = np.float32 if args.dtype == "f32" else np.float64
+    spec = SPECS[args.workload]
+    n_full, mesh_full = args.n or spec["n"], args.mesh or spec["mesh"]
+    # bounded sample: same density and mesh spacing, box shrunk by 2 per axis until the whole
+    # run fits ~150 s (measured here: ~1 us per particle-step on 8 cores)
+    total = args.steps + args.warmup
+    n, mesh, shrink = n_full, mesh_full, 0
+    while n * total * 1.0e-6 > 150.0 and mesh % 2 == 0 and mesh >= 32:
+        n, mesh, shrink = n // 8, mesh // 2, shrink + 1
+    sysm = make_system(args.workload, dtype=dtype, n=n, mesh=mesh)
+    cfg = copy.deepcopy(sysm.config)
+    h = OracleHamiltonian(cfg)
+    st = fo.FieldState(cfg, dtype)
+    cores = os.cpu_count() or 1
+
+    def cycle():
+        fo.update_field(st, h, sysm.positions, sysm.types, cfg, workers=-1, mt=True)
+        f = fo.compute_field_force(st, sysm.positions, sysm.types, cfg.n_types, mt=True)
+        if sysm.charges is not None:
+            fo.update_field_force_q(st, h, sysm.charges, sysm.positions, cfg, workers=-1, mt=True)
+        return f
+
+    for _ in range(args.warmup):
+        cycle()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cycle()
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = (f"{args.workload} at full size (N={n}, {mesh}^3)" if shrink == 0 else
+              f"{args.workload} shrunk {2 ** shrink}x per axis at equal density and mesh "
+              f"spacing (N={n}, {mesh}^3 instead of N={n_full}, {mesh_full}^3)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"{args.workload}: N={n_full}, mesh {mesh_full}^3, "
+                               f"T={cfg.n_types}, sigma=0.5, kappa=0.05, DefaultWithChi"},
+        "ns_per_day": args.steps / dt * 86400.0 * PS_PER_CYCLE / 1000.0,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample,
+                         "note": "CPU restatement of field.py + pmesh primitives (C CIC loops "
+                                 "on all threads + scipy.fft workers=-1); the reference's own "
+                                 "pmesh/PFFT/mpi4py stack is not installable in this image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(sysm, dtype):
+    """One cycle of the CPU port on the same inputs (bounded sample: <= ~30 s)."""
+    import copy
+    from oracle import field_oracle as fo
+    from oracle.hamiltonian_oracle import OracleHamiltonian
+    cfg = copy.deepcopy(sysm.config)
+    n = len(sysm.positions)
+    h = OracleHamiltonian(cfg)
+    st = fo.FieldState(cfg, dtype)
+    reps = 1 if n >= 5_000_000 else (3 if n >= 500_000 else 10)
+
+    def cycle():
+        fo.update_field(st, h, sysm.positions, sysm.types, cfg, workers=-1, mt=True)
+        fo.compute_field_force(st, sysm.positions, sysm.types, cfg.n_types, mt=True)
+        if sysm.charges is not None:
+            fo.update_field_force_q(st, h, sysm.charges, sysm.positions, cfg, workers=-1, mt=True)
+
+    if n < 5_000_000:
+        cycle()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cycle()
+    dt = time.perf_counter() - t0
+    return {"value": n * reps / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{reps} full cycle(s) of the same workload (N={n}), "
+                      f"{dt:.1f} s of wall time on all host threads"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (hymd_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from hymd_b200 import field as F
+    from hymd_b200.hamiltonian import get_hamiltonian
+
+    np_dtype = np.float32 if args.dtype == "f32" else np.float64
+    t_dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    b = 4 if args.dtype == "f32" else 8
+    sysm = build_system(args, world)
+    cfg = sysm.config
+    mesh = [int(x) for x in np.full(3, cfg.mesh_size)]
+    T = cfg.n_types
+    N = len(sysm.positions)
+    ham = get_hamiltonian(cfg)
+    pm, fl, ecl, cl = F.initialize_pm(None, cfg)
+    phi, phi_fourier, force_mesh, v_ext_fourier, v_ext, phi_transfer, phi_laplacian = fl
+    phi_q, phi_q_fourier, psi, elec_field = ecl
+    layouts = [pm.decompose(None) for _ in range(T)]
+    pme = sysm.charges is not None
+
+    # this rank's particles (slab along x); single GPU: all of them
+    pos_h, typ_h, q_h = sysm.positions, sysm.types, sysm.charges
+    if world > 1:
+        L = float(cfg.box_size[0])
+        cell = np.floor(pos_h[:, 0].astype(np.float64) * mesh[0] / L).astype(np.int64) % mesh[0]
+        mine = (cell // (mesh[0] // world)) == rank
+        pos_h, typ_h = pos_h[mine], typ_h[mine]
+        q_h = None if q_h is None else q_h[mine]
+    n_loc = len(pos_h)
+    dev = pm.device
+    pos_d = torch.as_tensor(np.ascontiguousarray(pos_h), dtype=t_dtype, device=dev)
+    typ_d = torch.as_tensor(typ_h.astype(np.int32), device=dev)
+    q_d = None if q_h is None else torch.as_tensor(q_h, dtype=t_dtype, device=dev)
+    force_d = torch.zeros((n_loc, 3), dtype=t_dtype, device=dev)
+    eforce_d = torch.zeros((n_loc, 3), dtype=t_dtype, device=dev) if pme else None
+
+    def cycle(pos, typ, q, force, eforce):
+        F.update_field(phi, phi_laplacian, phi_transfer, layouts, force_mesh, ham, pm, pos, typ,
+                       cfg, v_ext, phi_fourier, v_ext_fourier, cfg.m, compute_potential=False)
+        F.compute_field_force(layouts, pos, force_mesh, force, typ, T)
+        if pme:
+            F.update_field_force_q(q, phi_q, phi_q_fourier, psi, None, None, elec_field, eforce,
+                                   pm.decompose(None), ham, pm, pos, cfg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps between barrier+synchronize, CUDA events, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    # ---- device-resident run ---------------------------------------------------------------
+    dev_cycle = lambda: cycle(pos_d, typ_d, q_d, force_d, eforce_d)
+    for _ in range(max(args.warmup, 3)):
+        dev_cycle()
+    torch.cuda.synchronize()
+    pm.set_timing(True)
+    pm.timings()
+    launches0 = pm.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total = timed(dev_cycle, args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = pm.launch_count() - launches0
+    phase_ms = pm.timings()
+    pm.set_timing(False)
+    ms_per_step = ms_total / args.steps
+    N_global = N
+    value = N_global * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: host (pinned) in, host out, every step --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pos_p = torch.from_numpy(np.ascontiguousarray(pos_h)).pin_memory()
+        typ_p = torch.from_numpy(typ_h.astype(np.int32)).pin_memory()
+        q_p = None if q_h is None else torch.from_numpy(np.ascontiguousarray(q_h)).pin_memory()
+        force_p = torch.zeros((n_loc, 3), dtype=t_dtype).pin_memory()
+        eforce_p = torch.zeros((n_loc, 3), dtype=t_dtype).pin_memory() if pme else None
+        host_cycle = lambda: cycle(pos_p, typ_p, q_p, force_p, eforce_p)
+        for _ in range(2):
+            host_cycle()
+        k = max(3, min(args.steps, 10))
+        ms_e2e = timed(host_cycle, k)
+        if not np.isfinite(force_p.numpy()).all() or \
+                not torch.equal(force_p, force_d.cpu()):
+            raise SystemExit("end-to-end forces differ from the device-resident run")
+        h2d = pos_p.numel() * pos_p.element_size() + typ_p.numel() * 4 + \
+            (q_p.numel() * q_p.element_size() if pme else 0)
+        d2h = force_p.numel() * force_p.element_size() * (2 if pme else 1)
+        e2e = {"value": N_global * k / (ms_e2e * 1e-3), "unit": UNIT, "steps": k,
+               "ms_per_step": ms_e2e / k, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h),
+               "path": "hymd_b200.field.update_field + compute_field_force with pinned host "
+                       "tensors (per rank)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline / phases -----------------------------------------------------------------
+    peak, peak_src = peaks()
+    U = pm.status()["potential_rows"]
+    loc_mesh = [mesh[0] // world, mesh[1], mesh[2]]
+    alg = algorithmic_bytes(n_loc, T, U, loc_mesh, b, pme)
+    traffic = ncu_traffic(args.workload, args.dtype)
+    phases = {}
+    for name, (ms, calls) in phase_ms.items():
+        per = ms / args.steps
+        ent = {"ms_per_step": per, "share": per / ms_per_step}
+        if name in alg:
+            ent["algorithmic_bytes"] = int(alg[name])
+            ent["gbs"] = alg[name] / (per * 1e-3) / 1e9 if per > 0 else None
+            ent["frac_of_peak"] = ent["gbs"] / peak if per > 0 else None
+        phases[name] = ent
+    own = [k for k in ("paint", "kspace", "readout") if k in phases]
+    dom = max(own, key=lambda k: phases[k]["ms_per_step"])
+    roofline = {"kernel": {"paint": "paint_kernel", "kspace": "kspace_force_kernel",
+                           "readout": "readout_kernel"}[dom],
+                "bound": "hbm", "achieved": phases[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": phases[dom]["frac_of_peak"], "traffic": traffic.get(dom),
+                "algorithmic_bytes": phases[dom]["algorithmic_bytes"],
+                "peak_source": peak_src,
+                "timing": "CUDA events around the phase on the launch stream, averaged over the "
+                          "timed steps"}
+    total_alg = sum(alg.values())
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"{args.workload}: N={N_global}, mesh {mesh[0]}x{mesh[1]}x{mesh[2]}, "
+                               f"T={T} (U={U} distinct potential rows), sigma={cfg.sigma}, "
+                               f"kappa={cfg.kappa}, DefaultWithChi" + (", PME" if pme else ""),
+                   "l2": "inputs larger than L2 (per-step working set "
+                         f"{total_alg / 1e6:.0f} MB vs 126 MB L2), no flush",
+                   "parallelism": "single GPU" if world == 1 else f"{world} x-slabs (slab FFT, NCCL all-to-all)"},
+        "ns_per_day": args.steps / (ms_total * 1e-3) * 86400.0 * PS_PER_CYCLE / 1000.0,
+        "cycle_frac_of_hbm_roofline": total_alg / (ms_per_step * 1e-3) / 1e9 / peak,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "phases": phases,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(sysm, np_dtype)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

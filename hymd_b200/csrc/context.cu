@@ -223,6 +223,8 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     hymd_ctx* c = new hymd_ctx();
     memset(c, 0, sizeof(*c));
     c->cfg = *cfg;
+    c->ev_pool = new std::vector<cudaEvent_t>();
+    c->ev_open = new std::vector<PhaseInterval>();
     c->f64 = cfg->dtype == HYMD_F64;
     c->rsz = c->f64 ? 8 : 4;
     c->T = cfg->n_types;
@@ -301,7 +303,35 @@ int hymd_ctx_destroy(hymd_ctx* c) {
                     c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->emesh, c->psi, c->fft_work};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    if (c->ev_open) {
+        for (auto& iv : *c->ev_open) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
+        delete c->ev_open;
+    }
+    if (c->ev_pool) {
+        for (cudaEvent_t e : *c->ev_pool) cudaEventDestroy(e);
+        delete c->ev_pool;
+    }
     delete c;
+    return HYMD_OK;
+}
+
+int hymd_ctx_set_timing(hymd_ctx* c, int enable) {
+    if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    c->timing = enable != 0;
+    return HYMD_OK;
+}
+
+int hymd_ctx_get_timings(hymd_ctx* c, double* ms, int64_t* calls) {
+    if (!c || !ms || !calls) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    HYMD_CUDA(cudaDeviceSynchronize());
+    for (auto& iv : *c->ev_open) {
+        float t = 0.f;
+        HYMD_CUDA(cudaEventElapsedTime(&t, iv.a, iv.b));
+        if (iv.phase >= 0 && iv.phase < HYMD_PHASE_COUNT) { ms[iv.phase] += t; calls[iv.phase]++; }
+        c->ev_pool->push_back(iv.a);
+        c->ev_pool->push_back(iv.b);
+    }
+    c->ev_open->clear();
     return HYMD_OK;
 }
 
@@ -349,7 +379,10 @@ int hymd_sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types,
     HYMD_CHECK(ensure_particle_capacity(c, n));
     c->np = n;
     c->has_charges = d_charges != nullptr;
-    HYMD_CHECK(sort_particles(c, d_pos, d_types, d_charges, n, (cudaStream_t)stream));
+    {
+        PhaseScope ps(c, HYMD_PHASE_SORT, (cudaStream_t)stream);
+        HYMD_CHECK(sort_particles(c, d_pos, d_types, d_charges, n, (cudaStream_t)stream));
+    }
     c->sorted = true;
     return HYMD_OK;
 }
@@ -365,7 +398,10 @@ int hymd_set_charges(hymd_ctx* c, const void* d_charges, void* stream) {
 int hymd_paint(hymd_ctx* c, void* stream) {
     if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
     if (!c->sorted) { set_error("hymd_paint before hymd_sort_particles"); return HYMD_ERR_STATE; }
-    HYMD_CHECK(paint_types(c, (cudaStream_t)stream));
+    {
+        PhaseScope ps(c, HYMD_PHASE_PAINT, (cudaStream_t)stream);
+        HYMD_CHECK(paint_types(c, (cudaStream_t)stream));
+    }
     c->phi_is_filtered = false;
     c->have_phi_hat = false;
     return HYMD_OK;
@@ -393,19 +429,34 @@ int hymd_field_cycle(hymd_ctx* c, int compute_potential, void* stream) {
     const Geometry& g = c->g;
     const size_t kb = (size_t)g.k_elems * 2 * c->rsz;
     if (c->phi_is_filtered) { set_error("hymd_field_cycle needs a fresh hymd_paint"); return HYMD_ERR_STATE; }
-    HYMD_CHECK(exec_r2c(c, c->plan_r2c_T, c->phi, c->phi_hat, s));
+    {
+        PhaseScope ps(c, HYMD_PHASE_FFT_FWD, s);
+        HYMD_CHECK(exec_r2c(c, c->plan_r2c_T, c->phi, c->phi_hat, s));
+    }
     c->have_phi_hat = true;
     const bool cp = compute_potential != 0;
     if (cp) {
         HYMD_CHECK(dev_alloc(&c->v_hat, c->T * kb));
         HYMD_CHECK(dev_alloc(&c->phif_hat, c->T * kb));
     }
-    HYMD_CHECK(kspace_forces(c, cp, cp, s));
-    HYMD_CHECK(exec_c2r(c, c->plan_c2r_3U, c->f_hat, c->gmesh, s));
-    HYMD_CHECK(fill_ghosts(c, c->gmesh, 3 * c->U, s));
+    {
+        PhaseScope ps(c, HYMD_PHASE_KSPACE, s);
+        HYMD_CHECK(kspace_forces(c, cp, cp, s));
+    }
+    {
+        PhaseScope ps(c, HYMD_PHASE_FFT_INV, s);
+        HYMD_CHECK(exec_c2r(c, c->plan_c2r_3U, c->f_hat, c->gmesh, s));
+    }
+    {
+        PhaseScope ps(c, HYMD_PHASE_GHOST, s);
+        HYMD_CHECK(fill_ghosts(c, c->gmesh, 3 * c->U, s));
+    }
     c->have_forces = true;
     c->have_phif = cp;
-    if (cp) HYMD_CHECK(materialize_impl(c, true, true, s));
+    if (cp) {
+        PhaseScope ps(c, HYMD_PHASE_BYPRODUCTS, s);
+        HYMD_CHECK(materialize_impl(c, true, true, s));
+    }
     return HYMD_OK;
 }
 
@@ -446,6 +497,7 @@ int hymd_readout(hymd_ctx* c, void* d_force, void* stream) {
         return HYMD_ERR_STATE;
     }
     if (c->np == 0) return HYMD_OK;
+    PhaseScope ps(c, HYMD_PHASE_READOUT, (cudaStream_t)stream);
     return readout_forces(c, d_force, (cudaStream_t)stream);
 }
 
@@ -459,20 +511,35 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
     cudaStream_t s = (cudaStream_t)stream;
     const Geometry& g = c->g;
     const size_t kb = (size_t)g.k_elems * 2 * c->rsz, rb = (size_t)g.real_elems * c->rsz;
-    HYMD_CHECK(paint_charges(c, s));
-    HYMD_CHECK(exec_r2c(c, c->plan_r2c_1, c->phi_q, c->phiq_hat, s));
+    {
+        PhaseScope ps(c, HYMD_PHASE_PME_PAINT, s);
+        HYMD_CHECK(paint_charges(c, s));
+    }
+    {
+        PhaseScope ps(c, HYMD_PHASE_PME_FFT, s);
+        HYMD_CHECK(exec_r2c(c, c->plan_r2c_1, c->phi_q, c->phiq_hat, s));
+    }
     c->have_phiq_hat = true;
     if (want_psi) {
         HYMD_CHECK(dev_alloc(&c->phiqf_hat, kb));
         HYMD_CHECK(dev_alloc(&c->psi, rb));
     }
-    HYMD_CHECK(kspace_pme(c, want_psi != 0, s));
-    HYMD_CHECK(exec_c2r(c, c->plan_c2r_3, c->e_hat, c->emesh, s));
-    HYMD_CHECK(fill_ghosts(c, c->emesh, 3, s));
-    if (want_psi)
-        HYMD_CHECK(exec_c2r(c, c->plan_c2r_1, (char*)c->e_hat + 3 * kb, c->psi, s));
+    {
+        PhaseScope ps(c, HYMD_PHASE_PME_KSPACE, s);
+        HYMD_CHECK(kspace_pme(c, want_psi != 0, s));
+    }
+    {
+        PhaseScope ps(c, HYMD_PHASE_PME_FFT, s);
+        HYMD_CHECK(exec_c2r(c, c->plan_c2r_3, c->e_hat, c->emesh, s));
+        HYMD_CHECK(fill_ghosts(c, c->emesh, 3, s));
+        if (want_psi)
+            HYMD_CHECK(exec_c2r(c, c->plan_c2r_1, (char*)c->e_hat + 3 * kb, c->psi, s));
+    }
     c->have_psi = want_psi != 0;
-    if (c->np > 0 && d_elec_force) HYMD_CHECK(readout_pme(c, d_elec_force, s));
+    if (c->np > 0 && d_elec_force) {
+        PhaseScope ps(c, HYMD_PHASE_PME_READOUT, s);
+        HYMD_CHECK(readout_pme(c, d_elec_force, s));
+    }
     return HYMD_OK;
 }
 

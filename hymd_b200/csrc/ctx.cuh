@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <vector>
 
 #include "../../include/hymd_b200.h"
 
@@ -91,6 +92,11 @@ struct Geometry {
     long long k_elems;     // Nx*nyl*Nzcp  (complex elements per spectrum)
 };
 
+struct PhaseInterval {
+    int phase;
+    cudaEvent_t a, b;
+};
+
 }  // namespace hymd
 
 struct hymd_ctx {
@@ -157,9 +163,40 @@ struct hymd_ctx {
     size_t readout_smem, readout_smem_pme;
 
     int64_t launches;
+
+    // phase timing (hymd_ctx_set_timing)
+    bool timing;
+    std::vector<cudaEvent_t>* ev_pool;      // free events
+    std::vector<hymd::PhaseInterval>* ev_open;   // recorded, not yet read
 };
 
 namespace hymd {
+// Brackets a phase with CUDA events on stream s while timing is enabled (destructor closes it,
+// so early returns through HYMD_CHECK are covered).
+struct PhaseScope {
+    hymd_ctx* c;
+    cudaStream_t s;
+    cudaEvent_t a, b;
+    int phase;
+    bool on;
+    PhaseScope(hymd_ctx* c_, int phase_, cudaStream_t s_) : c(c_), s(s_), phase(phase_), on(c_->timing) {
+        if (!on) return;
+        a = take(); b = take();
+        cudaEventRecord(a, s);
+    }
+    ~PhaseScope() {
+        if (!on) return;
+        cudaEventRecord(b, s);
+        c->ev_open->push_back({phase, a, b});
+    }
+    cudaEvent_t take() {
+        cudaEvent_t e;
+        if (!c->ev_pool->empty()) { e = c->ev_pool->back(); c->ev_pool->pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+};
+
 // sort.cu
 int sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types, const void* d_q,
                    int64_t n, cudaStream_t s);

@@ -289,13 +289,14 @@ class ParticleMesh:
         probe = (float(a[0, 0]), float(a[n // 2, 1]), float(a[-1, -1])) if a.ndim == 2 and n else ()
         return ("n", id(x), a.ctypes.data, a.shape, probe)
 
-    def sort(self, positions, types, charges=None):
-        """Bin the local particles (all types at once).  Cached on the identity of the inputs:
-        ``compute_field_force`` / ``update_field_force_q`` called after ``update_field`` on the
-        same positions reuse its bins (``types=None`` means "whatever the bins hold")."""
+    def sort(self, positions, types, charges=None, force=False):
+        """Bin the local particles (all types at once).  ``update_field`` always re-bins
+        (``force=True``: it is the call that opens a step, ``main.py:976-996``);
+        ``compute_field_force`` / ``update_field_force_q`` called afterwards on the same
+        positions object reuse its bins (``types=None`` means "whatever the bins hold")."""
         pk = self._fingerprint(positions)
         tk = None if types is None else self._fingerprint_types(types)
-        if pk == self._sort_key and (tk is None or tk == self._sort_types_key):
+        if not force and pk == self._sort_key and (tk is None or tk == self._sort_types_key):
             if charges is not None and not self._sorted_with_charges:
                 q = self.as_device(charges, shape=(self._n_local,))
                 _lib.check(self.lib.hymd_set_charges(self._ctx, ctypes.c_void_p(q.data_ptr()),
@@ -350,6 +351,17 @@ class ParticleMesh:
         _lib.check(self.lib.hymd_ctx_status(self._ctx, out))
         return {"max_cell_count": out[0], "out_of_slab": out[1], "n_local": out[2],
                 "potential_rows": out[3]}
+
+    def set_timing(self, enable=True):
+        _lib.check(self.lib.hymd_ctx_set_timing(self._ctx, int(bool(enable))))
+
+    def timings(self):
+        """{phase: (milliseconds, intervals)} accumulated since the previous call."""
+        n = len(_lib.PHASES)
+        ms = (ctypes.c_double * n)()
+        calls = (ctypes.c_int64 * n)()
+        _lib.check(self.lib.hymd_ctx_get_timings(self._ctx, ms, calls))
+        return {_lib.PHASES[i]: (ms[i], calls[i]) for i in range(n) if calls[i]}
 
     def launch_count(self):
         return int(self.lib.hymd_launch_count(self._ctx))

@@ -149,6 +149,32 @@ int hymd_ctx_status(hymd_ctx* ctx, int64_t out[4]);
 /* Number of CUDA kernels launched by this context since creation (bench bookkeeping). */
 int64_t hymd_launch_count(hymd_ctx* ctx);
 
+/* Per-phase device timing (bench bookkeeping; nothing in the reference corresponds).  While
+ * enabled, every phase of the entry points above is bracketed by CUDA events on the caller's
+ * stream.  hymd_ctx_get_timings synchronizes, ADDS the elapsed milliseconds and the number of
+ * bracketed intervals of each phase since the last call into ms[HYMD_PHASE_COUNT] /
+ * calls[HYMD_PHASE_COUNT] (the caller zeroes them), and recycles the events. */
+typedef enum {
+    HYMD_PHASE_SORT = 0,        /* cell binning: count + scan + scatter            */
+    HYMD_PHASE_PAINT = 1,       /* CIC paint of all types                          */
+    HYMD_PHASE_FFT_FWD = 2,     /* density r2c (cuFFT + pack/transposes)           */
+    HYMD_PHASE_KSPACE = 3,      /* fused filter + potential + ik kernel            */
+    HYMD_PHASE_FFT_INV = 4,     /* force-mesh c2r (cuFFT + pack/transposes)        */
+    HYMD_PHASE_GHOST = 5,       /* periodic ghost planes / halo fetch of force meshes */
+    HYMD_PHASE_READOUT = 6,     /* CIC gather of the forces                        */
+    HYMD_PHASE_PME_PAINT = 7,
+    HYMD_PHASE_PME_FFT = 8,
+    HYMD_PHASE_PME_KSPACE = 9,
+    HYMD_PHASE_PME_READOUT = 10,
+    HYMD_PHASE_ALLTOALL = 11,   /* NCCL all-to-all of the slab FFT transposes (inside 2/4/8) */
+    HYMD_PHASE_HALO = 12,       /* paint ghost-plane reduce (inside 1/7)           */
+    HYMD_PHASE_MIGRATE = 13,    /* hymd_migrate                                    */
+    HYMD_PHASE_BYPRODUCTS = 14, /* phi~ / v_ext / psi materialization              */
+    HYMD_PHASE_COUNT = 16
+} hymd_phase;
+int hymd_ctx_set_timing(hymd_ctx* ctx, int enable);
+int hymd_ctx_get_timings(hymd_ctx* ctx, double* ms, int64_t* calls);
+
 /* domain_decomposition / layout.exchange (field.py:1115-1178): GPU-side particle migration
  * between slabs.  Packs particles whose wrapped x lies outside this slab, exchanges them with
  * NCCL, and compacts.  d_arrays[i] is an (capacity, width[i]) array of 4- or 8-byte elements

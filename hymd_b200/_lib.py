@@ -24,7 +24,7 @@ EXPORTS = [
     "hymd_ctx_destroy", "hymd_ctx_set_box", "hymd_ctx_set_interaction", "hymd_sort_particles",
     "hymd_set_charges", "hymd_paint", "hymd_field_cycle", "hymd_readout", "hymd_pme_cycle",
     "hymd_materialize", "hymd_field_energy", "hymd_get_field", "hymd_ctx_status",
-    "hymd_launch_count", "hymd_migrate", "hymd_ctx_set_timing", "hymd_ctx_get_timings",
+    "hymd_launch_count", "hymd_migrate_plan", "hymd_migrate_apply", "hymd_ctx_set_timing", "hymd_ctx_get_timings",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -89,7 +89,8 @@ def load():
     lib.hymd_launch_count.restype = i64
     lib.hymd_ctx_set_timing.argtypes = [vp, ctypes.c_int]
     lib.hymd_ctx_get_timings.argtypes = [vp, P(dbl), P(i64)]
-    lib.hymd_migrate.argtypes = [vp, P(vp), P(i32), P(i32), ctypes.c_int, i64, P(i64), vp]
+    lib.hymd_migrate_plan.argtypes = [vp, vp, i64, P(i64), vp]
+    lib.hymd_migrate_apply.argtypes = [vp, vp, vp, i32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("hymd_last_error", "hymd_launch_count"):

@@ -17,7 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhymd_b200.so")
-SOURCES = ["context.cu", "sort.cu", "paint.cu", "kspace.cu", "readout.cu", "energy.cu"]
+SOURCES = ["context.cu", "sort.cu", "paint.cu", "kspace.cu", "readout.cu", "energy.cu",
+           "slabfft.cu", "comm.cu", "migrate.cu"]
 HEADERS = [os.path.join(CSRC, "ctx.cuh"), os.path.join(HERE, "..", "include", "hymd_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -68,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force or jobs or _stale(LIB, objs):
         cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
         cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + [
-            "-L" + cuda_lib, "-lcufft", "-Xlinker", "-rpath," + cuda_lib]
+            "-L" + cuda_lib, "-lcufft", "-ldl", "-Xlinker", "-rpath," + cuda_lib]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

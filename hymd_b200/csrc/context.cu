@@ -107,70 +107,6 @@ static int build_interaction(hymd_ctx* c) {
     return upload_real(c, c->outscale, os);
 }
 
-struct PlanSpec {
-    cufftHandle* h;
-    bool forward;
-    int batch;
-    bool ghost_out;   // c2r into the ghost-padded layout
-};
-
-static int build_plans(hymd_ctx* c) {
-    const Geometry& g = c->g;
-    if (g.P != 1) {
-        set_error("multi-GPU slab FFT plans are built in slabfft (not available in this build)");
-        return HYMD_ERR_INVALID;
-    }
-    int n[3] = {g.Nx, g.Ny, g.Nz};
-    int real_embed[3] = {g.Nx, g.Ny, g.Nz};
-    int ghost_embed[3] = {g.Nx + 1, g.Ny + 1, g.Nzp};
-    int k_embed[3] = {g.Nx, g.Ny, g.Nzcp};
-    std::vector<PlanSpec> specs = {
-        {&c->plan_r2c_T, true, c->T, false},  {&c->plan_c2r_3U, false, 3 * c->U, true},
-        {&c->plan_c2r_T, false, c->T, false}, {&c->plan_c2r_U, false, c->U, false}};
-    if (c->cfg.pme) {
-        specs.push_back({&c->plan_r2c_1, true, 1, false});
-        specs.push_back({&c->plan_c2r_3, false, 3, true});
-        specs.push_back({&c->plan_c2r_1, false, 1, false});
-    }
-    size_t work = 0;
-    for (auto& sp : specs) {
-        HYMD_CUFFT(cufftCreate(sp.h));
-        HYMD_CUFFT(cufftSetAutoAllocation(*sp.h, 0));
-        size_t ws = 0;
-        if (sp.forward) {
-            HYMD_CUFFT(cufftMakePlanMany(*sp.h, 3, n, real_embed, 1, (int)g.real_elems, k_embed, 1,
-                                         (int)g.k_elems, c->f64 ? CUFFT_D2Z : CUFFT_R2C, sp.batch,
-                                         &ws));
-        } else {
-            int* oe = sp.ghost_out ? ghost_embed : real_embed;
-            long long od = sp.ghost_out ? g.ghost_elems : g.real_elems;
-            HYMD_CUFFT(cufftMakePlanMany(*sp.h, 3, n, k_embed, 1, (int)g.k_elems, oe, 1, (int)od,
-                                         c->f64 ? CUFFT_Z2D : CUFFT_C2R, sp.batch, &ws));
-        }
-        if (ws > work) work = ws;
-    }
-    HYMD_CHECK(dev_alloc(&c->fft_work, work));
-    for (auto& sp : specs) HYMD_CUFFT(cufftSetWorkArea(*sp.h, c->fft_work));
-    c->plans_ready = true;
-    return HYMD_OK;
-}
-
-static int exec_r2c(hymd_ctx* c, cufftHandle h, void* in, void* out, cudaStream_t s) {
-    HYMD_CUFFT(cufftSetStream(h, s));
-    if (c->f64) HYMD_CUFFT(cufftExecD2Z(h, (cufftDoubleReal*)in, (cufftDoubleComplex*)out));
-    else HYMD_CUFFT(cufftExecR2C(h, (cufftReal*)in, (cufftComplex*)out));
-    c->launches += 2;   // cuFFT launches >= 2 kernels per 3-D transform (not ours; lower bound)
-    return HYMD_OK;
-}
-
-static int exec_c2r(hymd_ctx* c, cufftHandle h, void* in, void* out, cudaStream_t s) {
-    HYMD_CUFFT(cufftSetStream(h, s));
-    if (c->f64) HYMD_CUFFT(cufftExecZ2D(h, (cufftDoubleComplex*)in, (cufftDoubleReal*)out));
-    else HYMD_CUFFT(cufftExecC2R(h, (cufftComplex*)in, (cufftReal*)out));
-    c->launches += 2;
-    return HYMD_OK;
-}
-
 static int ensure_particle_capacity(hymd_ctx* c, int64_t n) {
     if (n <= c->cap) return HYMD_OK;
     int64_t cap = n + n / 8 + 1024;
@@ -223,6 +159,7 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     hymd_ctx* c = new hymd_ctx();
     memset(c, 0, sizeof(*c));
     c->cfg = *cfg;
+    c->plans = new std::vector<PlanEntry>();
     c->ev_pool = new std::vector<cudaEvent_t>();
     c->ev_open = new std::vector<PhaseInterval>();
     c->f64 = cfg->dtype == HYMD_F64;
@@ -248,7 +185,8 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     }
     for (int a = 0; a < 3; ++a) g.box[a] = cfg->box[a];
     g.ncell = (long long)g.nxl * g.Ny * g.Nz;
-    g.real_elems = (long long)(P == 1 ? g.nxl : g.nxl + 1) * g.Ny * g.Nz;
+    g.vx = P == 1 ? g.nxl : g.nxl + 1;
+    g.real_elems = (long long)g.vx * g.Ny * g.Nz;
     g.ghost_elems = (long long)(g.nxl + 1) * (g.Ny + 1) * g.Nzp;
     g.k_elems = (long long)g.Nx * g.nyl * g.Nzcp;
     if (g.ncell + 1 >= (1LL << 31) || g.ghost_elems >= (1LL << 31) || g.k_elems >= (1LL << 31)) {
@@ -276,11 +214,14 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     if (cfg->pme) {
         if ((st = dev_alloc(&c->phi_q, rb))) return fail(st);
         if ((st = dev_alloc(&c->phiq_hat, kb))) return fail(st);
-        if ((st = dev_alloc(&c->e_hat, 4 * kb))) return fail(st);
+        if ((st = dev_alloc(&c->e_hat, 3 * kb))) return fail(st);
         if ((st = dev_alloc(&c->emesh, 3 * gb))) return fail(st);
         if (cudaMemset(c->emesh, 0, 3 * gb) != cudaSuccess) return fail(HYMD_ERR_CUDA);
     }
-    if ((st = build_plans(c))) return fail(st);
+    // slab pipeline: always with several GPUs; on one GPU only when asked for (testing)
+    const char* force_slab = getenv("HYMD_B200_FORCE_SLAB");
+    c->slab = P > 1 || (force_slab && force_slab[0] == '1');
+    if (P > 1 && (st = comm_create(c, nccl_id))) return fail(st);
     if ((st = readout_setup(c))) return fail(st);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(HYMD_ERR_CUDA);
     *out = c;
@@ -290,17 +231,14 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
 int hymd_ctx_destroy(hymd_ctx* c) {
     if (!c) return HYMD_OK;
     cudaDeviceSynchronize();
-    if (c->plans_ready) {
-        cufftHandle hs[] = {c->plan_r2c_T, c->plan_c2r_3U, c->plan_c2r_T, c->plan_c2r_U};
-        for (cufftHandle h : hs) cufftDestroy(h);
-        if (c->cfg.pme) {
-            cufftDestroy(c->plan_r2c_1); cufftDestroy(c->plan_c2r_3); cufftDestroy(c->plan_c2r_1);
-        }
-    }
+    if (c->plans) { destroy_plans(c); delete c->plans; c->plans = nullptr; }
+    migrate_destroy(c);
+    comm_destroy(c);
     void* bufs[] = {c->rec, c->key, c->rank_in_cell, c->cell_count, c->cell_start, c->q_sorted,
                     c->scalars, c->scan_tmp, c->tab, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
                     c->phi_hat, c->f_hat, c->gmesh, c->v_hat, c->phif_hat, c->tmp_hat, c->v_ext,
-                    c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->emesh, c->psi, c->fft_work};
+                    c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->psi_hat, c->emesh, c->psi, c->fft_work,
+                    c->wA, c->wS, c->halo};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->ev_open) {
@@ -356,13 +294,8 @@ int hymd_ctx_set_interaction(hymd_ctx* c, const double* A, const double* cc, con
     HYMD_CHECK(build_tables(c));
     HYMD_CHECK(build_interaction(c));
     if (c->U != oldU) {
-        // the number of distinct potential rows changed: batch sizes and the TMA box set change
-        cufftDestroy(c->plan_c2r_3U); cufftDestroy(c->plan_c2r_U);
-        cufftDestroy(c->plan_r2c_T); cufftDestroy(c->plan_c2r_T);
-        if (c->cfg.pme) { cufftDestroy(c->plan_r2c_1); cufftDestroy(c->plan_c2r_3); cufftDestroy(c->plan_c2r_1); }
-        c->plans_ready = false;
-        if (c->fft_work) { cudaFree(c->fft_work); c->fft_work = nullptr; }
-        HYMD_CHECK(build_plans(c));
+        // the number of distinct potential rows changed: the TMA box set changes (cuFFT plans
+        // are cached per batch size)
         HYMD_CHECK(readout_setup(c));
     }
     return HYMD_OK;
@@ -401,6 +334,7 @@ int hymd_paint(hymd_ctx* c, void* stream) {
     {
         PhaseScope ps(c, HYMD_PHASE_PAINT, (cudaStream_t)stream);
         HYMD_CHECK(paint_types(c, (cudaStream_t)stream));
+        HYMD_CHECK(halo_reduce(c, c->phi, c->T, (cudaStream_t)stream));
     }
     c->phi_is_filtered = false;
     c->have_phi_hat = false;
@@ -412,12 +346,12 @@ static int materialize_impl(hymd_ctx* c, bool want_phi, bool want_v, cudaStream_
     const size_t kb = (size_t)g.k_elems * 2 * c->rsz, rb = (size_t)g.real_elems * c->rsz;
     if (want_v) {
         HYMD_CHECK(dev_alloc(&c->v_ext, c->T * rb));
-        HYMD_CHECK(exec_c2r(c, c->plan_c2r_U, c->v_hat, c->v_ext, s));   // consumes v_hat
+        HYMD_CHECK(fft_inverse(c, c->v_hat, c->U, c->v_ext, false, s));   // consumes v_hat
     }
     if (want_phi) {
         HYMD_CHECK(dev_alloc(&c->tmp_hat, c->T * kb));
         HYMD_CUDA(cudaMemcpyAsync(c->tmp_hat, c->phif_hat, c->T * kb, cudaMemcpyDeviceToDevice, s));
-        HYMD_CHECK(exec_c2r(c, c->plan_c2r_T, c->tmp_hat, c->phi, s));
+        HYMD_CHECK(fft_inverse(c, c->tmp_hat, c->T, c->phi, false, s));
         c->phi_is_filtered = true;
     }
     return HYMD_OK;
@@ -431,7 +365,7 @@ int hymd_field_cycle(hymd_ctx* c, int compute_potential, void* stream) {
     if (c->phi_is_filtered) { set_error("hymd_field_cycle needs a fresh hymd_paint"); return HYMD_ERR_STATE; }
     {
         PhaseScope ps(c, HYMD_PHASE_FFT_FWD, s);
-        HYMD_CHECK(exec_r2c(c, c->plan_r2c_T, c->phi, c->phi_hat, s));
+        HYMD_CHECK(fft_forward(c, c->phi, c->T, c->phi_hat, s));
     }
     c->have_phi_hat = true;
     const bool cp = compute_potential != 0;
@@ -445,11 +379,12 @@ int hymd_field_cycle(hymd_ctx* c, int compute_potential, void* stream) {
     }
     {
         PhaseScope ps(c, HYMD_PHASE_FFT_INV, s);
-        HYMD_CHECK(exec_c2r(c, c->plan_c2r_3U, c->f_hat, c->gmesh, s));
+        HYMD_CHECK(fft_inverse(c, c->f_hat, 3 * c->U, c->gmesh, true, s));
     }
     {
         PhaseScope ps(c, HYMD_PHASE_GHOST, s);
         HYMD_CHECK(fill_ghosts(c, c->gmesh, 3 * c->U, s));
+        HYMD_CHECK(halo_fetch(c, c->gmesh, 3 * c->U, s));
     }
     c->have_forces = true;
     c->have_phif = cp;
@@ -471,9 +406,10 @@ int hymd_materialize(hymd_ctx* c, int want_phi, int want_phi_fourier, int want_v
             return HYMD_ERR_STATE;
         }
         HYMD_CHECK(dev_alloc(&c->phiqf_hat, kb));
+        HYMD_CHECK(dev_alloc(&c->psi_hat, kb));
         HYMD_CHECK(dev_alloc(&c->psi, (size_t)c->g.real_elems * c->rsz));
         HYMD_CHECK(kspace_pme(c, true, s));   // e_hat is scratch between cycles
-        HYMD_CHECK(exec_c2r(c, c->plan_c2r_1, (char*)c->e_hat + 3 * kb, c->psi, s));
+        HYMD_CHECK(fft_inverse(c, c->psi_hat, 1, c->psi, false, s));
         c->have_psi = true;
     }
     if (!(want_phi || want_phi_fourier || want_v_ext)) return HYMD_OK;
@@ -514,14 +450,16 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
     {
         PhaseScope ps(c, HYMD_PHASE_PME_PAINT, s);
         HYMD_CHECK(paint_charges(c, s));
+        HYMD_CHECK(halo_reduce(c, c->phi_q, 1, s));
     }
     {
         PhaseScope ps(c, HYMD_PHASE_PME_FFT, s);
-        HYMD_CHECK(exec_r2c(c, c->plan_r2c_1, c->phi_q, c->phiq_hat, s));
+        HYMD_CHECK(fft_forward(c, c->phi_q, 1, c->phiq_hat, s));
     }
     c->have_phiq_hat = true;
     if (want_psi) {
         HYMD_CHECK(dev_alloc(&c->phiqf_hat, kb));
+        HYMD_CHECK(dev_alloc(&c->psi_hat, kb));
         HYMD_CHECK(dev_alloc(&c->psi, rb));
     }
     {
@@ -530,10 +468,10 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
     }
     {
         PhaseScope ps(c, HYMD_PHASE_PME_FFT, s);
-        HYMD_CHECK(exec_c2r(c, c->plan_c2r_3, c->e_hat, c->emesh, s));
+        HYMD_CHECK(fft_inverse(c, c->e_hat, 3, c->emesh, true, s));
         HYMD_CHECK(fill_ghosts(c, c->emesh, 3, s));
-        if (want_psi)
-            HYMD_CHECK(exec_c2r(c, c->plan_c2r_1, (char*)c->e_hat + 3 * kb, c->psi, s));
+        HYMD_CHECK(halo_fetch(c, c->emesh, 3, s));
+        if (want_psi) HYMD_CHECK(fft_inverse(c, c->psi_hat, 1, c->psi, false, s));
     }
     c->have_psi = want_psi != 0;
     if (c->np > 0 && d_elec_force) {
@@ -561,8 +499,7 @@ int hymd_get_field(hymd_ctx* c, int field_id, int t, int d, void** d_ptr, int64_
                    int64_t pitch[3]) {
     if (!c || !d_ptr || !dims || !pitch) { set_error("null argument"); return HYMD_ERR_INVALID; }
     const Geometry& g = c->g;
-    const size_t rb = (size_t)g.real_elems * c->rsz, kb = (size_t)g.k_elems * 2 * c->rsz,
-                 gb = (size_t)g.ghost_elems * c->rsz;
+    const size_t rb = (size_t)g.real_elems * c->rsz, gb = (size_t)g.ghost_elems * c->rsz;
     auto real_geom = [&]() {
         dims[0] = g.nxl; dims[1] = g.Ny; dims[2] = g.Nz;
         pitch[0] = (int64_t)g.Ny * g.Nz; pitch[1] = g.Nz; pitch[2] = 1;
@@ -571,22 +508,24 @@ int hymd_get_field(hymd_ctx* c, int field_id, int t, int d, void** d_ptr, int64_
         dims[0] = g.nxl; dims[1] = g.Ny; dims[2] = g.Nz;
         pitch[0] = (int64_t)(g.Ny + 1) * g.Nzp; pitch[1] = g.Nzp; pitch[2] = 1;
     };
-    auto k_geom = [&]() {
+    auto k_geom = [&](int F) {
         dims[0] = g.Nx; dims[1] = g.nyl; dims[2] = g.Nzc;
-        pitch[0] = (int64_t)g.nyl * g.Nzcp; pitch[1] = g.Nzcp; pitch[2] = 1;
+        pitch[0] = klayout(c, F).xs; pitch[1] = g.Nzcp; pitch[2] = 1;
     };
+    const size_t csz = 2 * c->rsz;
     const bool t_ok = t >= 0 && t < c->T, d_ok = d >= 0 && d < 3;
     char* p = nullptr;
     switch (field_id) {
         case HYMD_FIELD_PHI: if (!t_ok) break; p = (char*)c->phi + t * rb; real_geom(); break;
         case HYMD_FIELD_PHI_FOURIER:
-            if (!t_ok || !c->phif_hat) break; p = (char*)c->phif_hat + t * kb; k_geom(); break;
+            if (!t_ok || !c->phif_hat) break;
+            p = (char*)c->phif_hat + (size_t)t * klayout(c, c->T).fs * csz; k_geom(c->T); break;
         case HYMD_FIELD_FORCE_MESH:
             if (!t_ok || !d_ok) break; p = (char*)c->gmesh + (3 * c->urow[t] + d) * gb; ghost_geom(); break;
         case HYMD_FIELD_V_EXT:
             if (!t_ok || !c->v_ext) break; p = (char*)c->v_ext + c->urow[t] * rb; real_geom(); break;
         case HYMD_FIELD_PHI_Q: if (!c->phi_q) break; p = (char*)c->phi_q; real_geom(); break;
-        case HYMD_FIELD_PHI_Q_FOURIER: if (!c->phiqf_hat) break; p = (char*)c->phiqf_hat; k_geom(); break;
+        case HYMD_FIELD_PHI_Q_FOURIER: if (!c->phiqf_hat) break; p = (char*)c->phiqf_hat; k_geom(1); break;
         case HYMD_FIELD_PSI: if (!c->psi) break; p = (char*)c->psi; real_geom(); break;
         case HYMD_FIELD_ELEC_FIELD:
             if (!d_ok || !c->emesh) break; p = (char*)c->emesh + d * gb; ghost_geom(); break;
@@ -613,18 +552,21 @@ int hymd_ctx_status(hymd_ctx* c, int64_t out[4]) {
 }
 
 int hymd_nccl_unique_id(uint8_t id[HYMD_NCCL_UNIQUE_ID_BYTES]) {
-    (void)id;
-    set_error("NCCL support is not compiled into this build yet");
-    return HYMD_ERR_NCCL;
+    if (!id) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    return comm_unique_id(id);
 }
 
-int hymd_migrate(hymd_ctx* c, void** d_arrays, const int32_t* width, const int32_t* elem_size,
-                 int n_arrays, int64_t capacity, int64_t* n_inout, void* stream) {
-    (void)d_arrays; (void)width; (void)elem_size; (void)n_arrays; (void)capacity; (void)stream;
-    if (!c || !n_inout) { set_error("null argument"); return HYMD_ERR_INVALID; }
-    if (c->g.P == 1) return HYMD_OK;   // one slab: nothing to exchange
-    set_error("hymd_migrate: multi-GPU exchange not available in this build");
-    return HYMD_ERR_NCCL;
+int hymd_migrate_plan(hymd_ctx* c, const void* d_pos, int64_t n, int64_t* n_new, void* stream) {
+    if (!c || !n_new || (n > 0 && !d_pos)) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (n < 0 || n >= (1LL << 31)) { set_error("n = %lld out of range", (long long)n); return HYMD_ERR_CAPACITY; }
+    if (c->g.P == 1) { *n_new = n; return HYMD_OK; }   // one slab: every particle is home
+    return migrate_plan(c, d_pos, n, n_new, (cudaStream_t)stream);
+}
+
+int hymd_migrate_apply(hymd_ctx* c, const void* d_in, void* d_out, int32_t row_bytes, void* stream) {
+    if (!c || !d_in || !d_out) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (c->g.P == 1) { set_error("hymd_migrate_apply: nothing to move with one slab"); return HYMD_ERR_STATE; }
+    return migrate_apply(c, d_in, d_out, row_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -90,7 +90,23 @@ struct Geometry {
     long long real_elems;  // nxl*Ny*Nz
     long long ghost_elems; // (nxl+1)*(Ny+1)*Nzp
     long long k_elems;     // Nx*nyl*Nzcp  (complex elements per spectrum)
+    int vx;                // x planes stored per real field: nxl (P == 1) or nxl+1 (ghost plane)
 };
+
+// Strides (in complex elements) of a k-space buffer holding F spectra.  Element (f, ix, iyl, iz)
+// lives at f*fs + ix*xs + iyl*Nzcp + iz.
+//   single GPU : [f][x][ky][kz]   fs = Nx*Ny*Nzcp, xs = Ny*Nzcp      (cuFFT batch order)
+//   P slabs    : [x][f][kyl][kz]  fs = nyl*Nzcp,   xs = F*nyl*Nzcp   (all-to-all receive order)
+struct KLayout {
+    long long fs, xs;
+};
+
+struct PlanEntry {
+    int kind, batch;
+    cufftHandle h;
+};
+struct Comm;
+struct MigrateState;
 
 struct PhaseInterval {
     int phase;
@@ -148,14 +164,24 @@ struct hymd_ctx {
     void* phi_q;          // real_elems
     void* phiq_hat;       // k_elems raw
     void* phiqf_hat;      // k_elems filtered/normalised (reference phi_q_fourier)
-    void* e_hat;          // 4 x k_elems: E_x,E_y,E_z, psi
+    void* e_hat;          // 3 x k_elems: E_x,E_y,E_z
+    void* psi_hat;        // k_elems (lazy)
     void* emesh;          // 3 x ghost_elems
     void* psi;            // real_elems
 
-    // cuFFT
-    cufftHandle plan_r2c_T, plan_c2r_3U, plan_c2r_T, plan_c2r_U, plan_r2c_1, plan_c2r_3, plan_c2r_1;
-    bool plans_ready;
-    void* fft_work;         // one work area shared by all plans (they run on one stream)
+    // cuFFT: plans are created on first use and cached by (kind, batch); they share one work
+    // area (everything runs on one stream)
+    std::vector<hymd::PlanEntry>* plans;
+    void* fft_work;
+    size_t fft_work_bytes;
+    bool slab;              // slab pipeline (2-D cuFFT per plane + x transform) instead of 3-D plans
+    void* wA;               // slab work: F x (nxl+1) x Ny x Nzcp complex (2-D transform side)
+    void* wS;               // slab work: all-to-all staging, F x nxl x Ny x Nzcp complex
+    size_t wA_bytes, wS_bytes;
+    void* halo;             // ghost-plane exchange staging
+    size_t halo_bytes;
+    hymd::Comm* comm;       // NCCL communicator (world_size > 1)
+    hymd::MigrateState* mig;
 
     // readout TMA
     CUtensorMap tmap_gmesh, tmap_emesh;
@@ -208,6 +234,31 @@ int paint_charges(hymd_ctx* c, cudaStream_t s);
 // kspace.cu
 int kspace_forces(hymd_ctx* c, bool want_v, bool want_phif, cudaStream_t s);
 int kspace_pme(hymd_ctx* c, bool want_psi, cudaStream_t s);
+// slabfft.cu: 3-D transforms of F fields between the real layout [f][vx][Ny][Nz] (or the
+// ghost-padded force-mesh layout) and the k layout klayout(c, F)
+KLayout klayout(const hymd_ctx* c, int F);
+int fft_forward(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s);
+int fft_inverse(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s);
+int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s);
+int ensure_work(hymd_ctx* c, int F);
+void destroy_plans(hymd_ctx* c);
+int halo_reduce(hymd_ctx* c, void* fields, int F, cudaStream_t s);
+int halo_fetch(hymd_ctx* c, void* ghost_meshes, int F, cudaStream_t s);
+// migrate.cu
+int migrate_plan(hymd_ctx* c, const void* d_pos, int64_t n, int64_t* n_new, cudaStream_t s);
+int migrate_apply(hymd_ctx* c, const void* d_in, void* d_out, int row_bytes, cudaStream_t s);
+void migrate_destroy(hymd_ctx* c);
+// comm.cu
+int comm_unique_id(uint8_t* id);
+int comm_create(hymd_ctx* c, const uint8_t* id);
+void comm_destroy(hymd_ctx* c);
+int comm_alltoall(hymd_ctx* c, const void* send, void* recv, size_t bytes_per_peer, cudaStream_t s);
+// ring exchange: send n blocks (sendp[i], bytes each) to rank+dir, receive n blocks from rank-dir
+int comm_ring(hymd_ctx* c, int dir, void* const* sendp, void* const* recvp, int n, size_t bytes,
+              cudaStream_t s);
+int comm_alltoallv(hymd_ctx* c, const void* send, const size_t* send_off, const size_t* send_bytes,
+                   void* recv, const size_t* recv_off, const size_t* recv_bytes, cudaStream_t s);
+int comm_allgather_host(hymd_ctx* c, const void* mine, void* all, size_t bytes, cudaStream_t s);
 // readout.cu
 int readout_setup(hymd_ctx* c);
 int readout_forces(hymd_ctx* c, void* d_force, cudaStream_t s);

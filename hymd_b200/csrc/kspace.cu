@@ -22,8 +22,9 @@ namespace hymd {
 struct KParams {
     int Nx, Ny, Nz, nyl, y0, Nzc, Nzcp;
     int T, U;
-    long long k_elems;   // complex elements per spectrum
     long long npairs;    // Nx*nyl*Nzcp/2
+    // strides in REALS (2 x complex elements) of each buffer: x stride, field stride
+    long long xs_in, fs_in, xs_f, fs_f, xs_v, fs_v, xs_pf, fs_pf;
 };
 
 __device__ __forceinline__ void load4(const float* p, float v[4]) {
@@ -98,8 +99,8 @@ __global__ void __launch_bounds__(256) kspace_force_kernel(
         real kxe[2], kye[2], kze[2], h[2];
         bool valid[2];
         wave_numbers(tb, p, ix, iy, iz, kxe, kye, kze, h, valid);
-        const long long off = 2 * (((long long)ix * p.nyl + iyl) * p.Nzcp + iz);  // in reals
-        const long long fs = 2 * p.k_elems;                                       // field stride
+        const long long col = 2 * ((long long)iyl * p.Nzcp + iz);   // in reals
+        const long long off = ix * p.xs_in + col, fs = p.fs_in;
         real in[TT > 0 ? TT : 1][4];
         if (TT > 0) {
 #pragma unroll
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(256) kspace_force_kernel(
                 if (TT > 0) { v[0] = in[t][0]; v[1] = in[t][1]; v[2] = in[t][2]; v[3] = in[t][3]; }
                 else load4(phi_hat + t * fs + off, v);
                 const real s0 = valid[0] ? h[0] * s : (real)0, s1 = valid[1] ? h[1] * s : (real)0;
-                store4(phif_hat + t * fs + off, v[0] * s0, v[1] * s0, v[2] * s1, v[3] * s1);
+                store4(phif_hat + t * p.fs_pf + ix * p.xs_pf + col, v[0] * s0, v[1] * s0, v[2] * s1,
+                       v[3] * s1);
             }
         }
         const real g0 = valid[0] ? h[0] * h[0] : (real)0, g1 = valid[1] ? h[1] * h[1] : (real)0;
@@ -135,13 +137,13 @@ __global__ void __launch_bounds__(256) kspace_force_kernel(
             }
             a0 *= g0; b0 *= g0; a1 *= g1; b1 *= g1;
             // F_d = -i k_d (a + i b) = k_d b - i k_d a
-            real* f = f_hat + (long long)(3 * u) * fs + off;
+            real* f = f_hat + (long long)(3 * u) * p.fs_f + ix * p.xs_f + col;
             store4(f, kxe[0] * b0, -kxe[0] * a0, kxe[1] * b1, -kxe[1] * a1);
-            store4(f + fs, kye[0] * b0, -kye[0] * a0, kye[1] * b1, -kye[1] * a1);
-            store4(f + 2 * fs, kze[0] * b0, -kze[0] * a0, kze[1] * b1, -kze[1] * a1);
+            store4(f + p.fs_f, kye[0] * b0, -kye[0] * a0, kye[1] * b1, -kye[1] * a1);
+            store4(f + 2 * p.fs_f, kze[0] * b0, -kze[0] * a0, kze[1] * b1, -kze[1] * a1);
             if (v_hat != nullptr) {
                 if (origin) a0 += cu[u];
-                store4(v_hat + (long long)u * fs + off, a0, b0, a1, b1);
+                store4(v_hat + (long long)u * p.fs_v + ix * p.xs_v + col, a0, b0, a1, b1);
             }
         }
     }
@@ -164,8 +166,9 @@ __global__ void __launch_bounds__(256) kspace_pme_kernel(
         real kxe[2], kye[2], kze[2], h[2];
         bool valid[2];
         wave_numbers(tb, p, ix, iy, iz, kxe, kye, kze, h, valid);
-        const long long off = 2 * (((long long)ix * p.nyl + iyl) * p.Nzcp + iz);
-        const long long fs = 2 * p.k_elems;
+        const long long col = 2 * ((long long)iyl * p.Nzcp + iz);
+        const long long off = ix * p.xs_in + col;       // single-field buffers (rho, psi, rho_f)
+        const long long offe = ix * p.xs_f + col, fs = p.fs_f;
         real v[4];
         load4(rho_hat + off, v);
         const real kx = tb.kx[ix], ky = tb.ky[iy];
@@ -183,9 +186,9 @@ __global__ void __launch_bounds__(256) kspace_pme_kernel(
             store4(rhof_hat + off, v[0] * s0, v[1] * s0, v[2] * s1, v[3] * s1);
         }
         const real a0 = v[0] * g[0], b0 = v[1] * g[0], a1 = v[2] * g[1], b1 = v[3] * g[1];
-        store4(e_hat + off, kxe[0] * b0, -kxe[0] * a0, kxe[1] * b1, -kxe[1] * a1);
-        store4(e_hat + fs + off, kye[0] * b0, -kye[0] * a0, kye[1] * b1, -kye[1] * a1);
-        store4(e_hat + 2 * fs + off, kze[0] * b0, -kze[0] * a0, kze[1] * b1, -kze[1] * a1);
+        store4(e_hat + offe, kxe[0] * b0, -kxe[0] * a0, kxe[1] * b1, -kxe[1] * a1);
+        store4(e_hat + fs + offe, kye[0] * b0, -kye[0] * a0, kye[1] * b1, -kye[1] * a1);
+        store4(e_hat + 2 * fs + offe, kze[0] * b0, -kze[0] * a0, kze[1] * b1, -kze[1] * a1);
         if (psi_hat != nullptr) store4(psi_hat + off, a0, b0, a1, b1);
     }
 }
@@ -195,8 +198,12 @@ static KParams make_kparams(const hymd_ctx* c) {
     KParams p;
     p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nyl = g.nyl; p.y0 = g.y0;
     p.Nzc = g.Nzc; p.Nzcp = g.Nzcp; p.T = c->T; p.U = c->U;
-    p.k_elems = g.k_elems;
     p.npairs = g.k_elems / 2;
+    const KLayout lin = klayout(c, c->T), lf = klayout(c, 3 * c->U), lv = klayout(c, c->U);
+    p.xs_in = 2 * lin.xs; p.fs_in = 2 * lin.fs;
+    p.xs_f = 2 * lf.xs; p.fs_f = 2 * lf.fs;
+    p.xs_v = 2 * lv.xs; p.fs_v = 2 * lv.fs;
+    p.xs_pf = p.xs_in; p.fs_pf = p.fs_in;
     return p;
 }
 
@@ -242,19 +249,19 @@ int kspace_forces(hymd_ctx* c, bool want_v, bool want_phif, cudaStream_t s) {
 
 int kspace_pme(hymd_ctx* c, bool want_psi, cudaStream_t s) {
     KParams p = make_kparams(c);
+    const KLayout l1 = klayout(c, 1), l3 = klayout(c, 3);
+    p.xs_in = 2 * l1.xs; p.fs_in = 2 * l1.fs;
+    p.xs_f = 2 * l3.xs; p.fs_f = 2 * l3.fs;
     const unsigned int grid = kgrid(p.npairs);
     const double m = (double)c->g.Nx * c->g.Ny * c->g.Nz;
     const double coef = 4.0 * 3.14159265358979323846 * c->cfg.elec_conversion / m;
-    const size_t fs = (size_t)2 * c->g.k_elems;
     if (c->f64) {
-        double* e = (double*)c->e_hat;
         kspace_pme_kernel<double><<<grid, 256, 0, s>>>(
-            (const double*)c->phiq_hat, e, want_psi ? e + 3 * fs : nullptr,
+            (const double*)c->phiq_hat, (double*)c->e_hat, want_psi ? (double*)c->psi_hat : nullptr,
             want_psi ? (double*)c->phiqf_hat : nullptr, (const double*)c->tab, coef, 1.0 / m, p);
     } else {
-        float* e = (float*)c->e_hat;
         kspace_pme_kernel<float><<<grid, 256, 0, s>>>(
-            (const float*)c->phiq_hat, e, want_psi ? e + 3 * fs : nullptr,
+            (const float*)c->phiq_hat, (float*)c->e_hat, want_psi ? (float*)c->psi_hat : nullptr,
             want_psi ? (float*)c->phiqf_hat : nullptr, (const float*)c->tab, (float)coef,
             (float)(1.0 / m), p);
     }

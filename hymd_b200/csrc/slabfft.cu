@@ -1,0 +1,356 @@
+// 3-D real transforms of the field-force cycle (RealField.r2c / ComplexField.c2r at
+// field.py:576-578, 584, 613, 616, 366, 377, 397), slab-decomposed so that one code path serves
+// 1..8 GPUs:
+//
+//   forward :  batched 2-D r2c over the (y,z) planes of the local x-slab            (cuFFT)
+//              pack [f][xl][ky][kz] -> [peer][xl][f][kyl][kz] + all-to-all          (ours + NCCL)
+//              1-D transform along x on the k-slab [x][f][kyl][kz]                  (cuFFT or the
+//              fused x-line kernel of xline.cu, which also does the k-space math)
+//   inverse :  the same steps backwards; the final 2-D c2r writes straight into the ghost-padded
+//              force-mesh layout the readout kernel stages through TMA.
+//
+// The receive order of the all-to-all IS the k layout, so the forward transpose needs one pack
+// and no unpack, the inverse one unpack and no pack.  With one GPU and no fused kernel for the
+// mesh size, plain 3-D cuFFT plans are used instead.
+#include "ctx.cuh"
+
+namespace hymd {
+
+enum PlanKind {
+    PK_3D_R2C = 0, PK_3D_C2R, PK_3D_C2R_GHOST,
+    PK_2D_R2C,          // real [F*vx planes]            -> [F*vx][Ny][Nzcp]
+    PK_2D_C2R,          // [F*vx][Ny][Nzcp]              -> real [F*vx planes]
+    PK_2D_C2R_GHOST,    // [F*(nxl+1)][Ny][Nzcp]         -> ghost [F*(nxl+1)][Ny+1][Nzp]
+    PK_1D_FWD_INV       // c2c along x, stride xs, batch = columns (direction given at exec)
+};
+
+KLayout klayout(const hymd_ctx* c, int F) {
+    const Geometry& g = c->g;
+    KLayout l;
+    if (g.P == 1) { l.xs = (long long)g.Ny * g.Nzcp; l.fs = (long long)g.Nx * l.xs; }
+    else { l.fs = (long long)g.nyl * g.Nzcp; l.xs = (long long)F * l.fs; }
+    return l;
+}
+
+void destroy_plans(hymd_ctx* c) {
+    if (!c->plans) return;
+    for (auto& p : *c->plans) cufftDestroy(p.h);
+    c->plans->clear();
+}
+
+static int grow(void** p, size_t* have, size_t want) {
+    if (*have >= want) return HYMD_OK;
+    if (*p) { cudaDeviceSynchronize(); cudaFree(*p); *p = nullptr; *have = 0; }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        return HYMD_ERR_NOMEM;
+    }
+    cudaMemset(*p, 0, want);
+    *have = want;
+    return HYMD_OK;
+}
+
+int ensure_work(hymd_ctx* c, int F) {
+    const Geometry& g = c->g;
+    const size_t csz = 2 * c->rsz;
+    HYMD_CHECK(grow(&c->wA, &c->wA_bytes, (size_t)F * (g.nxl + 1) * g.Ny * g.Nzcp * csz));
+    if (g.P > 1) HYMD_CHECK(grow(&c->wS, &c->wS_bytes, (size_t)F * g.nxl * g.Ny * g.Nzcp * csz));
+    return HYMD_OK;
+}
+
+static int plan_get(hymd_ctx* c, int kind, int F, cufftHandle* out) {
+    for (auto& p : *c->plans)
+        if (p.kind == kind && p.batch == F) { *out = p.h; return HYMD_OK; }
+    const Geometry& g = c->g;
+    cufftHandle h;
+    HYMD_CUFFT(cufftCreate(&h));
+    HYMD_CUFFT(cufftSetAutoAllocation(h, 0));
+    size_t ws = 0;
+    const cufftType r2c = c->f64 ? CUFFT_D2Z : CUFFT_R2C, c2r = c->f64 ? CUFFT_Z2D : CUFFT_C2R,
+                    c2c = c->f64 ? CUFFT_Z2Z : CUFFT_C2C;
+    long long n3[3] = {g.Nx, g.Ny, g.Nz}, n2[2] = {g.Ny, g.Nz}, n1[1] = {g.Nx};
+    long long real3[3] = {g.Nx, g.Ny, g.Nz}, ghost3[3] = {g.Nx + 1, g.Ny + 1, g.Nzp},
+              k3[3] = {g.Nx, g.Ny, g.Nzcp};
+    long long real2[2] = {g.Ny, g.Nz}, ghost2[2] = {g.Ny + 1, g.Nzp}, k2[2] = {g.Ny, g.Nzcp};
+    const long long plane_r = (long long)g.Ny * g.Nz, plane_k = (long long)g.Ny * g.Nzcp,
+                    plane_g = (long long)(g.Ny + 1) * g.Nzp;
+    switch (kind) {
+        case PK_3D_R2C:
+            HYMD_CUFFT(cufftMakePlanMany64(h, 3, n3, real3, 1, g.real_elems, k3, 1, g.k_elems, r2c, F, &ws));
+            break;
+        case PK_3D_C2R:
+            HYMD_CUFFT(cufftMakePlanMany64(h, 3, n3, k3, 1, g.k_elems, real3, 1, g.real_elems, c2r, F, &ws));
+            break;
+        case PK_3D_C2R_GHOST:
+            HYMD_CUFFT(cufftMakePlanMany64(h, 3, n3, k3, 1, g.k_elems, ghost3, 1, g.ghost_elems, c2r, F, &ws));
+            break;
+        case PK_2D_R2C:
+            HYMD_CUFFT(cufftMakePlanMany64(h, 2, n2, real2, 1, plane_r, k2, 1, plane_k, r2c,
+                                           (long long)F * g.vx, &ws));
+            break;
+        case PK_2D_C2R:
+            HYMD_CUFFT(cufftMakePlanMany64(h, 2, n2, k2, 1, plane_k, real2, 1, plane_r, c2r,
+                                           (long long)F * g.vx, &ws));
+            break;
+        case PK_2D_C2R_GHOST:
+            HYMD_CUFFT(cufftMakePlanMany64(h, 2, n2, k2, 1, plane_k, ghost2, 1, plane_g, c2r,
+                                           (long long)F * (g.nxl + 1), &ws));
+            break;
+        case PK_1D_FWD_INV: {
+            // P == 1: one field per call (F ignored, batch = Ny*Nzcp columns); P > 1: all F fields
+            const KLayout l = klayout(c, F);
+            const long long batch = g.P == 1 ? l.xs : l.xs;
+            long long embed[1] = {g.Nx};
+            HYMD_CUFFT(cufftMakePlanMany64(h, 1, n1, embed, l.xs, 1, embed, l.xs, 1, c2c, batch, &ws));
+            break;
+        }
+        default:
+            set_error("unknown plan kind %d", kind);
+            return HYMD_ERR_INVALID;
+    }
+    c->plans->push_back({kind, F, h});
+    if (ws > c->fft_work_bytes) {
+        HYMD_CHECK(grow(&c->fft_work, &c->fft_work_bytes, ws));
+        for (auto& p : *c->plans) HYMD_CUFFT(cufftSetWorkArea(p.h, c->fft_work));
+    } else {
+        HYMD_CUFFT(cufftSetWorkArea(h, c->fft_work));
+    }
+    *out = h;
+    return HYMD_OK;
+}
+
+static int exec_r2c(hymd_ctx* c, cufftHandle h, void* in, void* out, cudaStream_t s) {
+    HYMD_CUFFT(cufftSetStream(h, s));
+    if (c->f64) HYMD_CUFFT(cufftExecD2Z(h, (cufftDoubleReal*)in, (cufftDoubleComplex*)out));
+    else HYMD_CUFFT(cufftExecR2C(h, (cufftReal*)in, (cufftComplex*)out));
+    c->launches += 2;   // cuFFT launches >= 2 kernels per multi-dimensional transform (lower bound)
+    return HYMD_OK;
+}
+
+static int exec_c2r(hymd_ctx* c, cufftHandle h, void* in, void* out, cudaStream_t s) {
+    HYMD_CUFFT(cufftSetStream(h, s));
+    if (c->f64) HYMD_CUFFT(cufftExecZ2D(h, (cufftDoubleComplex*)in, (cufftDoubleReal*)out));
+    else HYMD_CUFFT(cufftExecC2R(h, (cufftComplex*)in, (cufftReal*)out));
+    c->launches += 2;
+    return HYMD_OK;
+}
+
+static int exec_c2c(hymd_ctx* c, cufftHandle h, void* data, int dir, cudaStream_t s) {
+    HYMD_CUFFT(cufftSetStream(h, s));
+    if (c->f64) HYMD_CUFFT(cufftExecZ2Z(h, (cufftDoubleComplex*)data, (cufftDoubleComplex*)data, dir));
+    else HYMD_CUFFT(cufftExecC2C(h, (cufftComplex*)data, (cufftComplex*)data, dir));
+    c->launches += 1;
+    return HYMD_OK;
+}
+
+// ---- pack / unpack around the all-to-all ------------------------------------------------------
+struct PackParams {
+    int P, rank, nxl, nyl, Ny, Nzcp, F, x0;
+    long long total;     // F*nxl*Ny*Nzcp
+    long long xs, fs;    // k layout strides
+};
+
+// forward: A[f][xl'][ky][kz] (nxl+1 planes per field) -> S[q][xl][f][kyl][kz]; the block for this
+// rank goes straight to its place in the k buffer.
+template <typename cx>
+__global__ void __launch_bounds__(256) pack_kernel(const cx* __restrict__ A, cx* __restrict__ S,
+                                                   cx* __restrict__ K, PackParams p) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < p.total; o += stride) {
+        long long r = o;
+        const int kz = (int)(r % p.Nzcp); r /= p.Nzcp;
+        const int kyl = (int)(r % p.nyl); r /= p.nyl;
+        const int f = (int)(r % p.F); r /= p.F;
+        const int xl = (int)(r % p.nxl);
+        const int q = (int)(r / p.nxl);
+        const cx v = A[(((long long)f * (p.nxl + 1) + xl) * p.Ny + (q * p.nyl + kyl)) * p.Nzcp + kz];
+        if (q == p.rank) K[(long long)(p.x0 + xl) * p.xs + f * p.fs + (long long)kyl * p.Nzcp + kz] = v;
+        else S[o] = v;
+    }
+}
+
+// inverse: S[q][xl][f][kyl][kz] (block q received from rank q; own block read from the k buffer)
+// -> A[f][xl'][ky][kz]
+template <typename cx>
+__global__ void __launch_bounds__(256) unpack_kernel(const cx* __restrict__ S, const cx* __restrict__ K,
+                                                     cx* __restrict__ A, PackParams p) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < p.total; o += stride) {
+        long long r = o;
+        const int kz = (int)(r % p.Nzcp); r /= p.Nzcp;
+        const int kyl = (int)(r % p.nyl); r /= p.nyl;
+        const int f = (int)(r % p.F); r /= p.F;
+        const int xl = (int)(r % p.nxl);
+        const int q = (int)(r / p.nxl);
+        const cx v = q == p.rank
+                         ? K[(long long)(p.x0 + xl) * p.xs + f * p.fs + (long long)kyl * p.Nzcp + kz]
+                         : S[o];
+        A[(((long long)f * (p.nxl + 1) + xl) * p.Ny + (q * p.nyl + kyl)) * p.Nzcp + kz] = v;
+    }
+}
+
+static PackParams make_pack(const hymd_ctx* c, int F) {
+    const Geometry& g = c->g;
+    PackParams p;
+    p.P = g.P; p.rank = g.rank; p.nxl = g.nxl; p.nyl = g.nyl; p.Ny = g.Ny; p.Nzcp = g.Nzcp;
+    p.F = F; p.x0 = g.x0;
+    p.total = (long long)F * g.nxl * g.Ny * g.Nzcp;
+    const KLayout l = klayout(c, F);
+    p.xs = l.xs; p.fs = l.fs;
+    return p;
+}
+
+static unsigned int stream_grid(long long n) {
+    long long b = (n + 255) / 256;
+    const long long cap = 148LL * 16;
+    return (unsigned int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+static int transpose_forward(hymd_ctx* c, int F, void* k_out, cudaStream_t s) {
+    const PackParams p = make_pack(c, F);
+    if (c->f64) pack_kernel<double2><<<stream_grid(p.total), 256, 0, s>>>(
+        (const double2*)c->wA, (double2*)c->wS, (double2*)k_out, p);
+    else pack_kernel<float2><<<stream_grid(p.total), 256, 0, s>>>(
+        (const float2*)c->wA, (float2*)c->wS, (float2*)k_out, p);
+    HYMD_LAUNCH_CHECK(c);
+    const size_t block = (size_t)p.total / p.P * 2 * c->rsz;
+    // block q of wS -> rank q; block p of the k buffer (x in slab p) <- rank p
+    return comm_alltoall(c, c->wS, k_out, block, s);
+}
+
+static int transpose_inverse(hymd_ctx* c, int F, void* k_in, cudaStream_t s) {
+    const PackParams p = make_pack(c, F);
+    const size_t block = (size_t)p.total / p.P * 2 * c->rsz;
+    HYMD_CHECK(comm_alltoall(c, k_in, c->wS, block, s));
+    if (c->f64) unpack_kernel<double2><<<stream_grid(p.total), 256, 0, s>>>(
+        (const double2*)c->wS, (const double2*)k_in, (double2*)c->wA, p);
+    else unpack_kernel<float2><<<stream_grid(p.total), 256, 0, s>>>(
+        (const float2*)c->wS, (const float2*)k_in, (float2*)c->wA, p);
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
+}
+
+// ---- public transforms ------------------------------------------------------------------------
+int fft_forward(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s) {
+    const Geometry& g = c->g;
+    cufftHandle h;
+    if (!c->slab) {
+        HYMD_CHECK(plan_get(c, PK_3D_R2C, F, &h));
+        return exec_r2c(c, h, real_in, k_out, s);
+    }
+    const size_t csz = 2 * c->rsz;
+    const KLayout l = klayout(c, F);
+    if (g.P == 1) {
+        HYMD_CHECK(plan_get(c, PK_2D_R2C, F, &h));
+        HYMD_CHECK(exec_r2c(c, h, real_in, k_out, s));
+        HYMD_CHECK(plan_get(c, PK_1D_FWD_INV, 1, &h));
+        for (int f = 0; f < F; ++f)
+            HYMD_CHECK(exec_c2c(c, h, (char*)k_out + (size_t)f * l.fs * csz, CUFFT_FORWARD, s));
+        return HYMD_OK;
+    }
+    HYMD_CHECK(ensure_work(c, F));
+    HYMD_CHECK(plan_get(c, PK_2D_R2C, F, &h));
+    HYMD_CHECK(exec_r2c(c, h, real_in, c->wA, s));
+    HYMD_CHECK(transpose_forward(c, F, k_out, s));
+    HYMD_CHECK(plan_get(c, PK_1D_FWD_INV, F, &h));
+    return exec_c2c(c, h, k_out, CUFFT_FORWARD, s);
+}
+
+// Copies [f][Nx][Ny][Nzcp] into the [f][Nx+1][Ny][Nzcp] work layout (single GPU, ghost output).
+static int copy_to_work(hymd_ctx* c, const void* k_in, int F, cudaStream_t s) {
+    const Geometry& g = c->g;
+    const size_t row = (size_t)g.Nx * g.Ny * g.Nzcp * 2 * c->rsz;
+    const size_t pitch = (size_t)(g.Nx + 1) * g.Ny * g.Nzcp * 2 * c->rsz;
+    HYMD_CUDA(cudaMemcpy2DAsync(c->wA, pitch, k_in, row, row, F, cudaMemcpyDeviceToDevice, s));
+    return HYMD_OK;
+}
+
+int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s) {
+    // the x transform has been applied; k_in is in the k layout (P > 1) or, for P == 1, already
+    // in the work layout the 2-D plans read
+    const Geometry& g = c->g;
+    cufftHandle h;
+    void* src = k_in;
+    if (g.P > 1) {
+        HYMD_CHECK(ensure_work(c, F));
+        HYMD_CHECK(transpose_inverse(c, F, k_in, s));
+        src = c->wA;
+    }
+    HYMD_CHECK(plan_get(c, ghost ? PK_2D_C2R_GHOST : PK_2D_C2R, F, &h));
+    return exec_c2r(c, h, src, real_out, s);
+}
+
+int fft_inverse(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s) {
+    const Geometry& g = c->g;
+    cufftHandle h;
+    if (!c->slab) {
+        HYMD_CHECK(plan_get(c, ghost ? PK_3D_C2R_GHOST : PK_3D_C2R, F, &h));
+        return exec_c2r(c, h, k_in, real_out, s);
+    }
+    const size_t csz = 2 * c->rsz;
+    const KLayout l = klayout(c, F);
+    if (g.P == 1) {
+        HYMD_CHECK(plan_get(c, PK_1D_FWD_INV, 1, &h));
+        for (int f = 0; f < F; ++f)
+            HYMD_CHECK(exec_c2c(c, h, (char*)k_in + (size_t)f * l.fs * csz, CUFFT_INVERSE, s));
+        if (!ghost) return fft_inverse_xdone(c, k_in, F, real_out, false, s);
+        HYMD_CHECK(ensure_work(c, F));
+        HYMD_CHECK(copy_to_work(c, k_in, F, s));
+        return fft_inverse_xdone(c, c->wA, F, real_out, true, s);
+    }
+    HYMD_CHECK(plan_get(c, PK_1D_FWD_INV, F, &h));
+    HYMD_CHECK(exec_c2c(c, h, k_in, CUFFT_INVERSE, s));
+    return fft_inverse_xdone(c, k_in, F, real_out, ghost, s);
+}
+
+// ---- ghost-plane exchange between neighbouring slabs ------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256) halo_add_kernel(real* __restrict__ fields,
+                                                       const real* __restrict__ halo, int F,
+                                                       long long plane, long long field_stride) {
+    const long long total = plane * F, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long f = i / plane, j = i % plane;
+        fields[f * field_stride + j] += halo[i];
+    }
+}
+
+// paint: plane nxl of every field (the ghost plane) is added into plane 0 of the next slab
+// (the Layout.exchange ghost copies of pm.paint, field.py:574).
+int halo_reduce(hymd_ctx* c, void* fields, int F, cudaStream_t s) {
+    const Geometry& g = c->g;
+    if (g.P == 1) return HYMD_OK;
+    PhaseScope ps(c, HYMD_PHASE_HALO, s);
+    const long long plane = (long long)g.Ny * g.Nz;
+    HYMD_CHECK(grow(&c->halo, &c->halo_bytes, (size_t)F * plane * c->rsz));
+    void* sp[HYMD_MAX_TYPES];
+    void* rp[HYMD_MAX_TYPES];
+    for (int f = 0; f < F; ++f) {
+        sp[f] = (char*)fields + ((size_t)f * g.real_elems + (size_t)g.nxl * plane) * c->rsz;
+        rp[f] = (char*)c->halo + (size_t)f * plane * c->rsz;
+    }
+    HYMD_CHECK(comm_ring(c, +1, sp, rp, F, (size_t)plane * c->rsz, s));
+    if (c->f64) halo_add_kernel<double><<<stream_grid(plane * F), 256, 0, s>>>(
+        (double*)fields, (const double*)c->halo, F, plane, g.real_elems);
+    else halo_add_kernel<float><<<stream_grid(plane * F), 256, 0, s>>>(
+        (float*)fields, (const float*)c->halo, F, plane, g.real_elems);
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
+}
+
+// readout: plane nxl of every ghost-padded mesh <- plane 0 (with its y/z ghosts) of the next slab
+int halo_fetch(hymd_ctx* c, void* meshes, int F, cudaStream_t s) {
+    const Geometry& g = c->g;
+    if (g.P == 1) return HYMD_OK;
+    const size_t plane = (size_t)(g.Ny + 1) * g.Nzp * c->rsz;
+    void* sp[3 * HYMD_MAX_TYPES];
+    void* rp[3 * HYMD_MAX_TYPES];
+    for (int f = 0; f < F; ++f) {
+        sp[f] = (char*)meshes + (size_t)f * g.ghost_elems * c->rsz;
+        rp[f] = (char*)sp[f] + (size_t)g.nxl * plane;
+    }
+    return comm_ring(c, -1, sp, rp, F, plane, s);
+}
+
+}  // namespace hymd

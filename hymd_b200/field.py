@@ -182,7 +182,19 @@ def domain_decomposition(positions, pm, *args, molecules=None, bonds=None, topol
             args = (*args, molecules)
     if pm.world_size == 1:
         return (positions, *args)
-    return pm.migrate(positions, *args, molecules=molecules)
+    route = None
+    if molecules is not None:
+        # every atom follows the first atom of its molecule (field.py:1156-1163)
+        mol = torch.as_tensor(np.asarray(molecules)) if not isinstance(molecules, torch.Tensor) \
+            else molecules
+        mol = mol.to(pm.device).long().reshape(-1)
+        pos = pm.as_device(positions)
+        n = mol.shape[0]
+        uniq, inv = torch.unique(mol, return_inverse=True)
+        first = torch.full((uniq.shape[0],), n, dtype=torch.long, device=pm.device)
+        first.scatter_reduce_(0, inv, torch.arange(n, device=pm.device), reduce="amin")
+        route = pos[first[inv]]
+    return pm.migrate(positions, *args, routing_positions=route)
 
 
 def _allreduce(t):

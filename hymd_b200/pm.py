@@ -374,8 +374,41 @@ class ParticleMesh:
         v = s.item()
         return v
 
-    def migrate(self, *arrays):
-        raise _lib.HymdError("multi-GPU particle migration is not available in this build")
+    def migrate(self, positions, *arrays, routing_positions=None):
+        """Re-home per-particle arrays on the rank owning their slab (``Layout.exchange`` of
+        ``domain_decomposition``, ``field.py:1165-1178``).  All arrays have one row per local
+        particle and are permuted identically; ``routing_positions`` (default: ``positions``)
+        decides the destination.  Returns new arrays (torch CUDA tensors; numpy in -> numpy out)."""
+        arrays = (positions,) + tuple(arrays)
+        route = positions if routing_positions is None else routing_positions
+        route_d = self.as_device(route)
+        n = route_d.shape[0]
+        n_new = ctypes.c_int64(0)
+        _lib.check(self.lib.hymd_migrate_plan(self._ctx, ctypes.c_void_p(route_d.data_ptr()), n,
+                                              ctypes.byref(n_new), self.stream))
+        out = []
+        for a in arrays:
+            was_numpy = not isinstance(a, torch.Tensor)
+            t = torch.as_tensor(np.ascontiguousarray(a)) if was_numpy else a
+            t = t.to(self.device).contiguous()
+            if t.shape[0] != n:
+                raise ValueError(f"array with {t.shape[0]} rows in a migration of {n} particles")
+            if t.dtype == torch.bool:
+                t = t.to(torch.uint8)
+            row_bytes = t.element_size() * int(np.prod(t.shape[1:], dtype=np.int64))
+            o = torch.empty((n_new.value,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+            _lib.check(self.lib.hymd_migrate_apply(self._ctx, ctypes.c_void_p(t.data_ptr()),
+                                                   ctypes.c_void_p(o.data_ptr()), row_bytes,
+                                                   self.stream))
+            if isinstance(a, torch.Tensor) and a.dtype == torch.bool:
+                o = o.to(torch.bool)
+            if was_numpy:
+                o = o.cpu().numpy()
+            elif a.device != self.device:
+                o = o.to(a.device)
+            out.append(o)
+        self._sort_key = None
+        return tuple(out)
 
 
 def _has_density_params(config):

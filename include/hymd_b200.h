@@ -175,12 +175,19 @@ typedef enum {
 int hymd_ctx_set_timing(hymd_ctx* ctx, int enable);
 int hymd_ctx_get_timings(hymd_ctx* ctx, double* ms, int64_t* calls);
 
-/* domain_decomposition / layout.exchange (field.py:1115-1178): GPU-side particle migration
- * between slabs.  Packs particles whose wrapped x lies outside this slab, exchanges them with
- * NCCL, and compacts.  d_arrays[i] is an (capacity, width[i]) array of 4- or 8-byte elements
- * (elem_size[i]); array 0 must be the positions.  n_inout: local count in, new count out. */
-int hymd_migrate(hymd_ctx* ctx, void** d_arrays, const int32_t* width, const int32_t* elem_size,
-                 int n_arrays, int64_t capacity, int64_t* n_inout, void* stream);
+/* domain_decomposition / layout.exchange (field.py:1115-1178, main.py:1171-1201): GPU-side
+ * particle migration between slabs, in two phases so the caller can size its output arrays.
+ *
+ * hymd_migrate_plan: d_pos is the (n,3) array of ROUTING positions in the context dtype (the
+ * particle positions, or for molecules the position of each molecule's first atom,
+ * field.py:1156-1163).  Decides the destination slab of every row, exchanges the counts and
+ * returns the new local row count in *n_new.  Synchronizes the stream.
+ * hymd_migrate_apply: moves one per-particle array of row_bytes bytes per row: d_in has n rows,
+ * d_out (distinct from d_in) receives n_new rows: first the rows that stay, in their original
+ * relative order, then the arrivals from rank 0, 1, ...  Call once per array of the plan. */
+int hymd_migrate_plan(hymd_ctx* ctx, const void* d_pos, int64_t n, int64_t* n_new, void* stream);
+int hymd_migrate_apply(hymd_ctx* ctx, const void* d_in, void* d_out, int32_t row_bytes,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,63 @@
+"""Slab-sharded cycle: the same parity gates as tests/test_gpu_parity.py, through the slab
+pipeline (2-D cuFFT per plane + pack/all-to-all + x transform, halo reduce/fetch).
+
+* one GPU, HYMD_B200_FORCE_SLAB=1: the slab pipeline without the exchange
+* two GPUs (skipped when the box has one): torchrun, NCCL over NVLink"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+WORKER = os.path.join(ROOT, "tests", "mgpu_worker.py")
+
+
+def _run(nproc, extra, env_extra=None, timeout=600):
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    if nproc == 1:
+        cmd = [sys.executable, WORKER] + extra
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1", "--master-port", "29571",
+               WORKER] + extra
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "OK" in r.stdout
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+@pytest.mark.parametrize("mesh", [[32, 24, 40], [9, 12, 10]])
+def test_slab_pipeline_single_gpu(dtype, mesh):
+    _run(1, ["--dtype", dtype, "--pme", "--mesh"] + [str(m) for m in mesh] + ["--particles", "6000"],
+         {"HYMD_B200_FORCE_SLAB": "1"})
+
+
+def _need(n):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_two_slabs_match_oracle(dtype):
+    _need(2)
+    _run(2, ["--dtype", dtype, "--pme"])
+
+
+def test_two_slabs_odd_planes():
+    _need(2)
+    _run(2, ["--dtype", "f64", "--mesh", "18", "12", "10", "--particles", "3000"])
+
+
+def test_four_slabs_match_oracle():
+    _need(4)
+    _run(4, ["--dtype", "f64", "--pme", "--mesh", "32", "24", "40"])
+
+
+def test_migration_rehomes_particles():
+    _need(2)
+    _run(2, ["--dtype", "f64", "--pme", "--migrate"])

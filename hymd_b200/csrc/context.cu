@@ -67,7 +67,14 @@ static int build_tables(hymd_ctx* c) {
     for (int a = 0; a < 3; ++a)
         for (int i = 0; i < len[a]; ++i) tab.push_back(k[a][i]);
     HYMD_CHECK(dev_alloc(&c->tab, tab.size() * c->rsz));
-    return upload_real(c, c->tab, tab);
+    HYMD_CHECK(upload_real(c, c->tab, tab));
+    std::vector<double> tw(2 * (size_t)g.Nx);
+    for (int j = 0; j < g.Nx; ++j) {
+        tw[2 * j] = cos(2.0 * M_PI * j / g.Nx);
+        tw[2 * j + 1] = -sin(2.0 * M_PI * j / g.Nx);
+    }
+    HYMD_CHECK(dev_alloc(&c->xtw, tw.size() * c->rsz));
+    return upload_real(c, c->xtw, tw);
 }
 
 static int build_interaction(hymd_ctx* c) {
@@ -220,7 +227,9 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     }
     // slab pipeline: always with several GPUs; on one GPU only when asked for (testing)
     const char* force_slab = getenv("HYMD_B200_FORCE_SLAB");
-    c->slab = P > 1 || (force_slab && force_slab[0] == '1');
+    const char* no_fused = getenv("HYMD_B200_NO_FUSED");
+    c->fused = xline_supported(c) && !(no_fused && no_fused[0] == '1');
+    c->slab = P > 1 || c->fused || (force_slab && force_slab[0] == '1');
     if (P > 1 && (st = comm_create(c, nccl_id))) return fail(st);
     if ((st = readout_setup(c))) return fail(st);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(HYMD_ERR_CUDA);
@@ -235,7 +244,7 @@ int hymd_ctx_destroy(hymd_ctx* c) {
     migrate_destroy(c);
     comm_destroy(c);
     void* bufs[] = {c->rec, c->key, c->rank_in_cell, c->cell_count, c->cell_start, c->q_sorted,
-                    c->scalars, c->scan_tmp, c->tab, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
+                    c->scalars, c->scan_tmp, c->tab, c->xtw, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
                     c->phi_hat, c->f_hat, c->gmesh, c->v_hat, c->phif_hat, c->tmp_hat, c->v_ext,
                     c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->psi_hat, c->emesh, c->psi, c->fft_work,
                     c->wA, c->wS, c->halo};
@@ -341,6 +350,24 @@ int hymd_paint(hymd_ctx* c, void* stream) {
     return HYMD_OK;
 }
 
+// Force spectra buffer the k-space stage writes: with the fused kernel on one GPU that is the
+// work layout of the batched 2-D c2r, otherwise f_hat in the k layout.
+static void* force_spectra(hymd_ctx* c) { return (c->fused && c->g.P == 1) ? c->wA : c->f_hat; }
+
+static int run_kspace(hymd_ctx* c, bool want_v, bool want_phif, cudaStream_t s) {
+    if (!c->fused) return kspace_forces(c, want_v, want_phif, s);
+    HYMD_CHECK(ensure_work(c, 3 * c->U > c->T ? 3 * c->U : c->T));
+    return xline_forces(c, c->phi_hat, force_spectra(c), want_v ? c->v_hat : nullptr,
+                        want_phif ? c->phif_hat : nullptr, s);
+}
+
+static int run_kspace_pme(hymd_ctx* c, bool want_psi, cudaStream_t s) {
+    if (!c->fused) return kspace_pme(c, want_psi, s);
+    HYMD_CHECK(ensure_work(c, 3 * c->U > c->T ? 3 * c->U : c->T));
+    return xline_pme(c, c->phiq_hat, (c->g.P == 1) ? c->wA : c->e_hat,
+                     want_psi ? c->psi_hat : nullptr, want_psi ? c->phiqf_hat : nullptr, s);
+}
+
 static int materialize_impl(hymd_ctx* c, bool want_phi, bool want_v, cudaStream_t s) {
     const Geometry& g = c->g;
     const size_t kb = (size_t)g.k_elems * 2 * c->rsz, rb = (size_t)g.real_elems * c->rsz;
@@ -363,9 +390,11 @@ int hymd_field_cycle(hymd_ctx* c, int compute_potential, void* stream) {
     const Geometry& g = c->g;
     const size_t kb = (size_t)g.k_elems * 2 * c->rsz;
     if (c->phi_is_filtered) { set_error("hymd_field_cycle needs a fresh hymd_paint"); return HYMD_ERR_STATE; }
+    if (c->fused) HYMD_CHECK(ensure_work(c, 3 * c->U > c->T ? 3 * c->U : c->T));
     {
         PhaseScope ps(c, HYMD_PHASE_FFT_FWD, s);
-        HYMD_CHECK(fft_forward(c, c->phi, c->T, c->phi_hat, s));
+        if (c->fused) HYMD_CHECK(fft_forward_yz(c, c->phi, c->T, c->phi_hat, s));
+        else HYMD_CHECK(fft_forward(c, c->phi, c->T, c->phi_hat, s));
     }
     c->have_phi_hat = true;
     const bool cp = compute_potential != 0;
@@ -375,11 +404,12 @@ int hymd_field_cycle(hymd_ctx* c, int compute_potential, void* stream) {
     }
     {
         PhaseScope ps(c, HYMD_PHASE_KSPACE, s);
-        HYMD_CHECK(kspace_forces(c, cp, cp, s));
+        HYMD_CHECK(run_kspace(c, cp, cp, s));
     }
     {
         PhaseScope ps(c, HYMD_PHASE_FFT_INV, s);
-        HYMD_CHECK(fft_inverse(c, c->f_hat, 3 * c->U, c->gmesh, true, s));
+        if (c->fused) HYMD_CHECK(fft_inverse_xdone(c, force_spectra(c), 3 * c->U, c->gmesh, true, s));
+        else HYMD_CHECK(fft_inverse(c, c->f_hat, 3 * c->U, c->gmesh, true, s));
     }
     {
         PhaseScope ps(c, HYMD_PHASE_GHOST, s);
@@ -408,7 +438,7 @@ int hymd_materialize(hymd_ctx* c, int want_phi, int want_phi_fourier, int want_v
         HYMD_CHECK(dev_alloc(&c->phiqf_hat, kb));
         HYMD_CHECK(dev_alloc(&c->psi_hat, kb));
         HYMD_CHECK(dev_alloc(&c->psi, (size_t)c->g.real_elems * c->rsz));
-        HYMD_CHECK(kspace_pme(c, true, s));   // e_hat is scratch between cycles
+        HYMD_CHECK(run_kspace_pme(c, true, s));   // e_hat / the work area are scratch between cycles
         HYMD_CHECK(fft_inverse(c, c->psi_hat, 1, c->psi, false, s));
         c->have_psi = true;
     }
@@ -420,7 +450,7 @@ int hymd_materialize(hymd_ctx* c, int want_phi, int want_phi_fourier, int want_v
     if (need_pf || need_v) {
         HYMD_CHECK(dev_alloc(&c->v_hat, c->T * kb));
         HYMD_CHECK(dev_alloc(&c->phif_hat, c->T * kb));
-        HYMD_CHECK(kspace_forces(c, true, true, s));   // f_hat is scratch between cycles
+        HYMD_CHECK(run_kspace(c, true, true, s));   // f_hat / the work area are scratch between cycles
         c->have_phif = true;
     }
     return materialize_impl(c, need_phi, need_v, s);
@@ -454,7 +484,8 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
     }
     {
         PhaseScope ps(c, HYMD_PHASE_PME_FFT, s);
-        HYMD_CHECK(fft_forward(c, c->phi_q, 1, c->phiq_hat, s));
+        if (c->fused) HYMD_CHECK(fft_forward_yz(c, c->phi_q, 1, c->phiq_hat, s));
+        else HYMD_CHECK(fft_forward(c, c->phi_q, 1, c->phiq_hat, s));
     }
     c->have_phiq_hat = true;
     if (want_psi) {
@@ -464,11 +495,13 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
     }
     {
         PhaseScope ps(c, HYMD_PHASE_PME_KSPACE, s);
-        HYMD_CHECK(kspace_pme(c, want_psi != 0, s));
+        HYMD_CHECK(run_kspace_pme(c, want_psi != 0, s));
     }
     {
         PhaseScope ps(c, HYMD_PHASE_PME_FFT, s);
-        HYMD_CHECK(fft_inverse(c, c->e_hat, 3, c->emesh, true, s));
+        if (c->fused)
+            HYMD_CHECK(fft_inverse_xdone(c, (c->g.P == 1) ? c->wA : c->e_hat, 3, c->emesh, true, s));
+        else HYMD_CHECK(fft_inverse(c, c->e_hat, 3, c->emesh, true, s));
         HYMD_CHECK(fill_ghosts(c, c->emesh, 3, s));
         HYMD_CHECK(halo_fetch(c, c->emesh, 3, s));
         if (want_psi) HYMD_CHECK(fft_inverse(c, c->psi_hat, 1, c->psi, false, s));

@@ -140,6 +140,8 @@ struct hymd_ctx {
 
     // k-space tables (real): hx,hy,hz Gaussian factors, kx,ky,kz wave numbers; Au (U x T) / M
     void* tab;            // packed: hx[Nx] hy[Ny] hz[Nzc] kx[Nx] ky[Ny] kz[Nzc]
+    void* xtw;            // Nx complex twiddles exp(-2 pi i j / Nx) for the fused x-line kernel
+    bool fused;           // fused x-line kernel in use (power-of-two Nx)
     void* Au;             // U*T reals, already divided by M
     void* cu;             // U offsets (added at k = 0 for v_ext)
     int* d_urow;          // T ints
@@ -238,12 +240,17 @@ int kspace_pme(hymd_ctx* c, bool want_psi, cudaStream_t s);
 // ghost-padded force-mesh layout) and the k layout klayout(c, F)
 KLayout klayout(const hymd_ctx* c, int F);
 int fft_forward(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s);
+int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s);
 int fft_inverse(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s);
 int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s);
 int ensure_work(hymd_ctx* c, int F);
 void destroy_plans(hymd_ctx* c);
 int halo_reduce(hymd_ctx* c, void* fields, int F, cudaStream_t s);
 int halo_fetch(hymd_ctx* c, void* ghost_meshes, int F, cudaStream_t s);
+// xline.cu
+bool xline_supported(const hymd_ctx* c);
+int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s);
+int xline_pme(hymd_ctx* c, const void* in, void* fout, void* psi_out, void* rhof_out, cudaStream_t s);
 // migrate.cu
 int migrate_plan(hymd_ctx* c, const void* d_pos, int64_t n, int64_t* n_new, cudaStream_t s);
 int migrate_apply(hymd_ctx* c, const void* d_in, void* d_out, int row_bytes, cudaStream_t s);

@@ -257,6 +257,17 @@ int fft_forward(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s) 
     return exec_c2c(c, h, k_out, CUFFT_FORWARD, s);
 }
 
+// Forward transform over y and z only (the fused x-line kernel does the rest): k_out receives
+// the k layout with x still in real space.
+int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s) {
+    cufftHandle h;
+    HYMD_CHECK(plan_get(c, PK_2D_R2C, F, &h));
+    if (c->g.P == 1) return exec_r2c(c, h, real_in, k_out, s);
+    HYMD_CHECK(ensure_work(c, F));
+    HYMD_CHECK(exec_r2c(c, h, real_in, c->wA, s));
+    return transpose_forward(c, F, k_out, s);
+}
+
 // Copies [f][Nx][Ny][Nzcp] into the [f][Nx+1][Ny][Nzcp] work layout (single GPU, ghost output).
 static int copy_to_work(hymd_ctx* c, const void* k_in, int F, cudaStream_t s) {
     const Geometry& g = c->g;

@@ -1,0 +1,374 @@
+// Fused x-line kernel: the third axis of the forward FFT, ALL the k-space arithmetic and the
+// first axis of the inverse FFT in one pass over the spectra.
+//
+// After the batched 2-D (y,z) transforms every rank holds complete x-lines of all T density
+// spectra for its (ky,kz) columns.  One CTA takes CH neighbouring columns, loads the T x Nx x CH
+// tile into shared memory, runs the Nx-point FFTs there, forms for every distinct potential row
+//     V^_u = H^2 sum_t A[u][t] phi^_t            (field.py:577-585, hamiltonian.py:402-412)
+// applies -i k_d (field.py:607-612; Nyquist rule of SURVEY.md section 7), transforms back along x
+// and writes the 3U force spectra, ready for the batched 2-D c2r.  This replaces three full
+// passes over HBM (x-FFT, k-space kernel, x-IFFT: T*3 + 3U*3 spectrum transfers) by one
+// (T reads + 3U writes), and because k_y, k_z are constant along an x-line only two inverse
+// transforms per row are needed (V and k_x V) instead of three.
+//
+// FFT: Nx = R1*R2, four-step inside the CTA, radix-R butterflies in registers.  The forward
+// transform leaves frequency k1 + R1*k2 at position k1*R2 + k2 (no reordering pass); the
+// inverse consumes exactly that order and ends in natural x order.
+//
+// PME variant (field.py:369-396): T = U = 1, G = 4 pi c_e H / k^2 (k = 0 divisor -> 1).
+#include "ctx.cuh"
+
+namespace hymd {
+
+template <typename real> struct Cx { real x, y; };
+
+template <typename real>
+__device__ __forceinline__ Cx<real> cmul(Cx<real> a, Cx<real> b) {
+    return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+
+// cos / sin of 2 pi j / 32 (j folded to a compile-time constant by unrolling)
+template <typename real>
+__device__ __forceinline__ real cos32(int j) {
+    constexpr double c[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613,
+                             0.83146961230254523708, 0.70710678118654752440,
+                             0.55557023301960222474, 0.38268343236508977173,
+                             0.19509032201612826785, 0.0};
+    j &= 31;
+    if (j > 16) j = 32 - j;
+    return j <= 8 ? (real)c[j] : (real)(-c[16 - j]);
+}
+template <typename real>
+__device__ __forceinline__ real sin32(int j) { return cos32<real>(j - 8); }
+
+// In-register radix-2 DIT DFT of size R (power of two <= 32), sign = -1 forward, +1 inverse.
+template <typename real, int R, int SIGN>
+__device__ __forceinline__ void dft_reg(Cx<real> (&v)[R]) {
+    // bit reversal
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        int r = 0;
+#pragma unroll
+        for (int b = 1, t = i; b < R; b <<= 1, t >>= 1) r = (r << 1) | (t & 1);
+        if (r > i) { Cx<real> tmp = v[i]; v[i] = v[r]; v[r] = tmp; }
+    }
+#pragma unroll
+    for (int m = 2; m <= R; m <<= 1) {
+#pragma unroll
+        for (int k = 0; k < R; k += m) {
+#pragma unroll
+            for (int j = 0; j < m / 2; ++j) {
+                const int tj = j * (32 / m);
+                const Cx<real> w = {cos32<real>(tj), (real)SIGN * sin32<real>(tj)};
+                const Cx<real> a = v[k + j];
+                const Cx<real> b = (j == 0) ? v[k + j + m / 2] : cmul(w, v[k + j + m / 2]);
+                v[k + j] = {a.x + b.x, a.y + b.y};
+                v[k + j + m / 2] = {a.x - b.x, a.y - b.y};
+            }
+        }
+    }
+}
+
+struct XParams {
+    int Nx, Ny, Nz, nyl, y0, Nzc, Nzcp;
+    int T, U;
+    long long ncols;                 // nyl * Nzcp
+    long long xs_in, fs_in;          // complex strides of the input spectra
+    long long xs_f, fs_f;            // ... of the 3U (or 3) force outputs
+    long long xs_v, fs_v, xs_pf, fs_pf;   // optional k-space outputs (not x-inverted)
+    int pme;
+};
+
+template <int NX> struct Radix;
+template <> struct Radix<16> { static constexpr int R1 = 4, R2 = 4; };
+template <> struct Radix<32> { static constexpr int R1 = 4, R2 = 8; };
+template <> struct Radix<64> { static constexpr int R1 = 8, R2 = 8; };
+template <> struct Radix<128> { static constexpr int R1 = 8, R2 = 16; };
+template <> struct Radix<256> { static constexpr int R1 = 16, R2 = 16; };
+template <> struct Radix<512> { static constexpr int R1 = 16, R2 = 32; };
+template <> struct Radix<1024> { static constexpr int R1 = 32, R2 = 32; };
+
+// shared-memory position of element (pos, c): rows of CH columns, one extra row of padding per
+// R2 positions so that the contiguous-radix step spreads over all banks
+template <int NX, int CH>
+__device__ __forceinline__ int spos(int pos, int c) {
+    return (pos + pos / Radix<NX>::R2) * CH + c;
+}
+template <int NX, int CH>
+constexpr int field_elems() { return (NX + NX / Radix<NX>::R2) * CH; }
+
+// forward: strided radix-R1 over n1 (+ twiddle), then contiguous radix-R2 over n2.
+template <typename real, int NX, int CH>
+__device__ __forceinline__ void fft_fwd_step1(Cx<real>* buf, const Cx<real>* __restrict__ tw, int task) {
+    constexpr int R1 = Radix<NX>::R1, R2 = Radix<NX>::R2;
+    const int c = task % CH, n2 = task / CH;
+    Cx<real> v[R1];
+#pragma unroll
+    for (int n1 = 0; n1 < R1; ++n1) v[n1] = buf[spos<NX, CH>(n1 * R2 + n2, c)];
+    dft_reg<real, R1, -1>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+        const Cx<real> w = tw[(n2 * k1) & (NX - 1)];   // exp(-2 pi i n2 k1 / NX)
+        buf[spos<NX, CH>(k1 * R2 + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+    }
+}
+template <typename real, int NX, int CH>
+__device__ __forceinline__ void fft_fwd_step2(Cx<real>* buf, int task) {
+    constexpr int R2 = Radix<NX>::R2;
+    const int c = task % CH, k1 = task / CH;
+    Cx<real> v[R2];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) v[n2] = buf[spos<NX, CH>(k1 * R2 + n2, c)];
+    dft_reg<real, R2, -1>(v);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) buf[spos<NX, CH>(k1 * R2 + k2, c)] = v[k2];
+}
+// inverse: contiguous radix-R2 over k2 (+ conjugate twiddle), then strided radix-R1 over k1.
+template <typename real, int NX, int CH>
+__device__ __forceinline__ void fft_inv_stepA(Cx<real>* buf, const Cx<real>* __restrict__ tw, int task) {
+    constexpr int R2 = Radix<NX>::R2;
+    const int c = task % CH, k1 = task / CH;
+    Cx<real> v[R2];
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) v[k2] = buf[spos<NX, CH>(k1 * R2 + k2, c)];
+    dft_reg<real, R2, +1>(v);
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) {
+        Cx<real> w = tw[(n2 * k1) & (NX - 1)];
+        w.y = -w.y;
+        buf[spos<NX, CH>(k1 * R2 + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+    }
+}
+template <typename real, int NX, int CH>
+__device__ __forceinline__ void fft_inv_stepB(Cx<real>* buf, int task) {
+    constexpr int R1 = Radix<NX>::R1, R2 = Radix<NX>::R2;
+    const int c = task % CH, n2 = task / CH;
+    Cx<real> v[R1];
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) v[k1] = buf[spos<NX, CH>(k1 * R2 + n2, c)];
+    dft_reg<real, R1, +1>(v);
+#pragma unroll
+    for (int n1 = 0; n1 < R1; ++n1) buf[spos<NX, CH>(n1 * R2 + n2, c)] = v[n1];
+}
+
+template <typename real, int NX, int CH>
+__global__ void __launch_bounds__(256) xline_kernel(
+    const Cx<real>* __restrict__ in, Cx<real>* __restrict__ fout, Cx<real>* __restrict__ vout,
+    Cx<real>* __restrict__ pfout, const real* __restrict__ tab, const Cx<real>* __restrict__ twg,
+    const real* __restrict__ Au, const real* __restrict__ cu, real coef, real inv_m, XParams p) {
+    constexpr int R1 = Radix<NX>::R1, R2 = Radix<NX>::R2;
+    constexpr int FE = field_elems<NX, CH>();
+    constexpr int NT = 256;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx<real>* tw = reinterpret_cast<Cx<real>*>(smem_raw);      // NX twiddles
+    Cx<real>* wV = tw + NX;                                     // FE: V^ (then its x-inverse)
+    Cx<real>* wK = wV + FE;                                     // FE: k_x V^
+    Cx<real>* data = wK + FE;                                   // T x FE input spectra
+    __shared__ real s_hk[2][CH][4];   // per column: [0] = {h_yz, ky_eff(unused), ...}
+
+    const real* hx = tab; const real* hy = hx + p.Nx; const real* hz = hy + p.Ny;
+    const real* kxt = hz + p.Nzc; const real* kyt = kxt + p.Nx; const real* kzt = kyt + p.Ny;
+
+    const int tid = threadIdx.x;
+    const long long col0 = (long long)blockIdx.x * CH;
+
+    for (int i = tid; i < NX; i += NT) tw[i] = twg[i];
+    // per-column constants
+    if (tid < CH) {
+        long long col = col0 + tid;
+        if (col >= p.ncols) col = p.ncols - 1;
+        const int iz = (int)(col % p.Nzcp), iyl = (int)(col / p.Nzcp);
+        const int iy = iyl + p.y0;
+        const bool zvalid = iz < p.Nzc;
+        const int zc = zvalid ? iz : 0;
+        const bool z_nyq = (p.Nz % 2 == 0) && zc == p.Nz / 2;
+        const bool self_conj = zc == 0 || z_nyq;
+        const bool y_nyq = (p.Ny % 2 == 0) && iy == p.Ny / 2;
+        s_hk[0][tid][0] = zvalid ? hy[iy] * hz[zc] : (real)0;           // h_y h_z (0 on the pad column)
+        s_hk[0][tid][1] = (y_nyq && self_conj) ? (real)0 : kyt[iy];     // effective k_y
+        s_hk[0][tid][2] = z_nyq ? (real)0 : kzt[zc];                    // effective k_z
+        s_hk[0][tid][3] = self_conj ? (real)1 : (real)0;
+        s_hk[1][tid][0] = kyt[iy];                                      // raw k_y, k_z (PME k^2)
+        s_hk[1][tid][1] = kzt[zc];
+        s_hk[1][tid][2] = (zvalid && iy == 0 && zc == 0) ? (real)1 : (real)0;   // column with k = 0
+        s_hk[1][tid][3] = 0;
+    }
+
+    // ---- load T x NX x CH ----
+    const bool full = col0 + CH <= p.ncols;
+    for (int e = tid; e < p.T * NX * CH; e += NT) {
+        const int c = e % CH, x = (e / CH) % NX, t = e / (CH * NX);
+        Cx<real> v = {0, 0};
+        if (full || col0 + c < p.ncols) v = in[t * p.fs_in + x * p.xs_in + col0 + c];
+        data[t * FE + spos<NX, CH>(x, c)] = v;
+    }
+    __syncthreads();
+    // ---- forward FFT along x, all fields ----
+    for (int task = tid; task < p.T * R2 * CH; task += NT)
+        fft_fwd_step1<real, NX, CH>(data + (task / (R2 * CH)) * FE, tw, task % (R2 * CH));
+    __syncthreads();
+    for (int task = tid; task < p.T * R1 * CH; task += NT)
+        fft_fwd_step2<real, NX, CH>(data + (task / (R1 * CH)) * FE, task % (R1 * CH));
+    __syncthreads();
+
+    // optional: filtered density spectra H phi^ / M in natural k order (phi_fourier, field.py:577)
+    if (pfout != nullptr) {
+        for (int e = tid; e < p.T * NX * CH; e += NT) {
+            const int c = e % CH, pos = (e / CH) % NX, t = e / (CH * NX);
+            const int kx = pos / R2 + R1 * (pos % R2);
+            if (full || col0 + c < p.ncols) {
+                const real s = hx[kx] * s_hk[0][c][0] * inv_m;
+                const Cx<real> v = data[t * FE + spos<NX, CH>(pos, c)];
+                pfout[t * p.fs_pf + kx * p.xs_pf + col0 + c] = {v.x * s, v.y * s};
+            }
+        }
+    }
+
+    for (int u = 0; u < p.U; ++u) {
+        // ---- potential and k_x * potential in frequency space ----
+        for (int e = tid; e < NX * CH; e += NT) {
+            const int c = e % CH, pos = e / CH;
+            const int kx = pos / R2 + R1 * (pos % R2);     // frequency index held at this position
+            real ar = 0, ai = 0;
+            for (int t = 0; t < p.T; ++t) {
+                const real a = Au[u * p.T + t];
+                const Cx<real> v = data[t * FE + spos<NX, CH>(pos, c)];
+                ar += a * v.x; ai += a * v.y;
+            }
+            const real h = hx[kx] * s_hk[0][c][0];
+            real g;
+            if (p.pme) {
+                const real kxr = kxt[kx], kyr = s_hk[1][c][0], kzr = s_hk[1][c][1];
+                real k2 = kxr * kxr + kyr * kyr + kzr * kzr;
+                if (kx == 0 && s_hk[1][c][2] != (real)0) k2 = (real)1;   // normp(p=2, zeromode=1)
+                g = coef * h / k2;
+            } else {
+                g = h * h;
+            }
+            ar *= g; ai *= g;
+            const bool x_nyq = (NX % 2 == 0) && kx == NX / 2;
+            const real kxe = (x_nyq && s_hk[0][c][3] != (real)0) ? (real)0 : kxt[kx];
+            const int sp = spos<NX, CH>(pos, c);
+            wV[sp] = {ar, ai};
+            wK[sp] = {kxe * ar, kxe * ai};
+            if (vout != nullptr && (full || col0 + c < p.ncols)) {
+                real vr = ar;
+                if (!p.pme && kx == 0 && s_hk[1][c][2] != (real)0) vr += cu[u];
+                vout[u * p.fs_v + kx * p.xs_v + col0 + c] = {vr, ai};
+            }
+        }
+        __syncthreads();
+        // ---- inverse FFT along x of V^ and k_x V^ (2 x R1 x CH tasks) ----
+        for (int task = tid; task < 2 * R1 * CH; task += NT)
+            fft_inv_stepA<real, NX, CH>(task < R1 * CH ? wV : wK, tw, task % (R1 * CH));
+        __syncthreads();
+        for (int task = tid; task < 2 * R2 * CH; task += NT)
+            fft_inv_stepB<real, NX, CH>(task < R2 * CH ? wV : wK, task % (R2 * CH));
+        __syncthreads();
+        // ---- F_d = -i k_d V:  -i (a + i b) = b - i a ----
+        Cx<real>* f0 = fout + (long long)(3 * u) * p.fs_f;
+        for (int e = tid; e < NX * CH; e += NT) {
+            const int c = e % CH, x = e / CH;
+            if (!(full || col0 + c < p.ncols)) continue;
+            const int sp = spos<NX, CH>(x, c);
+            const Cx<real> v = wV[sp], k = wK[sp];
+            const real ky = s_hk[0][c][1], kz = s_hk[0][c][2];
+            const long long o = x * p.xs_f + col0 + c;
+            f0[o] = {k.y, -k.x};
+            f0[p.fs_f + o] = {ky * v.y, -ky * v.x};
+            f0[2 * p.fs_f + o] = {kz * v.y, -kz * v.x};
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+static int xline_ch(int n, bool f64) { return n <= 256 ? 8 : (n == 512 ? 4 : 2); }
+
+static size_t xline_smem(int n, int T, bool f64) {
+    int r2 = 4;
+    switch (n) { case 32: case 64: r2 = 8; break; case 128: case 256: r2 = 16; break;
+                 case 512: case 1024: r2 = 32; break; default: break; }
+    const size_t fe = (size_t)(n + n / r2) * xline_ch(n, f64);
+    return (f64 ? 16 : 8) * ((size_t)n + (size_t)(2 + T) * fe);
+}
+
+bool xline_supported(const hymd_ctx* c) {
+    const int n = c->g.Nx;
+    if (n < 16 || n > 1024 || (n & (n - 1))) return false;
+    if (c->f64 && n > 256) return false;     // radix-32 butterflies in fp64 would spill
+    return xline_smem(n, c->T, c->f64) <= 220 * 1024;
+}
+
+template <typename real, int NX, int CH>
+static int launch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vout, void* pfout,
+                    int T, int U, cudaStream_t s) {
+    const Geometry& g = c->g;
+    XParams p;
+    p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nyl = g.nyl; p.y0 = g.y0; p.Nzc = g.Nzc; p.Nzcp = g.Nzcp;
+    p.T = T; p.U = U; p.pme = pme ? 1 : 0;
+    p.ncols = (long long)g.nyl * g.Nzcp;
+    const KLayout lin = klayout(c, T), lv = klayout(c, U);
+    p.xs_in = lin.xs; p.fs_in = lin.fs;
+    p.xs_pf = lin.xs; p.fs_pf = lin.fs;
+    p.xs_v = lv.xs; p.fs_v = lv.fs;
+    if (g.P == 1) {   // straight into the work layout of the batched 2-D c2r: [f][Nx+1][Ny][Nzcp]
+        p.xs_f = (long long)g.Ny * g.Nzcp;
+        p.fs_f = (long long)(g.Nx + 1) * p.xs_f;
+    } else {
+        const KLayout lf = klayout(c, 3 * U);
+        p.xs_f = lf.xs; p.fs_f = lf.fs;
+    }
+    const size_t smem = sizeof(Cx<real>) * ((size_t)NX + (size_t)(2 + T) * field_elems<NX, CH>());
+    if (smem > 227 * 1024) {
+        set_error("xline: %d types need %zu B of shared memory", T, smem);
+        return HYMD_ERR_INVALID;
+    }
+    auto kern = xline_kernel<real, NX, CH>;
+    HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double m = (double)g.Nx * g.Ny * g.Nz;
+    const real coef = (real)(4.0 * 3.14159265358979323846 * c->cfg.elec_conversion / m);
+    const unsigned int blocks = (unsigned int)((p.ncols + CH - 1) / CH);
+    // PME: A = [1/M] lives right after the U x T matrix (build_interaction); its row "0" is used
+    const real* Au = pme ? (const real*)c->Au + (size_t)c->U * c->T : (const real*)c->Au;
+    kern<<<blocks, 256, smem, s>>>((const Cx<real>*)in, (Cx<real>*)fout, (Cx<real>*)vout,
+                                   (Cx<real>*)pfout, (const real*)c->tab,
+                                   (const Cx<real>*)c->xtw, Au, (const real*)c->cu,
+                                   pme ? (real)(coef * m) : (real)0, (real)(1.0 / m), p);
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
+}
+
+template <typename real>
+static int dispatch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vout, void* pfout,
+                      int T, int U, cudaStream_t s) {
+    // columns per CTA: 8 complex = 64 B (fp32) / 128 B (fp64) contiguous per x row
+    switch (c->g.Nx) {
+        case 16: return launch_x<real, 16, 8>(c, pme, in, fout, vout, pfout, T, U, s);
+        case 32: return launch_x<real, 32, 8>(c, pme, in, fout, vout, pfout, T, U, s);
+        case 64: return launch_x<real, 64, 8>(c, pme, in, fout, vout, pfout, T, U, s);
+        case 128: return launch_x<real, 128, 8>(c, pme, in, fout, vout, pfout, T, U, s);
+        case 256: return launch_x<real, 256, 8>(c, pme, in, fout, vout, pfout, T, U, s);
+        default: break;
+    }
+    if (sizeof(real) == 4) {
+        if (c->g.Nx == 512) return launch_x<float, 512, 4>(c, pme, in, fout, vout, pfout, T, U, s);
+        if (c->g.Nx == 1024) return launch_x<float, 1024, 2>(c, pme, in, fout, vout, pfout, T, U, s);
+    }
+    set_error("xline: unsupported Nx = %d", c->g.Nx);
+    return HYMD_ERR_INVALID;
+}
+
+// in: spectra after the 2-D (y,z) transforms, k layout of T fields.  fout: 3U x-inverted force
+// spectra (P == 1: work layout of the ghost c2r; P > 1: k layout of 3U fields).
+int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s) {
+    return c->f64 ? dispatch_x<double>(c, false, in, fout, vout, pfout, c->T, c->U, s)
+                  : dispatch_x<float>(c, false, in, fout, vout, pfout, c->T, c->U, s);
+}
+
+int xline_pme(hymd_ctx* c, const void* in, void* fout, void* psi_out, void* rhof_out, cudaStream_t s) {
+    return c->f64 ? dispatch_x<double>(c, true, in, fout, psi_out, rhof_out, 1, 1, s)
+                  : dispatch_x<float>(c, true, in, fout, psi_out, rhof_out, 1, 1, s);
+}
+
+}  // namespace hymd

@@ -16,6 +16,8 @@
 // inverse consumes exactly that order and ends in natural x order.
 //
 // PME variant (field.py:369-396): T = U = 1, G = 4 pi c_e H / k^2 (k = 0 divisor -> 1).
+#include <type_traits>
+
 #include "ctx.cuh"
 
 namespace hymd {
@@ -27,46 +29,90 @@ __device__ __forceinline__ Cx<real> cmul(Cx<real> a, Cx<real> b) {
     return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }
 
-// cos / sin of 2 pi j / 32 (j folded to a compile-time constant by unrolling)
+// cos(2 pi j / 32); j is a compile-time constant after unrolling, so the switch folds away
 template <typename real>
 __device__ __forceinline__ real cos32(int j) {
-    constexpr double c[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613,
-                             0.83146961230254523708, 0.70710678118654752440,
-                             0.55557023301960222474, 0.38268343236508977173,
-                             0.19509032201612826785, 0.0};
     j &= 31;
     if (j > 16) j = 32 - j;
-    return j <= 8 ? (real)c[j] : (real)(-c[16 - j]);
+    switch (j) {
+        case 0: return (real)1.0;
+        case 1: return (real)0.98078528040323044913;
+        case 2: return (real)0.92387953251128675613;
+        case 3: return (real)0.83146961230254523708;
+        case 4: return (real)0.70710678118654752440;
+        case 5: return (real)0.55557023301960222474;
+        case 6: return (real)0.38268343236508977173;
+        case 7: return (real)0.19509032201612826785;
+        case 8: return (real)0.0;
+        case 9: return (real)-0.19509032201612826785;
+        case 10: return (real)-0.38268343236508977173;
+        case 11: return (real)-0.55557023301960222474;
+        case 12: return (real)-0.70710678118654752440;
+        case 13: return (real)-0.83146961230254523708;
+        case 14: return (real)-0.92387953251128675613;
+        case 15: return (real)-0.98078528040323044913;
+        default: return (real)-1.0;
+    }
 }
 template <typename real>
 __device__ __forceinline__ real sin32(int j) { return cos32<real>(j - 8); }
 
+template <int R> __host__ __device__ constexpr int log2c() { return R <= 1 ? 0 : 1 + log2c<R / 2>(); }
+template <int R> __host__ __device__ constexpr int bitrev(int i) {
+    int r = 0;
+    for (int b = 0; b < log2c<R>(); ++b) r |= ((i >> b) & 1) << (log2c<R>() - 1 - b);
+    return r;
+}
+
+// compile-time unrolled helpers (every register-array index is a constant expression)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
 // In-register radix-2 DIT DFT of size R (power of two <= 32), sign = -1 forward, +1 inverse.
 template <typename real, int R, int SIGN>
 __device__ __forceinline__ void dft_reg(Cx<real> (&v)[R]) {
-    // bit reversal
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-        int r = 0;
-#pragma unroll
-        for (int b = 1, t = i; b < R; b <<= 1, t >>= 1) r = (r << 1) | (t & 1);
-        if (r > i) { Cx<real> tmp = v[i]; v[i] = v[r]; v[r] = tmp; }
-    }
-#pragma unroll
-    for (int m = 2; m <= R; m <<= 1) {
-#pragma unroll
-        for (int k = 0; k < R; k += m) {
-#pragma unroll
-            for (int j = 0; j < m / 2; ++j) {
-                const int tj = j * (32 / m);
+    static_for<0, R>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int r = bitrev<R>(i);
+        if constexpr (r > i) { const Cx<real> tmp = v[i]; v[i] = v[r]; v[r] = tmp; }
+    });
+    static_for<1, log2c<R>() + 1>([&](auto sc) {
+        constexpr int m = 1 << decltype(sc)::value;
+        static_for<0, R / 2>([&](auto bc) {
+            constexpr int bfly = decltype(bc)::value;          // butterfly number 0 .. R/2-1
+            constexpr int k = (bfly / (m / 2)) * m, j = bfly % (m / 2);
+            constexpr int tj = j * (32 / m);
+            const Cx<real> a = v[k + j];
+            Cx<real> b = v[k + j + m / 2];
+            // w = exp(SIGN * 2 pi i tj / 32); quarter and eighth turns need no general multiply
+            if constexpr (tj == 8) {
+                b = {-(real)SIGN * b.y, (real)SIGN * b.x};
+            } else if constexpr (tj == 4) {
+                constexpr real h = (real)0.70710678118654752440;
+                b = {h * (b.x - (real)SIGN * b.y), h * ((real)SIGN * b.x + b.y)};
+            } else if constexpr (tj == 12) {
+                constexpr real h = (real)0.70710678118654752440;
+                b = {-h * (b.x + (real)SIGN * b.y), h * ((real)SIGN * b.x - b.y)};
+            } else if constexpr (j != 0) {
                 const Cx<real> w = {cos32<real>(tj), (real)SIGN * sin32<real>(tj)};
-                const Cx<real> a = v[k + j];
-                const Cx<real> b = (j == 0) ? v[k + j + m / 2] : cmul(w, v[k + j + m / 2]);
-                v[k + j] = {a.x + b.x, a.y + b.y};
-                v[k + j + m / 2] = {a.x - b.x, a.y - b.y};
+                b = cmul(w, b);
             }
-        }
-    }
+            v[k + j] = {a.x + b.x, a.y + b.y};
+            v[k + j + m / 2] = {a.x - b.x, a.y - b.y};
+        });
+    });
+}
+
+__device__ __forceinline__ void store16(Cx<float>* p, const Cx<float> (&v)[2]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+}
+__device__ __forceinline__ void store16(Cx<double>* p, const Cx<double> (&v)[1]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0].x, v[0].y);
 }
 
 struct XParams {
@@ -164,7 +210,9 @@ __global__ void __launch_bounds__(256) xline_kernel(
     Cx<real>* wV = tw + NX;                                     // FE: V^ (then its x-inverse)
     Cx<real>* wK = wV + FE;                                     // FE: k_x V^
     Cx<real>* data = wK + FE;                                   // T x FE input spectra
-    __shared__ real s_hk[2][CH][4];   // per column: [0] = {h_yz, ky_eff(unused), ...}
+    __shared__ real s_hk[2][CH][4];   // per column: {h_y h_z, k_y eff, k_z eff, self-conjugate}, {k_y, k_z, origin}
+    __shared__ real s_hx[NX], s_kx[NX];
+    __shared__ real s_A[HYMD_MAX_TYPES * HYMD_MAX_TYPES];
 
     const real* hx = tab; const real* hy = hx + p.Nx; const real* hz = hy + p.Ny;
     const real* kxt = hz + p.Nzc; const real* kyt = kxt + p.Nx; const real* kzt = kyt + p.Ny;
@@ -172,7 +220,8 @@ __global__ void __launch_bounds__(256) xline_kernel(
     const int tid = threadIdx.x;
     const long long col0 = (long long)blockIdx.x * CH;
 
-    for (int i = tid; i < NX; i += NT) tw[i] = twg[i];
+    for (int i = tid; i < NX; i += NT) { tw[i] = twg[i]; s_hx[i] = hx[i]; s_kx[i] = kxt[i]; }
+    for (int i = tid; i < p.U * p.T; i += NT) s_A[i] = Au[i];
     // per-column constants
     if (tid < CH) {
         long long col = col0 + tid;
@@ -194,14 +243,23 @@ __global__ void __launch_bounds__(256) xline_kernel(
         s_hk[1][tid][3] = 0;
     }
 
-    // ---- load T x NX x CH ----
+    // ---- load T x NX x CH (16-byte cp.async chunks) ----
+    constexpr int VEC = 16 / (int)sizeof(Cx<real>);     // complex elements per 16 bytes
     const bool full = col0 + CH <= p.ncols;
-    for (int e = tid; e < p.T * NX * CH; e += NT) {
-        const int c = e % CH, x = (e / CH) % NX, t = e / (CH * NX);
-        Cx<real> v = {0, 0};
-        if (full || col0 + c < p.ncols) v = in[t * p.fs_in + x * p.xs_in + col0 + c];
-        data[t * FE + spos<NX, CH>(x, c)] = v;
+    for (int e = tid; e < p.T * NX * (CH / VEC); e += NT) {
+        const int c = (e % (CH / VEC)) * VEC, x = (e / (CH / VEC)) % NX, t = e / ((CH / VEC) * NX);
+        Cx<real>* dst = data + t * FE + spos<NX, CH>(x, c);
+        if (full || col0 + c < p.ncols) {
+            const Cx<real>* src = in + t * p.fs_in + x * p.xs_in + col0 + c;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) dst[i] = {0, 0};
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- forward FFT along x, all fields ----
     for (int task = tid; task < p.T * R2 * CH; task += NT)
@@ -217,7 +275,7 @@ __global__ void __launch_bounds__(256) xline_kernel(
             const int c = e % CH, pos = (e / CH) % NX, t = e / (CH * NX);
             const int kx = pos / R2 + R1 * (pos % R2);
             if (full || col0 + c < p.ncols) {
-                const real s = hx[kx] * s_hk[0][c][0] * inv_m;
+                const real s = s_hx[kx] * s_hk[0][c][0] * inv_m;
                 const Cx<real> v = data[t * FE + spos<NX, CH>(pos, c)];
                 pfout[t * p.fs_pf + kx * p.xs_pf + col0 + c] = {v.x * s, v.y * s};
             }
@@ -226,35 +284,45 @@ __global__ void __launch_bounds__(256) xline_kernel(
 
     for (int u = 0; u < p.U; ++u) {
         // ---- potential and k_x * potential in frequency space ----
-        for (int e = tid; e < NX * CH; e += NT) {
-            const int c = e % CH, pos = e / CH;
+        for (int e = tid; e < NX * (CH / VEC); e += NT) {
+            const int c = (e % (CH / VEC)) * VEC, pos = e / (CH / VEC);
             const int kx = pos / R2 + R1 * (pos % R2);     // frequency index held at this position
-            real ar = 0, ai = 0;
-            for (int t = 0; t < p.T; ++t) {
-                const real a = Au[u * p.T + t];
-                const Cx<real> v = data[t * FE + spos<NX, CH>(pos, c)];
-                ar += a * v.x; ai += a * v.y;
-            }
-            const real h = hx[kx] * s_hk[0][c][0];
-            real g;
-            if (p.pme) {
-                const real kxr = kxt[kx], kyr = s_hk[1][c][0], kzr = s_hk[1][c][1];
-                real k2 = kxr * kxr + kyr * kyr + kzr * kzr;
-                if (kx == 0 && s_hk[1][c][2] != (real)0) k2 = (real)1;   // normp(p=2, zeromode=1)
-                g = coef * h / k2;
-            } else {
-                g = h * h;
-            }
-            ar *= g; ai *= g;
-            const bool x_nyq = (NX % 2 == 0) && kx == NX / 2;
-            const real kxe = (x_nyq && s_hk[0][c][3] != (real)0) ? (real)0 : kxt[kx];
             const int sp = spos<NX, CH>(pos, c);
-            wV[sp] = {ar, ai};
-            wK[sp] = {kxe * ar, kxe * ai};
-            if (vout != nullptr && (full || col0 + c < p.ncols)) {
-                real vr = ar;
-                if (!p.pme && kx == 0 && s_hk[1][c][2] != (real)0) vr += cu[u];
-                vout[u * p.fs_v + kx * p.xs_v + col0 + c] = {vr, ai};
+            const real hxv = s_hx[kx], kxr = s_kx[kx];
+            const bool x_nyq = (NX % 2 == 0) && kx == NX / 2;
+            Cx<real> acc[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = {0, 0};
+            for (int t = 0; t < p.T; ++t) {
+                const real a = s_A[u * p.T + t];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const Cx<real> v = data[t * FE + sp + i];
+                    acc[i].x += a * v.x; acc[i].y += a * v.y;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const int ci = c + i;
+                const real h = hxv * s_hk[0][ci][0];
+                real g;
+                if (p.pme) {
+                    const real kyr = s_hk[1][ci][0], kzr = s_hk[1][ci][1];
+                    real k2 = kxr * kxr + kyr * kyr + kzr * kzr;
+                    if (kx == 0 && s_hk[1][ci][2] != (real)0) k2 = (real)1;   // normp(p=2, zeromode=1)
+                    g = coef * h / k2;
+                } else {
+                    g = h * h;
+                }
+                const real ar = acc[i].x * g, ai = acc[i].y * g;
+                const real kxe = (x_nyq && s_hk[0][ci][3] != (real)0) ? (real)0 : kxr;
+                wV[sp + i] = {ar, ai};
+                wK[sp + i] = {kxe * ar, kxe * ai};
+                if (vout != nullptr && (full || col0 + ci < p.ncols)) {
+                    real vr = ar;
+                    if (!p.pme && kx == 0 && s_hk[1][ci][2] != (real)0) vr += cu[u];
+                    vout[u * p.fs_v + kx * p.xs_v + col0 + ci] = {vr, ai};
+                }
             }
         }
         __syncthreads();
@@ -265,18 +333,25 @@ __global__ void __launch_bounds__(256) xline_kernel(
         for (int task = tid; task < 2 * R2 * CH; task += NT)
             fft_inv_stepB<real, NX, CH>(task < R2 * CH ? wV : wK, task % (R2 * CH));
         __syncthreads();
-        // ---- F_d = -i k_d V:  -i (a + i b) = b - i a ----
+        // ---- F_d = -i k_d V:  -i (a + i b) = b - i a  (16-byte stores) ----
         Cx<real>* f0 = fout + (long long)(3 * u) * p.fs_f;
-        for (int e = tid; e < NX * CH; e += NT) {
-            const int c = e % CH, x = e / CH;
+        for (int e = tid; e < NX * (CH / VEC); e += NT) {
+            const int c = (e % (CH / VEC)) * VEC, x = e / (CH / VEC);
             if (!(full || col0 + c < p.ncols)) continue;
             const int sp = spos<NX, CH>(x, c);
-            const Cx<real> v = wV[sp], k = wK[sp];
-            const real ky = s_hk[0][c][1], kz = s_hk[0][c][2];
             const long long o = x * p.xs_f + col0 + c;
-            f0[o] = {k.y, -k.x};
-            f0[p.fs_f + o] = {ky * v.y, -ky * v.x};
-            f0[2 * p.fs_f + o] = {kz * v.y, -kz * v.x};
+            Cx<real> fx[VEC], fy[VEC], fz[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const Cx<real> v = wV[sp + i], k = wK[sp + i];
+                const real ky = s_hk[0][c + i][1], kz = s_hk[0][c + i][2];
+                fx[i] = {k.y, -k.x};
+                fy[i] = {ky * v.y, -ky * v.x};
+                fz[i] = {kz * v.y, -kz * v.x};
+            }
+            store16(f0 + o, fx);
+            store16(f0 + p.fs_f + o, fy);
+            store16(f0 + 2 * p.fs_f + o, fz);
         }
         __syncthreads();
     }

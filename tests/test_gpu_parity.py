@@ -57,7 +57,8 @@ def test_paint_matches_oracle(dtype, mesh):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("mesh,n", [([24, 24, 24], 10000), ([16, 12, 10], 700), ([9, 12, 10], 500),
-                                    ([32, 40, 64], 20000)])
+                                    ([32, 40, 64], 20000), ([64, 48, 40], 30000),
+                                    ([128, 16, 24], 8000), ([256, 10, 12], 6000)])
 def test_field_forces_match_oracle(dtype, mesh, n):
     from gpu_common import GpuRun, OracleRun, rel_err
     cfg, pos, types, _ = _system(n, mesh, [4.0, 5.0, 6.0], dtype, seed=1)
@@ -70,12 +71,14 @@ def test_field_forces_match_oracle(dtype, mesh, n):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("kind", ["DefaultNoChi", "SquaredPhi", "DefaultWithChi"])
-def test_energies_and_potentials_match_oracle(dtype, kind):
+@pytest.mark.parametrize("kind,mesh", [("DefaultNoChi", [20, 24, 28]), ("SquaredPhi", [20, 24, 28]),
+                                       ("DefaultWithChi", [20, 24, 28]),
+                                       ("DefaultWithChi", [32, 24, 28]), ("DefaultNoChi", [64, 20, 18])])
+def test_energies_and_potentials_match_oracle(dtype, kind, mesh):
     """compute_potential=True path: filtered densities, v_ext and the field energy
-    (field.py:578, 615-616, 692-693)."""
+    (field.py:578, 615-616, 692-693); power-of-two Nx runs the fused x-line kernel."""
     from gpu_common import GpuRun, OracleRun, rel_err
-    cfg, pos, types, _ = _system(5000, [20, 24, 28], [4.0, 5.0, 6.0], dtype, seed=2,
+    cfg, pos, types, _ = _system(5000, mesh, [4.0, 5.0, 6.0], dtype, seed=2,
                                  hamiltonian=kind)
     rng = np.random.default_rng(9)
     vel = rng.normal(size=pos.shape).astype(dtype)
@@ -98,11 +101,12 @@ def test_energies_and_potentials_match_oracle(dtype, kind):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_pme_matches_oracle(dtype):
+@pytest.mark.parametrize("mesh", [[24, 20, 28], [32, 20, 28], [128, 12, 16]])
+def test_pme_matches_oracle(dtype, mesh):
     from gpu_common import GpuRun, OracleRun, rel_err
     from hymd_b200.field import compute_self_energy_q
     from oracle.field_oracle import compute_self_energy_q as self_o
-    cfg, pos, types, q = _system(6000, [24, 20, 28], [4.0, 5.0, 6.0], dtype, seed=3, coulomb=True)
+    cfg, pos, types, q = _system(6000, mesh, [4.0, 5.0, 6.0], dtype, seed=3, coulomb=True)
     cfg.self_energy = self_o(cfg, q)
     assert compute_self_energy_q(cfg, torch.as_tensor(q, device="cuda")) == pytest.approx(cfg.self_energy, rel=1e-6)
     g = GpuRun(cfg, pos, types, charges=q)

@@ -48,6 +48,11 @@ def test_two_slabs_match_oracle(dtype):
     _run(2, ["--dtype", dtype, "--pme"])
 
 
+def test_two_slabs_unfused_path():
+    _need(2)
+    _run(2, ["--dtype", "f64", "--pme"], {"HYMD_B200_NO_FUSED": "1"})
+
+
 def test_two_slabs_odd_planes():
     _need(2)
     _run(2, ["--dtype", "f64", "--mesh", "18", "12", "10", "--particles", "3000"])

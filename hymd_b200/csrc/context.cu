@@ -117,14 +117,11 @@ static int build_interaction(hymd_ctx* c) {
 static int ensure_particle_capacity(hymd_ctx* c, int64_t n) {
     if (n <= c->cap) return HYMD_OK;
     int64_t cap = n + n / 8 + 1024;
-    void* bufs[] = {c->rec, c->key, c->rank_in_cell, c->q_sorted};
+    void* bufs[] = {c->rec, c->q_sorted};
     for (void* b : bufs)
         if (b) cudaFree(b);
     c->rec = c->q_sorted = nullptr;
-    c->key = c->rank_in_cell = nullptr;
     HYMD_CHECK(dev_alloc(&c->rec, (size_t)cap * (c->f64 ? sizeof(Rec64) : sizeof(Rec32))));
-    HYMD_CHECK(dev_alloc((void**)&c->key, (size_t)cap * 4));
-    HYMD_CHECK(dev_alloc((void**)&c->rank_in_cell, (size_t)cap * 4));
     HYMD_CHECK(dev_alloc(&c->q_sorted, (size_t)cap * c->rsz));
     c->cap = cap;
     return HYMD_OK;
@@ -204,8 +201,7 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
 
     int st = HYMD_OK;
     auto fail = [&](int code) { hymd_ctx_destroy(c); return code; };
-    if ((st = dev_alloc((void**)&c->cell_count, (size_t)(g.ncell + 1) * 4))) return fail(st);
-    if ((st = dev_alloc((void**)&c->cell_start, (size_t)(g.ncell + 1) * 4))) return fail(st);
+    if ((st = dev_alloc((void**)&c->cell_start, (size_t)(g.ncell + 2) * 4))) return fail(st);
     if ((st = dev_alloc((void**)&c->scalars, sizeof(DeviceScalars)))) return fail(st);
     c->scan_tmp_bytes = scan_temp_bytes(g.ncell + 1);
     if ((st = dev_alloc(&c->scan_tmp, c->scan_tmp_bytes))) return fail(st);
@@ -243,7 +239,7 @@ int hymd_ctx_destroy(hymd_ctx* c) {
     if (c->plans) { destroy_plans(c); delete c->plans; c->plans = nullptr; }
     migrate_destroy(c);
     comm_destroy(c);
-    void* bufs[] = {c->rec, c->key, c->rank_in_cell, c->cell_count, c->cell_start, c->q_sorted,
+    void* bufs[] = {c->rec, c->cell_start, c->q_sorted,
                     c->scalars, c->scan_tmp, c->tab, c->xtw, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
                     c->phi_hat, c->f_hat, c->gmesh, c->v_hat, c->phif_hat, c->tmp_hat, c->v_ext,
                     c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->psi_hat, c->emesh, c->psi, c->fft_work,

@@ -129,10 +129,7 @@ struct hymd_ctx {
     int64_t np, cap;
     bool sorted, has_charges;
     void* rec;
-    uint32_t* key;
-    uint32_t* rank_in_cell;
-    uint32_t* cell_count;   // ncell + 1
-    uint32_t* cell_start;   // ncell + 1
+    uint32_t* cell_start;   // ncell + 2: [0] = 0, then the per-cell cursors (see sort.cu)
     void* q_sorted;
     hymd::DeviceScalars* scalars;
     void* scan_tmp;

@@ -66,6 +66,8 @@ template <> struct RTraits<double> {
     static constexpr int IDX_BITS = REC64_IDX_BITS;
 };
 
+constexpr int READOUT_MAX_ROWS = 64;   // tx * ty of the largest tile
+
 template <typename real, bool CHARGE>
 __global__ void __launch_bounds__(256) readout_kernel(
     const __grid_constant__ CUtensorMap tmap, const typename RTraits<real>::Rec* __restrict__ rec,
@@ -77,27 +79,56 @@ __global__ void __launch_bounds__(256) readout_kernel(
     real* S = reinterpret_cast<real*>(smem_raw);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)p.U * p.box_stride);
     int* s_urow = reinterpret_cast<int*>(bar + 1);
+    __shared__ uint32_t s_begin[READOUT_MAX_ROWS];
+    __shared__ uint32_t s_off[READOUT_MAX_ROWS];
+    __shared__ uint32_t s_wsum[2];
 
     int b = blockIdx.x;
     const int tz_i = b % p.ntz; b /= p.ntz;
     const int ty_i = b % p.nty; b /= p.nty;
     const int tx_i = b;
     const int x0 = tx_i * p.tx, y0 = ty_i * p.ty, z0 = tz_i * p.tz;
+    const int rows = p.tx * p.ty;
+    const int zb = min(z0 + p.tz, p.Nz);
 
+    // the TMA boxes of all potential rows fly while the particle runs of the tile are located
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (!CHARGE)
-        for (int i = threadIdx.x; i < p.T; i += blockDim.x) s_urow[i] = urow[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
         mbar_expect_tx(bar, (uint32_t)p.U * p.box_bytes);
         for (int u = 0; u < p.U; ++u)
             tma_load_4d(smem_raw + (size_t)u * p.box_stride, &tmap, bar, z0, y0, x0, 3 * u);
     }
+    if (!CHARGE)
+        for (int i = threadIdx.x; i < p.T; i += blockDim.x) s_urow[i] = urow[i];
+    // one (x,y) row of the tile = one contiguous run of the cell-sorted records
+    if (threadIdx.x < 64) {
+        const int r = threadIdx.x;
+        uint32_t pa = 0, len = 0;
+        if (r < rows) {
+            const int gx = x0 + r / p.ty, gy = y0 + r % p.ty;
+            if (gx < p.nxl && gy < p.Ny) {
+                const long long rowbase = ((long long)gx * p.Ny + gy) * p.Nz;
+                pa = start[rowbase + z0];
+                len = start[rowbase + zb] - pa;
+            }
+        }
+        // exclusive prefix sum over the 64 rows (two warps, combined through shared memory)
+        uint32_t inc = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((r & 31) >= d) inc += v;
+        }
+        if ((r & 31) == 31) s_wsum[r >> 5] = inc;
+        s_begin[r] = pa;
+        s_off[r] = inc - len;                             // exclusive within its warp
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32 && threadIdx.x < 64) s_off[threadIdx.x] += s_wsum[0];
+    __syncthreads();
+    const uint32_t total = s_wsum[0] + s_wsum[1];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const UT mx = ((UT)1 << p.fbx) - 1, my = ((UT)1 << p.fby) - 1, mz = ((UT)1 << p.fbz) - 1;
     const real ifx = (real)1 / (real)((UT)1 << p.fbx), ify = (real)1 / (real)((UT)1 << p.fby),
                ifz = (real)1 / (real)((UT)1 << p.fbz);
@@ -105,46 +136,46 @@ __global__ void __launch_bounds__(256) readout_kernel(
     const int py = p.ty + 1, px = p.tx + 1;
     const int comp_stride = px * py * p.bz;                 // elements between components
     const int box_elems = (int)(p.box_stride / sizeof(real));
-    const int zb = min(z0 + p.tz, p.Nz);
 
-    mbar_wait(bar, 0);
-
-    for (int r = warp; r < p.tx * p.ty; r += nwarps) {
+    bool waited = false;
+    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
+        // row of particle j: largest r with s_off[r] <= j  (64 entries: 6 halvings)
+        int r = 0;
+#pragma unroll
+        for (int step = 32; step > 0; step >>= 1)
+            if (s_off[r + step] <= j && r + step < READOUT_MAX_ROWS) r += step;
+        const uint32_t i = s_begin[r] + (j - s_off[r]);
+        const typename Tr::Rec rc = rec[i];
+        real q = (real)1;
+        if (CHARGE) q = q_sorted[i];
         const int lx = r / p.ty, ly = r % p.ty;
-        const int gx = x0 + lx, gy = y0 + ly;
-        if (gx >= p.nxl || gy >= p.Ny) continue;
-        const long long rowbase = ((long long)gx * p.Ny + gy) * p.Nz;
-        const uint32_t pa = start[rowbase + z0], pb = start[rowbase + zb];
-        for (uint32_t i = pa + lane; i < pb; i += 32) {
-            const typename Tr::Rec rc = rec[i];
-            const real dx = (real)(rc.ux & mx) * ifx, dy = (real)(rc.uy & my) * ify,
-                       dz = (real)(rc.uz & mz) * ifz;
-            const int lz = (int)(rc.uz >> p.fbz) - z0;
-            int u = 0;
-            if (!CHARGE) u = s_urow[(int)(rc.meta >> Tr::IDX_BITS)];
-            const real* B = S + (size_t)u * box_elems + (lx * py + ly) * p.bz + lz;
-            real f0 = 0, f1 = 0, f2 = 0;
+        const real dx = (real)(rc.ux & mx) * ifx, dy = (real)(rc.uy & my) * ify,
+                   dz = (real)(rc.uz & mz) * ifz;
+        const int lz = (int)(rc.uz >> p.fbz) - z0;
+        int u = 0;
+        if (!CHARGE) u = s_urow[(int)(rc.meta >> Tr::IDX_BITS)];
+        if (!waited) { mbar_wait(bar, 0); waited = true; }
+        const real* B = S + (size_t)u * box_elems + (lx * py + ly) * p.bz + lz;
+        real f0 = 0, f1 = 0, f2 = 0;
 #pragma unroll
-            for (int ax = 0; ax < 2; ++ax) {
-                const real wx = ax ? dx : (real)1 - dx;
+        for (int ax = 0; ax < 2; ++ax) {
+            const real wx = ax ? dx : (real)1 - dx;
 #pragma unroll
-                for (int ay = 0; ay < 2; ++ay) {
-                    const real wxy = wx * (ay ? dy : (real)1 - dy);
-                    const real* c = B + (ax * py + ay) * p.bz;
-                    const real w0 = wxy * ((real)1 - dz), w1 = wxy * dz;
-                    f0 += w0 * c[0] + w1 * c[1];
-                    f1 += w0 * c[comp_stride] + w1 * c[comp_stride + 1];
-                    f2 += w0 * c[2 * comp_stride] + w1 * c[2 * comp_stride + 1];
-                }
+            for (int ay = 0; ay < 2; ++ay) {
+                const real wxy = wx * (ay ? dy : (real)1 - dy);
+                const real* c = B + (ax * py + ay) * p.bz;
+                const real w0 = wxy * ((real)1 - dz), w1 = wxy * dz;
+                f0 += w0 * c[0] + w1 * c[1];
+                f1 += w0 * c[comp_stride] + w1 * c[comp_stride + 1];
+                f2 += w0 * c[2 * comp_stride] + w1 * c[2 * comp_stride + 1];
             }
-            if (CHARGE) {
-                const real q = q_sorted[i];
-                f0 *= q; f1 *= q; f2 *= q;
-            }
-            const size_t o = (size_t)(rc.meta & idx_mask) * 3;
-            force[o] = f0; force[o + 1] = f1; force[o + 2] = f2;
         }
+        if (CHARGE) { f0 *= q; f1 *= q; f2 *= q; }
+        const size_t o = (size_t)(rc.meta & idx_mask) * 3;
+        force[o] = f0; force[o + 1] = f1; force[o + 2] = f2;
     }
+    // the CTA must not retire with the bulk copies still in flight
+    if (!waited) mbar_wait(bar, 0);
 }
 
 // Periodic images into the ghost planes of nfields ghost-padded meshes (single-GPU x; y and z

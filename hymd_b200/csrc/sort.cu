@@ -1,9 +1,12 @@
 // Cell binning of the local particles: replaces pm.decompose (main.py:977-980, 1007).
 //
-// A counting sort keyed by the (local-slab, row-major) mesh cell of each particle:
-//   count   : one global atomicAdd per particle on the per-cell counter -> rank within cell
-//   scan    : exclusive prefix sum over the ncell+1 counters            -> cell_start[]
-//   scatter : record[cell_start[key] + rank] = fixed-point coordinates | index | type
+// A counting sort keyed by the (local-slab, row-major) mesh cell of each particle, on ONE array
+// a[0 .. ncell] (a[0] stays 0, cur = a + 1):
+//   count   : atomicAdd(cur[key], 1) per particle                        -> cur[k] = count of cell k
+//   scan    : exclusive prefix sum of cur[0 .. ncell) in place           -> cur[k] = start of cell k
+//   scatter : slot = atomicAdd(cur[key], 1); record[slot] = fixed-point coordinates | index | type
+// after which cur[k] = start[k] + count[k] = start[k+1], i.e. a[] IS the cell_start array that
+// paint and readout index.  No per-particle key / rank arrays are written or re-read.
 // The order of particles inside a cell depends on atomic arrival order; paint accumulates in
 // integer fixed point (order independent) and readout is a pure gather, so results are
 // bitwise reproducible anyway.
@@ -42,8 +45,6 @@ __device__ __forceinline__ UT pack_coord(int cell, double frac, int fb) {
 template <typename real>
 __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos, long long n,
                                                     SortParams p, uint32_t* __restrict__ cnt,
-                                                    uint32_t* __restrict__ key,
-                                                    uint32_t* __restrict__ rnk,
                                                     DeviceScalars* __restrict__ sc) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     unsigned int r1 = 0, bad = 0;
@@ -59,10 +60,7 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
             lx = lx < 0 ? 0 : p.nxl - 1;
         }
         uint32_t k = (uint32_t)(((long long)lx * p.Ny + cy) * p.Nz + cz);
-        uint32_t r = atomicAdd(&cnt[k], 1u);
-        key[i] = k;
-        rnk[i] = r;
-        r1 = r + 1;
+        r1 = atomicAdd(&cnt[k], 1u) + 1;
     }
     unsigned int m = __reduce_max_sync(0xffffffffu, r1);
     unsigned int b = __reduce_add_sync(0xffffffffu, bad);
@@ -75,9 +73,8 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
 template <typename real, typename RecT, typename UT, int IDX_BITS>
 __global__ void __launch_bounds__(256) scatter_kernel(
     const real* __restrict__ pos, const int32_t* __restrict__ types, const real* __restrict__ q,
-    long long n, SortParams p, const uint32_t* __restrict__ start, const uint32_t* __restrict__ key,
-    const uint32_t* __restrict__ rnk, RecT* __restrict__ rec, real* __restrict__ q_sorted,
-    DeviceScalars* __restrict__ sc) {
+    long long n, SortParams p, uint32_t* __restrict__ cur, RecT* __restrict__ rec,
+    real* __restrict__ q_sorted, DeviceScalars* __restrict__ sc) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     float aq = 0.f;
     if (i < n) {
@@ -88,7 +85,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(
         split_coord((double)pos[3 * i + 2] * p.sz, p.Nz, cz, dz);
         int lx = cx - p.x0;
         lx = lx < 0 ? 0 : (lx >= p.nxl ? p.nxl - 1 : lx);
-        size_t slot = (size_t)start[key[i]] + rnk[i];
+        const uint32_t k = (uint32_t)(((long long)lx * p.Ny + cy) * p.Nz + cz);
+        const size_t slot = atomicAdd(&cur[k], 1u);
         RecT r;
         r.ux = pack_coord<UT>(lx, dx, p.fbx);
         r.uy = pack_coord<UT>(cy, dy, p.fby);
@@ -156,33 +154,29 @@ int sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types, const
     p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
     p.sx = g.Nx / g.box[0]; p.sy = g.Ny / g.box[1]; p.sz = g.Nz / g.box[2];
     long long ncell = g.ncell;
-    HYMD_CUDA(cudaMemsetAsync(c->cell_count, 0, (size_t)(ncell + 1) * sizeof(uint32_t), s));
+    uint32_t* cur = c->cell_start + 1;
+    HYMD_CUDA(cudaMemsetAsync(c->cell_start, 0, (size_t)(ncell + 2) * sizeof(uint32_t), s));
     HYMD_CUDA(cudaMemsetAsync(c->scalars, 0, sizeof(DeviceScalars), s));
     unsigned int blocks = (unsigned int)((n + 255) / 256);
     if (n > 0) {
         if (c->f64)
-            count_kernel<double><<<blocks, 256, 0, s>>>((const double*)d_pos, n, p, c->cell_count,
-                                                        c->key, c->rank_in_cell, c->scalars);
+            count_kernel<double><<<blocks, 256, 0, s>>>((const double*)d_pos, n, p, cur, c->scalars);
         else
-            count_kernel<float><<<blocks, 256, 0, s>>>((const float*)d_pos, n, p, c->cell_count,
-                                                       c->key, c->rank_in_cell, c->scalars);
+            count_kernel<float><<<blocks, 256, 0, s>>>((const float*)d_pos, n, p, cur, c->scalars);
         HYMD_LAUNCH_CHECK(c);
     }
     size_t tmp = c->scan_tmp_bytes;
-    HYMD_CUDA(cub::DeviceScan::ExclusiveSum(c->scan_tmp, tmp, c->cell_count, c->cell_start,
-                                            (int)(ncell + 1), s));
+    HYMD_CUDA(cub::DeviceScan::ExclusiveSum(c->scan_tmp, tmp, cur, cur, (int)ncell, s));
     c->launches += 2;  // cub scan: init + scan kernels
     if (n > 0) {
         if (c->f64)
             scatter_kernel<double, Rec64, unsigned long long, REC64_IDX_BITS>
-                <<<blocks, 256, 0, s>>>((const double*)d_pos, d_types, (const double*)d_q, n, p,
-                                        c->cell_start, c->key, c->rank_in_cell, (Rec64*)c->rec,
-                                        (double*)c->q_sorted, c->scalars);
+                <<<blocks, 256, 0, s>>>((const double*)d_pos, d_types, (const double*)d_q, n, p, cur,
+                                        (Rec64*)c->rec, (double*)c->q_sorted, c->scalars);
         else
             scatter_kernel<float, Rec32, uint32_t, REC32_IDX_BITS>
-                <<<blocks, 256, 0, s>>>((const float*)d_pos, d_types, (const float*)d_q, n, p,
-                                        c->cell_start, c->key, c->rank_in_cell, (Rec32*)c->rec,
-                                        (float*)c->q_sorted, c->scalars);
+                <<<blocks, 256, 0, s>>>((const float*)d_pos, d_types, (const float*)d_q, n, p, cur,
+                                        (Rec32*)c->rec, (float*)c->q_sorted, c->scalars);
         HYMD_LAUNCH_CHECK(c);
     }
     return HYMD_OK;

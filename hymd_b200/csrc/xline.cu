@@ -220,7 +220,10 @@ __global__ void __launch_bounds__(256) xline_kernel(
     const int tid = threadIdx.x;
     const long long col0 = (long long)blockIdx.x * CH;
 
-    for (int i = tid; i < NX; i += NT) { tw[i] = twg[i]; s_hx[i] = hx[i]; s_kx[i] = kxt[i]; }
+    for (int i = tid; i < NX; i += NT) {      // s_hx / s_kx are indexed by POSITION (frequency order of the in-place FFT)
+        const int kx = i / R2 + R1 * (i % R2);
+        tw[i] = twg[i]; s_hx[i] = hx[kx]; s_kx[i] = kxt[kx];
+    }
     for (int i = tid; i < p.U * p.T; i += NT) s_A[i] = Au[i];
     // per-column constants
     if (tid < CH) {
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(256) xline_kernel(
             const int c = e % CH, pos = (e / CH) % NX, t = e / (CH * NX);
             const int kx = pos / R2 + R1 * (pos % R2);
             if (full || col0 + c < p.ncols) {
-                const real s = s_hx[kx] * s_hk[0][c][0] * inv_m;
+                const real s = s_hx[pos] * s_hk[0][c][0] * inv_m;
                 const Cx<real> v = data[t * FE + spos<NX, CH>(pos, c)];
                 pfout[t * p.fs_pf + kx * p.xs_pf + col0 + c] = {v.x * s, v.y * s};
             }
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(256) xline_kernel(
             const int c = (e % (CH / VEC)) * VEC, pos = e / (CH / VEC);
             const int kx = pos / R2 + R1 * (pos % R2);     // frequency index held at this position
             const int sp = spos<NX, CH>(pos, c);
-            const real hxv = s_hx[kx], kxr = s_kx[kx];
+            const real hxv = s_hx[pos], kxr = s_kx[pos];
             const bool x_nyq = (NX % 2 == 0) && kx == NX / 2;
             Cx<real> acc[VEC];
 #pragma unroll

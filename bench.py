@@ -287,11 +287,30 @@ def main():
         q_h = None if q_h is None else q_h[mine]
     n_loc = len(pos_h)
     dev = pm.device
-    pos_d = torch.as_tensor(np.ascontiguousarray(pos_h), dtype=t_dtype, device=dev)
+    # MD-like input stream: step k sees the positions of step k-1 displaced by one outer step of
+    # thermal motion (v * respa_inner * time_step, ~0.05 nm = 12 % of a cell), so every step
+    # re-bins genuinely different coordinates.  NBUF trajectories frames, visited ping-pong.
+    NBUF = 6
+    vel_h = sysm.velocities[mine] if world > 1 else sysm.velocities
+    L = np.asarray(cfg.box_size, dtype=np.float64)
+    frames_h = []
+    for k in range(NBUF):
+        f = np.mod(pos_h.astype(np.float64) + k * PS_PER_CYCLE * vel_h.astype(np.float64), L)
+        f = f.astype(np_dtype)
+        f[f >= L.astype(np_dtype)] = 0
+        if world > 1:   # keep every particle inside this rank's slab (no migration in the timed loop)
+            lo = rank * (mesh[0] // world) * L[0] / mesh[0]
+            hi = (rank + 1) * (mesh[0] // world) * L[0] / mesh[0]
+            f[:, 0] = np.clip(f[:, 0], np.nextafter(np_dtype(lo), np_dtype(hi)) if lo > 0 else 0,
+                              np.nextafter(np_dtype(hi), np_dtype(lo)))
+        frames_h.append(np.ascontiguousarray(f))
+    order = list(range(NBUF)) + list(range(NBUF - 2, 0, -1))
+    frames_d = [torch.as_tensor(f, dtype=t_dtype, device=dev) for f in frames_h]
     typ_d = torch.as_tensor(typ_h.astype(np.int32), device=dev)
     q_d = None if q_h is None else torch.as_tensor(q_h, dtype=t_dtype, device=dev)
     force_d = torch.zeros((n_loc, 3), dtype=t_dtype, device=dev)
     eforce_d = torch.zeros((n_loc, 3), dtype=t_dtype, device=dev) if pme else None
+    counter = {"dev": 0, "host": 0}
 
     def cycle(pos, typ, q, force, eforce):
         F.update_field(phi, phi_laplacian, phi_transfer, layouts, force_mesh, ham, pm, pos, typ,
@@ -322,7 +341,11 @@ def main():
         return float(ms.item())
 
     # ---- device-resident run ---------------------------------------------------------------
-    dev_cycle = lambda: cycle(pos_d, typ_d, q_d, force_d, eforce_d)
+    def dev_cycle():
+        k = order[counter["dev"] % len(order)]
+        counter["dev"] += 1
+        cycle(frames_d[k], typ_d, q_d, force_d, eforce_d)
+
     for _ in range(max(args.warmup, 3)):
         dev_cycle()
     torch.cuda.synchronize()
@@ -342,20 +365,34 @@ def main():
     # ---- end to end: host (pinned) in, host out, every step --------------------------------
     e2e = None
     if not args.no_e2e:
-        pos_p = torch.from_numpy(np.ascontiguousarray(pos_h)).pin_memory()
+        frames_p = [torch.from_numpy(f).pin_memory() for f in frames_h[:4]]
+        order_p = [0, 1, 2, 3, 2, 1]
         typ_p = torch.from_numpy(typ_h.astype(np.int32)).pin_memory()
         q_p = None if q_h is None else torch.from_numpy(np.ascontiguousarray(q_h)).pin_memory()
         force_p = torch.zeros((n_loc, 3), dtype=t_dtype).pin_memory()
         eforce_p = torch.zeros((n_loc, 3), dtype=t_dtype).pin_memory() if pme else None
-        host_cycle = lambda: cycle(pos_p, typ_p, q_p, force_p, eforce_p)
+
+        def host_cycle():
+            k = order_p[counter["host"] % len(order_p)]
+            counter["host"] += 1
+            cycle(frames_p[k], typ_p, q_p, force_p, eforce_p)
+            return k
+
         for _ in range(2):
             host_cycle()
         k = max(3, min(args.steps, 10))
         ms_e2e = timed(host_cycle, k)
+        # the last host step against the same frame computed device-resident
+        last = order_p[(counter["host"] - 1) % len(order_p)]
+        cycle(frames_d[last], typ_d, q_d, force_d, eforce_d)
+        torch.cuda.synchronize()
         if not np.isfinite(force_p.numpy()).all() or \
                 not torch.equal(force_p, force_d.cpu()):
             raise SystemExit("end-to-end forces differ from the device-resident run")
-        h2d = pos_p.numel() * pos_p.element_size() + typ_p.numel() * 4 + \
+        pos_p = frames_p[0]
+        # positions (and charges for PME) cross PCIe every step; the types are static per-particle
+        # data and are uploaded once (the API re-uploads them only when a different array is passed)
+        h2d = pos_p.numel() * pos_p.element_size() + \
             (q_p.numel() * q_p.element_size() if pme else 0)
         d2h = force_p.numel() * force_p.element_size() * (2 if pme else 1)
         e2e = {"value": N_global * k / (ms_e2e * 1e-3), "unit": UNIT, "steps": k,
@@ -403,6 +440,8 @@ def main():
         "config": {"workload": f"{args.workload}: N={N_global}, mesh {mesh[0]}x{mesh[1]}x{mesh[2]}, "
                                f"T={T} (U={U} distinct potential rows), sigma={cfg.sigma}, "
                                f"kappa={cfg.kappa}, DefaultWithChi" + (", PME" if pme else ""),
+                   "inputs": f"{NBUF} trajectory frames visited ping-pong, consecutive frames differ by "
+                             "one outer step of thermal motion (0.25 ps at 323 K, ~0.05 nm)",
                    "l2": "inputs larger than L2 (per-step working set "
                          f"{total_alg / 1e6:.0f} MB vs 126 MB L2), no flush",
                    "parallelism": "single GPU" if world == 1 else f"{world} x-slabs (slab FFT, NCCL all-to-all)"},

@@ -15,6 +15,7 @@ HYMD_MAX_TYPES = 32
 NCCL_ID_BYTES = 128
 
 F32, F64 = 0, 1
+SORT_REUSE_ORDER = 1
 (FIELD_PHI, FIELD_PHI_FOURIER, FIELD_FORCE_MESH, FIELD_V_EXT, FIELD_PHI_Q, FIELD_PHI_Q_FOURIER,
  FIELD_PSI, FIELD_ELEC_FIELD) = range(8)
 
@@ -25,6 +26,7 @@ EXPORTS = [
     "hymd_set_charges", "hymd_paint", "hymd_field_cycle", "hymd_readout", "hymd_pme_cycle",
     "hymd_materialize", "hymd_field_energy", "hymd_get_field", "hymd_ctx_status",
     "hymd_launch_count", "hymd_migrate_plan", "hymd_migrate_apply", "hymd_ctx_set_timing", "hymd_ctx_get_timings",
+    "hymd_sort_particles_ex", "hymd_ctx_reset_order",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -77,6 +79,8 @@ def load():
     lib.hymd_ctx_set_interaction.argtypes = [vp, P(dbl), P(dbl), P(dbl), dbl, dbl]
     lib.hymd_sort_particles.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.hymd_set_charges.argtypes = [vp, vp, vp]
+    lib.hymd_sort_particles_ex.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, vp]
+    lib.hymd_ctx_reset_order.argtypes = [vp]
     lib.hymd_paint.argtypes = [vp, vp]
     lib.hymd_field_cycle.argtypes = [vp, ctypes.c_int, vp]
     lib.hymd_readout.argtypes = [vp, vp, vp]

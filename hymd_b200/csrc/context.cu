@@ -117,11 +117,13 @@ static int build_interaction(hymd_ctx* c) {
 static int ensure_particle_capacity(hymd_ctx* c, int64_t n) {
     if (n <= c->cap) return HYMD_OK;
     int64_t cap = n + n / 8 + 1024;
-    void* bufs[] = {c->rec, c->q_sorted};
+    void* bufs[] = {c->rec, c->rec_alt, c->q_sorted};
     for (void* b : bufs)
         if (b) cudaFree(b);
-    c->rec = c->q_sorted = nullptr;
+    c->rec = c->rec_alt = c->q_sorted = nullptr;
+    c->order_n = -1;
     HYMD_CHECK(dev_alloc(&c->rec, (size_t)cap * (c->f64 ? sizeof(Rec64) : sizeof(Rec32))));
+    HYMD_CHECK(dev_alloc(&c->rec_alt, (size_t)cap * (c->f64 ? sizeof(Rec64) : sizeof(Rec32))));
     HYMD_CHECK(dev_alloc(&c->q_sorted, (size_t)cap * c->rsz));
     c->cap = cap;
     return HYMD_OK;
@@ -167,6 +169,7 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     c->ev_pool = new std::vector<cudaEvent_t>();
     c->ev_open = new std::vector<PhaseInterval>();
     c->f64 = cfg->dtype == HYMD_F64;
+    c->order_n = -1;
     c->rsz = c->f64 ? 8 : 4;
     c->T = cfg->n_types;
     cudaGetDevice(&c->dev);
@@ -239,7 +242,7 @@ int hymd_ctx_destroy(hymd_ctx* c) {
     if (c->plans) { destroy_plans(c); delete c->plans; c->plans = nullptr; }
     migrate_destroy(c);
     comm_destroy(c);
-    void* bufs[] = {c->rec, c->cell_start, c->q_sorted,
+    void* bufs[] = {c->rec, c->rec_alt, c->cell_start, c->q_sorted,
                     c->scalars, c->scan_tmp, c->tab, c->xtw, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
                     c->phi_hat, c->f_hat, c->gmesh, c->v_hat, c->phif_hat, c->tmp_hat, c->v_ext,
                     c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->psi_hat, c->emesh, c->psi, c->fft_work,
@@ -308,7 +311,19 @@ int hymd_ctx_set_interaction(hymd_ctx* c, const double* A, const double* cc, con
 
 int hymd_sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types,
                         const void* d_charges, int64_t n, void* stream) {
-    if (!c || (n > 0 && (!d_pos || !d_types))) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    return hymd_sort_particles_ex(c, d_pos, d_types, d_charges, n, 0, stream);
+}
+
+int hymd_ctx_reset_order(hymd_ctx* c) {
+    if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    c->order_n = -1;
+    return HYMD_OK;
+}
+
+int hymd_sort_particles_ex(hymd_ctx* c, const void* d_pos, const int32_t* d_types,
+                           const void* d_charges, int64_t n, int flags, void* stream) {
+    const bool reuse = c && (flags & HYMD_SORT_REUSE_ORDER) && c->order_n == n && n > 0;
+    if (!c || (n > 0 && (!d_pos || (!d_types && !reuse)))) { set_error("null argument"); return HYMD_ERR_INVALID; }
     const int64_t lim = c->f64 ? (1LL << 31) : (1LL << REC32_IDX_BITS);
     if (n < 0 || n >= lim) {
         set_error("n = %lld particles exceeds the per-GPU limit %lld", (long long)n, (long long)lim);
@@ -319,9 +334,10 @@ int hymd_sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types,
     c->has_charges = d_charges != nullptr;
     {
         PhaseScope ps(c, HYMD_PHASE_SORT, (cudaStream_t)stream);
-        HYMD_CHECK(sort_particles(c, d_pos, d_types, d_charges, n, (cudaStream_t)stream));
+        HYMD_CHECK(sort_particles(c, d_pos, d_types, d_charges, n, reuse, (cudaStream_t)stream));
     }
     c->sorted = true;
+    c->order_n = n;
     return HYMD_OK;
 }
 

@@ -128,7 +128,9 @@ struct hymd_ctx {
     // particles
     int64_t np, cap;
     bool sorted, has_charges;
-    void* rec;
+    void* rec;              // cell-sorted records of the last sort
+    void* rec_alt;          // the other half of the double buffer (staging area of the next sort)
+    int64_t order_n;        // particle count the order in `rec` is valid for (-1: none)
     uint32_t* cell_start;   // ncell + 2: [0] = 0, then the per-cell cursors (see sort.cu)
     void* q_sorted;
     hymd::DeviceScalars* scalars;
@@ -224,7 +226,7 @@ struct PhaseScope {
 
 // sort.cu
 int sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types, const void* d_q,
-                   int64_t n, cudaStream_t s);
+                   int64_t n, bool reuse, cudaStream_t s);
 size_t scan_temp_bytes(long long n);
 int gather_charges(hymd_ctx* c, const void* d_q, cudaStream_t s);
 // paint.cu

@@ -42,24 +42,45 @@ __device__ __forceinline__ UT pack_coord(int cell, double frac, int fb) {
     return ((UT)cell << fb) | f;
 }
 
-template <typename real>
-__global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos, long long n,
-                                                    SortParams p, uint32_t* __restrict__ cnt,
+// Pass 1.  Thread j handles one particle: in REUSE mode the particle that sat at sorted slot j
+// in the previous call (its index and type come from the previous record), otherwise particle j
+// of the caller's arrays.  It converts the CURRENT position to the fixed-point record, leaves it
+// in stage[j] (in place over the previous record) and counts its cell.
+template <typename real, typename RecT, typename UT, int IDX_BITS, bool REUSE>
+__global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos,
+                                                    const int32_t* __restrict__ types, long long n,
+                                                    SortParams p, RecT* __restrict__ stage,
+                                                    uint32_t* __restrict__ cnt,
                                                     DeviceScalars* __restrict__ sc) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     unsigned int r1 = 0, bad = 0;
-    if (i < n) {
+    if (j < n) {
+        UT idx, type;
+        if (REUSE) {
+            const UT meta = stage[j].meta;
+            idx = meta & (((UT)1 << IDX_BITS) - 1);
+            type = meta >> IDX_BITS;
+        } else {
+            idx = (UT)j;
+            type = (UT)(uint32_t)types[j];
+        }
         int cx, cy, cz;
-        double d;
-        split_coord((double)pos[3 * i + 0] * p.sx, p.Nx, cx, d);
-        split_coord((double)pos[3 * i + 1] * p.sy, p.Ny, cy, d);
-        split_coord((double)pos[3 * i + 2] * p.sz, p.Nz, cz, d);
+        double dx, dy, dz;
+        split_coord((double)pos[3 * idx + 0] * p.sx, p.Nx, cx, dx);
+        split_coord((double)pos[3 * idx + 1] * p.sy, p.Ny, cy, dy);
+        split_coord((double)pos[3 * idx + 2] * p.sz, p.Nz, cz, dz);
         int lx = cx - p.x0;
         if (lx < 0 || lx >= p.nxl) {
             bad = 1;
             lx = lx < 0 ? 0 : p.nxl - 1;
         }
-        uint32_t k = (uint32_t)(((long long)lx * p.Ny + cy) * p.Nz + cz);
+        RecT r;
+        r.ux = pack_coord<UT>(lx, dx, p.fbx);
+        r.uy = pack_coord<UT>(cy, dy, p.fby);
+        r.uz = pack_coord<UT>(cz, dz, p.fbz);
+        r.meta = idx | (type << IDX_BITS);
+        stage[j] = r;
+        const uint32_t k = (uint32_t)(((long long)lx * p.Ny + cy) * p.Nz + cz);
         r1 = atomicAdd(&cnt[k], 1u) + 1;
     }
     unsigned int m = __reduce_max_sync(0xffffffffu, r1);
@@ -70,31 +91,23 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
     }
 }
 
+// Pass 2 (after the scan): staged record j goes to the next free slot of its cell.
 template <typename real, typename RecT, typename UT, int IDX_BITS>
 __global__ void __launch_bounds__(256) scatter_kernel(
-    const real* __restrict__ pos, const int32_t* __restrict__ types, const real* __restrict__ q,
-    long long n, SortParams p, uint32_t* __restrict__ cur, RecT* __restrict__ rec,
-    real* __restrict__ q_sorted, DeviceScalars* __restrict__ sc) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const RecT* __restrict__ stage, const real* __restrict__ q, long long n, SortParams p,
+    uint32_t* __restrict__ cur, RecT* __restrict__ rec, real* __restrict__ q_sorted,
+    DeviceScalars* __restrict__ sc) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     float aq = 0.f;
-    if (i < n) {
-        int cx, cy, cz;
-        double dx, dy, dz;
-        split_coord((double)pos[3 * i + 0] * p.sx, p.Nx, cx, dx);
-        split_coord((double)pos[3 * i + 1] * p.sy, p.Ny, cy, dy);
-        split_coord((double)pos[3 * i + 2] * p.sz, p.Nz, cz, dz);
-        int lx = cx - p.x0;
-        lx = lx < 0 ? 0 : (lx >= p.nxl ? p.nxl - 1 : lx);
-        const uint32_t k = (uint32_t)(((long long)lx * p.Ny + cy) * p.Nz + cz);
+    if (j < n) {
+        const RecT r = stage[j];
+        const long long lx = (long long)(r.ux >> p.fbx), cy = (long long)(r.uy >> p.fby),
+                        cz = (long long)(r.uz >> p.fbz);
+        const uint32_t k = (uint32_t)((lx * p.Ny + cy) * p.Nz + cz);
         const size_t slot = atomicAdd(&cur[k], 1u);
-        RecT r;
-        r.ux = pack_coord<UT>(lx, dx, p.fbx);
-        r.uy = pack_coord<UT>(cy, dy, p.fby);
-        r.uz = pack_coord<UT>(cz, dz, p.fbz);
-        r.meta = (UT)i | ((UT)(uint32_t)types[i] << IDX_BITS);
         rec[slot] = r;
         if (q != nullptr) {
-            real qi = q[i];
+            const real qi = q[r.meta & (((UT)1 << IDX_BITS) - 1)];
             q_sorted[slot] = qi;
             aq = fabsf((float)qi);
         }
@@ -146,40 +159,51 @@ size_t scan_temp_bytes(long long n) {
     return bytes;
 }
 
-int sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types, const void* d_q,
-                   int64_t n, cudaStream_t s) {
+template <typename real, typename RecT, typename UT, int IDX_BITS>
+static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, const void* d_q,
+                     int64_t n, bool reuse, cudaStream_t s) {
     const Geometry& g = c->g;
     SortParams p;
     p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nxl = g.nxl; p.x0 = g.x0;
     p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
     p.sx = g.Nx / g.box[0]; p.sy = g.Ny / g.box[1]; p.sz = g.Nz / g.box[2];
-    long long ncell = g.ncell;
+    const long long ncell = g.ncell;
     uint32_t* cur = c->cell_start + 1;
     HYMD_CUDA(cudaMemsetAsync(c->cell_start, 0, (size_t)(ncell + 2) * sizeof(uint32_t), s));
     HYMD_CUDA(cudaMemsetAsync(c->scalars, 0, sizeof(DeviceScalars), s));
-    unsigned int blocks = (unsigned int)((n + 255) / 256);
+    // stage = the buffer holding the previous sorted records (overwritten in place), out = the other
+    RecT* stage = (RecT*)c->rec;
+    RecT* out = (RecT*)c->rec_alt;
+    const unsigned int blocks = (unsigned int)((n + 255) / 256);
     if (n > 0) {
-        if (c->f64)
-            count_kernel<double><<<blocks, 256, 0, s>>>((const double*)d_pos, n, p, cur, c->scalars);
+        if (reuse)
+            count_kernel<real, RecT, UT, IDX_BITS, true><<<blocks, 256, 0, s>>>(
+                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars);
         else
-            count_kernel<float><<<blocks, 256, 0, s>>>((const float*)d_pos, n, p, cur, c->scalars);
+            count_kernel<real, RecT, UT, IDX_BITS, false><<<blocks, 256, 0, s>>>(
+                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars);
         HYMD_LAUNCH_CHECK(c);
     }
     size_t tmp = c->scan_tmp_bytes;
     HYMD_CUDA(cub::DeviceScan::ExclusiveSum(c->scan_tmp, tmp, cur, cur, (int)ncell, s));
     c->launches += 2;  // cub scan: init + scan kernels
     if (n > 0) {
-        if (c->f64)
-            scatter_kernel<double, Rec64, unsigned long long, REC64_IDX_BITS>
-                <<<blocks, 256, 0, s>>>((const double*)d_pos, d_types, (const double*)d_q, n, p, cur,
-                                        (Rec64*)c->rec, (double*)c->q_sorted, c->scalars);
-        else
-            scatter_kernel<float, Rec32, uint32_t, REC32_IDX_BITS>
-                <<<blocks, 256, 0, s>>>((const float*)d_pos, d_types, (const float*)d_q, n, p, cur,
-                                        (Rec32*)c->rec, (float*)c->q_sorted, c->scalars);
+        scatter_kernel<real, RecT, UT, IDX_BITS><<<blocks, 256, 0, s>>>(
+            stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars);
         HYMD_LAUNCH_CHECK(c);
     }
+    c->rec = out;
+    c->rec_alt = stage;
     return HYMD_OK;
+}
+
+// reuse: start from the order of the previous call (same n, same per-index types): consecutive
+// MD steps move particles by a fraction of a cell, so the staged records are almost sorted and
+// the counter atomics and record writes of both passes hit neighbouring addresses.
+int sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types, const void* d_q,
+                   int64_t n, bool reuse, cudaStream_t s) {
+    return c->f64 ? sort_impl<double, Rec64, unsigned long long, REC64_IDX_BITS>(c, d_pos, d_types, d_q, n, reuse, s)
+                  : sort_impl<float, Rec32, uint32_t, REC32_IDX_BITS>(c, d_pos, d_types, d_q, n, reuse, s);
 }
 
 }  // namespace hymd

@@ -149,6 +149,7 @@ class ParticleMesh:
         self._interaction_key = None
         self._sort_key = None
         self._sort_types_key = None
+        self._order_types_key = None
         self._keep = (None, None, None)
         self._n_local = 0
         self._sorted_with_charges = False
@@ -308,16 +309,27 @@ class ParticleMesh:
         if pos.ndim != 2 or pos.shape[1] != 3:
             raise ValueError(f"positions must be (N,3), got {tuple(pos.shape)}")
         n = pos.shape[0]
-        if types is None:
-            ty = torch.zeros(n, dtype=torch.int32, device=self.device)
-        else:
-            ty = self.as_device(types, dtype=torch.int32, shape=(n,))
+        # Consecutive MD steps pass the same types object (HyMD reads the types once,
+        # main.py:72-125): the library then re-bins starting from the previous cell order and
+        # does not need the types again (they ride along in the sorted records).
+        otk = ("none", n) if types is None else tk
+        reuse = self._order_types_key is not None and otk == self._order_types_key \
+            and n == self._n_local and n > 0
+        ty = None
+        if not reuse:
+            if types is None:
+                ty = torch.zeros(n, dtype=torch.int32, device=self.device)
+            else:
+                ty = self.as_device(types, dtype=torch.int32, shape=(n,))
         q = None if charges is None else self.as_device(charges, shape=(n,))
-        _lib.check(self.lib.hymd_sort_particles(
-            self._ctx, ctypes.c_void_p(pos.data_ptr()), ctypes.c_void_p(ty.data_ptr()),
-            ctypes.c_void_p(q.data_ptr()) if q is not None else None, n, self.stream))
+        _lib.check(self.lib.hymd_sort_particles_ex(
+            self._ctx, ctypes.c_void_p(pos.data_ptr()),
+            ctypes.c_void_p(ty.data_ptr()) if ty is not None else None,
+            ctypes.c_void_p(q.data_ptr()) if q is not None else None, n,
+            _lib.SORT_REUSE_ORDER if reuse else 0, self.stream))
         self._keep = (pos, ty, q)   # inputs must outlive the asynchronous kernels
         self._sort_key, self._sort_types_key = pk, tk
+        self._order_types_key = otk
         self._n_local = n
         self._sorted_with_charges = charges is not None
 
@@ -408,6 +420,8 @@ class ParticleMesh:
                 o = o.to(a.device)
             out.append(o)
         self._sort_key = None
+        self._order_types_key = None
+        _lib.check(self.lib.hymd_ctx_reset_order(self._ctx))
         return tuple(out)
 
 

@@ -104,6 +104,18 @@ int hymd_ctx_set_interaction(hymd_ctx* ctx, const double* A, const double* c, co
 int hymd_sort_particles(hymd_ctx* ctx, const void* d_pos, const int32_t* d_types,
                         const void* d_charges, int64_t n, void* stream);
 
+/* Same, with flags.  HYMD_SORT_REUSE_ORDER: the per-index particle types are the same as in the
+ * previous call and n is unchanged (true between consecutive MD steps: HyMD reads the types once
+ * from the input file); the binning then starts from the previous cell order, which turns the
+ * random scatter of a cold sort into nearly sequential traffic.  d_types may be NULL with this
+ * flag.  If there is no usable previous order the flag is ignored (then d_types is required).
+ * The result is identical either way. */
+#define HYMD_SORT_REUSE_ORDER 1
+int hymd_sort_particles_ex(hymd_ctx* ctx, const void* d_pos, const int32_t* d_types,
+                           const void* d_charges, int64_t n, int flags, void* stream);
+/* Forget the previous order (call when the caller's particle arrays were permuted or replaced). */
+int hymd_ctx_reset_order(hymd_ctx* ctx);
+
 /* Attach charges to an existing sort of the same positions (pm.decompose(positions) for the
  * charge layout, main.py:1007, without re-binning). */
 int hymd_set_charges(hymd_ctx* ctx, const void* d_charges, void* stream);

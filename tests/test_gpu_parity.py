@@ -199,3 +199,35 @@ def test_per_type_paint_mass_and_shared_potential_rows():
     o = OracleRun(cfg, pos, types)
     assert g.pm.status()["potential_rows"] == 1
     assert rel_err(g.forces(), o.force) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_consecutive_steps_reuse_previous_order(dtype):
+    """MD-like sequence on ONE context: positions drift between calls, the types tensor is the
+    same object, so the binning starts from the previous cell order (HYMD_SORT_REUSE_ORDER).
+    Results must be bitwise identical to a cold context and match the oracle."""
+    import torch
+    from gpu_common import GpuRun, OracleRun, rel_err
+    from hymd_b200 import field as F
+    cfg, pos, types, q = _system(15000, [32, 24, 20], [4.0, 5.0, 6.0], dtype, seed=12, coulomb=True)
+    rng = np.random.default_rng(3)
+    g = GpuRun(cfg, pos, types, charges=q)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    box = cfg.box_size.astype(dtype)
+    layouts = [g.pm.decompose(None) for _ in range(cfg.n_types)]
+    for step in range(3):
+        pos = np.mod(pos + rng.normal(scale=0.05, size=pos.shape).astype(dtype), box).astype(dtype)
+        pos[pos >= box] = 0
+        pos_d = torch.as_tensor(pos, dtype=tdt, device="cuda")
+        F.update_field(g.phi, g.phi_laplacian, g.phi_transfer, layouts, g.force_mesh, g.h, g.pm,
+                       pos_d, g.types, cfg, g.v_ext, g.phi_fourier, g.v_ext_fourier, cfg.m)
+        F.compute_field_force(layouts, pos_d, g.force_mesh, g.force, g.types, cfg.n_types)
+        F.update_field_force_q(g.q, g.phi_q, g.phi_q_fourier, g.psi, None, None, g.elec_field,
+                               g.elec_forces, g.pm.decompose(None), g.h, g.pm, pos_d, cfg)
+    torch.cuda.synchronize()
+    cold = GpuRun(cfg, pos, types, charges=q)
+    assert np.array_equal(g.forces(), cold.forces())
+    assert np.array_equal(g.eforces(), cold.eforces())
+    o = OracleRun(cfg, pos, types, charges=q)
+    assert rel_err(g.forces(), o.force) < TOL[dtype]
+    assert rel_err(g.eforces(), o.elec_forces) < TOL[dtype]

@@ -9,6 +9,8 @@
 // tile's cell-sorted particles -- one warp per (x,y) row, whose particles are contiguous -- and
 // interpolates from shared memory.  Results are written to the caller's (n,3) array at the
 // particle's original index, so the caller's order is preserved.
+#include <stdlib.h>
+
 #include "ctx.cuh"
 
 namespace hymd {
@@ -21,6 +23,7 @@ struct ReadoutParams {
     int U, T;
     unsigned int box_bytes;  // bytes of one TMA box (3 components)
     unsigned int box_stride; // box_bytes rounded up to 128 B (TMA destination alignment)
+    int debug_seq;           // TIMING EXPERIMENT ONLY: write forces in sorted order
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -77,16 +80,13 @@ __global__ void __launch_bounds__(256) readout_kernel(
     using UT = typename Tr::UT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     real* S = reinterpret_cast<real*>(smem_raw);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)p.box_stride);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)p.U * p.box_stride);
     int* s_urow = reinterpret_cast<int*>(bar + 1);
     __shared__ uint32_t s_begin[READOUT_MAX_ROWS];
     __shared__ uint32_t s_off[READOUT_MAX_ROWS];
     __shared__ uint32_t s_wsum[2];
 
-    // one CTA per (tile, potential row): the U CTAs of a tile are neighbours in the grid, so the
-    // tile's records are read from HBM once and served from L2 to the others
     int b = blockIdx.x;
-    const int my_u = b % p.U; b /= p.U;
     const int tz_i = b % p.ntz; b /= p.ntz;
     const int ty_i = b % p.nty; b /= p.nty;
     const int tx_i = b;
@@ -98,8 +98,9 @@ __global__ void __launch_bounds__(256) readout_kernel(
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar, p.box_bytes);
-        tma_load_4d(smem_raw, &tmap, bar, z0, y0, x0, 3 * my_u);
+        mbar_expect_tx(bar, (uint32_t)p.U * p.box_bytes);
+        for (int u = 0; u < p.U; ++u)
+            tma_load_4d(smem_raw + (size_t)u * p.box_stride, &tmap, bar, z0, y0, x0, 3 * u);
     }
     if (!CHARGE)
         for (int i = threadIdx.x; i < p.T; i += blockDim.x) s_urow[i] = urow[i];
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256) readout_kernel(
     const UT idx_mask = ((UT)1 << Tr::IDX_BITS) - 1;
     const int py = p.ty + 1, px = p.tx + 1;
     const int comp_stride = px * py * p.bz;                 // elements between components
+    const int box_elems = (int)(p.box_stride / sizeof(real));
 
     bool waited = false;
     for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
@@ -153,9 +155,10 @@ __global__ void __launch_bounds__(256) readout_kernel(
         const real dx = (real)(rc.ux & mx) * ifx, dy = (real)(rc.uy & my) * ify,
                    dz = (real)(rc.uz & mz) * ifz;
         const int lz = (int)(rc.uz >> p.fbz) - z0;
-        if (!CHARGE && s_urow[(int)(rc.meta >> Tr::IDX_BITS)] != my_u) continue;
+        int u = 0;
+        if (!CHARGE) u = s_urow[(int)(rc.meta >> Tr::IDX_BITS)];
         if (!waited) { mbar_wait(bar, 0); waited = true; }
-        const real* B = S + (lx * py + ly) * p.bz + lz;
+        const real* B = S + (size_t)u * box_elems + (lx * py + ly) * p.bz + lz;
         real f0 = 0, f1 = 0, f2 = 0;
 #pragma unroll
         for (int ax = 0; ax < 2; ++ax) {
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(256) readout_kernel(
             }
         }
         if (CHARGE) { f0 *= q; f1 *= q; f2 *= q; }
-        const size_t o = (size_t)(rc.meta & idx_mask) * 3;
+        const size_t o = p.debug_seq ? (size_t)i * 3 : (size_t)(rc.meta & idx_mask) * 3;
         force[o] = f0; force[o + 1] = f1; force[o + 2] = f2;
     }
     // the CTA must not retire with the bulk copies still in flight
@@ -257,20 +260,21 @@ static int encode_map(hymd_ctx* c, CUtensorMap* map, void* base, int nfields) {
 }
 
 int readout_setup(hymd_ctx* c) {
-    // one potential row per CTA: largest tile whose 3-component box fits ~40 KB (five or six CTAs per SM)
+    // largest tile whose boxes for all U potential rows fit ~100 KB (two CTAs per SM)
     static const int cand[][2] = {{8, 8}, {4, 8}, {4, 4}, {2, 4}, {2, 2}, {1, 2}, {1, 1}};
     const int tz = 32;
     const int bz = ((tz + 1 + 3) / 4) * 4;
-    const size_t budget = 40 * 1024;
+    size_t budget = 100 * 1024;
+    if (const char* e = getenv("HYMD_B200_READOUT_KB")) budget = (size_t)atoi(e) * 1024;   // tuning
     int pick = 6;
     for (int i = 0; i < 7; ++i) {
-        size_t bytes = (size_t)3 * (cand[i][0] + 1) * (cand[i][1] + 1) * bz * c->rsz;
+        size_t bytes = (size_t)c->U * 3 * (cand[i][0] + 1) * (cand[i][1] + 1) * bz * c->rsz;
         if (bytes <= budget) { pick = i; break; }
     }
     c->rtx = cand[pick][0]; c->rty = cand[pick][1]; c->rtz = tz; c->rbz = bz;
     const size_t box_bytes = (size_t)3 * (c->rtx + 1) * (c->rty + 1) * bz * c->rsz;
     const size_t box_stride = (box_bytes + 127) / 128 * 128;
-    c->readout_smem = box_stride + 16 + HYMD_MAX_TYPES * sizeof(int);
+    c->readout_smem = (size_t)c->U * box_stride + 16 + HYMD_MAX_TYPES * sizeof(int);
     c->readout_smem_pme = box_stride + 16 + HYMD_MAX_TYPES * sizeof(int);
     if (c->readout_smem > 227 * 1024) {
         set_error("readout: %d distinct potential rows need %zu B of shared memory", c->U,
@@ -297,10 +301,11 @@ static int launch_readout(hymd_ctx* c, void* d_force, cudaStream_t s) {
     p.T = c->T;
     p.box_bytes = (unsigned int)((size_t)3 * (p.tx + 1) * (p.ty + 1) * p.bz * sizeof(real));
     p.box_stride = (p.box_bytes + 127u) / 128u * 128u;
+    p.debug_seq = getenv("HYMD_B200_DEBUG_SEQ") != nullptr;
     const size_t smem = CHARGE ? c->readout_smem_pme : c->readout_smem;
     auto kern = readout_kernel<real, CHARGE>;
     HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long blocks = (long long)p.ntx * p.nty * p.ntz * p.U;
+    const long long blocks = (long long)p.ntx * p.nty * p.ntz;
     kern<<<(unsigned int)blocks, 256, smem, s>>>(CHARGE ? c->tmap_emesh : c->tmap_gmesh,
                                                  (const typename Tr::Rec*)c->rec,
                                                  (const real*)c->q_sorted, c->cell_start, c->d_urow,

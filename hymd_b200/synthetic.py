@@ -4,7 +4,10 @@ All systems: ``numpy.random.default_rng(seed)``, cubic box ``L = float32((N / 8.
 the number density is ~8.37 nm^-3 (``utils/units.py:5`` of the reference), kappa = 0.05,
 ``hamiltonian = "DefaultWithChi"``, ``m = [1.0] * T``, types assigned by fixed fractions.
 Polymer types are laid out as 20-bead random-walk chains (bond 0.47 nm) wrapped periodically;
-solvent is uniform.
+solvent is uniform.  Particle order follows HyMD's input format: the beads of a molecule are
+consecutive (``distribute_input`` hands out whole molecules by index range,
+``file_io.py:781-874``), molecules -- chains and single solvent beads alike -- appear in random
+order, so the order carries no spatial information beyond the chains themselves.
 """
 from __future__ import annotations
 
@@ -91,7 +94,23 @@ def make_system(name: str = "C2", dtype=np.float32, n: Optional[int] = None,
             steps[:, 0, :] = 0.0
             walk = np.cumsum(steps, axis=1) + pos[idx[:nb:20], None, :]
             pos[idx[:nb]] = np.mod(walk.reshape(nb, 3), L)
-    perm = rng.permutation(n)          # caller order is arbitrary in HyMD (file order)
+    # file order: molecules (20-bead chains, single solvent beads) in random order, the beads of
+    # one molecule consecutive
+    mol_start = []
+    for t, is_poly in enumerate(spec["polymer"]):
+        idx = np.nonzero(types == t)[0]
+        if is_poly and chains:
+            nb = len(idx) // 20 * 20
+            mol_start.append(np.stack([idx[:nb:20], np.full(nb // 20, 20)], axis=1))
+            rest = idx[nb:]
+        else:
+            rest = idx
+        mol_start.append(np.stack([rest, np.ones(len(rest), dtype=np.int64)], axis=1))
+    mols = np.concatenate(mol_start, axis=0)
+    mols = mols[rng.permutation(len(mols))]
+    ends = np.cumsum(mols[:, 1])
+    begins = ends - mols[:, 1]
+    perm = np.repeat(mols[:, 0] - begins, mols[:, 1]) + np.arange(n)
     pos, types = pos[perm], types[perm]
     charges = None
     coulomb = bool(spec.get("coulomb"))

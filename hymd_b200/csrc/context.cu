@@ -229,6 +229,7 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     const char* no_fused = getenv("HYMD_B200_NO_FUSED");
     c->fused = xline_supported(c) && !(no_fused && no_fused[0] == '1');
     c->slab = P > 1 || c->fused || (force_slab && force_slab[0] == '1');
+    c->plane = c->slab && plane_supported(c);
     if (P > 1 && (st = comm_create(c, nccl_id))) return fail(st);
     if ((st = readout_setup(c))) return fail(st);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(HYMD_ERR_CUDA);
@@ -246,7 +247,7 @@ int hymd_ctx_destroy(hymd_ctx* c) {
                     c->scalars, c->scan_tmp, c->tab, c->xtw, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
                     c->phi_hat, c->f_hat, c->gmesh, c->v_hat, c->phif_hat, c->tmp_hat, c->v_ext,
                     c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->psi_hat, c->emesh, c->psi, c->fft_work,
-                    c->wA, c->wS, c->halo};
+                    c->wA, c->wS, c->halo, c->ytw, c->ztw, c->plane_scratch};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (c->ev_open) {
@@ -425,7 +426,7 @@ int hymd_field_cycle(hymd_ctx* c, int compute_potential, void* stream) {
     }
     {
         PhaseScope ps(c, HYMD_PHASE_GHOST, s);
-        HYMD_CHECK(fill_ghosts(c, c->gmesh, 3 * c->U, s));
+        if (!c->plane) HYMD_CHECK(fill_ghosts(c, c->gmesh, 3 * c->U, s));
         HYMD_CHECK(halo_fetch(c, c->gmesh, 3 * c->U, s));
     }
     c->have_forces = true;
@@ -514,7 +515,7 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
         if (c->fused)
             HYMD_CHECK(fft_inverse_xdone(c, (c->g.P == 1) ? c->wA : c->e_hat, 3, c->emesh, true, s));
         else HYMD_CHECK(fft_inverse(c, c->e_hat, 3, c->emesh, true, s));
-        HYMD_CHECK(fill_ghosts(c, c->emesh, 3, s));
+        if (!c->plane) HYMD_CHECK(fill_ghosts(c, c->emesh, 3, s));
         HYMD_CHECK(halo_fetch(c, c->emesh, 3, s));
         if (want_psi) HYMD_CHECK(fft_inverse(c, c->psi_hat, 1, c->psi, false, s));
     }

@@ -141,6 +141,11 @@ struct hymd_ctx {
     void* tab;            // packed: hx[Nx] hy[Ny] hz[Nzc] kx[Nx] ky[Ny] kz[Nzc]
     void* xtw;            // Nx complex twiddles exp(-2 pi i j / Nx) for the fused x-line kernel
     bool fused;           // fused x-line kernel in use (power-of-two Nx)
+    bool plane;           // one-pass (y,z) plane transforms in use (planefft.cu)
+    void* ytw;            // Ny / Nz complex twiddles of the plane transforms
+    void* ztw;
+    void* plane_scratch;  // per-CTA scratch planes of the plane transforms (L2 resident)
+    size_t plane_scratch_bytes;
     void* Au;             // U*T reals, already divided by M
     void* cu;             // U offsets (added at k = 0 for v_ext)
     int* d_urow;          // T ints
@@ -246,6 +251,12 @@ int ensure_work(hymd_ctx* c, int F);
 void destroy_plans(hymd_ctx* c);
 int halo_reduce(hymd_ctx* c, void* fields, int F, cudaStream_t s);
 int halo_fetch(hymd_ctx* c, void* ghost_meshes, int F, cudaStream_t s);
+// planefft.cu
+bool plane_supported(const hymd_ctx* c);
+int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int nplanes, void* k_out,
+                  long long k_fs, cudaStream_t s);
+int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int nplanes, void* real_out,
+                  bool ghost, cudaStream_t s);
 // xline.cu
 bool xline_supported(const hymd_ctx* c);
 int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s);

@@ -1,0 +1,461 @@
+// (y,z) plane transforms of the slab pipeline: the batched 2-D r2c / c2r of RealField.r2c /
+// ComplexField.c2r (field.py:576-578, 584, 613, 616, 366, 377, 397) done in ONE pass over HBM
+// per direction instead of the two passes (y c2c, z r2c/c2r) a library 2-D plan makes.
+//
+// One persistent CTA per SM takes a whole (field, x-plane) unit at a time:
+//
+//   inverse (c2r)   phase 1: chunks of 8 kz-columns of the spectrum, inverse FFT along y (four
+//                            groups of 128 threads, each on its own chunk), stored to a per-CTA
+//                            scratch plane that is reused for every unit and therefore lives in L2;
+//                   phase 2: row pairs (y, y+1) of the scratch plane -> ONE complex inverse FFT
+//                            along z of A + iB (Hermitian extension built on the fly; the imaginary
+//                            parts of k_z = 0 and k_z = Nz/2 are dropped = c2r semantics), real part
+//                            -> row y, imaginary part -> row y+1, every warp on its own row pairs,
+//                            written straight into the ghost-padded force-mesh layout INCLUDING
+//                            the periodic images (z = Nz element, y = Ny row, x = nxl plane), so
+//                            no separate ghost-fill pass is needed.
+//   forward (r2c)   the mirror image: row pairs of the real plane -> one complex FFT along z,
+//                   split into the two half spectra, scratch plane, then column chunks along y.
+//
+// HBM traffic per unit = read the plane once + write it once; the y<->z exchange goes through
+// the L2-resident scratch (148 CTAs x Ny x (Nz/2+1) complex = 39 MB at 256^2 fp32).
+// Power-of-two Ny, Nz only; other mesh sizes keep the cuFFT plans of slabfft.cu.
+#include <stdlib.h>
+
+#include "ctx.cuh"
+#include "fft.cuh"
+
+namespace hymd {
+
+// ---- shared-memory layouts ---------------------------------------------------------------------
+// LayA: FFT along the strided axis, CH columns contiguous (column chunks).
+template <int N, int CH>
+struct LayA {
+    static constexpr int R2 = Radix<N>::R2;
+    static constexpr int ELEMS = (N + N / R2) * CH;
+    __device__ static __forceinline__ int at(int pos, int c) { return (pos + pos / R2) * CH + c; }
+};
+// LayB: FFT along the contiguous axis, one padded row per transform (row pairs).
+template <int N, int CP>
+struct LayB {
+    static constexpr int R2 = Radix<N>::R2;
+    static constexpr int PITCH = N + N / R2;
+    static constexpr int ELEMS = PITCH * CP;
+    __device__ static __forceinline__ int at(int pos, int c) { return c * PITCH + pos + pos / R2; }
+};
+
+// ---- memory access helpers ---------------------------------------------------------------------
+__device__ __forceinline__ Cx<float> ld_stream(const Cx<float>* p) {      // read once from HBM
+    const float2 t = __ldcs(reinterpret_cast<const float2*>(p)); return {t.x, t.y};
+}
+__device__ __forceinline__ Cx<double> ld_stream(const Cx<double>* p) {
+    const double2 t = __ldcs(reinterpret_cast<const double2*>(p)); return {t.x, t.y};
+}
+__device__ __forceinline__ Cx<float> ld_l2(const Cx<float>* p) {          // scratch plane: L2 only
+    const float2 t = __ldcg(reinterpret_cast<const float2*>(p)); return {t.x, t.y};
+}
+__device__ __forceinline__ Cx<double> ld_l2(const Cx<double>* p) {
+    const double2 t = __ldcg(reinterpret_cast<const double2*>(p)); return {t.x, t.y};
+}
+__device__ __forceinline__ void st_stream(Cx<float>* p, Cx<float> v) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+}
+__device__ __forceinline__ void st_stream(Cx<double>* p, Cx<double> v) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+}
+__device__ __forceinline__ void st_l2(Cx<float>* p, Cx<float> v) {
+    __stcg(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+}
+__device__ __forceinline__ void st_l2(Cx<double>* p, Cx<double> v) {
+    __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+}
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float shfl(float v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
+__device__ __forceinline__ double shfl(double v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
+
+struct PlaneParams {
+    int nunits, nplanes;            // units = fields x planes
+    long long k_fs, k_xs;           // complex strides (field, plane) of the spectra, row pitch Nzcp
+    long long r_fs, r_xs;           // real strides (field, plane)
+    int r_ys;                       // real row pitch
+    int ghost;                      // inverse: also write the z = Nz element and the y = Ny row
+    int xdup_plane;                 // inverse: plane 0 is written to this plane as well (-1: no)
+};
+
+// Work decomposition inside the 512-thread CTA.
+//   column phase: NG groups of GT threads, each on its own chunk of CG kz-columns (64 bytes per
+//                 spectrum row), synchronised with a named barrier per group;
+//   row phase   : every warp on its own CW row pairs, synchronised with __syncwarp only.
+// Butterfly inputs are loaded from global memory straight into registers and the last butterfly
+// stage stores straight to global memory, so each FFT makes exactly one trip through shared memory.
+template <typename real, int NY, int NZ> struct PlaneCfg {
+    static constexpr int NT = 512, NW = NT / 32;
+    static constexpr int R1y = Radix<NY>::R1, R2y = Radix<NY>::R2, R1z = Radix<NZ>::R1, R2z = Radix<NZ>::R2;
+    static constexpr int NZC = NZ / 2 + 1, NZCP = NZC + (NZC & 1);
+    static constexpr int CG = 64 / (int)sizeof(Cx<real>);
+    static constexpr int GT = CG * 16, NG = NT / GT;
+    using LA = LayA<NY, CG>;
+    static constexpr int NTILE = (2 * NG * LA::ELEMS * (int)sizeof(Cx<real>) <= 144 * 1024) ? 2 : 1;
+    static constexpr int CW = 32 / R1z;                                    // row pairs per warp pass
+    using LB = LayB<NZ, CW>;
+    static constexpr int COL_ELEMS = NG * NTILE * LA::ELEMS, ROW_ELEMS = NW * LB::ELEMS;
+    static constexpr int TILE = COL_ELEMS > ROW_ELEMS ? COL_ELEMS : ROW_ELEMS;
+    static constexpr size_t SMEM = sizeof(Cx<real>) * (size_t)(NY + NZ + TILE);
+    static_assert((NY / 2) % CW == 0, "row pairs per warp pass must divide the plane");
+};
+
+// ---- inverse: spectra [ky][kz] -> real plane ------------------------------------------------------
+template <typename real, int NY, int NZ>
+__global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_c2r_kernel(
+    const Cx<real>* __restrict__ in, Cx<real>* __restrict__ scratch, real* __restrict__ out,
+    const Cx<real>* __restrict__ twy_g, const Cx<real>* __restrict__ twz_g, PlaneParams p) {
+    using Cfg = PlaneCfg<real, NY, NZ>;
+    using LA = typename Cfg::LA;
+    using LB = typename Cfg::LB;
+    constexpr int NT = Cfg::NT, NW = Cfg::NW, CG = Cfg::CG, GT = Cfg::GT, NG = Cfg::NG, NTILE = Cfg::NTILE,
+                  CW = Cfg::CW, NZC = Cfg::NZC, NZCP = Cfg::NZCP;
+    constexpr int R1y = Cfg::R1y, R2y = Cfg::R2y, R1z = Cfg::R1z, R2z = Cfg::R2z;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx<real>* twy = reinterpret_cast<Cx<real>*>(smem_raw);
+    Cx<real>* twz = twy + NY;
+    Cx<real>* tile = twz + NZ;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NY; i += NT) twy[i] = twy_g[i];
+    for (int i = tid; i < NZ; i += NT) twz[i] = twz_g[i];
+    __syncthreads();
+    Cx<real>* scr = scratch + (size_t)blockIdx.x * NY * NZCP;
+    constexpr int NCHG = (NZC + CG - 1) / CG;             // the pad column is never read
+    const int g = tid / GT, gt = tid % GT;
+    const int warp = tid / 32, lane = tid % 32;
+    Cx<real>* gtile = tile + g * NTILE * LA::ELEMS;
+    Cx<real>* wtile = tile + warp * LB::ELEMS;
+
+    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+        const int f = unit / p.nplanes, x = unit % p.nplanes;
+        const Cx<real>* src = in + f * p.k_fs + x * p.k_xs;
+        // ---------------- column phase: inverse FFT along y ----------------
+        int it = 0;
+        for (int ch = (g + unit) % NG; ch < NCHG; ch += NG, ++it) {
+            Cx<real>* cur = gtile + (it & (NTILE - 1)) * LA::ELEMS;
+            const int c0 = ch * CG;
+            for (int task = gt; task < CG * R1y; task += GT) {
+                const int c = task % CG, k1 = task / CG;
+                const bool valid = c0 + c < NZC;
+                Cx<real> v[R2y];
+#pragma unroll
+                for (int k2 = 0; k2 < R2y; ++k2)
+                    v[k2] = valid ? ld_stream(src + (long long)(k1 + R1y * k2) * NZCP + c0 + c) : Cx<real>{0, 0};
+                dft_reg<real, R2y, +1>(v);
+#pragma unroll
+                for (int n2 = 0; n2 < R2y; ++n2) {
+                    Cx<real> w = twy[(n2 * k1) & (NY - 1)];
+                    w.y = -w.y;
+                    cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                }
+            }
+            group_sync(g + 1, GT);
+            for (int task = gt; task < CG * R2y; task += GT) {
+                const int c = task % CG, n2 = task / CG;
+                Cx<real> v[R1y];
+#pragma unroll
+                for (int k1 = 0; k1 < R1y; ++k1) v[k1] = cur[LA::at(k1 * R2y + n2, c)];
+                dft_reg<real, R1y, +1>(v);
+                if (c0 + c < NZC) {
+#pragma unroll
+                    for (int n1 = 0; n1 < R1y; ++n1)
+                        st_l2(scr + (long long)(n1 * R2y + n2) * NZCP + c0 + c, v[n1]);
+                }
+            }
+            if (NTILE == 1) group_sync(g + 1, GT);
+        }
+        __syncthreads();
+        // ---------------- row phase: c2r along z on row pairs (A + iB) ----------------
+        real* obase = out + f * p.r_fs + x * p.r_xs;
+        real* obase2 = (p.xdup_plane >= 0 && x == 0) ? out + f * p.r_fs + p.xdup_plane * p.r_xs : nullptr;
+        for (int pg = warp; pg < (NY / 2) / CW; pg += NW) {
+            {   // exactly 32 tasks: (row pair c, k1)
+                const int c = lane / R1z, k1 = lane % R1z;
+                const Cx<real>* rowA = scr + (long long)(2 * (pg * CW + c)) * NZCP;
+                const Cx<real>* rowB = rowA + NZCP;
+                Cx<real> v[R2z];
+#pragma unroll
+                for (int k2 = 0; k2 < R2z; ++k2) {
+                    const int k = k1 + R1z * k2;
+                    const int kk = (2 * k <= NZ) ? k : NZ - k;
+                    const Cx<real> A = ld_l2(rowA + kk), B = ld_l2(rowB + kk);
+                    real s = (2 * k < NZ) ? (real)1 : (real)-1;          // mirrored half: conjugates
+                    if (k == 0 || 2 * k == NZ) s = 0;                    // c2r drops these imaginary parts
+                    v[k2] = {A.x - s * B.y, s * A.y + B.x};
+                }
+                dft_reg<real, R2z, +1>(v);
+#pragma unroll
+                for (int n2 = 0; n2 < R2z; ++n2) {
+                    Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
+                    w.y = -w.y;
+                    wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                }
+            }
+            __syncwarp();
+            for (int task = lane; task < CW * R2z; task += 32) {
+                const int c = task / R2z, n2 = task % R2z;
+                Cx<real> v[R1z];
+#pragma unroll
+                for (int k1 = 0; k1 < R1z; ++k1) v[k1] = wtile[LB::at(k1 * R2z + n2, c)];
+                dft_reg<real, R1z, +1>(v);
+                const int y0 = 2 * (pg * CW + c);
+#pragma unroll
+                for (int dup = 0; dup < 2; ++dup) {
+                    real* ob = dup ? obase2 : obase;
+                    if (ob == nullptr) continue;
+                    real* oa = ob + (long long)y0 * p.r_ys + n2;
+#pragma unroll
+                    for (int n1 = 0; n1 < R1z; ++n1) {
+                        __stcs(oa + n1 * R2z, v[n1].x);
+                        __stcs(oa + p.r_ys + n1 * R2z, v[n1].y);
+                    }
+                    if (p.ghost) {
+                        if (n2 == 0) { oa[NZ] = v[0].x; oa[p.r_ys + NZ] = v[0].y; }
+                        if (y0 == 0) {
+                            real* og = ob + (long long)NY * p.r_ys + n2;
+#pragma unroll
+                            for (int n1 = 0; n1 < R1z; ++n1) __stcs(og + n1 * R2z, v[n1].x);
+                            if (n2 == 0) og[NZ] = v[0].x;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
+// ---- forward: real plane -> spectra [ky][kz] -----------------------------------------------------
+template <typename real, int NY, int NZ>
+__global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_r2c_kernel(
+    const real* __restrict__ in, Cx<real>* __restrict__ scratch, Cx<real>* __restrict__ out,
+    const Cx<real>* __restrict__ twy_g, const Cx<real>* __restrict__ twz_g, PlaneParams p) {
+    using Cfg = PlaneCfg<real, NY, NZ>;
+    using LA = typename Cfg::LA;
+    using LB = typename Cfg::LB;
+    constexpr int NT = Cfg::NT, NW = Cfg::NW, CG = Cfg::CG, GT = Cfg::GT, NG = Cfg::NG, NTILE = Cfg::NTILE,
+                  CW = Cfg::CW, NZC = Cfg::NZC, NZCP = Cfg::NZCP;
+    constexpr int R1y = Cfg::R1y, R2y = Cfg::R2y, R1z = Cfg::R1z, R2z = Cfg::R2z;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx<real>* twy = reinterpret_cast<Cx<real>*>(smem_raw);
+    Cx<real>* twz = twy + NY;
+    Cx<real>* tile = twz + NZ;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NY; i += NT) twy[i] = twy_g[i];
+    for (int i = tid; i < NZ; i += NT) twz[i] = twz_g[i];
+    __syncthreads();
+    Cx<real>* scr = scratch + (size_t)blockIdx.x * NY * NZCP;
+    constexpr int NCHG = (NZCP + CG - 1) / CG;            // the pad column is written (zeros)
+    const int g = tid / GT, gt = tid % GT;
+    const int warp = tid / 32, lane = tid % 32;
+    Cx<real>* gtile = tile + g * NTILE * LA::ELEMS;
+    Cx<real>* wtile = tile + warp * LB::ELEMS;
+
+    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+        const int f = unit / p.nplanes, x = unit % p.nplanes;
+        const real* src = in + f * p.r_fs + x * p.r_xs;
+        // ---------------- row phase: one complex FFT along z per row pair (a + ib) ----------------
+        for (int pg = warp; pg < (NY / 2) / CW; pg += NW) {
+            for (int task = lane; task < CW * R2z; task += 32) {
+                const int c = task / R2z, n2 = task % R2z;
+                const real* ra = src + (long long)(2 * (pg * CW + c)) * p.r_ys + n2;
+                Cx<real> v[R1z];
+#pragma unroll
+                for (int n1 = 0; n1 < R1z; ++n1) v[n1] = {__ldcs(ra + n1 * R2z), __ldcs(ra + p.r_ys + n1 * R2z)};
+                dft_reg<real, R1z, -1>(v);
+#pragma unroll
+                for (int k1 = 0; k1 < R1z; ++k1) {
+                    const Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
+                    wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+                }
+            }
+            __syncwarp();
+            {   // exactly 32 tasks: (row pair c, k1); v[k2] = Z[k1 + R1z k2]
+                const int c = lane / R1z, k1 = lane % R1z;
+                Cx<real> v[R2z];
+#pragma unroll
+                for (int n2 = 0; n2 < R2z; ++n2) v[n2] = wtile[LB::at(k1 * R2z + n2, c)];
+                dft_reg<real, R2z, -1>(v);
+                // Z[NZ - k] lives in lane (R1z - k1) % R1z of the same row, register R2z-1-k2
+                // (k1 == 0: own register (R2z - k2) % R2z)
+                const int partner = lane - k1 + ((R1z - k1) % R1z);
+                Cx<real>* rowA = scr + (long long)(2 * (pg * CW + c)) * NZCP;
+                Cx<real>* rowB = rowA + NZCP;
+                static_for<0, R2z / 2 + 1>([&](auto kc) {
+                    constexpr int k2 = decltype(kc)::value;
+                    const Cx<real> give = (k1 == 0) ? v[(R2z - k2) % R2z] : v[R2z - 1 - k2];
+                    const Cx<real> zn = {shfl(give.x, partner), shfl(give.y, partner)};
+                    const Cx<real> zk = v[k2];
+                    const int k = k1 + R1z * k2;
+                    if (2 * k <= NZ) {
+                        st_l2(rowA + k, Cx<real>{(real)0.5 * (zk.x + zn.x), (real)0.5 * (zk.y - zn.y)});
+                        st_l2(rowB + k, Cx<real>{(real)0.5 * (zk.y + zn.y), (real)0.5 * (zn.x - zk.x)});
+                    }
+                });
+                if (NZCP > NZC && k1 == 0) {
+                    st_l2(rowA + NZC, Cx<real>{0, 0});
+                    st_l2(rowB + NZC, Cx<real>{0, 0});
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---------------- column phase: FFT along y from the scratch plane ----------------
+        Cx<real>* dstp = out + f * p.k_fs + x * p.k_xs;
+        int it = 0;
+        for (int ch = (g + unit) % NG; ch < NCHG; ch += NG, ++it) {
+            Cx<real>* cur = gtile + (it & (NTILE - 1)) * LA::ELEMS;
+            const int c0 = ch * CG;
+            for (int task = gt; task < CG * R2y; task += GT) {
+                const int c = task % CG, n2 = task / CG;
+                const bool valid = c0 + c < NZCP;
+                Cx<real> v[R1y];
+#pragma unroll
+                for (int n1 = 0; n1 < R1y; ++n1)
+                    v[n1] = valid ? ld_l2(scr + (long long)(n1 * R2y + n2) * NZCP + c0 + c) : Cx<real>{0, 0};
+                dft_reg<real, R1y, -1>(v);
+#pragma unroll
+                for (int k1 = 0; k1 < R1y; ++k1) {
+                    const Cx<real> w = twy[(n2 * k1) & (NY - 1)];
+                    cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+                }
+            }
+            group_sync(g + 1, GT);
+            for (int task = gt; task < CG * R1y; task += GT) {
+                const int c = task % CG, k1 = task / CG;
+                Cx<real> v[R2y];
+#pragma unroll
+                for (int n2 = 0; n2 < R2y; ++n2) v[n2] = cur[LA::at(k1 * R2y + n2, c)];
+                dft_reg<real, R2y, -1>(v);
+                if (c0 + c < NZCP) {
+#pragma unroll
+                    for (int k2 = 0; k2 < R2y; ++k2)
+                        st_stream(dstp + (long long)(k1 + R1y * k2) * NZCP + c0 + c, v[k2]);
+                }
+            }
+            if (NTILE == 1) group_sync(g + 1, GT);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static bool pow2_in(int n, int lo, int hi) { return n >= lo && n <= hi && (n & (n - 1)) == 0; }
+
+bool plane_supported(const hymd_ctx* c) {
+    const Geometry& g = c->g;
+    if (const char* e = getenv("HYMD_B200_NO_PLANE")) if (e[0] == '1') return false;
+    if (g.Ny != g.Nz) return false;                       // square planes are instantiated
+    return pow2_in(g.Ny, 16, c->f64 ? 256 : 512);
+}
+
+static int plane_tables(hymd_ctx* c) {
+    if (c->ytw) return HYMD_OK;
+    const Geometry& g = c->g;
+    for (int a = 0; a < 2; ++a) {
+        const int n = a ? g.Nz : g.Ny;
+        std::vector<double> tw(2 * (size_t)n);
+        for (int j = 0; j < n; ++j) {
+            tw[2 * j] = cos(2.0 * M_PI * j / n);
+            tw[2 * j + 1] = -sin(2.0 * M_PI * j / n);
+        }
+        void* d = nullptr;
+        HYMD_CUDA(cudaMalloc(&d, tw.size() * c->rsz));
+        if (c->f64) {
+            HYMD_CUDA(cudaMemcpy(d, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice));
+        } else {
+            std::vector<float> h(tw.begin(), tw.end());
+            HYMD_CUDA(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        }
+        (a ? c->ztw : c->ytw) = d;
+    }
+    return HYMD_OK;
+}
+
+template <typename real, int N, bool INVERSE>
+static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
+    using Cfg = PlaneCfg<real, N, N>;
+    HYMD_CHECK(plane_tables(c));
+    int sms = 0;
+    HYMD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev));
+    int grid = sms;
+    if (const char* e = getenv("HYMD_B200_PLANE_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;   // tuning
+    if (grid > p.nunits) grid = p.nunits;
+    if (grid < 1) return HYMD_OK;
+    const size_t need = (size_t)sms * 2 * N * Cfg::NZCP * sizeof(Cx<real>);
+    if (c->plane_scratch_bytes < need) {
+        if (c->plane_scratch) { HYMD_CUDA(cudaDeviceSynchronize()); cudaFree(c->plane_scratch); c->plane_scratch = nullptr; }
+        HYMD_CUDA(cudaMalloc(&c->plane_scratch, need));
+        c->plane_scratch_bytes = need;
+    }
+    if ((size_t)grid * N * Cfg::NZCP * sizeof(Cx<real>) > c->plane_scratch_bytes) grid = 2 * sms;
+    if (INVERSE) {
+        auto kern = plane_c2r_kernel<real, N, N>;
+        HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>((const Cx<real>*)in, (Cx<real>*)c->plane_scratch, (real*)out,
+                                             (const Cx<real>*)c->ytw, (const Cx<real>*)c->ztw, p);
+    } else {
+        auto kern = plane_r2c_kernel<real, N, N>;
+        HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>((const real*)in, (Cx<real>*)c->plane_scratch, (Cx<real>*)out,
+                                             (const Cx<real>*)c->ytw, (const Cx<real>*)c->ztw, p);
+    }
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
+}
+
+template <typename real, bool INVERSE>
+static int dispatch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
+    switch (c->g.Ny) {
+        case 16: return launch_plane<real, 16, INVERSE>(c, in, out, p, s);
+        case 32: return launch_plane<real, 32, INVERSE>(c, in, out, p, s);
+        case 64: return launch_plane<real, 64, INVERSE>(c, in, out, p, s);
+        case 128: return launch_plane<real, 128, INVERSE>(c, in, out, p, s);
+        case 256: return launch_plane<real, 256, INVERSE>(c, in, out, p, s);
+        default: break;
+    }
+    if (sizeof(real) == 4 && c->g.Ny == 512) return launch_plane<float, 512, INVERSE>(c, in, out, p, s);
+    set_error("plane transform: unsupported plane %d x %d", c->g.Ny, c->g.Nz);
+    return HYMD_ERR_INVALID;
+}
+
+// real [f][plane][Ny][Nz] (strides r_*) -> spectra [f][plane][Ny][Nzcp] (strides k_*)
+int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int nplanes, void* k_out,
+                  long long k_fs, cudaStream_t s) {
+    const Geometry& g = c->g;
+    PlaneParams p;
+    p.nunits = F * nplanes; p.nplanes = nplanes;
+    p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
+    p.r_fs = r_fs; p.r_xs = (long long)g.Ny * g.Nz; p.r_ys = g.Nz;
+    p.ghost = 0; p.xdup_plane = -1;
+    return c->f64 ? dispatch_plane<double, false>(c, real_in, k_out, p, s)
+                  : dispatch_plane<float, false>(c, real_in, k_out, p, s);
+}
+
+// spectra [f][plane][Ny][Nzcp] -> real planes; ghost: the ghost-padded force-mesh layout with the
+// periodic y/z images (and plane 0 duplicated into plane nxl on a single GPU)
+int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int nplanes, void* real_out,
+                  bool ghost, cudaStream_t s) {
+    const Geometry& g = c->g;
+    PlaneParams p;
+    p.nunits = F * nplanes; p.nplanes = nplanes;
+    p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
+    if (ghost) {
+        p.r_ys = g.Nzp; p.r_xs = (long long)(g.Ny + 1) * g.Nzp; p.r_fs = g.ghost_elems;
+        p.ghost = 1; p.xdup_plane = g.P == 1 ? g.nxl : -1;
+    } else {
+        p.r_ys = g.Nz; p.r_xs = (long long)g.Ny * g.Nz; p.r_fs = g.real_elems;
+        p.ghost = 0; p.xdup_plane = -1;
+    }
+    return c->f64 ? dispatch_plane<double, true>(c, k_in, real_out, p, s)
+                  : dispatch_plane<float, true>(c, k_in, real_out, p, s);
+}
+
+}  // namespace hymd

@@ -231,6 +231,25 @@ static int transpose_inverse(hymd_ctx* c, int F, void* k_in, cudaStream_t s) {
     return HYMD_OK;
 }
 
+// 2-D (y,z) transforms of the local planes: the one-pass plane kernels (planefft.cu) when the
+// plane size is supported, batched cuFFT 2-D plans otherwise.
+static int yz_forward(hymd_ctx* c, void* real_in, int F, void* k_out, long long k_fs, cudaStream_t s) {
+    const Geometry& g = c->g;
+    if (c->plane) return plane_forward(c, real_in, g.real_elems, F, g.nxl, k_out, k_fs, s);
+    cufftHandle h;
+    HYMD_CHECK(plan_get(c, PK_2D_R2C, F, &h));
+    return exec_r2c(c, h, real_in, k_out, s);
+}
+
+static int yz_inverse(hymd_ctx* c, void* k_in, long long k_fs, int F, void* real_out, bool ghost,
+                      cudaStream_t s) {
+    const Geometry& g = c->g;
+    if (c->plane) return plane_inverse(c, k_in, k_fs, F, g.nxl, real_out, ghost, s);
+    cufftHandle h;
+    HYMD_CHECK(plan_get(c, ghost ? PK_2D_C2R_GHOST : PK_2D_C2R, F, &h));
+    return exec_c2r(c, h, k_in, real_out, s);
+}
+
 // ---- public transforms ------------------------------------------------------------------------
 int fft_forward(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s) {
     const Geometry& g = c->g;
@@ -241,18 +260,13 @@ int fft_forward(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s) 
     }
     const size_t csz = 2 * c->rsz;
     const KLayout l = klayout(c, F);
+    HYMD_CHECK(fft_forward_yz(c, real_in, F, k_out, s));
     if (g.P == 1) {
-        HYMD_CHECK(plan_get(c, PK_2D_R2C, F, &h));
-        HYMD_CHECK(exec_r2c(c, h, real_in, k_out, s));
         HYMD_CHECK(plan_get(c, PK_1D_FWD_INV, 1, &h));
         for (int f = 0; f < F; ++f)
             HYMD_CHECK(exec_c2c(c, h, (char*)k_out + (size_t)f * l.fs * csz, CUFFT_FORWARD, s));
         return HYMD_OK;
     }
-    HYMD_CHECK(ensure_work(c, F));
-    HYMD_CHECK(plan_get(c, PK_2D_R2C, F, &h));
-    HYMD_CHECK(exec_r2c(c, h, real_in, c->wA, s));
-    HYMD_CHECK(transpose_forward(c, F, k_out, s));
     HYMD_CHECK(plan_get(c, PK_1D_FWD_INV, F, &h));
     return exec_c2c(c, h, k_out, CUFFT_FORWARD, s);
 }
@@ -260,11 +274,10 @@ int fft_forward(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s) 
 // Forward transform over y and z only (the fused x-line kernel does the rest): k_out receives
 // the k layout with x still in real space.
 int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s) {
-    cufftHandle h;
-    HYMD_CHECK(plan_get(c, PK_2D_R2C, F, &h));
-    if (c->g.P == 1) return exec_r2c(c, h, real_in, k_out, s);
+    const Geometry& g = c->g;
+    if (g.P == 1) return yz_forward(c, real_in, F, k_out, klayout(c, F).fs, s);
     HYMD_CHECK(ensure_work(c, F));
-    HYMD_CHECK(exec_r2c(c, h, real_in, c->wA, s));
+    HYMD_CHECK(yz_forward(c, real_in, F, c->wA, (long long)(g.nxl + 1) * g.Ny * g.Nzcp, s));
     return transpose_forward(c, F, k_out, s);
 }
 
@@ -278,18 +291,17 @@ static int copy_to_work(hymd_ctx* c, const void* k_in, int F, cudaStream_t s) {
 }
 
 int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s) {
-    // the x transform has been applied; k_in is in the k layout (P > 1) or, for P == 1, already
-    // in the work layout the 2-D plans read
+    // the x transform has been applied.  P > 1: k_in is in the k layout and goes through the
+    // inverse transpose into the work layout.  P == 1: k_in is the work layout [f][Nx+1][Ny][Nzcp]
+    // for ghost outputs and the k layout [f][Nx][Ny][Nzcp] otherwise.
     const Geometry& g = c->g;
-    cufftHandle h;
-    void* src = k_in;
+    const long long plane = (long long)g.Ny * g.Nzcp;
     if (g.P > 1) {
         HYMD_CHECK(ensure_work(c, F));
         HYMD_CHECK(transpose_inverse(c, F, k_in, s));
-        src = c->wA;
+        return yz_inverse(c, c->wA, (g.nxl + 1) * plane, F, real_out, ghost, s);
     }
-    HYMD_CHECK(plan_get(c, ghost ? PK_2D_C2R_GHOST : PK_2D_C2R, F, &h));
-    return exec_c2r(c, h, src, real_out, s);
+    return yz_inverse(c, k_in, (ghost ? g.Nx + 1 : g.Nx) * plane, F, real_out, ghost, s);
 }
 
 int fft_inverse(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s) {

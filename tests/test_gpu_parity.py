@@ -58,7 +58,10 @@ def test_paint_matches_oracle(dtype, mesh):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("mesh,n", [([24, 24, 24], 10000), ([16, 12, 10], 700), ([9, 12, 10], 500),
                                     ([32, 40, 64], 20000), ([64, 48, 40], 30000),
-                                    ([128, 16, 24], 8000), ([256, 10, 12], 6000)])
+                                    ([128, 16, 24], 8000), ([256, 10, 12], 6000),
+                                    # power-of-two square (y,z) planes: one-pass plane transforms
+                                    ([16, 16, 16], 3000), ([32, 64, 64], 20000), ([64, 32, 32], 9000),
+                                    ([128, 128, 128], 60000), ([16, 256, 256], 30000)])
 def test_field_forces_match_oracle(dtype, mesh, n):
     from gpu_common import GpuRun, OracleRun, rel_err
     cfg, pos, types, _ = _system(n, mesh, [4.0, 5.0, 6.0], dtype, seed=1)
@@ -73,7 +76,8 @@ def test_field_forces_match_oracle(dtype, mesh, n):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("kind,mesh", [("DefaultNoChi", [20, 24, 28]), ("SquaredPhi", [20, 24, 28]),
                                        ("DefaultWithChi", [20, 24, 28]),
-                                       ("DefaultWithChi", [32, 24, 28]), ("DefaultNoChi", [64, 20, 18])])
+                                       ("DefaultWithChi", [32, 24, 28]), ("DefaultNoChi", [64, 20, 18]),
+                                       ("DefaultWithChi", [32, 64, 64]), ("DefaultWithChi", [16, 128, 128])])
 def test_energies_and_potentials_match_oracle(dtype, kind, mesh):
     """compute_potential=True path: filtered densities, v_ext and the field energy
     (field.py:578, 615-616, 692-693); power-of-two Nx runs the fused x-line kernel."""
@@ -101,7 +105,7 @@ def test_energies_and_potentials_match_oracle(dtype, kind, mesh):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("mesh", [[24, 20, 28], [32, 20, 28], [128, 12, 16]])
+@pytest.mark.parametrize("mesh", [[24, 20, 28], [32, 20, 28], [128, 12, 16], [32, 32, 32], [64, 128, 128]])
 def test_pme_matches_oracle(dtype, mesh):
     from gpu_common import GpuRun, OracleRun, rel_err
     from hymd_b200.field import compute_self_energy_q

@@ -54,6 +54,10 @@ def parse_args():
     ap.add_argument("--mesh", type=int, default=None, help="override mesh size (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-dd", action="store_true",
+                    help="skip the start-up domain_decomposition call (main.py:274-300): the "
+                         "particles then stay in the generator's molecule order instead of the "
+                         "mesh-cell order domain_decomposition hands back")
     return ap.parse_args()
 
 
@@ -285,13 +289,20 @@ def main():
         mine = (cell // (mesh[0] // world)) == rank
         pos_h, typ_h = pos_h[mine], typ_h[mine]
         q_h = None if q_h is None else q_h[mine]
+    vel_h = sysm.velocities[mine] if world > 1 else sysm.velocities
+    if not args.no_dd:
+        # what main.py does once at start-up (and every config.domain_decomposition steps) when
+        # the option is set: all per-particle arrays come back permuted identically
+        extra = (vel_h, typ_h) if q_h is None else (vel_h, typ_h, q_h)
+        out = F.domain_decomposition(pos_h, pm, *extra)
+        pos_h, vel_h, typ_h = out[0], out[1], out[2]
+        q_h = None if q_h is None else out[3]
     n_loc = len(pos_h)
     dev = pm.device
     # MD-like input stream: step k sees the positions of step k-1 displaced by one outer step of
     # thermal motion (v * respa_inner * time_step, ~0.05 nm = 12 % of a cell), so every step
     # re-bins genuinely different coordinates.  NBUF trajectories frames, visited ping-pong.
     NBUF = 6
-    vel_h = sysm.velocities[mine] if world > 1 else sysm.velocities
     L = np.asarray(cfg.box_size, dtype=np.float64)
     frames_h = []
     for k in range(NBUF):
@@ -441,7 +452,10 @@ def main():
                                f"T={T} (U={U} distinct potential rows), sigma={cfg.sigma}, "
                                f"kappa={cfg.kappa}, DefaultWithChi" + (", PME" if pme else ""),
                    "inputs": f"{NBUF} trajectory frames visited ping-pong, consecutive frames differ by "
-                             "one outer step of thermal motion (0.25 ps at 323 K, ~0.05 nm)",
+                             "one outer step of thermal motion (0.25 ps at 323 K, ~0.05 nm); particle "
+                             "order: " + ("generator (molecule) order" if args.no_dd else
+                                          "as returned by the start-up domain_decomposition call "
+                                          "(mesh-cell order of frame 0, main.py:274-300)"),
                    "l2": "inputs larger than L2 (per-step working set "
                          f"{total_alg / 1e6:.0f} MB vs 126 MB L2), no flush",
                    "parallelism": "single GPU" if world == 1 else f"{world} x-slabs (slab FFT, NCCL all-to-all)"},

@@ -192,6 +192,7 @@ struct hymd_ctx {
     // readout TMA
     CUtensorMap tmap_gmesh, tmap_emesh;
     int rtx, rty, rtz, rbz;       // readout tile and box z extent
+    int rstages;                  // box buffers in the readout TMA ring
     size_t readout_smem, readout_smem_pme;
 
     int64_t launches;

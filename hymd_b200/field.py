@@ -170,31 +170,69 @@ def compute_field_and_kinetic_energy(phi, phi_q, psi, velocity, hamiltonian, pos
     return field_energy, kinetic, field_q_energy
 
 
+def _first_atom_positions(pm, positions, molecules):
+    """Routing positions with molecules: every atom follows the first atom of its molecule
+    (``field.py:1156-1163``)."""
+    mol = torch.as_tensor(np.asarray(molecules)) if not isinstance(molecules, torch.Tensor) \
+        else molecules
+    mol = mol.to(pm.device).long().reshape(-1)
+    pos = pm.as_device(positions)
+    n = mol.shape[0]
+    uniq, inv = torch.unique(mol, return_inverse=True)
+    first = torch.full((uniq.shape[0],), n, dtype=torch.long, device=pm.device)
+    first.scatter_reduce_(0, inv, torch.arange(n, device=pm.device), reduce="amin")
+    return pos[first[inv]]
+
+
+def _cell_order(pm, route):
+    """Stable permutation sorting the local particles by the mesh cell of their routing
+    position (x slowest, z fastest = the storage order of the meshes)."""
+    mesh = torch.as_tensor(np.asarray(pm.Nmesh, dtype=np.int64), device=pm.device)
+    scale = torch.as_tensor(np.asarray(pm.Nmesh, dtype=np.float64) / np.asarray(pm.BoxSize, dtype=np.float64),
+                            device=pm.device)
+    c = torch.remainder(torch.floor(route.double() * scale).long(), mesh)
+    key = (c[:, 0] * mesh[1] + c[:, 1]) * mesh[2] + c[:, 2]
+    return torch.sort(key, stable=True).indices
+
+
+def _take_rows(a, perm):
+    if isinstance(a, torch.Tensor):
+        return a[perm.to(a.device)]
+    return np.asarray(a)[perm.cpu().numpy()]
+
+
 def domain_decomposition(positions, pm, *args, molecules=None, bonds=None, topol=False, verbose=0,
                          comm=None):
-    """Re-home particles on the rank owning their slab (``field.py:1115-1178``).  With one
-    GPU every particle is already home and the inputs are returned unchanged."""
+    """Re-home particles on the rank owning their slab (``field.py:1115-1178``) and hand the
+    per-particle arrays back in mesh-cell order.
+
+    Like the reference's ``Layout.exchange`` the call returns every array permuted identically;
+    the order itself is implementation defined there (it depends on the rank layout).  Here it
+    is the cell order of the routing position (molecules stay contiguous and keep their internal
+    order: all atoms are keyed by the first atom, stable sort), so that until the next call the
+    caller's particle order stays close to the order the field kernels stream in: the position
+    gather of the cell binning and the force write-back of ``compute_field_force`` then touch
+    neighbouring addresses.  ``HYMD_B200_DD_CELL_ORDER=0`` keeps the incoming order instead."""
+    import os
     if molecules is not None:
         if not topol:
             assert bonds is not None, "bonds must be provided with molecules"
             args = (*args, bonds, molecules)
         else:
             args = (*args, molecules)
-    if pm.world_size == 1:
-        return (positions, *args)
-    route = None
-    if molecules is not None:
-        # every atom follows the first atom of its molecule (field.py:1156-1163)
-        mol = torch.as_tensor(np.asarray(molecules)) if not isinstance(molecules, torch.Tensor) \
-            else molecules
-        mol = mol.to(pm.device).long().reshape(-1)
-        pos = pm.as_device(positions)
-        n = mol.shape[0]
-        uniq, inv = torch.unique(mol, return_inverse=True)
-        first = torch.full((uniq.shape[0],), n, dtype=torch.long, device=pm.device)
-        first.scatter_reduce_(0, inv, torch.arange(n, device=pm.device), reduce="amin")
-        route = pos[first[inv]]
-    return pm.migrate(positions, *args, routing_positions=route)
+    arrays = (positions, *args)
+    if pm.world_size > 1:
+        route = None if molecules is None else _first_atom_positions(pm, positions, molecules)
+        arrays = pm.migrate(positions, *args, routing_positions=route)
+    if os.environ.get("HYMD_B200_DD_CELL_ORDER", "1") != "0" and len(arrays[0]) > 0:
+        if molecules is None:
+            route = pm.as_device(arrays[0])
+        else:
+            route = _first_atom_positions(pm, arrays[0], arrays[-1])
+        perm = _cell_order(pm, route)
+        arrays = tuple(_take_rows(a, perm) for a in arrays)
+        pm.reset_order()
+    return tuple(arrays)
 
 
 def _allreduce(t):

@@ -378,6 +378,12 @@ class ParticleMesh:
     def launch_count(self):
         return int(self.lib.hymd_launch_count(self._ctx))
 
+    def reset_order(self):
+        """Forget the cached cell order / bins (the caller's particle order changed)."""
+        self._sort_key = None
+        self._order_types_key = None
+        _lib.check(self.lib.hymd_ctx_reset_order(self._ctx))
+
     def _allreduce_scalar(self, s):
         dist = _dist()
         if dist and self.world_size > 1:

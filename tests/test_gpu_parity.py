@@ -235,3 +235,46 @@ def test_consecutive_steps_reuse_previous_order(dtype):
     o = OracleRun(cfg, pos, types, charges=q)
     assert rel_err(g.forces(), o.force) < TOL[dtype]
     assert rel_err(g.eforces(), o.elec_forces) < TOL[dtype]
+
+
+def test_domain_decomposition_returns_cell_order_single_gpu():
+    """domain_decomposition (field.py:1115-1178) permutes every per-particle array identically;
+    this implementation hands them back in mesh-cell order with molecules contiguous and in
+    their internal order.  Forces computed on the permuted arrays are the same particles'
+    forces; numpy in -> numpy out, torch in -> torch out."""
+    from gpu_common import GpuRun
+    from hymd_b200 import field as F
+    cfg, pos, types, _ = _system(6000, [16, 16, 16], [3.0, 3.0, 3.0], np.float64, seed=21)
+    n = len(pos)
+    rng = np.random.default_rng(5)
+    # molecules of 1..6 consecutive atoms, atoms of a molecule close to its first atom
+    sizes = rng.integers(1, 7, size=n)
+    mol = np.repeat(np.arange(n), sizes)[:n].astype(np.int32)
+    first = np.concatenate([[0], np.nonzero(np.diff(mol))[0] + 1])
+    start_of = first[np.searchsorted(first, np.arange(n), side="right") - 1]
+    pos = np.mod(pos[start_of] + rng.normal(scale=0.05, size=pos.shape), cfg.box_size.astype(np.float64))
+    gid = np.arange(n, dtype=np.int64)
+    bonds = rng.integers(-1, 5, size=(n, 3)).astype(np.int32)
+    ref = GpuRun(cfg, pos, types)
+    out = F.domain_decomposition(pos, ref.pm, types, gid, molecules=mol, bonds=bonds)
+    p2, t2, g2, b2, m2 = out
+    assert all(isinstance(a, np.ndarray) for a in out)
+    assert np.array_equal(np.sort(g2), gid)
+    assert np.array_equal(p2, pos[g2]) and np.array_equal(t2, types[g2])
+    assert np.array_equal(b2, bonds[g2]) and np.array_equal(m2, mol[g2])
+    # molecules contiguous, atoms in their original order
+    change = np.nonzero(np.diff(m2))[0] + 1
+    assert len(change) + 1 == len(np.unique(mol))
+    assert (np.diff(g2)[np.diff(m2) == 0] == 1).all()
+    # first atoms are in mesh-cell order
+    firsts = np.concatenate([[0], change])
+    c = np.floor(p2[firsts] * 16 / 3.0).astype(np.int64) % 16
+    key = (c[:, 0] * 16 + c[:, 1]) * 16 + c[:, 2]
+    assert (np.diff(key) >= 0).all()
+    g = GpuRun(cfg, p2, t2)
+    assert np.array_equal(g.forces(), ref.forces()[g2])
+    # torch tensors in -> torch tensors out, same permutation
+    outt = F.domain_decomposition(torch.as_tensor(pos, device="cuda"), ref.pm,
+                                  torch.as_tensor(gid, device="cuda"))
+    assert isinstance(outt[0], torch.Tensor) and outt[0].is_cuda
+    assert np.array_equal(np.sort(outt[1].cpu().numpy()), gid)

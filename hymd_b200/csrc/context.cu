@@ -231,6 +231,8 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     c->slab = P > 1 || c->fused || (force_slab && force_slab[0] == '1');
     c->plane = c->slab && plane_supported(c);
     if (P > 1 && (st = comm_create(c, nccl_id))) return fail(st);
+    const char* nccl_x = getenv("HYMD_B200_NCCL_EXCHANGE");
+    c->p2p = P > 1 && !(nccl_x && nccl_x[0] == '1');
     if ((st = readout_setup(c))) return fail(st);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(HYMD_ERR_CUDA);
     *out = c;

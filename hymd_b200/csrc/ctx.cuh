@@ -67,6 +67,8 @@ struct __align__(16) Rec32 {
 struct __align__(16) Rec64 {
     unsigned long long ux, uy, uz, meta;
 };
+enum PeerBuffer : unsigned { PEER_WORK = 1u, PEER_HALO = 2u, PEER_K = 4u, PEER_MESH = 8u };
+constexpr int HYMD_MAX_PEERS = 8;    // slabs (GPUs of one NVLink domain)
 constexpr int REC32_IDX_BITS = 27;  // <= 134M particles per GPU, <= 32 types
 constexpr int REC64_IDX_BITS = 40;
 
@@ -187,6 +189,10 @@ struct hymd_ctx {
     void* halo;             // ghost-plane exchange staging
     size_t halo_bytes;
     hymd::Comm* comm;       // NCCL communicator (world_size > 1)
+    bool p2p;               // exchanges store into peer memory over NVLink (CUDA IPC) instead of NCCL send/recv
+    unsigned peer_busy;     // PEER_* buffers whose local consumers were enqueued after the last barrier:
+                            // a peer may not overwrite them before another barrier (same call sequence
+                            // on every rank, so the flags agree)
     hymd::MigrateState* mig;
 
     // readout TMA
@@ -276,6 +282,8 @@ int comm_ring(hymd_ctx* c, int dir, void* const* sendp, void* const* recvp, int 
               cudaStream_t s);
 int comm_alltoallv(hymd_ctx* c, const void* send, const size_t* send_off, const size_t* send_bytes,
                    void* recv, const size_t* recv_off, const size_t* recv_bytes, cudaStream_t s);
+int comm_peer_ptrs(hymd_ctx* c, void* local, void** peers, cudaStream_t s);
+int comm_barrier(hymd_ctx* c, cudaStream_t s);
 int comm_allgather_host(hymd_ctx* c, const void* mine, void* all, size_t bytes, cudaStream_t s);
 // readout.cu
 int readout_setup(hymd_ctx* c);

@@ -54,8 +54,10 @@ static int grow(void** p, size_t* have, size_t want) {
 int ensure_work(hymd_ctx* c, int F) {
     const Geometry& g = c->g;
     const size_t csz = 2 * c->rsz;
+    // peer-mapped buffers must never be re-allocated: size them for the largest batch (3T fields)
+    if (c->p2p && F < 3 * c->T) F = 3 * c->T;
     HYMD_CHECK(grow(&c->wA, &c->wA_bytes, (size_t)F * (g.nxl + 1) * g.Ny * g.Nzcp * csz));
-    if (g.P > 1) HYMD_CHECK(grow(&c->wS, &c->wS_bytes, (size_t)F * g.nxl * g.Ny * g.Nzcp * csz));
+    if (g.P > 1 && !c->p2p) HYMD_CHECK(grow(&c->wS, &c->wS_bytes, (size_t)F * g.nxl * g.Ny * g.Nzcp * csz));
     return HYMD_OK;
 }
 
@@ -207,8 +209,80 @@ static unsigned int stream_grid(long long n) {
     return (unsigned int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// ---- exchange over NVLink peer memory ------------------------------------------------------------
+// The pack / unpack kernels store straight into the destination rank's buffer (mapped through
+// CUDA IPC), so the transpose is ONE pass: read local HBM, write remote HBM over NVLink, no
+// staging buffer, no separate unpack, every SM drives the links.  A barrier (comm_barrier) after
+// the kernel makes the data visible to the consumers.  16-byte accesses (Nzcp is even).
+struct PeerPtrs {
+    void* p[HYMD_MAX_PEERS];
+};
+
+// forward: A[f][xl'][ky][kz] (nxl+1 planes per field)  ->  rank q = ky / nyl:
+//          K_q[(x0 + xl)][f][kyl][kz]   (the k layout of the receiver)
+template <typename vec, int CPV>
+__global__ void __launch_bounds__(256) pack_push_kernel(const vec* __restrict__ A, PeerPtrs K, PackParams p) {
+    const int rowv = p.Nzcp / CPV;                       // 16-byte vectors per spectrum row
+    const long long total = p.total / CPV, stride = (long long)gridDim.x * blockDim.x;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += stride) {
+        long long r = o;
+        const int kv = (int)(r % rowv); r /= rowv;
+        const int ky = (int)(r % p.Ny); r /= p.Ny;
+        const int xl = (int)(r % p.nxl);
+        const int f = (int)(r / p.nxl);
+        const int q = ky / p.nyl, kyl = ky % p.nyl;
+        const vec v = A[(((long long)f * (p.nxl + 1) + xl) * p.Ny + ky) * rowv + kv];
+        vec* dst = reinterpret_cast<vec*>(K.p[q]);
+        dst[((long long)(p.x0 + xl) * p.xs + f * p.fs + (long long)kyl * p.Nzcp) / CPV + kv] = v;
+    }
+}
+
+// inverse: local K[x][f][kyl][kz]  ->  rank q = x / nxl:  A_q[f][xl][ky = rank*nyl + kyl][kz]
+template <typename vec, int CPV>
+__global__ void __launch_bounds__(256) unpack_push_kernel(const vec* __restrict__ Kl, PeerPtrs A, PackParams p) {
+    const int rowv = p.Nzcp / CPV;
+    const long long total = p.total / CPV, stride = (long long)gridDim.x * blockDim.x;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < total; o += stride) {
+        long long r = o;
+        const int kv = (int)(r % rowv); r /= rowv;
+        const int kyl = (int)(r % p.nyl); r /= p.nyl;
+        const int f = (int)(r % p.F);
+        const int x = (int)(r / p.F);
+        const int q = x / p.nxl, xl = x % p.nxl;
+        const vec v = Kl[((long long)x * p.xs + f * p.fs + (long long)kyl * p.Nzcp) / CPV + kv];
+        vec* dst = reinterpret_cast<vec*>(A.p[q]);
+        dst[(((long long)f * (p.nxl + 1) + xl) * p.Ny + (p.rank * p.nyl + kyl)) * rowv + kv] = v;
+    }
+}
+
+static int peer_table(hymd_ctx* c, void* local, PeerPtrs* t, cudaStream_t s) {
+    memset(t, 0, sizeof(*t));
+    return comm_peer_ptrs(c, local, t->p, s);
+}
+
+// Before storing into a peer's buffer: its previous contents must have been consumed there.
+// Normally another barrier of the cycle has passed since (peer_busy cleared); back-to-back
+// transforms (by-product materialisation) need an extra one.
+static int peer_acquire(hymd_ctx* c, unsigned which, cudaStream_t s) {
+    if (c->peer_busy & which) return comm_barrier(c, s);
+    return HYMD_OK;
+}
+
 static int transpose_forward(hymd_ctx* c, int F, void* k_out, cudaStream_t s) {
     const PackParams p = make_pack(c, F);
+    if (c->p2p) {
+        PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+        PeerPtrs K;
+        HYMD_CHECK(peer_table(c, k_out, &K, s));
+        HYMD_CHECK(peer_acquire(c, PEER_K, s));
+        const unsigned int grid = stream_grid(p.total / 2);
+        if (c->f64) pack_push_kernel<double2, 1><<<grid, 256, 0, s>>>((const double2*)c->wA, K, p);
+        else pack_push_kernel<float4, 2><<<grid, 256, 0, s>>>((const float4*)c->wA, K, p);
+        HYMD_LAUNCH_CHECK(c);
+        HYMD_CHECK(comm_barrier(c, s));
+        c->peer_busy |= PEER_K;
+        return HYMD_OK;
+    }
     if (c->f64) pack_kernel<double2><<<stream_grid(p.total), 256, 0, s>>>(
         (const double2*)c->wA, (double2*)c->wS, (double2*)k_out, p);
     else pack_kernel<float2><<<stream_grid(p.total), 256, 0, s>>>(
@@ -221,6 +295,19 @@ static int transpose_forward(hymd_ctx* c, int F, void* k_out, cudaStream_t s) {
 
 static int transpose_inverse(hymd_ctx* c, int F, void* k_in, cudaStream_t s) {
     const PackParams p = make_pack(c, F);
+    if (c->p2p) {
+        PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+        PeerPtrs A;
+        HYMD_CHECK(peer_table(c, c->wA, &A, s));
+        HYMD_CHECK(peer_acquire(c, PEER_WORK, s));
+        const unsigned int grid = stream_grid(p.total / 2);
+        if (c->f64) unpack_push_kernel<double2, 1><<<grid, 256, 0, s>>>((const double2*)k_in, A, p);
+        else unpack_push_kernel<float4, 2><<<grid, 256, 0, s>>>((const float4*)k_in, A, p);
+        HYMD_LAUNCH_CHECK(c);
+        HYMD_CHECK(comm_barrier(c, s));
+        c->peer_busy |= PEER_WORK;
+        return HYMD_OK;
+    }
     const size_t block = (size_t)p.total / p.P * 2 * c->rsz;
     HYMD_CHECK(comm_alltoall(c, k_in, c->wS, block, s));
     if (c->f64) unpack_kernel<double2><<<stream_grid(p.total), 256, 0, s>>>(
@@ -346,14 +433,29 @@ int halo_reduce(hymd_ctx* c, void* fields, int F, cudaStream_t s) {
     if (g.P == 1) return HYMD_OK;
     PhaseScope ps(c, HYMD_PHASE_HALO, s);
     const long long plane = (long long)g.Ny * g.Nz;
-    HYMD_CHECK(grow(&c->halo, &c->halo_bytes, (size_t)F * plane * c->rsz));
-    void* sp[HYMD_MAX_TYPES];
-    void* rp[HYMD_MAX_TYPES];
-    for (int f = 0; f < F; ++f) {
-        sp[f] = (char*)fields + ((size_t)f * g.real_elems + (size_t)g.nxl * plane) * c->rsz;
-        rp[f] = (char*)c->halo + (size_t)f * plane * c->rsz;
+    // sized once for T fields: the buffer is mapped into the neighbour
+    HYMD_CHECK(grow(&c->halo, &c->halo_bytes, (size_t)(c->T > F ? c->T : F) * plane * c->rsz));
+    if (c->p2p) {
+        PeerPtrs H;
+        HYMD_CHECK(peer_table(c, c->halo, &H, s));
+        HYMD_CHECK(peer_acquire(c, PEER_HALO, s));
+        const int to = (g.rank + 1) % g.P;
+        // ghost plane nxl of every field -> the next slab's staging buffer, over NVLink
+        HYMD_CUDA(cudaMemcpy2DAsync(H.p[to], (size_t)plane * c->rsz,
+                                    (char*)fields + (size_t)g.nxl * plane * c->rsz,
+                                    (size_t)g.real_elems * c->rsz, (size_t)plane * c->rsz, F,
+                                    cudaMemcpyDeviceToDevice, s));
+        HYMD_CHECK(comm_barrier(c, s));
+        c->peer_busy |= PEER_HALO;
+    } else {
+        void* sp[HYMD_MAX_TYPES];
+        void* rp[HYMD_MAX_TYPES];
+        for (int f = 0; f < F; ++f) {
+            sp[f] = (char*)fields + ((size_t)f * g.real_elems + (size_t)g.nxl * plane) * c->rsz;
+            rp[f] = (char*)c->halo + (size_t)f * plane * c->rsz;
+        }
+        HYMD_CHECK(comm_ring(c, +1, sp, rp, F, (size_t)plane * c->rsz, s));
     }
-    HYMD_CHECK(comm_ring(c, +1, sp, rp, F, (size_t)plane * c->rsz, s));
     if (c->f64) halo_add_kernel<double><<<stream_grid(plane * F), 256, 0, s>>>(
         (double*)fields, (const double*)c->halo, F, plane, g.real_elems);
     else halo_add_kernel<float><<<stream_grid(plane * F), 256, 0, s>>>(
@@ -367,6 +469,19 @@ int halo_fetch(hymd_ctx* c, void* meshes, int F, cudaStream_t s) {
     const Geometry& g = c->g;
     if (g.P == 1) return HYMD_OK;
     const size_t plane = (size_t)(g.Ny + 1) * g.Nzp * c->rsz;
+    if (c->p2p) {
+        // push: my plane 0 is the ghost plane of the previous slab
+        PeerPtrs M;
+        HYMD_CHECK(peer_table(c, meshes, &M, s));
+        HYMD_CHECK(peer_acquire(c, PEER_MESH, s));
+        const int to = (g.rank - 1 + g.P) % g.P;
+        HYMD_CUDA(cudaMemcpy2DAsync((char*)M.p[to] + (size_t)g.nxl * plane, (size_t)g.ghost_elems * c->rsz,
+                                    meshes, (size_t)g.ghost_elems * c->rsz, plane, F,
+                                    cudaMemcpyDeviceToDevice, s));
+        HYMD_CHECK(comm_barrier(c, s));
+        c->peer_busy |= PEER_MESH;
+        return HYMD_OK;
+    }
     void* sp[3 * HYMD_MAX_TYPES];
     void* rp[3 * HYMD_MAX_TYPES];
     for (int f = 0; f < F; ++f) {

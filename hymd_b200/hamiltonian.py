@@ -29,7 +29,9 @@ class Hamiltonian:
     def _setup(self):
         cfg = self.config
         if getattr(cfg, "simulation_volume", None) is None:
-            cfg.simulation_volume = float(np.prod(np.asarray(cfg.box_size, dtype=np.float64)))
+            # the product is taken in box_size's own dtype (float32 from the input parser,
+            # input_parser.py:736), exactly like hamiltonian.py:40
+            cfg.simulation_volume = float(np.prod(np.asarray(cfg.box_size)))
         if not getattr(cfg, "barostat", None):
             cfg.rho0 = cfg.n_particles / cfg.simulation_volume
             cfg.a = cfg.rho0

@@ -37,6 +37,14 @@ def test_slab_pipeline_single_gpu(dtype, mesh):
          {"HYMD_B200_FORCE_SLAB": "1"})
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_slab_pipeline_plane_kernels_single_gpu(dtype):
+    """Power-of-two square (y,z) planes: the one-pass plane transforms inside the unfused slab
+    pipeline (cuFFT only along x)."""
+    _run(1, ["--dtype", dtype, "--pme", "--mesh", "24", "32", "32", "--particles", "6000"],
+         {"HYMD_B200_FORCE_SLAB": "1"})
+
+
 def _need(n):
     if torch.cuda.device_count() < n:
         pytest.skip(f"needs {n} GPUs")
@@ -46,6 +54,13 @@ def _need(n):
 def test_two_slabs_match_oracle(dtype):
     _need(2)
     _run(2, ["--dtype", dtype, "--pme"])
+
+
+@pytest.mark.parametrize("mesh", [[32, 32, 32], [16, 64, 64]])
+def test_two_slabs_plane_kernels(mesh):
+    """Plane transforms + fused x-line kernel on two slabs."""
+    _need(2)
+    _run(2, ["--dtype", "f32", "--pme", "--mesh"] + [str(m) for m in mesh] + ["--particles", "20000"])
 
 
 def test_two_slabs_unfused_path():

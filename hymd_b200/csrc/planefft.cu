@@ -136,39 +136,57 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_c2r_kerne
         const int f = unit / p.nplanes, x = unit % p.nplanes;
         const Cx<real>* src = in + f * p.k_fs + x * p.k_xs;
         // ---------------- column phase: inverse FFT along y ----------------
-        int it = 0;
-        for (int ch = (g + unit) % NG; ch < NCHG; ch += NG, ++it) {
-            Cx<real>* cur = gtile + (it & (NTILE - 1)) * LA::ELEMS;
-            const int c0 = ch * CG;
-            for (int task = gt; task < CG * R1y; task += GT) {
+        // (the spectrum comes from HBM: the next chunk's butterfly inputs are loaded into a second
+        // register set while the current chunk is transformed)
+        {
+            constexpr bool ONE_TASK = (CG * R1y <= GT) && sizeof(real) == 4 && R2y <= 16;   // one step-A task per thread: prefetchable
+            Cx<real> nx[R2y];
+            auto load_chunk = [&](int ch, int task, Cx<real> (&dst)[R2y]) {
                 const int c = task % CG, k1 = task / CG;
-                const bool valid = c0 + c < NZC;
-                Cx<real> v[R2y];
+                const bool valid = ch < NCHG && task < CG * R1y && ch * CG + c < NZC;
 #pragma unroll
                 for (int k2 = 0; k2 < R2y; ++k2)
-                    v[k2] = valid ? ld_stream(src + (long long)(k1 + R1y * k2) * NZCP + c0 + c) : Cx<real>{0, 0};
-                dft_reg<real, R2y, +1>(v);
+                    dst[k2] = valid ? ld_stream(src + (long long)(k1 + R1y * k2) * NZCP + ch * CG + c) : Cx<real>{0, 0};
+            };
+            int it = 0;
+            const int ch0 = (g + unit) % NG;
+            if (ONE_TASK) load_chunk(ch0, gt, nx);
+            for (int ch = ch0; ch < NCHG; ch += NG, ++it) {
+                Cx<real>* cur = gtile + (it & (NTILE - 1)) * LA::ELEMS;
+                const int c0 = ch * CG;
+                for (int task = gt; task < CG * R1y; task += GT) {
+                    const int c = task % CG, k1 = task / CG;
+                    Cx<real> v[R2y];
+                    if (ONE_TASK) {
 #pragma unroll
-                for (int n2 = 0; n2 < R2y; ++n2) {
-                    Cx<real> w = twy[(n2 * k1) & (NY - 1)];
-                    w.y = -w.y;
-                    cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                        for (int k2 = 0; k2 < R2y; ++k2) v[k2] = nx[k2];
+                        load_chunk(ch + NG, gt, nx);
+                    } else {
+                        load_chunk(ch, task, v);
+                    }
+                    dft_reg<real, R2y, +1>(v);
+#pragma unroll
+                    for (int n2 = 0; n2 < R2y; ++n2) {
+                        Cx<real> w = twy[(n2 * k1) & (NY - 1)];
+                        w.y = -w.y;
+                        cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                    }
                 }
-            }
-            group_sync(g + 1, GT);
-            for (int task = gt; task < CG * R2y; task += GT) {
-                const int c = task % CG, n2 = task / CG;
-                Cx<real> v[R1y];
+                group_sync(g + 1, GT);
+                for (int task = gt; task < CG * R2y; task += GT) {
+                    const int c = task % CG, n2 = task / CG;
+                    Cx<real> v[R1y];
 #pragma unroll
-                for (int k1 = 0; k1 < R1y; ++k1) v[k1] = cur[LA::at(k1 * R2y + n2, c)];
-                dft_reg<real, R1y, +1>(v);
-                if (c0 + c < NZC) {
+                    for (int k1 = 0; k1 < R1y; ++k1) v[k1] = cur[LA::at(k1 * R2y + n2, c)];
+                    dft_reg<real, R1y, +1>(v);
+                    if (c0 + c < NZC) {
 #pragma unroll
-                    for (int n1 = 0; n1 < R1y; ++n1)
-                        st_l2(scr + (long long)(n1 * R2y + n2) * NZCP + c0 + c, v[n1]);
+                        for (int n1 = 0; n1 < R1y; ++n1)
+                            st_l2(scr + (long long)(n1 * R2y + n2) * NZCP + c0 + c, v[n1]);
+                    }
                 }
+                if (NTILE == 1) group_sync(g + 1, GT);
             }
-            if (NTILE == 1) group_sync(g + 1, GT);
         }
         __syncthreads();
         // ---------------- row phase: c2r along z on row pairs (A + iB) ----------------
@@ -262,13 +280,31 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_r2c_kerne
         const int f = unit / p.nplanes, x = unit % p.nplanes;
         const real* src = in + f * p.r_fs + x * p.r_xs;
         // ---------------- row phase: one complex FFT along z per row pair (a + ib) ----------------
-        for (int pg = warp; pg < (NY / 2) / CW; pg += NW) {
+        // (the plane comes from HBM: the next pass's inputs are loaded into a second register set
+        // while the current pass is transformed)
+        constexpr bool ONE_ROW_TASK = (CW * R2z == 32) && sizeof(real) == 4;
+        constexpr int NPG = (NY / 2) / CW;
+        Cx<real> nx[R1z];
+        auto load_pair = [&](int pg, int task, Cx<real> (&dst)[R1z]) {
+            const int c = task / R2z, n2 = task % R2z;
+            const bool valid = pg < NPG;
+            const real* ra = src + (long long)(2 * (pg * CW + c)) * p.r_ys + n2;
+#pragma unroll
+            for (int n1 = 0; n1 < R1z; ++n1)
+                dst[n1] = valid ? Cx<real>{__ldcs(ra + n1 * R2z), __ldcs(ra + p.r_ys + n1 * R2z)} : Cx<real>{0, 0};
+        };
+        if (ONE_ROW_TASK) load_pair(warp, lane, nx);
+        for (int pg = warp; pg < NPG; pg += NW) {
             for (int task = lane; task < CW * R2z; task += 32) {
                 const int c = task / R2z, n2 = task % R2z;
-                const real* ra = src + (long long)(2 * (pg * CW + c)) * p.r_ys + n2;
                 Cx<real> v[R1z];
+                if (ONE_ROW_TASK) {
 #pragma unroll
-                for (int n1 = 0; n1 < R1z; ++n1) v[n1] = {__ldcs(ra + n1 * R2z), __ldcs(ra + p.r_ys + n1 * R2z)};
+                    for (int n1 = 0; n1 < R1z; ++n1) v[n1] = nx[n1];
+                    load_pair(pg + NW, lane, nx);
+                } else {
+                    load_pair(pg, task, v);
+                }
                 dft_reg<real, R1z, -1>(v);
 #pragma unroll
                 for (int k1 = 0; k1 < R1z; ++k1) {

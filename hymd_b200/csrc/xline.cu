@@ -21,6 +21,13 @@
 
 namespace hymd {
 
+__device__ __forceinline__ void store_cx(Cx<float>* p, Cx<float> v) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+}
+__device__ __forceinline__ void store_cx(Cx<double>* p, Cx<double> v) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+}
+
 struct XParams {
     int Nx, Ny, Nz, nyl, y0, Nzc, Nzcp;
     int T, U;
@@ -230,28 +237,30 @@ __global__ void __launch_bounds__(256) xline_kernel(
         for (int task = tid; task < 2 * R1 * CH; task += NT)
             fft_inv_stepA<real, NX, CH>(task < R1 * CH ? wV : wK, tw, task % (R1 * CH));
         __syncthreads();
-        for (int task = tid; task < 2 * R2 * CH; task += NT)
-            fft_inv_stepB<real, NX, CH>(task < R2 * CH ? wV : wK, task % (R2 * CH));
-        __syncthreads();
-        // ---- F_d = -i k_d V:  -i (a + i b) = b - i a  (16-byte stores) ----
+        // ---- last butterfly stage + F_d = -i k_d V:  -i (a + i b) = b - i a, stored straight from
+        // the registers (V -> F_y, F_z; k_x V -> F_x); lanes = neighbouring columns: 64-byte runs ----
         Cx<real>* f0 = fout + (long long)(3 * u) * p.fs_f;
-        for (int e = tid; e < NX * (CH / VEC); e += NT) {
-            const int c = (e % (CH / VEC)) * VEC, x = e / (CH / VEC);
-            if (!(full || col0 + c < p.ncols)) continue;
-            const int sp = spos<NX, CH>(x, c);
-            const long long o = x * p.xs_f + col0 + c;
-            Cx<real> fx[VEC], fy[VEC], fz[VEC];
+        for (int task = tid; task < 2 * R2 * CH; task += NT) {
+            const bool isK = task >= R2 * CH;
+            const int rem = task % (R2 * CH), c = rem % CH, n2 = rem / CH;
+            const Cx<real>* buf = isK ? wK : wV;
+            Cx<real> v[R1];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const Cx<real> v = wV[sp + i], k = wK[sp + i];
-                const real ky = s_hk[0][c + i][1], kz = s_hk[0][c + i][2];
-                fx[i] = {k.y, -k.x};
-                fy[i] = {ky * v.y, -ky * v.x};
-                fz[i] = {kz * v.y, -kz * v.x};
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = buf[spos<NX, CH>(k1 * R2 + n2, c)];
+            dft_reg<real, R1, +1>(v);
+            if (!(full || col0 + c < p.ncols)) continue;
+            const real ky = s_hk[0][c][1], kz = s_hk[0][c][2];
+            Cx<real>* o = f0 + (long long)n2 * p.xs_f + col0 + c;
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1) {
+                Cx<real>* ox = o + (long long)(n1 * R2) * p.xs_f;
+                if (isK) {
+                    store_cx(ox, Cx<real>{v[n1].y, -v[n1].x});
+                } else {
+                    store_cx(ox + p.fs_f, Cx<real>{ky * v[n1].y, -ky * v[n1].x});
+                    store_cx(ox + 2 * p.fs_f, Cx<real>{kz * v[n1].y, -kz * v[n1].x});
+                }
             }
-            store16(f0 + o, fx);
-            store16(f0 + p.fs_f + o, fy);
-            store16(f0 + 2 * p.fs_f + o, fz);
         }
         __syncthreads();
     }

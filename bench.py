@@ -127,16 +127,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def build_system(args, world):
-    from hymd_b200.synthetic import SPECS, make_system
+def build_system(args, world, rank=0):
+    """Strong scaling: the named workload, every rank keeps the particles of its x-slab.
+    Weak scaling: `world` independent boxes of the named workload stacked along x (mesh
+    [world * M, M, M], N * world particles: per-GPU work fixed, power-of-two planes kept);
+    every rank generates its own box only."""
+    from hymd_b200.synthetic import make_system
     dtype = np.float32 if args.dtype == "f32" else np.float64
-    n, mesh = args.n, args.mesh
     if args.scaling == "weak" and world > 1:
-        # per-GPU work fixed: N x world particles on a mesh with world x the cells
-        spec = SPECS[args.workload]
-        n = (n or spec["n"]) * world
-        mesh = int(round((mesh or spec["mesh"]) * world ** (1.0 / 3.0) / 8.0)) * 8
-    return make_system(args.workload, dtype=dtype, n=n, mesh=mesh)
+        return make_system(args.workload, dtype=dtype, n=args.n, mesh=args.mesh, x_copies=world,
+                           x_index=rank), True
+    return make_system(args.workload, dtype=dtype, n=args.n, mesh=args.mesh), False
 
 
 def algorithmic_bytes(N, T, U, mesh, b, pme):
@@ -269,11 +270,11 @@ def main():
     np_dtype = np.float32 if args.dtype == "f32" else np.float64
     t_dtype = torch.float32 if args.dtype == "f32" else torch.float64
     b = 4 if args.dtype == "f32" else 8
-    sysm = build_system(args, world)
+    sysm, presharded = build_system(args, world, rank)
     cfg = sysm.config
     mesh = [int(x) for x in np.full(3, cfg.mesh_size)]
     T = cfg.n_types
-    N = len(sysm.positions)
+    N = len(sysm.positions) * (world if presharded else 1)
     ham = get_hamiltonian(cfg)
     pm, fl, ecl, cl = F.initialize_pm(None, cfg)
     phi, phi_fourier, force_mesh, v_ext_fourier, v_ext, phi_transfer, phi_laplacian = fl
@@ -283,13 +284,13 @@ def main():
 
     # this rank's particles (slab along x); single GPU: all of them
     pos_h, typ_h, q_h = sysm.positions, sysm.types, sysm.charges
-    if world > 1:
+    vel_h = sysm.velocities
+    if world > 1 and not presharded:
         L = float(cfg.box_size[0])
         cell = np.floor(pos_h[:, 0].astype(np.float64) * mesh[0] / L).astype(np.int64) % mesh[0]
         mine = (cell // (mesh[0] // world)) == rank
-        pos_h, typ_h = pos_h[mine], typ_h[mine]
+        pos_h, typ_h, vel_h = pos_h[mine], typ_h[mine], vel_h[mine]
         q_h = None if q_h is None else q_h[mine]
-    vel_h = sysm.velocities[mine] if world > 1 else sysm.velocities
     if not args.no_dd:
         # what main.py does once at start-up (and every config.domain_decomposition steps) when
         # the option is set: all per-particle arrays come back permuted identically
@@ -433,16 +434,30 @@ def main():
             ent["gbs"] = alg[name] / (per * 1e-3) / 1e9 if per > 0 else None
             ent["frac_of_peak"] = ent["gbs"] / peak if per > 0 else None
         phases[name] = ent
-    own = [k for k in ("paint", "kspace", "readout") if k in phases]
+    paths = pm.paths()
+    kernel_of = {"paint": "paint_kernel", "readout": "readout_gather_kernel",
+                 "kspace": "xline_kernel" if paths["xline"] else "kspace_force_kernel"}
+    if paths["plane"]:          # the (y,z) transforms are hand-written too (planefft.cu)
+        kernel_of.update({"fft_fwd": "plane_r2c_kernel", "fft_inv": "plane_c2r_kernel"})
+    if os.environ.get("HYMD_B200_READOUT", "g")[0] == "t":
+        kernel_of["readout"] = "readout_kernel"
+    own = [k for k in kernel_of if k in phases]
     dom = max(own, key=lambda k: phases[k]["ms_per_step"])
-    roofline = {"kernel": {"paint": "paint_kernel", "kspace": "kspace_force_kernel",
-                           "readout": "readout_kernel"}[dom],
+    for k in own:
+        phases[k]["kernel"] = kernel_of[k]
+        if traffic.get(k):
+            phases[k]["ncu_dram_bytes"] = traffic[k]
+    nested = sum(phases[k]["ms_per_step"] for k in ("alltoall", "halo") if k in phases)
+    roofline = {"kernel": kernel_of[dom],
                 "bound": "hbm", "achieved": phases[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": phases[dom]["frac_of_peak"], "traffic": traffic.get(dom),
                 "algorithmic_bytes": phases[dom]["algorithmic_bytes"],
                 "peak_source": peak_src,
                 "timing": "CUDA events around the phase on the launch stream, averaged over the "
-                          "timed steps"}
+                          "timed steps" + (f" (multi-GPU: the transform phases include {nested:.3f} ms "
+                                           "of exchange + barrier per step)" if world > 1 else ""),
+                "all_hand_written": {k: {"kernel": kernel_of[k], "gbs": phases[k]["gbs"],
+                                         "frac": phases[k]["frac_of_peak"]} for k in own}}
     total_alg = sum(alg.values())
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -461,7 +476,7 @@ def main():
                    "parallelism": "single GPU" if world == 1 else f"{world} x-slabs (slab FFT, NCCL all-to-all)"},
         "ns_per_day": args.steps / (ms_total * 1e-3) * 86400.0 * PS_PER_CYCLE / 1000.0,
         "cycle_frac_of_hbm_roofline": total_alg / (ms_per_step * 1e-3) / 1e9 / peak,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "paths": paths,
         "roofline": roofline, "phases": phases,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -26,7 +26,7 @@ EXPORTS = [
     "hymd_set_charges", "hymd_paint", "hymd_field_cycle", "hymd_readout", "hymd_pme_cycle",
     "hymd_materialize", "hymd_field_energy", "hymd_get_field", "hymd_ctx_status",
     "hymd_launch_count", "hymd_migrate_plan", "hymd_migrate_apply", "hymd_ctx_set_timing", "hymd_ctx_get_timings",
-    "hymd_sort_particles_ex", "hymd_ctx_reset_order",
+    "hymd_sort_particles_ex", "hymd_ctx_reset_order", "hymd_ctx_paths",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -89,6 +89,7 @@ def load():
     lib.hymd_field_energy.argtypes = [vp, P(dbl), dbl, dbl, dbl, P(dbl), vp]
     lib.hymd_get_field.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, P(vp), P(i64), P(i64)]
     lib.hymd_ctx_status.argtypes = [vp, P(i64)]
+    lib.hymd_ctx_paths.argtypes = [vp, P(i32)]
     lib.hymd_launch_count.argtypes = [vp]
     lib.hymd_launch_count.restype = i64
     lib.hymd_ctx_set_timing.argtypes = [vp, ctypes.c_int]

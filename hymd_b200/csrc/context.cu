@@ -599,6 +599,12 @@ int hymd_ctx_status(hymd_ctx* c, int64_t out[4]) {
     return HYMD_OK;
 }
 
+int hymd_ctx_paths(hymd_ctx* c, int32_t out[4]) {
+    if (!c || !out) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    out[0] = c->fused; out[1] = c->plane; out[2] = c->slab; out[3] = c->p2p;
+    return HYMD_OK;
+}
+
 int hymd_nccl_unique_id(uint8_t id[HYMD_NCCL_UNIQUE_ID_BYTES]) {
     if (!id) { set_error("null argument"); return HYMD_ERR_INVALID; }
     return comm_unique_id(id);

@@ -364,6 +364,13 @@ class ParticleMesh:
         return {"max_cell_count": out[0], "out_of_slab": out[1], "n_local": out[2],
                 "potential_rows": out[3]}
 
+    def paths(self):
+        """Which kernels this context runs: fused x-line, plane transforms, slab pipeline,
+        NVLink peer-memory exchange."""
+        out = (ctypes.c_int32 * 4)()
+        _lib.check(self.lib.hymd_ctx_paths(self._ctx, out))
+        return {"xline": bool(out[0]), "plane": bool(out[1]), "slab": bool(out[2]), "p2p": bool(out[3])}
+
     def set_timing(self, enable=True):
         _lib.check(self.lib.hymd_ctx_set_timing(self._ctx, int(bool(enable))))
 

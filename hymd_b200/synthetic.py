@@ -67,12 +67,17 @@ def box_length(n: int) -> float:
 
 def make_system(name: str = "C2", dtype=np.float32, n: Optional[int] = None,
                 mesh: Optional[int] = None, sigma: float = 0.5, kappa: float = 0.05,
-                chains: bool = True) -> System:
-    """Build one of the C1..C5 systems (optionally at a reduced ``n`` / ``mesh``)."""
+                chains: bool = True, x_copies: int = 1, x_index: int = 0) -> System:
+    """Build one of the C1..C5 systems (optionally at a reduced ``n`` / ``mesh``).
+
+    ``x_copies > 1`` (weak scaling): the global system is ``x_copies`` independent boxes of ``n``
+    particles stacked along x (box ``[x_copies * L, L, L]``, mesh ``[x_copies * mesh, mesh,
+    mesh]``); the call returns the particles of box ``x_index`` only (own seed) together with the
+    GLOBAL config, so every rank generates just its own slab."""
     spec = SPECS[name]
     n = int(n if n is not None else spec["n"])
     mesh = int(mesh if mesh is not None else spec["mesh"])
-    rng = np.random.default_rng(spec["seed"])
+    rng = np.random.default_rng(spec["seed"] + 7919 * int(x_index))
     names: List[str] = spec["names"]
     L = box_length(n)
     frac = np.asarray(spec["frac"], dtype=np.float64)
@@ -124,12 +129,13 @@ def make_system(name: str = "C2", dtype=np.float32, n: Optional[int] = None,
         k = min(len(ions), int(round(abs(excess))))
         charges[ions[:k]] = -np.sign(excess)
     vel = rng.normal(size=(n, 3)) * np.sqrt(Config.gas_constant * 323.0 / 72.0)
-    cfg = Config(mesh_size=mesh, sigma=sigma, kappa=kappa, box_size=[L, L, L],
+    cfg = Config(mesh_size=mesh if x_copies == 1 else [mesh * x_copies, mesh, mesh], sigma=sigma,
+                 kappa=kappa, box_size=[L * x_copies, L, L],
                  hamiltonian="DefaultWithChi", chi=[Chi(*c) for c in spec["chi"]],
                  dtype=np.dtype(dtype), mass=72.0, time_step=0.01, respa_inner=25,
                  coulombtype="PIC_Spectral" if coulomb else None,
                  dielectric_const=80.0 if coulomb else None)
-    cfg.finalize(names, n_particles=n)
+    cfg.finalize(names, n_particles=n * x_copies)
     if coulomb:
         cfg.type_charges = [spec["charges"].get(nm, 0.0) for nm in cfg.unique_names]
     # names sorted alphabetically define the type ids (input_parser.py:546-557): remap
@@ -137,6 +143,8 @@ def make_system(name: str = "C2", dtype=np.float32, n: Optional[int] = None,
     types = remap[types]
     pos = np.mod(pos, L).astype(dtype)
     pos[pos >= np.asarray(L, dtype=dtype)] = 0.0
+    if x_index:
+        pos[:, 0] += np.asarray(L * x_index, dtype=dtype)
     return System(name=name, config=cfg, positions=pos, types=types.astype(np.int32),
                   charges=None if charges is None else charges.astype(dtype),
                   velocities=vel.astype(dtype))

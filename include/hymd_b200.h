@@ -158,6 +158,10 @@ int hymd_get_field(hymd_ctx* ctx, int field_id, int t, int d, void** d_ptr, int6
  * local particle count, distinct potential rows} of the last hymd_sort_particles. */
 int hymd_ctx_status(hymd_ctx* ctx, int64_t out[4]);
 
+/* Which code paths this context runs (bench / test bookkeeping): out = {fused x-line kernel,
+ * one-pass (y,z) plane transforms, slab pipeline, exchanges over NVLink peer memory}, 0 or 1. */
+int hymd_ctx_paths(hymd_ctx* ctx, int32_t out[4]);
+
 /* Number of CUDA kernels launched by this context since creation (bench bookkeeping). */
 int64_t hymd_launch_count(hymd_ctx* ctx);
 

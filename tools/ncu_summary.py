@@ -69,7 +69,9 @@ if os.path.exists(rep):
             ("dram__bytes_write.sum", "dram write"),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
             ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
-            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
+            ("smsp__issue_active.avg.pct", "issue active %"),
+            ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex (smem/L1) %"),
+            ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
             ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
             ("lts__t_sector_hit_rate.pct", "L2 hit %"),
             ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
@@ -98,13 +100,19 @@ if os.path.exists(rep):
             fh.write(f"## `{name}`\n\n| metric | value |\n|---|---|\n")
             for i, lbl in idx:
                 fh.write(f"| {lbl} | {r[i]} {units[i]} |\n")
+            pre, suf = "smsp__average_warps_issue_stalled_", "_per_issue_active.ratio"
+            st = sorted(((float(r[j] or 0), c[len(pre):-len(suf)]) for j, c in enumerate(h)
+                         if c.startswith(pre) and c.endswith(suf)), reverse=True)[:6]
+            fh.write("| top stalls (warps per issue) | " + ", ".join(f"{n} {v:.2f}" for v, n in st) + " |\n")
             fh.write("\n")
             try:
                 rd = to_bytes(r[h.index("dram__bytes_read.sum")], units[h.index("dram__bytes_read.sum")])
                 wr = to_bytes(r[h.index("dram__bytes_write.sum")], units[h.index("dram__bytes_write.sum")])
                 key = {"paint_kernel<float, 0>": "paint", "paint_kernel<double, 0>": "paint"}.get(name)
                 for frag, k in (("paint_kernel", "paint"), ("kspace_force", "kspace"),
-                                ("xline_force", "kspace"), ("readout_kernel", "readout"),
+                                ("xline_kernel", "kspace"), ("readout_kernel", "readout"),
+                                ("readout_gather_kernel", "readout"),
+                                ("plane_r2c_kernel", "fft_fwd"), ("plane_c2r_kernel", "fft_inv"),
                                 ("count_kernel", "sort_count"), ("scatter_kernel", "sort_scatter")):
                     if frag in name:
                         traffic[k] = int(rd + wr)

@@ -230,6 +230,8 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     c->fused = xline_supported(c) && !(no_fused && no_fused[0] == '1');
     c->slab = P > 1 || c->fused || (force_slab && force_slab[0] == '1');
     c->plane = c->slab && plane_supported(c);
+    const char* no_grad2 = getenv("HYMD_B200_GRAD2");
+    c->grad2 = c->fused && c->plane && !(no_grad2 && no_grad2[0] == '0');
     if (P > 1 && (st = comm_create(c, nccl_id))) return fail(st);
     const char* nccl_x = getenv("HYMD_B200_NCCL_EXCHANGE");
     c->p2p = P > 1 && !(nccl_x && nccl_x[0] == '1');
@@ -423,7 +425,7 @@ int hymd_field_cycle(hymd_ctx* c, int compute_potential, void* stream) {
     }
     {
         PhaseScope ps(c, HYMD_PHASE_FFT_INV, s);
-        if (c->fused) HYMD_CHECK(fft_inverse_xdone(c, force_spectra(c), 3 * c->U, c->gmesh, true, s));
+        if (c->fused) HYMD_CHECK(fft_inverse_xdone(c, force_spectra(c), 3 * c->U, c->gmesh, true, s, c->grad2));
         else HYMD_CHECK(fft_inverse(c, c->f_hat, 3 * c->U, c->gmesh, true, s));
     }
     {
@@ -515,7 +517,7 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
     {
         PhaseScope ps(c, HYMD_PHASE_PME_FFT, s);
         if (c->fused)
-            HYMD_CHECK(fft_inverse_xdone(c, (c->g.P == 1) ? c->wA : c->e_hat, 3, c->emesh, true, s));
+            HYMD_CHECK(fft_inverse_xdone(c, (c->g.P == 1) ? c->wA : c->e_hat, 3, c->emesh, true, s, c->grad2));
         else HYMD_CHECK(fft_inverse(c, c->e_hat, 3, c->emesh, true, s));
         if (!c->plane) HYMD_CHECK(fill_ghosts(c, c->emesh, 3, s));
         HYMD_CHECK(halo_fetch(c, c->emesh, 3, s));

@@ -182,6 +182,8 @@ struct hymd_ctx {
     std::vector<hymd::PlanEntry>* plans;
     void* fft_work;
     size_t fft_work_bytes;
+    bool grad2;             // fused x-line + plane kernels: 2 spectra per potential row cross HBM (and the
+                            // inverse transpose) instead of 3; the plane c2r applies k_y / k_z itself
     bool slab;              // slab pipeline (2-D cuFFT per plane + x transform) instead of 3-D plans
     void* wA;               // slab work: F x (nxl+1) x Ny x Nzcp complex (2-D transform side)
     void* wS;               // slab work: all-to-all staging, F x nxl x Ny x Nzcp complex
@@ -253,7 +255,8 @@ KLayout klayout(const hymd_ctx* c, int F);
 int fft_forward(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s);
 int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t s);
 int fft_inverse(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s);
-int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s);
+int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s,
+                      bool derive = false);
 int ensure_work(hymd_ctx* c, int F);
 void destroy_plans(hymd_ctx* c);
 int halo_reduce(hymd_ctx* c, void* fields, int F, cudaStream_t s);
@@ -263,7 +266,7 @@ bool plane_supported(const hymd_ctx* c);
 int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int nplanes, void* k_out,
                   long long k_fs, cudaStream_t s);
 int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int nplanes, void* real_out,
-                  bool ghost, cudaStream_t s);
+                  bool ghost, bool derive, cudaStream_t s);
 // xline.cu
 bool xline_supported(const hymd_ctx* c);
 int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s);

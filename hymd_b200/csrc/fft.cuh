@@ -13,6 +13,12 @@ __device__ __forceinline__ Cx<real> cmul(Cx<real> a, Cx<real> b) {
     return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }
 
+// conj(a) * b
+template <typename real>
+__device__ __forceinline__ Cx<real> cmulc(Cx<real> a, Cx<real> b) {
+    return {a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x};
+}
+
 // cos(2 pi j / 32); j is a compile-time constant after unrolling, so the switch folds away
 template <typename real>
 __device__ __forceinline__ real cos32(int j) {
@@ -91,6 +97,33 @@ __device__ __forceinline__ void dft_reg(Cx<real> (&v)[R]) {
         });
     });
 }
+
+// Four-step twiddles w^(i j), i = 0 .. LEN-1, for a THREAD-CONSTANT j (w = exp(-2 pi i / N)), held in
+// registers as two short tables: S[b-1] = w^(b j), b = 1..3, and T[a-1] = w^(4 a j), a = 1..LEN/4-1,
+// so that w^(i j) = T[i >> 2] * S[i & 3].  Replaces LEN dependent shared-memory loads per
+// butterfly group (a third of the shared-memory instructions of a four-step pass, and the ones
+// whose latency the few resident warps cannot hide) by at most LEN/2 extra complex multiplies.
+template <typename real, int LEN>
+struct TwiddleRegs {
+    static constexpr int NA = LEN / 4;
+    Cx<real> S[3], T[NA > 1 ? NA - 1 : 1];
+    __device__ __forceinline__ void init(const Cx<real>* __restrict__ tw, int j, int n) {
+#pragma unroll
+        for (int b = 1; b < 4; ++b) S[b - 1] = tw[(b * j) & (n - 1)];
+#pragma unroll
+        for (int a = 1; a < NA; ++a) T[a - 1] = tw[(4 * a * j) & (n - 1)];
+    }
+    // v[i] *= w^(i j)  (CONJ: the conjugate, inverse transforms)
+    template <bool CONJ>
+    __device__ __forceinline__ void apply(Cx<real> (&v)[LEN]) const {
+        static_for<1, LEN>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int b = i & 3, a = i >> 2;
+            if constexpr (b != 0) v[i] = CONJ ? cmulc(S[b - 1], v[i]) : cmul(S[b - 1], v[i]);
+            if constexpr (a != 0) v[i] = CONJ ? cmulc(T[a - 1], v[i]) : cmul(T[a - 1], v[i]);
+        });
+    }
+};
 
 __device__ __forceinline__ void store16(Cx<float>* p, const Cx<float> (&v)[2]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);

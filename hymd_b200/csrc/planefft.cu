@@ -82,6 +82,11 @@ struct PlaneParams {
     int r_ys;                       // real row pitch
     int ghost;                      // inverse: also write the z = Nz element and the y = Ny row
     int xdup_plane;                 // inverse: plane 0 is written to this plane as well (-1: no)
+    // inverse, "derive" mode: a unit is (potential row u, plane) and produces the three force
+    // meshes 3u+d from TWO input spectra: slot 2u = -i k_x V (x-inverted), slot 2u+1 = -i V;
+    // k_y / k_z (with the Nyquist rule of SURVEY.md section 7) are applied while loading.
+    int derive;
+    double dky, dkz;                // 2 pi / L_y, 2 pi / L_z
 };
 
 // Work decomposition inside the 512-thread CTA.
@@ -90,14 +95,14 @@ struct PlaneParams {
 //   row phase   : every warp on its own CW row pairs, synchronised with __syncwarp only.
 // Butterfly inputs are loaded from global memory straight into registers and the last butterfly
 // stage stores straight to global memory, so each FFT makes exactly one trip through shared memory.
-template <typename real, int NY, int NZ> struct PlaneCfg {
-    static constexpr int NT = 512, NW = NT / 32;
+template <typename real, int NY, int NZ, int NT_> struct PlaneCfg {
+    static constexpr int NT = NT_, NW = NT / 32, CTAS = 512 / NT;            // CTAs per SM
     static constexpr int R1y = Radix<NY>::R1, R2y = Radix<NY>::R2, R1z = Radix<NZ>::R1, R2z = Radix<NZ>::R2;
     static constexpr int NZC = NZ / 2 + 1, NZCP = NZC + (NZC & 1);
     static constexpr int CG = 64 / (int)sizeof(Cx<real>);
     static constexpr int GT = CG * 16, NG = NT / GT;
     using LA = LayA<NY, CG>;
-    static constexpr int NTILE = (2 * NG * LA::ELEMS * (int)sizeof(Cx<real>) <= 144 * 1024) ? 2 : 1;
+    static constexpr int NTILE = (2 * NG * LA::ELEMS * (int)sizeof(Cx<real>) <= 144 * 1024 / CTAS) ? 2 : 1;
     static constexpr int CW = 32 / R1z;                                    // row pairs per warp pass
     using LB = LayB<NZ, CW>;
     static constexpr int COL_ELEMS = NG * NTILE * LA::ELEMS, ROW_ELEMS = NW * LB::ELEMS;
@@ -107,11 +112,11 @@ template <typename real, int NY, int NZ> struct PlaneCfg {
 };
 
 // ---- inverse: spectra [ky][kz] -> real plane ------------------------------------------------------
-template <typename real, int NY, int NZ>
-__global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_c2r_kernel(
+template <typename real, int NY, int NZ, int NTH>
+__global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
     const Cx<real>* __restrict__ in, Cx<real>* __restrict__ scratch, real* __restrict__ out,
     const Cx<real>* __restrict__ twy_g, const Cx<real>* __restrict__ twz_g, PlaneParams p) {
-    using Cfg = PlaneCfg<real, NY, NZ>;
+    using Cfg = PlaneCfg<real, NY, NZ, NTH>;
     using LA = typename Cfg::LA;
     using LB = typename Cfg::LB;
     constexpr int NT = Cfg::NT, NW = Cfg::NW, CG = Cfg::CG, GT = Cfg::GT, NG = Cfg::NG, NTILE = Cfg::NTILE,
@@ -131,25 +136,61 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_c2r_kerne
     const int warp = tid / 32, lane = tid % 32;
     Cx<real>* gtile = tile + g * NTILE * LA::ELEMS;
     Cx<real>* wtile = tile + warp * LB::ELEMS;
+    // one step-A task per thread (k1 fixed for the whole kernel): prefetchable, twiddles in registers
+    constexpr bool ONE_TASK = (CG * R1y <= GT) && sizeof(real) == 4 && R2y <= 16;
+    constexpr bool REGC = ONE_TASK && R2y >= 4, REGR = sizeof(real) == 4 && R2z <= 16 && R2z >= 4;
+    TwiddleRegs<real, R2y> twc;
+    TwiddleRegs<real, R2z> twr;
+    if constexpr (REGC) twc.init(twy, (gt / CG) % R1y, NY);
+    if constexpr (REGR) twr.init(twz, lane % R1z, NZ);
 
+    const int ND = p.derive ? 3 : 1;
+    const real dky = (real)p.dky, dkz = (real)p.dkz;
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
-        const int f = unit / p.nplanes, x = unit % p.nplanes;
-        const Cx<real>* src = in + f * p.k_fs + x * p.k_xs;
+      const int fu = unit / p.nplanes, x = unit % p.nplanes;
+      for (int d = 0; d < ND; ++d) {
+        // derive: d = 1, 2 read the same spectrum plane (the second time from L2)
+        const int fin = p.derive ? 2 * fu + (d > 0 ? 1 : 0) : fu;
+        const int f = p.derive ? 3 * fu + d : fu;
+        const int mode = p.derive ? d : 0;
+        const Cx<real>* src = in + fin * p.k_fs + x * p.k_xs;
+        // v[k2] = spectrum element (k_y = k1 + R1y k2, column col): times k_y (mode 1) or k_z (mode 2)
+        auto scale_chunk = [&](Cx<real> (&v)[R2y], int k1, int col) {
+            if (mode == 1) {
+                const bool selfc = col == 0 || 2 * col == NZ;
+                const real fk1 = (real)k1;
+#pragma unroll
+                for (int k2 = 0; k2 < R2y; ++k2) {
+                    // signed frequency of row k1 + R1y k2 (rows >= NY/2 <=> k2 >= R2y/2)
+                    const real nn = fk1 + (real)(R1y * k2 - (2 * k2 >= R2y ? NY : 0));
+                    real sk = dky * nn;
+                    if (2 * k2 == R2y && k1 == 0 && selfc) sk = 0;      // y-Nyquist on a self-conjugate column
+                    v[k2].x *= sk; v[k2].y *= sk;
+                }
+            } else if (mode == 2) {
+                const real sk = (2 * col == NZ) ? (real)0 : dkz * (real)col;
+#pragma unroll
+                for (int k2 = 0; k2 < R2y; ++k2) { v[k2].x *= sk; v[k2].y *= sk; }
+            }
+        };
         // ---------------- column phase: inverse FFT along y ----------------
         // (the spectrum comes from HBM: the next chunk's butterfly inputs are loaded into a second
         // register set while the current chunk is transformed)
         {
-            constexpr bool ONE_TASK = (CG * R1y <= GT) && sizeof(real) == 4 && R2y <= 16;   // one step-A task per thread: prefetchable
             Cx<real> nx[R2y];
             auto load_chunk = [&](int ch, int task, Cx<real> (&dst)[R2y]) {
                 const int c = task % CG, k1 = task / CG;
                 const bool valid = ch < NCHG && task < CG * R1y && ch * CG + c < NZC;
 #pragma unroll
                 for (int k2 = 0; k2 < R2y; ++k2)
-                    dst[k2] = valid ? ld_stream(src + (long long)(k1 + R1y * k2) * NZCP + ch * CG + c) : Cx<real>{0, 0};
+                {
+                    const Cx<real>* e = src + (long long)(k1 + R1y * k2) * NZCP + ch * CG + c;
+                    // derive: the plane read for the k_y component is read again for k_z: keep it in L2
+                    dst[k2] = valid ? (mode == 1 ? ld_l2(e) : ld_stream(e)) : Cx<real>{0, 0};
+                }
             };
             int it = 0;
-            const int ch0 = (g + unit) % NG;
+            const int ch0 = (g + unit + d) % NG;
             if (ONE_TASK) load_chunk(ch0, gt, nx);
             for (int ch = ch0; ch < NCHG; ch += NG, ++it) {
                 Cx<real>* cur = gtile + (it & (NTILE - 1)) * LA::ELEMS;
@@ -164,12 +205,19 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_c2r_kerne
                     } else {
                         load_chunk(ch, task, v);
                     }
+                    scale_chunk(v, k1, c0 + c);
                     dft_reg<real, R2y, +1>(v);
+                    if constexpr (REGC) {
+                        twc.template apply<true>(v);
 #pragma unroll
-                    for (int n2 = 0; n2 < R2y; ++n2) {
-                        Cx<real> w = twy[(n2 * k1) & (NY - 1)];
-                        w.y = -w.y;
-                        cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                        for (int n2 = 0; n2 < R2y; ++n2) cur[LA::at(k1 * R2y + n2, c)] = v[n2];
+                    } else {
+#pragma unroll
+                        for (int n2 = 0; n2 < R2y; ++n2) {
+                            Cx<real> w = twy[(n2 * k1) & (NY - 1)];
+                            w.y = -w.y;
+                            cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                        }
                     }
                 }
                 group_sync(g + 1, GT);
@@ -208,11 +256,17 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_c2r_kerne
                     v[k2] = {A.x - s * B.y, s * A.y + B.x};
                 }
                 dft_reg<real, R2z, +1>(v);
+                if constexpr (REGR) {
+                    twr.template apply<true>(v);
 #pragma unroll
-                for (int n2 = 0; n2 < R2z; ++n2) {
-                    Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
-                    w.y = -w.y;
-                    wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                    for (int n2 = 0; n2 < R2z; ++n2) wtile[LB::at(k1 * R2z + n2, c)] = v[n2];
+                } else {
+#pragma unroll
+                    for (int n2 = 0; n2 < R2z; ++n2) {
+                        Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
+                        w.y = -w.y;
+                        wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                    }
                 }
             }
             __syncwarp();
@@ -247,15 +301,16 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_c2r_kerne
             __syncwarp();
         }
         __syncthreads();
+      }
     }
 }
 
 // ---- forward: real plane -> spectra [ky][kz] -----------------------------------------------------
-template <typename real, int NY, int NZ>
-__global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_r2c_kernel(
+template <typename real, int NY, int NZ, int NTH>
+__global__ void __launch_bounds__(NTH, 512 / NTH) plane_r2c_kernel(
     const real* __restrict__ in, Cx<real>* __restrict__ scratch, Cx<real>* __restrict__ out,
     const Cx<real>* __restrict__ twy_g, const Cx<real>* __restrict__ twz_g, PlaneParams p) {
-    using Cfg = PlaneCfg<real, NY, NZ>;
+    using Cfg = PlaneCfg<real, NY, NZ, NTH>;
     using LA = typename Cfg::LA;
     using LB = typename Cfg::LB;
     constexpr int NT = Cfg::NT, NW = Cfg::NW, CG = Cfg::CG, GT = Cfg::GT, NG = Cfg::NG, NTILE = Cfg::NTILE,
@@ -275,6 +330,14 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_r2c_kerne
     const int warp = tid / 32, lane = tid % 32;
     Cx<real>* gtile = tile + g * NTILE * LA::ELEMS;
     Cx<real>* wtile = tile + warp * LB::ELEMS;
+    // one task per thread in the twiddled stages (n2 fixed for the whole kernel): twiddles in registers
+    constexpr bool ONE_ROW_TASK = (CW * R2z == 32) && sizeof(real) == 4;
+    constexpr bool REGR = ONE_ROW_TASK && R1z <= 16 && R1z >= 4;
+    constexpr bool REGC = sizeof(real) == 4 && (CG * R2y <= GT) && R1y <= 16 && R1y >= 4;
+    TwiddleRegs<real, R1z> twr;
+    TwiddleRegs<real, R1y> twc;
+    if constexpr (REGR) twr.init(twz, lane % R2z, NZ);
+    if constexpr (REGC) twc.init(twy, (gt / CG) % R2y, NY);
 
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
         const int f = unit / p.nplanes, x = unit % p.nplanes;
@@ -282,7 +345,6 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_r2c_kerne
         // ---------------- row phase: one complex FFT along z per row pair (a + ib) ----------------
         // (the plane comes from HBM: the next pass's inputs are loaded into a second register set
         // while the current pass is transformed)
-        constexpr bool ONE_ROW_TASK = (CW * R2z == 32) && sizeof(real) == 4;
         constexpr int NPG = (NY / 2) / CW;
         Cx<real> nx[R1z];
         auto load_pair = [&](int pg, int task, Cx<real> (&dst)[R1z]) {
@@ -306,10 +368,16 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_r2c_kerne
                     load_pair(pg, task, v);
                 }
                 dft_reg<real, R1z, -1>(v);
+                if constexpr (REGR) {
+                    twr.template apply<false>(v);
 #pragma unroll
-                for (int k1 = 0; k1 < R1z; ++k1) {
-                    const Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
-                    wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+                    for (int k1 = 0; k1 < R1z; ++k1) wtile[LB::at(k1 * R2z + n2, c)] = v[k1];
+                } else {
+#pragma unroll
+                    for (int k1 = 0; k1 < R1z; ++k1) {
+                        const Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
+                        wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+                    }
                 }
             }
             __syncwarp();
@@ -357,10 +425,16 @@ __global__ void __launch_bounds__(PlaneCfg<real, NY, NZ>::NT, 1) plane_r2c_kerne
                 for (int n1 = 0; n1 < R1y; ++n1)
                     v[n1] = valid ? ld_l2(scr + (long long)(n1 * R2y + n2) * NZCP + c0 + c) : Cx<real>{0, 0};
                 dft_reg<real, R1y, -1>(v);
+                if constexpr (REGC) {
+                    twc.template apply<false>(v);
 #pragma unroll
-                for (int k1 = 0; k1 < R1y; ++k1) {
-                    const Cx<real> w = twy[(n2 * k1) & (NY - 1)];
-                    cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+                    for (int k1 = 0; k1 < R1y; ++k1) cur[LA::at(k1 * R2y + n2, c)] = v[k1];
+                } else {
+#pragma unroll
+                    for (int k1 = 0; k1 < R1y; ++k1) {
+                        const Cx<real> w = twy[(n2 * k1) & (NY - 1)];
+                        cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+                    }
                 }
             }
             group_sync(g + 1, GT);
@@ -415,13 +489,21 @@ static int plane_tables(hymd_ctx* c) {
     return HYMD_OK;
 }
 
-template <typename real, int N, bool INVERSE>
+// Threads per CTA: 512 (one CTA per SM, default) or 256 (two CTAs per SM; measured slower at
+// 256^2 planes: 0.84 vs 0.69 ms for the 12 inverse transforms of C4 -- the second scratch
+// plane per SM costs more L2 than the phase overlap gains).
+static int plane_threads() {
+    if (const char* e = getenv("HYMD_B200_PLANE_NT")) return atoi(e) == 256 ? 256 : 512;
+    return 512;
+}
+
+template <typename real, int N, int NTH, bool INVERSE>
 static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
-    using Cfg = PlaneCfg<real, N, N>;
+    using Cfg = PlaneCfg<real, N, N, NTH>;
     HYMD_CHECK(plane_tables(c));
     int sms = 0;
     HYMD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev));
-    int grid = sms;
+    int grid = sms * Cfg::CTAS;
     if (const char* e = getenv("HYMD_B200_PLANE_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;   // tuning
     if (grid > p.nunits) grid = p.nunits;
     if (grid < 1) return HYMD_OK;
@@ -433,12 +515,12 @@ static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParam
     }
     if ((size_t)grid * N * Cfg::NZCP * sizeof(Cx<real>) > c->plane_scratch_bytes) grid = 2 * sms;
     if (INVERSE) {
-        auto kern = plane_c2r_kernel<real, N, N>;
+        auto kern = plane_c2r_kernel<real, N, N, NTH>;
         HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>((const Cx<real>*)in, (Cx<real>*)c->plane_scratch, (real*)out,
                                              (const Cx<real>*)c->ytw, (const Cx<real>*)c->ztw, p);
     } else {
-        auto kern = plane_r2c_kernel<real, N, N>;
+        auto kern = plane_r2c_kernel<real, N, N, NTH>;
         HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>((const real*)in, (Cx<real>*)c->plane_scratch, (Cx<real>*)out,
                                              (const Cx<real>*)c->ytw, (const Cx<real>*)c->ztw, p);
@@ -447,17 +529,23 @@ static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParam
     return HYMD_OK;
 }
 
+template <typename real, int N, bool INVERSE>
+static int launch_plane_nt(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
+    return plane_threads() == 512 ? launch_plane<real, N, 512, INVERSE>(c, in, out, p, s)
+                                  : launch_plane<real, N, 256, INVERSE>(c, in, out, p, s);
+}
+
 template <typename real, bool INVERSE>
 static int dispatch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
     switch (c->g.Ny) {
-        case 16: return launch_plane<real, 16, INVERSE>(c, in, out, p, s);
-        case 32: return launch_plane<real, 32, INVERSE>(c, in, out, p, s);
-        case 64: return launch_plane<real, 64, INVERSE>(c, in, out, p, s);
-        case 128: return launch_plane<real, 128, INVERSE>(c, in, out, p, s);
-        case 256: return launch_plane<real, 256, INVERSE>(c, in, out, p, s);
+        case 16: return launch_plane_nt<real, 16, INVERSE>(c, in, out, p, s);
+        case 32: return launch_plane_nt<real, 32, INVERSE>(c, in, out, p, s);
+        case 64: return launch_plane_nt<real, 64, INVERSE>(c, in, out, p, s);
+        case 128: return launch_plane_nt<real, 128, INVERSE>(c, in, out, p, s);
+        case 256: return launch_plane_nt<real, 256, INVERSE>(c, in, out, p, s);
         default: break;
     }
-    if (sizeof(real) == 4 && c->g.Ny == 512) return launch_plane<float, 512, INVERSE>(c, in, out, p, s);
+    if (sizeof(real) == 4 && c->g.Ny == 512) return launch_plane_nt<float, 512, INVERSE>(c, in, out, p, s);
     set_error("plane transform: unsupported plane %d x %d", c->g.Ny, c->g.Nz);
     return HYMD_ERR_INVALID;
 }
@@ -470,18 +558,23 @@ int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int n
     p.nunits = F * nplanes; p.nplanes = nplanes;
     p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
     p.r_fs = r_fs; p.r_xs = (long long)g.Ny * g.Nz; p.r_ys = g.Nz;
-    p.ghost = 0; p.xdup_plane = -1;
+    p.ghost = 0; p.xdup_plane = -1; p.derive = 0; p.dky = p.dkz = 0;
     return c->f64 ? dispatch_plane<double, false>(c, real_in, k_out, p, s)
                   : dispatch_plane<float, false>(c, real_in, k_out, p, s);
 }
 
-// spectra [f][plane][Ny][Nzcp] -> real planes; ghost: the ghost-padded force-mesh layout with the
-// periodic y/z images (and plane 0 duplicated into plane nxl on a single GPU)
+// spectra [f][plane][Ny][Nzcp] -> F real planes; ghost: the ghost-padded force-mesh layout with the
+// periodic y/z images (and plane 0 duplicated into plane nxl on a single GPU).
+// derive: k_in holds 2F/3 spectra (per potential row: -i k_x V and -i V, x-inverted) and the
+// kernel forms the k_y / k_z components itself (PlaneParams::derive).
 int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int nplanes, void* real_out,
-                  bool ghost, cudaStream_t s) {
+                  bool ghost, bool derive, cudaStream_t s) {
     const Geometry& g = c->g;
     PlaneParams p;
-    p.nunits = F * nplanes; p.nplanes = nplanes;
+    if (derive && F % 3 != 0) { set_error("plane_inverse: derive needs 3 outputs per row"); return HYMD_ERR_INVALID; }
+    p.nunits = (derive ? F / 3 : F) * nplanes; p.nplanes = nplanes;
+    p.derive = derive ? 1 : 0;
+    p.dky = 2.0 * M_PI / g.box[1]; p.dkz = 2.0 * M_PI / g.box[2];
     p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
     if (ghost) {
         p.r_ys = g.Nzp; p.r_xs = (long long)(g.Ny + 1) * g.Nzp; p.r_fs = g.ghost_elems;

@@ -329,9 +329,10 @@ static int yz_forward(hymd_ctx* c, void* real_in, int F, void* k_out, long long 
 }
 
 static int yz_inverse(hymd_ctx* c, void* k_in, long long k_fs, int F, void* real_out, bool ghost,
-                      cudaStream_t s) {
+                      cudaStream_t s, bool derive = false) {
     const Geometry& g = c->g;
-    if (c->plane) return plane_inverse(c, k_in, k_fs, F, g.nxl, real_out, ghost, s);
+    if (c->plane) return plane_inverse(c, k_in, k_fs, F, g.nxl, real_out, ghost, derive, s);
+    if (derive) { set_error("derived force components need the plane kernels"); return HYMD_ERR_STATE; }
     cufftHandle h;
     HYMD_CHECK(plan_get(c, ghost ? PK_2D_C2R_GHOST : PK_2D_C2R, F, &h));
     return exec_c2r(c, h, k_in, real_out, s);
@@ -377,18 +378,21 @@ static int copy_to_work(hymd_ctx* c, const void* k_in, int F, cudaStream_t s) {
     return HYMD_OK;
 }
 
-int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s) {
+int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s,
+                      bool derive) {
+    // derive: k_in holds 2F/3 spectra (xline.cu, XParams::two); only those cross the transpose
     // the x transform has been applied.  P > 1: k_in is in the k layout and goes through the
     // inverse transpose into the work layout.  P == 1: k_in is the work layout [f][Nx+1][Ny][Nzcp]
     // for ghost outputs and the k layout [f][Nx][Ny][Nzcp] otherwise.
     const Geometry& g = c->g;
     const long long plane = (long long)g.Ny * g.Nzcp;
+    const int Fin = derive ? F / 3 * 2 : F;
     if (g.P > 1) {
-        HYMD_CHECK(ensure_work(c, F));
-        HYMD_CHECK(transpose_inverse(c, F, k_in, s));
-        return yz_inverse(c, c->wA, (g.nxl + 1) * plane, F, real_out, ghost, s);
+        HYMD_CHECK(ensure_work(c, Fin));
+        HYMD_CHECK(transpose_inverse(c, Fin, k_in, s));
+        return yz_inverse(c, c->wA, (g.nxl + 1) * plane, F, real_out, ghost, s, derive);
     }
-    return yz_inverse(c, k_in, (ghost ? g.Nx + 1 : g.Nx) * plane, F, real_out, ghost, s);
+    return yz_inverse(c, k_in, (ghost ? g.Nx + 1 : g.Nx) * plane, F, real_out, ghost, s, derive);
 }
 
 int fft_inverse(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost, cudaStream_t s) {

@@ -36,6 +36,7 @@ struct XParams {
     long long xs_f, fs_f;            // ... of the 3U (or 3) force outputs
     long long xs_v, fs_v, xs_pf, fs_pf;   // optional k-space outputs (not x-inverted)
     int pme;
+    int two;                         // 2 outputs per row (-i k_x V, -i V): the plane c2r applies k_y, k_z
 };
 
 // shared-memory position of element (pos, c): rows of CH columns, one extra row of padding per
@@ -48,18 +49,26 @@ template <int NX, int CH>
 constexpr int field_elems() { return (NX + NX / Radix<NX>::R2) * CH; }
 
 // forward: strided radix-R1 over n1 (+ twiddle), then contiguous radix-R2 over n2.
-template <typename real, int NX, int CH>
-__device__ __forceinline__ void fft_fwd_step1(Cx<real>* buf, const Cx<real>* __restrict__ tw, int task) {
+// REG: the twiddles w^(n2 k1) of this thread's (constant) n2 come from registers (TwiddleRegs)
+template <typename real, int NX, int CH, bool REG>
+__device__ __forceinline__ void fft_fwd_step1(Cx<real>* buf, const Cx<real>* __restrict__ tw,
+                                              const TwiddleRegs<real, Radix<NX>::R1>& twr, int task) {
     constexpr int R1 = Radix<NX>::R1, R2 = Radix<NX>::R2;
     const int c = task % CH, n2 = task / CH;
     Cx<real> v[R1];
 #pragma unroll
     for (int n1 = 0; n1 < R1; ++n1) v[n1] = buf[spos<NX, CH>(n1 * R2 + n2, c)];
     dft_reg<real, R1, -1>(v);
+    if constexpr (REG) {
+        twr.template apply<false>(v);
 #pragma unroll
-    for (int k1 = 0; k1 < R1; ++k1) {
-        const Cx<real> w = tw[(n2 * k1) & (NX - 1)];   // exp(-2 pi i n2 k1 / NX)
-        buf[spos<NX, CH>(k1 * R2 + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+        for (int k1 = 0; k1 < R1; ++k1) buf[spos<NX, CH>(k1 * R2 + n2, c)] = v[k1];
+    } else {
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            const Cx<real> w = tw[(n2 * k1) & (NX - 1)];   // exp(-2 pi i n2 k1 / NX)
+            buf[spos<NX, CH>(k1 * R2 + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+        }
     }
 }
 template <typename real, int NX, int CH>
@@ -74,19 +83,26 @@ __device__ __forceinline__ void fft_fwd_step2(Cx<real>* buf, int task) {
     for (int k2 = 0; k2 < R2; ++k2) buf[spos<NX, CH>(k1 * R2 + k2, c)] = v[k2];
 }
 // inverse: contiguous radix-R2 over k2 (+ conjugate twiddle), then strided radix-R1 over k1.
-template <typename real, int NX, int CH>
-__device__ __forceinline__ void fft_inv_stepA(Cx<real>* buf, const Cx<real>* __restrict__ tw, int task) {
+template <typename real, int NX, int CH, bool REG>
+__device__ __forceinline__ void fft_inv_stepA(Cx<real>* buf, const Cx<real>* __restrict__ tw,
+                                              const TwiddleRegs<real, Radix<NX>::R2>& twr, int task) {
     constexpr int R2 = Radix<NX>::R2;
     const int c = task % CH, k1 = task / CH;
     Cx<real> v[R2];
 #pragma unroll
     for (int k2 = 0; k2 < R2; ++k2) v[k2] = buf[spos<NX, CH>(k1 * R2 + k2, c)];
     dft_reg<real, R2, +1>(v);
+    if constexpr (REG) {
+        twr.template apply<true>(v);
 #pragma unroll
-    for (int n2 = 0; n2 < R2; ++n2) {
-        Cx<real> w = tw[(n2 * k1) & (NX - 1)];
-        w.y = -w.y;
-        buf[spos<NX, CH>(k1 * R2 + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+        for (int n2 = 0; n2 < R2; ++n2) buf[spos<NX, CH>(k1 * R2 + n2, c)] = v[n2];
+    } else {
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) {
+            Cx<real> w = tw[(n2 * k1) & (NX - 1)];
+            w.y = -w.y;
+            buf[spos<NX, CH>(k1 * R2 + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+        }
     }
 }
 template <typename real, int NX, int CH>
@@ -166,11 +182,21 @@ __global__ void __launch_bounds__(256) xline_kernel(
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    // twiddles of this thread's constant sub-index (R*CH divides the CTA size, so every task a
+    // thread gets in the strided task loops below has the same n2 / k1), loaded while the tile flies
+    constexpr bool REG = sizeof(real) == 4 && R1 <= 16 && R2 <= 16 && R1 >= 4 && NT % (R1 * CH) == 0 &&
+                         NT % (R2 * CH) == 0;
+    TwiddleRegs<real, R1> twf;      // forward: n2 constant, k1 = 0 .. R1-1
+    TwiddleRegs<real, R2> twi;      // inverse: k1 constant, n2 = 0 .. R2-1
+    if constexpr (REG) {
+        twf.init(twg, (tid % (R2 * CH)) / CH, NX);
+        twi.init(twg, (tid % (R1 * CH)) / CH, NX);
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- forward FFT along x, all fields ----
     for (int task = tid; task < p.T * R2 * CH; task += NT)
-        fft_fwd_step1<real, NX, CH>(data + (task / (R2 * CH)) * FE, tw, task % (R2 * CH));
+        fft_fwd_step1<real, NX, CH, REG>(data + (task / (R2 * CH)) * FE, tw, twf, task % (R2 * CH));
     __syncthreads();
     for (int task = tid; task < p.T * R1 * CH; task += NT)
         fft_fwd_step2<real, NX, CH>(data + (task / (R1 * CH)) * FE, task % (R1 * CH));
@@ -235,11 +261,11 @@ __global__ void __launch_bounds__(256) xline_kernel(
         __syncthreads();
         // ---- inverse FFT along x of V^ and k_x V^ (2 x R1 x CH tasks) ----
         for (int task = tid; task < 2 * R1 * CH; task += NT)
-            fft_inv_stepA<real, NX, CH>(task < R1 * CH ? wV : wK, tw, task % (R1 * CH));
+            fft_inv_stepA<real, NX, CH, REG>(task < R1 * CH ? wV : wK, tw, twi, task % (R1 * CH));
         __syncthreads();
         // ---- last butterfly stage + F_d = -i k_d V:  -i (a + i b) = b - i a, stored straight from
         // the registers (V -> F_y, F_z; k_x V -> F_x); lanes = neighbouring columns: 64-byte runs ----
-        Cx<real>* f0 = fout + (long long)(3 * u) * p.fs_f;
+        Cx<real>* f0 = fout + (long long)((p.two ? 2 : 3) * u) * p.fs_f;
         for (int task = tid; task < 2 * R2 * CH; task += NT) {
             const bool isK = task >= R2 * CH;
             const int rem = task % (R2 * CH), c = rem % CH, n2 = rem / CH;
@@ -256,6 +282,8 @@ __global__ void __launch_bounds__(256) xline_kernel(
                 Cx<real>* ox = o + (long long)(n1 * R2) * p.xs_f;
                 if (isK) {
                     store_cx(ox, Cx<real>{v[n1].y, -v[n1].x});
+                } else if (p.two) {
+                    store_cx(ox + p.fs_f, Cx<real>{v[n1].y, -v[n1].x});
                 } else {
                     store_cx(ox + p.fs_f, Cx<real>{ky * v[n1].y, -ky * v[n1].x});
                     store_cx(ox + 2 * p.fs_f, Cx<real>{kz * v[n1].y, -kz * v[n1].x});
@@ -290,7 +318,7 @@ static int launch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vou
     const Geometry& g = c->g;
     XParams p;
     p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nyl = g.nyl; p.y0 = g.y0; p.Nzc = g.Nzc; p.Nzcp = g.Nzcp;
-    p.T = T; p.U = U; p.pme = pme ? 1 : 0;
+    p.T = T; p.U = U; p.pme = pme ? 1 : 0; p.two = c->grad2 ? 1 : 0;
     p.ncols = (long long)g.nyl * g.Nzcp;
     const KLayout lin = klayout(c, T), lv = klayout(c, U);
     p.xs_in = lin.xs; p.fs_in = lin.fs;
@@ -300,7 +328,7 @@ static int launch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vou
         p.xs_f = (long long)g.Ny * g.Nzcp;
         p.fs_f = (long long)(g.Nx + 1) * p.xs_f;
     } else {
-        const KLayout lf = klayout(c, 3 * U);
+        const KLayout lf = klayout(c, (c->grad2 ? 2 : 3) * U);
         p.xs_f = lf.xs; p.fs_f = lf.fs;
     }
     const size_t smem = sizeof(Cx<real>) * ((size_t)NX + (size_t)(2 + T) * field_elems<NX, CH>());

@@ -278,3 +278,24 @@ def test_domain_decomposition_returns_cell_order_single_gpu():
                                   torch.as_tensor(gid, device="cuda"))
     assert isinstance(outt[0], torch.Tensor) and outt[0].is_cuda
     assert np.array_equal(np.sort(outt[1].cpu().numpy()), gid)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("env", [{"HYMD_B200_GRAD2": "0"}, {"HYMD_B200_PLANE_NT": "256"},
+                                 {"HYMD_B200_PLANE_NT": "256", "HYMD_B200_GRAD2": "0"},
+                                 {"HYMD_B200_NO_FUSED": "1"}, {"HYMD_B200_NO_PLANE": "1"}])
+def test_kernel_variants_match_oracle(dtype, env, monkeypatch):
+    """The tuning switches select other kernels for the same arithmetic: three force spectra per
+    potential row instead of two (+ k_y, k_z applied by the plane c2r), two 256-thread CTAs per SM
+    in the plane transforms instead of one of 512, cuFFT instead of the x-line / plane kernels."""
+    from gpu_common import GpuRun, OracleRun, rel_err
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cfg, pos, types, q = _system(20000, [32, 64, 64], [4.0, 5.0, 6.0], dtype, seed=31, coulomb=True)
+    g = GpuRun(cfg, pos, types, charges=q)
+    o = OracleRun(cfg, pos, types, charges=q)
+    assert rel_err(g.forces(), o.force) < TOL[dtype]
+    assert rel_err(g.eforces(), o.elec_forces) < TOL[dtype]
+    for t in range(cfg.n_types):
+        for d in range(3):
+            assert rel_err(g.force_mesh[t][d].value.cpu().numpy(), o.st.force_mesh[t][d]) < TOL[dtype]

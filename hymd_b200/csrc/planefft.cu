@@ -72,6 +72,43 @@ __device__ __forceinline__ void st_l2(Cx<double>* p, Cx<double> v) {
 __device__ __forceinline__ void group_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// ---- bulk async copies (TMA, non-tensor form) + mbarrier -------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PLANE_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PLANE_WAIT_DONE;\n"
+        "bra PLANE_WAIT_LOOP;\n"
+        "PLANE_WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared, completion counted in bytes on an mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_store(void* dst, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes (st.shared / st.global) made visible to the async proxy (the copy engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 __device__ __forceinline__ float shfl(float v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 __device__ __forceinline__ double shfl(double v, int lane) { return __shfl_sync(0xffffffffu, v, lane); }
 
@@ -87,6 +124,7 @@ struct PlaneParams {
     // k_y / k_z (with the Nyquist rule of SURVEY.md section 7) are applied while loading.
     int derive;
     double dky, dkz;                // 2 pi / L_y, 2 pi / L_z
+    int row_tma;                    // staged row phase (Cfg::TMA_ROWS): bit 0 = inputs, bit 1 = outputs via bulk copies
 };
 
 // Work decomposition inside the 512-thread CTA.
@@ -95,28 +133,46 @@ struct PlaneParams {
 //   row phase   : every warp on its own CW row pairs, synchronised with __syncwarp only.
 // Butterfly inputs are loaded from global memory straight into registers and the last butterfly
 // stage stores straight to global memory, so each FFT makes exactly one trip through shared memory.
-template <typename real, int NY, int NZ, int NT_> struct PlaneCfg {
+template <typename real, int NY, int NZ, int NT_, int TILES> struct PlaneCfg {
     static constexpr int NT = NT_, NW = NT / 32, CTAS = 512 / NT;            // CTAs per SM
     static constexpr int R1y = Radix<NY>::R1, R2y = Radix<NY>::R2, R1z = Radix<NZ>::R1, R2z = Radix<NZ>::R2;
     static constexpr int NZC = NZ / 2 + 1, NZCP = NZC + (NZC & 1);
     static constexpr int CG = 64 / (int)sizeof(Cx<real>);
     static constexpr int GT = CG * 16, NG = NT / GT;
     using LA = LayA<NY, CG>;
-    static constexpr int NTILE = (2 * NG * LA::ELEMS * (int)sizeof(Cx<real>) <= 144 * 1024 / CTAS) ? 2 : 1;
+    static constexpr int NTILE = (TILES == 2 && 2 * NG * LA::ELEMS * (int)sizeof(Cx<real>) <= 144 * 1024 / CTAS) ? 2 : 1;
     static constexpr int CW = 32 / R1z;                                    // row pairs per warp pass
     using LB = LayB<NZ, CW>;
     static constexpr int COL_ELEMS = NG * NTILE * LA::ELEMS, ROW_ELEMS = NW * LB::ELEMS;
+    // Row phase of the inverse, fp32: every warp stages its input rows (CW row pairs of the scratch
+    // plane = ONE contiguous block) and its output rows in shared memory and moves them with bulk
+    // async copies (TMA) instead of 8-byte loads / 4-byte stores: the load/store unit was the
+    // limiter (ncu: lg_throttle + long_scoreboard = 45 % of the stall samples).
+    static constexpr int IN_ELEMS = CW * 2 * NZCP;                    // complex, per warp
+    static constexpr bool HAS_IN = TILES == 2;                        // single-tile build: no staged inputs (L1 matters more)
+    static constexpr int IN_ALLOC = HAS_IN ? IN_ELEMS : 0;
+    static constexpr int OUT_REALS = CW * 2 * (NZ + 4) + 32 * CW;     // reals, per warp (ghost pitch + bank gaps)
+    static constexpr size_t ROW_BYTES = sizeof(Cx<real>) * (size_t)ROW_ELEMS;
+    static constexpr size_t ROW_IN_BYTES = ROW_BYTES + (size_t)NW * IN_ALLOC * sizeof(Cx<real>);
+    static constexpr size_t ROW_TMA_BYTES = ROW_IN_BYTES + (size_t)NW * OUT_REALS * sizeof(real);
+    static constexpr bool TMA_ROWS = TILES == 2 && sizeof(real) == 4 && (NZCP % 2 == 0) && (NZ % 4 == 0) &&
+                                     ROW_TMA_BYTES + sizeof(Cx<real>) * (NY + NZ) <= (size_t)216 * 1024 / CTAS;
+    static constexpr size_t COL_BYTES = sizeof(Cx<real>) * (size_t)COL_ELEMS;
     static constexpr int TILE = COL_ELEMS > ROW_ELEMS ? COL_ELEMS : ROW_ELEMS;
     static constexpr size_t SMEM = sizeof(Cx<real>) * (size_t)(NY + NZ + TILE);
-    static_assert((NY / 2) % CW == 0, "row pairs per warp pass must divide the plane");
+    // inverse kernel: staged inputs only / staged inputs + outputs
+    static constexpr size_t smem_inv(bool staged_out) {
+        size_t row = TMA_ROWS ? (staged_out ? ROW_TMA_BYTES : ROW_IN_BYTES) : ROW_BYTES;
+        return sizeof(Cx<real>) * (size_t)(NY + NZ) + (COL_BYTES > row ? COL_BYTES : row);
+    }
 };
 
 // ---- inverse: spectra [ky][kz] -> real plane ------------------------------------------------------
-template <typename real, int NY, int NZ, int NTH>
+template <typename real, int NY, int NZ, int NTH, int TILES>
 __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
     const Cx<real>* __restrict__ in, Cx<real>* __restrict__ scratch, real* __restrict__ out,
     const Cx<real>* __restrict__ twy_g, const Cx<real>* __restrict__ twz_g, PlaneParams p) {
-    using Cfg = PlaneCfg<real, NY, NZ, NTH>;
+    using Cfg = PlaneCfg<real, NY, NZ, NTH, TILES>;
     using LA = typename Cfg::LA;
     using LB = typename Cfg::LB;
     constexpr int NT = Cfg::NT, NW = Cfg::NW, CG = Cfg::CG, GT = Cfg::GT, NG = Cfg::NG, NTILE = Cfg::NTILE,
@@ -143,6 +199,21 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
     TwiddleRegs<real, R2z> twr;
     if constexpr (REGC) twc.init(twy, (gt / CG) % R1y, NY);
     if constexpr (REGR) twr.init(twz, lane % R1z, NZ);
+    // staged row phase (Cfg::TMA_ROWS): per-warp input rows, output rows and one mbarrier
+    __shared__ __align__(8) uint64_t row_bar[NW];
+    unsigned char* row_stage = reinterpret_cast<unsigned char*>(tile) + Cfg::ROW_BYTES;
+    Cx<real>* inb = reinterpret_cast<Cx<real>*>(row_stage) + warp * Cfg::IN_ALLOC;
+    real* outb = reinterpret_cast<real*>(row_stage + (size_t)NW * Cfg::IN_ALLOC * sizeof(Cx<real>)) +
+                 warp * Cfg::OUT_REALS;
+    // output row rr of this warp starts at rr * r_ys + (rr / 2) * ogap: row pairs stay contiguous
+    // (one bulk store each) and the two pairs of a pass fall into different banks
+    const int ogap = (48 - (2 * p.r_ys) % 32) % 32;
+    uint32_t row_parity = 0;
+    if constexpr (Cfg::TMA_ROWS) {
+        if (lane == 0) mbar_init(&row_bar[warp], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
 
     const int ND = p.derive ? 3 : 1;
     const real dky = (real)p.dky, dkz = (real)p.dkz;
@@ -236,10 +307,120 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
                 if (NTILE == 1) group_sync(g + 1, GT);
             }
         }
+        if constexpr (Cfg::TMA_ROWS) fence_async_global();   // scratch stores -> visible to the copy engine
         __syncthreads();
         // ---------------- row phase: c2r along z on row pairs (A + iB) ----------------
         real* obase = out + f * p.r_fs + x * p.r_xs;
         real* obase2 = (p.xdup_plane >= 0 && x == 0) ? out + f * p.r_fs + p.xdup_plane * p.r_xs : nullptr;
+        if constexpr (Cfg::TMA_ROWS) {
+            constexpr int NPG = (NY / 2) / CW;
+            constexpr uint32_t IN_BYTES = Cfg::IN_ELEMS * sizeof(Cx<real>);
+            // the CW row pairs of a pass are 2 CW consecutive rows of the scratch plane: one copy
+            const bool tin = Cfg::HAS_IN && (p.row_tma & 1), tout = p.row_tma & 2;
+            if (tin && lane == 0 && warp < NPG) {
+                mbar_expect_tx(&row_bar[warp], IN_BYTES);
+                bulk_load(inb, scr + (long long)(2 * warp * CW) * NZCP, IN_BYTES, &row_bar[warp]);
+            }
+            for (int pg = warp; pg < NPG; pg += NW) {
+                const int c = lane / R1z, k1 = lane % R1z;
+                Cx<real> v[R2z];
+                if (tin) {
+                    mbar_wait(&row_bar[warp], row_parity);
+                    row_parity ^= 1;
+                }
+                {
+                    const Cx<real>* rowA = tin ? inb + (2 * c) * NZCP : scr + (long long)(2 * (pg * CW + c)) * NZCP;
+                    const Cx<real>* rowB = rowA + NZCP;
+#pragma unroll
+                    for (int k2 = 0; k2 < R2z; ++k2) {
+                        const int k = k1 + R1z * k2;
+                        const int kk = (2 * k <= NZ) ? k : NZ - k;
+                        const Cx<real> A = tin ? rowA[kk] : ld_l2(rowA + kk), B = tin ? rowB[kk] : ld_l2(rowB + kk);
+                        real sg = (2 * k < NZ) ? (real)1 : (real)-1;         // mirrored half: conjugates
+                        if (k == 0 || 2 * k == NZ) sg = 0;                   // c2r drops these imaginary parts
+                        v[k2] = {A.x - sg * B.y, sg * A.y + B.x};
+                    }
+                }
+                __syncwarp();                                               // staged rows consumed
+                if (tin && lane == 0 && pg + NW < NPG) {                    // next pass flies during this one
+                    mbar_expect_tx(&row_bar[warp], IN_BYTES);
+                    bulk_load(inb, scr + (long long)(2 * (pg + NW) * CW) * NZCP, IN_BYTES, &row_bar[warp]);
+                }
+                dft_reg<real, R2z, +1>(v);
+                if constexpr (REGR) {
+                    twr.template apply<true>(v);
+#pragma unroll
+                    for (int n2 = 0; n2 < R2z; ++n2) wtile[LB::at(k1 * R2z + n2, c)] = v[n2];
+                } else {
+#pragma unroll
+                    for (int n2 = 0; n2 < R2z; ++n2) {
+                        Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
+                        w.y = -w.y;
+                        wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                    }
+                }
+                __syncwarp();
+                if (tout && lane < CW) bulk_wait_read();                    // previous pass's stores have left outb
+                __syncwarp();
+                for (int task = lane; task < CW * R2z; task += 32) {
+                    const int c2 = task / R2z, n2 = task % R2z;
+                    Cx<real> u[R1z];
+#pragma unroll
+                    for (int k1b = 0; k1b < R1z; ++k1b) u[k1b] = wtile[LB::at(k1b * R2z + n2, c2)];
+                    dft_reg<real, R1z, +1>(u);
+                    if (!tout) {                                            // straight from the registers
+                        const int y0 = 2 * (pg * CW + c2);
+#pragma unroll
+                        for (int dup = 0; dup < 2; ++dup) {
+                            real* ob = dup ? obase2 : obase;
+                            if (ob == nullptr) continue;
+                            real* og = ob + (long long)y0 * p.r_ys + n2;
+#pragma unroll
+                            for (int n1 = 0; n1 < R1z; ++n1) {
+                                __stcs(og + n1 * R2z, u[n1].x);
+                                __stcs(og + p.r_ys + n1 * R2z, u[n1].y);
+                            }
+                            if (p.ghost) {
+                                if (n2 == 0) { og[NZ] = u[0].x; og[p.r_ys + NZ] = u[0].y; }
+                                if (y0 == 0) {
+                                    real* oy = ob + (long long)NY * p.r_ys + n2;
+#pragma unroll
+                                    for (int n1 = 0; n1 < R1z; ++n1) __stcs(oy + n1 * R2z, u[n1].x);
+                                    if (n2 == 0) oy[NZ] = u[0].x;
+                                }
+                            }
+                        }
+                        continue;
+                    }
+                    real* oa = outb + (2 * c2) * p.r_ys + c2 * ogap + n2;
+#pragma unroll
+                    for (int n1 = 0; n1 < R1z; ++n1) {
+                        oa[n1 * R2z] = u[n1].x;
+                        oa[p.r_ys + n1 * R2z] = u[n1].y;
+                    }
+                    if (p.ghost && n2 < p.r_ys - NZ) {      // periodic image z = Nz, zeros in the row padding
+                        oa[NZ] = n2 == 0 ? u[0].x : (real)0;
+                        oa[p.r_ys + NZ] = n2 == 0 ? u[0].y : (real)0;
+                    }
+                }
+                if (tout) fence_async_smem();
+                __syncwarp();
+                if (tout && lane < CW) {                                    // lane = row pair: 2 rows, contiguous
+                    const int y0 = 2 * (pg * CW + lane);
+                    const real* sb = outb + (2 * lane) * p.r_ys + lane * ogap;
+                    const uint32_t pair_bytes = 2u * (uint32_t)p.r_ys * (uint32_t)sizeof(real);
+#pragma unroll
+                    for (int dup = 0; dup < 2; ++dup) {
+                        real* ob = dup ? obase2 : obase;
+                        if (ob == nullptr) continue;
+                        bulk_store(ob + (long long)y0 * p.r_ys, sb, pair_bytes);
+                        if (p.ghost && y0 == 0) bulk_store(ob + (long long)NY * p.r_ys, sb, pair_bytes / 2);
+                    }
+                    bulk_commit();
+                }
+            }
+            if (tout && lane < CW) bulk_wait_read();                        // before the tiles are reused
+        } else
         for (int pg = warp; pg < (NY / 2) / CW; pg += NW) {
             {   // exactly 32 tasks: (row pair c, k1)
                 const int c = lane / R1z, k1 = lane % R1z;
@@ -306,11 +487,11 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
 }
 
 // ---- forward: real plane -> spectra [ky][kz] -----------------------------------------------------
-template <typename real, int NY, int NZ, int NTH>
+template <typename real, int NY, int NZ, int NTH, int TILES>
 __global__ void __launch_bounds__(NTH, 512 / NTH) plane_r2c_kernel(
     const real* __restrict__ in, Cx<real>* __restrict__ scratch, Cx<real>* __restrict__ out,
     const Cx<real>* __restrict__ twy_g, const Cx<real>* __restrict__ twz_g, PlaneParams p) {
-    using Cfg = PlaneCfg<real, NY, NZ, NTH>;
+    using Cfg = PlaneCfg<real, NY, NZ, NTH, TILES>;
     using LA = typename Cfg::LA;
     using LB = typename Cfg::LB;
     constexpr int NT = Cfg::NT, NW = Cfg::NW, CG = Cfg::CG, GT = Cfg::GT, NG = Cfg::NG, NTILE = Cfg::NTILE,
@@ -489,17 +670,25 @@ static int plane_tables(hymd_ctx* c) {
     return HYMD_OK;
 }
 
-// Threads per CTA: 512 (one CTA per SM, default) or 256 (two CTAs per SM; measured slower at
-// 256^2 planes: 0.84 vs 0.69 ms for the 12 inverse transforms of C4 -- the second scratch
-// plane per SM costs more L2 than the phase overlap gains).
-static int plane_threads() {
-    if (const char* e = getenv("HYMD_B200_PLANE_NT")) return atoi(e) == 256 ? 256 : 512;
-    return 512;
+// Build variants of the plane kernels (HYMD_B200_PLANE_TILES):
+//   1 (default): one column tile per group (two group barriers per chunk), row phase straight
+//                from / to global memory; 74 KB of shared memory at 256^2 fp32;
+//   2          : double-buffered column tiles (one barrier per chunk) and, in the inverse, row
+//                inputs (and with HYMD_B200_ROW_TMA=3 outputs) staged through bulk async copies;
+//                143 - 208 KB of shared memory.
+// Measured at C4 (12 inverse transforms): 0.623 ms (1) vs 0.656 (2, staged inputs) vs 0.68 - 0.82
+// (2, staged outputs).  These kernels speed up with every KB of L1 left to the load/store unit
+// (padding the allocation of the same kernel by 64 KB: 0.66 -> 0.85 ms), which outweighs what the
+// copy engine saves in load/store instructions.  Two 256-thread CTAs per SM instead of one of 512
+// were slower as well (0.84 vs 0.69 ms: the second scratch plane per SM) and are gone.
+static int plane_tiles() {
+    if (const char* e = getenv("HYMD_B200_PLANE_TILES")) return atoi(e) == 2 ? 2 : 1;
+    return 1;
 }
 
-template <typename real, int N, int NTH, bool INVERSE>
+template <typename real, int N, int NTH, int TILES, bool INVERSE>
 static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
-    using Cfg = PlaneCfg<real, N, N, NTH>;
+    using Cfg = PlaneCfg<real, N, N, NTH, TILES>;
     HYMD_CHECK(plane_tables(c));
     int sms = 0;
     HYMD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev));
@@ -515,14 +704,18 @@ static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParam
     }
     if ((size_t)grid * N * Cfg::NZCP * sizeof(Cx<real>) > c->plane_scratch_bytes) grid = 2 * sms;
     if (INVERSE) {
-        auto kern = plane_c2r_kernel<real, N, N, NTH>;
-        HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>((const Cx<real>*)in, (Cx<real>*)c->plane_scratch, (real*)out,
+        auto kern = plane_c2r_kernel<real, N, N, NTH, TILES>;
+        size_t smem = Cfg::smem_inv((p.row_tma & 2) != 0);
+        if (const char* e = getenv("HYMD_B200_PLANE_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;   // L1 carve-out experiment
+        HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, Cfg::NT, smem, s>>>((const Cx<real>*)in, (Cx<real>*)c->plane_scratch, (real*)out,
                                              (const Cx<real>*)c->ytw, (const Cx<real>*)c->ztw, p);
     } else {
-        auto kern = plane_r2c_kernel<real, N, N, NTH>;
-        HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>((const real*)in, (Cx<real>*)c->plane_scratch, (Cx<real>*)out,
+        auto kern = plane_r2c_kernel<real, N, N, NTH, TILES>;
+        size_t smem = Cfg::SMEM;
+        if (const char* e = getenv("HYMD_B200_PLANE_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;
+        HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, Cfg::NT, smem, s>>>((const real*)in, (Cx<real>*)c->plane_scratch, (Cx<real>*)out,
                                              (const Cx<real>*)c->ytw, (const Cx<real>*)c->ztw, p);
     }
     HYMD_LAUNCH_CHECK(c);
@@ -531,8 +724,8 @@ static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParam
 
 template <typename real, int N, bool INVERSE>
 static int launch_plane_nt(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
-    return plane_threads() == 512 ? launch_plane<real, N, 512, INVERSE>(c, in, out, p, s)
-                                  : launch_plane<real, N, 256, INVERSE>(c, in, out, p, s);
+    return plane_tiles() == 1 ? launch_plane<real, N, 512, 1, INVERSE>(c, in, out, p, s)
+                              : launch_plane<real, N, 512, 2, INVERSE>(c, in, out, p, s);
 }
 
 template <typename real, bool INVERSE>
@@ -558,7 +751,7 @@ int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int n
     p.nunits = F * nplanes; p.nplanes = nplanes;
     p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
     p.r_fs = r_fs; p.r_xs = (long long)g.Ny * g.Nz; p.r_ys = g.Nz;
-    p.ghost = 0; p.xdup_plane = -1; p.derive = 0; p.dky = p.dkz = 0;
+    p.ghost = 0; p.xdup_plane = -1; p.derive = 0; p.dky = p.dkz = 0; p.row_tma = 0;
     return c->f64 ? dispatch_plane<double, false>(c, real_in, k_out, p, s)
                   : dispatch_plane<float, false>(c, real_in, k_out, p, s);
 }
@@ -575,6 +768,8 @@ int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int npla
     p.nunits = (derive ? F / 3 : F) * nplanes; p.nplanes = nplanes;
     p.derive = derive ? 1 : 0;
     p.dky = 2.0 * M_PI / g.box[1]; p.dkz = 2.0 * M_PI / g.box[2];
+    p.row_tma = 1;
+    if (const char* e = getenv("HYMD_B200_ROW_TMA")) p.row_tma = atoi(e) & 3;
     p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
     if (ghost) {
         p.r_ys = g.Nzp; p.r_xs = (long long)(g.Ny + 1) * g.Nzp; p.r_fs = g.ghost_elems;

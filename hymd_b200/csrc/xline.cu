@@ -117,14 +117,14 @@ __device__ __forceinline__ void fft_inv_stepB(Cx<real>* buf, int task) {
     for (int n1 = 0; n1 < R1; ++n1) buf[spos<NX, CH>(n1 * R2 + n2, c)] = v[n1];
 }
 
-template <typename real, int NX, int CH>
-__global__ void __launch_bounds__(256) xline_kernel(
+template <typename real, int NX, int CH, int NTH>
+__global__ void __launch_bounds__(NTH) xline_kernel(
     const Cx<real>* __restrict__ in, Cx<real>* __restrict__ fout, Cx<real>* __restrict__ vout,
     Cx<real>* __restrict__ pfout, const real* __restrict__ tab, const Cx<real>* __restrict__ twg,
     const real* __restrict__ Au, const real* __restrict__ cu, real coef, real inv_m, XParams p) {
     constexpr int R1 = Radix<NX>::R1, R2 = Radix<NX>::R2;
     constexpr int FE = field_elems<NX, CH>();
-    constexpr int NT = 256;
+    constexpr int NT = NTH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Cx<real>* tw = reinterpret_cast<Cx<real>*>(smem_raw);      // NX twiddles
     Cx<real>* wV = tw + NX;                                     // FE: V^ (then its x-inverse)
@@ -312,7 +312,7 @@ bool xline_supported(const hymd_ctx* c) {
     return xline_smem(n, c->T, c->f64) <= 220 * 1024;
 }
 
-template <typename real, int NX, int CH>
+template <typename real, int NX, int CH, int NTH = 256>
 static int launch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vout, void* pfout,
                     int T, int U, cudaStream_t s) {
     const Geometry& g = c->g;
@@ -336,14 +336,14 @@ static int launch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vou
         set_error("xline: %d types need %zu B of shared memory", T, smem);
         return HYMD_ERR_INVALID;
     }
-    auto kern = xline_kernel<real, NX, CH>;
+    auto kern = xline_kernel<real, NX, CH, NTH>;
     HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const double m = (double)g.Nx * g.Ny * g.Nz;
     const real coef = (real)(4.0 * 3.14159265358979323846 * c->cfg.elec_conversion / m);
     const unsigned int blocks = (unsigned int)((p.ncols + CH - 1) / CH);
     // PME: A = [1/M] lives right after the U x T matrix (build_interaction); its row "0" is used
     const real* Au = pme ? (const real*)c->Au + (size_t)c->U * c->T : (const real*)c->Au;
-    kern<<<blocks, 256, smem, s>>>((const Cx<real>*)in, (Cx<real>*)fout, (Cx<real>*)vout,
+    kern<<<blocks, NTH, smem, s>>>((const Cx<real>*)in, (Cx<real>*)fout, (Cx<real>*)vout,
                                    (Cx<real>*)pfout, (const real*)c->tab,
                                    (const Cx<real>*)c->xtw, Au, (const real*)c->cu,
                                    pme ? (real)(coef * m) : (real)0, (real)(1.0 / m), p);

@@ -281,13 +281,13 @@ def test_domain_decomposition_returns_cell_order_single_gpu():
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("env", [{"HYMD_B200_GRAD2": "0"}, {"HYMD_B200_PLANE_NT": "256"},
-                                 {"HYMD_B200_PLANE_NT": "256", "HYMD_B200_GRAD2": "0"},
+@pytest.mark.parametrize("env", [{"HYMD_B200_GRAD2": "0"}, {"HYMD_B200_PLANE_TILES": "2"},
+                                 {"HYMD_B200_PLANE_TILES": "2", "HYMD_B200_ROW_TMA": "3", "HYMD_B200_GRAD2": "0"},
                                  {"HYMD_B200_NO_FUSED": "1"}, {"HYMD_B200_NO_PLANE": "1"}])
 def test_kernel_variants_match_oracle(dtype, env, monkeypatch):
     """The tuning switches select other kernels for the same arithmetic: three force spectra per
-    potential row instead of two (+ k_y, k_z applied by the plane c2r), two 256-thread CTAs per SM
-    in the plane transforms instead of one of 512, cuFFT instead of the x-line / plane kernels."""
+    potential row instead of two (+ k_y, k_z applied by the plane c2r), double-buffered column
+    tiles with row inputs / outputs staged by bulk async copies in the plane transforms, cuFFT instead of the x-line / plane kernels."""
     from gpu_common import GpuRun, OracleRun, rel_err
     for k, v in env.items():
         monkeypatch.setenv(k, v)

@@ -69,6 +69,35 @@ __device__ __forceinline__ void st_l2(Cx<float>* p, Cx<float> v) {
 __device__ __forceinline__ void st_l2(Cx<double>* p, Cx<double> v) {
     __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
 }
+// Scratch plane with explicit L2 eviction priorities (HYMD_B200_SCR_HINT, PlaneParams::scr_hint):
+// written "evict last" (it must survive in L2 until the other phase reads it, next to the
+// streaming traffic of 148 CTAs), read "evict first" (dead after the read).
+__device__ __forceinline__ uint64_t l2_policy_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ Cx<float> ld_hint(const Cx<float>* p, uint64_t pol) {
+    Cx<float> v;
+    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ Cx<double> ld_hint(const Cx<double>* p, uint64_t pol) {
+    Cx<double> v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_hint(Cx<float>* p, Cx<float> v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(Cx<double>* p, Cx<double> v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void group_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -124,6 +153,8 @@ struct PlaneParams {
     // k_y / k_z (with the Nyquist rule of SURVEY.md section 7) are applied while loading.
     int derive;
     double dky, dkz;                // 2 pi / L_y, 2 pi / L_z
+    int scr_hint;                   // scratch plane accesses carry L2 eviction priorities
+    int scr_alt;                    // experiment: alternate between two scratch planes per CTA (L2 footprint x2)
     int row_tma;                    // staged row phase (Cfg::TMA_ROWS): bit 0 = inputs, bit 1 = outputs via bulk copies
 };
 
@@ -183,10 +214,12 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
     Cx<real>* twz = twy + NY;
     Cx<real>* tile = twz + NZ;
     const int tid = threadIdx.x;
+    const uint64_t pol_last = l2_policy_last(), pol_first = l2_policy_first();
     for (int i = tid; i < NY; i += NT) twy[i] = twy_g[i];
     for (int i = tid; i < NZ; i += NT) twz[i] = twz_g[i];
     __syncthreads();
-    Cx<real>* scr = scratch + (size_t)blockIdx.x * NY * NZCP;
+    Cx<real>* scr0 = scratch + (size_t)blockIdx.x * NY * NZCP;
+    Cx<real>* scr = scr0;
     constexpr int NCHG = (NZC + CG - 1) / CG;             // the pad column is never read
     const int g = tid / GT, gt = tid % GT;
     const int warp = tid / 32, lane = tid % 32;
@@ -224,6 +257,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
         const int fin = p.derive ? 2 * fu + (d > 0 ? 1 : 0) : fu;
         const int f = p.derive ? 3 * fu + d : fu;
         const int mode = p.derive ? d : 0;
+        if (p.scr_alt) scr = scr0 + (size_t)((unit / gridDim.x * 3 + d) & 1) * gridDim.x * NY * NZCP;
         const Cx<real>* src = in + fin * p.k_fs + x * p.k_xs;
         // v[k2] = spectrum element (k_y = k1 + R1y k2, column col): times k_y (mode 1) or k_z (mode 2)
         auto scale_chunk = [&](Cx<real> (&v)[R2y], int k1, int col) {
@@ -301,7 +335,10 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
                     if (c0 + c < NZC) {
 #pragma unroll
                         for (int n1 = 0; n1 < R1y; ++n1)
-                            st_l2(scr + (long long)(n1 * R2y + n2) * NZCP + c0 + c, v[n1]);
+                        {
+                            Cx<real>* e = scr + (long long)(n1 * R2y + n2) * NZCP + c0 + c;
+                            if (p.scr_hint) st_hint(e, v[n1], pol_last); else st_l2(e, v[n1]);
+                        }
                     }
                 }
                 if (NTILE == 1) group_sync(g + 1, GT);
@@ -431,7 +468,8 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
                 for (int k2 = 0; k2 < R2z; ++k2) {
                     const int k = k1 + R1z * k2;
                     const int kk = (2 * k <= NZ) ? k : NZ - k;
-                    const Cx<real> A = ld_l2(rowA + kk), B = ld_l2(rowB + kk);
+                    const Cx<real> A = p.scr_hint ? ld_hint(rowA + kk, pol_first) : ld_l2(rowA + kk),
+                                   B = p.scr_hint ? ld_hint(rowB + kk, pol_first) : ld_l2(rowB + kk);
                     real s = (2 * k < NZ) ? (real)1 : (real)-1;          // mirrored half: conjugates
                     if (k == 0 || 2 * k == NZ) s = 0;                    // c2r drops these imaginary parts
                     v[k2] = {A.x - s * B.y, s * A.y + B.x};
@@ -751,7 +789,9 @@ int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int n
     p.nunits = F * nplanes; p.nplanes = nplanes;
     p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
     p.r_fs = r_fs; p.r_xs = (long long)g.Ny * g.Nz; p.r_ys = g.Nz;
-    p.ghost = 0; p.xdup_plane = -1; p.derive = 0; p.dky = p.dkz = 0; p.row_tma = 0;
+    p.ghost = 0; p.xdup_plane = -1; p.derive = 0; p.dky = p.dkz = 0; p.row_tma = 0; p.scr_alt = 0;
+    p.scr_hint = 1;
+    if (const char* e = getenv("HYMD_B200_SCR_HINT")) p.scr_hint = atoi(e) != 0;
     return c->f64 ? dispatch_plane<double, false>(c, real_in, k_out, p, s)
                   : dispatch_plane<float, false>(c, real_in, k_out, p, s);
 }
@@ -770,6 +810,10 @@ int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int npla
     p.dky = 2.0 * M_PI / g.box[1]; p.dkz = 2.0 * M_PI / g.box[2];
     p.row_tma = 1;
     if (const char* e = getenv("HYMD_B200_ROW_TMA")) p.row_tma = atoi(e) & 3;
+    p.scr_alt = 0;
+    if (const char* e = getenv("HYMD_B200_SCR_ALT")) p.scr_alt = atoi(e) != 0;
+    p.scr_hint = 1;
+    if (const char* e = getenv("HYMD_B200_SCR_HINT")) p.scr_hint = atoi(e) != 0;
     p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
     if (ghost) {
         p.r_ys = g.Nzp; p.r_xs = (long long)(g.Ny + 1) * g.Nzp; p.r_fs = g.ghost_elems;

@@ -191,7 +191,8 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
         if (g.fbz > 52) g.fbz = 52;
     }
     for (int a = 0; a < 3; ++a) g.box[a] = cfg->box[a];
-    g.ncell = (long long)g.nxl * g.Ny * g.Nz;
+    g.nbz = zbins_per_row(g.Nz);
+    g.ncell = (long long)g.nxl * g.Ny * g.nbz;
     g.vx = P == 1 ? g.nxl : g.nxl + 1;
     g.real_elems = (long long)g.vx * g.Ny * g.Nz;
     g.ghost_elems = (long long)(g.nxl + 1) * (g.Ny + 1) * g.Nzp;

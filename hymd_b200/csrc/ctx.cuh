@@ -59,6 +59,20 @@ void set_error(const char* fmt, ...);
 // Tile of mesh cells a paint CTA owns (vertices) / a readout CTA stages through TMA.
 constexpr int PAINT_TX = 8, PAINT_TY = 8, PAINT_TZ = 32;
 
+// Binning granularity of the counting sort (sort.cu).  Paint and readout never need the particles
+// of a single cell, only those of the z-range a 32-vertex tile draws from -- cells z0-1 .. z0+31
+// for the paint, z0 .. z0+31 for the tiled readout -- so every (x,y) cell row is cut into bins
+//     [0..30] [31] [32..62] [63] ...          (the cell Nz-1 is always a bin of its own)
+// i.e. 2 bins per tile: bin 2t = cells 32t .. 32t+30, bin 2t+1 = the boundary cell shared by the
+// tiles t and t+1 (and by the periodic wrap).  1/16 of the counters of a per-cell sort: the
+// counter array (4 MB instead of 67 MB at 256^3) stays in L2 and the scan is negligible.
+constexpr int ZBIN = 32;
+static_assert(PAINT_TZ == ZBIN, "paint tiles and sort bins share their z extent");
+__host__ __device__ inline int zbins_per_row(int Nz) { return 2 * ((Nz + ZBIN - 1) / ZBIN); }
+__host__ __device__ inline int zbin_of(int cz, int Nz) {
+    return 2 * (cz / ZBIN) + ((cz % ZBIN == ZBIN - 1 || cz == Nz - 1) ? 1 : 0);
+}
+
 // Sorted particle record.  Coordinates are unsigned fixed point in local-slab grid units:
 // integer part = mesh cell, fraction = CIC offset d.  meta = original index | type << idx_bits.
 struct __align__(16) Rec32 {
@@ -73,7 +87,7 @@ constexpr int REC32_IDX_BITS = 27;  // <= 134M particles per GPU, <= 32 types
 constexpr int REC64_IDX_BITS = 40;
 
 struct DeviceScalars {
-    unsigned int max_cell_count;   // max particles in one cell (paint fixed-point scale)
+    unsigned int max_cell_count;   // max particles in one sort bin (>= any cell: bound for the paint fixed-point scale)
     unsigned int qmax_bits;        // max |charge| as float bits
     unsigned int out_of_slab;      // particles outside the local slab (multi-GPU)
     unsigned int pad;
@@ -88,7 +102,8 @@ struct Geometry {
     int Nzp;               // padded real z pitch of ghost meshes
     int fbx, fby, fbz;     // fraction bits of the fixed-point coordinates
     double box[3];
-    long long ncell;       // nxl*Ny*Nz
+    long long ncell;       // sort bins: nxl*Ny*zbins_per_row(Nz)
+    int nbz;               // bins per (x,y) cell row
     long long real_elems;  // nxl*Ny*Nz
     long long ghost_elems; // (nxl+1)*(Ny+1)*Nzp
     long long k_elems;     // Nx*nyl*Nzcp  (complex elements per spectrum)
@@ -133,7 +148,7 @@ struct hymd_ctx {
     void* rec;              // cell-sorted records of the last sort
     void* rec_alt;          // the other half of the double buffer (staging area of the next sort)
     int64_t order_n;        // particle count the order in `rec` is valid for (-1: none)
-    uint32_t* cell_start;   // ncell + 2: [0] = 0, then the per-cell cursors (see sort.cu)
+    uint32_t* cell_start;   // ncell + 2: [0] = 0, then the per-bin cursors (see sort.cu)
     void* q_sorted;
     hymd::DeviceScalars* scalars;
     void* scan_tmp;

@@ -18,7 +18,7 @@
 namespace hymd {
 
 struct ReadoutParams {
-    int Nx, Ny, Nz, nxl;
+    int Nx, Ny, Nz, nxl, nbz;
     int fbx, fby, fbz;
     int tx, ty, tz, bz;      // tile of cells and box z extent (tz + 1 rounded up for TMA)
     int ntx, nty, ntz;
@@ -73,6 +73,7 @@ template <> struct RTraits<double> {
 
 constexpr int READOUT_NT = 512, READOUT_NW = READOUT_NT / 32;
 constexpr int READOUT_TZ = 32, READOUT_BZ = 36;   // tile z extent and box z extent (tz + 1 -> x4)
+static_assert(READOUT_TZ == ZBIN, "readout tiles and sort bins share their z extent");
 constexpr int READOUT_MAX_STAGES = 8;
 
 // Persistent CTAs (one per SM) walk the tiles of TX x TY x 32 cells in a software pipeline:
@@ -119,13 +120,14 @@ __global__ void __launch_bounds__(READOUT_NT, 1) readout_kernel(
     auto load_runs = [&](int it) {
         int x0, y0, z0;
         tile_origin(it, x0, y0, z0);
-        const int zb = min(z0 + TZ, p.Nz);
         run_pa = 0; run_len = 0;
         const int gx = x0 + tid / TY, gy = y0 + tid % TY;
         if (gx < p.nxl && gy < p.Ny) {
-            const long long rowbase = ((long long)gx * p.Ny + gy) * p.Nz;
-            run_pa = start[rowbase + z0];
-            run_len = start[rowbase + zb] - run_pa;
+            // cells z0 .. z0+31 of the row = sort bins 2 tz and 2 tz + 1 (ctx.cuh, ZBIN)
+            const long long rowbase = ((long long)gx * p.Ny + gy) * p.nbz;
+            const int tzi = z0 / TZ;
+            run_pa = start[rowbase + 2 * tzi];
+            run_len = start[rowbase + min(2 * tzi + 2, p.nbz)] - run_pa;
         }
     };
     auto publish_runs = [&](int it) {
@@ -426,7 +428,7 @@ static int launch_readout_tile(hymd_ctx* c, void* d_force, cudaStream_t s) {
     using Tr = RTraits<real>;
     const Geometry& g = c->g;
     ReadoutParams p;
-    p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nxl = g.nxl;
+    p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nxl = g.nxl; p.nbz = g.nbz;
     p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
     p.tx = TX; p.ty = TY; p.tz = c->rtz; p.bz = c->rbz;
     p.ntx = (g.nxl + p.tx - 1) / p.tx;

@@ -1,7 +1,8 @@
 // Cell binning of the local particles: replaces pm.decompose (main.py:977-980, 1007).
 //
-// A counting sort keyed by the (local-slab, row-major) mesh cell of each particle, on ONE array
-// a[0 .. ncell] (a[0] stays 0, cur = a + 1):
+// A counting sort keyed by the (local-slab, row-major) z-bin of each particle's mesh cell (ctx.cuh,
+// ZBIN: two bins per 32 cells of an (x,y) cell row), on ONE array a[0 .. nbins] (a[0] stays 0,
+// cur = a + 1):
 //   count   : atomicAdd(cur[key], 1) per particle                        -> cur[k] = count of cell k
 //   scan    : exclusive prefix sum of cur[0 .. ncell) in place           -> cur[k] = start of cell k
 //   scatter : slot = atomicAdd(cur[key], 1); record[slot] = fixed-point coordinates | index | type
@@ -17,7 +18,7 @@
 namespace hymd {
 
 struct SortParams {
-    int Nx, Ny, Nz, nxl, x0;
+    int Nx, Ny, Nz, nxl, x0, nbz;
     int fbx, fby, fbz;
     double sx, sy, sz;  // N/L per axis
 };
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
         r.uz = pack_coord<UT>(cz, dz, p.fbz);
         r.meta = idx | (type << IDX_BITS);
         stage[j] = r;
-        const uint32_t k = (uint32_t)(((long long)lx * p.Ny + cy) * p.Nz + cz);
+        const uint32_t k = (uint32_t)(((long long)lx * p.Ny + cy) * p.nbz + zbin_of(cz, p.Nz));
         r1 = atomicAdd(&cnt[k], 1u) + 1;
     }
     unsigned int m = __reduce_max_sync(0xffffffffu, r1);
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(
         const RecT r = stage[j];
         const long long lx = (long long)(r.ux >> p.fbx), cy = (long long)(r.uy >> p.fby),
                         cz = (long long)(r.uz >> p.fbz);
-        const uint32_t k = (uint32_t)((lx * p.Ny + cy) * p.Nz + cz);
+        const uint32_t k = (uint32_t)((lx * p.Ny + cy) * p.nbz + zbin_of((int)cz, p.Nz));
         const size_t slot = atomicAdd(&cur[k], 1u);
         rec[slot] = r;
         if (q != nullptr) {
@@ -164,7 +165,7 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
                      int64_t n, bool reuse, cudaStream_t s) {
     const Geometry& g = c->g;
     SortParams p;
-    p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nxl = g.nxl; p.x0 = g.x0;
+    p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nxl = g.nxl; p.x0 = g.x0; p.nbz = g.nbz;
     p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
     p.sx = g.Nx / g.box[0]; p.sy = g.Ny / g.box[1]; p.sz = g.Nz / g.box[2];
     const long long ncell = g.ncell;

@@ -43,6 +43,22 @@ __device__ __forceinline__ UT pack_coord(int cell, double frac, int fb) {
     return ((UT)cell << fb) | f;
 }
 
+// Consecutive lanes with the same key form a run (in REUSE mode the lanes walk the previous bin
+// order, so a warp usually holds two or three runs): one counter atomic per run instead of one per
+// lane.  Returns this lane's run head, its rank inside the run and the run length.
+__device__ __forceinline__ void warp_runs(uint32_t key, unsigned& head_lane, unsigned& rank, unsigned& count) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || key != prev;
+    const unsigned H = __ballot_sync(0xffffffffu, head);
+    const unsigned upto = (2u << lane) - 1u;          // lanes 0 .. lane (lane 31: all)
+    head_lane = 31u - (unsigned)__clz((int)(H & upto));
+    const unsigned above = H & ~upto;
+    const unsigned next = above ? (unsigned)__ffs((int)above) - 1u : 32u;
+    rank = lane - head_lane;
+    count = next - head_lane;
+}
+
 // Pass 1.  Thread j handles one particle: in REUSE mode the particle that sat at sorted slot j
 // in the previous call (its index and type come from the previous record), otherwise particle j
 // of the caller's arrays.  It converts the CURRENT position to the fixed-point record, leaves it
@@ -55,6 +71,7 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
                                                     DeviceScalars* __restrict__ sc) {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     unsigned int r1 = 0, bad = 0;
+    uint32_t key = 0xffffffffu;                        // lanes past the end: a run of their own
     if (j < n) {
         UT idx, type;
         if (REUSE) {
@@ -81,9 +98,11 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
         r.uz = pack_coord<UT>(cz, dz, p.fbz);
         r.meta = idx | (type << IDX_BITS);
         stage[j] = r;
-        const uint32_t k = (uint32_t)(((long long)lx * p.Ny + cy) * p.nbz + zbin_of(cz, p.Nz));
-        r1 = atomicAdd(&cnt[k], 1u) + 1;
+        key = (uint32_t)(((long long)lx * p.Ny + cy) * p.nbz + zbin_of(cz, p.Nz));
     }
+    unsigned head_lane, rank, count;
+    warp_runs(key, head_lane, rank, count);
+    if (rank == 0 && j < n) r1 = atomicAdd(&cnt[key], count) + count;
     unsigned int m = __reduce_max_sync(0xffffffffu, r1);
     unsigned int b = __reduce_add_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0) {
@@ -100,12 +119,21 @@ __global__ void __launch_bounds__(256) scatter_kernel(
     DeviceScalars* __restrict__ sc) {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     float aq = 0.f;
+    RecT r;
+    uint32_t key = 0xffffffffu;
     if (j < n) {
-        const RecT r = stage[j];
+        r = stage[j];
         const long long lx = (long long)(r.ux >> p.fbx), cy = (long long)(r.uy >> p.fby),
                         cz = (long long)(r.uz >> p.fbz);
-        const uint32_t k = (uint32_t)((lx * p.Ny + cy) * p.nbz + zbin_of((int)cz, p.Nz));
-        const size_t slot = atomicAdd(&cur[k], 1u);
+        key = (uint32_t)((lx * p.Ny + cy) * p.nbz + zbin_of((int)cz, p.Nz));
+    }
+    unsigned head_lane, rank, count;
+    warp_runs(key, head_lane, rank, count);
+    uint32_t base = 0;
+    if (rank == 0 && j < n) base = atomicAdd(&cur[key], count);
+    base = __shfl_sync(0xffffffffu, base, (int)head_lane);
+    if (j < n) {
+        const size_t slot = (size_t)base + rank;
         rec[slot] = r;
         if (q != nullptr) {
             const real qi = q[r.meta & (((UT)1 << IDX_BITS) - 1)];

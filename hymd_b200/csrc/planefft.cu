@@ -34,6 +34,9 @@ struct LayA {
     static constexpr int R2 = Radix<N>::R2;
     static constexpr int ELEMS = (N + N / R2) * CH;
     __device__ static __forceinline__ int at(int pos, int c) { return (pos + pos / R2) * CH + c; }
+    // pos = hi * R2 + lo with lo < R2 (no division; with a compile-time hi or lo the compiler folds
+    // the product into the address offset)
+    __device__ static __forceinline__ int at2(int hi, int lo, int c) { return (hi * (R2 + 1) + lo) * CH + c; }
 };
 // LayB: FFT along the contiguous axis, one padded row per transform (row pairs).
 template <int N, int CP>
@@ -42,6 +45,7 @@ struct LayB {
     static constexpr int PITCH = N + N / R2;
     static constexpr int ELEMS = PITCH * CP;
     __device__ static __forceinline__ int at(int pos, int c) { return c * PITCH + pos + pos / R2; }
+    __device__ static __forceinline__ int at2(int hi, int lo, int c) { return c * PITCH + hi * (R2 + 1) + lo; }
 };
 
 // ---- memory access helpers ---------------------------------------------------------------------
@@ -315,13 +319,13 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
                     if constexpr (REGC) {
                         twc.template apply<true>(v);
 #pragma unroll
-                        for (int n2 = 0; n2 < R2y; ++n2) cur[LA::at(k1 * R2y + n2, c)] = v[n2];
+                        for (int n2 = 0; n2 < R2y; ++n2) cur[LA::at2(k1, n2, c)] = v[n2];
                     } else {
 #pragma unroll
                         for (int n2 = 0; n2 < R2y; ++n2) {
                             Cx<real> w = twy[(n2 * k1) & (NY - 1)];
                             w.y = -w.y;
-                            cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                            cur[LA::at2(k1, n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
                         }
                     }
                 }
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
                     const int c = task % CG, n2 = task / CG;
                     Cx<real> v[R1y];
 #pragma unroll
-                    for (int k1 = 0; k1 < R1y; ++k1) v[k1] = cur[LA::at(k1 * R2y + n2, c)];
+                    for (int k1 = 0; k1 < R1y; ++k1) v[k1] = cur[LA::at2(k1, n2, c)];
                     dft_reg<real, R1y, +1>(v);
                     if (c0 + c < NZC) {
 #pragma unroll
@@ -387,13 +391,13 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
                 if constexpr (REGR) {
                     twr.template apply<true>(v);
 #pragma unroll
-                    for (int n2 = 0; n2 < R2z; ++n2) wtile[LB::at(k1 * R2z + n2, c)] = v[n2];
+                    for (int n2 = 0; n2 < R2z; ++n2) wtile[LB::at2(k1, n2, c)] = v[n2];
                 } else {
 #pragma unroll
                     for (int n2 = 0; n2 < R2z; ++n2) {
                         Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
                         w.y = -w.y;
-                        wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                        wtile[LB::at2(k1, n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
                     }
                 }
                 __syncwarp();
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
                     const int c2 = task / R2z, n2 = task % R2z;
                     Cx<real> u[R1z];
 #pragma unroll
-                    for (int k1b = 0; k1b < R1z; ++k1b) u[k1b] = wtile[LB::at(k1b * R2z + n2, c2)];
+                    for (int k1b = 0; k1b < R1z; ++k1b) u[k1b] = wtile[LB::at2(k1b, n2, c2)];
                     dft_reg<real, R1z, +1>(u);
                     if (!tout) {                                            // straight from the registers
                         const int y0 = 2 * (pg * CW + c2);
@@ -478,13 +482,13 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
                 if constexpr (REGR) {
                     twr.template apply<true>(v);
 #pragma unroll
-                    for (int n2 = 0; n2 < R2z; ++n2) wtile[LB::at(k1 * R2z + n2, c)] = v[n2];
+                    for (int n2 = 0; n2 < R2z; ++n2) wtile[LB::at2(k1, n2, c)] = v[n2];
                 } else {
 #pragma unroll
                     for (int n2 = 0; n2 < R2z; ++n2) {
                         Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
                         w.y = -w.y;
-                        wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                        wtile[LB::at2(k1, n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
                     }
                 }
             }
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
                 const int c = task / R2z, n2 = task % R2z;
                 Cx<real> v[R1z];
 #pragma unroll
-                for (int k1 = 0; k1 < R1z; ++k1) v[k1] = wtile[LB::at(k1 * R2z + n2, c)];
+                for (int k1 = 0; k1 < R1z; ++k1) v[k1] = wtile[LB::at2(k1, n2, c)];
                 dft_reg<real, R1z, +1>(v);
                 const int y0 = 2 * (pg * CW + c);
 #pragma unroll
@@ -590,12 +594,12 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_r2c_kernel(
                 if constexpr (REGR) {
                     twr.template apply<false>(v);
 #pragma unroll
-                    for (int k1 = 0; k1 < R1z; ++k1) wtile[LB::at(k1 * R2z + n2, c)] = v[k1];
+                    for (int k1 = 0; k1 < R1z; ++k1) wtile[LB::at2(k1, n2, c)] = v[k1];
                 } else {
 #pragma unroll
                     for (int k1 = 0; k1 < R1z; ++k1) {
                         const Cx<real> w = twz[(n2 * k1) & (NZ - 1)];
-                        wtile[LB::at(k1 * R2z + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+                        wtile[LB::at2(k1, n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
                     }
                 }
             }
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_r2c_kernel(
                 const int c = lane / R1z, k1 = lane % R1z;
                 Cx<real> v[R2z];
 #pragma unroll
-                for (int n2 = 0; n2 < R2z; ++n2) v[n2] = wtile[LB::at(k1 * R2z + n2, c)];
+                for (int n2 = 0; n2 < R2z; ++n2) v[n2] = wtile[LB::at2(k1, n2, c)];
                 dft_reg<real, R2z, -1>(v);
                 // Z[NZ - k] lives in lane (R1z - k1) % R1z of the same row, register R2z-1-k2
                 // (k1 == 0: own register (R2z - k2) % R2z)
@@ -647,12 +651,12 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_r2c_kernel(
                 if constexpr (REGC) {
                     twc.template apply<false>(v);
 #pragma unroll
-                    for (int k1 = 0; k1 < R1y; ++k1) cur[LA::at(k1 * R2y + n2, c)] = v[k1];
+                    for (int k1 = 0; k1 < R1y; ++k1) cur[LA::at2(k1, n2, c)] = v[k1];
                 } else {
 #pragma unroll
                     for (int k1 = 0; k1 < R1y; ++k1) {
                         const Cx<real> w = twy[(n2 * k1) & (NY - 1)];
-                        cur[LA::at(k1 * R2y + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+                        cur[LA::at2(k1, n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
                     }
                 }
             }
@@ -661,7 +665,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_r2c_kernel(
                 const int c = task % CG, k1 = task / CG;
                 Cx<real> v[R2y];
 #pragma unroll
-                for (int n2 = 0; n2 < R2y; ++n2) v[n2] = cur[LA::at(k1 * R2y + n2, c)];
+                for (int n2 = 0; n2 < R2y; ++n2) v[n2] = cur[LA::at2(k1, n2, c)];
                 dft_reg<real, R2y, -1>(v);
                 if (c0 + c < NZCP) {
 #pragma unroll

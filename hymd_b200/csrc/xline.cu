@@ -45,6 +45,11 @@ template <int NX, int CH>
 __device__ __forceinline__ int spos(int pos, int c) {
     return (pos + pos / Radix<NX>::R2) * CH + c;
 }
+// pos = hi * R2 + lo with lo < R2: no division
+template <int NX, int CH>
+__device__ __forceinline__ int spos2(int hi, int lo, int c) {
+    return (hi * (Radix<NX>::R2 + 1) + lo) * CH + c;
+}
 template <int NX, int CH>
 constexpr int field_elems() { return (NX + NX / Radix<NX>::R2) * CH; }
 
@@ -57,17 +62,17 @@ __device__ __forceinline__ void fft_fwd_step1(Cx<real>* buf, const Cx<real>* __r
     const int c = task % CH, n2 = task / CH;
     Cx<real> v[R1];
 #pragma unroll
-    for (int n1 = 0; n1 < R1; ++n1) v[n1] = buf[spos<NX, CH>(n1 * R2 + n2, c)];
+    for (int n1 = 0; n1 < R1; ++n1) v[n1] = buf[spos2<NX, CH>(n1, n2, c)];
     dft_reg<real, R1, -1>(v);
     if constexpr (REG) {
         twr.template apply<false>(v);
 #pragma unroll
-        for (int k1 = 0; k1 < R1; ++k1) buf[spos<NX, CH>(k1 * R2 + n2, c)] = v[k1];
+        for (int k1 = 0; k1 < R1; ++k1) buf[spos2<NX, CH>(k1, n2, c)] = v[k1];
     } else {
 #pragma unroll
         for (int k1 = 0; k1 < R1; ++k1) {
             const Cx<real> w = tw[(n2 * k1) & (NX - 1)];   // exp(-2 pi i n2 k1 / NX)
-            buf[spos<NX, CH>(k1 * R2 + n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
+            buf[spos2<NX, CH>(k1, n2, c)] = (k1 == 0) ? v[k1] : cmul(w, v[k1]);
         }
     }
 }
@@ -77,10 +82,10 @@ __device__ __forceinline__ void fft_fwd_step2(Cx<real>* buf, int task) {
     const int c = task % CH, k1 = task / CH;
     Cx<real> v[R2];
 #pragma unroll
-    for (int n2 = 0; n2 < R2; ++n2) v[n2] = buf[spos<NX, CH>(k1 * R2 + n2, c)];
+    for (int n2 = 0; n2 < R2; ++n2) v[n2] = buf[spos2<NX, CH>(k1, n2, c)];
     dft_reg<real, R2, -1>(v);
 #pragma unroll
-    for (int k2 = 0; k2 < R2; ++k2) buf[spos<NX, CH>(k1 * R2 + k2, c)] = v[k2];
+    for (int k2 = 0; k2 < R2; ++k2) buf[spos2<NX, CH>(k1, k2, c)] = v[k2];
 }
 // inverse: contiguous radix-R2 over k2 (+ conjugate twiddle), then strided radix-R1 over k1.
 template <typename real, int NX, int CH, bool REG>
@@ -90,18 +95,18 @@ __device__ __forceinline__ void fft_inv_stepA(Cx<real>* buf, const Cx<real>* __r
     const int c = task % CH, k1 = task / CH;
     Cx<real> v[R2];
 #pragma unroll
-    for (int k2 = 0; k2 < R2; ++k2) v[k2] = buf[spos<NX, CH>(k1 * R2 + k2, c)];
+    for (int k2 = 0; k2 < R2; ++k2) v[k2] = buf[spos2<NX, CH>(k1, k2, c)];
     dft_reg<real, R2, +1>(v);
     if constexpr (REG) {
         twr.template apply<true>(v);
 #pragma unroll
-        for (int n2 = 0; n2 < R2; ++n2) buf[spos<NX, CH>(k1 * R2 + n2, c)] = v[n2];
+        for (int n2 = 0; n2 < R2; ++n2) buf[spos2<NX, CH>(k1, n2, c)] = v[n2];
     } else {
 #pragma unroll
         for (int n2 = 0; n2 < R2; ++n2) {
             Cx<real> w = tw[(n2 * k1) & (NX - 1)];
             w.y = -w.y;
-            buf[spos<NX, CH>(k1 * R2 + n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+            buf[spos2<NX, CH>(k1, n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
         }
     }
 }
@@ -111,10 +116,10 @@ __device__ __forceinline__ void fft_inv_stepB(Cx<real>* buf, int task) {
     const int c = task % CH, n2 = task / CH;
     Cx<real> v[R1];
 #pragma unroll
-    for (int k1 = 0; k1 < R1; ++k1) v[k1] = buf[spos<NX, CH>(k1 * R2 + n2, c)];
+    for (int k1 = 0; k1 < R1; ++k1) v[k1] = buf[spos2<NX, CH>(k1, n2, c)];
     dft_reg<real, R1, +1>(v);
 #pragma unroll
-    for (int n1 = 0; n1 < R1; ++n1) buf[spos<NX, CH>(n1 * R2 + n2, c)] = v[n1];
+    for (int n1 = 0; n1 < R1; ++n1) buf[spos2<NX, CH>(n1, n2, c)] = v[n1];
 }
 
 template <typename real, int NX, int CH, int NTH>
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(NTH) xline_kernel(
             const Cx<real>* buf = isK ? wK : wV;
             Cx<real> v[R1];
 #pragma unroll
-            for (int k1 = 0; k1 < R1; ++k1) v[k1] = buf[spos<NX, CH>(k1 * R2 + n2, c)];
+            for (int k1 = 0; k1 < R1; ++k1) v[k1] = buf[spos2<NX, CH>(k1, n2, c)];
             dft_reg<real, R1, +1>(v);
             if (!(full || col0 + c < p.ncols)) continue;
             const real ky = s_hk[0][c][1], kz = s_hk[0][c][2];

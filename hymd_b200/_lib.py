@@ -17,7 +17,7 @@ NCCL_ID_BYTES = 128
 F32, F64 = 0, 1
 SORT_REUSE_ORDER = 1
 (FIELD_PHI, FIELD_PHI_FOURIER, FIELD_FORCE_MESH, FIELD_V_EXT, FIELD_PHI_Q, FIELD_PHI_Q_FOURIER,
- FIELD_PSI, FIELD_ELEC_FIELD) = range(8)
+ FIELD_PSI, FIELD_ELEC_FIELD, FIELD_PHI_LAPLACIAN) = range(9)
 
 # every symbol include/hymd_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -26,7 +26,8 @@ EXPORTS = [
     "hymd_set_charges", "hymd_paint", "hymd_field_cycle", "hymd_readout", "hymd_pme_cycle",
     "hymd_materialize", "hymd_field_energy", "hymd_get_field", "hymd_ctx_status",
     "hymd_launch_count", "hymd_migrate_plan", "hymd_migrate_apply", "hymd_ctx_set_timing", "hymd_ctx_get_timings",
-    "hymd_sort_particles_ex", "hymd_ctx_reset_order", "hymd_ctx_paths",
+    "hymd_sort_particles_ex", "hymd_ctx_reset_order", "hymd_ctx_paths", "hymd_laplacian",
+    "hymd_field_pressure",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -87,6 +88,8 @@ def load():
     lib.hymd_pme_cycle.argtypes = [vp, vp, ctypes.c_int, vp]
     lib.hymd_materialize.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.hymd_field_energy.argtypes = [vp, P(dbl), dbl, dbl, dbl, P(dbl), vp]
+    lib.hymd_laplacian.argtypes = [vp, vp]
+    lib.hymd_field_pressure.argtypes = [vp, P(dbl), P(dbl), P(dbl), P(dbl), vp]
     lib.hymd_get_field.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, P(vp), P(i64), P(i64)]
     lib.hymd_ctx_status.argtypes = [vp, P(i64)]
     lib.hymd_ctx_paths.argtypes = [vp, P(i32)]

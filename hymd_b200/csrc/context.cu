@@ -251,7 +251,7 @@ int hymd_ctx_destroy(hymd_ctx* c) {
     void* bufs[] = {c->rec, c->rec_alt, c->cell_start, c->q_sorted,
                     c->scalars, c->scan_tmp, c->tab, c->xtw, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
                     c->phi_hat, c->f_hat, c->gmesh, c->v_hat, c->phif_hat, c->tmp_hat, c->v_ext,
-                    c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->psi_hat, c->emesh, c->psi, c->fft_work,
+                    c->phi_q, c->phiq_hat, c->phiqf_hat, c->e_hat, c->psi_hat, c->emesh, c->psi, c->fft_work, c->lap_hat, c->lap,
                     c->wA, c->wS, c->halo, c->ytw, c->ztw, c->plane_scratch};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -365,6 +365,7 @@ int hymd_paint(hymd_ctx* c, void* stream) {
     }
     c->phi_is_filtered = false;
     c->have_phi_hat = false;
+    c->have_lap = false;
     return HYMD_OK;
 }
 
@@ -474,6 +475,36 @@ int hymd_materialize(hymd_ctx* c, int want_phi, int want_phi_fourier, int want_v
     return materialize_impl(c, need_phi, need_v, s);
 }
 
+int hymd_laplacian(hymd_ctx* c, void* stream) {
+    if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (c->have_lap) return HYMD_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    // phi_fourier of the current spectra (field.py:577), then -k_d^2 and 3T inverse transforms
+    HYMD_CHECK(hymd_materialize(c, 0, 1, 0, 0, stream));
+    const size_t kb = (size_t)c->g.k_elems * 2 * c->rsz, rb = (size_t)c->g.real_elems * c->rsz;
+    HYMD_CHECK(dev_alloc(&c->lap_hat, 3 * (size_t)c->T * kb));
+    HYMD_CHECK(dev_alloc(&c->lap, 3 * (size_t)c->T * rb));
+    PhaseScope ps(c, HYMD_PHASE_BYPRODUCTS, s);
+    HYMD_CHECK(kspace_laplacian(c, s));
+    HYMD_CHECK(fft_inverse(c, c->lap_hat, 3 * c->T, c->lap, false, s));   // consumes lap_hat
+    c->have_lap = true;
+    return HYMD_OK;
+}
+
+int hymd_field_pressure(hymd_ctx* c, const double* A, const double* cc, const double* type_charges,
+                        double out[4], void* stream) {
+    if (!c || !A || !cc || !out) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (!c->phi_is_filtered || !c->have_lap) {
+        set_error("hymd_field_pressure needs the filtered densities (hymd_materialize) and hymd_laplacian");
+        return HYMD_ERR_STATE;
+    }
+    if (type_charges && !(c->cfg.pme && c->have_psi)) {
+        set_error("hymd_field_pressure with type charges needs psi (hymd_pme_cycle with want_psi)");
+        return HYMD_ERR_STATE;
+    }
+    return field_pressure(c, A, cc, type_charges, out, (cudaStream_t)stream);
+}
+
 int hymd_readout(hymd_ctx* c, void* d_force, void* stream) {
     if (!c || (c->np > 0 && !d_force)) { set_error("null argument"); return HYMD_ERR_INVALID; }
     if (!c->sorted || !c->have_forces) {
@@ -580,6 +611,9 @@ int hymd_get_field(hymd_ctx* c, int field_id, int t, int d, void** d_ptr, int64_
         case HYMD_FIELD_PSI: if (!c->psi) break; p = (char*)c->psi; real_geom(); break;
         case HYMD_FIELD_ELEC_FIELD:
             if (!d_ok || !c->emesh) break; p = (char*)c->emesh + d * gb; ghost_geom(); break;
+        case HYMD_FIELD_PHI_LAPLACIAN:
+            if (!t_ok || !d_ok || !c->lap || !c->have_lap) break;
+            p = (char*)c->lap + (size_t)(3 * t + d) * rb; real_geom(); break;
         default: break;
     }
     if (!p) {

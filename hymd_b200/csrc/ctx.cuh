@@ -177,6 +177,9 @@ struct hymd_ctx {
     void* phif_hat;       // T x k_elems (lazy, filtered & normalised = reference phi_fourier)
     void* tmp_hat;        // max(T,U) x k_elems (lazy scratch for c2r of by-products)
     void* v_ext;          // T x real_elems (lazy)
+    void* lap_hat;        // 3T x k_elems (lazy scratch): -k_d^2 phi_fourier
+    void* lap;            // 3T x real_elems (lazy): phi_laplacian[t][d], field.py:406-425
+    bool have_lap;          // lap valid for the current spectra
     bool phi_is_filtered;   // phi holds the filtered densities (reference semantics after update_field)
     bool have_phi_hat;      // raw density spectra of the last paint are valid
     bool have_phif;         // phif_hat valid for the current spectra
@@ -264,6 +267,7 @@ int paint_charges(hymd_ctx* c, cudaStream_t s);
 // kspace.cu
 int kspace_forces(hymd_ctx* c, bool want_v, bool want_phif, cudaStream_t s);
 int kspace_pme(hymd_ctx* c, bool want_psi, cudaStream_t s);
+int kspace_laplacian(hymd_ctx* c, cudaStream_t s);
 // slabfft.cu: 3-D transforms of F fields between the real layout [f][vx][Ny][Nz] (or the
 // ghost-padded force-mesh layout) and the k layout klayout(c, F)
 KLayout klayout(const hymd_ctx* c, int F);
@@ -311,4 +315,6 @@ int fill_ghosts(hymd_ctx* c, void* mesh, int nfields, cudaStream_t s);
 // energy.cu
 int field_energy(hymd_ctx* c, const double* chi, double kappa, double rho0, double a,
                  double out[2], cudaStream_t s);
+int field_pressure(hymd_ctx* c, const double* A, const double* cc, const double* qt, double out[4],
+                   cudaStream_t s);
 }  // namespace hymd

@@ -55,6 +55,92 @@ __global__ void energy_final_kernel(const double* __restrict__ partial, int nblo
     if (threadIdx.x == 0) { out[0] = s0[0] * dv; out[1] = s1[0] * dv; }
 }
 
+// Field terms of comp_pressure (pressure.py:105-127): per cell, with V_t = c_t + sum_j A_tj phi~_j
+// (+ q_t psi with electrostatics; V_bar_0 / V_bar of hamiltonian.py:157-186, 271-301, 423-475),
+//   s0 = sum_t V_t phi~_t,   s_{1+d} = sum_t V_t lap[t][d];
+// same fixed-order two-stage double reduction as the energies.
+constexpr int PR_TERMS = 4;
+
+template <typename real>
+__global__ void __launch_bounds__(256) pressure_partial_kernel(
+    const real* __restrict__ phi, const real* __restrict__ lap, long long field_stride, long long n,
+    int T, const double* __restrict__ A, const double* __restrict__ cc, const double* __restrict__ qt,
+    const real* __restrict__ psi, double* __restrict__ partial) {
+    double acc[PR_TERMS] = {0.0, 0.0, 0.0, 0.0};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ps = (qt != nullptr) ? (double)psi[i] : 0.0;
+        for (int t = 0; t < T; ++t) {
+            double v = cc[t];
+            for (int j = 0; j < T; ++j) v += A[t * T + j] * (double)phi[j * field_stride + i];
+            if (qt != nullptr) v += qt[t] * ps;
+            acc[0] += v * (double)phi[t * field_stride + i];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) acc[1 + d] += v * (double)lap[(3 * t + d) * field_stride + i];
+        }
+    }
+    __shared__ double sh[PR_TERMS][256];
+#pragma unroll
+    for (int k = 0; k < PR_TERMS; ++k) sh[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+#pragma unroll
+            for (int k = 0; k < PR_TERMS; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + w];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < PR_TERMS) partial[PR_TERMS * blockIdx.x + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void pressure_final_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+    __shared__ double sh[PR_TERMS][256];
+    double acc[PR_TERMS] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += 256)
+        for (int k = 0; k < PR_TERMS; ++k) acc[k] += partial[PR_TERMS * i + k];
+    for (int k = 0; k < PR_TERMS; ++k) sh[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+            for (int k = 0; k < PR_TERMS; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x < PR_TERMS) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+int field_pressure(hymd_ctx* c, const double* A, const double* cc, const double* qt, double out[4],
+                   cudaStream_t s) {
+    const Geometry& g = c->g;
+    const long long n = (long long)g.nxl * g.Ny * g.Nz;
+    const int T = c->T;
+    double* scratch = nullptr;   // [T*T A][T c][T q][4*EN_BLOCKS partial][4 out]
+    const size_t nd = (size_t)T * T + 2 * T + PR_TERMS * EN_BLOCKS + PR_TERMS;
+    HYMD_CUDA(cudaMallocAsync((void**)&scratch, sizeof(double) * nd, s));
+    double* d_A = scratch;
+    double* d_c = d_A + (size_t)T * T;
+    double* d_q = d_c + T;
+    double* d_part = d_q + T;
+    double* d_out = d_part + PR_TERMS * EN_BLOCKS;
+    HYMD_CUDA(cudaMemcpyAsync(d_A, A, sizeof(double) * T * T, cudaMemcpyHostToDevice, s));
+    HYMD_CUDA(cudaMemcpyAsync(d_c, cc, sizeof(double) * T, cudaMemcpyHostToDevice, s));
+    if (qt) HYMD_CUDA(cudaMemcpyAsync(d_q, qt, sizeof(double) * T, cudaMemcpyHostToDevice, s));
+    if (c->f64)
+        pressure_partial_kernel<double><<<EN_BLOCKS, 256, 0, s>>>(
+            (const double*)c->phi, (const double*)c->lap, g.real_elems, n, T, d_A, d_c,
+            qt ? d_q : nullptr, (const double*)c->psi, d_part);
+    else
+        pressure_partial_kernel<float><<<EN_BLOCKS, 256, 0, s>>>(
+            (const float*)c->phi, (const float*)c->lap, g.real_elems, n, T, d_A, d_c,
+            qt ? d_q : nullptr, (const float*)c->psi, d_part);
+    HYMD_LAUNCH_CHECK(c);
+    pressure_final_kernel<<<1, 256, 0, s>>>(d_part, EN_BLOCKS, d_out);
+    HYMD_LAUNCH_CHECK(c);
+    HYMD_CUDA(cudaMemcpyAsync(out, d_out, PR_TERMS * sizeof(double), cudaMemcpyDeviceToHost, s));
+    HYMD_CUDA(cudaStreamSynchronize(s));
+    HYMD_CUDA(cudaFreeAsync(scratch, s));
+    return HYMD_OK;
+}
+
 int field_energy(hymd_ctx* c, const double* chi, double kappa, double rho0, double a,
                  double out[2], cudaStream_t s) {
     const Geometry& g = c->g;

@@ -193,6 +193,43 @@ __global__ void __launch_bounds__(256) kspace_pme_kernel(
     }
 }
 
+// comp_laplacian (field.py:406-425): out[3t+d] = -k_d^2 * phi_fourier[t] (phi_fourier = the
+// filtered, 1/M-normalised density spectra), one pass for all types and directions.  -k^2 is
+// even, so the products stay Hermitian and the Nyquist entries need no special rule.
+template <typename real>
+__global__ void __launch_bounds__(256) kspace_laplacian_kernel(
+    const real* __restrict__ phif_hat, real* __restrict__ lap_hat, const real* __restrict__ tab, KParams p) {
+    const KTables<real> tb = make_tables(tab, p);
+    const int hz2 = p.Nzcp / 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.npairs; i += stride) {
+        const int iz = (int)(i % hz2) * 2;
+        const long long r = i / hz2;
+        const int iyl = (int)(r % p.nyl);
+        const int ix = (int)(r / p.nyl);
+        const int iy = iyl + p.y0;
+        const real kx2 = -tb.kx[ix] * tb.kx[ix], ky2 = -tb.ky[iy] * tb.ky[iy];
+        real kz2[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const bool valid = iz + j < p.Nzc;
+            const real kz = tb.kz[valid ? iz + j : 0];
+            kz2[j] = valid ? -kz * kz : (real)0;
+        }
+        const bool v1 = iz + 1 < p.Nzc;
+        const long long col = 2 * ((long long)iyl * p.Nzcp + iz);
+        for (int t = 0; t < p.T; ++t) {
+            real v[4];
+            load4(phif_hat + t * p.fs_in + ix * p.xs_in + col, v);
+            if (!v1) { v[2] = 0; v[3] = 0; }
+            real* o = lap_hat + (long long)(3 * t) * p.fs_f + ix * p.xs_f + col;
+            store4(o, kx2 * v[0], kx2 * v[1], kx2 * v[2], kx2 * v[3]);
+            store4(o + p.fs_f, ky2 * v[0], ky2 * v[1], ky2 * v[2], ky2 * v[3]);
+            store4(o + 2 * p.fs_f, kz2[0] * v[0], kz2[0] * v[1], kz2[1] * v[2], kz2[1] * v[3]);
+        }
+    }
+}
+
 static KParams make_kparams(const hymd_ctx* c) {
     const Geometry& g = c->g;
     KParams p;
@@ -245,6 +282,23 @@ static int launch_force(hymd_ctx* c, bool want_v, bool want_phif, cudaStream_t s
 int kspace_forces(hymd_ctx* c, bool want_v, bool want_phif, cudaStream_t s) {
     return c->f64 ? launch_force<double>(c, want_v, want_phif, s)
                   : launch_force<float>(c, want_v, want_phif, s);
+}
+
+// phif_hat (T fields) -> lap_hat (3T fields, k layout of 3T fields)
+int kspace_laplacian(hymd_ctx* c, cudaStream_t s) {
+    KParams p = make_kparams(c);
+    const KLayout lin = klayout(c, c->T), lo = klayout(c, 3 * c->T);
+    p.xs_in = 2 * lin.xs; p.fs_in = 2 * lin.fs;
+    p.xs_f = 2 * lo.xs; p.fs_f = 2 * lo.fs;
+    const unsigned int grid = kgrid(p.npairs);
+    if (c->f64)
+        kspace_laplacian_kernel<double><<<grid, 256, 0, s>>>((const double*)c->phif_hat, (double*)c->lap_hat,
+                                                            (const double*)c->tab, p);
+    else
+        kspace_laplacian_kernel<float><<<grid, 256, 0, s>>>((const float*)c->phif_hat, (float*)c->lap_hat,
+                                                           (const float*)c->tab, p);
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
 }
 
 int kspace_pme(hymd_ctx* c, bool want_psi, cudaStream_t s) {

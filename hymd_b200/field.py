@@ -12,6 +12,7 @@ this module                           reference
 ``update_field_force_q``              ``field.py:241-403``
 ``compute_self_energy_q``             ``field.py:203-238``
 ``compute_field_and_kinetic_energy``  ``field.py:619-703``
+``comp_laplacian``                    ``field.py:406-425``
 ``domain_decomposition``              ``field.py:1115-1178``
 ====================================  =========================
 
@@ -53,7 +54,7 @@ def initialize_pm(pmesh, config, comm=None):
     v_ext_fourier = [UnusedField(f"v_ext_fourier[{i}]") for i in range(4)]
     v_ext = [pm.field(_lib.FIELD_V_EXT, t) for t in range(T)]
     phi_transfer = [UnusedField(f"phi_transfer[{i}]") for i in range(3)]
-    phi_laplacian = [[UnusedField(f"phi_laplacian[{t}][{d}]") for d in range(3)] for t in range(T)]
+    phi_laplacian = [[pm.field(_lib.FIELD_PHI_LAPLACIAN, t, d) for d in range(3)] for t in range(T)]
     field_list = [phi, phi_fourier, force_on_grid, v_ext_fourier, v_ext, phi_transfer,
                   phi_laplacian]
     elec_common_list = [None, None, None, None]
@@ -168,6 +169,13 @@ def compute_field_and_kinetic_energy(phi, phi_q, psi, velocity, hamiltonian, pos
     else:
         field_q_energy = 0.0
     return field_energy, kinetic, field_q_energy
+
+
+def comp_laplacian(phi_fourier, phi_transfer, phi_laplacian, hamiltonian, config):
+    """``phi_laplacian[t][d] = c2r(-k_d^2 * phi_fourier[t])`` (``field.py:406-425``): one k-space
+    kernel for all types and directions and 3T inverse transforms, from the density spectra of the
+    last ``update_field``.  ``phi_transfer`` (the reference's scratch) is not used."""
+    phi_laplacian[0][0].pm.laplacian()
 
 
 def _first_atom_positions(pm, positions, molecules):

@@ -66,6 +66,9 @@ class MeshField:
 
     def _materialize(self):
         fid = self.field_id
+        if fid == _lib.FIELD_PHI_LAPLACIAN:
+            self.pm.laplacian()
+            return
         self.pm._materialize(
             want_phi=fid == _lib.FIELD_PHI, want_phi_fourier=fid == _lib.FIELD_PHI_FOURIER,
             want_v_ext=fid == _lib.FIELD_V_EXT,
@@ -343,6 +346,24 @@ class ParticleMesh:
         if want_phi or want_phi_fourier or want_v_ext or want_psi:
             _lib.check(self.lib.hymd_materialize(self._ctx, int(want_phi), int(want_phi_fourier),
                                                  int(want_v_ext), int(want_psi), self.stream))
+
+    def laplacian(self):
+        """``phi_laplacian[t][d] = c2r(-k_d^2 phi_fourier[t])`` for the current spectra
+        (``comp_laplacian``, ``field.py:406-425``); cached until the next paint."""
+        _lib.check(self.lib.hymd_laplacian(self._ctx, self.stream))
+
+    def field_pressure_sums(self, A, c, type_charges=None):
+        """Local sums ``[sum V_t phi_t, sum V_t lap_t,x, .. y, .. z]`` over this slab's cells with
+        ``V_t = c_t + sum_j A_tj phi_j (+ q_t psi)`` (field terms of ``pressure.py:105-127``)."""
+        dp = ctypes.POINTER(ctypes.c_double)
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        q = None if type_charges is None else np.ascontiguousarray(type_charges, dtype=np.float64)
+        out = (ctypes.c_double * 4)()
+        _lib.check(self.lib.hymd_field_pressure(
+            self._ctx, A.ctypes.data_as(dp), c.ctypes.data_as(dp),
+            None if q is None else q.ctypes.data_as(dp), out, self.stream))
+        return np.array(list(out), dtype=np.float64)
 
     def _view(self, field_id, t, d, kind):
         ptr = ctypes.c_void_p()

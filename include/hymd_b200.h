@@ -54,7 +54,8 @@ typedef enum {
     HYMD_FIELD_PHI_Q = 4,        /*          real  (nxl,Ny,Nz) unfiltered charge density */
     HYMD_FIELD_PHI_Q_FOURIER = 5,/*          cplx  k-layout: H * r2c(phi_q)/M */
     HYMD_FIELD_PSI = 6,          /*          real  (nxl,Ny,Nz) electrostatic potential */
-    HYMD_FIELD_ELEC_FIELD = 7    /* [d]      real  ghost-padded (nxl+1,Ny+1,Nzp) */
+    HYMD_FIELD_ELEC_FIELD = 7,   /* [d]      real  ghost-padded (nxl+1,Ny+1,Nzp) */
+    HYMD_FIELD_PHI_LAPLACIAN = 8 /* [t][d]   real  (nxl,Ny,Nz): c2r(-k_d^2 phi_fourier[t]) (hymd_laplacian) */
 } hymd_field_id;
 
 typedef struct {
@@ -148,6 +149,18 @@ int hymd_materialize(hymd_ctx* ctx, int want_phi, int want_phi_fourier, int want
  * kappa/rho0/a the Hamiltonian parameters, shift_a = 0 for SquaredPhi.  Synchronous. */
 int hymd_field_energy(hymd_ctx* ctx, const double* chi, double kappa, double rho0, double a,
                       double out[2], void* stream);
+
+/* comp_laplacian (field.py:406-425): HYMD_FIELD_PHI_LAPLACIAN[t][d] = c2r(-k_d^2 phi_fourier[t])
+ * for the spectra of the last hymd_paint + hymd_field_cycle (cached until the next paint). */
+int hymd_laplacian(hymd_ctx* ctx, void* stream);
+
+/* Field terms of comp_pressure (pressure.py:105-127) for this slab.  With
+ * V_t = c[t] + sum_j A[t*T+j] phi~_j (+ type_charges[t] psi when type_charges != NULL) writes 4
+ * doubles to the HOST array out: {sum_cells sum_t V_t phi~_t, sum_cells sum_t V_t lap[t][d], d =
+ * x,y,z}; the caller scales by dV/V (and sigma^2) and all-reduces.  Needs hymd_materialize
+ * (filtered phi~), hymd_laplacian and, with type_charges, psi.  Synchronous. */
+int hymd_field_pressure(hymd_ctx* ctx, const double* A, const double* c, const double* type_charges,
+                        double out[4], void* stream);
 
 /* Pointer + geometry of a context-owned buffer.  dims[3] = logical extents, pitch[3] = element
  * strides (in elements of the scalar or complex type). */

@@ -130,6 +130,45 @@ def compute_field_and_kinetic_energy(state, hamiltonian, velocity, config):
     return field_energy, kinetic, field_q
 
 
+def comp_laplacian(state, config, workers=1):
+    """``field.py:406-425``: ``phi_laplacian[t][d] = c2r(-k_d^2 * phi_fourier[t])``."""
+    k = pmo.kgrid(state.mesh, state.box, state.dtype)
+    state.phi_laplacian = [[None] * 3 for _ in range(config.n_types)]
+    for t in range(config.n_types):
+        for d in range(3):
+            tr = (-k[d] ** 2 * state.phi_fourier[t]).astype(state.phi_fourier[t].dtype, copy=False)
+            state.phi_laplacian[t][d] = pmo.c2r(tr, state.mesh, workers)
+    return state.phi_laplacian
+
+
+def comp_pressure(state, hamiltonian, velocities, config, bond_pr=None, angle_pr=None, workers=1):
+    """``pressure.py:84-200`` (single rank): the 18 pressure contributions
+    ``[p_kin, p0, p1, p2x, p2y, p2z, bond(3), angle(3), dihedral(3), total(3)]``."""
+    bond_pr = np.zeros(3) if bond_pr is None else np.asarray(bond_pr, dtype=np.float64)
+    angle_pr = np.zeros(3) if angle_pr is None else np.asarray(angle_pr, dtype=np.float64)
+    V = float(np.prod(np.asarray(config.box_size, dtype=np.float64)))
+    dv = volume_per_cell(config)
+    elec = config.coulombtype in ("PIC_Spectral", "PIC_Spectral_GPE") and state.psi is not None
+    w = hamiltonian.w_0(state.phi) * dv                                   # pressure.py:89-95
+    if elec:
+        w = w + hamiltonian.w_elec([state.phi_q, state.psi]) * dv
+    kinetic = 0.5 * config.mass * float(np.sum(np.asarray(velocities, dtype=np.float64) ** 2))
+    p_kin = 2.0 / (3.0 * V) * kinetic                                     # pressure.py:98-99
+    p0 = -1.0 / V * float(np.sum(w, dtype=np.float64))                    # pressure.py:102
+    if elec:                                                              # pressure.py:105-108
+        v_bar = np.array([hamiltonian.V_bar[t]([state.phi, state.psi]) for t in range(config.n_types)])
+    else:
+        v_bar = np.array([hamiltonian.V_bar_0[t](state.phi) for t in range(config.n_types)])
+    p1 = float(np.sum((dv / V) * v_bar * np.asarray(state.phi), dtype=np.float64))   # pressure.py:110
+    comp_laplacian(state, config, workers)                                # pressure.py:113-119
+    lap = np.asarray(state.phi_laplacian)                                 # (T, 3, Nx, Ny, Nz)
+    p2 = np.sum(dv / V * config.sigma ** 2 * np.repeat(v_bar[:, np.newaxis], 3, axis=1) * lap,
+                axis=(0, 2, 3, 4), dtype=np.float64)                      # pressure.py:121-127
+    p_bond, p_angle, p_dih = bond_pr / V, angle_pr / V, np.zeros(3)      # pressure.py:130-136
+    p_tot = p_kin + p0 + p1 + p2 + p_bond + p_angle + p_dih              # pressure.py:154
+    return np.array([p_kin, p0, p1, p2[0], p2[1], p2[2], *p_bond, *p_angle, *p_dih, *p_tot])
+
+
 # --- multi-threaded CIC (CPU baseline only; same arithmetic) ----------------------------
 
 def _paint_mt(pos, mass, mesh, box, dtype, use_c=True):

@@ -13,6 +13,7 @@ reference's lambdas.
 * ``DefaultNoChi.setup``  ``hamiltonian.py:256-319``
 * ``DefaultWithChi.setup````hamiltonian.py:369-486``
 * ``w_elec``              ``hamiltonian.py:148-155`` (identical in all three)
+* ``V_bar_0`` / ``V_bar`` ``hamiltonian.py:157-186, 271-301, 423-475`` (pressure terms)
 """
 from __future__ import annotations
 
@@ -93,8 +94,17 @@ class OracleHamiltonian:
             phi_q, psi = args
             return 0.5 * phi_q * psi - config.self_energy / config.simulation_volume
 
+        def make_vbar(t):
+            # V_bar_0(phi, t) + V_bar_elec(psi, t) = V_bar_0 + type_charges[t] * psi
+            v0 = make_v(t)
+            return lambda args: v0(args[0]) + config.type_charges[t] * args[1]
+
         self.w_0 = w_0
         self.v_ext = [make_v(t) for t in range(n)]
+        # V_bar_0[t] is written out separately in the reference but is the same expression as
+        # dw/dphi_t for all three functionals (pinned by the golden vectors)
+        self.V_bar_0 = [make_v(t) for t in range(n)]
+        self.V_bar = [make_vbar(t) for t in range(n)]
         self.w_elec = w_elec
 
     def H(self, k, v):

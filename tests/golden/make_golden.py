@@ -8,7 +8,8 @@ Run in the build container only (needs /root/reference):
 (the ``hymd`` package itself cannot be imported: h5py/mpi4py/pmesh are absent).
 Outputs ``tests/golden/hamiltonian_golden.npz``: for each of the three
 functionals and several parameter sets, the reference's ``H``, ``v_ext[t]``,
-``w_0`` and ``w_elec`` evaluated on seeded random inputs.
+``w_0``, ``w_elec`` and the pressure helpers ``V_bar_0[t]`` / ``V_bar[t]`` evaluated on seeded
+random inputs.
 """
 import importlib.util
 import json
@@ -52,7 +53,8 @@ CASES = [
     dict(name="chi_4_pme", kind="DefaultWithChi", names=["A", "B", "C", "W"],
          chi=[("A", "B", 20.0), ("A", "C", -5.0), ("B", "C", 10.0), ("A", "W", 30.0),
               ("B", "W", 5.0)], kappa=0.05, sigma=0.5, box=[10.0, 10.0, 10.0], n=8370,
-         coulombtype="PIC_Spectral", dielectric_const=80.0, self_energy=123.456),
+         coulombtype="PIC_Spectral", dielectric_const=80.0, self_energy=123.456,
+         type_charges=[1.0, -1.0, 0.5, 0.0]),
 ]
 
 
@@ -73,6 +75,8 @@ def main():
         # write rho0/a/simulation_volume the way Hamiltonian._setup does
         ns = types.SimpleNamespace(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
         ns.coulomb_constant = Config.coulomb_constant
+        if case.get("type_charges") is not None:
+            ns.type_charges = list(case["type_charges"])
         if not case.get("f32_params"):
             # float64 copy of the (float32-representable) box: pins the algebra exactly.
             # With the float32 box the reference derives a float32 rho0 and sympy then prints
@@ -97,6 +101,10 @@ def main():
         out[pre + "/v_ext"] = np.stack(
             [np.asarray(h.v_ext[i](phi), dtype=np.float64) * np.ones((4, 3, 5)) for i in range(t)])
         out[pre + "/w_elec"] = np.asarray(h.w_elec([phi_q, psi]), dtype=np.float64)
+        out[pre + "/V_bar_0"] = np.stack(
+            [np.asarray(h.V_bar_0[i](phi), dtype=np.float64) * np.ones((4, 3, 5)) for i in range(t)])
+        out[pre + "/V_bar"] = np.stack(
+            [np.asarray(h.V_bar[i]([phi, psi]), dtype=np.float64) * np.ones((4, 3, 5)) for i in range(t)])
         out[pre + "/rho0_a_vol"] = np.array([ns.rho0, ns.a, ns.simulation_volume])
         meta.append({k2: v2 for k2, v2 in case.items()})
     np.savez_compressed(os.path.join(HERE, "hamiltonian_golden.npz"), **out)

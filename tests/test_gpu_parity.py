@@ -299,3 +299,38 @@ def test_kernel_variants_match_oracle(dtype, env, monkeypatch):
     for t in range(cfg.n_types):
         for d in range(3):
             assert rel_err(g.force_mesh[t][d].value.cpu().numpy(), o.st.force_mesh[t][d]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mesh,coulomb", [([24, 20, 28], True), ([32, 32, 32], False), ([9, 12, 10], True)])
+def test_laplacian_and_pressure_match_oracle(dtype, mesh, coulomb):
+    """comp_laplacian (field.py:406-425) and the 18 pressure contributions of comp_pressure
+    (pressure.py:84-200) against the oracle's restatement."""
+    from gpu_common import GpuRun, OracleRun, rel_err
+    from hymd_b200 import field as F
+    from hymd_b200.pressure import comp_pressure
+    from oracle import field_oracle as fo
+    cfg, pos, types, q = _system(9000, mesh, [4.0, 5.0, 6.0], dtype, seed=41, coulomb=coulomb)
+    if coulomb:
+        cfg.type_charges = [0.7, -0.4, 0.1]
+        cfg.self_energy = 12.5
+    rng = np.random.default_rng(9)
+    vel = rng.normal(size=pos.shape).astype(dtype)
+    bond_pr, angle_pr = np.array([1.0, -2.0, 0.5]), np.array([0.25, 0.5, -0.75])
+    g = GpuRun(cfg, pos, types, charges=q, compute_potential=True)
+    o = OracleRun(cfg, pos, types, charges=q)
+    o.cfg.type_charges, o.cfg.self_energy = cfg.type_charges, getattr(cfg, "self_energy", 0.0)
+    F.comp_laplacian(g.phi_fourier, g.phi_transfer, g.phi_laplacian, g.h, cfg)
+    lap_ref = fo.comp_laplacian(o.st, o.cfg)
+    scale = max(np.abs(lap_ref[t][d]).max() for t in range(cfg.n_types) for d in range(3))
+    for t in range(cfg.n_types):
+        for d in range(3):
+            got = g.phi_laplacian[t][d].value.cpu().numpy()
+            assert np.abs(got - lap_ref[t][d]).max() < TOL[dtype] * scale
+    got = comp_pressure(g.phi, g.phi_q, g.psi, g.h, vel, cfg, g.phi_fourier, g.phi_laplacian,
+                        g.phi_transfer, g.pos, bond_pr, angle_pr)
+    want = fo.comp_pressure(o.st, o.h, vel, o.cfg, bond_pr, angle_pr)
+    assert got.shape == (18,)
+    # every term against the largest term (the total mixes terms of both signs)
+    ref = np.abs(want).max()
+    assert np.abs(got - want).max() < 10 * TOL[dtype] * ref, (got, want)

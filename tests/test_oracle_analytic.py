@@ -112,3 +112,22 @@ def test_c_and_numpy_cic_agree(dtype):
     c = fo._paint_mt(r, m, mesh, box, dtype)
     assert np.abs(c - b).max() < tol
     assert np.abs(fo._readout_mt(g, r, box) - vb).max() == 0.0
+
+
+def test_laplacian_of_a_plane_wave():
+    """comp_laplacian (field.py:406-425) on phi = cos(q.x): every component is -q_d^2 cos(q.x)."""
+    from types import SimpleNamespace
+    from oracle import field_oracle as fo
+    from oracle import pm_oracle as pmo
+    mesh, box = (16, 12, 10), np.array([4.0, 5.0, 6.0])
+    n = (2, 1, 3)
+    q = 2.0 * np.pi * np.array(n) / box
+    x = [np.arange(mesh[a]) * box[a] / mesh[a] for a in range(3)]
+    phase = q[0] * x[0][:, None, None] + q[1] * x[1][None, :, None] + q[2] * x[2][None, None, :]
+    phi = np.cos(phase)
+    cfg = SimpleNamespace(mesh_size=list(mesh), box_size=box, n_types=1)
+    st = fo.FieldState(SimpleNamespace(mesh_size=list(mesh), box_size=box, n_types=1, dtype=np.float64))
+    st.phi_fourier[0] = pmo.r2c(phi)
+    lap = fo.comp_laplacian(st, cfg)
+    for d in range(3):
+        np.testing.assert_allclose(lap[0][d], -q[d] ** 2 * phi, atol=1e-12 * q[d] ** 2 + 1e-13)

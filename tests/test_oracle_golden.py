@@ -22,6 +22,8 @@ def test_hamiltonian_matches_reference(case):
                  coulombtype=case.get("coulombtype"), dielectric_const=case.get("dielectric_const"),
                  self_energy=case.get("self_energy"))
     cfg.finalize(case["names"], n_particles=case["n"])
+    if case.get("type_charges") is not None:
+        cfg.type_charges = list(case["type_charges"])
     if not case.get("f32_params"):
         cfg.box_size = np.asarray(cfg.box_size, dtype=np.float64)
     W = OracleHamiltonian(cfg)
@@ -49,3 +51,9 @@ def test_hamiltonian_matches_reference(case):
         np.testing.assert_allclose(W.v_ext[t](phi), GOLD[pre + "/v_ext"][t], rtol=1e-11, atol=1e-9)
     np.testing.assert_allclose(W.w_elec([GOLD[pre + "/phi_q"], GOLD[pre + "/psi"]]),
                                GOLD[pre + "/w_elec"], rtol=1e-13, atol=1e-13)
+    # pressure helpers (pressure.py:105-108)
+    psi = GOLD[pre + "/psi"]
+    for t in range(cfg.n_types):
+        np.testing.assert_allclose(W.V_bar_0[t](phi), GOLD[pre + "/V_bar_0"][t], rtol=1e-11, atol=1e-9)
+        np.testing.assert_allclose(W.V_bar[t]([phi, psi]), GOLD[pre + "/V_bar"][t], rtol=1e-11,
+                                   atol=1e-9)

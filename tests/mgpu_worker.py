@@ -105,6 +105,11 @@ def main():
     vel = torch.zeros_like(pos_d)
     energies = F.compute_field_and_kinetic_energy(phi, phi_q, psi, vel, ham, pos_d, typ_d, v_ext,
                                                   cfg, layouts)
+    # by-products of the print step: Laplacians and the pressure vector (all ranks, collective)
+    from hymd_b200.pressure import comp_pressure
+    bond_pr, angle_pr = np.array([1.0, -2.0, 0.5]) / world, np.array([0.25, 0.5, -0.75]) / world
+    pressure = comp_pressure(phi, phi_q, psi if args.pme else None, ham, vel, cfg, phi_fourier,
+                             phi_laplacian, phi_transfer, pos_d, bond_pr, angle_pr)
     torch.cuda.synchronize()
 
     payload = {
@@ -115,6 +120,7 @@ def main():
         "v_ext": [v.value.cpu().numpy() for v in v_ext],
         "psi": None if not args.pme else psi.value.cpu().numpy(),
         "phi_fourier": [p.value.cpu().numpy() for p in phi_fourier],
+        "lap": [[phi_laplacian[t][d].value.cpu().numpy() for d in range(3)] for t in range(cfg.n_types)],
     }
     if world > 1:
         gathered = [None] * world
@@ -154,6 +160,14 @@ def main():
         checks["field_energy"] = abs(energies[0] - e_o[0]) / escale
         if args.pme:
             checks["field_q_energy"] = abs(energies[2] - e_o[2]) / max(abs(e_o[2]), 1e-300)
+        from oracle import field_oracle as fo
+        want_p = fo.comp_pressure(o.st, o.h, np.zeros_like(pos), o.cfg, bond_pr * world, angle_pr * world)
+        checks["pressure"] = np.abs(pressure - want_p).max() / np.abs(want_p).max() / 10.0
+        lscale = max(np.abs(o.st.phi_laplacian[t][d]).max() for t in range(cfg.n_types) for d in range(3))
+        for t in range(cfg.n_types):
+            for d in range(3):
+                got = np.concatenate([g["lap"][t][d] for g in gathered], axis=0)
+                checks[f"lap{t}{d}"] = np.abs(got - o.st.phi_laplacian[t][d]).max() / lscale
         worst = max(checks.values())
         ok = worst < tol
         print(f"MGPU world={world} dtype={args.dtype} pme={args.pme} mesh={args.mesh} "

@@ -255,6 +255,7 @@ int hymd_ctx_destroy(hymd_ctx* c) {
                     c->wA, c->wS, c->halo, c->ytw, c->ztw, c->plane_scratch};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    if (c->h_out_of_slab) { cudaFreeHost(c->h_out_of_slab); cudaEventDestroy(c->ev_slab); }
     if (c->ev_open) {
         for (auto& iv : *c->ev_open) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
         delete c->ev_open;
@@ -344,6 +345,32 @@ int hymd_sort_particles_ex(hymd_ctx* c, const void* d_pos, const int32_t* d_type
     }
     c->sorted = true;
     c->order_n = n;
+    if (c->g.P > 1) {
+        if (!c->h_out_of_slab) {
+            HYMD_CUDA(cudaMallocHost((void**)&c->h_out_of_slab, sizeof(unsigned int)));
+            HYMD_CUDA(cudaEventCreateWithFlags(&c->ev_slab, cudaEventDisableTiming));
+        }
+        HYMD_CUDA(cudaMemcpyAsync(c->h_out_of_slab, &c->scalars->out_of_slab, sizeof(unsigned int),
+                                  cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        HYMD_CUDA(cudaEventRecord(c->ev_slab, (cudaStream_t)stream));
+        c->slab_check_pending = true;
+    }
+    return HYMD_OK;
+}
+
+// Multi-GPU: every particle handed to hymd_sort_particles must lie inside this rank's slab (the
+// caller re-homes them with hymd_migrate / domain_decomposition); particles outside would be
+// painted into the edge planes.  Never silently: the count of the last sort is checked here.
+static int check_slab(hymd_ctx* c) {
+    if (!c->slab_check_pending) return HYMD_OK;
+    HYMD_CUDA(cudaEventSynchronize(c->ev_slab));     // the count kernel ran long ago: no GPU bubble
+    c->slab_check_pending = false;
+    if (*c->h_out_of_slab > 0) {
+        set_error("%u particles lie outside the x-slab of rank %d: call domain_decomposition "
+                  "(hymd_migrate_plan/apply) before update_field, and often enough that particles "
+                  "cannot leave their slab in between", *c->h_out_of_slab, c->g.rank);
+        return HYMD_ERR_STATE;
+    }
     return HYMD_OK;
 }
 
@@ -511,6 +538,7 @@ int hymd_readout(hymd_ctx* c, void* d_force, void* stream) {
         set_error("hymd_readout needs hymd_sort_particles and hymd_field_cycle first");
         return HYMD_ERR_STATE;
     }
+    HYMD_CHECK(check_slab(c));
     if (c->np == 0) return HYMD_OK;
     PhaseScope ps(c, HYMD_PHASE_READOUT, (cudaStream_t)stream);
     return readout_forces(c, d_force, (cudaStream_t)stream);
@@ -556,6 +584,7 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
         if (want_psi) HYMD_CHECK(fft_inverse(c, c->psi_hat, 1, c->psi, false, s));
     }
     c->have_psi = want_psi != 0;
+    HYMD_CHECK(check_slab(c));
     if (c->np > 0 && d_elec_force) {
         PhaseScope ps(c, HYMD_PHASE_PME_READOUT, s);
         HYMD_CHECK(readout_pme(c, d_elec_force, s));

@@ -214,6 +214,11 @@ struct hymd_ctx {
                             // a peer may not overwrite them before another barrier (same call sequence
                             // on every rank, so the flags agree)
     hymd::MigrateState* mig;
+    // multi-GPU: particles found outside the local slab by the last sort, copied to pinned host memory
+    // right after the count kernel and checked (without stalling the GPU) before the readout
+    unsigned int* h_out_of_slab;
+    cudaEvent_t ev_slab;
+    bool slab_check_pending;
 
     // readout TMA
     CUtensorMap tmap_gmesh, tmap_emesh;

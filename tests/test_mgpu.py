@@ -81,3 +81,11 @@ def test_four_slabs_match_oracle():
 def test_migration_rehomes_particles():
     _need(2)
     _run(2, ["--dtype", "f64", "--pme", "--migrate"])
+
+
+def test_particles_outside_their_slab_fail_loudly():
+    """No domain_decomposition and particles that are not at home: the cycle must raise (the count
+    of out-of-slab particles of every sort is checked before the readout), never paint them into
+    the edge planes."""
+    _need(2)
+    _run(2, ["--dtype", "f64", "--guests"])

@@ -172,7 +172,7 @@ template <typename real, int NY, int NZ, int NT_, int TILES> struct PlaneCfg {
     static constexpr int NT = NT_, NW = NT / 32, CTAS = 512 / NT;            // CTAs per SM
     static constexpr int R1y = Radix<NY>::R1, R2y = Radix<NY>::R2, R1z = Radix<NZ>::R1, R2z = Radix<NZ>::R2;
     static constexpr int NZC = NZ / 2 + 1, NZCP = NZC + (NZC & 1);
-    static constexpr int CG = 64 / (int)sizeof(Cx<real>);
+    static constexpr int CG = (TILES == 3 ? 128 : 64) / (int)sizeof(Cx<real>);   // columns per chunk: 64- or 128-byte rows
     static constexpr int GT = CG * 16, NG = NT / GT;
     using LA = LayA<NY, CG>;
     static constexpr int NTILE = (TILES == 2 && 2 * NG * LA::ELEMS * (int)sizeof(Cx<real>) <= 144 * 1024 / CTAS) ? 2 : 1;
@@ -724,7 +724,7 @@ static int plane_tables(hymd_ctx* c) {
 // copy engine saves in load/store instructions.  Two 256-thread CTAs per SM instead of one of 512
 // were slower as well (0.84 vs 0.69 ms: the second scratch plane per SM) and are gone.
 static int plane_tiles() {
-    if (const char* e = getenv("HYMD_B200_PLANE_TILES")) return atoi(e) == 2 ? 2 : 1;
+    if (const char* e = getenv("HYMD_B200_PLANE_TILES")) { const int v = atoi(e); return v >= 1 && v <= 3 ? v : 1; }
     return 1;
 }
 
@@ -766,8 +766,11 @@ static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParam
 
 template <typename real, int N, bool INVERSE>
 static int launch_plane_nt(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
-    return plane_tiles() == 1 ? launch_plane<real, N, 512, 1, INVERSE>(c, in, out, p, s)
-                              : launch_plane<real, N, 512, 2, INVERSE>(c, in, out, p, s);
+    switch (plane_tiles()) {
+        case 2: return launch_plane<real, N, 512, 2, INVERSE>(c, in, out, p, s);
+        case 3: return launch_plane<real, N, 512, 3, INVERSE>(c, in, out, p, s);
+        default: return launch_plane<real, N, 512, 1, INVERSE>(c, in, out, p, s);
+    }
 }
 
 template <typename real, bool INVERSE>

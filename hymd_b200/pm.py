@@ -201,10 +201,20 @@ class ParticleMesh:
     def sync_interaction(self, hamiltonian, config, m=None):
         """Push (A, c, m, sigma, k_e/eps) to the context if they changed since the last call
         (barostat runs change rho0 / a; ``update_field`` receives ``m`` explicitly)."""
+        # Probing the functional (T^2 Python calls, affine_parameters) every MD step would cost
+        # more than the kernels of a small system: skip it while the objects and the scalars the
+        # functional is built from are the ones of the previous call (a barostat changes rho0 / a).
+        quick = (id(hamiltonian), id(config), getattr(config, "rho0", None), getattr(config, "a", None),
+                 getattr(config, "kappa", None), getattr(config, "sigma", None), id(getattr(config, "chi", None)),
+                 tuple(float(x) for x in (m if m is not None else (getattr(config, "m", None) or ()))),
+                 getattr(config, "dielectric_const", None))
+        if quick == getattr(self, "_interaction_quick", None):
+            return
         A, c, m_cfg, sigma, conv = self._interaction(config, hamiltonian)
         if m is not None:
             m_cfg = np.asarray(list(m), dtype=np.float64)
         key = (A.tobytes(), c.tobytes(), m_cfg.tobytes(), sigma, conv)
+        self._interaction_quick = quick
         if key == self._interaction_key:
             return
         dp = ctypes.POINTER(ctypes.c_double)

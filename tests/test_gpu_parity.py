@@ -282,6 +282,7 @@ def test_domain_decomposition_returns_cell_order_single_gpu():
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("env", [{"HYMD_B200_GRAD2": "0"}, {"HYMD_B200_PLANE_TILES": "2"},
+                                 {"HYMD_B200_PLANE_TILES": "3"},
                                  {"HYMD_B200_PLANE_TILES": "2", "HYMD_B200_ROW_TMA": "3", "HYMD_B200_GRAD2": "0"},
                                  {"HYMD_B200_NO_FUSED": "1"}, {"HYMD_B200_NO_PLANE": "1"}])
 def test_kernel_variants_match_oracle(dtype, env, monkeypatch):

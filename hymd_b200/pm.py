@@ -215,6 +215,8 @@ class ParticleMesh:
             m_cfg = np.asarray(list(m), dtype=np.float64)
         key = (A.tobytes(), c.tobytes(), m_cfg.tobytes(), sigma, conv)
         self._interaction_quick = quick
+        # keep the probed objects alive: their id()s are part of the key and must not be recycled
+        self._interaction_refs = (hamiltonian, config, getattr(config, "chi", None))
         if key == self._interaction_key:
             return
         dp = ctypes.POINTER(ctypes.c_double)

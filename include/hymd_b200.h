@@ -98,7 +98,7 @@ int hymd_ctx_set_interaction(hymd_ctx* ctx, const double* A, const double* c, co
                              double sigma, double elec_conversion);
 
 /* pm.decompose(positions[types==t]) for all t (main.py:977-980, 1007): bins the n local
- * particles by mesh cell.  d_pos is (n,3) row-major in the context dtype, d_types int32 (n),
+ * particles by mesh-cell bin (two bins per 32 cells of a cell row).  d_pos is (n,3) row-major in the context dtype, d_types int32 (n),
  * d_charges (n) in the context dtype or NULL.  Positions may lie anywhere (they are wrapped
  * periodically); with world_size > 1 every particle must lie inside this rank's slab
  * (see hymd_migrate).  Keeps no reference to the inputs after the stream work completes. */
@@ -107,7 +107,7 @@ int hymd_sort_particles(hymd_ctx* ctx, const void* d_pos, const int32_t* d_types
 
 /* Same, with flags.  HYMD_SORT_REUSE_ORDER: the per-index particle types are the same as in the
  * previous call and n is unchanged (true between consecutive MD steps: HyMD reads the types once
- * from the input file); the binning then starts from the previous cell order, which turns the
+ * from the input file); the binning then starts from the previous bin order, which turns the
  * random scatter of a cold sort into nearly sequential traffic.  d_types may be NULL with this
  * flag.  If there is no usable previous order the flag is ignored (then d_types is required).
  * The result is identical either way. */
@@ -167,7 +167,7 @@ int hymd_field_pressure(hymd_ctx* ctx, const double* A, const double* c, const d
 int hymd_get_field(hymd_ctx* ctx, int field_id, int t, int d, void** d_ptr, int64_t dims[3],
                    int64_t pitch[3]);
 
-/* Synchronizes and reports {max particles per cell, particles outside the local slab,
+/* Synchronizes and reports {max particles per sort bin (>= per cell), particles outside the local slab,
  * local particle count, distinct potential rows} of the last hymd_sort_particles. */
 int hymd_ctx_status(hymd_ctx* ctx, int64_t out[4]);
 

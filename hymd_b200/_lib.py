@@ -28,6 +28,9 @@ EXPORTS = [
     "hymd_launch_count", "hymd_migrate_plan", "hymd_migrate_apply", "hymd_ctx_set_timing", "hymd_ctx_get_timings",
     "hymd_sort_particles_ex", "hymd_ctx_reset_order", "hymd_ctx_paths", "hymd_laplacian",
     "hymd_field_pressure",
+    "hymd_bonded_create", "hymd_bonded_destroy", "hymd_bonded_forces", "hymd_bonded_launch_count",
+    "hymd_md_kick_drift", "hymd_velocity_moments", "hymd_velocity_moments_scratch_doubles",
+    "hymd_csvr_apply", "hymd_cancel_com",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -99,9 +102,25 @@ def load():
     lib.hymd_ctx_get_timings.argtypes = [vp, P(dbl), P(i64)]
     lib.hymd_migrate_plan.argtypes = [vp, vp, i64, P(i64), vp]
     lib.hymd_migrate_apply.argtypes = [vp, vp, vp, i32, vp]
+    I32P, F64P = P(i32), P(dbl)
+    lib.hymd_bonded_create.argtypes = [i64, i64, I32P, I32P, F64P, F64P, i64, I32P, I32P, I32P, F64P, F64P,
+                                       i64, I32P, I32P, I32P, I32P, F64P, I32P, P(vp)]
+    lib.hymd_bonded_destroy.argtypes = [vp]
+    lib.hymd_bonded_forces.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, P(dbl), vp, F64P, vp]
+    lib.hymd_bonded_launch_count.argtypes = [vp]
+    lib.hymd_bonded_launch_count.restype = i64
+    lib.hymd_md_kick_drift.argtypes = [ctypes.c_int, vp, vp, P(vp), ctypes.c_int, ctypes.c_int, dbl, dbl, dbl,
+                                       P(dbl), i64, vp]
+    lib.hymd_velocity_moments.argtypes = [ctypes.c_int, vp, I32P, ctypes.c_int, i64, F64P, F64P, vp]
+    lib.hymd_velocity_moments_scratch_doubles.argtypes = []
+    lib.hymd_velocity_moments_scratch_doubles.restype = i64
+    lib.hymd_csvr_apply.argtypes = [ctypes.c_int, vp, I32P, ctypes.c_int, i64, F64P, dbl, dbl, dbl, dbl, dbl,
+                                    ctypes.c_int, F64P, vp]
+    lib.hymd_cancel_com.argtypes = [ctypes.c_int, vp, i64, F64P, dbl, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("hymd_last_error", "hymd_launch_count"):
+        if name not in ("hymd_last_error", "hymd_launch_count", "hymd_bonded_launch_count",
+                        "hymd_velocity_moments_scratch_doubles"):
             fn.restype = ctypes.c_int
     if lib.hymd_abi_version() != 1:
         raise HymdError(f"libhymd_b200.so ABI {lib.hymd_abi_version()} != 1")

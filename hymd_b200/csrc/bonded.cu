@@ -1,0 +1,206 @@
+// Intramolecular forces on the device: hymd_bonded_create / _forces.
+// Replaces the f2py kernels cbf / caf / cdf (hymd/compute_bond_forces.f90, compute_angle_forces.f90,
+// compute_dihedral_forces.f90) that main.py:841-887 calls respa_inner times per outer step.
+// The arithmetic lives in bonded.cuh (shared with the CPU check of tests/native/).
+#include "bonded.cuh"
+#include "ctx.cuh"
+
+struct hymd_bonded {
+    long long n_particles;
+    long long n_terms[3];        // bonds, angles, dihedrals
+    uint32_t* start[3];          // [n_particles + 1]
+    uint32_t* refs[3];           // [n_terms * slots]
+    int32_t* idx[3];             // [n_terms][4]
+    double* par[3];              // [n_terms][2] / [n_terms][30]
+    int32_t* dih_type;           // [n4]
+    double* partial;             // [max_blocks][4] block partials of {energy, pr_x, pr_y, pr_z}
+    int max_blocks;
+    int64_t launches;
+};
+
+namespace hymd {
+
+constexpr int BONDED_THREADS = 128;
+
+template <typename real, int KIND>
+__global__ void __launch_bounds__(BONDED_THREADS) bonded_kernel(
+    const real* __restrict__ pos, long long n, Vec3d box, const uint32_t* __restrict__ start,
+    const uint32_t* __restrict__ refs, const int32_t* __restrict__ idx, const double* __restrict__ par,
+    const int32_t* __restrict__ dtype, real* __restrict__ force, double* __restrict__ partial) {
+    const long long p = (long long)blockIdx.x * BONDED_THREADS + threadIdx.x;
+    BondAcc acc = {{0.0, 0.0, 0.0}, 0.0, {0.0, 0.0, 0.0}};
+    if (p < n) {
+        acc = particle_terms<real, KIND>(p, pos, box, start, refs, idx, par, dtype);
+        force[3 * p + 0] = (real)acc.f.x;
+        force[3 * p + 1] = (real)acc.f.y;
+        force[3 * p + 2] = (real)acc.f.z;
+    }
+    // fixed-order block reduction of {e, pr}: lanes by shuffle, warps through shared memory
+    double v[4] = {acc.e, acc.pr.x, acc.pr.y, acc.pr.z};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    __shared__ double sh[BONDED_THREADS / 32][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 4; ++k) sh[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < BONDED_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
+        partial[4 * (long long)blockIdx.x + threadIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) bonded_final_kernel(const double* __restrict__ partial, int nblocks,
+                                                           double* __restrict__ out) {
+    __shared__ double sh[4][256];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += 256)
+        for (int k = 0; k < 4; ++k) acc[k] += partial[4 * (long long)i + k];
+    for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+            for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+template <typename T>
+static int to_device(T** dst, const T* src, size_t count) {
+    *dst = nullptr;
+    HYMD_CUDA(cudaMalloc((void**)dst, (count ? count : 1) * sizeof(T)));
+    if (count) HYMD_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return HYMD_OK;
+}
+
+static int upload_kind(hymd_bonded* b, int kind, long long n_terms, int slots,
+                       const int32_t* const* index, const double* par, size_t par_per_term) {
+    std::vector<uint32_t> start, refs;
+    if (!build_particle_csr(b->n_particles, n_terms, slots, index, start, refs)) {
+        set_error("bonded terms of %d particles: index outside [0, %lld), a particle twice in one term, "
+                  "or more than 2^30 terms", slots, b->n_particles);
+        return HYMD_ERR_INVALID;
+    }
+    std::vector<int32_t> idx((size_t)n_terms * 4, 0);
+    for (long long t = 0; t < n_terms; ++t)
+        for (int s = 0; s < slots; ++s) idx[(size_t)4 * t + s] = index[s][t];
+    b->n_terms[kind] = n_terms;
+    HYMD_CHECK(to_device(&b->start[kind], start.data(), start.size()));
+    HYMD_CHECK(to_device(&b->refs[kind], refs.data(), refs.size()));
+    HYMD_CHECK(to_device(&b->idx[kind], idx.data(), idx.size()));
+    HYMD_CHECK(to_device(&b->par[kind], par, (size_t)n_terms * par_per_term));
+    return HYMD_OK;
+}
+
+template <typename real>
+static int launch_kind(hymd_bonded* b, int kind, const real* pos, Vec3d box, real* force, double* d_out,
+                       cudaStream_t s) {
+    const long long n = b->n_particles;
+    const int blocks = (int)((n + BONDED_THREADS - 1) / BONDED_THREADS);
+    if (blocks > 0) {
+        if (kind == 0)
+            bonded_kernel<real, 2><<<blocks, BONDED_THREADS, 0, s>>>(
+                pos, n, box, b->start[0], b->refs[0], b->idx[0], b->par[0], nullptr, force, b->partial);
+        else if (kind == 1)
+            bonded_kernel<real, 3><<<blocks, BONDED_THREADS, 0, s>>>(
+                pos, n, box, b->start[1], b->refs[1], b->idx[1], b->par[1], nullptr, force, b->partial);
+        else
+            bonded_kernel<real, 4><<<blocks, BONDED_THREADS, 0, s>>>(
+                pos, n, box, b->start[2], b->refs[2], b->idx[2], b->par[2], b->dih_type, force, b->partial);
+        HYMD_LAUNCH_CHECK(b);
+    }
+    bonded_final_kernel<<<1, 256, 0, s>>>(b->partial, blocks, d_out);
+    HYMD_LAUNCH_CHECK(b);
+    return HYMD_OK;
+}
+
+}  // namespace hymd
+
+using namespace hymd;
+
+extern "C" {
+
+int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const int32_t* b2,
+                       const double* r0_2, const double* k_2, int64_t n3, const int32_t* a3,
+                       const int32_t* b3, const int32_t* c3, const double* t0_3, const double* k_3,
+                       int64_t n4, const int32_t* a4, const int32_t* b4, const int32_t* c4,
+                       const int32_t* d4, const double* coeff4, const int32_t* type4, hymd_bonded** out) {
+    if (!out || n_particles < 0 || n2 < 0 || n3 < 0 || n4 < 0 || (n2 && (!a2 || !b2 || !r0_2 || !k_2)) ||
+        (n3 && (!a3 || !b3 || !c3 || !t0_3 || !k_3)) || (n4 && (!a4 || !b4 || !c4 || !d4 || !coeff4 || !type4))) {
+        set_error("hymd_bonded_create: null or negative argument");
+        return HYMD_ERR_INVALID;
+    }
+    if (n_particles >= (1LL << 31)) { set_error("more than 2^31 particles per GPU"); return HYMD_ERR_INVALID; }
+    for (int64_t t = 0; t < n4; ++t)
+        if (type4[t] != 0 && type4[t] != 2) {
+            set_error("dihedral %lld has dih_type %d: only 0 (cosine series) and 2 (improper) are built; "
+                      "1 (combined bending-torsion + dipole reconstruction) is not", (long long)t, type4[t]);
+            return HYMD_ERR_INVALID;
+        }
+    hymd_bonded* b = new hymd_bonded();
+    memset(b, 0, sizeof(*b));
+    b->n_particles = n_particles;
+    int st = HYMD_OK;
+    {
+        std::vector<double> par((size_t)n2 * 2);
+        for (int64_t t = 0; t < n2; ++t) { par[2 * t] = r0_2[t]; par[2 * t + 1] = k_2[t]; }
+        const int32_t* index[2] = {a2, b2};
+        st = upload_kind(b, 0, n2, 2, index, par.data(), 2);
+    }
+    if (st == HYMD_OK) {
+        std::vector<double> par((size_t)n3 * 2);
+        for (int64_t t = 0; t < n3; ++t) { par[2 * t] = t0_3[t]; par[2 * t + 1] = k_3[t]; }
+        const int32_t* index[3] = {a3, b3, c3};
+        st = upload_kind(b, 1, n3, 3, index, par.data(), 2);
+    }
+    if (st == HYMD_OK) {
+        const int32_t* index[4] = {a4, b4, c4, d4};
+        st = upload_kind(b, 2, n4, 4, index, coeff4, (size_t)DIH_ROWS * DIH_COLS);
+    }
+    if (st == HYMD_OK) st = to_device(&b->dih_type, type4, (size_t)n4);
+    if (st == HYMD_OK) {
+        b->max_blocks = (int)((n_particles + BONDED_THREADS - 1) / BONDED_THREADS);
+        cudaError_t e = cudaMalloc((void**)&b->partial, sizeof(double) * 4 * (size_t)(b->max_blocks + 1));
+        if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); st = HYMD_ERR_NOMEM; }
+    }
+    if (st != HYMD_OK) { hymd_bonded_destroy(b); return st; }
+    *out = b;
+    return HYMD_OK;
+}
+
+int hymd_bonded_destroy(hymd_bonded* b) {
+    if (!b) return HYMD_OK;
+    for (int k = 0; k < 3; ++k) {
+        cudaFree(b->start[k]);
+        cudaFree(b->refs[k]);
+        cudaFree(b->idx[k]);
+        cudaFree(b->par[k]);
+    }
+    cudaFree(b->dih_type);
+    cudaFree(b->partial);
+    delete b;
+    return HYMD_OK;
+}
+
+int hymd_bonded_forces(hymd_bonded* b, int kind, int dtype, const void* d_pos, const double box[3],
+                       void* d_force, double* d_out, void* stream) {
+    if (!b || !box || !d_out || (b->n_particles > 0 && (!d_pos || !d_force))) {
+        set_error("hymd_bonded_forces: null argument");
+        return HYMD_ERR_INVALID;
+    }
+    if (kind < 2 || kind > 4) { set_error("kind = %d, expected 2, 3 or 4 particles per term", kind); return HYMD_ERR_INVALID; }
+    if (dtype != HYMD_F32 && dtype != HYMD_F64) { set_error("bad dtype %d", dtype); return HYMD_ERR_INVALID; }
+    const Vec3d bx = {box[0], box[1], box[2]};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == HYMD_F64)
+        return launch_kind<double>(b, kind - 2, (const double*)d_pos, bx, (double*)d_force, d_out, s);
+    return launch_kind<float>(b, kind - 2, (const float*)d_pos, bx, (float*)d_force, d_out, s);
+}
+
+int64_t hymd_bonded_launch_count(hymd_bonded* b) { return b ? b->launches : 0; }
+
+}  // extern "C"

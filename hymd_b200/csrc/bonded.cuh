@@ -1,0 +1,216 @@
+// Per-particle evaluation of HyMD's intramolecular forces (bonds, angles, dihedrals).
+//
+// Reference kernels (Fortran, sequential over terms, read-modify-write of f per term):
+//   hymd/compute_bond_forces.f90:1-61        cbf
+//   hymd/compute_angle_forces.f90:1-93       caf
+//   hymd/compute_dihedral_forces.f90:1-137   cdf   (dtype 0: cosine series, 2: improper)
+//   hymd/dipole_reconstruction.f90:37-48     cosine_series
+//
+// B200 design: no scatter, no atomics.  A host-built CSR lists, for every particle, the terms it
+// takes part in (term index and slot a/b/c/d, ascending term order = the Fortran accumulation
+// order); one thread owns one particle, re-evaluates each of its terms from the (L1/L2-resident,
+// molecule-contiguous) neighbour positions and writes its force exactly once.  Re-evaluating a term
+// 2-4 times costs flops the kernel has to spare; it saves the term-force round trip through HBM and
+// makes the result bitwise reproducible.  Energy and the pressure by-products are counted by the
+// thread that holds slot 0 of a term and reduced in a fixed order.
+//
+// Arithmetic follows the Fortran: position differences in the position type (real(4) for the fp32
+// build), everything after that in double (the Fortran locals are real(8) in both builds).
+//
+// The per-particle functions are __host__ __device__ so that tests/native/bonded_host_check.cu can
+// run exactly this source on the CPU against the oracle when no GPU is present.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include <vector>
+
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#endif
+
+namespace hymd {
+
+constexpr int DIH_ROWS = 6, DIH_COLS = 5;   // prepare_bonds: bonds_4_coeff (D,6,5), force.py:678-690
+
+struct Vec3d {
+    double x, y, z;
+};
+__host__ __device__ inline Vec3d operator+(Vec3d a, Vec3d b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__host__ __device__ inline Vec3d operator-(Vec3d a, Vec3d b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__host__ __device__ inline Vec3d operator*(Vec3d a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__host__ __device__ inline Vec3d mul(Vec3d a, Vec3d b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+__host__ __device__ inline double dot(Vec3d a, Vec3d b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__host__ __device__ inline Vec3d cross(Vec3d a, Vec3d b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// r(i,:) - r(j,:) in the position type, then minimum image `d - box * nint(d / box)` in double
+// (compute_bond_forces.f90:47-48; nint rounds half away from zero like round()).
+template <typename real>
+__host__ __device__ inline Vec3d mic_diff(const real* __restrict__ pos, long long i, long long j, Vec3d box) {
+    Vec3d d = {(double)(pos[3 * i + 0] - pos[3 * j + 0]), (double)(pos[3 * i + 1] - pos[3 * j + 1]),
+               (double)(pos[3 * i + 2] - pos[3 * j + 2])};
+    d.x -= box.x * round(d.x / box.x);
+    d.y -= box.y * round(d.y / box.y);
+    d.z -= box.z * round(d.z / box.z);
+    return d;
+}
+
+struct BondAcc {      // what one particle accumulates
+    Vec3d f;          // force on the particle
+    double e;         // energy of the terms it holds slot 0 of
+    Vec3d pr;         // pressure by-product of those terms
+};
+
+// ---- two-particle bonds ------------------------------------------------------------------------
+template <typename real>
+__host__ __device__ inline void bond_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, double r0,
+                                          double k, int slot, BondAcc& acc) {
+    const Vec3d rab = mic_diff(pos, (long long)ib, (long long)ia, box);
+    const double n = sqrt(dot(rab, rab));
+    const double df = k * (n - r0);
+    const Vec3d fa = rab * (-df / n);
+    if (slot == 0) {
+        acc.f = acc.f - fa;
+        acc.e += 0.5 * k * (n - r0) * (n - r0);
+        acc.pr = acc.pr + mul(fa, rab);
+    } else {
+        acc.f = acc.f + fa;
+    }
+}
+
+// ---- three-particle angles ---------------------------------------------------------------------
+template <typename real>
+__host__ __device__ inline void angle_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
+                                           double t0, double k, int slot, BondAcc& acc) {
+    const Vec3d ra = mic_diff(pos, (long long)ia, (long long)ib, box);
+    const Vec3d rc = mic_diff(pos, (long long)ic, (long long)ib, box);
+    const double na = sqrt(dot(ra, ra)), nc = sqrt(dot(rc, rc));
+    const Vec3d ea = ra * (1.0 / na), ec = rc * (1.0 / nc);
+    const double cosphi = dot(ea, ec);
+    if (cosphi * cosphi < 1.0) {
+        const double theta = acos(cosphi);
+        const double sinphi = sin(theta);
+        const double d = theta - t0;
+        const double ff = k * d;
+        const double xra = -ff / (na * sinphi), xrc = -ff / (nc * sinphi);
+        const Vec3d fa = (ec - ea * cosphi) * xra;
+        const Vec3d fc = (ea - ec * cosphi) * xrc;
+        if (slot == 0) {
+            acc.f = acc.f - fa;
+            acc.e += 0.5 * ff * d;
+            acc.pr = acc.pr - mul(fa, ra) - mul(fc, rc);
+        } else if (slot == 2) {
+            acc.f = acc.f - fc;
+        } else {
+            acc.f = acc.f + fa + fc;
+        }
+    }
+}
+
+// ---- four-particle dihedrals -------------------------------------------------------------------
+__host__ __device__ inline void cosine_series(const double* __restrict__ c_n, const double* __restrict__ d_n,
+                                              double phi, double& energy, double& de) {
+    for (int i = 0; i < DIH_COLS; ++i) {
+        energy += c_n[i] * (1.0 + cos(i * phi - d_n[i]));
+        de -= i * c_n[i] * sin(i * phi - d_n[i]);
+    }
+}
+
+template <typename real>
+__host__ __device__ inline void dihedral_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
+                                              int id, const double* __restrict__ coeff, int dtype, int slot,
+                                              BondAcc& acc) {
+    const Vec3d f = mic_diff(pos, (long long)ia, (long long)ib, box);
+    const Vec3d g = mic_diff(pos, (long long)ib, (long long)ic, box);
+    const Vec3d h = mic_diff(pos, (long long)id, (long long)ic, box);
+    const Vec3d v = cross(f, g), w = cross(h, g);
+    const double v_sq = dot(v, v), w_sq = dot(w, w);
+    const double g_norm = sqrt(dot(g, g));
+    const double cos_phi = dot(v, w);
+    const double sin_phi = dot(w, f) * g_norm;
+    const double phi = atan2(sin_phi, cos_phi);
+    const double f_dot_g = dot(f, g), h_dot_g = dot(h, g);
+    double df = 0.0, e = 0.0;
+    if (dtype == 0) {
+        cosine_series(coeff, coeff + DIH_COLS, phi, e, df);
+        const double* c_coil = coeff + 2 * DIH_COLS;
+        const double* d_coil = coeff + 3 * DIH_COLS;
+        bool c_any = false, d_any = false;
+        for (int i = 0; i < DIH_COLS; ++i) {
+            c_any |= (c_coil[i] != 0.0);
+            d_any |= (d_coil[i] != 0.0);
+        }
+        if (c_any && d_any) cosine_series(c_coil, d_coil, phi, e, df);
+    } else {   // dtype 2 (improper): coeff(1,1) = equilibrium, coeff(1,2) = force constant
+        const double eq = coeff[0], fc = coeff[1];
+        df = fc * (phi - eq);
+        e = 0.5 * fc * (phi - eq) * (phi - eq);
+    }
+    const Vec3d sc = v * (f_dot_g / (v_sq * g_norm)) - w * (h_dot_g / (w_sq * g_norm));
+    const Vec3d fa = v * (-df * g_norm / v_sq);
+    const Vec3d fd = w * (df * g_norm / w_sq);
+    if (slot == 0) {
+        acc.f = acc.f + fa;
+        acc.e += e;
+    } else if (slot == 1) {
+        acc.f = acc.f + (sc * df - fa);
+    } else if (slot == 2) {
+        acc.f = acc.f + (sc * (-df) - fd);
+    } else {
+        acc.f = acc.f + fd;
+    }
+}
+
+// ---- per-particle term lists -------------------------------------------------------------------
+// refs[start[p] .. start[p+1]) = term * 4 + slot for every (term, slot) with index[slot][term] == p,
+// ascending in term.  Returns false if an index is out of range or a particle occurs twice in a term.
+inline bool build_particle_csr(long long n_particles, long long n_terms, int n_slots,
+                               const int32_t* const* index, std::vector<uint32_t>& start,
+                               std::vector<uint32_t>& refs) {
+    start.assign((size_t)n_particles + 1, 0u);
+    if (n_terms >= (1LL << 30)) return false;
+    for (long long t = 0; t < n_terms; ++t)
+        for (int s = 0; s < n_slots; ++s) {
+            const long long p = index[s][t];
+            if (p < 0 || p >= n_particles) return false;
+            for (int s2 = 0; s2 < s; ++s2)
+                if (index[s2][t] == p) return false;
+            start[(size_t)p + 1]++;
+        }
+    for (long long p = 0; p < n_particles; ++p) start[(size_t)p + 1] += start[(size_t)p];
+    refs.assign((size_t)n_terms * n_slots, 0u);
+    std::vector<uint32_t> cur(start.begin(), start.end() - 1);
+    for (long long t = 0; t < n_terms; ++t)
+        for (int s = 0; s < n_slots; ++s) refs[cur[(size_t)index[s][t]]++] = (uint32_t)(t * 4 + s);
+    return true;
+}
+
+// One particle's bonded forces of one kind (KIND = 2, 3, 4 particles per term).
+template <typename real, int KIND>
+__host__ __device__ inline BondAcc particle_terms(long long p, const real* __restrict__ pos, Vec3d box,
+                                                  const uint32_t* __restrict__ start,
+                                                  const uint32_t* __restrict__ refs,
+                                                  const int32_t* __restrict__ idx,     // [term][4]
+                                                  const double* __restrict__ par,      // [term][2] or [term][30]
+                                                  const int32_t* __restrict__ dtype) {
+    BondAcc acc = {{0.0, 0.0, 0.0}, 0.0, {0.0, 0.0, 0.0}};
+    for (uint32_t r = start[p]; r < start[p + 1]; ++r) {
+        const uint32_t ref = refs[r];
+        const long long t = ref >> 2;
+        const int slot = (int)(ref & 3u);
+        const int32_t* ix = idx + 4 * t;
+        if (KIND == 2)
+            bond_term(pos, box, ix[0], ix[1], par[2 * t], par[2 * t + 1], slot, acc);
+        else if (KIND == 3)
+            angle_term(pos, box, ix[0], ix[1], ix[2], par[2 * t], par[2 * t + 1], slot, acc);
+        else
+            dihedral_term(pos, box, ix[0], ix[1], ix[2], ix[3], par + (long long)DIH_ROWS * DIH_COLS * t,
+                          dtype[t], slot, acc);
+    }
+    return acc;
+}
+
+}  // namespace hymd

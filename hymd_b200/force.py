@@ -1,0 +1,219 @@
+"""Device versions of HyMD's intramolecular force kernels.
+
+Same names, argument order and in-place output convention as the f2py kernels that ``hymd/main.py``
+calls ``respa_inner`` times per outer step (``main.py:841-887``):
+
+=============================  ==========================================================
+this module                    reference
+=============================  ==========================================================
+``compute_bond_forces``        ``cbf``  ``hymd/compute_bond_forces.f90:1-61``
+``compute_angle_forces``       ``caf``  ``hymd/compute_angle_forces.f90:1-93``
+``compute_dihedral_forces``    ``cdf``  ``hymd/compute_dihedral_forces.f90:1-137`` (dtype 0, 2)
+=============================  ==========================================================
+
+The index / parameter arrays are the ones ``prepare_bonds`` returns (``hymd/force.py:573-728``;
+host numpy arrays).  They are uploaded once into a device-resident :class:`BondedTopology`
+(``hymd_bonded_create``: per-particle term lists, see ``csrc/bonded.cuh``) that is cached on the
+identity of the index arrays, so the per-step calls only launch kernels.  Positions and forces may
+be torch CUDA tensors (no copies) or numpy arrays (copied in and out).  There is no CPU fallback.
+
+Return values follow the reference (energy, pressure by-product).  With CUDA tensor inputs they are
+0-dim / (3,) float64 DEVICE tensors, so the inner rRESPA loop never synchronizes with the host
+(``main.py:964-970`` only reads the energies of the last inner step); with numpy inputs they are a
+Python float and a numpy array exactly like the f2py kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_I32P = ctypes.POINTER(ctypes.c_int32)
+_F64P = ctypes.POINTER(ctypes.c_double)
+
+
+def _i32(x):
+    return np.ascontiguousarray(np.asarray(x), dtype=np.int32).reshape(-1)
+
+
+def _f64(x):
+    return np.ascontiguousarray(np.asarray(x), dtype=np.float64)
+
+
+def _default_device():
+    return f"cuda:{torch.cuda.current_device()}"
+
+
+class BondedTopology:
+    """Device-resident term lists of one rank's molecules (``hymd_bonded`` handle)."""
+
+    def __init__(self, n_particles, bonds=None, angles=None, dihedrals=None, device=None):
+        """``bonds = (a, b, r0, k)``, ``angles = (a, b, c, theta0, k)``,
+        ``dihedrals = (a, b, c, d, coeff (D,6,5), dih_type)``; any of them may be ``None``."""
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.HymdError("hymd_b200.force needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device if device is not None else _default_device())
+        self.n_particles = int(n_particles)
+        empty_i, empty_f = np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float64)
+        a2, b2, r0, k2 = bonds if bonds is not None else (empty_i, empty_i, empty_f, empty_f)
+        a3, b3, c3, t0, k3 = angles if angles is not None else (empty_i,) * 3 + (empty_f,) * 2
+        if dihedrals is not None:
+            a4, b4, c4, d4, coeff, dtype4 = dihedrals
+        else:
+            a4 = b4 = c4 = d4 = dtype4 = empty_i
+            coeff = np.zeros((0, 6, 5))
+        keep = [_i32(a2), _i32(b2), _f64(r0).reshape(-1), _f64(k2).reshape(-1),
+                _i32(a3), _i32(b3), _i32(c3), _f64(t0).reshape(-1), _f64(k3).reshape(-1),
+                _i32(a4), _i32(b4), _i32(c4), _i32(d4), _f64(coeff).reshape(-1), _i32(dtype4)]
+        self.n_terms = (len(keep[0]), len(keep[4]), len(keep[9]))
+        if len(keep[13]) != 30 * self.n_terms[2]:
+            raise ValueError("bonds_4_coeff must have shape (D, 6, 5) (prepare_bonds, force.py:678-690)")
+
+        def ip(x):
+            return x.ctypes.data_as(_I32P)
+
+        def fp(x):
+            return x.ctypes.data_as(_F64P)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.hymd_bonded_create(
+                self.n_particles,
+                self.n_terms[0], ip(keep[0]), ip(keep[1]), fp(keep[2]), fp(keep[3]),
+                self.n_terms[1], ip(keep[4]), ip(keep[5]), ip(keep[6]), fp(keep[7]), fp(keep[8]),
+                self.n_terms[2], ip(keep[9]), ip(keep[10]), ip(keep[11]), ip(keep[12]), fp(keep[13]),
+                ip(keep[14]), ctypes.byref(handle)))
+        self._h = handle
+        self._out = torch.zeros((3, 4), dtype=torch.float64, device=self.device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.hymd_bonded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self):
+        return int(self.lib.hymd_bonded_launch_count(self._h))
+
+    def forces(self, kind, positions, box_size, out):
+        """Launch the kernel for ``kind`` (2, 3 or 4 particles per term): ``out`` (n,3) device
+        tensor is overwritten; returns the (4,) float64 device tensor {energy, pr_x, pr_y, pr_z}."""
+        n = self.n_particles
+        if tuple(positions.shape) != (n, 3) or tuple(out.shape) != (n, 3):
+            raise ValueError(f"positions / forces must have shape ({n}, 3)")
+        if positions.dtype != out.dtype or positions.dtype not in (torch.float32, torch.float64):
+            raise ValueError("positions and forces must share dtype float32 or float64")
+        box = (ctypes.c_double * 3)(*[float(b) for b in np.asarray(box_size).reshape(-1)[:3]])
+        res = self._out[kind - 2]
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.hymd_bonded_forces(
+            self._h, int(kind), _lib.F64 if positions.dtype == torch.float64 else _lib.F32,
+            ctypes.c_void_p(positions.data_ptr()), box, ctypes.c_void_p(out.data_ptr()),
+            ctypes.cast(ctypes.c_void_p(res.data_ptr()), _F64P), stream))
+        return res
+
+
+# topology cache: keyed by the identity and length of the caller's index arrays, so that the
+# reference's call pattern (same prepare_bonds arrays every inner step) uploads once
+_cache = {}
+
+
+def _topology(kind, n_particles, device, arrays, build):
+    key = (kind, n_particles, str(device)) + tuple((id(a), len(a)) for a in arrays)
+    hit = _cache.get(key)
+    if hit is not None and all(r() is a for r, a in zip(hit[1], arrays)):
+        return hit[0]
+    topo = build()
+    try:
+        refs = [weakref.ref(a) for a in arrays]
+    except TypeError:      # lists cannot be weak-referenced: no caching
+        return topo
+    if len(_cache) > 64:
+        _cache.clear()
+    _cache[key] = (topo, refs)
+    return topo
+
+
+def _device_io(r, f):
+    """(device positions, device force buffer, copy-back callback or None)."""
+    if isinstance(r, torch.Tensor) and r.is_cuda:
+        pos = r.contiguous()
+        if isinstance(f, torch.Tensor) and f.is_cuda and f.is_contiguous() and f.dtype == pos.dtype:
+            return pos, f, None
+        buf = torch.empty_like(pos)
+        return pos, buf, (lambda: f.copy_(buf)) if isinstance(f, torch.Tensor) else (lambda: f.__setitem__(Ellipsis, buf.cpu().numpy()))
+    if not torch.cuda.is_available():
+        raise _lib.HymdError("hymd_b200.force needs a CUDA device (no CPU fallback)")
+    arr = np.asarray(r)
+    dt = torch.float64 if arr.dtype == np.float64 else torch.float32
+    pos = torch.as_tensor(np.ascontiguousarray(arr), dtype=dt).cuda()
+    buf = torch.empty_like(pos)
+
+    def back():
+        if isinstance(f, torch.Tensor):
+            f.copy_(buf)
+        else:
+            f[...] = buf.cpu().numpy()
+    return pos, buf, back
+
+
+def _result(res, on_device, with_pr=True):
+    if on_device:
+        res = res.clone()      # the topology reuses its result buffer on the next call
+        return (res[0], res[1:4]) if with_pr else res[0]
+    host = res.cpu().numpy()
+    return (float(host[0]), host[1:4].copy()) if with_pr else float(host[0])
+
+
+def compute_bond_forces(f_bonds, r, box_size, a, b, r0, k):
+    """``cbf``: harmonic two-particle bonds; writes ``f_bonds`` in place, returns
+    ``(energy, bond_pr)``."""
+    pos, buf, back = _device_io(r, f_bonds)
+    topo = _topology(2, pos.shape[0], pos.device, (a, b, r0, k),
+                     lambda: BondedTopology(pos.shape[0], bonds=(a, b, r0, k), device=pos.device))
+    res = topo.forces(2, pos, box_size, buf)
+    if back is not None:
+        back()
+    return _result(res, back is None)
+
+
+def compute_angle_forces(f_angles, r, box_size, a, b, c, t0, k):
+    """``caf``: harmonic three-particle angles; returns ``(energy, angle_pr)``."""
+    pos, buf, back = _device_io(r, f_angles)
+    topo = _topology(3, pos.shape[0], pos.device, (a, b, c, t0, k),
+                     lambda: BondedTopology(pos.shape[0], angles=(a, b, c, t0, k), device=pos.device))
+    res = topo.forces(3, pos, box_size, buf)
+    if back is not None:
+        back()
+    return _result(res, back is None)
+
+
+def compute_dihedral_forces(f_dihedrals, r, dipoles, transfer_matrix, box_size, a, b, c, d, coeff,
+                            dtype, bb_index=None, dipole_flag=0):
+    """``cdf`` for ``dtype`` 0 (cosine series) and 2 (improper); returns the energy.  ``dipoles`` and
+    ``transfer_matrix`` are zeroed like the Fortran does (``compute_dihedral_forces.f90:27-28``);
+    terms of ``dtype`` 1 (combined bending-torsion + dipole reconstruction) raise ``HymdError``."""
+    pos, buf, back = _device_io(r, f_dihedrals)
+    topo = _topology(4, pos.shape[0], pos.device, (a, b, c, d, coeff, dtype),
+                     lambda: BondedTopology(pos.shape[0], dihedrals=(a, b, c, d, coeff, dtype),
+                                            device=pos.device))
+    res = topo.forces(4, pos, box_size, buf)
+    for arr in (dipoles, transfer_matrix):
+        if arr is None:
+            continue
+        if isinstance(arr, torch.Tensor):
+            arr.zero_()
+        else:
+            arr[...] = 0
+    if back is not None:
+        back()
+    return _result(res, back is None, with_pr=False)

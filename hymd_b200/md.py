@@ -64,3 +64,93 @@ class FieldOnlyMD:
         forces = self.force_fn(positions)                                         # main.py:976-1004
         velocities = integrate_velocity(velocities, forces / self.mass, outer)   # main.py:1144-1148
         return positions, velocities, forces
+
+
+# --- device-resident rRESPA step -----------------------------------
+
+def kick_drift(vel, pos, forces, mass, kick_dt, drift_dt=0.0, box=None, sequential=False):
+    """Fused velocity-Verlet update on CUDA tensors, in place (``csrc/md.cu``):
+    ``vel += 0.5*kick_dt*(sum forces)/mass`` (or one kick per force array in turn with
+    ``sequential``, the way ``main.py:803-827`` applies field / electrostatic / ... forces), then,
+    if ``pos`` is given, ``pos = mod(pos + drift_dt*vel, box)`` (``main.py:835-837``) in the same
+    pass over the arrays."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from . import _lib
+    lib = _lib.load()
+    forces = [f for f in forces if f is not None]
+    for t in [vel] + forces + ([pos] if pos is not None else []):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous() and t.dtype == vel.dtype
+                and t.shape == vel.shape):
+            raise ValueError("kick_drift needs contiguous CUDA tensors of one dtype and shape (N,3)")
+    code = _lib.F64 if vel.dtype == torch.float64 else _lib.F32
+    fptr = (ctypes.c_void_p * max(len(forces), 1))(*[f.data_ptr() for f in forces])
+    bx = None
+    if pos is not None:
+        bx = (ctypes.c_double * 3)(*[float(b) for b in np.asarray(box).reshape(-1)[:3]])
+    _lib.check(lib.hymd_md_kick_drift(
+        code, ctypes.c_void_p(vel.data_ptr()), ctypes.c_void_p(pos.data_ptr()) if pos is not None else None,
+        fptr, len(forces), 1 if sequential else 0, float(mass), float(kick_dt), float(drift_dt), bx,
+        int(vel.shape[0]), ctypes.c_void_p(torch.cuda.current_stream(vel.device).cuda_stream)))
+
+
+class RespaMD:
+    """One outer rRESPA step of ``main.py:764-1169`` with everything resident on the GPU.
+
+    ``field_force_fn(positions) -> list of (N,3) slow-force tensors`` (field forces, and the
+    electrostatic forces when charges are present: each gets its own kick, ``main.py:803-827``);
+    ``topology`` is a :class:`hymd_b200.force.BondedTopology` (or ``None`` for monatomic systems).
+    Positions and velocities are CUDA tensors updated in place; per inner step the launches are one
+    fused kick+drift+wrap kernel, the bonded kernels and one kick kernel.  ``thermostat`` is a
+    callable ``(velocities) -> None`` applied every ``n_b`` outer steps (``main.py:1290-1292``)."""
+
+    def __init__(self, field_force_fn, box, mass, time_step, respa_inner=1, topology=None,
+                 thermostat=None, n_b=1):
+        self.field_force_fn = field_force_fn
+        self.box = box
+        self.mass = float(mass)
+        self.dt = float(time_step)
+        self.inner = int(respa_inner)
+        self.topology = topology
+        self.thermostat = thermostat
+        self.n_b = int(n_b)
+        self.step_count = 0
+        self.fast = None
+        self.bonded_results = {}
+
+    def fast_forces(self, positions):
+        """Bond / angle / dihedral forces at ``positions`` (``main.py:841-887``): list of tensors."""
+        import torch
+        topo = self.topology
+        if topo is None:
+            return []
+        if self.fast is None:
+            self.fast = [torch.zeros_like(positions) if topo.n_terms[k] > 0 else None for k in range(3)]
+        for k in range(3):
+            if self.fast[k] is not None:
+                self.bonded_results[k + 2] = topo.forces(k + 2, positions, self.box, self.fast[k])
+        return [f for f in self.fast if f is not None]
+
+    def bonded_energies(self):
+        """{2: bond, 3: angle, 4: dihedral} energies of the last inner step (``main.py:964-970``);
+        reads the device results (synchronizes)."""
+        return {k: float(v[0].item()) for k, v in self.bonded_results.items()}
+
+    def step(self, positions, velocities, slow_forces):
+        """From ``(x, v, slow forces at x)`` to the next outer step; returns the new slow forces."""
+        outer = self.inner * self.dt
+        kick_drift(velocities, None, slow_forces, self.mass, outer, sequential=True)     # main.py:803-827
+        fast = self.fast_forces(positions) if self.fast is None else [f for f in self.fast if f is not None]
+        for _ in range(self.inner):                                                      # main.py:829-893
+            kick_drift(velocities, positions, fast, self.mass, self.dt, self.dt, self.box)
+            fast = self.fast_forces(positions)
+            kick_drift(velocities, None, fast, self.mass, self.dt)
+        slow_forces = self.field_force_fn(positions)                                     # main.py:976-1058
+        kick_drift(velocities, None, slow_forces, self.mass, outer, sequential=True)     # main.py:1144-1169
+        self.step_count += 1
+        if self.thermostat is not None and self.step_count % self.n_b == 0:             # main.py:1290-1292
+            self.thermostat(velocities)
+        return slow_forces

@@ -218,6 +218,71 @@ int hymd_migrate_plan(hymd_ctx* ctx, const void* d_pos, int64_t n, int64_t* n_ne
 int hymd_migrate_apply(hymd_ctx* ctx, const void* d_in, void* d_out, int32_t row_bytes,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row f2: the caller side of the hot path kept on the device -- intramolecular
+ * forces, velocity-Verlet / rRESPA updates and the CSVR thermostat -- so that positions and velocities
+ * never leave HBM between field-force cycles.  These entry points are stateless with respect to
+ * hymd_ctx (any stream, any number of contexts).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Device-resident term lists built from what prepare_bonds returns (hymd/force.py:573-728; HOST arrays
+ * of local particle indices and parameters).  coeff4 is bonds_4_coeff (n4,6,5) row-major, type4 is
+ * bonds_4_type; dih_type 1 (combined bending-torsion with dipole reconstruction,
+ * dipole_reconstruction.f90:50-221) is rejected with HYMD_ERR_INVALID.  Synchronous.  Rebuild after
+ * domain_decomposition permutes the particles (main.py:1239-1262 does the same with prepare_bonds). */
+typedef struct hymd_bonded hymd_bonded;
+int hymd_bonded_create(int64_t n_particles,
+                       int64_t n2, const int32_t* a2, const int32_t* b2, const double* r0_2, const double* k_2,
+                       int64_t n3, const int32_t* a3, const int32_t* b3, const int32_t* c3,
+                       const double* t0_3, const double* k_3,
+                       int64_t n4, const int32_t* a4, const int32_t* b4, const int32_t* c4, const int32_t* d4,
+                       const double* coeff4, const int32_t* type4, hymd_bonded** out);
+int hymd_bonded_destroy(hymd_bonded* b);
+
+/* cbf / caf / cdf (hymd/compute_bond_forces.f90:1-61, compute_angle_forces.f90:1-93,
+ * compute_dihedral_forces.f90:1-137; call sites main.py:841-887): kind = 2, 3 or 4 particles per term.
+ * d_pos (n,3) and d_force (n,3) row-major in `dtype` (hymd_dtype); d_force is overwritten for every
+ * particle (the Fortran zeroes f first).  d_out is a DEVICE array of 4 doubles that receives
+ * {energy, pr_x, pr_y, pr_z} (bond_pr / angle_pr; zeros for dihedrals) -- no host synchronization. */
+int hymd_bonded_forces(hymd_bonded* b, int kind, int dtype, const void* d_pos, const double box[3],
+                       void* d_force, double* d_out, void* stream);
+int64_t hymd_bonded_launch_count(hymd_bonded* b);
+
+/* integrate_velocity / integrate_position (hymd/integrator.py:9-75) fused over the arrays:
+ *   sequential == 0:  v += 0.5*kick_dt * (f_0 + ... + f_{n_forces-1}) / mass      (main.py:830-834, 889-893)
+ *   sequential == 1:  v += 0.5*kick_dt * f_k / mass  for k = 0, 1, ... in turn    (main.py:803-827, 1144-1169)
+ * and, if d_pos != NULL,  x = mod(x + drift_dt * v, box)                           (main.py:835-837)
+ * in the same pass.  d_forces is a HOST array of n_forces (<= 8) device pointers; n_forces may be 0
+ * (drift only). */
+int hymd_md_kick_drift(int dtype, void* d_vel, void* d_pos, const void* const* d_forces, int n_forces,
+                       int sequential, double mass, double kick_dt, double drift_dt, const double box[3],
+                       int64_t n, void* stream);
+
+/* Velocity moments {count, sum vx, sum vy, sum vz, sum |v|^2} of the particles with d_group[i] == group
+ * (every particle if d_group == NULL or group < 0) -> d_out[0..4], and of all n particles ->
+ * d_out[5..9] (DEVICE doubles; the caller all-reduces them across ranks where the reference calls
+ * comm.allreduce: thermostat.py:13, 184-191; kinetic energy field.py:695).  d_scratch holds
+ * hymd_velocity_moments_scratch_doubles() doubles.  Fixed summation order. */
+int hymd_velocity_moments(int dtype, const void* d_vel, const int32_t* d_group, int group, int64_t n,
+                          double* d_scratch, double* d_out, void* stream);
+int64_t hymd_velocity_moments_scratch_doubles(void);
+
+/* csvr_thermostat for ONE coupling group (hymd/thermostat.py:184-219) given the reduced moments:
+ * kT15 = 1.5 * gas_constant * target_temperature, c = exp(-time_step*respa_inner/tau), R and SNf the
+ * Gaussian and chi-squared draws of this group (drawn on the host from the caller's prng in the
+ * reference's order).  remove_com != 0 and more than one particle in the group: the group is rescaled
+ * about its centre-of-mass velocity; otherwise, like the reference, the kinetic energy of ALL particles
+ * is used and ALL velocities are rescaled.  Adds the thermostat work dK to d_work[0] (device double;
+ * may be NULL). */
+int hymd_csvr_apply(int dtype, void* d_vel, const int32_t* d_group, int group, int64_t n,
+                    const double* d_moments, double mass, double kT15, double c, double R, double SNf,
+                    int remove_com, double* d_work, void* stream);
+
+/* cancel_com_momentum (hymd/thermostat.py:12-15): v -= (sum v over all particles) / n_particles with
+ * the sums taken from d_moments[6..8]. */
+int hymd_cancel_com(int dtype, void* d_vel, int64_t n, const double* d_moments, double n_particles,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,16 +27,20 @@ import numpy as np
 
 
 def _mic(d, box):
-    """``d - box * nint(d / box)`` (Fortran ``nint`` rounds half away from zero)."""
+    """``d - box * nint(d / box)`` (Fortran ``nint`` rounds half away from zero).  ``d`` arrives as the
+    difference of two positions IN THE POSITION DTYPE (``r`` is ``real(4)`` in the default build, so
+    ``r(bb,:) - r(aa,:)`` is a single-precision subtraction) and is widened to float64 here, like the
+    assignment to the ``real(8)`` local does."""
+    d = np.asarray(d, dtype=np.float64)
     q = d / box
     return d - box * (np.sign(q) * np.floor(np.abs(q) + 0.5))
 
 
 def compute_bond_forces(r, box, a, b, r0, k):
     """``cbf``: returns ``(f (N,3) float64, energy, bond_pr (3,))``."""
-    r = np.asarray(r, dtype=np.float64)
+    r = np.asarray(r)
     box = np.asarray(box, dtype=np.float64)
-    f = np.zeros_like(r)
+    f = np.zeros(r.shape, dtype=np.float64)
     energy = 0.0
     pr = np.zeros(3)
     for aa, bb, r0i, ki in zip(a, b, r0, k):
@@ -53,9 +57,9 @@ def compute_bond_forces(r, box, a, b, r0, k):
 
 def compute_angle_forces(r, box, a, b, c, t0, k):
     """``caf``: returns ``(f, energy, angle_pr)``."""
-    r = np.asarray(r, dtype=np.float64)
+    r = np.asarray(r)
     box = np.asarray(box, dtype=np.float64)
-    f = np.zeros_like(r)
+    f = np.zeros(r.shape, dtype=np.float64)
     energy = 0.0
     pr = np.zeros(3)
     for aa, bb, cc, t0i, ki in zip(a, b, c, t0, k):
@@ -93,10 +97,10 @@ def _cosine_series(c_n, d_n, phi):
 def compute_dihedral_forces(r, box, a, b, c, d, coeff, dtype):
     """``cdf`` for ``dtype`` 0 and 2: returns ``(f, energy)``.  ``coeff`` is the (D,6,5) array that
     ``prepare_bonds`` builds (``force.py:678-690``)."""
-    r = np.asarray(r, dtype=np.float64)
+    r = np.asarray(r)
     box = np.asarray(box, dtype=np.float64)
     coeff = np.asarray(coeff, dtype=np.float64)
-    force = np.zeros_like(r)
+    force = np.zeros(r.shape, dtype=np.float64)
     energy = 0.0
     for ind, (aa, bb, cc, dd) in enumerate(zip(a, b, c, d)):
         f = _mic(r[aa] - r[bb], box)

@@ -1,0 +1,212 @@
+// TEST INFRASTRUCTURE: runs the __host__ __device__ per-particle functions of
+// hymd_b200/csrc/bonded.cuh and md.cuh -- the same source the sm_100a kernels compile -- on the CPU,
+// so tests/test_native_host_check.py can compare the device arithmetic (term lists, slot logic,
+// minimum image, cosine series, CSVR scale) with the oracle in the GPU-less container.  Built by the
+// test with g++; never linked into libhymd_b200.so and never used by the product.
+#include "../../hymd_b200/csrc/bonded.cuh"
+#include "../../hymd_b200/csrc/md.cuh"
+
+using namespace hymd;
+
+template <typename real, int KIND>
+static void run_kind(const real* pos, Vec3d box, long long n, const std::vector<uint32_t>& start,
+                     const std::vector<uint32_t>& refs, const std::vector<int32_t>& idx, const double* par,
+                     const int32_t* dtype, real* force, double* out4) {
+    out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
+    for (long long p = 0; p < n; ++p) {
+        BondAcc a = particle_terms<real, KIND>(p, pos, box, start.data(), refs.data(), idx.data(), par, dtype);
+        force[3 * p] = (real)a.f.x; force[3 * p + 1] = (real)a.f.y; force[3 * p + 2] = (real)a.f.z;
+        out4[0] += a.e; out4[1] += a.pr.x; out4[2] += a.pr.y; out4[3] += a.pr.z;
+    }
+}
+
+extern "C" int host_bonded(int kind, int f64, const void* pos, const double* box, long long n, long long nt,
+                           const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d,
+                           const double* par, const int32_t* dtype, void* force, double* out4) {
+    const int32_t* index[4] = {a, b, c, d};
+    std::vector<uint32_t> start, refs;
+    if (!build_particle_csr(n, nt, kind, index, start, refs)) return -1;
+    std::vector<int32_t> idx((size_t)nt * 4, 0);
+    for (long long t = 0; t < nt; ++t)
+        for (int s = 0; s < kind; ++s) idx[4 * t + s] = index[s][t];
+    const Vec3d bx = {box[0], box[1], box[2]};
+#define RUN(real, K) run_kind<real, K>((const real*)pos, bx, n, start, refs, idx, par, dtype, (real*)force, out4)
+    if (f64) { if (kind == 2) RUN(double, 2); else if (kind == 3) RUN(double, 3); else RUN(double, 4); }
+    else     { if (kind == 2) RUN(float, 2);  else if (kind == 3) RUN(float, 3);  else RUN(float, 4); }
+#undef RUN
+    return 0;
+}
+
+template <typename real>
+static void kd(real* vel, real* pos, const void* const* forces, int nf, int sequential, double mass,
+               double kick_dt, double drift_dt, const double* box, long long n) {
+    for (long long i = 0; i < 3 * n; ++i) {
+        real v = vel[i];
+        if (nf > 0) {
+            real ft[MD_MAX_FORCES];
+            for (int k = 0; k < nf; ++k) ft[k] = ((const real*)forces[k])[i];
+            if (sequential) for (int k = 0; k < nf; ++k) v = kick(v, &ft[k], 1, (real)mass, (real)(0.5 * kick_dt));
+            else v = kick(v, ft, nf, (real)mass, (real)(0.5 * kick_dt));
+            vel[i] = v;
+        }
+        if (pos) pos[i] = drift_wrap(pos[i], v, (real)drift_dt, (real)box[i % 3]);
+    }
+}
+
+extern "C" int host_kick_drift(int f64, void* vel, void* pos, const void* const* forces, int nf,
+                               int sequential, double mass, double kick_dt, double drift_dt,
+                               const double* box, long long n) {
+    if (f64) kd<double>((double*)vel, (double*)pos, forces, nf, sequential, mass, kick_dt, drift_dt, box, n);
+    else kd<float>((float*)vel, (float*)pos, forces, nf, sequential, mass, kick_dt, drift_dt, box, n);
+    return 0;
+}
+
+template <typename real>
+static void csvr(real* vel, const int32_t* group, int g, long long n, double mass, double kT15, double c,
+                 double R, double SNf, int remove_com, double* work) {
+    double mom[2 * MOM] = {0};
+    for (long long i = 0; i < n; ++i) {
+        const double vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+        const bool in_g = (!group || g < 0) ? true : group[i] == g;
+        if (in_g) { mom[0] += 1; mom[1] += vx; mom[2] += vy; mom[3] += vz; mom[4] += vx * vx + vy * vy + vz * vz; }
+        mom[5] += 1; mom[6] += vx; mom[7] += vy; mom[8] += vz; mom[9] += vx * vx + vy * vy + vz * vz;
+    }
+    double dK;
+    const CsvrScale s = csvr_scale(mom, mass, kT15, c, R, SNf, remove_com, &dK);
+    for (long long i = 0; i < n; ++i)
+        csvr_apply_particle(vel + 3 * i, s, (!group || g < 0) ? true : group[i] == g);
+    work[0] += dK;
+}
+
+extern "C" int host_csvr(int f64, void* vel, const int32_t* group, int g, long long n, double mass,
+                         double kT15, double c, double R, double SNf, int remove_com, double* work) {
+    if (f64) csvr<double>((double*)vel, group, g, n, mass, kT15, c, R, SNf, remove_com, work);
+    else csvr<float>((float*)vel, group, g, n, mass, kT15, c, R, SNf, remove_com, work);
+    return 0;
+}
+
+// ---- the row-f2 C ABI (include/hymd_b200.h) emulated on HOST memory ------------------------------
+// Same entry-point names and signatures as libhymd_b200.so, so that tests/test_md_host_emulation.py
+// can run the Python host layer (hymd_b200/force.py, thermostat.py, md.py) and the GPU test bodies
+// on CPU tensors in the GPU-less container.  The loops call the same per-particle functions the
+// kernels call; only launch geometry and the parallel reductions differ.
+struct HostBonded {
+    long long n;
+    std::vector<uint32_t> start[3], refs[3];
+    std::vector<int32_t> idx[3], dtype;
+    std::vector<double> par[3];
+    long long launches;
+};
+
+static bool host_upload(HostBonded* b, int kind, long long nt, int slots, const int32_t* const* index,
+                        const double* par, size_t per_term) {
+    if (!build_particle_csr(b->n, nt, slots, index, b->start[kind], b->refs[kind])) return false;
+    b->idx[kind].assign((size_t)nt * 4, 0);
+    for (long long t = 0; t < nt; ++t)
+        for (int s = 0; s < slots; ++s) b->idx[kind][4 * t + s] = index[s][t];
+    b->par[kind].assign(par, par + (size_t)nt * per_term);
+    return true;
+}
+
+extern "C" int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const int32_t* b2,
+                                  const double* r0_2, const double* k_2, int64_t n3, const int32_t* a3,
+                                  const int32_t* b3, const int32_t* c3, const double* t0_3, const double* k_3,
+                                  int64_t n4, const int32_t* a4, const int32_t* b4, const int32_t* c4,
+                                  const int32_t* d4, const double* coeff4, const int32_t* type4, void** out) {
+    for (int64_t t = 0; t < n4; ++t)
+        if (type4[t] != 0 && type4[t] != 2) return -1;
+    HostBonded* b = new HostBonded();
+    b->n = n_particles;
+    b->launches = 0;
+    std::vector<double> p2((size_t)n2 * 2), p3((size_t)n3 * 2);
+    for (int64_t t = 0; t < n2; ++t) { p2[2 * t] = r0_2[t]; p2[2 * t + 1] = k_2[t]; }
+    for (int64_t t = 0; t < n3; ++t) { p3[2 * t] = t0_3[t]; p3[2 * t + 1] = k_3[t]; }
+    const int32_t* i2[2] = {a2, b2};
+    const int32_t* i3[3] = {a3, b3, c3};
+    const int32_t* i4[4] = {a4, b4, c4, d4};
+    if (!host_upload(b, 0, n2, 2, i2, p2.data(), 2) || !host_upload(b, 1, n3, 3, i3, p3.data(), 2) ||
+        !host_upload(b, 2, n4, 4, i4, coeff4, (size_t)DIH_ROWS * DIH_COLS)) {
+        delete b;
+        return -1;
+    }
+    b->dtype.assign(type4, type4 + n4);
+    *out = b;
+    return 0;
+}
+
+extern "C" int hymd_bonded_destroy(void* b) { delete (HostBonded*)b; return 0; }
+extern "C" int64_t hymd_bonded_launch_count(void* b) { return ((HostBonded*)b)->launches; }
+
+extern "C" int hymd_bonded_forces(void* h, int kind, int dtype, const void* pos, const double* box,
+                                  void* force, double* out, void* stream) {
+    HostBonded* b = (HostBonded*)h;
+    const int k = kind - 2;
+    const Vec3d bx = {box[0], box[1], box[2]};
+    b->launches += 2;
+#define RUN(real, K) run_kind<real, K>((const real*)pos, bx, b->n, b->start[k], b->refs[k], b->idx[k], \
+                                       b->par[k].data(), b->dtype.data(), (real*)force, out)
+    if (dtype == 1) { if (kind == 2) RUN(double, 2); else if (kind == 3) RUN(double, 3); else RUN(double, 4); }
+    else            { if (kind == 2) RUN(float, 2);  else if (kind == 3) RUN(float, 3);  else RUN(float, 4); }
+#undef RUN
+    return 0;
+}
+
+extern "C" int hymd_md_kick_drift(int dtype, void* vel, void* pos, const void* const* forces, int nf,
+                                  int sequential, double mass, double kick_dt, double drift_dt,
+                                  const double* box, int64_t n, void* stream) {
+    if (nf < 0 || nf > MD_MAX_FORCES) return -1;
+    return host_kick_drift(dtype == 1, vel, pos, forces, nf, sequential, mass, kick_dt, drift_dt, box, n);
+}
+
+extern "C" int64_t hymd_velocity_moments_scratch_doubles(void) { return 16; }
+
+template <typename real>
+static void moments(const real* vel, const int32_t* group, int g, long long n, double* mom) {
+    for (int k = 0; k < 2 * MOM; ++k) mom[k] = 0.0;
+    for (long long i = 0; i < n; ++i) {
+        const double vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+        const bool in_g = (!group || g < 0) ? true : group[i] == g;
+        if (in_g) { mom[0] += 1; mom[1] += vx; mom[2] += vy; mom[3] += vz; mom[4] += vx * vx + vy * vy + vz * vz; }
+        mom[5] += 1; mom[6] += vx; mom[7] += vy; mom[8] += vz; mom[9] += vx * vx + vy * vy + vz * vz;
+    }
+}
+
+extern "C" int hymd_velocity_moments(int dtype, const void* vel, const int32_t* group, int g, int64_t n,
+                                     double* scratch, double* out, void* stream) {
+    if (dtype == 1) moments<double>((const double*)vel, group, g, n, out);
+    else moments<float>((const float*)vel, group, g, n, out);
+    return 0;
+}
+
+template <typename real>
+static void apply(real* vel, const int32_t* group, int g, long long n, const double* mom, double mass,
+                  double kT15, double c, double R, double SNf, int remove_com, double* work) {
+    double dK;
+    const CsvrScale s = csvr_scale(mom, mass, kT15, c, R, SNf, remove_com, &dK);
+    for (long long i = 0; i < n; ++i)
+        csvr_apply_particle(vel + 3 * i, s, (!group || g < 0) ? true : group[i] == g);
+    if (work) work[0] += dK;
+}
+
+extern "C" int hymd_csvr_apply(int dtype, void* vel, const int32_t* group, int g, int64_t n, const double* mom,
+                               double mass, double kT15, double c, double R, double SNf, int remove_com,
+                               double* work, void* stream) {
+    if (dtype == 1) apply<double>((double*)vel, group, g, n, mom, mass, kT15, c, R, SNf, remove_com, work);
+    else apply<float>((float*)vel, group, g, n, mom, mass, kT15, c, R, SNf, remove_com, work);
+    return 0;
+}
+
+extern "C" int hymd_cancel_com(int dtype, void* vel, int64_t n, const double* mom, double n_particles,
+                               void* stream) {
+    const double cx = mom[MOM + 1] / n_particles, cy = mom[MOM + 2] / n_particles, cz = mom[MOM + 3] / n_particles;
+    for (long long i = 0; i < n; ++i) {
+        if (dtype == 1) {
+            double* v = (double*)vel + 3 * i;
+            v[0] -= cx; v[1] -= cy; v[2] -= cz;
+        } else {
+            float* v = (float*)vel + 3 * i;
+            v[0] = (float)((double)v[0] - cx); v[1] = (float)((double)v[1] - cy); v[2] = (float)((double)v[2] - cz);
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,191 @@
+"""The device arithmetic of csrc/bonded.cuh and csrc/md.cuh, executed on the CPU.
+
+The per-particle functions of the bonded / integrator / thermostat kernels are ``__host__ __device__``;
+tests/native/host_check.cpp wraps exactly that source in plain loops and is compiled here with g++.
+This checks, without a GPU, what the kernels compute per particle (term lists and slots, minimum image,
+angle / dihedral algebra, cosine series, kick / drift / wrap rounding, CSVR scale) against the oracle
+and the reference's golden vectors; the launch geometry and reductions are covered by the ``-m gpu``
+tests (tests/test_zgpu_md.py)."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import bonded_oracle as bo
+from oracle import thermostat_oracle as to
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "bonded_golden.npz"))
+TG = np.load(os.path.join(HERE, "golden", "thermostat_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    so = str(tmp_path_factory.mktemp("native") / "libhost_check.so")
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", so,
+                    os.path.join(HERE, "native", "host_check.cpp")], check=True)
+    return ctypes.CDLL(so)
+
+
+def i32(x):
+    return np.ascontiguousarray(x, dtype=np.int32)
+
+
+def run_bonded(lib, kind, r, box, idx, par, dtype4=None, real=np.float64):
+    r = np.ascontiguousarray(r, dtype=real)
+    n, nt = r.shape[0], len(idx[0])
+    idx = [i32(x) for x in idx] + [i32(np.zeros(nt))] * (4 - len(idx))
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    dt = i32(dtype4 if dtype4 is not None else np.zeros(nt))
+    f = np.zeros_like(r)
+    out = np.zeros(4)
+    box = np.ascontiguousarray(box, dtype=np.float64)
+    vp = ctypes.c_void_p
+    rc = lib.host_bonded(kind, int(real == np.float64), r.ctypes.data_as(vp), box.ctypes.data_as(vp),
+                         ctypes.c_longlong(n), ctypes.c_longlong(nt), *[x.ctypes.data_as(vp) for x in idx],
+                         par.ctypes.data_as(vp), dt.ctypes.data_as(vp), f.ctypes.data_as(vp),
+                         out.ctypes.data_as(vp))
+    assert rc == 0
+    return f, out
+
+
+# float32: the kernel rounds the force to float32 once (<= 6e-8 relative to its own magnitude); the
+# position differences are float32 subtractions in the Fortran, the oracle and the kernel alike
+@pytest.mark.parametrize("real,tol", [(np.float64, 1e-12), (np.float32, 1e-7)])
+def test_bonds_angles_dihedrals_match_oracle(lib, real, tol):
+    r, box = G["chains/r"], G["chains/box"]
+    rr = r.astype(real)
+    a, b, r0, k = (G["chains/b2_" + x] for x in ("a", "b", "r0", "k"))
+    f, out = run_bonded(lib, 2, rr, box, [a, b], np.stack([r0, k], 1), real=real)
+    fo_, e, pr = bo.compute_bond_forces(rr, box, a, b, r0, k)
+    scale = np.abs(fo_).max()
+    assert np.abs(f - fo_).max() <= tol * scale
+    assert out[0] == pytest.approx(e, rel=max(tol, 1e-12))
+    np.testing.assert_allclose(out[1:], pr, rtol=0, atol=max(tol, 1e-12) * np.abs(pr).max())
+    if real == np.float64:      # and the reference's own plain function, through the golden file
+        assert np.abs(f - G["chains/b2_force"]).max() <= 1e-10 * scale
+
+    a, b, c, t0, k = (G["chains/b3_" + x] for x in ("a", "b", "c", "t0", "k"))
+    f, out = run_bonded(lib, 3, rr, box, [a, b, c], np.stack([t0, k], 1), real=real)
+    fo_, e, pr = bo.compute_angle_forces(rr, box, a, b, c, t0, k)
+    scale = np.abs(fo_).max()
+    assert np.abs(f - fo_).max() <= tol * scale
+    assert out[0] == pytest.approx(e, rel=max(tol, 1e-11))
+    if real == np.float64:
+        assert np.abs(f - G["chains/b3_force"]).max() <= 1e-9 * scale
+
+    r, box = G["dih/r"], G["dih/box"]
+    rr = r.astype(real)
+    a, b, c, d, coeff = (G["dih/" + x] for x in ("a", "b", "c", "d", "coeff"))
+    dt = np.zeros(len(a), dtype=int)
+    dt[::3] = 2
+    coeff = coeff.copy()
+    coeff[::3, 0, 0] = 0.3
+    coeff[::3, 0, 1] = 40.0
+    coeff[1::3, 2] = 0.5 * coeff[1::3, 0]        # coil series switched on for a third of the terms
+    coeff[1::3, 3] = 0.25 + coeff[1::3, 1]
+    f, out = run_bonded(lib, 4, rr, box, [a, b, c, d], coeff.reshape(len(a), -1), dt, real=real)
+    fo_, e = bo.compute_dihedral_forces(rr, box, a, b, c, d, coeff, dt)
+    scale = np.abs(fo_).max()
+    assert np.abs(f - fo_).max() <= tol * scale
+    assert out[0] == pytest.approx(e, rel=max(tol, 1e-11))
+    assert np.all(out[1:] == 0)
+
+
+def test_reference_kats_through_the_device_source(lib):
+    """test/test_force.py known answers (see tests/test_oracle_bonded.py) through bonded.cuh."""
+    r, box = G["dppc/r"], G["dppc/box"]
+    a, b, r0, k = (G["dppc/b2_" + x] for x in ("a", "b", "r0", "k"))
+    f, out = run_bonded(lib, 2, r, box, [a, b], np.stack([r0, k], 1))
+    np.testing.assert_allclose(f, G["dppc/b2_force"], rtol=0, atol=1e-11)
+    assert out[0] == pytest.approx(float(G["dppc/b2_energy"]), abs=1e-12)
+    a, b, c, t0, k = (G["dppc/b3_" + x] for x in ("a", "b", "c", "t0", "k"))
+    f, out = run_bonded(lib, 3, r, box, [a, b, c], np.stack([t0, k], 1))
+    np.testing.assert_allclose(f, G["dppc/b3_force"], rtol=0, atol=1e-10)
+    assert out[0] == pytest.approx(float(G["dppc/b3_energy"]), abs=1e-11)
+    r, box = G["ala/r"], G["ala/box"]
+    a, b, c, d, coeff, dt = (G["ala/" + x] for x in ("a", "b", "c", "d", "coeff", "dtype"))
+    f, out = run_bonded(lib, 4, r, box, [a, b, c, d], coeff.reshape(len(a), -1), dt)
+    np.testing.assert_allclose(f, -G["ala/term_force_plain"].sum(axis=0), rtol=0, atol=1e-10)
+    assert out[0] == pytest.approx(float(G["ala/term_energy"].sum()), abs=1e-11)
+
+
+def test_term_list_rejects_bad_indices(lib):
+    r = np.zeros((4, 3))
+    vp = ctypes.c_void_p
+    for a, b in (([0, 5], [1, 2]), ([0, 1], [0, 2]), ([-1], [2])):
+        a, b = i32(a), i32(b)
+        z = i32(np.zeros(len(a)))
+        par = np.zeros((len(a), 2))
+        f, out = np.zeros_like(r), np.zeros(4)
+        box = np.ones(3)
+        rc = lib.host_bonded(2, 1, r.ctypes.data_as(vp), box.ctypes.data_as(vp), ctypes.c_longlong(4),
+                             ctypes.c_longlong(len(a)), a.ctypes.data_as(vp), b.ctypes.data_as(vp),
+                             z.ctypes.data_as(vp), z.ctypes.data_as(vp), par.ctypes.data_as(vp),
+                             z.ctypes.data_as(vp), f.ctypes.data_as(vp), out.ctypes.data_as(vp))
+        assert rc == -1
+
+
+@pytest.mark.parametrize("real", [np.float64, np.float32])
+def test_kick_drift_matches_numpy_expressions(lib, real):
+    """main.py:803-837 evaluated by numpy in the array dtype (what the reference does) vs md.cuh."""
+    rng = np.random.default_rng(5)
+    n = 1000
+    box = np.array([3.0, 4.0, 5.0])
+    x = (rng.random((n, 3)) * box).astype(real)
+    v = rng.normal(scale=2.0, size=(n, 3)).astype(real)
+    fs = [rng.normal(scale=300.0, size=(n, 3)).astype(real) for _ in range(3)]
+    mass, dt = 72.0, 0.03
+    vp = ctypes.c_void_p
+    fptr = (vp * 3)(*[f.ctypes.data for f in fs])
+    bx = np.ascontiguousarray(box)
+    d = ctypes.c_double
+    # inner step: summed forces, then drift + wrap
+    v1, x1 = v.copy(), x.copy()
+    lib.host_kick_drift(int(real == np.float64), v1.ctypes.data_as(vp), x1.ctypes.data_as(vp), fptr, 3, 0,
+                        d(mass), d(dt), d(dt), bx.ctypes.data_as(vp), ctypes.c_longlong(n))
+    v_ref = v + real(0.5 * dt) * ((fs[0] + fs[1] + fs[2]) / real(mass))
+    x_ref = np.mod(x + real(dt) * v_ref, box.astype(real)[None, :])
+    np.testing.assert_array_equal(v1, v_ref)
+    assert np.abs(x1 - x_ref).max() <= 4 * np.finfo(real).eps * box.max()
+    assert (x1 >= 0).all() and (x1 < box.astype(real)).all()
+    # outer step: one kick per force in turn
+    v2 = v.copy()
+    lib.host_kick_drift(int(real == np.float64), v2.ctypes.data_as(vp), None, fptr, 2, 1, d(mass), d(5 * dt),
+                        d(0.0), None, ctypes.c_longlong(n))
+    v_ref = v + real(0.5 * 5 * dt) * (fs[0] / real(mass))
+    v_ref = v_ref + real(0.5 * 5 * dt) * (fs[1] / real(mass))
+    np.testing.assert_array_equal(v2, v_ref)
+
+
+def _groups(names, groups):
+    out = np.full(len(names), -1, dtype=np.int32)
+    for i, g in enumerate(groups):
+        for t in g:
+            out[names == np.bytes_(t)] = i
+    return out
+
+
+@pytest.mark.parametrize("remove", [False, True])
+@pytest.mark.parametrize("case,groups", [("all", None), ("abcd", [["A"], ["B"], ["C"], ["D"]]),
+                                         ("abc_d", [["A", "B", "C"], ["D"]])])
+def test_csvr_matches_reference_golden(lib, case, groups, remove):
+    pre = f"mws/{case}_{'com' if remove else 'nocom'}"
+    mass, gas, T0, dt, inner, tau = TG["mws/params"]
+    v = np.ascontiguousarray(TG["mws/velocities"].copy())
+    names = TG["mws/names"]
+    grp = np.zeros(len(names), dtype=np.int32) if groups is None else _groups(names, groups)
+    work = np.zeros(1)
+    vp, d = ctypes.c_void_p, ctypes.c_double
+    c = float(np.exp(-(dt * inner) / tau))
+    for g, (R, S) in enumerate(zip(TG[pre + "/gauss"], TG[pre + "/chi2"])):
+        lib.host_csvr(1, v.ctypes.data_as(vp), grp.ctypes.data_as(vp), g, ctypes.c_longlong(len(v)), d(mass),
+                      d(1.5 * gas * T0), d(c), d(R), d(S), int(remove), work.ctypes.data_as(vp))
+    np.testing.assert_allclose(v, TG[pre + "/v"], rtol=1e-12, atol=1e-14)
+    assert work[0] == pytest.approx(float(TG[pre + "/work"]), abs=1e-10)

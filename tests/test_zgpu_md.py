@@ -1,0 +1,276 @@
+"""GPU parity of row f2 (bonded forces, rRESPA updates, CSVR thermostat) against the oracle and the
+reference's golden vectors, through hymd_b200.force / .thermostat / .md (ctypes -> C ABI).
+
+Tolerances: forces 1e-10 (fp64) / 1e-6 (fp32: one rounding of the float64 force to float32; the oracle
+takes position differences in float32 like the Fortran), relative to the largest force; energies and
+pressure by-products 1e-11 / 1e-6.  The file name sorts after the field-force parity tests on purpose:
+these kernels were added after the round's GPU budget was spent."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bonded_oracle as bo
+from oracle import thermostat_oracle as to
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "bonded_golden.npz"))
+TG = np.load(os.path.join(HERE, "golden", "thermostat_golden.npz"))
+FTOL = {np.float32: 1e-6, np.float64: 1e-10}
+ETOL = {np.float32: 1e-6, np.float64: 1e-11}
+
+
+def chains(rng, n_chains, length, box, real):
+    r = np.empty((n_chains * length, 3))
+    for m in range(n_chains):
+        steps = rng.normal(size=(length - 1, 3))
+        steps *= 0.47 / np.linalg.norm(steps, axis=1)[:, None]
+        r[m * length:(m + 1) * length] = rng.random(3) * box + np.concatenate([np.zeros((1, 3)), np.cumsum(steps, 0)])
+    r = np.mod(r, box).astype(real)
+    first = (np.arange(n_chains) * length)[:, None]
+    a2 = (first + np.arange(length - 1)[None, :]).ravel()
+    a3 = (first + np.arange(length - 2)[None, :]).ravel()
+    a4 = (first + np.arange(length - 3)[None, :]).ravel()
+    return r, a2, a3, a4
+
+
+DEVICE = "cuda"       # tests/test_md_host_emulation.py re-runs these bodies on "cpu" through a host shim
+
+
+def dev(x, real):
+    return torch.tensor(np.ascontiguousarray(x), dtype=torch.float64 if real == np.float64 else torch.float32,
+                        device=DEVICE)        # always a copy (as_tensor would alias x on the CPU dry run)
+
+
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_bonded_forces_match_oracle(real):
+    from hymd_b200 import force as F
+    rng = np.random.default_rng(31)
+    box = np.array([5.0, 6.0, 7.0])
+    r, a2, a3, a4 = chains(rng, 300, 11, box, real)     # 3300 particles: several CTAs, ragged tail
+    n = len(r)
+    r0, k2 = 0.47 + 0.1 * rng.random(len(a2)), 1250.0 * (0.5 + rng.random(len(a2)))
+    t0, k3 = np.radians(rng.choice([120.0, 180.0], size=len(a3))), 25.0 * (0.5 + rng.random(len(a3)))
+    coeff = np.zeros((len(a4), 6, 5))
+    coeff[:, 0] = rng.normal(size=(len(a4), 5)) * 4
+    coeff[:, 1] = rng.uniform(-np.pi, np.pi, size=(len(a4), 5))
+    coeff[1::3, 2] = rng.normal(size=coeff[1::3, 2].shape)
+    coeff[1::3, 3] = rng.normal(size=coeff[1::3, 3].shape)
+    dt4 = np.zeros(len(a4), dtype=np.int64)
+    dt4[::3] = 2
+    coeff[::3, 0, 0], coeff[::3, 0, 1] = 0.3, 40.0
+    pos = dev(r, real)
+
+    f = torch.full((n, 3), 7.0, dtype=pos.dtype, device=DEVICE)      # must be overwritten
+    e, pr = F.compute_bond_forces(f, pos, box, a2, a2 + 1, r0, k2)
+    fo_, eo, pro = bo.compute_bond_forces(r, box, a2, a2 + 1, r0, k2)
+    assert np.abs(f.cpu().numpy() - fo_).max() <= FTOL[real] * np.abs(fo_).max()
+    assert float(e) == pytest.approx(eo, rel=ETOL[real])
+    np.testing.assert_allclose(pr.cpu().numpy(), pro, rtol=0, atol=ETOL[real] * np.abs(pro).max())
+
+    f = torch.full((n, 3), 7.0, dtype=pos.dtype, device=DEVICE)
+    e, pr = F.compute_angle_forces(f, pos, box, a3, a3 + 1, a3 + 2, t0, k3)
+    fo_, eo, pro = bo.compute_angle_forces(r, box, a3, a3 + 1, a3 + 2, t0, k3)
+    assert np.abs(f.cpu().numpy() - fo_).max() <= FTOL[real] * np.abs(fo_).max()
+    assert float(e) == pytest.approx(eo, rel=ETOL[real])
+    np.testing.assert_allclose(pr.cpu().numpy(), pro, rtol=0, atol=ETOL[real] * np.abs(pro).max())
+
+    f = torch.full((n, 3), 7.0, dtype=pos.dtype, device=DEVICE)
+    e = F.compute_dihedral_forces(f, pos, None, None, box, a4, a4 + 1, a4 + 2, a4 + 3, coeff, dt4)
+    fo_, eo = bo.compute_dihedral_forces(r, box, a4, a4 + 1, a4 + 2, a4 + 3, coeff, dt4)
+    assert np.abs(f.cpu().numpy() - fo_).max() <= FTOL[real] * np.abs(fo_).max()
+    assert float(e) == pytest.approx(eo, rel=ETOL[real])
+
+
+def test_reference_kats_on_the_device_and_numpy_interface():
+    """test/test_force.py known answers (via the golden file) with numpy in / numpy out like the f2py
+    kernels; the dihedral sign is the production Fortran's (see tests/test_oracle_bonded.py)."""
+    from hymd_b200 import force as F
+    r, box = G["dppc/r"], G["dppc/box"]
+    a, b, r0, k = (G["dppc/b2_" + x] for x in ("a", "b", "r0", "k"))
+    f = np.zeros_like(r)
+    e, pr = F.compute_bond_forces(f, r, box, a, b, r0, k)
+    assert isinstance(e, float) and isinstance(pr, np.ndarray)
+    np.testing.assert_allclose(f, G["dppc/b2_force"], rtol=0, atol=1e-10)
+    assert e == pytest.approx(float(G["dppc/b2_energy"]), abs=1e-11)
+    a, b, c, t0, k = (G["dppc/b3_" + x] for x in ("a", "b", "c", "t0", "k"))
+    f = np.asfortranarray(np.zeros_like(r))           # main.py:500-506 hands Fortran-ordered arrays
+    e, pr = F.compute_angle_forces(f, np.asfortranarray(r), box, a, b, c, t0, k)
+    np.testing.assert_allclose(f, G["dppc/b3_force"], rtol=0, atol=1e-9)
+    assert e == pytest.approx(float(G["dppc/b3_energy"]), abs=1e-10)
+    r, box = G["ala/r"], G["ala/box"]
+    a, b, c, d, coeff, dt = (G["ala/" + x] for x in ("a", "b", "c", "d", "coeff", "dtype"))
+    f = np.zeros_like(r)
+    dip, tm = np.ones((5, 4, 3)), np.ones((5, 6, 3, 3))
+    e = F.compute_dihedral_forces(f, r, dip, tm, box, a, b, c, d, coeff, dt, np.zeros(5, dtype=int), 0)
+    np.testing.assert_allclose(f, -G["ala/term_force_plain"].sum(axis=0), rtol=0, atol=1e-10)
+    assert e == pytest.approx(float(G["ala/term_energy"].sum()), abs=1e-11)
+    assert not dip.any() and not tm.any()
+
+
+def test_bonded_edge_cases():
+    from hymd_b200 import _lib
+    from hymd_b200 import force as F
+    box = np.array([3.0, 3.0, 3.0])
+    pos = torch.rand((5, 3), dtype=torch.float64, device=DEVICE)
+    f = torch.ones_like(pos)
+    empty = np.zeros(0, dtype=np.int64)
+    e, pr = F.compute_bond_forces(f, pos, box, empty, empty, np.zeros(0), np.zeros(0))   # no terms: f = 0
+    assert float(e) == 0.0 and not f.any()
+    with pytest.raises(_lib.HymdError):          # index outside the local particles
+        F.compute_bond_forces(f, pos, box, np.array([0]), np.array([9]), np.array([0.4]), np.array([1.0]))
+    with pytest.raises(_lib.HymdError):          # dih_type 1 is not built
+        F.compute_dihedral_forces(f, pos, None, None, box, np.array([0]), np.array([1]), np.array([2]),
+                                  np.array([3]), np.zeros((1, 6, 5)), np.array([1]))
+    # bitwise reproducible
+    a = np.arange(4)
+    args = (box, a, a + 1, np.full(4, 0.4), np.full(4, 100.0))
+    f1, f2 = torch.empty_like(pos), torch.empty_like(pos)
+    e1, _ = F.compute_bond_forces(f1, pos, *args)
+    e2, _ = F.compute_bond_forces(f2, pos, *args)
+    assert torch.equal(f1, f2) and float(e1) == float(e2)
+
+
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_kick_drift_matches_numpy(real):
+    from hymd_b200.md import kick_drift
+    rng = np.random.default_rng(5)
+    n = 70001
+    box = np.array([3.0, 4.0, 5.0])
+    x = (rng.random((n, 3)) * box).astype(real)
+    v = rng.normal(scale=2.0, size=(n, 3)).astype(real)
+    fs = [rng.normal(scale=300.0, size=(n, 3)).astype(real) for _ in range(3)]
+    mass, dt = 72.0, 0.03
+    xd, vd, fd = dev(x, real), dev(v, real), [dev(f, real) for f in fs]
+    kick_drift(vd, xd, fd, mass, dt, dt, box)
+    v_ref = v + real(0.5 * dt) * ((fs[0] + fs[1] + fs[2]) / real(mass))
+    x_ref = np.mod(x + real(dt) * v_ref, box.astype(real)[None, :])
+    eps = np.finfo(real).eps
+    assert np.abs(vd.cpu().numpy() - v_ref).max() <= 2 * eps * np.abs(v_ref).max()   # FMA contraction only
+    xg = xd.cpu().numpy()
+    wrapdiff = np.abs(xg - x_ref)
+    wrapdiff = np.minimum(wrapdiff, np.abs(wrapdiff - box.astype(real)[None, :]))
+    assert wrapdiff.max() <= 8 * eps * box.max()
+    assert (xg >= 0).all() and (xg < box.astype(real)).all()
+    vd2 = dev(v, real)
+    kick_drift(vd2, None, fd[:2], mass, 5 * dt, sequential=True)
+    v_ref = v + real(0.5 * 5 * dt) * (fs[0] / real(mass))
+    v_ref = v_ref + real(0.5 * 5 * dt) * (fs[1] / real(mass))
+    assert np.abs(vd2.cpu().numpy() - v_ref).max() <= 2 * eps * np.abs(v_ref).max()
+
+
+class _Cfg:
+    gas_constant = 0.0083144621
+
+    def __init__(self, names, groups, params, n_particles):
+        self.mass, _, self.target_temperature, self.time_step, inner, self.tau = [float(x) for x in params]
+        self.respa_inner = int(inner)
+        self.gas_constant = float(params[1])
+        self.unique_names = sorted({n.decode() for n in names})
+        self.name_to_type_map = {n: i for i, n in enumerate(self.unique_names)}
+        self.thermostat_coupling_groups = [list(g) for g in groups]
+        self.thermostat_work = 0.0
+        self.n_particles = n_particles
+
+
+class _Mock:
+    def __init__(self, x):
+        self.x, self.i = list(x), 0
+
+    def __call__(self, *args):
+        self.i += 1
+        return self.x[self.i - 1]
+
+
+@pytest.mark.parametrize("remove", [False, True])
+@pytest.mark.parametrize("case,groups", [("all", []), ("abcd", [["A"], ["B"], ["C"], ["D"]]),
+                                         ("abc_d", [["A", "B", "C"], ["D"]])])
+def test_csvr_matches_reference_golden(case, groups, remove):
+    """The reference's own csvr_thermostat outputs (test/test_thermostat.py fixture and draws)."""
+    from hymd_b200 import thermostat as T
+    pre = f"mws/{case}_{'com' if remove else 'nocom'}"
+    names = TG["mws/names"]
+    cfg = _Cfg(names, groups, TG["mws/params"], len(names))
+    v = dev(TG["mws/velocities"], np.float64)
+    T.csvr_thermostat(v, names, cfg, None, random_gaussian=_Mock(TG[pre + "/gauss"]),
+                      random_chi_squared=_Mock(TG[pre + "/chi2"]), remove_center_of_mass_momentum=remove)
+    np.testing.assert_allclose(v.cpu().numpy(), TG[pre + "/v"], rtol=1e-11, atol=1e-13)
+    assert float(cfg.thermostat_work) == pytest.approx(float(TG[pre + "/work"]), abs=1e-10)
+
+
+def test_csvr_larger_system_numpy_interface_and_cancel_com():
+    from hymd_b200 import thermostat as T
+    names = TG["rand/names"]
+    cfg = _Cfg(names, [["A", "B"], ["W"]], TG["rand/params"], len(names))
+    v = TG["rand/v0"].copy()
+    T.csvr_thermostat(v, names, cfg, None, random_gaussian=_Mock(TG["rand/gauss"]),
+                      random_chi_squared=_Mock(TG["rand/chi2"]))
+    np.testing.assert_allclose(v, TG["rand/v"], rtol=1e-11, atol=1e-13)
+    assert isinstance(cfg.thermostat_work, float)
+    assert cfg.thermostat_work == pytest.approx(float(TG["rand/work"]), rel=1e-10)
+    # float32 velocities, type ids instead of names
+    cfg = _Cfg(names, [["A", "B"], ["W"]], TG["rand/params"], len(names))
+    types = torch.as_tensor(np.array([cfg.name_to_type_map[n.decode()] for n in names], dtype=np.int32), device=DEVICE)
+    v32 = dev(TG["rand/v0"], np.float32)
+    T.csvr_thermostat(v32, types, cfg, None, random_gaussian=_Mock(TG["rand/gauss"]),
+                      random_chi_squared=_Mock(TG["rand/chi2"]))
+    ref = TG["rand/v0"].astype(np.float32).astype(np.float64)
+    grp = np.where(names == b"W", 1, 0).astype(np.int32)
+    mass, gas, T0, dt, inner, tau = TG["rand/params"]
+    to.csvr_thermostat(ref, grp, 2, mass=mass, gas_constant=gas, target_temperature=T0, time_step=dt,
+                       respa_inner=int(inner), tau=tau, draws=list(zip(TG["rand/gauss"], TG["rand/chi2"])))
+    assert np.abs(v32.cpu().numpy() - ref).max() <= 2e-7 * np.abs(ref).max()
+    # cancel_com_momentum (thermostat.py:12-15)
+    cfg = _Cfg(TG["mws/names"], [], TG["mws/params"], len(TG["mws/names"]))
+    v = dev(TG["mws/velocities"], np.float64)
+    T.cancel_com_momentum(v, cfg)
+    np.testing.assert_allclose(v.cpu().numpy(), TG["mws/cancel_com"], rtol=1e-13, atol=1e-15)
+    assert float(T.kinetic_energy(dev(TG["mws/velocities"], np.float64), 72.0)) == pytest.approx(
+        168.45555165866017, abs=1e-11)                     # test_thermostat.py:74
+
+
+def test_respa_md_with_bonds_conserves_energy_like_the_oracle():
+    """A short NVE run of bonded chains (no field forces: the slow-force callback returns nothing):
+    the device rRESPA step and a float64 numpy velocity-Verlet driven by the bonded oracle follow the
+    same trajectory, and bonded + kinetic energy is conserved."""
+    from hymd_b200.force import BondedTopology
+    from hymd_b200.md import RespaMD
+    rng = np.random.default_rng(9)
+    box = np.array([4.0, 4.0, 4.0])
+    r, a2, a3, _ = chains(rng, 40, 8, box, np.float64)
+    n = len(r)
+    r0, k2 = np.full(len(a2), 0.47), np.full(len(a2), 1250.0)
+    t0, k3 = np.full(len(a3), np.radians(120.0)), np.full(len(a3), 25.0)
+    v = rng.normal(scale=0.15, size=(n, 3))
+    mass, dt, inner, steps = 72.0, 0.005, 4, 25
+
+    def oracle_forces(x):
+        fb, eb, _ = bo.compute_bond_forces(x, box, a2, a2 + 1, r0, k2)
+        fa, ea, _ = bo.compute_angle_forces(x, box, a3, a3 + 1, a3 + 2, t0, k3)
+        return fb + fa, eb + ea
+    xo, vo = r.copy(), v.copy()
+    fo_, e_pot = oracle_forces(xo)
+    e0 = e_pot + 0.5 * mass * np.sum(vo ** 2)
+    for _ in range(steps * inner):
+        vo = vo + 0.5 * dt * (fo_ / mass)
+        xo = np.mod(xo + dt * vo, box[None, :])
+        fo_, e_pot = oracle_forces(xo)
+        vo = vo + 0.5 * dt * (fo_ / mass)
+    e1 = e_pot + 0.5 * mass * np.sum(vo ** 2)
+    assert abs(e1 - e0) < 2e-3 * abs(e0)
+
+    topo = BondedTopology(n, bonds=(a2, a2 + 1, r0, k2), angles=(a3, a3 + 1, a3 + 2, t0, k3))
+    md = RespaMD(lambda x: [], box, mass, dt, respa_inner=inner, topology=topo)
+    xd, vd = dev(r, np.float64), dev(v, np.float64)
+    slow = []
+    for _ in range(steps):
+        slow = md.step(xd, vd, slow)
+    d = np.abs(xd.cpu().numpy() - xo)
+    d = np.minimum(d, np.abs(d - box[None, :]))
+    assert d.max() < 1e-9
+    assert np.abs(vd.cpu().numpy() - vo).max() < 1e-9
+    en = md.bonded_energies()
+    assert en[2] + en[3] == pytest.approx(e_pot, rel=1e-9)

@@ -53,6 +53,63 @@ __global__ void __launch_bounds__(BONDED_THREADS) bonded_kernel(
     }
 }
 
+struct ForceOut {
+    void* f[3];
+};
+
+// Fused inner rRESPA step: bonded forces of all kinds + velocity kick(s) + drift/wrap in one pass
+// (48 B per particle of HBM traffic in fp32 instead of 176 B for the four separate launches; the
+// per-kind force arrays are only written on request).
+template <typename real>
+__global__ void __launch_bounds__(BONDED_THREADS) inner_step_kernel(
+    const real* __restrict__ x_in, real* __restrict__ x_out, real* __restrict__ vel, long long n, Vec3d box,
+    TermLists t, real mass, real half_dt, int n_kicks, real dt, ForceOut fo, double* __restrict__ partial) {
+    const long long p = (long long)blockIdx.x * BONDED_THREADS + threadIdx.x;
+    BondAcc acc[3];
+    double v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = 0.0;
+    if (p < n) {
+        real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
+        inner_step_particle<real>(p, x_in, x_out, vel, box, t, mass, half_dt, n_kicks, dt, f_out, acc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[4 * k] = acc[k].e; v[4 * k + 1] = acc[k].pr.x; v[4 * k + 2] = acc[k].pr.y; v[4 * k + 3] = acc[k].pr.z;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    __shared__ double sh[BONDED_THREADS / 32][12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 12; ++k) sh[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < BONDED_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
+        partial[12 * (long long)blockIdx.x + threadIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) inner_final_kernel(const double* __restrict__ partial, int nblocks,
+                                                          double* __restrict__ out) {
+    __shared__ double sh[12][256];
+    double acc[12];
+    for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 256)
+        for (int k = 0; k < 12; ++k) acc[k] += partial[12 * (long long)i + k];
+    for (int k = 0; k < 12; ++k) sh[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w)
+            for (int k = 0; k < 12; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x < 12) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+
 __global__ void __launch_bounds__(256) bonded_final_kernel(const double* __restrict__ partial, int nblocks,
                                                            double* __restrict__ out) {
     __shared__ double sh[4][256];
@@ -118,6 +175,33 @@ static int launch_kind(hymd_bonded* b, int kind, const real* pos, Vec3d box, rea
     return HYMD_OK;
 }
 
+template <typename real>
+static int launch_inner(hymd_bonded* b, const real* x_in, real* x_out, real* vel, Vec3d box, double mass,
+                        double kick_dt, int n_kicks, double drift_dt, void* const* d_force_out, double* d_out,
+                        cudaStream_t s) {
+    const long long n = b->n_particles;
+    const int blocks = (int)((n + BONDED_THREADS - 1) / BONDED_THREADS);
+    TermLists t;
+    for (int k = 0; k < 3; ++k) {
+        t.start[k] = b->start[k]; t.refs[k] = b->refs[k]; t.idx[k] = b->idx[k]; t.par[k] = b->par[k];
+        t.n_terms[k] = b->n_terms[k];
+    }
+    t.dih_type = b->dih_type;
+    ForceOut fo;
+    for (int k = 0; k < 3; ++k) fo.f[k] = d_force_out ? d_force_out[k] : nullptr;
+    if (blocks > 0) {
+        inner_step_kernel<real><<<blocks, BONDED_THREADS, 0, s>>>(x_in, x_out, vel, n, box, t, (real)mass,
+                                                                  (real)(0.5 * kick_dt), n_kicks,
+                                                                  (real)drift_dt, fo, b->partial);
+        HYMD_LAUNCH_CHECK(b);
+    }
+    if (d_out) {
+        inner_final_kernel<<<1, 256, 0, s>>>(b->partial, blocks, d_out);
+        HYMD_LAUNCH_CHECK(b);
+    }
+    return HYMD_OK;
+}
+
 }  // namespace hymd
 
 using namespace hymd;
@@ -164,7 +248,7 @@ int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const
     if (st == HYMD_OK) st = to_device(&b->dih_type, type4, (size_t)n4);
     if (st == HYMD_OK) {
         b->max_blocks = (int)((n_particles + BONDED_THREADS - 1) / BONDED_THREADS);
-        cudaError_t e = cudaMalloc((void**)&b->partial, sizeof(double) * 4 * (size_t)(b->max_blocks + 1));
+        cudaError_t e = cudaMalloc((void**)&b->partial, sizeof(double) * 12 * (size_t)(b->max_blocks + 1));
         if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); st = HYMD_ERR_NOMEM; }
     }
     if (st != HYMD_OK) { hymd_bonded_destroy(b); return st; }
@@ -199,6 +283,25 @@ int hymd_bonded_forces(hymd_bonded* b, int kind, int dtype, const void* d_pos, c
     if (dtype == HYMD_F64)
         return launch_kind<double>(b, kind - 2, (const double*)d_pos, bx, (double*)d_force, d_out, s);
     return launch_kind<float>(b, kind - 2, (const float*)d_pos, bx, (float*)d_force, d_out, s);
+}
+
+int hymd_bonded_inner_step(hymd_bonded* b, int dtype, const void* d_pos_in, void* d_pos_out, void* d_vel,
+                           const double box[3], double mass, double kick_dt, int n_kicks, double drift_dt,
+                           void* const* d_force_out, double* d_out, void* stream) {
+    if (!b || !box || (b->n_particles > 0 && (!d_pos_in || !d_vel))) {
+        set_error("hymd_bonded_inner_step: null argument");
+        return HYMD_ERR_INVALID;
+    }
+    if (n_kicks < 0 || n_kicks > 2) { set_error("n_kicks = %d, expected 0, 1 or 2", n_kicks); return HYMD_ERR_INVALID; }
+    if (d_pos_out == d_pos_in) { set_error("hymd_bonded_inner_step: d_pos_out must not alias d_pos_in"); return HYMD_ERR_INVALID; }
+    if (dtype != HYMD_F32 && dtype != HYMD_F64) { set_error("bad dtype %d", dtype); return HYMD_ERR_INVALID; }
+    const Vec3d bx = {box[0], box[1], box[2]};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == HYMD_F64)
+        return launch_inner<double>(b, (const double*)d_pos_in, (double*)d_pos_out, (double*)d_vel, bx, mass,
+                                    kick_dt, n_kicks, drift_dt, d_force_out, d_out, s);
+    return launch_inner<float>(b, (const float*)d_pos_in, (float*)d_pos_out, (float*)d_vel, bx, mass, kick_dt,
+                               n_kicks, drift_dt, d_force_out, d_out, s);
 }
 
 int64_t hymd_bonded_launch_count(hymd_bonded* b) { return b ? b->launches : 0; }

@@ -25,6 +25,8 @@
 
 #include <vector>
 
+#include "md.cuh"
+
 #ifndef __CUDACC__
 #define __host__
 #define __device__
@@ -211,6 +213,47 @@ __host__ __device__ inline BondAcc particle_terms(long long p, const real* __res
                           dtype[t], slot, acc);
     }
     return acc;
+}
+
+// All three kinds of one rank's molecules (device or host pointers).
+struct TermLists {
+    const uint32_t* start[3];
+    const uint32_t* refs[3];
+    const int32_t* idx[3];
+    const double* par[3];
+    const int32_t* dih_type;
+    long long n_terms[3];
+};
+
+// One particle's share of a fused inner rRESPA step (main.py:829-893):
+//   F = bonded forces at x_in (each kind rounded to the array type like the Fortran's f arrays),
+//   n_kicks x  v += half_dt * (f_bond + f_angle + f_dihedral) / mass   (closing kick of the previous
+//              inner step and opening kick of the next one: same forces, two roundings like the
+//              reference's two integrate_velocity calls),
+//   x_out = mod(x_in + dt * v, box)   if x_out != nullptr (double-buffered: other threads still read x_in).
+// acc[k] returns the energy / pressure by-products of the terms this particle owns.
+template <typename real>
+__host__ __device__ inline void inner_step_particle(long long p, const real* __restrict__ x_in,
+                                                    real* __restrict__ x_out, real* __restrict__ vel,
+                                                    Vec3d box, const TermLists& t, real mass, real half_dt,
+                                                    int n_kicks, real dt, real* const* f_out, BondAcc* acc) {
+    const BondAcc zero = {{0.0, 0.0, 0.0}, 0.0, {0.0, 0.0, 0.0}};
+    acc[0] = t.n_terms[0] ? particle_terms<real, 2>(p, x_in, box, t.start[0], t.refs[0], t.idx[0], t.par[0], nullptr) : zero;
+    acc[1] = t.n_terms[1] ? particle_terms<real, 3>(p, x_in, box, t.start[1], t.refs[1], t.idx[1], t.par[1], nullptr) : zero;
+    acc[2] = t.n_terms[2] ? particle_terms<real, 4>(p, x_in, box, t.start[2], t.refs[2], t.idx[2], t.par[2], t.dih_type) : zero;
+    const real L[3] = {(real)box.x, (real)box.y, (real)box.z};
+    for (int d = 0; d < 3; ++d) {
+        real ft[3];
+        for (int k = 0; k < 3; ++k) {
+            const double fk = d == 0 ? acc[k].f.x : (d == 1 ? acc[k].f.y : acc[k].f.z);
+            ft[k] = (real)fk;
+            if (f_out != nullptr && f_out[k] != nullptr) f_out[k][3 * p + d] = ft[k];
+        }
+        real v = vel[3 * p + d];
+        for (int r = 0; r < n_kicks; ++r) v = kick(v, ft, 3, mass, half_dt);
+        if (n_kicks > 0) vel[3 * p + d] = v;
+        if (x_out != nullptr) x_out[3 * p + d] = drift_wrap(x_in[3 * p + d], v, dt, L[d]);
+    }
 }
 
 }  // namespace hymd

@@ -89,6 +89,7 @@ class BondedTopology:
                 ip(keep[14]), ctypes.byref(handle)))
         self._h = handle
         self._out = torch.zeros((3, 4), dtype=torch.float64, device=self.device)
+        self._out12 = torch.zeros((3, 4), dtype=torch.float64, device=self.device)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -119,6 +120,35 @@ class BondedTopology:
             self._h, int(kind), _lib.F64 if positions.dtype == torch.float64 else _lib.F32,
             ctypes.c_void_p(positions.data_ptr()), box, ctypes.c_void_p(out.data_ptr()),
             ctypes.cast(ctypes.c_void_p(res.data_ptr()), _F64P), stream))
+        return res
+
+
+    def inner_step(self, x_in, x_out, vel, box_size, mass, kick_dt, n_kicks, drift_dt, force_out=None,
+                   want_energies=True):
+        """One fused inner rRESPA step (``hymd_bonded_inner_step``): bonded forces at ``x_in``,
+        ``n_kicks`` half kicks of ``vel`` (in place) and, if ``x_out`` is given (a different tensor),
+        ``x_out = mod(x_in + drift_dt*vel, box)``.  ``force_out`` = optional 3-list of (n,3) tensors
+        (bond, angle, dihedral; entries may be None).  Returns the (3,4) float64 device tensor
+        {energy, pr_x, pr_y, pr_z} per kind (aliases an internal buffer) or None."""
+        n = self.n_particles
+        tensors = [x_in, vel] + ([x_out] if x_out is not None else []) + \
+            [f for f in (force_out or []) if f is not None]
+        for t in tensors:
+            if tuple(t.shape) != (n, 3) or t.dtype != x_in.dtype or not t.is_contiguous():
+                raise ValueError(f"inner_step needs contiguous ({n}, 3) tensors of one dtype")
+        if x_in.dtype not in (torch.float32, torch.float64):
+            raise ValueError("positions must be float32 or float64")
+        box = (ctypes.c_double * 3)(*[float(b) for b in np.asarray(box_size).reshape(-1)[:3]])
+        fptr = None
+        if force_out is not None:
+            fptr = (ctypes.c_void_p * 3)(*[f.data_ptr() if f is not None else None for f in force_out])
+        res = self._out12 if want_energies else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.hymd_bonded_inner_step(
+            self._h, _lib.F64 if x_in.dtype == torch.float64 else _lib.F32,
+            ctypes.c_void_p(x_in.data_ptr()), ctypes.c_void_p(x_out.data_ptr()) if x_out is not None else None,
+            ctypes.c_void_p(vel.data_ptr()), box, float(mass), float(kick_dt), int(n_kicks), float(drift_dt),
+            fptr, ctypes.cast(ctypes.c_void_p(res.data_ptr()), _F64P) if res is not None else None, stream))
         return res
 
 

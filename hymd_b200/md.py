@@ -108,7 +108,7 @@ class RespaMD:
     callable ``(velocities) -> None`` applied every ``n_b`` outer steps (``main.py:1290-1292``)."""
 
     def __init__(self, field_force_fn, box, mass, time_step, respa_inner=1, topology=None,
-                 thermostat=None, n_b=1):
+                 thermostat=None, n_b=1, fused=True, force_out=None):
         self.field_force_fn = field_force_fn
         self.box = box
         self.mass = float(mass)
@@ -120,6 +120,9 @@ class RespaMD:
         self.step_count = 0
         self.fast = None
         self.bonded_results = {}
+        self.fused = bool(fused)
+        self.force_out = force_out      # optional [bond, angle, dihedral] (N,3) tensors filled at the
+        self._x_alt = None              # end of every outer step by the fused path
 
     def fast_forces(self, positions):
         """Bond / angle / dihedral forces at ``positions`` (``main.py:841-887``): list of tensors."""
@@ -140,17 +143,43 @@ class RespaMD:
         return {k: float(v[0].item()) for k, v in self.bonded_results.items()}
 
     def step(self, positions, velocities, slow_forces):
-        """From ``(x, v, slow forces at x)`` to the next outer step; returns the new slow forces."""
+        """From ``(x, v, slow forces at x)`` to the next outer step, in place; returns the new slow
+        forces.  With a topology the inner loop is ``respa_inner + 1`` launches of the fused kernel
+        ``hymd_bonded_inner_step`` (forces + kick(s) + drift in one pass, positions double-buffered);
+        ``fused=False`` (or no topology) runs the four separate launches per inner step."""
         outer = self.inner * self.dt
         kick_drift(velocities, None, slow_forces, self.mass, outer, sequential=True)     # main.py:803-827
-        fast = self.fast_forces(positions) if self.fast is None else [f for f in self.fast if f is not None]
-        for _ in range(self.inner):                                                      # main.py:829-893
-            kick_drift(velocities, positions, fast, self.mass, self.dt, self.dt, self.box)
-            fast = self.fast_forces(positions)
-            kick_drift(velocities, None, fast, self.mass, self.dt)
+        if self.topology is not None and self.fused:
+            self._fused_inner(positions, velocities)
+        else:
+            fast = self.fast_forces(positions) if self.fast is None else [f for f in self.fast if f is not None]
+            for _ in range(self.inner):                                                  # main.py:829-893
+                kick_drift(velocities, positions, fast, self.mass, self.dt, self.dt, self.box)
+                fast = self.fast_forces(positions)
+                kick_drift(velocities, None, fast, self.mass, self.dt)
         slow_forces = self.field_force_fn(positions)                                     # main.py:976-1058
         kick_drift(velocities, None, slow_forces, self.mass, outer, sequential=True)     # main.py:1144-1169
         self.step_count += 1
         if self.thermostat is not None and self.step_count % self.n_b == 0:             # main.py:1290-1292
             self.thermostat(velocities)
         return slow_forces
+
+    def _fused_inner(self, positions, velocities):
+        """k d F k | k d F k | ... regrouped as [F k d] [F k k d] ... [F k]: the bonded forces at the
+        current positions are evaluated inside the kernel that consumes them (the first launch
+        re-evaluates the forces of the previous outer step's last positions instead of storing
+        them), so no force array goes through HBM."""
+        import torch
+        topo = self.topology
+        if self._x_alt is None or self._x_alt.shape != positions.shape or self._x_alt.dtype != positions.dtype:
+            self._x_alt = torch.empty_like(positions)
+        cur, alt = positions, self._x_alt
+        for i in range(self.inner):
+            topo.inner_step(cur, alt, velocities, self.box, self.mass, self.dt, 1 if i == 0 else 2, self.dt,
+                            want_energies=False)
+            cur, alt = alt, cur
+        res = topo.inner_step(cur, None, velocities, self.box, self.mass, self.dt, 1, 0.0,
+                              force_out=self.force_out, want_energies=True)
+        self.bonded_results = {k + 2: res[k] for k in range(3) if topo.n_terms[k] > 0}
+        if cur is not positions:
+            positions.copy_(cur)

@@ -248,6 +248,20 @@ int hymd_bonded_forces(hymd_bonded* b, int kind, int dtype, const void* d_pos, c
                        void* d_force, double* d_out, void* stream);
 int64_t hymd_bonded_launch_count(hymd_bonded* b);
 
+/* One fused inner rRESPA step (main.py:829-893) in a single pass over the particles:
+ *   F = bond + angle + dihedral forces at d_pos_in (every kind rounded to `dtype` like the f arrays),
+ *   n_kicks (0, 1 or 2) times  v += 0.5*kick_dt * F / mass   -- the closing kick of the previous inner
+ *   step and the opening kick of the next one use the same forces and stay two separate roundings --
+ *   then, if d_pos_out != NULL,  d_pos_out = mod(d_pos_in + drift_dt * v, box)  (a different buffer:
+ *   neighbours still read d_pos_in).
+ * An inner loop of r steps is r+1 launches: (1 kick, drift), r-1 x (2 kicks, drift), (1 kick, no drift).
+ * d_force_out: NULL or HOST array of 3 device pointers (bond, angle, dihedral forces; entries may be
+ * NULL) for callers that want the per-kind arrays; d_out: NULL or DEVICE array of 12 doubles =
+ * {energy, pr_x, pr_y, pr_z} x {bonds, angles, dihedrals} at d_pos_in. */
+int hymd_bonded_inner_step(hymd_bonded* b, int dtype, const void* d_pos_in, void* d_pos_out, void* d_vel,
+                           const double box[3], double mass, double kick_dt, int n_kicks, double drift_dt,
+                           void* const* d_force_out, double* d_out, void* stream);
+
 /* integrate_velocity / integrate_position (hymd/integrator.py:9-75) fused over the arrays:
  *   sequential == 0:  v += 0.5*kick_dt * (f_0 + ... + f_{n_forces-1}) / mass      (main.py:830-834, 889-893)
  *   sequential == 1:  v += 0.5*kick_dt * f_k / mass  for k = 0, 1, ... in turn    (main.py:803-827, 1144-1169)

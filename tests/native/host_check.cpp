@@ -210,3 +210,39 @@ extern "C" int hymd_cancel_com(int dtype, void* vel, int64_t n, const double* mo
     }
     return 0;
 }
+
+template <typename real>
+static void inner(HostBonded* b, const real* x_in, real* x_out, real* vel, Vec3d box, double mass, double kick_dt,
+                  int n_kicks, double drift_dt, void* const* f_out, double* out12) {
+    TermLists t;
+    for (int k = 0; k < 3; ++k) {
+        t.start[k] = b->start[k].data(); t.refs[k] = b->refs[k].data(); t.idx[k] = b->idx[k].data();
+        t.par[k] = b->par[k].data(); t.n_terms[k] = (long long)(b->idx[k].size() / 4);
+    }
+    t.dih_type = b->dtype.data();
+    real* fo[3] = {f_out ? (real*)f_out[0] : nullptr, f_out ? (real*)f_out[1] : nullptr,
+                   f_out ? (real*)f_out[2] : nullptr};
+    double acc12[12] = {0};
+    for (long long p = 0; p < b->n; ++p) {
+        BondAcc acc[3];
+        inner_step_particle<real>(p, x_in, x_out, vel, box, t, (real)mass, (real)(0.5 * kick_dt), n_kicks,
+                                  (real)drift_dt, fo, acc);
+        for (int k = 0; k < 3; ++k) {
+            acc12[4 * k] += acc[k].e; acc12[4 * k + 1] += acc[k].pr.x; acc12[4 * k + 2] += acc[k].pr.y;
+            acc12[4 * k + 3] += acc[k].pr.z;
+        }
+    }
+    if (out12) for (int k = 0; k < 12; ++k) out12[k] = acc12[k];
+}
+
+extern "C" int hymd_bonded_inner_step(void* h, int dtype, const void* x_in, void* x_out, void* vel,
+                                      const double* box, double mass, double kick_dt, int n_kicks,
+                                      double drift_dt, void* const* f_out, double* out12, void* stream) {
+    HostBonded* b = (HostBonded*)h;
+    if (n_kicks < 0 || n_kicks > 2 || x_in == x_out) return -1;
+    const Vec3d bx = {box[0], box[1], box[2]};
+    b->launches += out12 ? 2 : 1;
+    if (dtype == 1) inner<double>(b, (const double*)x_in, (double*)x_out, (double*)vel, bx, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
+    else inner<float>(b, (const float*)x_in, (float*)x_out, (float*)vel, bx, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
+    return 0;
+}

@@ -19,7 +19,7 @@ import pytest
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-F2 = ["hymd_bonded_create", "hymd_bonded_destroy", "hymd_bonded_forces", "hymd_bonded_launch_count",
+F2 = ["hymd_bonded_inner_step", "hymd_bonded_create", "hymd_bonded_destroy", "hymd_bonded_forces", "hymd_bonded_launch_count",
       "hymd_md_kick_drift", "hymd_velocity_moments", "hymd_velocity_moments_scratch_doubles",
       "hymd_csvr_apply", "hymd_cancel_com"]
 
@@ -83,4 +83,10 @@ def test_csvr(emulated, case, groups, remove):
 
 def test_csvr_interfaces_and_md(emulated):
     emulated.test_csvr_larger_system_numpy_interface_and_cancel_com()
-    emulated.test_respa_md_with_bonds_conserves_energy_like_the_oracle()
+    emulated.test_respa_md_with_bonds_conserves_energy_like_the_oracle(True)
+    emulated.test_respa_md_with_bonds_conserves_energy_like_the_oracle(False)
+
+
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_fused_inner_step(emulated, real):
+    emulated.test_fused_inner_step_equals_separate_launches(real)

@@ -232,7 +232,8 @@ def test_csvr_larger_system_numpy_interface_and_cancel_com():
         168.45555165866017, abs=1e-11)                     # test_thermostat.py:74
 
 
-def test_respa_md_with_bonds_conserves_energy_like_the_oracle():
+@pytest.mark.parametrize("fused", [True, False])
+def test_respa_md_with_bonds_conserves_energy_like_the_oracle(fused):
     """A short NVE run of bonded chains (no field forces: the slow-force callback returns nothing):
     the device rRESPA step and a float64 numpy velocity-Verlet driven by the bonded oracle follow the
     same trajectory, and bonded + kinetic energy is conserved."""
@@ -263,7 +264,9 @@ def test_respa_md_with_bonds_conserves_energy_like_the_oracle():
     assert abs(e1 - e0) < 2e-3 * abs(e0)
 
     topo = BondedTopology(n, bonds=(a2, a2 + 1, r0, k2), angles=(a3, a3 + 1, a3 + 2, t0, k3))
-    md = RespaMD(lambda x: [], box, mass, dt, respa_inner=inner, topology=topo)
+    fout = [torch.zeros((n, 3), dtype=torch.float64, device=DEVICE) for _ in range(2)] + [None]
+    md = RespaMD(lambda x: [], box, mass, dt, respa_inner=inner, topology=topo, fused=fused,
+                 force_out=fout if fused else None)
     xd, vd = dev(r, np.float64), dev(v, np.float64)
     slow = []
     for _ in range(steps):
@@ -274,3 +277,42 @@ def test_respa_md_with_bonds_conserves_energy_like_the_oracle():
     assert np.abs(vd.cpu().numpy() - vo).max() < 1e-9
     en = md.bonded_energies()
     assert en[2] + en[3] == pytest.approx(e_pot, rel=1e-9)
+    if fused:       # per-kind force arrays of the last positions, on request
+        assert np.abs((fout[0] + fout[1]).cpu().numpy() - fo_).max() < 1e-7 * np.abs(fo_).max()
+
+
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_fused_inner_step_equals_separate_launches(real):
+    """hymd_bonded_inner_step (forces + kicks + drift in one pass) against the four separate launches
+    per inner step on the same inputs, all three kinds present, odd respa_inner (result lands in the
+    alternate position buffer and is copied back)."""
+    from hymd_b200.force import BondedTopology
+    from hymd_b200.md import RespaMD
+    rng = np.random.default_rng(12)
+    box = np.array([4.0, 5.0, 4.5])
+    r, a2, a3, a4 = chains(rng, 150, 9, box, real)
+    n = len(r)
+    coeff = np.zeros((len(a4), 6, 5))
+    coeff[:, 0] = rng.normal(size=(len(a4), 5))
+    coeff[:, 1] = rng.uniform(-np.pi, np.pi, size=(len(a4), 5))
+    topo = BondedTopology(n, bonds=(a2, a2 + 1, np.full(len(a2), 0.47), np.full(len(a2), 1250.0)),
+                          angles=(a3, a3 + 1, a3 + 2, np.full(len(a3), 2.0), np.full(len(a3), 25.0)),
+                          dihedrals=(a4, a4 + 1, a4 + 2, a4 + 3, coeff, np.zeros(len(a4), dtype=int)),
+                          device=DEVICE if DEVICE != "cuda" else None)
+    v = rng.normal(scale=0.15, size=(n, 3)).astype(real)
+    slow = dev(rng.normal(scale=50.0, size=(n, 3)), real)
+    out = {}
+    for fused in (True, False):
+        md = RespaMD(lambda x: [slow], box, 72.0, 0.004, respa_inner=3, topology=topo, fused=fused)
+        xd, vd = dev(r, real), dev(v, real)
+        f = [slow]
+        for _ in range(4):
+            f = md.step(xd, vd, f)
+        out[fused] = (xd.cpu().numpy().astype(np.float64), vd.cpu().numpy().astype(np.float64), md.bonded_energies())
+    eps = np.finfo(real).eps
+    d = np.abs(out[True][0] - out[False][0])
+    d = np.minimum(d, np.abs(d - box[None, :]))
+    assert d.max() <= 64 * eps * box.max()
+    assert np.abs(out[True][1] - out[False][1]).max() <= 64 * eps * np.abs(out[False][1]).max()
+    for k in (2, 3, 4):
+        assert out[True][2][k] == pytest.approx(out[False][2][k], rel=1e-6 if real == np.float32 else 1e-11)

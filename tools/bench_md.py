@@ -103,6 +103,9 @@ def main():
     prng = np.random.default_rng(3)
     ms = timed(lambda: T.csvr_thermostat(v3, grp, cfg, prng), max(args.iters // 4, 3))
     line("csvr_2groups", ms, 2 * n * (12 + 24 + 8))
+    x3, x4, v4 = x.clone(), torch.empty_like(x), v.clone()
+    ms = timed(lambda: topo.inner_step(x3, x4, v4, box, 72.0, 0.01, 2, 0.0, want_energies=False), args.iters)
+    line("fused_inner_step", ms, n * 12 * 4 + len(a2) * 40 + len(a3) * 44 + n * 8)
     inner = res["kick_drift_2forces"]["ms"] + res["bonds"]["ms"] + res["angles"]["ms"] + res["kick_2forces"]["ms"]
     res["inner_rrespa_step_ms"] = inner
     res["launches_topology"] = topo.launch_count()

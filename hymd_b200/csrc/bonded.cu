@@ -2,6 +2,8 @@
 // Replaces the f2py kernels cbf / caf / cdf (hymd/compute_bond_forces.f90, compute_angle_forces.f90,
 // compute_dihedral_forces.f90) that main.py:841-887 calls respa_inner times per outer step.
 // The arithmetic lives in bonded.cuh (shared with the CPU check of tests/native/).
+#include <stdlib.h>
+
 #include "bonded.cuh"
 #include "ctx.cuh"
 
@@ -13,6 +15,13 @@ struct hymd_bonded {
     int32_t* idx[3];             // [n_terms][4]
     double* par[3];              // [n_terms][2] / [n_terms][30]
     int32_t* dih_type;           // [n4]
+    uint32_t* cta_start[3];      // CTA-cooperative evaluation (bonded.cuh, CtaLists)
+    uint32_t* cta_terms[3];
+    uint32_t* lrefs[3];
+    int max_terms[3];
+    size_t cta_smem;             // dynamic shared memory of inner_step_cta_kernel
+    int use_cta;                 // HYMD_B200_BONDED_CTA / hymd_bonded_set_cta
+    double* out12;               // scratch result of the fused kernels
     double* partial;             // [max_blocks][4] block partials of {energy, pr_x, pr_y, pr_z}
     int max_blocks;
     int64_t launches;
@@ -93,6 +102,45 @@ __global__ void __launch_bounds__(BONDED_THREADS) inner_step_kernel(
     }
 }
 
+// Same step, CTA-cooperative term evaluation (bonded.cuh): every term touching the CTA's 128
+// particles is evaluated once into shared memory, then each particle gathers its slots.
+template <typename real>
+__global__ void __launch_bounds__(BONDED_THREADS) inner_step_cta_kernel(
+    const real* __restrict__ x_in, real* __restrict__ x_out, real* __restrict__ vel, long long n, Vec3d box,
+    TermLists t, CtaLists c, real mass, real half_dt, int n_kicks, real dt, ForceOut fo,
+    double* __restrict__ partial) {
+    extern __shared__ double sm[];
+    const long long cta = blockIdx.x;
+    const long long p0 = cta * BONDED_THREADS;
+    const long long p1 = p0 + BONDED_THREADS < n ? p0 + BONDED_THREADS : n;
+    double v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = 0.0;
+    cta_eval_terms<real>((int)threadIdx.x, BONDED_THREADS, cta, p0, p1, x_in, box, t, c, sm, v);
+    __syncthreads();
+    const long long p = p0 + threadIdx.x;
+    if (p < n) {
+        BondAcc acc[3];
+        cta_gather_particle(p, t, c, sm, acc);
+        real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
+        finish_particle<real>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    __shared__ double sh[BONDED_THREADS / 32][12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 12; ++k) sh[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < BONDED_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
+        partial[12 * (long long)blockIdx.x + threadIdx.x] = s;
+    }
+}
+
 __global__ void __launch_bounds__(256) inner_final_kernel(const double* __restrict__ partial, int nblocks,
                                                           double* __restrict__ out) {
     __shared__ double sh[12][256];
@@ -145,6 +193,12 @@ static int upload_kind(hymd_bonded* b, int kind, long long n_terms, int slots,
     std::vector<int32_t> idx((size_t)n_terms * 4, 0);
     for (long long t = 0; t < n_terms; ++t)
         for (int s = 0; s < slots; ++s) idx[(size_t)4 * t + s] = index[s][t];
+    std::vector<uint32_t> cta_start, cta_terms, lrefs;
+    build_cta_lists(b->n_particles, n_terms, slots, index, BONDED_THREADS, start, cta_start, cta_terms, lrefs,
+                    b->max_terms[kind]);
+    HYMD_CHECK(to_device(&b->cta_start[kind], cta_start.data(), cta_start.size()));
+    HYMD_CHECK(to_device(&b->cta_terms[kind], cta_terms.data(), cta_terms.size()));
+    HYMD_CHECK(to_device(&b->lrefs[kind], lrefs.data(), lrefs.size()));
     b->n_terms[kind] = n_terms;
     HYMD_CHECK(to_device(&b->start[kind], start.data(), start.size()));
     HYMD_CHECK(to_device(&b->refs[kind], refs.data(), refs.size()));
@@ -175,30 +229,58 @@ static int launch_kind(hymd_bonded* b, int kind, const real* pos, Vec3d box, rea
     return HYMD_OK;
 }
 
+constexpr size_t CTA_SMEM_LIMIT = 160 * 1024;
+
 template <typename real>
-static int launch_inner(hymd_bonded* b, const real* x_in, real* x_out, real* vel, Vec3d box, double mass,
-                        double kick_dt, int n_kicks, double drift_dt, void* const* d_force_out, double* d_out,
-                        cudaStream_t s) {
+static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x_out, real* vel, Vec3d box,
+                        double mass, double kick_dt, int n_kicks, double drift_dt, void* const* d_force_out,
+                        double* d_out, cudaStream_t s) {
     const long long n = b->n_particles;
     const int blocks = (int)((n + BONDED_THREADS - 1) / BONDED_THREADS);
     TermLists t;
+    CtaLists c;
     for (int k = 0; k < 3; ++k) {
         t.start[k] = b->start[k]; t.refs[k] = b->refs[k]; t.idx[k] = b->idx[k]; t.par[k] = b->par[k];
-        t.n_terms[k] = b->n_terms[k];
+        t.n_terms[k] = (kind_mask >> k) & 1 ? b->n_terms[k] : 0;
+        c.cta_start[k] = b->cta_start[k]; c.cta_terms[k] = b->cta_terms[k]; c.lrefs[k] = b->lrefs[k];
+        c.max_terms[k] = b->max_terms[k];
     }
     t.dih_type = b->dih_type;
     ForceOut fo;
     for (int k = 0; k < 3; ++k) fo.f[k] = d_force_out ? d_force_out[k] : nullptr;
     if (blocks > 0) {
-        inner_step_kernel<real><<<blocks, BONDED_THREADS, 0, s>>>(x_in, x_out, vel, n, box, t, (real)mass,
-                                                                  (real)(0.5 * kick_dt), n_kicks,
-                                                                  (real)drift_dt, fo, b->partial);
+        if (b->use_cta)
+            inner_step_cta_kernel<real><<<blocks, BONDED_THREADS, b->cta_smem, s>>>(
+                x_in, x_out, vel, n, box, t, c, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt, fo,
+                b->partial);
+        else
+            inner_step_kernel<real><<<blocks, BONDED_THREADS, 0, s>>>(x_in, x_out, vel, n, box, t, (real)mass,
+                                                                      (real)(0.5 * kick_dt), n_kicks,
+                                                                      (real)drift_dt, fo, b->partial);
         HYMD_LAUNCH_CHECK(b);
     }
     if (d_out) {
         inner_final_kernel<<<1, 256, 0, s>>>(b->partial, blocks, d_out);
         HYMD_LAUNCH_CHECK(b);
     }
+    return HYMD_OK;
+}
+
+static int set_cta(hymd_bonded* b, int enable) {
+    if (!enable) { b->use_cta = 0; return HYMD_OK; }
+    if (b->cta_smem > CTA_SMEM_LIMIT) {
+        set_error("CTA-cooperative bonded evaluation needs %zu bytes of shared memory per CTA (limit %zu): "
+                  "a block of %d consecutive particles takes part in too many terms", b->cta_smem,
+                  CTA_SMEM_LIMIT, BONDED_THREADS);
+        return HYMD_ERR_CAPACITY;
+    }
+    if (b->cta_smem > 48 * 1024) {
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)b->cta_smem));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)b->cta_smem));
+    }
+    b->use_cta = 1;
     return HYMD_OK;
 }
 
@@ -251,6 +333,16 @@ int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const
         cudaError_t e = cudaMalloc((void**)&b->partial, sizeof(double) * 12 * (size_t)(b->max_blocks + 1));
         if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); st = HYMD_ERR_NOMEM; }
     }
+    if (st == HYMD_OK) {
+        cudaError_t e = cudaMalloc((void**)&b->out12, sizeof(double) * 12);
+        if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); st = HYMD_ERR_NOMEM; }
+    }
+    if (st == HYMD_OK) {
+        b->cta_smem = 0;
+        for (int k = 0; k < 3; ++k) b->cta_smem += sizeof(double) * CTA_DOUBLES[k] * (size_t)b->max_terms[k];
+        const char* env = getenv("HYMD_B200_BONDED_CTA");
+        if (env && atoi(env) != 0 && b->cta_smem <= CTA_SMEM_LIMIT) st = set_cta(b, 1);
+    }
     if (st != HYMD_OK) { hymd_bonded_destroy(b); return st; }
     *out = b;
     return HYMD_OK;
@@ -263,7 +355,11 @@ int hymd_bonded_destroy(hymd_bonded* b) {
         cudaFree(b->refs[k]);
         cudaFree(b->idx[k]);
         cudaFree(b->par[k]);
+        cudaFree(b->cta_start[k]);
+        cudaFree(b->cta_terms[k]);
+        cudaFree(b->lrefs[k]);
     }
+    cudaFree(b->out12);
     cudaFree(b->dih_type);
     cudaFree(b->partial);
     delete b;
@@ -280,6 +376,19 @@ int hymd_bonded_forces(hymd_bonded* b, int kind, int dtype, const void* d_pos, c
     if (dtype != HYMD_F32 && dtype != HYMD_F64) { set_error("bad dtype %d", dtype); return HYMD_ERR_INVALID; }
     const Vec3d bx = {box[0], box[1], box[2]};
     cudaStream_t s = (cudaStream_t)stream;
+    if (b->use_cta) {   // one kind through the CTA-cooperative kernel: no velocities, force array on request
+        void* fo[3] = {nullptr, nullptr, nullptr};
+        fo[kind - 2] = d_force;
+        const int st = dtype == HYMD_F64
+            ? launch_inner<double>(b, 1 << (kind - 2), (const double*)d_pos, nullptr, nullptr, bx, 1.0, 0.0, 0,
+                                   0.0, fo, b->out12, s)
+            : launch_inner<float>(b, 1 << (kind - 2), (const float*)d_pos, nullptr, nullptr, bx, 1.0, 0.0, 0,
+                                  0.0, fo, b->out12, s);
+        if (st != HYMD_OK) return st;
+        HYMD_CUDA(cudaMemcpyAsync(d_out, b->out12 + 4 * (kind - 2), 4 * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, s));
+        return HYMD_OK;
+    }
     if (dtype == HYMD_F64)
         return launch_kind<double>(b, kind - 2, (const double*)d_pos, bx, (double*)d_force, d_out, s);
     return launch_kind<float>(b, kind - 2, (const float*)d_pos, bx, (float*)d_force, d_out, s);
@@ -298,10 +407,15 @@ int hymd_bonded_inner_step(hymd_bonded* b, int dtype, const void* d_pos_in, void
     const Vec3d bx = {box[0], box[1], box[2]};
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == HYMD_F64)
-        return launch_inner<double>(b, (const double*)d_pos_in, (double*)d_pos_out, (double*)d_vel, bx, mass,
+        return launch_inner<double>(b, 7, (const double*)d_pos_in, (double*)d_pos_out, (double*)d_vel, bx, mass,
                                     kick_dt, n_kicks, drift_dt, d_force_out, d_out, s);
-    return launch_inner<float>(b, (const float*)d_pos_in, (float*)d_pos_out, (float*)d_vel, bx, mass, kick_dt,
-                               n_kicks, drift_dt, d_force_out, d_out, s);
+    return launch_inner<float>(b, 7, (const float*)d_pos_in, (float*)d_pos_out, (float*)d_vel, bx, mass,
+                               kick_dt, n_kicks, drift_dt, d_force_out, d_out, s);
+}
+
+int hymd_bonded_set_cta(hymd_bonded* b, int enable) {
+    if (!b) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    return set_cta(b, enable);
 }
 
 int64_t hymd_bonded_launch_count(hymd_bonded* b) { return b ? b->launches : 0; }

@@ -67,47 +67,76 @@ struct BondAcc {      // what one particle accumulates
 };
 
 // ---- two-particle bonds ------------------------------------------------------------------------
+// Every *_eval function evaluates one term completely (all slot forces, energy, pressure by-product);
+// the per-particle path keeps the share of its slot, the CTA-cooperative path stores all of them.
 template <typename real>
-__host__ __device__ inline void bond_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, double r0,
-                                          double k, int slot, BondAcc& acc) {
+__host__ __device__ inline void bond_eval(const real* __restrict__ pos, Vec3d box, int ia, int ib, double r0,
+                                          double k, Vec3d& fa, double& e, Vec3d& pr) {
     const Vec3d rab = mic_diff(pos, (long long)ib, (long long)ia, box);
     const double n = sqrt(dot(rab, rab));
     const double df = k * (n - r0);
-    const Vec3d fa = rab * (-df / n);
+    fa = rab * (-df / n);
+    e = 0.5 * k * (n - r0) * (n - r0);
+    pr = mul(fa, rab);
+}
+
+__host__ __device__ inline void bond_apply(int slot, Vec3d fa, Vec3d& f) {
+    f = slot == 0 ? f - fa : f + fa;       // f(aa) -= fa, f(bb) += fa
+}
+
+template <typename real>
+__host__ __device__ inline void bond_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, double r0,
+                                          double k, int slot, BondAcc& acc) {
+    Vec3d fa, pr;
+    double e;
+    bond_eval(pos, box, ia, ib, r0, k, fa, e, pr);
+    bond_apply(slot, fa, acc.f);
     if (slot == 0) {
-        acc.f = acc.f - fa;
-        acc.e += 0.5 * k * (n - r0) * (n - r0);
-        acc.pr = acc.pr + mul(fa, rab);
-    } else {
-        acc.f = acc.f + fa;
+        acc.e += e;
+        acc.pr = acc.pr + pr;
     }
 }
 
 // ---- three-particle angles ---------------------------------------------------------------------
+// Returns false (nothing to add) when cos^2 >= 1, like the Fortran's `if (cosphi2 < 1.0)`.
 template <typename real>
-__host__ __device__ inline void angle_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
-                                           double t0, double k, int slot, BondAcc& acc) {
+__host__ __device__ inline bool angle_eval(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
+                                           double t0, double k, Vec3d& fa, Vec3d& fc, double& e, Vec3d& pr) {
     const Vec3d ra = mic_diff(pos, (long long)ia, (long long)ib, box);
     const Vec3d rc = mic_diff(pos, (long long)ic, (long long)ib, box);
     const double na = sqrt(dot(ra, ra)), nc = sqrt(dot(rc, rc));
     const Vec3d ea = ra * (1.0 / na), ec = rc * (1.0 / nc);
     const double cosphi = dot(ea, ec);
-    if (cosphi * cosphi < 1.0) {
-        const double theta = acos(cosphi);
-        const double sinphi = sin(theta);
-        const double d = theta - t0;
-        const double ff = k * d;
-        const double xra = -ff / (na * sinphi), xrc = -ff / (nc * sinphi);
-        const Vec3d fa = (ec - ea * cosphi) * xra;
-        const Vec3d fc = (ea - ec * cosphi) * xrc;
+    if (!(cosphi * cosphi < 1.0)) return false;
+    const double theta = acos(cosphi);
+    const double sinphi = sin(theta);
+    const double d = theta - t0;
+    const double ff = k * d;
+    const double xra = -ff / (na * sinphi), xrc = -ff / (nc * sinphi);
+    fa = (ec - ea * cosphi) * xra;
+    fc = (ea - ec * cosphi) * xrc;
+    e = 0.5 * ff * d;
+    const Vec3d zero = {0.0, 0.0, 0.0};
+    pr = zero - mul(fa, ra) - mul(fc, rc);
+    return true;
+}
+
+__host__ __device__ inline void angle_apply(int slot, Vec3d fa, Vec3d fc, Vec3d& f) {
+    if (slot == 0) f = f - fa;             // f(aa) -= fa
+    else if (slot == 2) f = f - fc;        // f(cc) -= fc
+    else f = f + fa + fc;                  // f(bb) += fa + fc
+}
+
+template <typename real>
+__host__ __device__ inline void angle_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
+                                           double t0, double k, int slot, BondAcc& acc) {
+    Vec3d fa, fc, pr;
+    double e;
+    if (angle_eval(pos, box, ia, ib, ic, t0, k, fa, fc, e, pr)) {
+        angle_apply(slot, fa, fc, acc.f);
         if (slot == 0) {
-            acc.f = acc.f - fa;
-            acc.e += 0.5 * ff * d;
-            acc.pr = acc.pr - mul(fa, ra) - mul(fc, rc);
-        } else if (slot == 2) {
-            acc.f = acc.f - fc;
-        } else {
-            acc.f = acc.f + fa + fc;
+            acc.e += e;
+            acc.pr = acc.pr + pr;
         }
     }
 }
@@ -121,10 +150,11 @@ __host__ __device__ inline void cosine_series(const double* __restrict__ c_n, co
     }
 }
 
+// out[slot] = what is ADDED to the force of the particle in that slot (compute_dihedral_forces.f90:121-134)
 template <typename real>
-__host__ __device__ inline void dihedral_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
-                                              int id, const double* __restrict__ coeff, int dtype, int slot,
-                                              BondAcc& acc) {
+__host__ __device__ inline void dihedral_eval(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
+                                              int id, const double* __restrict__ coeff, int dtype, Vec3d* out,
+                                              double& e) {
     const Vec3d f = mic_diff(pos, (long long)ia, (long long)ib, box);
     const Vec3d g = mic_diff(pos, (long long)ib, (long long)ic, box);
     const Vec3d h = mic_diff(pos, (long long)id, (long long)ic, box);
@@ -135,7 +165,8 @@ __host__ __device__ inline void dihedral_term(const real* __restrict__ pos, Vec3
     const double sin_phi = dot(w, f) * g_norm;
     const double phi = atan2(sin_phi, cos_phi);
     const double f_dot_g = dot(f, g), h_dot_g = dot(h, g);
-    double df = 0.0, e = 0.0;
+    double df = 0.0;
+    e = 0.0;
     if (dtype == 0) {
         cosine_series(coeff, coeff + DIH_COLS, phi, e, df);
         const double* c_coil = coeff + 2 * DIH_COLS;
@@ -154,16 +185,21 @@ __host__ __device__ inline void dihedral_term(const real* __restrict__ pos, Vec3
     const Vec3d sc = v * (f_dot_g / (v_sq * g_norm)) - w * (h_dot_g / (w_sq * g_norm));
     const Vec3d fa = v * (-df * g_norm / v_sq);
     const Vec3d fd = w * (df * g_norm / w_sq);
-    if (slot == 0) {
-        acc.f = acc.f + fa;
-        acc.e += e;
-    } else if (slot == 1) {
-        acc.f = acc.f + (sc * df - fa);
-    } else if (slot == 2) {
-        acc.f = acc.f + (sc * (-df) - fd);
-    } else {
-        acc.f = acc.f + fd;
-    }
+    out[0] = fa;
+    out[1] = sc * df - fa;
+    out[2] = sc * (-df) - fd;
+    out[3] = fd;
+}
+
+template <typename real>
+__host__ __device__ inline void dihedral_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
+                                              int id, const double* __restrict__ coeff, int dtype, int slot,
+                                              BondAcc& acc) {
+    Vec3d out[4];
+    double e;
+    dihedral_eval(pos, box, ia, ib, ic, id, coeff, dtype, out, e);
+    acc.f = acc.f + out[slot];
+    if (slot == 0) acc.e += e;
 }
 
 // ---- per-particle term lists -------------------------------------------------------------------
@@ -225,6 +261,29 @@ struct TermLists {
     long long n_terms[3];
 };
 
+// Tail of a fused step for one particle: round each kind's force to the array type (the Fortran's f
+// arrays are real(4) in the default build), optional per-kind output, kick(s), drift + wrap.
+template <typename real>
+__host__ __device__ inline void finish_particle(long long p, const real* __restrict__ x_in,
+                                                real* __restrict__ x_out, real* __restrict__ vel, Vec3d box,
+                                                real mass, real half_dt, int n_kicks, real dt,
+                                                real* const* f_out, const BondAcc* acc) {
+    const real L[3] = {(real)box.x, (real)box.y, (real)box.z};
+    for (int d = 0; d < 3; ++d) {
+        real ft[3];
+        for (int k = 0; k < 3; ++k) {
+            const double fk = d == 0 ? acc[k].f.x : (d == 1 ? acc[k].f.y : acc[k].f.z);
+            ft[k] = (real)fk;
+            if (f_out != nullptr && f_out[k] != nullptr) f_out[k][3 * p + d] = ft[k];
+        }
+        if (vel == nullptr) continue;
+        real v = vel[3 * p + d];
+        for (int r = 0; r < n_kicks; ++r) v = kick(v, ft, 3, mass, half_dt);
+        if (n_kicks > 0) vel[3 * p + d] = v;
+        if (x_out != nullptr) x_out[3 * p + d] = drift_wrap(x_in[3 * p + d], v, dt, L[d]);
+    }
+}
+
 // One particle's share of a fused inner rRESPA step (main.py:829-893):
 //   F = bonded forces at x_in (each kind rounded to the array type like the Fortran's f arrays),
 //   n_kicks x  v += half_dt * (f_bond + f_angle + f_dihedral) / mass   (closing kick of the previous
@@ -241,19 +300,157 @@ __host__ __device__ inline void inner_step_particle(long long p, const real* __r
     acc[0] = t.n_terms[0] ? particle_terms<real, 2>(p, x_in, box, t.start[0], t.refs[0], t.idx[0], t.par[0], nullptr) : zero;
     acc[1] = t.n_terms[1] ? particle_terms<real, 3>(p, x_in, box, t.start[1], t.refs[1], t.idx[1], t.par[1], nullptr) : zero;
     acc[2] = t.n_terms[2] ? particle_terms<real, 4>(p, x_in, box, t.start[2], t.refs[2], t.idx[2], t.par[2], t.dih_type) : zero;
-    const real L[3] = {(real)box.x, (real)box.y, (real)box.z};
-    for (int d = 0; d < 3; ++d) {
-        real ft[3];
-        for (int k = 0; k < 3; ++k) {
-            const double fk = d == 0 ? acc[k].f.x : (d == 1 ? acc[k].f.y : acc[k].f.z);
-            ft[k] = (real)fk;
-            if (f_out != nullptr && f_out[k] != nullptr) f_out[k][3 * p + d] = ft[k];
+    finish_particle<real>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);
+}
+
+// ---- CTA-cooperative evaluation ----------------------------------------------------------------
+// The per-particle path evaluates every term once per participant (2x, 3x, 4x).  Here a CTA of
+// `cta_size` consecutive particles first evaluates every term that touches it ONCE (its threads
+// stride over the CTA's term list) into shared memory -- 3 / 6 / 12 doubles per bond / angle /
+// dihedral -- and every particle then sums its own (term, slot) references in the same ascending
+// term order with the same additions as the per-particle path, so the forces are bitwise identical.
+// Terms of molecules that straddle a CTA boundary are evaluated by each CTA they touch.
+struct CtaLists {
+    const uint32_t* cta_start[3];   // [n_cta + 1]
+    const uint32_t* cta_terms[3];   // term ids per CTA, ascending
+    const uint32_t* lrefs[3];       // parallel to TermLists::refs: (position in the CTA list << 2) | slot
+    int max_terms[3];               // largest CTA list per kind (sizes the shared memory)
+};
+constexpr int CTA_DOUBLES[3] = {3, 6, 12};
+
+inline void build_cta_lists(long long n_particles, long long n_terms, int n_slots, const int32_t* const* index,
+                            int cta_size, const std::vector<uint32_t>& start, std::vector<uint32_t>& cta_start,
+                            std::vector<uint32_t>& cta_terms, std::vector<uint32_t>& lrefs, int& max_terms) {
+    const long long n_cta = (n_particles + cta_size - 1) / cta_size;
+    cta_start.assign((size_t)n_cta + 1, 0u);
+    auto distinct = [&](long long t, long long* c) {
+        int m = 0;
+        for (int s = 0; s < n_slots; ++s) {
+            const long long cs = index[s][t] / cta_size;
+            bool seen = false;
+            for (int j = 0; j < m; ++j) seen |= (c[j] == cs);
+            if (!seen) c[m++] = cs;
         }
-        real v = vel[3 * p + d];
-        for (int r = 0; r < n_kicks; ++r) v = kick(v, ft, 3, mass, half_dt);
-        if (n_kicks > 0) vel[3 * p + d] = v;
-        if (x_out != nullptr) x_out[3 * p + d] = drift_wrap(x_in[3 * p + d], v, dt, L[d]);
+        return m;
+    };
+    long long c[4];
+    for (long long t = 0; t < n_terms; ++t) {
+        const int m = distinct(t, c);
+        for (int j = 0; j < m; ++j) cta_start[(size_t)c[j] + 1]++;
     }
+    max_terms = 0;
+    for (long long i = 0; i < n_cta; ++i) {
+        if ((int)cta_start[(size_t)i + 1] > max_terms) max_terms = (int)cta_start[(size_t)i + 1];
+        cta_start[(size_t)i + 1] += cta_start[(size_t)i];
+    }
+    cta_terms.assign(cta_start[(size_t)n_cta], 0u);
+    lrefs.assign((size_t)n_terms * n_slots, 0u);
+    std::vector<uint32_t> cur(cta_start.begin(), cta_start.end() - 1);
+    std::vector<uint32_t> pcur(start.begin(), start.end() - 1);
+    for (long long t = 0; t < n_terms; ++t) {
+        const int m = distinct(t, c);
+        uint32_t lpos[4];
+        for (int j = 0; j < m; ++j) {
+            const uint32_t pos = cur[(size_t)c[j]]++;
+            cta_terms[pos] = (uint32_t)t;
+            lpos[j] = pos - cta_start[(size_t)c[j]];
+        }
+        // refs of a particle are filled in (term, slot) ascending order: the next free one is (t, s)
+        for (int s = 0; s < n_slots; ++s) {
+            const long long p = index[s][t];
+            int j = 0;
+            while (c[j] != p / cta_size) ++j;
+            lrefs[pcur[(size_t)p]++] = (lpos[j] << 2) | (uint32_t)s;
+        }
+    }
+}
+
+// Phase 1: thread `tid` of `nthreads` evaluates its share of CTA `cta`'s terms of all kinds into `sm`
+// (layout: [bonds: max_terms[0]*3][angles: max_terms[1]*6][dihedrals: max_terms[2]*12] doubles) and
+// accumulates energy / pressure of the terms whose slot-0 particle lies in [p0, p1) into own[12].
+template <typename real>
+__host__ __device__ inline void cta_eval_terms(int tid, int nthreads, long long cta, long long p0, long long p1,
+                                               const real* __restrict__ x, Vec3d box, const TermLists& t,
+                                               const CtaLists& c, double* __restrict__ sm, double* own) {
+    double* sm2 = sm;
+    double* sm3 = sm2 + (long long)c.max_terms[0] * CTA_DOUBLES[0];
+    double* sm4 = sm3 + (long long)c.max_terms[1] * CTA_DOUBLES[1];
+    if (t.n_terms[0]) {
+        const uint32_t b = c.cta_start[0][cta], e = c.cta_start[0][cta + 1];
+        for (uint32_t i = b + tid; i < e; i += nthreads) {
+            const long long term = c.cta_terms[0][i];
+            const int32_t* ix = t.idx[0] + 4 * term;
+            Vec3d fa, pr;
+            double en;
+            bond_eval(x, box, ix[0], ix[1], t.par[0][2 * term], t.par[0][2 * term + 1], fa, en, pr);
+            double* o = sm2 + (long long)(i - b) * 3;
+            o[0] = fa.x; o[1] = fa.y; o[2] = fa.z;
+            if (ix[0] >= p0 && ix[0] < p1) { own[0] += en; own[1] += pr.x; own[2] += pr.y; own[3] += pr.z; }
+        }
+    }
+    if (t.n_terms[1]) {
+        const uint32_t b = c.cta_start[1][cta], e = c.cta_start[1][cta + 1];
+        for (uint32_t i = b + tid; i < e; i += nthreads) {
+            const long long term = c.cta_terms[1][i];
+            const int32_t* ix = t.idx[1] + 4 * term;
+            Vec3d fa = {0.0, 0.0, 0.0}, fc = {0.0, 0.0, 0.0}, pr = {0.0, 0.0, 0.0};
+            double en = 0.0;
+            const bool ok = angle_eval(x, box, ix[0], ix[1], ix[2], t.par[1][2 * term], t.par[1][2 * term + 1],
+                                       fa, fc, en, pr);
+            double* o = sm3 + (long long)(i - b) * 6;
+            // an invalid angle is marked with a NaN in the first slot: the particle phase skips it,
+            // exactly like the per-particle path skips the additions
+            o[0] = ok ? fa.x : nan(""); o[1] = fa.y; o[2] = fa.z; o[3] = fc.x; o[4] = fc.y; o[5] = fc.z;
+            if (ok && ix[0] >= p0 && ix[0] < p1) { own[4] += en; own[5] += pr.x; own[6] += pr.y; own[7] += pr.z; }
+        }
+    }
+    if (t.n_terms[2]) {
+        const uint32_t b = c.cta_start[2][cta], e = c.cta_start[2][cta + 1];
+        for (uint32_t i = b + tid; i < e; i += nthreads) {
+            const long long term = c.cta_terms[2][i];
+            const int32_t* ix = t.idx[2] + 4 * term;
+            Vec3d out[4];
+            double en;
+            dihedral_eval(x, box, ix[0], ix[1], ix[2], ix[3], t.par[2] + (long long)DIH_ROWS * DIH_COLS * term,
+                          t.dih_type[term], out, en);
+            double* o = sm4 + (long long)(i - b) * 12;
+            for (int s = 0; s < 4; ++s) { o[3 * s] = out[s].x; o[3 * s + 1] = out[s].y; o[3 * s + 2] = out[s].z; }
+            if (ix[0] >= p0 && ix[0] < p1) own[8] += en;
+        }
+    }
+}
+
+// Phase 2: particle p sums its references out of shared memory (same order and additions as
+// particle_terms); acc[k].e / .pr stay zero (phase 1 accounts for them).
+__host__ __device__ inline void cta_gather_particle(long long p, const TermLists& t, const CtaLists& c,
+                                                    const double* __restrict__ sm, BondAcc* acc) {
+    const BondAcc zero = {{0.0, 0.0, 0.0}, 0.0, {0.0, 0.0, 0.0}};
+    const double* sm2 = sm;
+    const double* sm3 = sm2 + (long long)c.max_terms[0] * CTA_DOUBLES[0];
+    const double* sm4 = sm3 + (long long)c.max_terms[1] * CTA_DOUBLES[1];
+    acc[0] = acc[1] = acc[2] = zero;
+    if (t.n_terms[0])
+        for (uint32_t r = t.start[0][p]; r < t.start[0][p + 1]; ++r) {
+            const uint32_t lr = c.lrefs[0][r];
+            const double* o = sm2 + (long long)(lr >> 2) * 3;
+            const Vec3d fa = {o[0], o[1], o[2]};
+            bond_apply((int)(lr & 3u), fa, acc[0].f);
+        }
+    if (t.n_terms[1])
+        for (uint32_t r = t.start[1][p]; r < t.start[1][p + 1]; ++r) {
+            const uint32_t lr = c.lrefs[1][r];
+            const double* o = sm3 + (long long)(lr >> 2) * 6;
+            if (o[0] != o[0]) continue;
+            const Vec3d fa = {o[0], o[1], o[2]}, fc = {o[3], o[4], o[5]};
+            angle_apply((int)(lr & 3u), fa, fc, acc[1].f);
+        }
+    if (t.n_terms[2])
+        for (uint32_t r = t.start[2][p]; r < t.start[2][p + 1]; ++r) {
+            const uint32_t lr = c.lrefs[2][r];
+            const double* o = sm4 + (long long)(lr >> 2) * 12 + 3 * (lr & 3u);
+            const Vec3d add = {o[0], o[1], o[2]};
+            acc[2].f = acc[2].f + add;
+        }
 }
 
 }  // namespace hymd

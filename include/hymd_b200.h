@@ -248,6 +248,13 @@ int hymd_bonded_forces(hymd_bonded* b, int kind, int dtype, const void* d_pos, c
                        void* d_force, double* d_out, void* stream);
 int64_t hymd_bonded_launch_count(hymd_bonded* b);
 
+/* Evaluation strategy of hymd_bonded_forces / hymd_bonded_inner_step.  0 (default): every particle
+ * re-evaluates the terms it takes part in.  1: every CTA of 128 consecutive particles evaluates each
+ * term touching it once into shared memory and the particles gather their slots (2-4x fewer
+ * evaluations; bitwise the same forces).  HYMD_ERR_CAPACITY if a CTA's term list does not fit in shared
+ * memory.  The environment variable HYMD_B200_BONDED_CTA=1 selects it at creation. */
+int hymd_bonded_set_cta(hymd_bonded* b, int enable);
+
 /* One fused inner rRESPA step (main.py:829-893) in a single pass over the particles:
  *   F = bond + angle + dihedral forces at d_pos_in (every kind rounded to `dtype` like the f arrays),
  *   n_kicks (0, 1 or 2) times  v += 0.5*kick_dt * F / mass   -- the closing kick of the previous inner

@@ -95,8 +95,12 @@ struct HostBonded {
     std::vector<uint32_t> start[3], refs[3];
     std::vector<int32_t> idx[3], dtype;
     std::vector<double> par[3];
+    std::vector<uint32_t> cta_start[3], cta_terms[3], lrefs[3];
+    int max_terms[3];
+    int use_cta;
     long long launches;
 };
+constexpr int HOST_CTA = 128;   // BONDED_THREADS of csrc/bonded.cu
 
 static bool host_upload(HostBonded* b, int kind, long long nt, int slots, const int32_t* const* index,
                         const double* par, size_t per_term) {
@@ -105,6 +109,8 @@ static bool host_upload(HostBonded* b, int kind, long long nt, int slots, const 
     for (long long t = 0; t < nt; ++t)
         for (int s = 0; s < slots; ++s) b->idx[kind][4 * t + s] = index[s][t];
     b->par[kind].assign(par, par + (size_t)nt * per_term);
+    build_cta_lists(b->n, nt, slots, index, HOST_CTA, b->start[kind], b->cta_start[kind], b->cta_terms[kind],
+                    b->lrefs[kind], b->max_terms[kind]);
     return true;
 }
 
@@ -118,6 +124,7 @@ extern "C" int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t
     HostBonded* b = new HostBonded();
     b->n = n_particles;
     b->launches = 0;
+    b->use_cta = 0;
     std::vector<double> p2((size_t)n2 * 2), p3((size_t)n3 * 2);
     for (int64_t t = 0; t < n2; ++t) { p2[2 * t] = r0_2[t]; p2[2 * t + 1] = k_2[t]; }
     for (int64_t t = 0; t < n3; ++t) { p3[2 * t] = t0_3[t]; p3[2 * t + 1] = k_3[t]; }
@@ -137,12 +144,25 @@ extern "C" int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t
 extern "C" int hymd_bonded_destroy(void* b) { delete (HostBonded*)b; return 0; }
 extern "C" int64_t hymd_bonded_launch_count(void* b) { return ((HostBonded*)b)->launches; }
 
+template <typename real>
+static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, real* vel, Vec3d box, double mass,
+                  double kick_dt, int n_kicks, double drift_dt, void* const* f_out, double* out12);
+
 extern "C" int hymd_bonded_forces(void* h, int kind, int dtype, const void* pos, const double* box,
                                   void* force, double* out, void* stream) {
     HostBonded* b = (HostBonded*)h;
     const int k = kind - 2;
     const Vec3d bx = {box[0], box[1], box[2]};
     b->launches += 2;
+    if (b->use_cta) {
+        void* fo[3] = {nullptr, nullptr, nullptr};
+        fo[k] = force;
+        double out12[12];
+        if (dtype == 1) inner<double>(b, 1 << k, (const double*)pos, nullptr, nullptr, bx, 1.0, 0.0, 0, 0.0, fo, out12);
+        else inner<float>(b, 1 << k, (const float*)pos, nullptr, nullptr, bx, 1.0, 0.0, 0, 0.0, fo, out12);
+        for (int j = 0; j < 4; ++j) out[j] = out12[4 * k + j];
+        return 0;
+    }
 #define RUN(real, K) run_kind<real, K>((const real*)pos, bx, b->n, b->start[k], b->refs[k], b->idx[k], \
                                        b->par[k].data(), b->dtype.data(), (real*)force, out)
     if (dtype == 1) { if (kind == 2) RUN(double, 2); else if (kind == 3) RUN(double, 3); else RUN(double, 4); }
@@ -212,28 +232,52 @@ extern "C" int hymd_cancel_com(int dtype, void* vel, int64_t n, const double* mo
 }
 
 template <typename real>
-static void inner(HostBonded* b, const real* x_in, real* x_out, real* vel, Vec3d box, double mass, double kick_dt,
-                  int n_kicks, double drift_dt, void* const* f_out, double* out12) {
+static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, real* vel, Vec3d box, double mass,
+                  double kick_dt, int n_kicks, double drift_dt, void* const* f_out, double* out12) {
     TermLists t;
+    CtaLists c;
     for (int k = 0; k < 3; ++k) {
         t.start[k] = b->start[k].data(); t.refs[k] = b->refs[k].data(); t.idx[k] = b->idx[k].data();
-        t.par[k] = b->par[k].data(); t.n_terms[k] = (long long)(b->idx[k].size() / 4);
+        t.par[k] = b->par[k].data();
+        t.n_terms[k] = (kind_mask >> k) & 1 ? (long long)(b->idx[k].size() / 4) : 0;
+        c.cta_start[k] = b->cta_start[k].data(); c.cta_terms[k] = b->cta_terms[k].data();
+        c.lrefs[k] = b->lrefs[k].data(); c.max_terms[k] = b->max_terms[k];
     }
     t.dih_type = b->dtype.data();
     real* fo[3] = {f_out ? (real*)f_out[0] : nullptr, f_out ? (real*)f_out[1] : nullptr,
                    f_out ? (real*)f_out[2] : nullptr};
     double acc12[12] = {0};
-    for (long long p = 0; p < b->n; ++p) {
-        BondAcc acc[3];
-        inner_step_particle<real>(p, x_in, x_out, vel, box, t, (real)mass, (real)(0.5 * kick_dt), n_kicks,
-                                  (real)drift_dt, fo, acc);
-        for (int k = 0; k < 3; ++k) {
-            acc12[4 * k] += acc[k].e; acc12[4 * k + 1] += acc[k].pr.x; acc12[4 * k + 2] += acc[k].pr.y;
-            acc12[4 * k + 3] += acc[k].pr.z;
+    if (b->use_cta) {
+        // the kernel's structure: per CTA, phase 1 (threads stride over the CTA's terms), barrier, phase 2
+        std::vector<double> sm((size_t)3 * c.max_terms[0] + 6 * c.max_terms[1] + 12 * c.max_terms[2] + 1);
+        const long long n_cta = (b->n + HOST_CTA - 1) / HOST_CTA;
+        for (long long cta = 0; cta < n_cta; ++cta) {
+            const long long p0 = cta * HOST_CTA, p1 = p0 + HOST_CTA < b->n ? p0 + HOST_CTA : b->n;
+            for (size_t i = 0; i < sm.size(); ++i) sm[i] = -777.0;      // stale data must never be read
+            for (int tid = 0; tid < HOST_CTA; ++tid)
+                cta_eval_terms<real>(tid, HOST_CTA, cta, p0, p1, x_in, box, t, c, sm.data(), acc12);
+            for (long long p = p0; p < p1; ++p) {
+                BondAcc acc[3];
+                cta_gather_particle(p, t, c, sm.data(), acc);
+                finish_particle<real>(p, x_in, x_out, vel, box, (real)mass, (real)(0.5 * kick_dt), n_kicks,
+                                      (real)drift_dt, fo, acc);
+            }
+        }
+    } else {
+        for (long long p = 0; p < b->n; ++p) {
+            BondAcc acc[3];
+            inner_step_particle<real>(p, x_in, x_out, vel, box, t, (real)mass, (real)(0.5 * kick_dt), n_kicks,
+                                      (real)drift_dt, fo, acc);
+            for (int k = 0; k < 3; ++k) {
+                acc12[4 * k] += acc[k].e; acc12[4 * k + 1] += acc[k].pr.x; acc12[4 * k + 2] += acc[k].pr.y;
+                acc12[4 * k + 3] += acc[k].pr.z;
+            }
         }
     }
     if (out12) for (int k = 0; k < 12; ++k) out12[k] = acc12[k];
 }
+
+extern "C" int hymd_bonded_set_cta(void* h, int enable) { ((HostBonded*)h)->use_cta = enable ? 1 : 0; return 0; }
 
 extern "C" int hymd_bonded_inner_step(void* h, int dtype, const void* x_in, void* x_out, void* vel,
                                       const double* box, double mass, double kick_dt, int n_kicks,
@@ -242,7 +286,7 @@ extern "C" int hymd_bonded_inner_step(void* h, int dtype, const void* x_in, void
     if (n_kicks < 0 || n_kicks > 2 || x_in == x_out) return -1;
     const Vec3d bx = {box[0], box[1], box[2]};
     b->launches += out12 ? 2 : 1;
-    if (dtype == 1) inner<double>(b, (const double*)x_in, (double*)x_out, (double*)vel, bx, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
-    else inner<float>(b, (const float*)x_in, (float*)x_out, (float*)vel, bx, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
+    if (dtype == 1) inner<double>(b, 7, (const double*)x_in, (double*)x_out, (double*)vel, bx, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
+    else inner<float>(b, 7, (const float*)x_in, (float*)x_out, (float*)vel, bx, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
     return 0;
 }

@@ -316,3 +316,78 @@ def test_fused_inner_step_equals_separate_launches(real):
     assert np.abs(out[True][1] - out[False][1]).max() <= 64 * eps * np.abs(out[False][1]).max()
     for k in (2, 3, 4):
         assert out[True][2][k] == pytest.approx(out[False][2][k], rel=1e-6 if real == np.float32 else 1e-11)
+
+
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_cta_cooperative_evaluation_matches_the_per_particle_result(real):
+    """hymd_bonded_set_cta(1): each CTA evaluates every term touching its 128 particles once into shared
+    memory and the particles gather their slots.  Same additions in the same order => the forces equal the
+    per-particle kernels' up to FMA contraction across the inlined term evaluation (bit-identical when
+    the same source runs on the CPU, tests/test_md_host_emulation.py); energies agree to rounding.  Branched molecules (DPPC
+    topology of the reference's fixture), chains straddling CTA boundaries, all three kinds, a solvent
+    tail without terms; then a fused rRESPA run with the switch on."""
+    from hymd_b200.force import BondedTopology
+    from hymd_b200.md import RespaMD
+    rng = np.random.default_rng(77)
+    box = np.array([6.0, 5.0, 7.0])
+    # 90 copies of the 12-bead DPPC graph (test/conftest.py dppc_single) + 140 chains of 9 + 300 solvent
+    dppc_b = np.array([[0, 1], [1, 2], [2, 3], [2, 4], [3, 8], [4, 5], [5, 6], [6, 7], [8, 9], [9, 10], [10, 11]])
+    dppc_a = np.array([[1, 2, 3], [1, 2, 4], [3, 8, 9], [2, 4, 5], [4, 5, 6], [5, 6, 7], [8, 9, 10], [9, 10, 11]])
+    n_d = 90
+    r_d = (G["dppc/r"][None] - G["dppc/r"].mean(axis=0) + (rng.random((n_d, 1, 3)) * box)).reshape(-1, 3)
+    b2 = (dppc_b[None] + 12 * np.arange(n_d)[:, None, None]).reshape(-1, 2)
+    b3 = (dppc_a[None] + 12 * np.arange(n_d)[:, None, None]).reshape(-1, 3)
+    r_c, a2, a3, a4 = chains(rng, 140, 9, box, np.float64)
+    off = 12 * n_d
+    b2 = np.concatenate([b2, np.stack([a2, a2 + 1], 1) + off])
+    b3 = np.concatenate([b3, np.stack([a3, a3 + 1, a3 + 2], 1) + off])
+    b4 = np.stack([a4, a4 + 1, a4 + 2, a4 + 3], 1) + off
+    r = np.mod(np.concatenate([r_d, r_c, rng.random((300, 3)) * box]), box).astype(real)
+    n = len(r)
+    r0, k2 = 0.47 + 0.05 * rng.random(len(b2)), 1250.0 * (0.5 + rng.random(len(b2)))
+    t0, k3 = np.radians(rng.choice([120.0, 180.0], size=len(b3))), 25.0 * (0.5 + rng.random(len(b3)))
+    coeff = np.zeros((len(b4), 6, 5))
+    coeff[:, 0] = rng.normal(size=(len(b4), 5))
+    coeff[:, 1] = rng.uniform(-np.pi, np.pi, size=(len(b4), 5))
+    dt4 = np.zeros(len(b4), dtype=int)
+    dt4[::4] = 2
+    coeff[::4, 0, 0], coeff[::4, 0, 1] = -0.5, 30.0
+    topo = BondedTopology(n, bonds=(b2[:, 0], b2[:, 1], r0, k2), angles=(b3[:, 0], b3[:, 1], b3[:, 2], t0, k3),
+                          dihedrals=(b4[:, 0], b4[:, 1], b4[:, 2], b4[:, 3], coeff, dt4),
+                          device=DEVICE if DEVICE != "cuda" else None)
+    pos = dev(r, real)
+    ref = {}
+    for cta in (0, 1):
+        topo.set_cta(bool(cta))
+        for kind in (2, 3, 4):
+            f = torch.full((n, 3), 3.0, dtype=pos.dtype, device=DEVICE)
+            res = topo.forces(kind, pos, box, f).clone()
+            if cta == 0:
+                ref[kind] = (f.clone(), res)
+            else:
+                fs = float(ref[kind][0].abs().max())
+                assert float((f - ref[kind][0]).abs().max()) <= 4 * np.finfo(real).eps * fs, f"kind {kind}"
+                if DEVICE == "cpu":
+                    assert torch.equal(f, ref[kind][0])
+                scale = float(ref[kind][1].abs().max()) or 1.0
+                assert float((res - ref[kind][1]).abs().max()) <= 1e-12 * scale
+    fo_, eo, pro = bo.compute_angle_forces(r, box, b3[:, 0], b3[:, 1], b3[:, 2], t0, k3)
+    assert np.abs(ref[3][0].cpu().numpy() - fo_).max() <= FTOL[real] * np.abs(fo_).max()
+    # fused rRESPA steps with the switch on == off
+    v = rng.normal(scale=0.15, size=(n, 3)).astype(real)
+    out = {}
+    for cta in (0, 1):
+        topo.set_cta(bool(cta))
+        md = RespaMD(lambda x: [], box, 72.0, 0.004, respa_inner=4, topology=topo)
+        xd, vd = dev(r, real), dev(v, real)
+        for _ in range(3):
+            md.step(xd, vd, [])
+        out[cta] = (xd.clone(), vd.clone(), md.bonded_energies())
+    eps = np.finfo(real).eps
+    d = (out[0][0] - out[1][0]).abs().cpu().numpy()
+    d = np.minimum(d, np.abs(d - box[None, :].astype(real)))
+    assert d.max() <= 256 * eps * box.max()
+    assert float((out[0][1] - out[1][1]).abs().max()) <= 256 * eps * float(out[0][1].abs().max())
+    for k in (2, 3, 4):
+        assert out[1][2][k] == pytest.approx(out[0][2][k], rel=1e-5 if real == np.float32 else 1e-10)
+    topo.set_cta(False)

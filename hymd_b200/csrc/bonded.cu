@@ -18,9 +18,10 @@ struct hymd_bonded {
     uint32_t* cta_start[3];      // CTA-cooperative evaluation (bonded.cuh, CtaLists)
     uint32_t* cta_terms[3];
     uint32_t* lrefs[3];
+    hymd::TermRec* rec[2];       // inline bond / angle records of the CTA lists (mode 2)
     int max_terms[3];
     size_t cta_smem;             // dynamic shared memory of inner_step_cta_kernel
-    int use_cta;                 // HYMD_B200_BONDED_CTA / hymd_bonded_set_cta
+    int use_cta;                 // HYMD_B200_BONDED_CTA / hymd_bonded_set_cta: 0, 1 or 2
     double* out12;               // scratch result of the fused kernels
     double* partial;             // [max_blocks][4] block partials of {energy, pr_x, pr_y, pr_z}
     int max_blocks;
@@ -141,6 +142,53 @@ __global__ void __launch_bounds__(BONDED_THREADS) inner_step_cta_kernel(
     }
 }
 
+// Mode 2: own positions staged in shared memory, inline term records (bonded.cuh).  The per-particle
+// list bounds are fetched before the first barrier so their latency overlaps phase 1.
+template <typename real>
+__global__ void __launch_bounds__(BONDED_THREADS) inner_step_cta2_kernel(
+    const real* __restrict__ x_in, real* __restrict__ x_out, real* __restrict__ vel, long long n, Vec3d box,
+    TermLists t, CtaLists c, CtaRecs rc, real mass, real half_dt, int n_kicks, real dt, ForceOut fo,
+    double* __restrict__ partial) {
+    extern __shared__ double sm[];
+    real* tile = (real*)sm;                                            // [BONDED_THREADS * 3] reals
+    double* vecs = sm + (BONDED_THREADS * 3 * sizeof(real) + 7) / 8;
+    const long long cta = blockIdx.x;
+    const long long p0 = cta * BONDED_THREADS;
+    const long long p1 = p0 + BONDED_THREADS < n ? p0 + BONDED_THREADS : n;
+    const int n_own = (int)(p1 - p0);
+    for (int i = threadIdx.x; i < 3 * n_own; i += BONDED_THREADS) tile[i] = x_in[3 * p0 + i];
+    __syncthreads();
+    const PosTile<real> x = {x_in, tile, p0, p1};
+    const long long p = p0 + threadIdx.x;
+    RefBounds rb;
+    if (p < n) rb = ref_bounds(p, t);          // in flight during phase 1
+    double v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = 0.0;
+    cta2_eval_terms<real>((int)threadIdx.x, BONDED_THREADS, cta, p0, p1, x, box, t, c, rc, vecs, v);
+    __syncthreads();
+    if (p < n) {
+        BondAcc acc[3];
+        cta_gather_bounds(rb, c, vecs, acc);
+        real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
+        finish_particle<real>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    __shared__ double sh[BONDED_THREADS / 32][12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 12; ++k) sh[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < BONDED_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
+        partial[12 * (long long)blockIdx.x + threadIdx.x] = s;
+    }
+}
+
 __global__ void __launch_bounds__(256) inner_final_kernel(const double* __restrict__ partial, int nblocks,
                                                           double* __restrict__ out) {
     __shared__ double sh[12][256];
@@ -199,6 +247,11 @@ static int upload_kind(hymd_bonded* b, int kind, long long n_terms, int slots,
     HYMD_CHECK(to_device(&b->cta_start[kind], cta_start.data(), cta_start.size()));
     HYMD_CHECK(to_device(&b->cta_terms[kind], cta_terms.data(), cta_terms.size()));
     HYMD_CHECK(to_device(&b->lrefs[kind], lrefs.data(), lrefs.size()));
+    if (kind < 2) {
+        std::vector<TermRec> rec;
+        build_cta_records(cta_terms, idx.data(), par, rec);
+        HYMD_CHECK(to_device(&b->rec[kind], rec.data(), rec.size()));
+    }
     b->n_terms[kind] = n_terms;
     HYMD_CHECK(to_device(&b->start[kind], start.data(), start.size()));
     HYMD_CHECK(to_device(&b->refs[kind], refs.data(), refs.size()));
@@ -249,7 +302,14 @@ static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x
     ForceOut fo;
     for (int k = 0; k < 3; ++k) fo.f[k] = d_force_out ? d_force_out[k] : nullptr;
     if (blocks > 0) {
-        if (b->use_cta)
+        if (b->use_cta == 2) {
+            CtaRecs rc;
+            rc.rec[0] = b->rec[0];
+            rc.rec[1] = b->rec[1];
+            inner_step_cta2_kernel<real><<<blocks, BONDED_THREADS, b->cta_smem + BONDED_THREADS * 3 * sizeof(real) + 8, s>>>(
+                x_in, x_out, vel, n, box, t, c, rc, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt,
+                fo, b->partial);
+        } else if (b->use_cta)
             inner_step_cta_kernel<real><<<blocks, BONDED_THREADS, b->cta_smem, s>>>(
                 x_in, x_out, vel, n, box, t, c, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt, fo,
                 b->partial);
@@ -274,13 +334,14 @@ static int set_cta(hymd_bonded* b, int enable) {
                   CTA_SMEM_LIMIT, BONDED_THREADS);
         return HYMD_ERR_CAPACITY;
     }
-    if (b->cta_smem > 48 * 1024) {
-        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)b->cta_smem));
-        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)b->cta_smem));
+    if (b->cta_smem + 4096 > 48 * 1024) {
+        const int bytes = (int)b->cta_smem + BONDED_THREADS * 3 * (int)sizeof(double) + 8;
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta2_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
-    b->use_cta = 1;
+    b->use_cta = enable == 2 ? 2 : 1;
     return HYMD_OK;
 }
 
@@ -341,7 +402,7 @@ int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const
         b->cta_smem = 0;
         for (int k = 0; k < 3; ++k) b->cta_smem += sizeof(double) * CTA_DOUBLES[k] * (size_t)b->max_terms[k];
         const char* env = getenv("HYMD_B200_BONDED_CTA");
-        if (env && atoi(env) != 0 && b->cta_smem <= CTA_SMEM_LIMIT) st = set_cta(b, 1);
+        if (env && atoi(env) != 0 && b->cta_smem <= CTA_SMEM_LIMIT) st = set_cta(b, atoi(env));
     }
     if (st != HYMD_OK) { hymd_bonded_destroy(b); return st; }
     *out = b;
@@ -358,6 +419,7 @@ int hymd_bonded_destroy(hymd_bonded* b) {
         cudaFree(b->cta_start[k]);
         cudaFree(b->cta_terms[k]);
         cudaFree(b->lrefs[k]);
+        if (k < 2) cudaFree(b->rec[k]);
     }
     cudaFree(b->out12);
     cudaFree(b->dih_type);

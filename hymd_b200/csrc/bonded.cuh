@@ -60,6 +60,27 @@ __host__ __device__ inline Vec3d mic_diff(const real* __restrict__ pos, long lon
     return d;
 }
 
+// Positions of a CTA's own particles [p0, p1) staged in shared memory, everything else from global
+// memory (atoms of molecules that straddle the CTA boundary).
+template <typename real>
+struct PosTile {
+    const real* g;
+    const real* s;
+    long long p0, p1;
+    __host__ __device__ inline real get(long long i, int d) const {
+        return (i >= p0 && i < p1) ? s[3 * (i - p0) + d] : g[3 * i + d];
+    }
+};
+template <typename real>
+__host__ __device__ inline Vec3d mic_diff(const PosTile<real>& pos, long long i, long long j, Vec3d box) {
+    Vec3d d = {(double)(pos.get(i, 0) - pos.get(j, 0)), (double)(pos.get(i, 1) - pos.get(j, 1)),
+               (double)(pos.get(i, 2) - pos.get(j, 2))};
+    d.x -= box.x * round(d.x / box.x);
+    d.y -= box.y * round(d.y / box.y);
+    d.z -= box.z * round(d.z / box.z);
+    return d;
+}
+
 struct BondAcc {      // what one particle accumulates
     Vec3d f;          // force on the particle
     double e;         // energy of the terms it holds slot 0 of
@@ -69,8 +90,8 @@ struct BondAcc {      // what one particle accumulates
 // ---- two-particle bonds ------------------------------------------------------------------------
 // Every *_eval function evaluates one term completely (all slot forces, energy, pressure by-product);
 // the per-particle path keeps the share of its slot, the CTA-cooperative path stores all of them.
-template <typename real>
-__host__ __device__ inline void bond_eval(const real* __restrict__ pos, Vec3d box, int ia, int ib, double r0,
+template <typename P>
+__host__ __device__ inline void bond_eval(const P& pos, Vec3d box, int ia, int ib, double r0,
                                           double k, Vec3d& fa, double& e, Vec3d& pr) {
     const Vec3d rab = mic_diff(pos, (long long)ib, (long long)ia, box);
     const double n = sqrt(dot(rab, rab));
@@ -99,8 +120,8 @@ __host__ __device__ inline void bond_term(const real* __restrict__ pos, Vec3d bo
 
 // ---- three-particle angles ---------------------------------------------------------------------
 // Returns false (nothing to add) when cos^2 >= 1, like the Fortran's `if (cosphi2 < 1.0)`.
-template <typename real>
-__host__ __device__ inline bool angle_eval(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
+template <typename P>
+__host__ __device__ inline bool angle_eval(const P& pos, Vec3d box, int ia, int ib, int ic,
                                            double t0, double k, Vec3d& fa, Vec3d& fc, double& e, Vec3d& pr) {
     const Vec3d ra = mic_diff(pos, (long long)ia, (long long)ib, box);
     const Vec3d rc = mic_diff(pos, (long long)ic, (long long)ib, box);
@@ -151,8 +172,8 @@ __host__ __device__ inline void cosine_series(const double* __restrict__ c_n, co
 }
 
 // out[slot] = what is ADDED to the force of the particle in that slot (compute_dihedral_forces.f90:121-134)
-template <typename real>
-__host__ __device__ inline void dihedral_eval(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic,
+template <typename P>
+__host__ __device__ inline void dihedral_eval(const P& pos, Vec3d box, int ia, int ib, int ic,
                                               int id, const double* __restrict__ coeff, int dtype, Vec3d* out,
                                               double& e) {
     const Vec3d f = mic_diff(pos, (long long)ia, (long long)ib, box);
@@ -420,37 +441,124 @@ __host__ __device__ inline void cta_eval_terms(int tid, int nthreads, long long 
     }
 }
 
+// ---- CTA-cooperative evaluation, second layout ("mode 2") ----------------------------------------
+// Cuts the dependent global loads of phase 1 from four levels (list bounds -> term id -> indices and
+// parameters -> positions) to two: the bond / angle records {indices, parameters} are stored INLINE in
+// the CTA's list (32 B, one coalesced load per thread) and the CTA's own positions are staged in
+// shared memory first, so a term only goes back to global memory for atoms outside the CTA.
+struct TermRec {
+    int32_t i[4];
+    double p[2];
+};
+struct CtaRecs {
+    const TermRec* rec[2];      // bonds, angles: parallel to CtaLists::cta_terms[0], [1]
+};
+
+inline void build_cta_records(const std::vector<uint32_t>& cta_terms, const int32_t* idx4, const double* par2,
+                              std::vector<TermRec>& rec) {
+    rec.resize(cta_terms.size());
+    for (size_t i = 0; i < cta_terms.size(); ++i) {
+        const size_t t = cta_terms[i];
+        for (int s = 0; s < 4; ++s) rec[i].i[s] = idx4[4 * t + s];
+        rec[i].p[0] = par2[2 * t];
+        rec[i].p[1] = par2[2 * t + 1];
+    }
+}
+
+template <typename real>
+__host__ __device__ inline void cta2_eval_terms(int tid, int nthreads, long long cta, long long p0, long long p1,
+                                                const PosTile<real>& x, Vec3d box, const TermLists& t,
+                                                const CtaLists& c, const CtaRecs& rc, double* __restrict__ sm,
+                                                double* own) {
+    double* sm2 = sm;
+    double* sm3 = sm2 + (long long)c.max_terms[0] * CTA_DOUBLES[0];
+    double* sm4 = sm3 + (long long)c.max_terms[1] * CTA_DOUBLES[1];
+    if (t.n_terms[0]) {
+        const uint32_t b = c.cta_start[0][cta], e = c.cta_start[0][cta + 1];
+        for (uint32_t i = b + tid; i < e; i += nthreads) {
+            const TermRec r = rc.rec[0][i];
+            Vec3d fa, pr;
+            double en;
+            bond_eval(x, box, r.i[0], r.i[1], r.p[0], r.p[1], fa, en, pr);
+            double* o = sm2 + (long long)(i - b) * 3;
+            o[0] = fa.x; o[1] = fa.y; o[2] = fa.z;
+            if (r.i[0] >= p0 && r.i[0] < p1) { own[0] += en; own[1] += pr.x; own[2] += pr.y; own[3] += pr.z; }
+        }
+    }
+    if (t.n_terms[1]) {
+        const uint32_t b = c.cta_start[1][cta], e = c.cta_start[1][cta + 1];
+        for (uint32_t i = b + tid; i < e; i += nthreads) {
+            const TermRec r = rc.rec[1][i];
+            Vec3d fa = {0.0, 0.0, 0.0}, fc = {0.0, 0.0, 0.0}, pr = {0.0, 0.0, 0.0};
+            double en = 0.0;
+            const bool ok = angle_eval(x, box, r.i[0], r.i[1], r.i[2], r.p[0], r.p[1], fa, fc, en, pr);
+            double* o = sm3 + (long long)(i - b) * 6;
+            o[0] = ok ? fa.x : nan(""); o[1] = fa.y; o[2] = fa.z; o[3] = fc.x; o[4] = fc.y; o[5] = fc.z;
+            if (ok && r.i[0] >= p0 && r.i[0] < p1) { own[4] += en; own[5] += pr.x; own[6] += pr.y; own[7] += pr.z; }
+        }
+    }
+    if (t.n_terms[2]) {
+        const uint32_t b = c.cta_start[2][cta], e = c.cta_start[2][cta + 1];
+        for (uint32_t i = b + tid; i < e; i += nthreads) {
+            const long long term = c.cta_terms[2][i];
+            const int32_t* ix = t.idx[2] + 4 * term;
+            Vec3d out[4];
+            double en;
+            dihedral_eval(x, box, ix[0], ix[1], ix[2], ix[3], t.par[2] + (long long)DIH_ROWS * DIH_COLS * term,
+                          t.dih_type[term], out, en);
+            double* o = sm4 + (long long)(i - b) * 12;
+            for (int s = 0; s < 4; ++s) { o[3 * s] = out[s].x; o[3 * s + 1] = out[s].y; o[3 * s + 2] = out[s].z; }
+            if (ix[0] >= p0 && ix[0] < p1) own[8] += en;
+        }
+    }
+}
+
 // Phase 2: particle p sums its references out of shared memory (same order and additions as
-// particle_terms); acc[k].e / .pr stay zero (phase 1 accounts for them).
-__host__ __device__ inline void cta_gather_particle(long long p, const TermLists& t, const CtaLists& c,
-                                                    const double* __restrict__ sm, BondAcc* acc) {
+// particle_terms); acc[k].e / .pr stay zero (phase 1 accounts for them).  The list bounds can be
+// fetched ahead of the barrier (RefBounds).
+struct RefBounds {
+    uint32_t b[3], e[3];
+};
+__host__ __device__ inline RefBounds ref_bounds(long long p, const TermLists& t) {
+    RefBounds r;
+    for (int k = 0; k < 3; ++k) {
+        r.b[k] = t.n_terms[k] ? t.start[k][p] : 0u;
+        r.e[k] = t.n_terms[k] ? t.start[k][p + 1] : 0u;
+    }
+    return r;
+}
+
+__host__ __device__ inline void cta_gather_bounds(const RefBounds& rb, const CtaLists& c,
+                                                  const double* __restrict__ sm, BondAcc* acc) {
     const BondAcc zero = {{0.0, 0.0, 0.0}, 0.0, {0.0, 0.0, 0.0}};
     const double* sm2 = sm;
     const double* sm3 = sm2 + (long long)c.max_terms[0] * CTA_DOUBLES[0];
     const double* sm4 = sm3 + (long long)c.max_terms[1] * CTA_DOUBLES[1];
     acc[0] = acc[1] = acc[2] = zero;
-    if (t.n_terms[0])
-        for (uint32_t r = t.start[0][p]; r < t.start[0][p + 1]; ++r) {
-            const uint32_t lr = c.lrefs[0][r];
-            const double* o = sm2 + (long long)(lr >> 2) * 3;
-            const Vec3d fa = {o[0], o[1], o[2]};
-            bond_apply((int)(lr & 3u), fa, acc[0].f);
-        }
-    if (t.n_terms[1])
-        for (uint32_t r = t.start[1][p]; r < t.start[1][p + 1]; ++r) {
-            const uint32_t lr = c.lrefs[1][r];
-            const double* o = sm3 + (long long)(lr >> 2) * 6;
-            if (o[0] != o[0]) continue;
-            const Vec3d fa = {o[0], o[1], o[2]}, fc = {o[3], o[4], o[5]};
-            angle_apply((int)(lr & 3u), fa, fc, acc[1].f);
-        }
-    if (t.n_terms[2])
-        for (uint32_t r = t.start[2][p]; r < t.start[2][p + 1]; ++r) {
-            const uint32_t lr = c.lrefs[2][r];
-            const double* o = sm4 + (long long)(lr >> 2) * 12 + 3 * (lr & 3u);
-            const Vec3d add = {o[0], o[1], o[2]};
-            acc[2].f = acc[2].f + add;
-        }
+    for (uint32_t r = rb.b[0]; r < rb.e[0]; ++r) {
+        const uint32_t lr = c.lrefs[0][r];
+        const double* o = sm2 + (long long)(lr >> 2) * 3;
+        const Vec3d fa = {o[0], o[1], o[2]};
+        bond_apply((int)(lr & 3u), fa, acc[0].f);
+    }
+    for (uint32_t r = rb.b[1]; r < rb.e[1]; ++r) {
+        const uint32_t lr = c.lrefs[1][r];
+        const double* o = sm3 + (long long)(lr >> 2) * 6;
+        if (o[0] != o[0]) continue;
+        const Vec3d fa = {o[0], o[1], o[2]}, fc = {o[3], o[4], o[5]};
+        angle_apply((int)(lr & 3u), fa, fc, acc[1].f);
+    }
+    for (uint32_t r = rb.b[2]; r < rb.e[2]; ++r) {
+        const uint32_t lr = c.lrefs[2][r];
+        const double* o = sm4 + (long long)(lr >> 2) * 12 + 3 * (lr & 3u);
+        const Vec3d add = {o[0], o[1], o[2]};
+        acc[2].f = acc[2].f + add;
+    }
+}
+
+__host__ __device__ inline void cta_gather_particle(long long p, const TermLists& t, const CtaLists& c,
+                                                    const double* __restrict__ sm, BondAcc* acc) {
+    cta_gather_bounds(ref_bounds(p, t), c, sm, acc);
 }
 
 }  // namespace hymd

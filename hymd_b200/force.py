@@ -103,9 +103,10 @@ class BondedTopology:
             pass
 
     def set_cta(self, enable=True):
-        """Switch between per-particle (default) and CTA-cooperative term evaluation
-        (``hymd_bonded_set_cta``): same forces bit for bit, 2-4x fewer term evaluations."""
-        _lib.check(self.lib.hymd_bonded_set_cta(self._h, 1 if enable else 0))
+        """Switch between per-particle (0, default) and CTA-cooperative term evaluation
+        (``hymd_bonded_set_cta``; 1: indirect term lists, 2: inline records + positions staged in shared
+        memory): same forces, 2-4x fewer term evaluations."""
+        _lib.check(self.lib.hymd_bonded_set_cta(self._h, int(enable)))
 
     def launch_count(self):
         return int(self.lib.hymd_bonded_launch_count(self._h))

@@ -96,6 +96,7 @@ struct HostBonded {
     std::vector<int32_t> idx[3], dtype;
     std::vector<double> par[3];
     std::vector<uint32_t> cta_start[3], cta_terms[3], lrefs[3];
+    std::vector<TermRec> rec[2];
     int max_terms[3];
     int use_cta;
     long long launches;
@@ -111,6 +112,7 @@ static bool host_upload(HostBonded* b, int kind, long long nt, int slots, const 
     b->par[kind].assign(par, par + (size_t)nt * per_term);
     build_cta_lists(b->n, nt, slots, index, HOST_CTA, b->start[kind], b->cta_start[kind], b->cta_terms[kind],
                     b->lrefs[kind], b->max_terms[kind]);
+    if (kind < 2) build_cta_records(b->cta_terms[kind], b->idx[kind].data(), b->par[kind].data(), b->rec[kind]);
     return true;
 }
 
@@ -254,8 +256,18 @@ static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, r
         for (long long cta = 0; cta < n_cta; ++cta) {
             const long long p0 = cta * HOST_CTA, p1 = p0 + HOST_CTA < b->n ? p0 + HOST_CTA : b->n;
             for (size_t i = 0; i < sm.size(); ++i) sm[i] = -777.0;      // stale data must never be read
-            for (int tid = 0; tid < HOST_CTA; ++tid)
-                cta_eval_terms<real>(tid, HOST_CTA, cta, p0, p1, x_in, box, t, c, sm.data(), acc12);
+            if (b->use_cta == 2) {      // mode 2: own positions staged, inline records
+                std::vector<real> tile((size_t)3 * HOST_CTA, (real)-555);
+                for (long long i = 0; i < 3 * (p1 - p0); ++i) tile[i] = x_in[3 * p0 + i];
+                const PosTile<real> xt = {x_in, tile.data(), p0, p1};
+                CtaRecs rc;
+                rc.rec[0] = b->rec[0].data();
+                rc.rec[1] = b->rec[1].data();
+                for (int tid = 0; tid < HOST_CTA; ++tid)
+                    cta2_eval_terms<real>(tid, HOST_CTA, cta, p0, p1, xt, box, t, c, rc, sm.data(), acc12);
+            } else
+                for (int tid = 0; tid < HOST_CTA; ++tid)
+                    cta_eval_terms<real>(tid, HOST_CTA, cta, p0, p1, x_in, box, t, c, sm.data(), acc12);
             for (long long p = p0; p < p1; ++p) {
                 BondAcc acc[3];
                 cta_gather_particle(p, t, c, sm.data(), acc);
@@ -277,7 +289,7 @@ static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, r
     if (out12) for (int k = 0; k < 12; ++k) out12[k] = acc12[k];
 }
 
-extern "C" int hymd_bonded_set_cta(void* h, int enable) { ((HostBonded*)h)->use_cta = enable ? 1 : 0; return 0; }
+extern "C" int hymd_bonded_set_cta(void* h, int enable) { ((HostBonded*)h)->use_cta = enable == 2 ? 2 : (enable ? 1 : 0); return 0; }
 
 extern "C" int hymd_bonded_inner_step(void* h, int dtype, const void* x_in, void* x_out, void* vel,
                                       const double* box, double mass, double kick_dt, int n_kicks,

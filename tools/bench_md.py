@@ -107,17 +107,18 @@ def main():
     fused_bytes = n * 12 * 4 + len(a2) * 40 + len(a3) * 44 + n * 8
     ms = timed(lambda: topo.inner_step(x3, x4, v4, box, 72.0, 0.01, 2, 0.0, want_energies=False), args.iters)
     line("fused_inner_step", ms, fused_bytes)
-    try:    # CTA-cooperative term evaluation (hymd_bonded_set_cta)
-        topo.set_cta(True)
-        ms = timed(lambda: topo.forces(2, x, box, fb), args.iters)
-        line("bonds_cta", ms, n * 28 + len(a2) * (16 + 16 + 8))
-        ms = timed(lambda: topo.forces(3, x, box, fa), args.iters)
-        line("angles_cta", ms, n * 28 + len(a3) * (16 + 16 + 12))
-        ms = timed(lambda: topo.inner_step(x3, x4, v4, box, 72.0, 0.01, 2, 0.0, want_energies=False), args.iters)
-        line("fused_inner_step_cta", ms, fused_bytes)
-        topo.set_cta(False)
-    except Exception as exc:   # keep the lines measured so far
-        res["cta_error"] = repr(exc)
+    for mode, tag in ((1, "cta"), (2, "cta2")):    # CTA-cooperative term evaluation (hymd_bonded_set_cta)
+        try:
+            topo.set_cta(mode)
+            ms = timed(lambda: topo.forces(2, x, box, fb), args.iters)
+            line("bonds_" + tag, ms, n * 28 + len(a2) * (16 + 16 + 8))
+            ms = timed(lambda: topo.forces(3, x, box, fa), args.iters)
+            line("angles_" + tag, ms, n * 28 + len(a3) * (16 + 16 + 12))
+            ms = timed(lambda: topo.inner_step(x3, x4, v4, box, 72.0, 0.01, 2, 0.0, want_energies=False), args.iters)
+            line("fused_inner_step_" + tag, ms, fused_bytes)
+        except Exception as exc:   # keep the lines measured so far
+            res[tag + "_error"] = repr(exc)
+    topo.set_cta(0)
     inner = res["kick_drift_2forces"]["ms"] + res["bonds"]["ms"] + res["angles"]["ms"] + res["kick_2forces"]["ms"]
     res["inner_rrespa_step_ms"] = inner
     res["launches_topology"] = topo.launch_count()

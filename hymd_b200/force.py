@@ -90,6 +90,7 @@ class BondedTopology:
         self._h = handle
         self._out = torch.zeros((3, 4), dtype=torch.float64, device=self.device)
         self._out12 = torch.zeros((3, 4), dtype=torch.float64, device=self.device)
+        self._cta = None     # unknown until set (HYMD_B200_BONDED_CTA may have chosen at creation)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -107,6 +108,7 @@ class BondedTopology:
         (``hymd_bonded_set_cta``; 1: indirect term lists, 2: inline records + positions staged in shared
         memory): same forces, 2-4x fewer term evaluations."""
         _lib.check(self.lib.hymd_bonded_set_cta(self._h, int(enable)))
+        self._cta = int(enable)
 
     def launch_count(self):
         return int(self.lib.hymd_bonded_launch_count(self._h))
@@ -130,12 +132,19 @@ class BondedTopology:
 
 
     def inner_step(self, x_in, x_out, vel, box_size, mass, kick_dt, n_kicks, drift_dt, force_out=None,
-                   want_energies=True):
+                   want_energies=True, cta=None):
         """One fused inner rRESPA step (``hymd_bonded_inner_step``): bonded forces at ``x_in``,
         ``n_kicks`` half kicks of ``vel`` (in place) and, if ``x_out`` is given (a different tensor),
         ``x_out = mod(x_in + drift_dt*vel, box)``.  ``force_out`` = optional 3-list of (n,3) tensors
         (bond, angle, dihedral; entries may be None).  Returns the (3,4) float64 device tensor
-        {energy, pr_x, pr_y, pr_z} per kind (aliases an internal buffer) or None."""
+        {energy, pr_x, pr_y, pr_z} per kind (aliases an internal buffer) or None.  ``cta`` selects the
+        evaluation strategy for this and later calls (see :meth:`set_cta`)."""
+        if cta is not None and cta != self._cta:
+            try:
+                self.set_cta(cta)
+            except _lib.HymdError:      # a CTA's term list does not fit in shared memory: per-particle
+                self.set_cta(0)
+                self._cta = cta         # do not retry every step
         n = self.n_particles
         tensors = [x_in, vel] + ([x_out] if x_out is not None else []) + \
             [f for f in (force_out or []) if f is not None]

@@ -108,7 +108,7 @@ class RespaMD:
     callable ``(velocities) -> None`` applied every ``n_b`` outer steps (``main.py:1290-1292``)."""
 
     def __init__(self, field_force_fn, box, mass, time_step, respa_inner=1, topology=None,
-                 thermostat=None, n_b=1, fused=True, force_out=None):
+                 thermostat=None, n_b=1, fused=True, force_out=None, cta=1):
         self.field_force_fn = field_force_fn
         self.box = box
         self.mass = float(mass)
@@ -121,6 +121,8 @@ class RespaMD:
         self.fast = None
         self.bonded_results = {}
         self.fused = bool(fused)
+        self.cta = cta                  # term evaluation of the fused kernel: 1 = once per CTA (measured
+                                        # fastest at C4, profiles/r1h_md_bench.json), 0 = per particle
         self.force_out = force_out      # optional [bond, angle, dihedral] (N,3) tensors filled at the
         self._x_alt = None              # end of every outer step by the fused path
 
@@ -152,6 +154,8 @@ class RespaMD:
         if self.topology is not None and self.fused:
             self._fused_inner(positions, velocities)
         else:
+            if self.topology is not None and self.topology._cta not in (None, 0):
+                self.topology.set_cta(0)     # the separate kernels are fastest per particle
             fast = self.fast_forces(positions) if self.fast is None else [f for f in self.fast if f is not None]
             for _ in range(self.inner):                                                  # main.py:829-893
                 kick_drift(velocities, positions, fast, self.mass, self.dt, self.dt, self.box)
@@ -176,10 +180,10 @@ class RespaMD:
         cur, alt = positions, self._x_alt
         for i in range(self.inner):
             topo.inner_step(cur, alt, velocities, self.box, self.mass, self.dt, 1 if i == 0 else 2, self.dt,
-                            want_energies=False)
+                            want_energies=False, cta=self.cta)
             cur, alt = alt, cur
         res = topo.inner_step(cur, None, velocities, self.box, self.mass, self.dt, 1, 0.0,
-                              force_out=self.force_out, want_energies=True)
+                              force_out=self.force_out, want_energies=True, cta=self.cta)
         self.bonded_results = {k + 2: res[k] for k in range(3) if topo.n_terms[k] > 0}
         if cur is not positions:
             positions.copy_(cur)

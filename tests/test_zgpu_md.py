@@ -378,7 +378,7 @@ def test_cta_cooperative_evaluation_matches_the_per_particle_result(real):
     out = {}
     for cta in (0, 1, 2):
         topo.set_cta(cta)
-        md = RespaMD(lambda x: [], box, 72.0, 0.004, respa_inner=4, topology=topo)
+        md = RespaMD(lambda x: [], box, 72.0, 0.004, respa_inner=4, topology=topo, cta=cta)
         xd, vd = dev(r, real), dev(v, real)
         for _ in range(3):
             md.step(xd, vd, [])

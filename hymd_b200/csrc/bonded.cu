@@ -22,6 +22,7 @@ struct hymd_bonded {
     int max_terms[3];
     size_t cta_smem;             // dynamic shared memory of inner_step_cta_kernel
     int use_cta;                 // HYMD_B200_BONDED_CTA / hymd_bonded_set_cta: 0, 1 or 2
+    int tile;                    // particles per CTA of the cooperative kernels (HYMD_B200_BONDED_TILE)
     double* out12;               // scratch result of the fused kernels
     double* partial;             // [max_blocks][4] block partials of {energy, pr_x, pr_y, pr_z}
     int max_blocks;
@@ -108,22 +109,21 @@ __global__ void __launch_bounds__(BONDED_THREADS) inner_step_kernel(
 template <typename real>
 __global__ void __launch_bounds__(BONDED_THREADS) inner_step_cta_kernel(
     const real* __restrict__ x_in, real* __restrict__ x_out, real* __restrict__ vel, long long n, Vec3d box,
-    TermLists t, CtaLists c, real mass, real half_dt, int n_kicks, real dt, ForceOut fo,
+    TermLists t, CtaLists c, int tile, real mass, real half_dt, int n_kicks, real dt, ForceOut fo,
     double* __restrict__ partial) {
     extern __shared__ double sm[];
     const long long cta = blockIdx.x;
-    const long long p0 = cta * BONDED_THREADS;
-    const long long p1 = p0 + BONDED_THREADS < n ? p0 + BONDED_THREADS : n;
+    const long long p0 = cta * tile;                  // tile = 128 * (particles per thread)
+    const long long p1 = p0 + tile < n ? p0 + tile : n;
     double v[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) v[k] = 0.0;
     cta_eval_terms<real>((int)threadIdx.x, BONDED_THREADS, cta, p0, p1, x_in, box, t, c, sm, v);
     __syncthreads();
-    const long long p = p0 + threadIdx.x;
-    if (p < n) {
+    real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
+    for (long long p = p0 + threadIdx.x; p < p1; p += BONDED_THREADS) {
         BondAcc acc[3];
         cta_gather_particle(p, t, c, sm, acc);
-        real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
         finish_particle<real>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);
     }
 #pragma unroll
@@ -147,30 +147,30 @@ __global__ void __launch_bounds__(BONDED_THREADS) inner_step_cta_kernel(
 template <typename real>
 __global__ void __launch_bounds__(BONDED_THREADS) inner_step_cta2_kernel(
     const real* __restrict__ x_in, real* __restrict__ x_out, real* __restrict__ vel, long long n, Vec3d box,
-    TermLists t, CtaLists c, CtaRecs rc, real mass, real half_dt, int n_kicks, real dt, ForceOut fo,
+    TermLists t, CtaLists c, CtaRecs rc, int tile, real mass, real half_dt, int n_kicks, real dt, ForceOut fo,
     double* __restrict__ partial) {
     extern __shared__ double sm[];
-    real* tile = (real*)sm;                                            // [BONDED_THREADS * 3] reals
-    double* vecs = sm + (BONDED_THREADS * 3 * sizeof(real) + 7) / 8;
+    real* own_pos = (real*)sm;                                         // [tile * 3] reals
+    double* vecs = sm + ((size_t)tile * 3 * sizeof(real) + 7) / 8;
     const long long cta = blockIdx.x;
-    const long long p0 = cta * BONDED_THREADS;
-    const long long p1 = p0 + BONDED_THREADS < n ? p0 + BONDED_THREADS : n;
+    const long long p0 = cta * tile;
+    const long long p1 = p0 + tile < n ? p0 + tile : n;
     const int n_own = (int)(p1 - p0);
-    for (int i = threadIdx.x; i < 3 * n_own; i += BONDED_THREADS) tile[i] = x_in[3 * p0 + i];
+    for (int i = threadIdx.x; i < 3 * n_own; i += BONDED_THREADS) own_pos[i] = x_in[3 * p0 + i];
     __syncthreads();
-    const PosTile<real> x = {x_in, tile, p0, p1};
-    const long long p = p0 + threadIdx.x;
-    RefBounds rb;
-    if (p < n) rb = ref_bounds(p, t);          // in flight during phase 1
+    const PosTile<real> x = {x_in, own_pos, p0, p1};
+    const long long first = p0 + threadIdx.x;
+    RefBounds rb0;
+    if (first < p1) rb0 = ref_bounds(first, t);     // in flight during phase 1
     double v[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) v[k] = 0.0;
     cta2_eval_terms<real>((int)threadIdx.x, BONDED_THREADS, cta, p0, p1, x, box, t, c, rc, vecs, v);
     __syncthreads();
-    if (p < n) {
+    real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
+    for (long long p = first; p < p1; p += BONDED_THREADS) {
         BondAcc acc[3];
-        cta_gather_bounds(rb, c, vecs, acc);
-        real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
+        cta_gather_bounds(p == first ? rb0 : ref_bounds(p, t), c, vecs, acc);
         finish_particle<real>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);
     }
 #pragma unroll
@@ -242,7 +242,7 @@ static int upload_kind(hymd_bonded* b, int kind, long long n_terms, int slots,
     for (long long t = 0; t < n_terms; ++t)
         for (int s = 0; s < slots; ++s) idx[(size_t)4 * t + s] = index[s][t];
     std::vector<uint32_t> cta_start, cta_terms, lrefs;
-    build_cta_lists(b->n_particles, n_terms, slots, index, BONDED_THREADS, start, cta_start, cta_terms, lrefs,
+    build_cta_lists(b->n_particles, n_terms, slots, index, b->tile, start, cta_start, cta_terms, lrefs,
                     b->max_terms[kind]);
     HYMD_CHECK(to_device(&b->cta_start[kind], cta_start.data(), cta_start.size()));
     HYMD_CHECK(to_device(&b->cta_terms[kind], cta_terms.data(), cta_terms.size()));
@@ -289,7 +289,8 @@ static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x
                         double mass, double kick_dt, int n_kicks, double drift_dt, void* const* d_force_out,
                         double* d_out, cudaStream_t s) {
     const long long n = b->n_particles;
-    const int blocks = (int)((n + BONDED_THREADS - 1) / BONDED_THREADS);
+    const int per_cta = b->use_cta ? b->tile : BONDED_THREADS;
+    const int blocks = (int)((n + per_cta - 1) / per_cta);
     TermLists t;
     CtaLists c;
     for (int k = 0; k < 3; ++k) {
@@ -306,12 +307,12 @@ static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x
             CtaRecs rc;
             rc.rec[0] = b->rec[0];
             rc.rec[1] = b->rec[1];
-            inner_step_cta2_kernel<real><<<blocks, BONDED_THREADS, b->cta_smem + BONDED_THREADS * 3 * sizeof(real) + 8, s>>>(
-                x_in, x_out, vel, n, box, t, c, rc, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt,
+            inner_step_cta2_kernel<real><<<blocks, BONDED_THREADS, b->cta_smem + (size_t)b->tile * 3 * sizeof(real) + 8, s>>>(
+                x_in, x_out, vel, n, box, t, c, rc, b->tile, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt,
                 fo, b->partial);
         } else if (b->use_cta)
             inner_step_cta_kernel<real><<<blocks, BONDED_THREADS, b->cta_smem, s>>>(
-                x_in, x_out, vel, n, box, t, c, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt, fo,
+                x_in, x_out, vel, n, box, t, c, b->tile, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt, fo,
                 b->partial);
         else
             inner_step_kernel<real><<<blocks, BONDED_THREADS, 0, s>>>(x_in, x_out, vel, n, box, t, (real)mass,
@@ -331,11 +332,11 @@ static int set_cta(hymd_bonded* b, int enable) {
     if (b->cta_smem > CTA_SMEM_LIMIT) {
         set_error("CTA-cooperative bonded evaluation needs %zu bytes of shared memory per CTA (limit %zu): "
                   "a block of %d consecutive particles takes part in too many terms", b->cta_smem,
-                  CTA_SMEM_LIMIT, BONDED_THREADS);
+                  CTA_SMEM_LIMIT, b->tile);
         return HYMD_ERR_CAPACITY;
     }
     if (b->cta_smem + 4096 > 48 * 1024) {
-        const int bytes = (int)b->cta_smem + BONDED_THREADS * 3 * (int)sizeof(double) + 8;
+        const int bytes = (int)b->cta_smem + b->tile * 3 * (int)sizeof(double) + 8;
         HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -371,6 +372,16 @@ int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const
     hymd_bonded* b = new hymd_bonded();
     memset(b, 0, sizeof(*b));
     b->n_particles = n_particles;
+    b->tile = BONDED_THREADS;
+    if (const char* env = getenv("HYMD_B200_BONDED_TILE")) {
+        const int tile = atoi(env);
+        if (tile < BONDED_THREADS || tile > 2048 || tile % BONDED_THREADS != 0) {
+            set_error("HYMD_B200_BONDED_TILE = %s: expected a multiple of %d up to 2048", env, BONDED_THREADS);
+            delete b;
+            return HYMD_ERR_INVALID;
+        }
+        b->tile = tile;
+    }
     int st = HYMD_OK;
     {
         std::vector<double> par((size_t)n2 * 2);

@@ -3,6 +3,8 @@
 // so tests/test_native_host_check.py can compare the device arithmetic (term lists, slot logic,
 // minimum image, cosine series, CSVR scale) with the oracle in the GPU-less container.  Built by the
 // test with g++; never linked into libhymd_b200.so and never used by the product.
+#include <stdlib.h>
+
 #include "../../hymd_b200/csrc/bonded.cuh"
 #include "../../hymd_b200/csrc/md.cuh"
 
@@ -99,9 +101,10 @@ struct HostBonded {
     std::vector<TermRec> rec[2];
     int max_terms[3];
     int use_cta;
+    int tile;                   // particles per CTA (HYMD_B200_BONDED_TILE, default BONDED_THREADS = 128)
     long long launches;
 };
-constexpr int HOST_CTA = 128;   // BONDED_THREADS of csrc/bonded.cu
+constexpr int HOST_THREADS = 128;   // BONDED_THREADS of csrc/bonded.cu
 
 static bool host_upload(HostBonded* b, int kind, long long nt, int slots, const int32_t* const* index,
                         const double* par, size_t per_term) {
@@ -110,7 +113,7 @@ static bool host_upload(HostBonded* b, int kind, long long nt, int slots, const 
     for (long long t = 0; t < nt; ++t)
         for (int s = 0; s < slots; ++s) b->idx[kind][4 * t + s] = index[s][t];
     b->par[kind].assign(par, par + (size_t)nt * per_term);
-    build_cta_lists(b->n, nt, slots, index, HOST_CTA, b->start[kind], b->cta_start[kind], b->cta_terms[kind],
+    build_cta_lists(b->n, nt, slots, index, b->tile, b->start[kind], b->cta_start[kind], b->cta_terms[kind],
                     b->lrefs[kind], b->max_terms[kind]);
     if (kind < 2) build_cta_records(b->cta_terms[kind], b->idx[kind].data(), b->par[kind].data(), b->rec[kind]);
     return true;
@@ -127,6 +130,11 @@ extern "C" int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t
     b->n = n_particles;
     b->launches = 0;
     b->use_cta = 0;
+    b->tile = HOST_THREADS;
+    if (const char* env = getenv("HYMD_B200_BONDED_TILE")) {
+        b->tile = atoi(env);
+        if (b->tile < HOST_THREADS || b->tile > 2048 || b->tile % HOST_THREADS != 0) { delete b; return -1; }
+    }
     std::vector<double> p2((size_t)n2 * 2), p3((size_t)n3 * 2);
     for (int64_t t = 0; t < n2; ++t) { p2[2 * t] = r0_2[t]; p2[2 * t + 1] = k_2[t]; }
     for (int64_t t = 0; t < n3; ++t) { p3[2 * t] = t0_3[t]; p3[2 * t + 1] = k_3[t]; }
@@ -252,12 +260,13 @@ static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, r
     if (b->use_cta) {
         // the kernel's structure: per CTA, phase 1 (threads stride over the CTA's terms), barrier, phase 2
         std::vector<double> sm((size_t)3 * c.max_terms[0] + 6 * c.max_terms[1] + 12 * c.max_terms[2] + 1);
-        const long long n_cta = (b->n + HOST_CTA - 1) / HOST_CTA;
+        const int HOST_CTA = HOST_THREADS;      // threads striding over the CTA's terms
+        const long long n_cta = (b->n + b->tile - 1) / b->tile;
         for (long long cta = 0; cta < n_cta; ++cta) {
-            const long long p0 = cta * HOST_CTA, p1 = p0 + HOST_CTA < b->n ? p0 + HOST_CTA : b->n;
+            const long long p0 = cta * b->tile, p1 = p0 + b->tile < b->n ? p0 + b->tile : b->n;
             for (size_t i = 0; i < sm.size(); ++i) sm[i] = -777.0;      // stale data must never be read
             if (b->use_cta == 2) {      // mode 2: own positions staged, inline records
-                std::vector<real> tile((size_t)3 * HOST_CTA, (real)-555);
+                std::vector<real> tile((size_t)3 * b->tile, (real)-555);
                 for (long long i = 0; i < 3 * (p1 - p0); ++i) tile[i] = x_in[3 * p0 + i];
                 const PosTile<real> xt = {x_in, tile.data(), p0, p1};
                 CtaRecs rc;

@@ -92,6 +92,7 @@ def test_fused_inner_step(emulated, real):
     emulated.test_fused_inner_step_equals_separate_launches(real)
 
 
+@pytest.mark.parametrize("tile", [128, 256, 512])
 @pytest.mark.parametrize("real", [np.float32, np.float64])
-def test_cta_cooperative(emulated, real):
-    emulated.test_cta_cooperative_evaluation_matches_the_per_particle_result(real)
+def test_cta_cooperative(emulated, real, tile, monkeypatch):
+    emulated.test_cta_cooperative_evaluation_matches_the_per_particle_result(real, tile, monkeypatch)

@@ -318,14 +318,17 @@ def test_fused_inner_step_equals_separate_launches(real):
         assert out[True][2][k] == pytest.approx(out[False][2][k], rel=1e-6 if real == np.float32 else 1e-11)
 
 
+@pytest.mark.parametrize("tile", [128, 512])
 @pytest.mark.parametrize("real", [np.float32, np.float64])
-def test_cta_cooperative_evaluation_matches_the_per_particle_result(real):
+def test_cta_cooperative_evaluation_matches_the_per_particle_result(real, tile, monkeypatch):
     """hymd_bonded_set_cta(1): each CTA evaluates every term touching its 128 particles once into shared
     memory and the particles gather their slots.  Same additions in the same order => the forces equal the
     per-particle kernels' up to FMA contraction across the inlined term evaluation (bit-identical when
     the same source runs on the CPU, tests/test_md_host_emulation.py); energies agree to rounding.  Branched molecules (DPPC
     topology of the reference's fixture), chains straddling CTA boundaries, all three kinds, a solvent
-    tail without terms; then a fused rRESPA run with the switch on."""
+    tail without terms; then a fused rRESPA run with the switch on.  ``tile`` = particles per CTA
+    (HYMD_B200_BONDED_TILE: 512 = four particles per thread)."""
+    monkeypatch.setenv("HYMD_B200_BONDED_TILE", str(tile))
     from hymd_b200.force import BondedTopology
     from hymd_b200.md import RespaMD
     rng = np.random.default_rng(77)

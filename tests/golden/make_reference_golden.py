@@ -289,9 +289,73 @@ def field(out):
         out[pre + "/pressure"] = np.asarray(p, dtype=np.float64)
 
 
+GPE_CASES = [
+    dict(name="gpe3", names=["A", "B", "W"], frac=[0.25, 0.25, 0.5], n=900, mesh=[10, 12, 8],
+         box=[3.5, 4.0, 3.0], sigma=0.5, kappa=0.05, chi=[("A", "B", 15.0), ("A", "W", 25.0)],
+         type_charges=[1.0, -1.0, 0.0], dielectric_type=[5.0, 10.0, 80.0], pol_mixing=0.6, conv_crit=1e-6),
+    dict(name="gpe2_odd", names=["A", "W"], frac=[0.4, 0.6], n=700, mesh=[9, 8, 11],
+         box=[3.0, 3.2, 3.4], sigma=0.45, kappa=0.05, chi=[("A", "W", 10.0)],
+         type_charges=[0.5, -0.3333333333333333], dielectric_type=[20.0, 60.0], pol_mixing=0.5,
+         conv_crit=1e-7),
+]
+
+
+def gpe(out):
+    """update_field_force_q_GPE / compute_field_energy_q_GPE (field.py:964-1112, 706-760) of the real
+    hymd/field.py over the pmesh stand-in: groundwork for SURVEY.md section 8 row f3."""
+    fd = rl.ref("field")
+    hm = rl.ref("hamiltonian")
+    pmesh = sys.modules["pmesh.pm"]
+    comm = sys.modules["mpi4py"].MPI.COMM_WORLD
+    from hymd_b200.config import Chi, Config
+    for ci, case in enumerate(GPE_CASES):
+        rng = np.random.default_rng(4300 + ci)
+        n, T = case["n"], len(case["names"])
+        cfg = Config(mesh_size=case["mesh"], sigma=case["sigma"], kappa=case["kappa"], box_size=case["box"],
+                     hamiltonian="DefaultWithChi", chi=[Chi(*c) for c in case["chi"]],
+                     coulombtype="PIC_Spectral_GPE", dtype=np.float64)
+        cfg.finalize(case["names"], n_particles=n)
+        ns = types.SimpleNamespace(**{k: getattr(cfg, k) for k in cfg.__dataclass_fields__})
+        ns.coulomb_constant, ns.gas_constant = Config.coulomb_constant, Config.gas_constant
+        ns.box_size = np.asarray(cfg.box_size, dtype=np.float64)
+        ns.type_charges = np.array(case["type_charges"])
+        ns.dielectric_type = np.array(case["dielectric_type"])
+        ns.pol_mixing, ns.conv_crit = case["pol_mixing"], case["conv_crit"]
+        types_ = rng.choice(T, size=n, p=case["frac"]).astype(np.int64)
+        pos = rng.random((n, 3)) * ns.box_size
+        charges = ns.type_charges[types_].astype(np.float64)
+        h = hm.get_hamiltonian(ns)
+        pm, field_list, elec_common, coulomb = fd.initialize_pm(pmesh, ns, comm=comm)
+        phi, phi_fourier, force_on_grid, v_ext_fourier, v_ext, phi_transfer, phi_laplacian = field_list
+        phi_q, phi_q_fourier, psi, elec_field = elec_common
+        (phi_eps, phi_eps_fourier, phi_eta, phi_eta_fourier, phi_pol, phi_pol_prev, elec_dot,
+         elec_field_contrib, Vbar_elec, Vbar_elec_fourier, force_mesh_elec, force_mesh_elec_fourier) = coulomb
+        layouts = [pm.decompose(pos[types_ == t]) for t in range(T)]
+        fd.update_field(phi, phi_laplacian, phi_transfer, layouts, force_on_grid, h, pm, pos, types_, ns,
+                        v_ext, phi_fourier, v_ext_fourier, ns.m)
+
+        def conv_fun(comm_, diffmesh):        # main.py:158-163 (default "max_diff")
+            return comm_.allreduce(np.max(diffmesh), op="MAX")
+        elec_forces = np.zeros((n, 3))
+        Vbar, eps, dot = fd.update_field_force_q_GPE(
+            conv_fun, phi, types_, charges, phi_q, phi_q_fourier, phi_eps, phi_eps_fourier, phi_eta,
+            phi_eta_fourier, phi_pol_prev, phi_pol, elec_field, elec_forces, elec_field_contrib, psi, Vbar_elec,
+            Vbar_elec_fourier, force_mesh_elec, force_mesh_elec_fourier, h, pm.decompose(pos), layouts, pm,
+            pos, ns, comm=comm)
+        energy = fd.compute_field_energy_q_GPE(ns, eps, 0.0, dot, comm=comm)
+        pre = "gpe/" + case["name"]
+        out[pre + "/pos"], out[pre + "/types"], out[pre + "/charges"] = pos, types_, charges
+        out[pre + "/phi"] = np.stack([np.asarray(x) for x in phi])
+        out[pre + "/elec_forces"] = elec_forces
+        out[pre + "/psi"], out[pre + "/phi_eps"] = np.asarray(psi), np.asarray(eps)
+        out[pre + "/elec_dot"] = np.asarray(dot)
+        out[pre + "/Vbar_elec"] = np.stack([np.asarray(x) for x in Vbar])
+        out[pre + "/energy"] = np.float64(energy)
+
+
 def main():
     for fn, name in ((bonded, "bonded_golden.npz"), (thermostat, "thermostat_golden.npz"),
-                     (field, "field_golden.npz")):
+                     (field, "field_golden.npz"), (gpe, "gpe_golden.npz")):
         out = {}
         fn(out)
         np.savez_compressed(os.path.join(HERE, name), **out)

@@ -168,8 +168,10 @@ class BondedTopology:
 
 
 # topology cache: keyed by the identity and length of the caller's index arrays, so that the
-# reference's call pattern (same prepare_bonds arrays every inner step) uploads once
+# reference's call pattern (same prepare_bonds arrays every inner step) uploads once.  An entry dies
+# with its arrays (weak references); at most _CACHE_MAX device topologies are kept alive.
 _cache = {}
+_CACHE_MAX = 6
 
 
 def _topology(kind, n_particles, device, arrays, build):
@@ -179,11 +181,11 @@ def _topology(kind, n_particles, device, arrays, build):
         return hit[0]
     topo = build()
     try:
-        refs = [weakref.ref(a) for a in arrays]
+        refs = [weakref.ref(a, lambda _r, k=key: _cache.pop(k, None)) for a in arrays]
     except TypeError:      # lists cannot be weak-referenced: no caching
         return topo
-    if len(_cache) > 64:
-        _cache.clear()
+    while len(_cache) >= _CACHE_MAX:
+        _cache.pop(next(iter(_cache)))
     _cache[key] = (topo, refs)
     return topo
 

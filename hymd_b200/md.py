@@ -1,15 +1,15 @@
-"""Field-only MD stepping around the field-force cycle (the caller side of the hot path).
+"""MD stepping around the field-force cycle (the caller side of the hot path).
 
-``hymd/integrator.py:9-75`` (velocity Verlet) and the outer rRESPA skeleton of
-``hymd/main.py:801-1148`` restated for device tensors, with only the particle-field forces
-switched on (no bonds / angles / thermostat): kick by the field forces over the outer step
-``respa_inner * time_step``, ``respa_inner`` drifts of ``time_step`` with periodic wrapping
-(``main.py:836-837``), field-force cycle (``main.py:976-1004``), second kick
-(``main.py:1144-1148``).  It exists to drive the NVE energy-conservation check of the
-field-force path (``tools/nve_drift.py``, ``tests/test_gpu_nve.py``); bonded forces,
-thermostat, barostat and I/O stay with the caller.
+``hymd/integrator.py:9-75`` (velocity Verlet) and the outer rRESPA loop of ``hymd/main.py:801-1169``:
 
-Every function works on torch tensors (GPU path) and on numpy arrays (oracle path) alike.
+* :class:`FieldOnlyMD` -- only the particle-field forces switched on (no bonds / angles / thermostat),
+  on torch tensors or numpy arrays alike; drives the NVE energy-conservation check of the field-force
+  path (``tools/nve_drift.py``, ``tests/test_gpu_nve.py``) with the CUDA path and with the oracle.
+* :func:`kick_drift` and :class:`RespaMD` -- the full outer step with
+  positions and velocities resident on the GPU: outer kicks by the slow (field, electrostatic) forces,
+  ``respa_inner`` inner steps of bonded forces + kick + drift + wrap as fused kernels
+  (``hymd_bonded_inner_step``, ``hymd_md_kick_drift``), the field-force cycle, and the thermostat
+  (``hymd_b200.thermostat``).  Barostat, PLUMED and I/O stay with the caller.
 """
 from __future__ import annotations
 

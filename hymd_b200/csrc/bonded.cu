@@ -23,6 +23,7 @@ struct hymd_bonded {
     size_t cta_smem;             // dynamic shared memory of inner_step_cta_kernel
     int use_cta;                 // HYMD_B200_BONDED_CTA / hymd_bonded_set_cta: 0, 1 or 2
     int tile;                    // particles per CTA of the cooperative kernels (HYMD_B200_BONDED_TILE)
+    int occ;                     // HYMD_B200_BONDED_OCC: 0 (default, no register limit), 6 or 8 resident CTAs per SM
     double* out12;               // scratch result of the fused kernels
     double* partial;             // [max_blocks][4] block partials of {energy, pr_x, pr_y, pr_z}
     int max_blocks;
@@ -106,8 +107,10 @@ __global__ void __launch_bounds__(BONDED_THREADS) inner_step_kernel(
 
 // Same step, CTA-cooperative term evaluation (bonded.cuh): every term touching the CTA's 128
 // particles is evaluated once into shared memory, then each particle gathers its slots.
-template <typename real>
-__global__ void __launch_bounds__(BONDED_THREADS) inner_step_cta_kernel(
+// MINB = resident CTAs per SM the register allocation is limited for (0: no limit, 94 registers,
+// 5 CTAs; 6: 80 registers; 8: 64 registers with spills) -- HYMD_B200_BONDED_OCC, to be measured.
+template <typename real, int MINB>
+__global__ void __launch_bounds__(BONDED_THREADS, MINB) inner_step_cta_kernel(
     const real* __restrict__ x_in, real* __restrict__ x_out, real* __restrict__ vel, long long n, Vec3d box,
     TermLists t, CtaLists c, int tile, real mass, real half_dt, int n_kicks, real dt, ForceOut fo,
     double* __restrict__ partial) {
@@ -310,10 +313,16 @@ static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x
             inner_step_cta2_kernel<real><<<blocks, BONDED_THREADS, b->cta_smem + (size_t)b->tile * 3 * sizeof(real) + 8, s>>>(
                 x_in, x_out, vel, n, box, t, c, rc, b->tile, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt,
                 fo, b->partial);
-        } else if (b->use_cta)
-            inner_step_cta_kernel<real><<<blocks, BONDED_THREADS, b->cta_smem, s>>>(
-                x_in, x_out, vel, n, box, t, c, b->tile, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt, fo,
-                b->partial);
+        } else if (b->use_cta) {
+#define HYMD_CTA_LAUNCH(MINB)                                                                              \
+    inner_step_cta_kernel<real, MINB><<<blocks, BONDED_THREADS, b->cta_smem, s>>>(                         \
+        x_in, x_out, vel, n, box, t, c, b->tile, (real)mass, (real)(0.5 * kick_dt), n_kicks, (real)drift_dt, fo, \
+        b->partial)
+            if (b->occ == 8) HYMD_CTA_LAUNCH(8);
+            else if (b->occ == 6) HYMD_CTA_LAUNCH(6);
+            else HYMD_CTA_LAUNCH(0);
+#undef HYMD_CTA_LAUNCH
+        }
         else
             inner_step_kernel<real><<<blocks, BONDED_THREADS, 0, s>>>(x_in, x_out, vel, n, box, t, (real)mass,
                                                                       (real)(0.5 * kick_dt), n_kicks,
@@ -337,8 +346,12 @@ static int set_cta(hymd_bonded* b, int enable) {
     }
     if (b->cta_smem + 4096 > 48 * 1024) {
         const int bytes = (int)b->cta_smem + b->tile * 3 * (int)sizeof(double) + 8;
-        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<float, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<double, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta2_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
@@ -381,6 +394,15 @@ int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const
             return HYMD_ERR_INVALID;
         }
         b->tile = tile;
+    }
+    b->occ = 0;
+    if (const char* env = getenv("HYMD_B200_BONDED_OCC")) {
+        b->occ = atoi(env);
+        if (b->occ != 0 && b->occ != 6 && b->occ != 8) {
+            set_error("HYMD_B200_BONDED_OCC = %s: expected 0, 6 or 8", env);
+            delete b;
+            return HYMD_ERR_INVALID;
+        }
     }
     int st = HYMD_OK;
     {

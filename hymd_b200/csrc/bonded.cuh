@@ -396,45 +396,44 @@ __host__ __device__ inline void cta_eval_terms(int tid, int nthreads, long long 
     double* sm2 = sm;
     double* sm3 = sm2 + (long long)c.max_terms[0] * CTA_DOUBLES[0];
     double* sm4 = sm3 + (long long)c.max_terms[1] * CTA_DOUBLES[1];
-    if (t.n_terms[0]) {
-        const uint32_t b = c.cta_start[0][cta], e = c.cta_start[0][cta + 1];
-        for (uint32_t i = b + tid; i < e; i += nthreads) {
-            const long long term = c.cta_terms[0][i];
+    // one flat work list over the three kinds, so that a CTA with few terms of each kind (chains and
+    // solvent interleave in domain_decomposition order) still keeps all of its threads busy in one round
+    const uint32_t b2 = t.n_terms[0] ? c.cta_start[0][cta] : 0u, n2 = t.n_terms[0] ? c.cta_start[0][cta + 1] - b2 : 0u;
+    const uint32_t b3 = t.n_terms[1] ? c.cta_start[1][cta] : 0u, n3 = t.n_terms[1] ? c.cta_start[1][cta + 1] - b3 : 0u;
+    const uint32_t b4 = t.n_terms[2] ? c.cta_start[2][cta] : 0u, n4 = t.n_terms[2] ? c.cta_start[2][cta + 1] - b4 : 0u;
+    for (uint32_t j = (uint32_t)tid; j < n2 + n3 + n4; j += (uint32_t)nthreads) {
+        if (j < n2) {
+            const uint32_t i = j;
+            const long long term = c.cta_terms[0][b2 + i];
             const int32_t* ix = t.idx[0] + 4 * term;
             Vec3d fa, pr;
             double en;
             bond_eval(x, box, ix[0], ix[1], t.par[0][2 * term], t.par[0][2 * term + 1], fa, en, pr);
-            double* o = sm2 + (long long)(i - b) * 3;
+            double* o = sm2 + (long long)i * 3;
             o[0] = fa.x; o[1] = fa.y; o[2] = fa.z;
             if (ix[0] >= p0 && ix[0] < p1) { own[0] += en; own[1] += pr.x; own[2] += pr.y; own[3] += pr.z; }
-        }
-    }
-    if (t.n_terms[1]) {
-        const uint32_t b = c.cta_start[1][cta], e = c.cta_start[1][cta + 1];
-        for (uint32_t i = b + tid; i < e; i += nthreads) {
-            const long long term = c.cta_terms[1][i];
+        } else if (j < n2 + n3) {
+            const uint32_t i = j - n2;
+            const long long term = c.cta_terms[1][b3 + i];
             const int32_t* ix = t.idx[1] + 4 * term;
             Vec3d fa = {0.0, 0.0, 0.0}, fc = {0.0, 0.0, 0.0}, pr = {0.0, 0.0, 0.0};
             double en = 0.0;
             const bool ok = angle_eval(x, box, ix[0], ix[1], ix[2], t.par[1][2 * term], t.par[1][2 * term + 1],
                                        fa, fc, en, pr);
-            double* o = sm3 + (long long)(i - b) * 6;
+            double* o = sm3 + (long long)i * 6;
             // an invalid angle is marked with a NaN in the first slot: the particle phase skips it,
             // exactly like the per-particle path skips the additions
             o[0] = ok ? fa.x : nan(""); o[1] = fa.y; o[2] = fa.z; o[3] = fc.x; o[4] = fc.y; o[5] = fc.z;
             if (ok && ix[0] >= p0 && ix[0] < p1) { own[4] += en; own[5] += pr.x; own[6] += pr.y; own[7] += pr.z; }
-        }
-    }
-    if (t.n_terms[2]) {
-        const uint32_t b = c.cta_start[2][cta], e = c.cta_start[2][cta + 1];
-        for (uint32_t i = b + tid; i < e; i += nthreads) {
-            const long long term = c.cta_terms[2][i];
+        } else {
+            const uint32_t i = j - n2 - n3;
+            const long long term = c.cta_terms[2][b4 + i];
             const int32_t* ix = t.idx[2] + 4 * term;
             Vec3d out[4];
             double en;
             dihedral_eval(x, box, ix[0], ix[1], ix[2], ix[3], t.par[2] + (long long)DIH_ROWS * DIH_COLS * term,
                           t.dih_type[term], out, en);
-            double* o = sm4 + (long long)(i - b) * 12;
+            double* o = sm4 + (long long)i * 12;
             for (int s = 0; s < 4; ++s) { o[3 * s] = out[s].x; o[3 * s + 1] = out[s].y; o[3 * s + 2] = out[s].z; }
             if (ix[0] >= p0 && ix[0] < p1) own[8] += en;
         }
@@ -473,40 +472,37 @@ __host__ __device__ inline void cta2_eval_terms(int tid, int nthreads, long long
     double* sm2 = sm;
     double* sm3 = sm2 + (long long)c.max_terms[0] * CTA_DOUBLES[0];
     double* sm4 = sm3 + (long long)c.max_terms[1] * CTA_DOUBLES[1];
-    if (t.n_terms[0]) {
-        const uint32_t b = c.cta_start[0][cta], e = c.cta_start[0][cta + 1];
-        for (uint32_t i = b + tid; i < e; i += nthreads) {
-            const TermRec r = rc.rec[0][i];
+    const uint32_t b2 = t.n_terms[0] ? c.cta_start[0][cta] : 0u, n2 = t.n_terms[0] ? c.cta_start[0][cta + 1] - b2 : 0u;
+    const uint32_t b3 = t.n_terms[1] ? c.cta_start[1][cta] : 0u, n3 = t.n_terms[1] ? c.cta_start[1][cta + 1] - b3 : 0u;
+    const uint32_t b4 = t.n_terms[2] ? c.cta_start[2][cta] : 0u, n4 = t.n_terms[2] ? c.cta_start[2][cta + 1] - b4 : 0u;
+    for (uint32_t j = (uint32_t)tid; j < n2 + n3 + n4; j += (uint32_t)nthreads) {
+        if (j < n2) {
+            const uint32_t i = j;
+            const TermRec r = rc.rec[0][b2 + i];
             Vec3d fa, pr;
             double en;
             bond_eval(x, box, r.i[0], r.i[1], r.p[0], r.p[1], fa, en, pr);
-            double* o = sm2 + (long long)(i - b) * 3;
+            double* o = sm2 + (long long)i * 3;
             o[0] = fa.x; o[1] = fa.y; o[2] = fa.z;
             if (r.i[0] >= p0 && r.i[0] < p1) { own[0] += en; own[1] += pr.x; own[2] += pr.y; own[3] += pr.z; }
-        }
-    }
-    if (t.n_terms[1]) {
-        const uint32_t b = c.cta_start[1][cta], e = c.cta_start[1][cta + 1];
-        for (uint32_t i = b + tid; i < e; i += nthreads) {
-            const TermRec r = rc.rec[1][i];
+        } else if (j < n2 + n3) {
+            const uint32_t i = j - n2;
+            const TermRec r = rc.rec[1][b3 + i];
             Vec3d fa = {0.0, 0.0, 0.0}, fc = {0.0, 0.0, 0.0}, pr = {0.0, 0.0, 0.0};
             double en = 0.0;
             const bool ok = angle_eval(x, box, r.i[0], r.i[1], r.i[2], r.p[0], r.p[1], fa, fc, en, pr);
-            double* o = sm3 + (long long)(i - b) * 6;
+            double* o = sm3 + (long long)i * 6;
             o[0] = ok ? fa.x : nan(""); o[1] = fa.y; o[2] = fa.z; o[3] = fc.x; o[4] = fc.y; o[5] = fc.z;
             if (ok && r.i[0] >= p0 && r.i[0] < p1) { own[4] += en; own[5] += pr.x; own[6] += pr.y; own[7] += pr.z; }
-        }
-    }
-    if (t.n_terms[2]) {
-        const uint32_t b = c.cta_start[2][cta], e = c.cta_start[2][cta + 1];
-        for (uint32_t i = b + tid; i < e; i += nthreads) {
-            const long long term = c.cta_terms[2][i];
+        } else {
+            const uint32_t i = j - n2 - n3;
+            const long long term = c.cta_terms[2][b4 + i];
             const int32_t* ix = t.idx[2] + 4 * term;
             Vec3d out[4];
             double en;
             dihedral_eval(x, box, ix[0], ix[1], ix[2], ix[3], t.par[2] + (long long)DIH_ROWS * DIH_COLS * term,
                           t.dih_type[term], out, en);
-            double* o = sm4 + (long long)(i - b) * 12;
+            double* o = sm4 + (long long)i * 12;
             for (int s = 0; s < 4; ++s) { o[3 * s] = out[s].x; o[3 * s + 1] = out[s].y; o[3 * s + 2] = out[s].z; }
             if (ix[0] >= p0 && ix[0] < p1) own[8] += en;
         }

@@ -18,6 +18,14 @@ from .field import _allreduce, comp_laplacian, compute_field_and_kinetic_energy
 from .hamiltonian import affine_parameters
 
 
+def _host3(x):
+    """bond_pr / angle_pr as 3 host doubles (hymd_b200.force returns them as device tensors when the
+    positions live on the GPU)."""
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, dtype=np.float64).reshape(3)
+
+
 def comp_pressure(phi, phi_q, psi, hamiltonian, velocities, config, phi_fourier, phi_laplacian,
                   phi_transfer, positions, bond_pr, angle_pr, comm=None):
     pm = phi[0].pm
@@ -45,8 +53,7 @@ def comp_pressure(phi, phi_q, psi, hamiltonian, velocities, config, phi_fourier,
     p2 = dv / V * float(config.sigma) ** 2 * sums[1:4]
     # the reference adds the per-rank bonded terms and sums the whole vector over ranks; the field
     # and kinetic terms above are already global, so only the bonded inputs are reduced here
-    bonded = np.concatenate([np.asarray(bond_pr, dtype=np.float64).reshape(3),
-                             np.asarray(angle_pr, dtype=np.float64).reshape(3)])
+    bonded = np.concatenate([_host3(bond_pr), _host3(angle_pr)])
     if pm.world_size > 1:
         bonded = _allreduce(torch.as_tensor(bonded)).numpy()
     p_bond, p_angle = bonded[:3] / V, bonded[3:] / V

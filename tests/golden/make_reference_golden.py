@@ -353,9 +353,43 @@ def gpe(out):
         out[pre + "/energy"] = np.float64(energy)
 
 
+BAROSTAT_PRESSURE = np.array([3.1, -2.0, 0.4, 0.1, 0.2, 0.3, 0.01, 0.02, 0.03, -0.01, 0.0, 0.02, 0.0, 0.0, 0.0,
+                              1.7, 2.3, -0.9])        # what the patched comp_pressure returns
+
+
+def barostat(out):
+    """isotropic / semiisotropic of hymd/barostat.py (Berendsen) and hymd/barostat_scr.py (SCR) with
+    ``comp_pressure`` patched to return BAROSTAT_PRESSURE and ``initialize_pm`` patched to a marker: the
+    scaling arithmetic, the prng call order and the in-place updates of box and positions are the
+    reference's own."""
+    ip = rl.ref("input_parser")
+    mods = {"berendsen": rl.ref("barostat"), "scr": rl.ref("barostat_scr")}
+    comm = sys.modules["mpi4py"].MPI.COMM_WORLD
+    rng = np.random.default_rng(4400)
+    pos0 = rng.random((7, 3)) * np.array([5.0, 6.0, 7.0])
+    out["barostat/pressure"], out["barostat/pos0"] = BAROSTAT_PRESSURE, pos0
+    for kind, mod in mods.items():
+        mod.comp_pressure = lambda *a, **k: BAROSTAT_PRESSURE.copy()
+        mod.initialize_pm = lambda pmesh, config, comm=None: "reinitialized"
+        for fn in ("isotropic", "semiisotropic"):
+            for step, (P_L, P_N) in ((4, (1.0, 1.0)), (4, (1.0, None)), (5, (1.0, 1.0))):
+                config = ip.Config(n_steps=1, time_step=0.03, mesh_size=[8, 8, 8], sigma=0.5, kappa=0.05,
+                                   box_size=np.array([5.0, 6.0, 7.0]), respa_inner=5, n_b=2, tau_p=1.5,
+                                   target_temperature=323.0)
+                config.target_pressure = mod.Target_pressure(P_L=P_L, P_N=P_N)
+                pos = pos0.copy()
+                res, change = getattr(mod, fn)(None, "old", None, None, None, None, pos, None, config, None,
+                                               None, None, np.zeros(3), np.zeros(3), step,
+                                               np.random.default_rng(99), comm=comm)
+                pre = f"barostat/{kind}/{fn}/{step}_{P_L}_{P_N}"
+                out[pre + "/box"], out[pre + "/pos"] = np.asarray(config.box_size, dtype=np.float64), pos
+                out[pre + "/change"] = np.array([bool(change), res == "reinitialized"])
+                out[pre + "/surface_tension"] = np.float64(getattr(config, "surface_tension", None) or 0.0)
+
+
 def main():
     for fn, name in ((bonded, "bonded_golden.npz"), (thermostat, "thermostat_golden.npz"),
-                     (field, "field_golden.npz"), (gpe, "gpe_golden.npz")):
+                     (field, "field_golden.npz"), (gpe, "gpe_golden.npz"), (barostat, "barostat_golden.npz")):
         out = {}
         fn(out)
         np.savez_compressed(os.path.join(HERE, name), **out)

@@ -395,3 +395,46 @@ def test_cta_cooperative_evaluation_matches_the_per_particle_result(real, tile, 
         for k in (2, 3, 4):
             assert out[cta][2][k] == pytest.approx(out[0][2][k], rel=1e-5 if real == np.float32 else 1e-10)
     topo.set_cta(False)
+
+
+def test_barostat_rescale_then_fields_match_the_oracle_in_the_new_box():
+    """NPT step (main.py:889-935): hymd_b200.barostat.isotropic computes the pressure on the device,
+    rescales box and positions in place and tells the context the new box (hymd_ctx_set_box) instead of
+    re-running initialize_pm; the next field-force cycle must equal the oracle's in the rescaled box."""
+    import types as pytypes
+
+    from conftest import make_config
+    from gpu_common import GpuRun, OracleRun, rel_err
+    from hymd_b200 import barostat as B
+    from hymd_b200 import field as F
+    from oracle import field_oracle as fo
+    rng = np.random.default_rng(21)
+    n, mesh, box = 4000, [16, 12, 10], np.array([4.0, 5.0, 6.0], dtype=np.float32)
+    names = [("A", "B")[i % 2] for i in range(n)]
+    cfg = make_config(names, n, mesh, box, chi=[("A", "B", 15.0)], dtype=np.float64)
+    cfg.n_b, cfg.tau_p, cfg.target_pressure = 1, 0.05, pytypes.SimpleNamespace(P_L=1.0, P_N=1.0)
+    cfg.barostat = "isotropic"          # Hamiltonian._setup then keeps rho0 / a fixed (hamiltonian.py:41-47)
+    cfg.rho0 = cfg.a = n / float(np.prod(box.astype(np.float64)))
+    types_ = np.array([cfg.name_to_type_map[t] for t in names], dtype=np.int32)
+    pos = (rng.random((n, 3)) * box).astype(np.float64)
+    vel = rng.normal(scale=0.2, size=(n, 3))
+    g = GpuRun(cfg, pos, types_, compute_potential=True)
+    o = OracleRun(cfg, pos, types_)
+    bond_pr, angle_pr = np.array([1.0, -2.0, 0.5]), np.array([0.25, 0.5, -1.0])
+    p_ref = fo.comp_pressure(o.st, o.h, vel, o.cfg, bond_pr, angle_pr)
+    P = np.average(p_ref[-3:-1]) * 16.61
+    alpha = (1.0 - cfg.time_step * cfg.respa_inner * cfg.n_b / cfg.tau_p * 4.6e-5 * (1.0 - P)) ** (1 / 3)
+    assert abs(alpha - 1.0) > 1e-4            # a rescale the parity tolerance can see
+    stuff = (g.pm, None, None, None)
+    box_before = np.array(cfg.box_size, dtype=np.float64)
+    res, change = B.isotropic(None, stuff, g.phi, g.phi_q, g.psi, g.h, g.pos, dev(vel, np.float64), cfg,
+                              g.phi_fourier, g.phi_laplacian, g.phi_transfer, bond_pr, angle_pr, 3, None)
+    assert change and res is stuff
+    np.testing.assert_allclose(np.asarray(cfg.box_size, dtype=np.float64), box_before * alpha, rtol=1e-6)
+    np.testing.assert_allclose(g.pos.cpu().numpy(), pos * alpha, rtol=1e-9)
+    layouts = [g.pm.decompose(None) for _ in range(cfg.n_types)]
+    F.update_field(g.phi, g.phi_laplacian, g.phi_transfer, layouts, g.force_mesh, g.h, g.pm, g.pos, g.types,
+                   cfg, g.v_ext, g.phi_fourier, g.v_ext_fourier, cfg.m)
+    F.compute_field_force(layouts, g.pos, g.force_mesh, g.force, g.types, cfg.n_types)
+    o2 = OracleRun(cfg, g.pos.cpu().numpy(), types_)
+    assert rel_err(g.forces(), o2.force) < 1e-10

@@ -397,6 +397,8 @@ def test_cta_cooperative_evaluation_matches_the_per_particle_result(real, tile, 
     topo.set_cta(False)
 
 
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: first run on a GPU "
+                                        "is the driver's; XPASS = verified, remove the mark next round")
 def test_barostat_rescale_then_fields_match_the_oracle_in_the_new_box():
     """NPT step (main.py:889-935): hymd_b200.barostat.isotropic computes the pressure on the device,
     rescales box and positions in place and tells the context the new box (hymd_ctx_set_box) instead of

@@ -1,0 +1,19 @@
+#!/bin/bash
+# First GPU job of the next round for row f2: verify the two CPU-only-verified kernel
+# changes, then measure the variants of the fused inner-step kernel end to end and profile it.
+#   gpurun --timeout 600 -- 'bash tools/gpu_md_next.sh'
+OUT=gpurun_out/r2md; mkdir -p $OUT
+timeout 120 python -m pytest tests/test_zgpu_md.py -q -m gpu --tb=short > $OUT/pytest.log 2>&1; tail -5 $OUT/pytest.log
+timeout 60 python tools/bench_md.py --out $OUT/md_bench.json > $OUT/md_bench.log 2>&1; tail -1 $OUT/md_bench.log | cut -c1-400
+for V in "" "HYMD_B200_BONDED_TILE=256" "HYMD_B200_BONDED_TILE=512" "HYMD_B200_BONDED_TILE=1024" \
+         "HYMD_B200_BONDED_OCC=6" "HYMD_B200_BONDED_OCC=8" "HYMD_B200_BONDED_TILE=512 HYMD_B200_BONDED_OCC=6"; do
+    TAG=$(echo "${V:-default}" | tr ' =' '__')
+    env $V timeout 60 python tools/bench_md_e2e.py --out $OUT/e2e_$TAG.json > $OUT/e2e_$TAG.log 2>&1
+    echo "$TAG: $(python -c "import json;d=json.load(open('$OUT/e2e_$TAG.json'));print(d['ms_per_outer_step'],'ms',d['ns_per_day'],'ns/day')" 2>&1 | tail -1)"
+done
+# launch list + one full capture of the fused kernel in the domain_decomposition layout
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/launches.csv \
+    python tools/bench_md_e2e.py --steps 1 > $OUT/ncu_launch.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:inner_step_cta_kernel -s 30 -c 1 \
+    -o $OUT/inner_step_cta python tools/bench_md_e2e.py --steps 1 > $OUT/ncu_full.log 2>&1
+ls -la $OUT | tail -20

@@ -131,3 +131,55 @@ def test_synthetic_systems(name, n, mesh):
         assert s.config.coulombtype == "PIC_Spectral"
     s2 = make_system(name, np.float32, n=n, mesh=mesh)
     assert np.array_equal(s.positions, s2.positions)
+
+
+def test_row_f2_signatures_mirror_reference():
+    """Argument names of the f2py kernels (compute_bond_forces.f90:1, compute_angle_forces.f90:1,
+    compute_dihedral_forces.f90:1), of thermostat.py:12, 18, 111-121, of barostat.py:43-61 and of
+    pressure.py:84-98."""
+    from hymd_b200 import barostat, force, pressure, thermostat
+    expect = [
+        (force.compute_bond_forces, ["f_bonds", "r", "box_size", "a", "b", "r0", "k"]),
+        (force.compute_angle_forces, ["f_angles", "r", "box_size", "a", "b", "c", "t0", "k"]),
+        (force.compute_dihedral_forces, ["f_dihedrals", "r", "dipoles", "transfer_matrix", "box_size", "a", "b",
+                                         "c", "d", "coeff", "dtype", "bb_index", "dipole_flag"]),
+        (thermostat.csvr_thermostat, ["velocity", "names", "config", "prng", "comm", "random_gaussian",
+                                      "random_chi_squared", "remove_center_of_mass_momentum"]),
+        (thermostat.cancel_com_momentum, ["velocities", "config", "comm"]),
+        (thermostat.generate_initial_velocities, ["velocities", "config", "prng", "comm"]),
+        (pressure.comp_pressure, ["phi", "phi_q", "psi", "hamiltonian", "velocities", "config", "phi_fourier",
+                                  "phi_laplacian", "phi_transfer", "positions", "bond_pr", "angle_pr", "comm"]),
+    ]
+    baro = ["pmesh", "pm_stuff", "phi", "phi_q", "psi", "hamiltonian", "positions", "velocities", "config",
+            "phi_fft", "phi_laplacian", "phi_transfer", "bond_pr", "angle_pr", "step", "prng", "comm"]
+    for ns in (barostat.berendsen, barostat.scr):
+        expect += [(ns.isotropic, baro), (ns.semiisotropic, baro)]
+    for fn, args in expect:
+        assert list(inspect.signature(fn).parameters) == args, fn.__name__
+
+
+def test_product_never_imports_the_oracle_or_the_test_shim():
+    """oracle/ and tests/native are test infrastructure: no module of the product may import them."""
+    import re
+    pkg = os.path.join(ROOT, "hymd_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", text, re.M), f
+                assert not re.search(r"#\s*include\s+[<\"][^>\"]*(oracle|tests)/", text), f
+                assert "libhost_check" not in text, f
+
+
+def test_row_f2_needs_a_gpu_and_says_so():
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hymd_b200 import _lib, force, thermostat
+    r = np.zeros((4, 3))
+    a = np.arange(3)
+    with pytest.raises(_lib.HymdError):
+        force.compute_bond_forces(np.zeros_like(r), r, np.ones(3), a, a + 1, np.ones(3), np.ones(3))
+    with pytest.raises(_lib.HymdError):
+        thermostat.cancel_com_momentum(np.zeros((4, 3)), type("C", (), {"n_particles": 4})())

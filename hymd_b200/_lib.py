@@ -17,7 +17,8 @@ NCCL_ID_BYTES = 128
 F32, F64 = 0, 1
 SORT_REUSE_ORDER = 1
 (FIELD_PHI, FIELD_PHI_FOURIER, FIELD_FORCE_MESH, FIELD_V_EXT, FIELD_PHI_Q, FIELD_PHI_Q_FOURIER,
- FIELD_PSI, FIELD_ELEC_FIELD, FIELD_PHI_LAPLACIAN) = range(9)
+ FIELD_PSI, FIELD_ELEC_FIELD, FIELD_PHI_LAPLACIAN, FIELD_GPE_EPS, FIELD_GPE_ELEC_DOT,
+ FIELD_GPE_VBAR) = range(12)
 
 # every symbol include/hymd_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -31,6 +32,7 @@ EXPORTS = [
     "hymd_bonded_create", "hymd_bonded_destroy", "hymd_bonded_forces", "hymd_bonded_launch_count", "hymd_bonded_inner_step", "hymd_bonded_set_cta",
     "hymd_md_kick_drift", "hymd_velocity_moments", "hymd_velocity_moments_scratch_doubles",
     "hymd_csvr_apply", "hymd_cancel_com",
+    "hymd_gpe_cycle", "hymd_gpe_energy",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -52,6 +54,20 @@ class HymdConfig(ctypes.Structure):
         ("A", ctypes.c_double * (HYMD_MAX_TYPES * HYMD_MAX_TYPES)),
         ("c", ctypes.c_double * HYMD_MAX_TYPES),
         ("m", ctypes.c_double * HYMD_MAX_TYPES),
+    ]
+
+
+class HymdGpeParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_int32),
+        ("convergence_type", ctypes.c_int32),
+        ("max_iter", ctypes.c_int32),
+        ("pad", ctypes.c_int32),
+        ("pol_mixing", ctypes.c_double),
+        ("conv_crit", ctypes.c_double),
+        ("coulomb_constant", ctypes.c_double),
+        ("dielectric_type", ctypes.c_double * HYMD_MAX_TYPES),
+        ("type_charges", ctypes.c_double * HYMD_MAX_TYPES),
     ]
 
 
@@ -120,6 +136,8 @@ def load():
     lib.hymd_csvr_apply.argtypes = [ctypes.c_int, vp, I32P, ctypes.c_int, i64, F64P, dbl, dbl, dbl, dbl, dbl,
                                     ctypes.c_int, F64P, vp]
     lib.hymd_cancel_com.argtypes = [ctypes.c_int, vp, i64, F64P, dbl, vp]
+    lib.hymd_gpe_cycle.argtypes = [vp, P(HymdGpeParams), vp, P(i32), vp]
+    lib.hymd_gpe_energy.argtypes = [vp, dbl, P(dbl), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("hymd_last_error", "hymd_launch_count", "hymd_bonded_launch_count", "hymd_bonded_inner_step", "hymd_bonded_set_cta",

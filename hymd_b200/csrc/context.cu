@@ -248,6 +248,7 @@ int hymd_ctx_destroy(hymd_ctx* c) {
     if (c->plans) { destroy_plans(c); delete c->plans; c->plans = nullptr; }
     migrate_destroy(c);
     comm_destroy(c);
+    gpe_destroy(c);
     void* bufs[] = {c->rec, c->rec_alt, c->cell_start, c->q_sorted,
                     c->scalars, c->scan_tmp, c->tab, c->xtw, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
                     c->phi_hat, c->f_hat, c->gmesh, c->v_hat, c->phif_hat, c->tmp_hat, c->v_ext,
@@ -643,6 +644,9 @@ int hymd_get_field(hymd_ctx* c, int field_id, int t, int d, void** d_ptr, int64_
         case HYMD_FIELD_PHI_LAPLACIAN:
             if (!t_ok || !d_ok || !c->lap || !c->have_lap) break;
             p = (char*)c->lap + (size_t)(3 * t + d) * rb; real_geom(); break;
+        case HYMD_FIELD_GPE_EPS: p = (char*)gpe_field(c, 0, 0); if (p) real_geom(); break;
+        case HYMD_FIELD_GPE_ELEC_DOT: p = (char*)gpe_field(c, 1, 0); if (p) real_geom(); break;
+        case HYMD_FIELD_GPE_VBAR: p = (char*)gpe_field(c, 2, t); if (p) real_geom(); break;
         default: break;
     }
     if (!p) {

@@ -124,6 +124,7 @@ struct PlanEntry {
 };
 struct Comm;
 struct MigrateState;
+struct GpeState;
 
 struct PhaseInterval {
     int phase;
@@ -214,6 +215,7 @@ struct hymd_ctx {
                             // a peer may not overwrite them before another barrier (same call sequence
                             // on every rank, so the flags agree)
     hymd::MigrateState* mig;
+    hymd::GpeState* gpe;    // general-Poisson-equation electrostatics (gpe.cu), allocated on first use
     // multi-GPU: particles found outside the local slab by the last sort, copied to pinned host memory
     // right after the count kernel and checked (without stalling the GPU) before the readout
     unsigned int* h_out_of_slab;
@@ -317,6 +319,9 @@ int readout_setup(hymd_ctx* c);
 int readout_forces(hymd_ctx* c, void* d_force, cudaStream_t s);
 int readout_pme(hymd_ctx* c, void* d_force, cudaStream_t s);
 int fill_ghosts(hymd_ctx* c, void* mesh, int nfields, cudaStream_t s);
+// gpe.cu
+void gpe_destroy(hymd_ctx* c);
+void* gpe_field(hymd_ctx* c, int which, int t);
 // energy.cu
 int field_energy(hymd_ctx* c, const double* chi, double kappa, double rho0, double a,
                  double out[2], cudaStream_t s);

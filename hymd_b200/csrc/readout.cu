@@ -477,6 +477,27 @@ static int launch_readout(hymd_ctx* c, void* d_force, cudaStream_t s) {
     return HYMD_ERR_INVALID;
 }
 
+// Per-type gather from a caller-chosen set of ghost-padded force meshes (3 per row of d_urow): the
+// GPE electrostatic forces (gpe.cu) read 3T meshes with the identity type -> row map.
+template <typename real>
+static int launch_gather_custom(hymd_ctx* c, const void* mesh, const int* d_urow, void* d_force, cudaStream_t s) {
+    using Tr = RTraits<real>;
+    const Geometry& g = c->g;
+    GatherParams p;
+    p.n = c->np; p.ghost_elems = g.ghost_elems; p.Ny1 = g.Ny + 1; p.Nzp = g.Nzp;
+    p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
+    const unsigned int blocks = (unsigned int)((p.n + 255) / 256);
+    readout_gather_kernel<real, false><<<blocks, 256, 0, s>>>(
+        (const real*)mesh, (const typename Tr::Rec*)c->rec, (const real*)c->q_sorted, d_urow, (real*)d_force, p);
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
+}
+
+int readout_custom(hymd_ctx* c, const void* mesh, const int* d_urow, void* d_force, cudaStream_t s) {
+    return c->f64 ? launch_gather_custom<double>(c, mesh, d_urow, d_force, s)
+                  : launch_gather_custom<float>(c, mesh, d_urow, d_force, s);
+}
+
 int readout_forces(hymd_ctx* c, void* d_force, cudaStream_t s) {
     return c->f64 ? launch_readout<double, false>(c, d_force, s)
                   : launch_readout<float, false>(c, d_force, s);

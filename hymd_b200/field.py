@@ -42,9 +42,15 @@ def initialize_pm(pmesh, config, comm=None):
     dtype = "f8" if np.dtype(config.dtype) == np.float64 else "f4"
     coulombtype = getattr(config, "coulombtype", None)
     if coulombtype == "PIC_Spectral_GPE":
-        raise NotImplementedError(
-            "coulombtype='PIC_Spectral_GPE' (field.py:764-1112) is outside the accelerated "
-            "field-force cycle; use 'PIC_Spectral'")
+        import os
+        import torch.distributed as dist
+        if os.environ.get("HYMD_B200_ENABLE_GPE", "0") != "1":
+            raise NotImplementedError(
+                "coulombtype='PIC_Spectral_GPE' (field.py:764-1112): the device path (hymd_gpe_cycle) "
+                "exists but has not been run on a GPU yet; set HYMD_B200_ENABLE_GPE=1 to try it, or use "
+                "'PIC_Spectral'")
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise NotImplementedError("coulombtype='PIC_Spectral_GPE' runs on a single GPU only")
     pm = ParticleMesh(config.mesh_size, BoxSize=config.box_size, dtype=dtype, comm=comm,
                       config=config)
     T = config.n_types
@@ -67,6 +73,21 @@ def initialize_pm(pmesh, config, comm=None):
         elec_common_list = [phi_q, phi_q_fourier, psi, elec_field]
         coulomb_list = [[UnusedField(f"elec_field_fourier[{d}]") for d in range(3)],
                         UnusedField("psi_fourier")]
+    if coulombtype == "PIC_Spectral_GPE":          # list layouts of field.py:66-75, 88-137
+        phi_q = pm.field(_lib.FIELD_PHI_Q)
+        psi = pm.field(_lib.FIELD_PSI)
+        elec_common_list = [phi_q, UnusedField("phi_q_fourier"), psi,
+                            [UnusedField(f"elec_field[{d}]") for d in range(3)]]
+        coulomb_list = [
+            pm.field(_lib.FIELD_GPE_EPS), UnusedField("phi_eps_fourier"),
+            [UnusedField(f"phi_eta[{d}]") for d in range(3)],
+            [UnusedField(f"phi_eta_fourier[{d}]") for d in range(3)],
+            UnusedField("phi_pol"), UnusedField("phi_pol_prev"), pm.field(_lib.FIELD_GPE_ELEC_DOT),
+            UnusedField("elec_field_contrib"), [pm.field(_lib.FIELD_GPE_VBAR, t) for t in range(T)],
+            [UnusedField(f"Vbar_elec_fourier[{t}]") for t in range(T)],
+            [[UnusedField(f"force_mesh_elec[{t}][{d}]") for d in range(3)] for t in range(T)],
+            [[UnusedField(f"force_mesh_elec_fourier[{t}][{d}]") for d in range(3)] for t in range(T)],
+        ]
     return (pm, field_list, elec_common_list, coulomb_list)
 
 
@@ -135,6 +156,52 @@ def update_field_force_q(charges, phi_q, phi_q_fourier, psi, psi_fourier, elec_f
     _lib.check(pm.lib.hymd_pme_cycle(pm._ctx, ctypes.c_void_p(buf.data_ptr()), 0, pm.stream))
     if back is not None:
         back()
+
+
+_CONVERGENCE = {None: 0, "max_diff": 0, "csum": 1, "euclidean_norm": 2}
+
+
+def update_field_force_q_GPE(conv_fun, phi, types, charges, phi_q, phi_q_fourier, phi_eps, phi_eps_fourier,
+                             phi_eta, phi_eta_fourier, phi_pol_prev, phi_pol, elec_field, elec_forces,
+                             elec_field_contrib, psi, Vbar_elec, Vbar_elec_fourier, force_mesh_elec,
+                             force_mesh_elec_fourier, hamiltonian, layout_q, layouts, pm, positions, config,
+                             comm=None):
+    """General-Poisson-equation electrostatics (``field.py:964-1112``): dielectric field from the type
+    densities of the last ``update_field``, polarisation-charge iteration, potential, field, per-type
+    electrostatic potential and the forces, written in place into ``elec_forces``.  ``conv_fun`` (the
+    reference's closure over ``config.convergence_type``, ``main.py:141-163``) is accepted and ignored:
+    the convergence measure is evaluated on the device according to ``config.convergence_type``.
+    Returns ``(Vbar_elec, phi_eps, elec_dot)`` like the reference (``elec_dot`` as a mesh handle).
+    NOT YET RUN ON A GPU."""
+    pm.sync_interaction(hamiltonian, config)
+    pm.sort(positions, None, charges)
+    n = pm._n_local
+    prm = _lib.HymdGpeParams()
+    prm.struct_size = ctypes.sizeof(_lib.HymdGpeParams)
+    prm.convergence_type = _CONVERGENCE[getattr(config, "convergence_type", None)]
+    prm.max_iter = 100
+    prm.pol_mixing = float(config.pol_mixing if getattr(config, "pol_mixing", None) is not None else 0.6)
+    prm.conv_crit = float(config.conv_crit if getattr(config, "conv_crit", None) is not None else 1e-6)
+    prm.coulomb_constant = float(config.coulomb_constant)
+    for t in range(config.n_types):
+        prm.dielectric_type[t] = float(config.dielectric_type[t])
+        prm.type_charges[t] = float(config.type_charges[t])
+    buf, back = _output_buffer(pm, elec_forces, n)
+    iters = ctypes.c_int32(0)
+    _lib.check(pm.lib.hymd_gpe_cycle(pm._ctx, ctypes.byref(prm), ctypes.c_void_p(buf.data_ptr()),
+                                     ctypes.byref(iters), pm.stream))
+    pm.gpe_iterations = int(iters.value)
+    if back is not None:
+        back()
+    return Vbar_elec, phi_eps, pm.field(_lib.FIELD_GPE_ELEC_DOT)
+
+
+def compute_field_energy_q_GPE(config, phi_eps, field_q_energy, dot_elec, comm=None):
+    """``dV * eps_0 / 2 * sum(phi_eps * |E|^2)`` summed over ranks (``field.py:706-760``)."""
+    pm = phi_eps.pm
+    out = ctypes.c_double(0.0)
+    _lib.check(pm.lib.hymd_gpe_energy(pm._ctx, float(config.coulomb_constant), ctypes.byref(out), pm.stream))
+    return float(_allreduce(torch.tensor([out.value], dtype=torch.float64))[0])
 
 
 def compute_field_and_kinetic_energy(phi, phi_q, psi, velocity, hamiltonian, positions, types,

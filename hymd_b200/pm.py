@@ -146,7 +146,8 @@ class ParticleMesh:
         self.np = (self.world_size, 1)          # processor mesh, logged at main.py:252
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.n_types = int(config.n_types)
-        self.pme = getattr(config, "coulombtype", None) == "PIC_Spectral"
+        self.gpe = getattr(config, "coulombtype", None) == "PIC_Spectral_GPE"
+        self.pme = getattr(config, "coulombtype", None) == "PIC_Spectral" or self.gpe
         self._config = config
         self._ctx = ctypes.c_void_p()
         self._interaction_key = None
@@ -173,7 +174,7 @@ class ParticleMesh:
             A, c = np.zeros((T, T)), np.zeros(T)
         m = list(getattr(config, "m", None) or [1.0] * T)
         conv = 0.0
-        if self.pme:
+        if self.pme and getattr(config, "dielectric_const", None):
             conv = float(config.coulomb_constant) / float(config.dielectric_const)
         return A, c, np.asarray(m, dtype=np.float64), float(config.sigma), conv
 

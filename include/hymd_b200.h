@@ -55,7 +55,10 @@ typedef enum {
     HYMD_FIELD_PHI_Q_FOURIER = 5,/*          cplx  k-layout: H * r2c(phi_q)/M */
     HYMD_FIELD_PSI = 6,          /*          real  (nxl,Ny,Nz) electrostatic potential */
     HYMD_FIELD_ELEC_FIELD = 7,   /* [d]      real  ghost-padded (nxl+1,Ny+1,Nzp) */
-    HYMD_FIELD_PHI_LAPLACIAN = 8 /* [t][d]   real  (nxl,Ny,Nz): c2r(-k_d^2 phi_fourier[t]) (hymd_laplacian) */
+    HYMD_FIELD_PHI_LAPLACIAN = 8,/* [t][d]   real  (nxl,Ny,Nz): c2r(-k_d^2 phi_fourier[t]) (hymd_laplacian) */
+    HYMD_FIELD_GPE_EPS = 9,      /*          real  (nxl,Ny,Nz) relative dielectric phi_eps   (hymd_gpe_cycle) */
+    HYMD_FIELD_GPE_ELEC_DOT = 10,/*          real  (nxl,Ny,Nz) |E|^2                         (hymd_gpe_cycle) */
+    HYMD_FIELD_GPE_VBAR = 11     /* [t]      real  (nxl,Ny,Nz) Vbar_elec[t]                  (hymd_gpe_cycle) */
 } hymd_field_id;
 
 typedef struct {
@@ -217,6 +220,36 @@ int hymd_ctx_get_timings(hymd_ctx* ctx, double* ms, int64_t* calls);
 int hymd_migrate_plan(hymd_ctx* ctx, const void* d_pos, int64_t n, int64_t* n_new, void* stream);
 int hymd_migrate_apply(hymd_ctx* ctx, const void* d_in, void* d_out, int32_t row_bytes,
                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row f3: general-Poisson-equation electrostatics, coulombtype "PIC_Spectral_GPE".
+ * NOT YET RUN ON A GPU (written after the round's GPU minutes were spent); single GPU only.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t struct_size;                     /* = sizeof(hymd_gpe_params) */
+    int32_t convergence_type;                /* config.convergence_type: 0 "max_diff" (default), 1 "csum",
+                                                2 "euclidean_norm" (main.py:141-163) */
+    int32_t max_iter;                        /* 100 in the reference (field.py:1037); <= 0 selects it */
+    int32_t pad;
+    double pol_mixing;                       /* config.pol_mixing (default 0.6) */
+    double conv_crit;                        /* config.conv_crit (default 1e-6) */
+    double coulomb_constant;                 /* config.coulomb_constant: eps0_inv = 4 pi k_e (field.py:1068) */
+    double dielectric_type[HYMD_MAX_TYPES];  /* config.dielectric_type by type id (input_parser.py:1166-1177) */
+    double type_charges[HYMD_MAX_TYPES];     /* config.type_charges */
+} hymd_gpe_params;
+
+/* update_field_force_q_GPE (hymd/field.py:964-1112) for the charges given to hymd_sort_particles and the
+ * type densities of the last hymd_paint + hymd_field_cycle (they are materialized in filtered form
+ * first).  Writes d_elec_force (n,3) in caller order (may be NULL) and the number of polarisation
+ * iterations to *iterations (may be NULL).  Afterwards HYMD_FIELD_PHI_Q holds the filtered charge density
+ * divided by the dielectric (field.py:1010, 1021), HYMD_FIELD_PSI the potential, HYMD_FIELD_GPE_* the
+ * dielectric, |E|^2 and the per-type electrostatic potentials.  The context must have been created with
+ * pme = 1.  Synchronizes the stream once per iteration (the convergence test). */
+int hymd_gpe_cycle(hymd_ctx* ctx, const hymd_gpe_params* params, void* d_elec_force, int32_t* iterations,
+                   void* stream);
+/* compute_field_energy_q_GPE (field.py:706-760): dV * eps_0 / 2 * sum_cells phi_eps |E|^2 of this slab to the
+ * HOST double *out.  Synchronous. */
+int hymd_gpe_energy(hymd_ctx* ctx, double coulomb_constant, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row f2: the caller side of the hot path kept on the device -- intramolecular

@@ -13,7 +13,8 @@ single rank.  Pinned against the reference's own function executed over ``oracle
 
 Kept from the reference on purpose: the masks ``where=np.abs(x > 1e-6)`` (a boolean, i.e. ``x > 1e-6``:
 cells at or below the threshold keep the previous content of the output array); ``phi_q`` is divided by
-``phi_eps`` in place before the iteration; the iteration starts from the caller's ``phi_pol_prev``.
+``phi_eps`` in place before the iteration; the iteration starts from the caller's ``phi_pol_prev``,
+which the reference never writes back (zeros at every call in ``main.py``).
 """
 from __future__ import annotations
 
@@ -85,8 +86,8 @@ def update_field_force_q_GPE(st, phi, types, charges, positions, hamiltonian, co
             delta = float(np.sum(np.abs(diff) ** 2))
         pol_prev = pol.copy()
         i += 1
-    st.iterations = i
-    st.phi_pol_prev = pol_prev
+    st.iterations = i      # the caller's phi_pol_prev mesh is NOT updated: the reference rebinds its local
+                           # name (field.py:1062), so every call starts the iteration from the same field
     # potential and field (field.py:1066-1084)
     eps0_inv = config.coulomb_constant * 4 * np.pi
     f = pmo.r2c(eps0_inv * (phi_q + pol)) / k2

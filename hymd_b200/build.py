@@ -20,7 +20,7 @@ LIB = os.path.join(LIBDIR, "libhymd_b200.so")
 SOURCES = ["context.cu", "sort.cu", "paint.cu", "kspace.cu", "readout.cu", "energy.cu",
            "slabfft.cu", "comm.cu", "migrate.cu", "xline.cu", "planefft.cu", "bonded.cu", "md.cu", "gpe.cu"]
 HEADERS = [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "fft.cuh"), os.path.join(CSRC, "bonded.cuh"),
-           os.path.join(CSRC, "md.cuh"), os.path.join(HERE, "..", "include", "hymd_b200.h")]
+           os.path.join(CSRC, "md.cuh"), os.path.join(CSRC, "gpe.cuh"), os.path.join(HERE, "..", "include", "hymd_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
               "-Xptxas", "-v"]

@@ -311,3 +311,19 @@ extern "C" int hymd_bonded_inner_step(void* h, int dtype, const void* x_in, void
     else inner<float>(b, 7, (const float*)x_in, (float*)x_out, (float*)vel, bx, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
     return 0;
 }
+
+// ---- k-space arithmetic of the GPE electrostatics (csrc/gpe.cuh) on host memory -----------------------
+#include "../../hymd_b200/csrc/gpe.cuh"
+
+extern "C" int host_gpe_kspace(const double* in, double* out_s, double* out_v, const double* tab, int Nx, int Ny,
+                               int Nz, int F, double coef, int use_h, int div_k2, double sign) {
+    GKParams p;
+    p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.nyl = Ny; p.y0 = 0; p.Nzc = Nz / 2 + 1; p.Nzcp = (p.Nzc + 1) / 2 * 2; p.F = F;
+    const long long xs = (long long)Ny * p.Nzcp, fs = (long long)Nx * xs;
+    p.npairs = fs / 2;
+    p.xs_in = p.xs_s = p.xs_v = 2 * xs;
+    p.fs_in = p.fs_s = p.fs_v = 2 * fs;
+    for (long long i = 0; i < p.npairs; ++i)
+        gpe_kspace_pair<double>(i, in, out_s, out_v, tab, coef, use_h, div_k2, sign, p);
+    return 0;
+}

@@ -189,3 +189,81 @@ def test_csvr_matches_reference_golden(lib, case, groups, remove):
                       d(1.5 * gas * T0), d(c), d(R), d(S), int(remove), work.ctypes.data_as(vp))
     np.testing.assert_allclose(v, TG[pre + "/v"], rtol=1e-12, atol=1e-14)
     assert work[0] == pytest.approx(float(TG[pre + "/work"]), abs=1e-10)
+
+
+@pytest.mark.parametrize("mesh", [(8, 8, 8), (10, 12, 8), (9, 8, 11), (6, 5, 7)])
+def test_gpe_kspace_arithmetic_matches_numpy(lib, mesh):
+    """csrc/gpe.cuh (the four k-space modes of hymd_gpe_cycle, with the Nyquist rule and the padded
+    z pitch of the k layout) executed on the CPU between numpy's raw rfftn and irfftn, against the
+    oracle's expressions `c2r(op(k) * r2c(x))` (oracle/gpe_oracle.py = hymd/field.py:1006-1111)."""
+    from oracle import pm_oracle as pmo
+    nx, ny, nz = mesh
+    box = np.array([3.5, 4.0, 3.0])
+    sigma = 0.5
+    rng = np.random.default_rng(3)
+    nzc = nz // 2 + 1
+    nzcp = (nzc + 1) // 2 * 2
+    M = nx * ny * nz
+    # tables exactly as context.cu build_tables lays them out
+    def kax(n, L, m):
+        idx = np.arange(m)
+        ni = np.where(idx < (n + 1) // 2, idx, idx - n)
+        return 2.0 * np.pi * ni / L
+    ks = [kax(nx, box[0], nx), kax(ny, box[1], ny), kax(nz, box[2], nzc)]
+    tab = np.concatenate([np.exp(-0.5 * sigma ** 2 * k ** 2) for k in ks] + ks)
+    k = pmo.kgrid(mesh, box)
+    k2 = pmo.knorm2_zeromode1(k)
+    H = np.exp(-0.5 * sigma ** 2 * (k[0] ** 2 + k[1] ** 2 + k[2] ** 2))
+
+    def pack(spec):                      # (F,nx,ny,nzc) complex -> [f][x][y][Nzcp] interleaved reals
+        F = spec.shape[0]
+        buf = np.zeros((F, nx, ny, nzcp), dtype=np.complex128)
+        buf[..., :nzc] = spec
+        buf[..., nzc:] = 7.0 + 3.0j      # padding must never leak into the result
+        return np.ascontiguousarray(buf).view(np.float64).ravel()
+
+    def unpack(flat, F):
+        return flat.view(np.complex128).reshape(F, nx, ny, nzcp)[..., :nzc]
+
+    def run(x, F, coef, use_h, div_k2, sign, want_s, want_v):
+        raw = np.stack([np.fft.rfftn(x[f]) for f in range(F)])            # unnormalised r2c
+        inp = pack(raw)
+        out_s = np.full(F * nx * ny * nzcp * 2, np.nan) if want_s else None
+        out_v = np.full(3 * F * nx * ny * nzcp * 2, np.nan) if want_v else None
+        vp = ctypes.c_void_p
+        lib.host_gpe_kspace(inp.ctypes.data_as(vp), out_s.ctypes.data_as(vp) if want_s else None,
+                            out_v.ctypes.data_as(vp) if want_v else None, tab.ctypes.data_as(vp), nx, ny, nz, F,
+                            ctypes.c_double(coef), use_h, div_k2, ctypes.c_double(sign))
+        c2r = lambda spec: np.fft.irfftn(spec, s=mesh, axes=(0, 1, 2)) * M                 # unnormalised c2r
+        s_real = np.stack([c2r(a) for a in unpack(out_s, F)]) if want_s else None
+        v_real = np.stack([c2r(a) for a in unpack(out_v, 3 * F)]) if want_v else None
+        return s_real, v_real
+
+    def close(a, b):
+        assert np.abs(a - b).max() <= 1e-11 * max(np.abs(b).max(), 1e-300)
+
+    x = rng.normal(size=(1,) + tuple(mesh))
+    xf = pmo.r2c(x[0])
+    # filter: c2r(H * r2c(x))   (field.py:1008-1010)
+    s_real, _ = run(x, 1, 1.0 / M, 1, 0, 1.0, True, False)
+    close(s_real[0], pmo.c2r(H * xf, mesh))
+    # gradient of the dielectric: c2r(+i k_d r2c(x))   (field.py:1027-1032)
+    _, v_real = run(x, 1, 1.0 / M, 0, 0, 1.0, False, True)
+    for d in range(3):
+        close(v_real[d], pmo.c2r(1j * k[d] * xf, mesh))
+    # iteration field: c2r(-i k_d r2c(x) / k^2)   (field.py:1049-1052)
+    _, v_real = run(x, 1, 1.0 / M, 0, 1, -1.0, False, True)
+    for d in range(3):
+        close(v_real[d], pmo.c2r(-1j * k[d] * xf / k2, mesh))
+    # potential and field in one pass   (field.py:1070-1078)
+    s_real, v_real = run(x, 1, 1.0 / M, 0, 1, -1.0, True, True)
+    close(s_real[0], pmo.c2r(xf / k2, mesh))
+    for d in range(3):
+        close(v_real[d], pmo.c2r(-1j * k[d] * (xf / k2), mesh))
+    # filtered -grad of T potentials, 3T outputs ordered [3t+d]   (field.py:1099-1108)
+    T = 3
+    xs = rng.normal(size=(T,) + tuple(mesh))
+    _, v_real = run(xs, T, 1.0 / M, 1, 0, -1.0, False, True)
+    for t in range(T):
+        for d in range(3):
+            close(v_real[3 * t + d], pmo.c2r(-1j * k[d] * (H * pmo.r2c(xs[t])), mesh))

@@ -267,3 +267,99 @@ def test_gpe_kspace_arithmetic_matches_numpy(lib, mesh):
     for t in range(T):
         for d in range(3):
             close(v_real[3 * t + d], pmo.c2r(-1j * k[d] * (H * pmo.r2c(xs[t])), mesh))
+
+
+def test_gpe_cycle_plan_matches_reference_golden(lib):
+    """The data flow of csrc/gpe.cu::gpe_cycle_t transcribed step by step -- raw (unnormalised) forward
+    transforms, the gpe.cuh k-space kernel with exactly the (coef, use_h, div_k2, sign) arguments the
+    driver passes, unnormalised inverse transforms, the pointwise updates with the reference's masks --
+    reproduces the reference's own update_field_force_q_GPE (tests/golden/gpe_golden.npz).  This pins
+    the plan (normalisation, signs, scalings, buffer roles); the CUDA glue itself is GPU-only."""
+    from oracle import pm_oracle as pmo
+    GG = np.load(os.path.join(HERE, "golden", "gpe_golden.npz"))
+    pre = "gpe/gpe3"
+    mesh, box = (10, 12, 8), np.array([3.5, 4.0, 3.0])
+    sigma, k_e = 0.5, 138.935458
+    eps_t, q_t, w, crit = np.array([5.0, 10.0, 80.0]), np.array([1.0, -1.0, 0.0]), 0.6, 1e-6
+    nx, ny, nz = mesh
+    nzc = nz // 2 + 1
+    nzcp = (nzc + 1) // 2 * 2
+    M = nx * ny * nz
+    dv = np.prod(box) / M
+
+    def kax(n, L, m):
+        idx = np.arange(m)
+        return 2.0 * np.pi * np.where(idx < (n + 1) // 2, idx, idx - n) / L
+    ks = [kax(nx, box[0], nx), kax(ny, box[1], ny), kax(nz, box[2], nzc)]
+    tab = np.concatenate([np.exp(-0.5 * sigma ** 2 * k ** 2) for k in ks] + ks)
+    vp = ctypes.c_void_p
+
+    def fwd(x):                                   # fft_forward: raw spectra in the padded k layout
+        x = np.asarray(x).reshape((-1,) + mesh)
+        buf = np.zeros((x.shape[0], nx, ny, nzcp), dtype=np.complex128)
+        buf[..., :nzc] = np.fft.rfftn(x, axes=(1, 2, 3))
+        return buf
+
+    def inv(buf):                                 # fft_inverse: unnormalised c2r
+        return np.fft.irfftn(buf[..., :nzc], s=mesh, axes=(1, 2, 3)) * M
+
+    def kspace(inp, want_s, want_v, coef, use_h, div_k2, sign):
+        F = inp.shape[0]
+        flat = np.ascontiguousarray(inp).view(np.float64).ravel()
+        out_s = np.zeros(F * nx * ny * nzcp * 2) if want_s else None
+        out_v = np.zeros(3 * F * nx * ny * nzcp * 2) if want_v else None
+        lib.host_gpe_kspace(flat.ctypes.data_as(vp), out_s.ctypes.data_as(vp) if want_s else None,
+                            out_v.ctypes.data_as(vp) if want_v else None, tab.ctypes.data_as(vp), nx, ny, nz, F,
+                            ctypes.c_double(coef), int(use_h), int(div_k2), ctypes.c_double(sign))
+        s = out_s.view(np.complex128).reshape(F, nx, ny, nzcp) if want_s else None
+        v = out_v.view(np.complex128).reshape(3 * F, nx, ny, nzcp) if want_v else None
+        return s, v
+
+    phi = GG[pre + "/phi"]
+    pos, types_, charges = GG[pre + "/pos"], GG[pre + "/types"], GG[pre + "/charges"]
+    T = len(eps_t)
+    # --- the driver, line by line
+    phi_q = pmo.cic_paint(pos, charges, mesh, box, np.float64, use_c=False) / dv          # paint_charges
+    kS, _ = kspace(fwd(phi_q), True, False, 1.0 / M, True, False, 1.0)
+    phi_q = inv(kS)[0]
+    den = phi.sum(axis=0)
+    eps = np.zeros(mesh)
+    np.divide((eps_t[:, None, None, None] * phi).sum(axis=0), den, where=den > 1e-6, out=eps)   # gpe_eps_kernel
+    _, kB = kspace(fwd(eps), False, True, 1.0 / M, False, False, 1.0)
+    eta = inv(kB)
+    mask = eps > 1e-6                                                                       # gpe_divide_kernel
+    phi_q = np.where(mask, phi_q / np.where(mask, eps, 1.0), phi_q)
+    eta = np.where(mask, eta / np.where(mask, eps, 1.0), eta)
+    pol = np.zeros(mesh)
+    it, delta = 0, 1.0
+    while it < 100 and delta > crit:
+        _, kB = kspace(fwd(phi_q + pol), False, True, 1.0 / M, False, True, -1.0)
+        E = inv(kB)
+        new = w * (-(eta * E).sum(axis=0)) + (1.0 - w) * pol                               # gpe_pol_kernel
+        delta = np.abs(new - pol).max()
+        pol = new
+        it += 1
+    eps0_inv = k_e * 4 * np.pi
+    kS, kB = kspace(fwd(eps0_inv * (phi_q + pol)), True, True, 1.0 / M, False, True, -1.0)
+    psi, E = inv(kS)[0], inv(kB)
+    dot = (E ** 2).sum(axis=0)                                                              # gpe_vbar_kernel
+    contrib = np.zeros(mesh)
+    np.divide(dot, den, where=den > 1e-6, out=contrib)
+    vbar = np.stack([q_t[t] * psi - (0.5 / eps0_inv) * (eps_t[t] - eps) * contrib for t in range(T)])
+    _, kB = kspace(fwd(vbar), False, True, 1.0 / M, True, False, -1.0)
+    fmesh = inv(kB)
+    forces = np.zeros((len(pos), 3))
+    for t in range(T):
+        ind = types_ == t
+        for d in range(3):
+            forces[ind, d] = pmo.cic_readout(np.ascontiguousarray(fmesh[3 * t + d]), pos[ind], box, use_c=False)
+    energy = dv * 0.5 / eps0_inv * np.sum(eps * dot)                                        # gpe_energy
+
+    def close(a, b, tol=1e-9):
+        assert np.abs(a - b).max() <= tol * np.abs(b).max()
+    close(eps, GG[pre + "/phi_eps"], 1e-12)
+    close(psi, GG[pre + "/psi"])
+    close(dot, GG[pre + "/elec_dot"])
+    close(vbar, GG[pre + "/Vbar_elec"])
+    close(forces, GG[pre + "/elec_forces"])
+    assert energy == pytest.approx(float(GG[pre + "/energy"]), rel=1e-9)

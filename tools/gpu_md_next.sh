@@ -16,4 +16,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --c
     python tools/bench_md_e2e.py --steps 1 > $OUT/ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:inner_step_cta_kernel -s 30 -c 1 \
     -o $OUT/inner_step_cta python tools/bench_md_e2e.py --steps 1 > $OUT/ncu_full.log 2>&1
+# row f3: first run of the GPE device path (non-strict xfails: look for XPASS / the failure text)
+HYMD_B200_ENABLE_GPE=1 timeout 300 python -m pytest tests/test_zzgpu_gpe.py -q -m gpu -rxX --tb=short > $OUT/pytest_gpe.log 2>&1; tail -15 $OUT/pytest_gpe.log
 ls -la $OUT | tail -20

@@ -29,7 +29,7 @@ EXPORTS = [
     "hymd_launch_count", "hymd_migrate_plan", "hymd_migrate_apply", "hymd_ctx_set_timing", "hymd_ctx_get_timings",
     "hymd_sort_particles_ex", "hymd_ctx_reset_order", "hymd_ctx_paths", "hymd_laplacian",
     "hymd_field_pressure",
-    "hymd_bonded_create", "hymd_bonded_destroy", "hymd_bonded_forces", "hymd_bonded_launch_count", "hymd_bonded_inner_step", "hymd_bonded_set_cta",
+    "hymd_bonded_create", "hymd_bonded_destroy", "hymd_bonded_forces", "hymd_bonded_launch_count", "hymd_bonded_inner_step", "hymd_bonded_set_cta", "hymd_bonded_set_math",
     "hymd_md_kick_drift", "hymd_velocity_moments", "hymd_velocity_moments_scratch_doubles",
     "hymd_csvr_apply", "hymd_cancel_com",
     "hymd_gpe_cycle", "hymd_gpe_energy",
@@ -126,6 +126,7 @@ def load():
     lib.hymd_bonded_inner_step.argtypes = [vp, ctypes.c_int, vp, vp, vp, P(dbl), dbl, dbl, ctypes.c_int, dbl,
                                            P(vp), F64P, vp]
     lib.hymd_bonded_set_cta.argtypes = [vp, ctypes.c_int]
+    lib.hymd_bonded_set_math.argtypes = [vp, ctypes.c_int]
     lib.hymd_bonded_launch_count.argtypes = [vp]
     lib.hymd_bonded_launch_count.restype = i64
     lib.hymd_md_kick_drift.argtypes = [ctypes.c_int, vp, vp, P(vp), ctypes.c_int, ctypes.c_int, dbl, dbl, dbl,
@@ -140,7 +141,7 @@ def load():
     lib.hymd_gpe_energy.argtypes = [vp, dbl, P(dbl), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("hymd_last_error", "hymd_launch_count", "hymd_bonded_launch_count", "hymd_bonded_inner_step", "hymd_bonded_set_cta",
+        if name not in ("hymd_last_error", "hymd_launch_count", "hymd_bonded_launch_count", "hymd_bonded_inner_step", "hymd_bonded_set_cta", "hymd_bonded_set_math",
                         "hymd_velocity_moments_scratch_doubles"):
             fn.restype = ctypes.c_int
     if lib.hymd_abi_version() != 1:

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include "bonded.cuh"
+#include "bonded_f32.cuh"
 #include "ctx.cuh"
 
 struct hymd_bonded {
@@ -23,6 +24,8 @@ struct hymd_bonded {
     size_t cta_smem;             // dynamic shared memory of inner_step_cta_kernel
     int use_cta;                 // HYMD_B200_BONDED_CTA / hymd_bonded_set_cta: 0, 1 or 2
     int tile;                    // particles per CTA of the cooperative kernels (HYMD_B200_BONDED_TILE)
+    int f32math;                 // hymd_bonded_set_math / HYMD_B200_BONDED_F32MATH: float arithmetic for bonds
+                                 // and angles in the fp32 build's per-particle fused step (bonded_f32.cuh)
     int occ;                     // HYMD_B200_BONDED_OCC: 0 (default, no register limit), 6 or 8 resident CTAs per SM
     double* out12;               // scratch result of the fused kernels
     double* partial;             // [max_blocks][4] block partials of {energy, pr_x, pr_y, pr_z}
@@ -84,6 +87,39 @@ __global__ void __launch_bounds__(BONDED_THREADS) inner_step_kernel(
     if (p < n) {
         real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
         inner_step_particle<real>(p, x_in, x_out, vel, box, t, mass, half_dt, n_kicks, dt, f_out, acc);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[4 * k] = acc[k].e; v[4 * k + 1] = acc[k].pr.x; v[4 * k + 2] = acc[k].pr.y; v[4 * k + 3] = acc[k].pr.z;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    __shared__ double sh[BONDED_THREADS / 32][12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 12; ++k) sh[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < BONDED_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
+        partial[12 * (long long)blockIdx.x + threadIdx.x] = s;
+    }
+}
+
+// Same step with single-precision bond / angle arithmetic (bonded_f32.cuh; fp32 build, opt-in).
+__global__ void __launch_bounds__(BONDED_THREADS) inner_step_f32_kernel(
+    const float* __restrict__ x_in, float* __restrict__ x_out, float* __restrict__ vel, long long n, Vec3d box,
+    TermLists t, float mass, float half_dt, int n_kicks, float dt, ForceOut fo, double* __restrict__ partial) {
+    const long long p = (long long)blockIdx.x * BONDED_THREADS + threadIdx.x;
+    BondAcc acc[3];
+    double v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = 0.0;
+    if (p < n) {
+        float* f_out[3] = {(float*)fo.f[0], (float*)fo.f[1], (float*)fo.f[2]};
+        inner_step_particle_f32(p, x_in, x_out, vel, box, t, mass, half_dt, n_kicks, dt, f_out, acc);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             v[4 * k] = acc[k].e; v[4 * k + 1] = acc[k].pr.x; v[4 * k + 2] = acc[k].pr.y; v[4 * k + 3] = acc[k].pr.z;
@@ -305,7 +341,12 @@ static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x
     t.dih_type = b->dih_type;
     ForceOut fo;
     for (int k = 0; k < 3; ++k) fo.f[k] = d_force_out ? d_force_out[k] : nullptr;
-    if (blocks > 0) {
+    if (blocks > 0 && b->f32math && sizeof(real) == 4 && !b->use_cta) {
+        inner_step_f32_kernel<<<blocks, BONDED_THREADS, 0, s>>>((const float*)x_in, (float*)x_out, (float*)vel, n, box,
+                                                              t, (float)mass, (float)(0.5 * kick_dt), n_kicks,
+                                                              (float)drift_dt, fo, b->partial);
+        HYMD_LAUNCH_CHECK(b);
+    } else if (blocks > 0) {
         if (b->use_cta == 2) {
             CtaRecs rc;
             rc.rec[0] = b->rec[0];
@@ -395,6 +436,7 @@ int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const
         }
         b->tile = tile;
     }
+    if (const char* env = getenv("HYMD_B200_BONDED_F32MATH")) b->f32math = atoi(env) != 0;
     b->occ = 0;
     if (const char* env = getenv("HYMD_B200_BONDED_OCC")) {
         b->occ = atoi(env);
@@ -506,6 +548,12 @@ int hymd_bonded_inner_step(hymd_bonded* b, int dtype, const void* d_pos_in, void
                                     kick_dt, n_kicks, drift_dt, d_force_out, d_out, s);
     return launch_inner<float>(b, 7, (const float*)d_pos_in, (float*)d_pos_out, (float*)d_vel, bx, mass,
                                kick_dt, n_kicks, drift_dt, d_force_out, d_out, s);
+}
+
+int hymd_bonded_set_math(hymd_bonded* b, int f32math) {
+    if (!b) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    b->f32math = f32math ? 1 : 0;
+    return HYMD_OK;
 }
 
 int hymd_bonded_set_cta(hymd_bonded* b, int enable) {

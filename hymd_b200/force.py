@@ -110,6 +110,12 @@ class BondedTopology:
         _lib.check(self.lib.hymd_bonded_set_cta(self._h, int(enable)))
         self._cta = int(enable)
 
+    def set_math(self, f32=True):
+        """Single-precision arithmetic for bonds and angles in the per-particle fused inner step of the
+        fp32 build (``hymd_bonded_set_math``, ``csrc/bonded_f32.cuh``); the default is the Fortran's double
+        arithmetic.  Not yet run on a GPU."""
+        _lib.check(self.lib.hymd_bonded_set_math(self._h, 1 if f32 else 0))
+
     def launch_count(self):
         return int(self.lib.hymd_bonded_launch_count(self._h))
 

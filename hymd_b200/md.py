@@ -121,6 +121,8 @@ class RespaMD:
         self.fast = None
         self.bonded_results = {}
         self.fused = bool(fused)
+        import os
+        cta = int(os.environ.get("HYMD_B200_RESPA_CTA", cta))      # tuning override (tools/gpu_md_next.sh)
         self.cta = cta                  # term evaluation of the fused kernel: 1 = once per CTA (measured
                                         # fastest at C4, profiles/r1h_md_bench.json), 0 = per particle
         self.force_out = force_out      # optional [bond, angle, dihedral] (N,3) tensors filled at the

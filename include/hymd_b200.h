@@ -288,6 +288,14 @@ int64_t hymd_bonded_launch_count(hymd_bonded* b);
  * memory.  The environment variable HYMD_B200_BONDED_CTA=1 selects it at creation. */
 int hymd_bonded_set_cta(hymd_bonded* b, int enable);
 
+/* Arithmetic of the bond and angle terms in hymd_bonded_inner_step for float32 positions with per-particle
+ * evaluation.  0 (default): double, term by term like the Fortran.  1: single precision with formulas that
+ * stay accurate there (atan2 of cross and dot products instead of acos, no cancelling subtractions):
+ * <= 1e-5 of the largest force against the double path (measured 3e-7 ... 1.3e-6 on the CPU), i.e. inside the
+ * fp32 build's tolerance, for a fraction of the fp64 instruction count.  HYMD_B200_BONDED_F32MATH=1 selects
+ * it at creation.  Never run on a GPU yet. */
+int hymd_bonded_set_math(hymd_bonded* b, int f32math);
+
 /* One fused inner rRESPA step (main.py:829-893) in a single pass over the particles:
  *   F = bond + angle + dihedral forces at d_pos_in (every kind rounded to `dtype` like the f arrays),
  *   n_kicks (0, 1 or 2) times  v += 0.5*kick_dt * F / mass   -- the closing kick of the previous inner

@@ -101,6 +101,7 @@ struct HostBonded {
     std::vector<TermRec> rec[2];
     int max_terms[3];
     int use_cta;
+    int f32math;
     int tile;                   // particles per CTA (HYMD_B200_BONDED_TILE, default BONDED_THREADS = 128)
     long long launches;
 };
@@ -130,6 +131,7 @@ extern "C" int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t
     b->n = n_particles;
     b->launches = 0;
     b->use_cta = 0;
+    b->f32math = 0;
     b->tile = HOST_THREADS;
     if (const char* env = getenv("HYMD_B200_BONDED_TILE")) {
         b->tile = atoi(env);
@@ -300,11 +302,21 @@ static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, r
 
 extern "C" int hymd_bonded_set_cta(void* h, int enable) { ((HostBonded*)h)->use_cta = enable == 2 ? 2 : (enable ? 1 : 0); return 0; }
 
+extern "C" int host_inner_step_f32(void* h, const float* x_in, float* x_out, float* vel, const double* box,
+                                   double mass, double kick_dt, int n_kicks, double drift_dt, void* const* f_out,
+                                   double* out12);
+extern "C" int hymd_bonded_set_math(void* h, int f32math) { ((HostBonded*)h)->f32math = f32math ? 1 : 0; return 0; }
+
 extern "C" int hymd_bonded_inner_step(void* h, int dtype, const void* x_in, void* x_out, void* vel,
                                       const double* box, double mass, double kick_dt, int n_kicks,
                                       double drift_dt, void* const* f_out, double* out12, void* stream) {
     HostBonded* b = (HostBonded*)h;
     if (n_kicks < 0 || n_kicks > 2 || x_in == x_out) return -1;
+    if (b->f32math && dtype == 0 && !b->use_cta) {
+        b->launches += out12 ? 2 : 1;
+        return host_inner_step_f32(h, (const float*)x_in, (float*)x_out, (float*)vel, box, mass, kick_dt, n_kicks,
+                                   drift_dt, f_out, out12);
+    }
     const Vec3d bx = {box[0], box[1], box[2]};
     b->launches += out12 ? 2 : 1;
     if (dtype == 1) inner<double>(b, 7, (const double*)x_in, (double*)x_out, (double*)vel, bx, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
@@ -325,5 +337,35 @@ extern "C" int host_gpe_kspace(const double* in, double* out_s, double* out_v, c
     p.fs_in = p.fs_s = p.fs_v = 2 * fs;
     for (long long i = 0; i < p.npairs; ++i)
         gpe_kspace_pair<double>(i, in, out_s, out_v, tab, coef, use_h, div_k2, sign, p);
+    return 0;
+}
+
+// ---- single-precision bond / angle evaluators (csrc/bonded_f32.cuh) on host memory -------------------
+#include "../../hymd_b200/csrc/bonded_f32.cuh"
+
+extern "C" int host_inner_step_f32(void* h, const float* x_in, float* x_out, float* vel, const double* box,
+                                   double mass, double kick_dt, int n_kicks, double drift_dt, void* const* f_out,
+                                   double* out12) {
+    HostBonded* b = (HostBonded*)h;
+    TermLists t;
+    for (int k = 0; k < 3; ++k) {
+        t.start[k] = b->start[k].data(); t.refs[k] = b->refs[k].data(); t.idx[k] = b->idx[k].data();
+        t.par[k] = b->par[k].data(); t.n_terms[k] = (long long)(b->idx[k].size() / 4);
+    }
+    t.dih_type = b->dtype.data();
+    const Vec3d bx = {box[0], box[1], box[2]};
+    float* fo[3] = {f_out ? (float*)f_out[0] : nullptr, f_out ? (float*)f_out[1] : nullptr,
+                    f_out ? (float*)f_out[2] : nullptr};
+    double acc12[12] = {0};
+    for (long long p = 0; p < b->n; ++p) {
+        BondAcc acc[3];
+        inner_step_particle_f32(p, x_in, x_out, vel, bx, t, (float)mass, (float)(0.5 * kick_dt), n_kicks,
+                                (float)drift_dt, fo, acc);
+        for (int k = 0; k < 3; ++k) {
+            acc12[4 * k] += acc[k].e; acc12[4 * k + 1] += acc[k].pr.x; acc12[4 * k + 2] += acc[k].pr.y;
+            acc12[4 * k + 3] += acc[k].pr.z;
+        }
+    }
+    if (out12) for (int k = 0; k < 12; ++k) out12[k] = acc12[k];
     return 0;
 }

@@ -19,7 +19,7 @@ import pytest
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-F2 = ["hymd_bonded_set_cta", "hymd_bonded_inner_step", "hymd_bonded_create", "hymd_bonded_destroy", "hymd_bonded_forces", "hymd_bonded_launch_count",
+F2 = ["hymd_bonded_set_math", "hymd_bonded_set_cta", "hymd_bonded_inner_step", "hymd_bonded_create", "hymd_bonded_destroy", "hymd_bonded_forces", "hymd_bonded_launch_count",
       "hymd_md_kick_drift", "hymd_velocity_moments", "hymd_velocity_moments_scratch_doubles",
       "hymd_csvr_apply", "hymd_cancel_com"]
 
@@ -96,3 +96,7 @@ def test_fused_inner_step(emulated, real):
 @pytest.mark.parametrize("real", [np.float32, np.float64])
 def test_cta_cooperative(emulated, real, tile, monkeypatch):
     emulated.test_cta_cooperative_evaluation_matches_the_per_particle_result(real, tile, monkeypatch)
+
+
+def test_f32_math_fused_step(emulated):
+    emulated.test_f32_math_inner_step_stays_within_the_fp32_tolerance()

@@ -363,3 +363,70 @@ def test_gpe_cycle_plan_matches_reference_golden(lib):
     close(vbar, GG[pre + "/Vbar_elec"])
     close(forces, GG[pre + "/elec_forces"])
     assert energy == pytest.approx(float(GG[pre + "/energy"]), rel=1e-9)
+
+
+def test_f32_math_accuracy(lib):
+    """csrc/bonded_f32.cuh (opt-in single-precision arithmetic for the fp32 build) against the float64
+    oracle on the same float32 positions: bonds and angles within 1e-5 of the largest force (the
+    north_star tolerance of the fp32 build), including chains that are straight to 1e-3 rad with
+    180-degree equilibrium angles, where acos-based float arithmetic loses every digit."""
+    rng = np.random.default_rng(17)
+    box = np.array([6.0, 7.0, 5.0])
+    vp = ctypes.c_void_p
+
+    def run(r, a2, a3, t0v):
+        n = len(r)
+        r0, k2 = np.full(len(a2), 0.47), np.full(len(a2), 1250.0)
+        k3 = np.full(len(a3), 25.0)
+        h = vp()
+        empty = i32(np.zeros(0))
+        ia2, ib2 = i32(a2), i32(a2 + 1)
+        ia3, ib3, ic3 = i32(a3), i32(a3 + 1), i32(a3 + 2)
+        lib.hymd_bonded_create.argtypes = None
+        rc = lib.hymd_bonded_create(ctypes.c_int64(n), ctypes.c_int64(len(a2)), ia2.ctypes.data_as(vp),
+                                    ib2.ctypes.data_as(vp), r0.ctypes.data_as(vp), k2.ctypes.data_as(vp),
+                                    ctypes.c_int64(len(a3)), ia3.ctypes.data_as(vp), ib3.ctypes.data_as(vp),
+                                    ic3.ctypes.data_as(vp), t0v.ctypes.data_as(vp), k3.ctypes.data_as(vp),
+                                    ctypes.c_int64(0), empty.ctypes.data_as(vp), empty.ctypes.data_as(vp),
+                                    empty.ctypes.data_as(vp), empty.ctypes.data_as(vp), np.zeros(1).ctypes.data_as(vp),
+                                    empty.ctypes.data_as(vp), ctypes.byref(h))
+        assert rc == 0
+        x = np.ascontiguousarray(r, dtype=np.float32)
+        fb, fa = np.zeros_like(x), np.zeros_like(x)
+        fptr = (vp * 3)(fb.ctypes.data, fa.ctypes.data, None)
+        out = np.zeros(12)
+        bx = np.ascontiguousarray(box)
+        lib.host_inner_step_f32(h, x.ctypes.data_as(vp), None, None, bx.ctypes.data_as(vp), ctypes.c_double(72.0),
+                                ctypes.c_double(0.0), 0, ctypes.c_double(0.0), fptr, out.ctypes.data_as(vp))
+        lib.hymd_bonded_destroy(h)
+        fbo, eb, prb = bo.compute_bond_forces(x, box, a2, a2 + 1, r0, k2)
+        fao, ea, pra = bo.compute_angle_forces(x, box, a3, a3 + 1, a3 + 2, t0v, k3)
+        return (fb, fbo, out[0], eb, out[1:4], prb), (fa, fao, out[4], ea, out[5:8], pra)
+
+    # random-walk chains (all angles), 120 / 180 degree equilibria
+    n_ch, L = 200, 10
+    steps = rng.normal(size=(n_ch, L - 1, 3))
+    steps *= 0.47 * (1.0 + 0.1 * rng.normal(size=(n_ch, L - 1, 1))) / np.linalg.norm(steps, axis=2, keepdims=True)
+    r = (rng.random((n_ch, 1, 3)) * box + np.concatenate([np.zeros((n_ch, 1, 3)), np.cumsum(steps, 1)], 1)).reshape(-1, 3)
+    r = np.mod(r, box)
+    first = (np.arange(n_ch) * L)[:, None]
+    a2 = (first + np.arange(L - 1)[None, :]).ravel()
+    a3 = (first + np.arange(L - 2)[None, :]).ravel()
+    t0v = np.radians(rng.choice([120.0, 180.0], size=len(a3)))
+    for got, want, e, e_ref, pr, pr_ref in run(r, a2, a3, t0v):
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+        assert e == pytest.approx(e_ref, rel=1e-5)
+        assert np.abs(pr - pr_ref).max() <= 1e-5 * max(np.abs(pr_ref).max(), np.abs(want).max())
+    # nearly straight chains (bending 1e-3 .. 3e-2 rad), 180-degree equilibrium: the hard case in float
+    base = rng.normal(size=(n_ch, 1, 3))
+    base /= np.linalg.norm(base, axis=2, keepdims=True)
+    wob = rng.normal(size=(n_ch, L - 1, 3)) * rng.choice([1e-3, 1e-2, 3e-2], size=(n_ch, 1, 1))
+    steps = base + wob
+    steps *= 0.47 * (1.0 + 0.05 * rng.normal(size=(n_ch, L - 1, 1))) / np.linalg.norm(steps, axis=2, keepdims=True)
+    r = (rng.random((n_ch, 1, 3)) * box + np.concatenate([np.zeros((n_ch, 1, 3)), np.cumsum(steps, 1)], 1)).reshape(-1, 3)
+    r = np.mod(r, box)
+    (fb, fbo, *_), (fa, fao, e, e_ref, pr, pr_ref) = run(r, a2, a3, np.full(len(a3), np.pi))
+    scale = max(np.abs(fbo).max(), np.abs(fao).max())
+    assert np.abs(fa - fao).max() <= 1e-5 * scale
+    assert np.abs(fb - fbo).max() <= 1e-5 * scale
+    assert e == pytest.approx(e_ref, rel=1e-3)      # tiny energies (theta - pi)^2 of float32 positions

@@ -31,7 +31,7 @@ from hymd_b200.md import RespaMD  # noqa: E402
 from hymd_b200.synthetic import SPECS  # noqa: E402
 
 
-def build_system(n, mesh, rng):
+def build_system(n, mesh, rng, order="cell", block=4):
     L = float(np.float32((n / 8.37) ** (1.0 / 3.0)))
     nch = n // 40
     steps = rng.normal(size=(nch, 20, 3)).astype(np.float32)
@@ -44,6 +44,13 @@ def build_system(n, mesh, rng):
     first = np.concatenate([chains[:, 0], solvent])
     cell = np.minimum((first * (mesh / L)).astype(np.int64), mesh - 1)
     key = (cell[:, 0] * mesh + cell[:, 1]) * mesh + cell[:, 2]
+    if order == "block":
+        # molecules ordered by (block of block^3 cells, chains before solvent, cell): CTAs of the bonded
+        # kernels become homogeneous again while the field kernels keep block-level locality
+        nb = (mesh + block - 1) // block
+        blk = ((cell[:, 0] // block) * nb + cell[:, 1] // block) * nb + cell[:, 2] // block
+        is_solvent = (np.arange(len(first)) >= nch).astype(np.int64)
+        key = (blk * 2 + is_solvent) * (mesh ** 3) + key
     order = np.argsort(key, kind="stable")
     mlen = np.concatenate([np.full(nch, 20, dtype=np.int64), np.ones(len(solvent), dtype=np.int64)])[order]
     start = np.cumsum(mlen) - mlen
@@ -69,11 +76,14 @@ def main():
     ap.add_argument("--mesh", type=int, default=256)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--inner", type=int, default=25)
+    ap.add_argument("--order", choices=["cell", "block"], default="cell",
+                    help="particle order: cell = what domain_decomposition returns today; block = molecules "
+                         "grouped by (4^3-cell block, has bonds) -- DESIGN.md section 8")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     t0 = time.time()
     rng = np.random.default_rng(1004)
-    L, pos, types, a2, a3 = build_system(args.n, args.mesh, rng)
+    L, pos, types, a2, a3 = build_system(args.n, args.mesh, rng, args.order)
     n = args.n
     names = ["A", "B", "C", "W"]
     cfg = Config(mesh_size=args.mesh, sigma=0.5, kappa=0.05, box_size=[L, L, L], hamiltonian="DefaultWithChi",
@@ -120,6 +130,7 @@ def main():
     en = md.bonded_energies()
     temp = float(T.kinetic_energy(v, cfg.mass)) * 2.0 / (3.0 * Config.gas_constant * n)
     res = {"workload": f"C4 + bonded chains: N={n}, mesh {args.mesh}^3, T=4, respa_inner={args.inner}, CSVR",
+           "order": args.order,
            "ms_per_outer_step": ms, "outer_steps_per_s": 1e3 / ms,
            "ns_per_day": 1e3 / ms * ps_per_step * 1e-3 * 86400.0,
            "particle_steps_per_s": n * 1e3 / ms, "bonds": int(len(a2)), "angles": int(len(a3)),

@@ -12,6 +12,8 @@ for V in "" "HYMD_B200_BONDED_TILE=256" "HYMD_B200_BONDED_TILE=512" "HYMD_B200_B
     env $V timeout 60 python tools/bench_md_e2e.py --out $OUT/e2e_$TAG.json > $OUT/e2e_$TAG.log 2>&1
     echo "$TAG: $(python -c "import json;d=json.load(open('$OUT/e2e_$TAG.json'));print(d['ms_per_outer_step'],'ms',d['ns_per_day'],'ns/day')" 2>&1 | tail -1)"
 done
+timeout 60 python tools/bench_md_e2e.py --order block --out $OUT/e2e_order_block.json > $OUT/e2e_order_block.log 2>&1
+echo "order=block: $(python -c "import json;d=json.load(open('$OUT/e2e_order_block.json'));print(d['ms_per_outer_step'],'ms')" 2>&1 | tail -1)"
 # launch list + one full capture of the fused kernel in the domain_decomposition layout
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/launches.csv \
     python tools/bench_md_e2e.py --steps 1 > $OUT/ncu_launch.log 2>&1

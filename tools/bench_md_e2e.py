@@ -31,7 +31,7 @@ from hymd_b200.md import RespaMD  # noqa: E402
 from hymd_b200.synthetic import SPECS  # noqa: E402
 
 
-def build_system(n, mesh, rng, order="cell", block=4):
+def build_system(n, mesh, rng, order="cell", block=16):
     L = float(np.float32((n / 8.37) ** (1.0 / 3.0)))
     nch = n // 40
     steps = rng.normal(size=(nch, 20, 3)).astype(np.float32)
@@ -78,7 +78,7 @@ def main():
     ap.add_argument("--inner", type=int, default=25)
     ap.add_argument("--order", choices=["cell", "block"], default="cell",
                     help="particle order: cell = what domain_decomposition returns today; block = molecules "
-                         "grouped by (4^3-cell block, has bonds) -- DESIGN.md section 8")
+                         "grouped by (16^3-cell block of ~2400 particles, has bonds) -- DESIGN.md section 8")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     t0 = time.time()

@@ -68,6 +68,37 @@ __global__ void __launch_bounds__(BONDED_THREADS) bonded_kernel(
     }
 }
 
+// bonds / angles with the single-precision evaluators (bonded_f32.cuh; fp32 build, opt-in)
+template <int KIND>
+__global__ void __launch_bounds__(BONDED_THREADS) bonded_f32_kernel(
+    const float* __restrict__ pos, long long n, Vec3d box, const uint32_t* __restrict__ start,
+    const uint32_t* __restrict__ refs, const int32_t* __restrict__ idx, const double* __restrict__ par,
+    float* __restrict__ force, double* __restrict__ partial) {
+    const long long p = (long long)blockIdx.x * BONDED_THREADS + threadIdx.x;
+    BondAcc acc = {{0.0, 0.0, 0.0}, 0.0, {0.0, 0.0, 0.0}};
+    if (p < n) {
+        acc = particle_terms_f32<KIND>(p, pos, box, start, refs, idx, par);
+        force[3 * p + 0] = (float)acc.f.x;
+        force[3 * p + 1] = (float)acc.f.y;
+        force[3 * p + 2] = (float)acc.f.z;
+    }
+    double v[4] = {acc.e, acc.pr.x, acc.pr.y, acc.pr.z};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    __shared__ double sh[BONDED_THREADS / 32][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 4; ++k) sh[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < BONDED_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
+        partial[4 * (long long)blockIdx.x + threadIdx.x] = s;
+    }
+}
+
 struct ForceOut {
     void* f[3];
 };
@@ -304,7 +335,15 @@ static int launch_kind(hymd_bonded* b, int kind, const real* pos, Vec3d box, rea
                        cudaStream_t s) {
     const long long n = b->n_particles;
     const int blocks = (int)((n + BONDED_THREADS - 1) / BONDED_THREADS);
-    if (blocks > 0) {
+    if (blocks > 0 && b->f32math && sizeof(real) == 4 && kind < 2) {
+        if (kind == 0)
+            bonded_f32_kernel<2><<<blocks, BONDED_THREADS, 0, s>>>((const float*)pos, n, box, b->start[0], b->refs[0],
+                                                                 b->idx[0], b->par[0], (float*)force, b->partial);
+        else
+            bonded_f32_kernel<3><<<blocks, BONDED_THREADS, 0, s>>>((const float*)pos, n, box, b->start[1], b->refs[1],
+                                                                 b->idx[1], b->par[1], (float*)force, b->partial);
+        HYMD_LAUNCH_CHECK(b);
+    } else if (blocks > 0) {
         if (kind == 0)
             bonded_kernel<real, 2><<<blocks, BONDED_THREADS, 0, s>>>(
                 pos, n, box, b->start[0], b->refs[0], b->idx[0], b->par[0], nullptr, force, b->partial);

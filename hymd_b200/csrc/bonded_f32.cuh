@@ -84,29 +84,40 @@ __host__ __device__ inline void angle_term_f(const float* __restrict__ pos, Vec3
     }
 }
 
+// One particle's bonds (KIND 2) or angles (KIND 3) with the float evaluators; same result layout as
+// particle_terms (bonded.cuh).
+template <int KIND>
+__host__ __device__ inline BondAcc particle_terms_f32(long long p, const float* __restrict__ pos, Vec3d box,
+                                                      const uint32_t* __restrict__ start,
+                                                      const uint32_t* __restrict__ refs,
+                                                      const int32_t* __restrict__ idx,
+                                                      const double* __restrict__ par) {
+    const Vec3f bf = {(float)box.x, (float)box.y, (float)box.z};
+    BondAccF a = {{0.0f, 0.0f, 0.0f}, 0.0, {0.0, 0.0, 0.0}};
+    for (uint32_t r = start[p]; r < start[p + 1]; ++r) {
+        const uint32_t ref = refs[r];
+        const long long term = ref >> 2;
+        const int slot = (int)(ref & 3u);
+        const int32_t* ix = idx + 4 * term;
+        const float p0 = (float)par[2 * term], p1 = (float)par[2 * term + 1];
+        if (KIND == 2) bond_term_f(pos, bf, ix[0], ix[1], p0, p1, slot, a);
+        else angle_term_f(pos, bf, ix[0], ix[1], ix[2], p0, p1, slot, a);
+    }
+    BondAcc out;
+    out.f = {(double)a.f.x, (double)a.f.y, (double)a.f.z};
+    out.e = a.e;
+    out.pr = a.pr;
+    return out;
+}
+
 // Same contract as inner_step_particle<float> (bonded.cuh) with the float evaluators for bonds and angles.
 __host__ __device__ inline void inner_step_particle_f32(long long p, const float* __restrict__ x_in,
                                                         float* __restrict__ x_out, float* __restrict__ vel,
                                                         Vec3d box, const TermLists& t, float mass, float half_dt,
                                                         int n_kicks, float dt, float* const* f_out, BondAcc* acc) {
     const BondAcc zero = {{0.0, 0.0, 0.0}, 0.0, {0.0, 0.0, 0.0}};
-    const Vec3f bf = {(float)box.x, (float)box.y, (float)box.z};
-    for (int kind = 0; kind < 2; ++kind) {
-        BondAccF a = {{0.0f, 0.0f, 0.0f}, 0.0, {0.0, 0.0, 0.0}};
-        if (t.n_terms[kind])
-            for (uint32_t r = t.start[kind][p]; r < t.start[kind][p + 1]; ++r) {
-                const uint32_t ref = t.refs[kind][r];
-                const long long term = ref >> 2;
-                const int slot = (int)(ref & 3u);
-                const int32_t* ix = t.idx[kind] + 4 * term;
-                const float p0 = (float)t.par[kind][2 * term], p1 = (float)t.par[kind][2 * term + 1];
-                if (kind == 0) bond_term_f(x_in, bf, ix[0], ix[1], p0, p1, slot, a);
-                else angle_term_f(x_in, bf, ix[0], ix[1], ix[2], p0, p1, slot, a);
-            }
-        acc[kind].f = {(double)a.f.x, (double)a.f.y, (double)a.f.z};
-        acc[kind].e = a.e;
-        acc[kind].pr = a.pr;
-    }
+    acc[0] = t.n_terms[0] ? particle_terms_f32<2>(p, x_in, box, t.start[0], t.refs[0], t.idx[0], t.par[0]) : zero;
+    acc[1] = t.n_terms[1] ? particle_terms_f32<3>(p, x_in, box, t.start[1], t.refs[1], t.idx[1], t.par[1]) : zero;
     acc[2] = t.n_terms[2] ? particle_terms<float, 4>(p, x_in, box, t.start[2], t.refs[2], t.idx[2], t.par[2], t.dih_type)
                           : zero;
     finish_particle<float>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);

@@ -159,6 +159,9 @@ extern "C" int64_t hymd_bonded_launch_count(void* b) { return ((HostBonded*)b)->
 template <typename real>
 static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, real* vel, Vec3d box, double mass,
                   double kick_dt, int n_kicks, double drift_dt, void* const* f_out, double* out12);
+extern "C" int host_inner_step_f32(void* h, const float* x_in, float* x_out, float* vel, const double* box,
+                                   double mass, double kick_dt, int n_kicks, double drift_dt, void* const* f_out,
+                                   double* out12);
 
 extern "C" int hymd_bonded_forces(void* h, int kind, int dtype, const void* pos, const double* box,
                                   void* force, double* out, void* stream) {
@@ -166,6 +169,15 @@ extern "C" int hymd_bonded_forces(void* h, int kind, int dtype, const void* pos,
     const int k = kind - 2;
     const Vec3d bx = {box[0], box[1], box[2]};
     b->launches += 2;
+    if (b->f32math && dtype == 0 && !b->use_cta && k < 2) {
+        void* fo1[3] = {nullptr, nullptr, nullptr};
+        fo1[k] = force;
+        double o12[12];
+        host_inner_step_f32(h, (const float*)pos, nullptr, nullptr, box, 1.0, 0.0, 0, 0.0, fo1, o12);
+        // (the fused f32 evaluator with the other kinds present but unrequested gives the same kind-k result)
+        for (int j = 0; j < 4; ++j) out[j] = o12[4 * k + j];
+        return 0;
+    }
     if (b->use_cta) {
         void* fo[3] = {nullptr, nullptr, nullptr};
         fo[k] = force;

@@ -472,6 +472,17 @@ def test_f32_math_inner_step_stays_within_the_fp32_tolerance():
         v, x2 = dev(v0, np.float32), torch.empty_like(x)
         e = topo.inner_step(x, x2, v, box, 72.0, 0.01, 2, 0.01, force_out=f).clone()
         res[f32] = ([t.cpu().numpy().astype(np.float64) for t in f], v.cpu().numpy(), x2.cpu().numpy(), e.cpu().numpy())
+    # the standalone bond / angle kernels follow the same switch
+    for kind in (2, 3):
+        out = {}
+        for f32 in (False, True):
+            topo.set_math(f32)
+            fk = torch.zeros((n, 3), dtype=torch.float32, device=DEVICE)
+            ek = topo.forces(kind, x, box, fk).clone()
+            out[f32] = (fk.cpu().numpy().astype(np.float64), ek.cpu().numpy())
+        assert np.abs(out[True][0] - out[False][0]).max() <= 1e-5 * np.abs(out[False][0]).max()
+        assert out[True][1][0] == pytest.approx(out[False][1][0], rel=1e-5)
+        assert np.abs(out[True][0] - res[True][0][kind - 2]).max() <= 1e-6 * np.abs(out[False][0]).max()
     topo.set_math(False)
     scale = max(np.abs(t).max() for t in res[False][0])
     for k in range(3):

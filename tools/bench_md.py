@@ -119,6 +119,17 @@ def main():
         except Exception as exc:   # keep the lines measured so far
             res[tag + "_error"] = repr(exc)
     topo.set_cta(0)
+    try:    # single-precision bond / angle arithmetic (hymd_bonded_set_math)
+        topo.set_math(True)
+        ms = timed(lambda: topo.forces(2, x, box, fb), args.iters)
+        line("bonds_f32math", ms, n * 28 + len(a2) * (16 + 16 + 8))
+        ms = timed(lambda: topo.forces(3, x, box, fa), args.iters)
+        line("angles_f32math", ms, n * 28 + len(a3) * (16 + 16 + 12))
+        ms = timed(lambda: topo.inner_step(x3, x4, v4, box, 72.0, 0.01, 2, 0.0, want_energies=False), args.iters)
+        line("fused_inner_step_f32math", ms, fused_bytes)
+    except Exception as exc:
+        res["f32math_error"] = repr(exc)
+    topo.set_math(False)
     inner = res["kick_drift_2forces"]["ms"] + res["bonds"]["ms"] + res["angles"]["ms"] + res["kick_2forces"]["ms"]
     res["inner_rrespa_step_ms"] = inner
     res["launches_topology"] = topo.launch_count()

@@ -22,7 +22,7 @@ struct hymd_bonded {
     hymd::TermRec* rec[2];       // inline bond / angle records of the CTA lists (mode 2)
     int max_terms[3];
     size_t cta_smem;             // dynamic shared memory of inner_step_cta_kernel
-    int use_cta;                 // HYMD_B200_BONDED_CTA / hymd_bonded_set_cta: 0, 1 or 2
+    int use_cta;                 // HYMD_B200_BONDED_CTA / hymd_bonded_set_cta: 0, 1, 2 or 3
     int tile;                    // particles per CTA of the cooperative kernels (HYMD_B200_BONDED_TILE)
     int f32math;                 // hymd_bonded_set_math / HYMD_B200_BONDED_F32MATH: float arithmetic for bonds
                                  // and angles in the fp32 build's per-particle fused step (bonded_f32.cuh)
@@ -235,12 +235,54 @@ __global__ void __launch_bounds__(BONDED_THREADS) inner_step_cta2_kernel(
     double v[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) v[k] = 0.0;
-    cta2_eval_terms<real>((int)threadIdx.x, BONDED_THREADS, cta, p0, p1, x, box, t, c, rc, vecs, v);
+    cta2_eval_terms<real, PosTile<real>>((int)threadIdx.x, BONDED_THREADS, cta, p0, p1, x, box, t, c, rc, vecs, v);
     __syncthreads();
     real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
     for (long long p = first; p < p1; p += BONDED_THREADS) {
         BondAcc acc[3];
         cta_gather_bounds(p == first ? rb0 : ref_bounds(p, t), c, vecs, acc);
+        finish_particle<real>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+    __shared__ double sh[BONDED_THREADS / 32][12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 12; ++k) sh[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < BONDED_THREADS / 32; ++w2) s += sh[w2][threadIdx.x];
+        partial[12 * (long long)blockIdx.x + threadIdx.x] = s;
+    }
+}
+
+// Mode 3: inline term records like mode 2, positions read from global memory like mode 1: one dependent
+// load level less than mode 1 without mode 2's staging barrier.
+template <typename real>
+__global__ void __launch_bounds__(BONDED_THREADS) inner_step_cta3_kernel(
+    const real* __restrict__ x_in, real* __restrict__ x_out, real* __restrict__ vel, long long n, Vec3d box,
+    TermLists t, CtaLists c, CtaRecs rc, int tile, real mass, real half_dt, int n_kicks, real dt, ForceOut fo,
+    double* __restrict__ partial) {
+    extern __shared__ double sm[];
+    const long long cta = blockIdx.x;
+    const long long p0 = cta * tile;
+    const long long p1 = p0 + tile < n ? p0 + tile : n;
+    const long long first = p0 + threadIdx.x;
+    RefBounds rb0;
+    if (first < p1) rb0 = ref_bounds(first, t);
+    double v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = 0.0;
+    const real* xg = x_in;     // plain pointer: the accessor parameter is a const reference
+    cta2_eval_terms<real, const real*>((int)threadIdx.x, BONDED_THREADS, cta, p0, p1, xg, box, t, c, rc, sm, v);
+    __syncthreads();
+    real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
+    for (long long p = first; p < p1; p += BONDED_THREADS) {
+        BondAcc acc[3];
+        cta_gather_bounds(p == first ? rb0 : ref_bounds(p, t), c, sm, acc);
         finish_particle<real>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);
     }
 #pragma unroll
@@ -386,7 +428,14 @@ static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x
                                                               (float)drift_dt, fo, b->partial);
         HYMD_LAUNCH_CHECK(b);
     } else if (blocks > 0) {
-        if (b->use_cta == 2) {
+        if (b->use_cta == 3) {
+            CtaRecs rc;
+            rc.rec[0] = b->rec[0];
+            rc.rec[1] = b->rec[1];
+            inner_step_cta3_kernel<real><<<blocks, BONDED_THREADS, b->cta_smem, s>>>(
+                x_in, x_out, vel, n, box, t, c, rc, b->tile, (real)mass, (real)(0.5 * kick_dt), n_kicks,
+                (real)drift_dt, fo, b->partial);
+        } else if (b->use_cta == 2) {
             CtaRecs rc;
             rc.rec[0] = b->rec[0];
             rc.rec[1] = b->rec[1];
@@ -434,8 +483,10 @@ static int set_cta(hymd_bonded* b, int enable) {
         HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta_kernel<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta2_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HYMD_CUDA(cudaFuncSetAttribute(inner_step_cta3_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     }
-    b->use_cta = enable == 2 ? 2 : 1;
+    b->use_cta = (enable == 2 || enable == 3) ? enable : 1;
     return HYMD_OK;
 }
 

@@ -464,9 +464,11 @@ inline void build_cta_records(const std::vector<uint32_t>& cta_terms, const int3
     }
 }
 
-template <typename real>
+// P = PosTile<real> (mode 2: own positions staged in shared memory) or const real* (mode 3: inline
+// records only, positions straight from global memory / L2, no staging barrier).
+template <typename real, typename P>
 __host__ __device__ inline void cta2_eval_terms(int tid, int nthreads, long long cta, long long p0, long long p1,
-                                                const PosTile<real>& x, Vec3d box, const TermLists& t,
+                                                const P& x, Vec3d box, const TermLists& t,
                                                 const CtaLists& c, const CtaRecs& rc, double* __restrict__ sm,
                                                 double* own) {
     double* sm2 = sm;

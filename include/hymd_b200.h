@@ -284,7 +284,9 @@ int64_t hymd_bonded_launch_count(hymd_bonded* b);
 /* Evaluation strategy of hymd_bonded_forces / hymd_bonded_inner_step.  0 (default): every particle
  * re-evaluates the terms it takes part in.  1: every CTA of 128 consecutive particles evaluates each
  * term touching it once into shared memory and the particles gather their slots (2-4x fewer
- * evaluations; bitwise the same forces).  HYMD_ERR_CAPACITY if a CTA's term list does not fit in shared
+ * evaluations; the same forces).  2: as 1 with the bond / angle records stored inline in the CTA lists
+ * and the CTA's own positions staged in shared memory.  3: inline records, positions from global memory
+ * (not yet run on a GPU).  HYMD_ERR_CAPACITY if a CTA's term list does not fit in shared
  * memory.  The environment variable HYMD_B200_BONDED_CTA=1 selects it at creation. */
 int hymd_bonded_set_cta(hymd_bonded* b, int enable);
 

@@ -279,7 +279,13 @@ static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, r
         for (long long cta = 0; cta < n_cta; ++cta) {
             const long long p0 = cta * b->tile, p1 = p0 + b->tile < b->n ? p0 + b->tile : b->n;
             for (size_t i = 0; i < sm.size(); ++i) sm[i] = -777.0;      // stale data must never be read
-            if (b->use_cta == 2) {      // mode 2: own positions staged, inline records
+            if (b->use_cta == 3) {      // mode 3: inline records, positions from global memory
+                CtaRecs rc;
+                rc.rec[0] = b->rec[0].data();
+                rc.rec[1] = b->rec[1].data();
+                for (int tid = 0; tid < HOST_CTA; ++tid)
+                    cta2_eval_terms<real, const real*>(tid, HOST_CTA, cta, p0, p1, x_in, box, t, c, rc, sm.data(), acc12);
+            } else if (b->use_cta == 2) {      // mode 2: own positions staged, inline records
                 std::vector<real> tile((size_t)3 * b->tile, (real)-555);
                 for (long long i = 0; i < 3 * (p1 - p0); ++i) tile[i] = x_in[3 * p0 + i];
                 const PosTile<real> xt = {x_in, tile.data(), p0, p1};
@@ -287,7 +293,7 @@ static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, r
                 rc.rec[0] = b->rec[0].data();
                 rc.rec[1] = b->rec[1].data();
                 for (int tid = 0; tid < HOST_CTA; ++tid)
-                    cta2_eval_terms<real>(tid, HOST_CTA, cta, p0, p1, xt, box, t, c, rc, sm.data(), acc12);
+                    cta2_eval_terms<real, PosTile<real>>(tid, HOST_CTA, cta, p0, p1, xt, box, t, c, rc, sm.data(), acc12);
             } else
                 for (int tid = 0; tid < HOST_CTA; ++tid)
                     cta_eval_terms<real>(tid, HOST_CTA, cta, p0, p1, x_in, box, t, c, sm.data(), acc12);
@@ -312,7 +318,7 @@ static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, r
     if (out12) for (int k = 0; k < 12; ++k) out12[k] = acc12[k];
 }
 
-extern "C" int hymd_bonded_set_cta(void* h, int enable) { ((HostBonded*)h)->use_cta = enable == 2 ? 2 : (enable ? 1 : 0); return 0; }
+extern "C" int hymd_bonded_set_cta(void* h, int enable) { ((HostBonded*)h)->use_cta = (enable == 2 || enable == 3) ? enable : (enable ? 1 : 0); return 0; }
 
 extern "C" int host_inner_step_f32(void* h, const float* x_in, float* x_out, float* vel, const double* box,
                                    double mass, double kick_dt, int n_kicks, double drift_dt, void* const* f_out,

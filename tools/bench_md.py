@@ -107,7 +107,7 @@ def main():
     fused_bytes = n * 12 * 4 + len(a2) * 40 + len(a3) * 44 + n * 8
     ms = timed(lambda: topo.inner_step(x3, x4, v4, box, 72.0, 0.01, 2, 0.0, want_energies=False), args.iters)
     line("fused_inner_step", ms, fused_bytes)
-    for mode, tag in ((1, "cta"), (2, "cta2")):    # CTA-cooperative term evaluation (hymd_bonded_set_cta)
+    for mode, tag in ((1, "cta"), (2, "cta2"), (3, "cta3")):    # CTA-cooperative term evaluation (hymd_bonded_set_cta)
         try:
             topo.set_cta(mode)
             ms = timed(lambda: topo.forces(2, x, box, fb), args.iters)

@@ -3,10 +3,11 @@
 # changes, then measure the variants of the fused inner-step kernel end to end and profile it.
 #   gpurun --timeout 600 -- 'bash tools/gpu_md_next.sh'
 OUT=gpurun_out/r2md; mkdir -p $OUT
-timeout 120 python -m pytest tests/test_zgpu_md.py -q -m gpu --tb=short > $OUT/pytest.log 2>&1; tail -5 $OUT/pytest.log
+HYMD_TEST_CTA3=1 timeout 120 python -m pytest tests/test_zgpu_md.py -q -m gpu -rxX --tb=short > $OUT/pytest.log 2>&1; tail -5 $OUT/pytest.log
 timeout 60 python tools/bench_md.py --out $OUT/md_bench.json > $OUT/md_bench.log 2>&1; tail -1 $OUT/md_bench.log | cut -c1-400
 for V in "" "HYMD_B200_BONDED_TILE=256" "HYMD_B200_BONDED_TILE=512" "HYMD_B200_BONDED_TILE=1024" \
          "HYMD_B200_BONDED_OCC=6" "HYMD_B200_BONDED_OCC=8" "HYMD_B200_BONDED_TILE=512 HYMD_B200_BONDED_OCC=6" \
+         "HYMD_B200_RESPA_CTA=3" "HYMD_B200_RESPA_CTA=3 HYMD_B200_BONDED_TILE=512" \
          "HYMD_B200_RESPA_CTA=0" "HYMD_B200_RESPA_CTA=0 HYMD_B200_BONDED_F32MATH=1"; do
     TAG=$(echo "${V:-default}" | tr ' =' '__')
     env $V timeout 60 python tools/bench_md_e2e.py --out $OUT/e2e_$TAG.json > $OUT/e2e_$TAG.log 2>&1

@@ -259,14 +259,27 @@ def _first_atom_positions(pm, positions, molecules):
     return pos[first[inv]]
 
 
-def _cell_order(pm, route):
+def _cell_order(pm, route, molecules=None, block=0):
     """Stable permutation sorting the local particles by the mesh cell of their routing
-    position (x slowest, z fastest = the storage order of the meshes)."""
+    position (x slowest, z fastest = the storage order of the meshes).
+
+    ``block > 0`` (``HYMD_B200_DD_BLOCK``, opt-in, needs ``molecules``): the primary key becomes (block
+    of ``block``^3 cells, single-bead molecule?), the cell order is kept inside every such group.  The
+    CTAs of the bonded kernels then hold either chain beads or solvent, not a mix,
+    while the field kernels keep their locality at block granularity."""
     mesh = torch.as_tensor(np.asarray(pm.Nmesh, dtype=np.int64), device=pm.device)
     scale = torch.as_tensor(np.asarray(pm.Nmesh, dtype=np.float64) / np.asarray(pm.BoxSize, dtype=np.float64),
                             device=pm.device)
     c = torch.remainder(torch.floor(route.double() * scale).long(), mesh)
     key = (c[:, 0] * mesh[1] + c[:, 1]) * mesh[2] + c[:, 2]
+    if block > 0 and molecules is not None:
+        mol = torch.as_tensor(np.asarray(molecules)) if not isinstance(molecules, torch.Tensor) else molecules
+        mol = mol.to(pm.device).long().reshape(-1)
+        _, inv, counts = torch.unique(mol, return_inverse=True, return_counts=True)
+        single = (counts[inv] == 1).long()
+        nb = (mesh + block - 1) // block
+        blk = ((c[:, 0] // block) * nb[1] + c[:, 1] // block) * nb[2] + c[:, 2] // block
+        key = (blk * 2 + single) * (mesh[0] * mesh[1] * mesh[2]) + key
     return torch.sort(key, stable=True).indices
 
 
@@ -304,7 +317,8 @@ def domain_decomposition(positions, pm, *args, molecules=None, bonds=None, topol
             route = pm.as_device(arrays[0])
         else:
             route = _first_atom_positions(pm, arrays[0], arrays[-1])
-        perm = _cell_order(pm, route)
+        perm = _cell_order(pm, route, None if molecules is None else arrays[-1],
+                           int(os.environ.get("HYMD_B200_DD_BLOCK", "0")))
         arrays = tuple(_take_rows(a, perm) for a in arrays)
         pm.reset_order()
     return tuple(arrays)

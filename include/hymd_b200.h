@@ -262,7 +262,8 @@ int hymd_gpe_energy(hymd_ctx* ctx, double coulomb_constant, double* out, void* s
  * of local particle indices and parameters).  coeff4 is bonds_4_coeff (n4,6,5) row-major, type4 is
  * bonds_4_type; dih_type 1 (combined bending-torsion with dipole reconstruction,
  * dipole_reconstruction.f90:50-221) is rejected with HYMD_ERR_INVALID.  Synchronous.  Rebuild after
- * domain_decomposition permutes the particles (main.py:1239-1262 does the same with prepare_bonds). */
+ * domain_decomposition permutes the particles (main.py:1239-1262 does the same with prepare_bonds).
+ * A hymd_bonded owns one set of reduction scratch buffers: use it from one stream at a time. */
 typedef struct hymd_bonded hymd_bonded;
 int hymd_bonded_create(int64_t n_particles,
                        int64_t n2, const int32_t* a2, const int32_t* b2, const double* r0_2, const double* k_2,

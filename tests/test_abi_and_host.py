@@ -183,3 +183,32 @@ def test_row_f2_needs_a_gpu_and_says_so():
         force.compute_bond_forces(np.zeros_like(r), r, np.ones(3), a, a + 1, np.ones(3), np.ones(3))
     with pytest.raises(_lib.HymdError):
         thermostat.cancel_com_momentum(np.zeros((4, 3)), type("C", (), {"n_particles": 4})())
+
+
+def test_block_ordering_keeps_molecules_whole_and_separates_chains_from_solvent():
+    """HYMD_B200_DD_BLOCK (hymd_b200.field._cell_order with block > 0), on CPU tensors: a permutation,
+    molecules contiguous with their internal order kept, and 128-particle tiles mostly homogeneous."""
+    import types
+
+    import numpy as np
+    import torch
+    from hymd_b200 import field as F
+    pm = types.SimpleNamespace(Nmesh=np.array([32, 32, 32]), BoxSize=np.array([13.0, 13.0, 13.0]),
+                               device=torch.device("cpu"))
+    rng = np.random.default_rng(0)
+    nch, length, nsol = 400, 10, 4000
+    first = rng.random((nch, 1, 3)) * 13
+    pos = torch.tensor(np.concatenate([(first + np.zeros((nch, length, 3))).reshape(-1, 3), rng.random((nsol, 3)) * 13]))
+    mol = torch.tensor(np.concatenate([np.repeat(np.arange(nch), length), nch + np.arange(nsol)]))
+    n = len(pos)
+    for block in (0, 16):
+        perm = F._cell_order(pm, pos, mol, block).numpy()
+        assert sorted(perm.tolist()) == list(range(n))
+        m = mol.numpy()[perm]
+        starts = np.nonzero(np.diff(m, prepend=-1))[0]
+        assert len(starts) == nch + nsol                       # every molecule is one contiguous run
+        chain_rows = perm[m < nch].reshape(nch, length)
+        assert (np.diff(chain_rows, axis=1) == 1).all()        # internal order kept
+    single = (np.arange(n) >= nch * length)[perm]
+    tiles = single[: n // 128 * 128].reshape(-1, 128).mean(axis=1)
+    assert ((tiles > 0) & (tiles < 1)).mean() < 0.4            # cell order alone: every tile is mixed

@@ -109,6 +109,17 @@ def update_field(phi, phi_laplacian, phi_transfer, layouts, force_mesh, hamilton
 
 def _output_buffer(pm, out, n):
     """Device tensor the kernel writes into, and a callback copying it back if needed."""
+    if getattr(pm, "auto_route", False):
+        # the kernel writes the working set's rows; they travel back to their owners afterwards
+        buf = torch.empty((n, 3), dtype=pm.dtype, device=pm.device)
+
+        def routed_back():
+            res = pm.route_back(buf)
+            if isinstance(out, torch.Tensor):
+                out.copy_(res)
+            else:
+                out[...] = res.cpu().numpy()
+        return buf, routed_back
     if isinstance(out, torch.Tensor) and out.device == pm.device and out.dtype == pm.dtype \
             and out.is_contiguous() and tuple(out.shape) == (n, 3):
         return out, None

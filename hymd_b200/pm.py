@@ -157,6 +157,11 @@ class ParticleMesh:
         self._keep = (None, None, None)
         self._n_local = 0
         self._sorted_with_charges = False
+        # per-step routing of particles that are not on the rank owning their slab (pmesh's
+        # Layout.exchange inside paint / readout): opt-in until it has run on several GPUs
+        import os
+        self.auto_route = self.world_size > 1 and os.environ.get("HYMD_B200_AUTO_ROUTE", "0") == "1"
+        self._route = None
         if hamiltonian is None:
             hamiltonian = get_hamiltonian(config) if _has_density_params(config) else None
         cfg = self._make_config(config, hamiltonian)
@@ -315,6 +320,11 @@ class ParticleMesh:
         tk = None if types is None else self._fingerprint_types(types)
         if not force and pk == self._sort_key and (tk is None or tk == self._sort_types_key):
             if charges is not None and not self._sorted_with_charges:
+                if self.auto_route:      # same positions => same plan => same working order
+                    saved = self._route
+                    _, charges = self.route_in(positions, charges)
+                    self._route = saved
+                    self._sort_key, self._sort_types_key = pk, tk     # migrate() cleared them
                 q = self.as_device(charges, shape=(self._n_local,))
                 _lib.check(self.lib.hymd_set_charges(self._ctx, ctypes.c_void_p(q.data_ptr()),
                                                      self.stream))
@@ -324,6 +334,10 @@ class ParticleMesh:
         pos = self.as_device(positions)
         if pos.ndim != 2 or pos.shape[1] != 3:
             raise ValueError(f"positions must be (N,3), got {tuple(pos.shape)}")
+        if self.auto_route:
+            # working set = residents at home + guests from the other ranks; its composition changes
+            # from step to step, so every routed sort is a cold one (migrate() forgets the order)
+            pos, types, charges = self.route_in(pos, types, charges)
         n = pos.shape[0]
         # Consecutive MD steps pass the same types object (HyMD reads the types once,
         # main.py:72-125): the library then re-bins starting from the previous cell order and
@@ -432,6 +446,41 @@ class ParticleMesh:
             dist.all_reduce(s)
         v = s.item()
         return v
+
+    # ---- per-step routing (world_size > 1, HYMD_B200_AUTO_ROUTE=1) ---------------------------------
+    # The reference never requires a particle to sit on the rank that owns its mesh cell: pm.decompose
+    # routes copies to the owners for the paint and brings the read-out values back
+    # (main.py:977-980, field.py:200).  Molecules make this the normal case: domain_decomposition keeps a
+    # molecule on the rank of its FIRST bead (field.py:1156-1163), so beads of chains that straddle a slab
+    # face are guests on their rank.  route_in / route_back do the same with the migration kernels: the
+    # working set of a field call is "my particles that are at home + the guests the other ranks sent
+    # me", and results travel back by a second migration whose routing position is a point inside the
+    # origin rank's slab.
+    def route_in(self, positions, *arrays):
+        """Working copies of ``positions`` and ``arrays`` on the ranks owning the particles' slabs."""
+        pos = self.as_device(positions)
+        n = pos.shape[0]
+        origin_rank = torch.full((n,), self.rank, dtype=torch.int32, device=self.device)
+        origin_index = torch.arange(n, dtype=torch.int64, device=self.device)
+        keep = [a for a in arrays if a is not None]
+        out = self.migrate(pos, *keep, origin_rank, origin_index)
+        self._route = {"n": n, "rank": out[-2], "index": out[-1]}
+        it = iter(out[1:-2])
+        return (out[0],) + tuple(None if a is None else next(it) for a in arrays)
+
+    def route_back(self, values):
+        """Per-particle results of the working set (rows as ``route_in`` returned them) back to the
+        caller's particles, in the caller's order."""
+        r = self._route
+        if r is None or values.shape[0] != r["rank"].shape[0]:
+            raise _lib.HymdError("route_back without a matching route_in")
+        slab = float(self.BoxSize[0]) / self.world_size
+        fake = torch.zeros((values.shape[0], 3), dtype=self.dtype, device=self.device)
+        fake[:, 0] = ((r["rank"].to(torch.float64) + 0.5) * slab).to(self.dtype)
+        back, index = self.migrate(values, r["index"], routing_positions=fake)
+        out = torch.empty((r["n"],) + tuple(values.shape[1:]), dtype=values.dtype, device=self.device)
+        out[index] = back
+        return out
 
     def migrate(self, positions, *arrays, routing_positions=None):
         """Re-home per-particle arrays on the rank owning their slab (``Layout.exchange`` of

@@ -38,6 +38,9 @@ def main():
     ap.add_argument("--particles", dest="n", type=int, default=20000)
     ap.add_argument("--migrate", action="store_true")
     ap.add_argument("--guests", action="store_true")
+    ap.add_argument("--route", action="store_true",
+                    help="arbitrary share WITHOUT re-homing, HYMD_B200_AUTO_ROUTE=1 in the environment: the "
+                         "per-step routing layer must make the cycle equal the oracle")
     ap.add_argument("--seed", type=int, default=11)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -69,7 +72,7 @@ def main():
     # ownership
     nxl = args.mesh[0] // world
     cell = np.floor(pos[:, 0].astype(np.float64) * args.mesh[0] / float(box[0])).astype(np.int64) % args.mesh[0]
-    if args.migrate or args.guests:
+    if args.migrate or args.guests or args.route:
         mine = (np.arange(n) % world) == rank          # arbitrary share, most particles not home
     else:
         mine = (cell // nxl) == rank

@@ -318,10 +318,10 @@ def test_fused_inner_step_equals_separate_launches(real):
         assert out[True][2][k] == pytest.approx(out[False][2][k], rel=1e-6 if real == np.float32 else 1e-11)
 
 
+@pytest.mark.parametrize("real", [np.float32, np.float64])
 @pytest.mark.parametrize("tile", [128, pytest.param(512, marks=pytest.mark.xfail(
     strict=False, reason="several particles per thread + opt-in shared memory > 48 KB: CPU-verified only, first "
-                         "GPU run is the driver's (XPASS = verified)"))])
-@pytest.mark.parametrize("real", [np.float32, np.float64])
+                         "GPU run is the driver's (XPASS = verified)"))])      # unverified cases run last
 def test_cta_cooperative_evaluation_matches_the_per_particle_result(real, tile, monkeypatch):
     """hymd_bonded_set_cta(1): each CTA evaluates every term touching its 128 particles once into shared
     memory and the particles gather their slots.  Same additions in the same order => the forces equal the

@@ -100,3 +100,7 @@ def test_cta_cooperative(emulated, real, tile, monkeypatch):
 
 def test_f32_math_fused_step(emulated):
     emulated.test_f32_math_inner_step_stays_within_the_fp32_tolerance()
+
+
+def test_fused_step_edge_cases(emulated):
+    emulated.test_fused_step_edge_cases()

@@ -318,6 +318,45 @@ def test_fused_inner_step_equals_separate_launches(real):
         assert out[True][2][k] == pytest.approx(out[False][2][k], rel=1e-6 if real == np.float32 else 1e-11)
 
 
+def test_fused_step_edge_cases():
+    """Empty topology (monatomic system), a single particle, and a 129-particle chain whose terms straddle
+    the CTA boundary, through the fused inner step in per-particle and CTA-cooperative mode."""
+    from hymd_b200.force import BondedTopology
+    box = np.array([50.0, 50.0, 50.0])
+    rng = np.random.default_rng(3)
+    for n in (1, 7):
+        topo = BondedTopology(n, device=DEVICE if DEVICE != "cuda" else None)
+        x = dev(rng.random((n, 3)) * 5, np.float64)
+        v = dev(rng.normal(size=(n, 3)), np.float64)
+        for cta in (0, 1):
+            x1, v1, x2 = x.clone(), v.clone(), torch.empty_like(x)
+            res = topo.inner_step(x1, x2, v1, box, 72.0, 0.01, 2, 0.01, cta=cta)
+            assert float(res.abs().max()) == 0.0 and torch.equal(v1, v)          # no forces: pure drift
+            assert torch.allclose(x2, x + 0.01 * v, rtol=0, atol=1e-14)
+    n = 129
+    steps = rng.normal(size=(n - 1, 3))
+    steps *= 0.3 / np.linalg.norm(steps, axis=1)[:, None]
+    r = 10.0 + np.concatenate([np.zeros((1, 3)), np.cumsum(steps, 0)])
+    a2, a3, a4 = np.arange(n - 1), np.arange(n - 2), np.arange(n - 3)
+    coeff = np.zeros((n - 3, 6, 5))
+    coeff[:, 0, 1:3] = [1.0, -0.5]
+    terms = dict(bonds=(a2, a2 + 1, np.full(n - 1, 0.25), np.full(n - 1, 500.0)),
+                 angles=(a3, a3 + 1, a3 + 2, np.full(n - 2, 2.0), np.full(n - 2, 20.0)),
+                 dihedrals=(a4, a4 + 1, a4 + 2, a4 + 3, coeff, np.zeros(n - 3, dtype=int)))
+    topo = BondedTopology(n, device=DEVICE if DEVICE != "cuda" else None, **terms)
+    fb, eb, _ = bo.compute_bond_forces(r, box, *terms["bonds"])
+    fa, ea, _ = bo.compute_angle_forces(r, box, *terms["angles"])
+    fd, ed = bo.compute_dihedral_forces(r, box, *terms["dihedrals"])
+    x = dev(r, np.float64)
+    for cta in (0, 1, 2):
+        f = [torch.zeros((n, 3), dtype=torch.float64, device=DEVICE) for _ in range(3)]
+        res = topo.inner_step(x, None, torch.zeros_like(x), box, 72.0, 0.0, 0, 0.0, force_out=f, cta=cta).clone()
+        for got, want in zip(f, (fb, fa, fd)):
+            assert np.abs(got.cpu().numpy() - want).max() <= 1e-10 * np.abs(want).max()
+        np.testing.assert_allclose(res[:, 0].cpu().numpy(), [eb, ea, ed], rtol=1e-11)
+    topo.set_cta(0)
+
+
 @pytest.mark.parametrize("real", [np.float32, np.float64])
 @pytest.mark.parametrize("tile", [128, pytest.param(512, marks=pytest.mark.xfail(
     strict=False, reason="several particles per thread + opt-in shared memory > 48 KB: CPU-verified only, first "

@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--mesh", type=int, default=None, help="override mesh size (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--parity-max-n", type=int, default=25_000_000,
+                    help="largest global particle count for which rank 0 runs a CPU oracle cycle "
+                         "and compares every particle's force (above: momentum conservation only)")
     ap.add_argument("--no-dd", action="store_true",
                     help="skip the start-up domain_decomposition call (main.py:274-300): the "
                          "particles then stay in the generator's molecule order instead of the "
@@ -159,53 +162,108 @@ def algorithmic_bytes(N, T, U, mesh, b, pme):
     return out
 
 
+def workload_config(args, world, cfg, n_global, pme):
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm of
+    one invocation (the driver compares them)."""
+    from hymd_b200.hamiltonian import affine_parameters, get_hamiltonian
+    mesh = [int(x) for x in np.full(3, cfg.mesh_size)]
+    T = cfg.n_types
+    A, c = affine_parameters(get_hamiltonian(cfg), T)
+    U = len({(tuple(A[t]), c[t]) for t in range(T)})
+    return {"workload": f"{args.workload}: N={n_global}, mesh {mesh[0]}x{mesh[1]}x{mesh[2]}, "
+                        f"T={T} (U={U} distinct potential rows), sigma={cfg.sigma}, "
+                        f"kappa={cfg.kappa}, DefaultWithChi" + (", PME" if pme else ""),
+            "inputs": f"{NBUF} trajectory frames visited ping-pong, consecutive frames differ by one "
+                      "outer step of thermal motion (0.25 ps at 323 K, ~0.05 nm)",
+            "parallelism": "single GPU" if world == 1 else
+                           f"{world} x-slabs: slab FFT with transposes and halos stored into peer HBM "
+                           "over NVLink (CUDA IPC), particles routed to their slab every step inside "
+                           "the timed loop"}
+
+
+NBUF = 6
+
+
+class OracleCycle:
+    """The CPU restatement of the cycle (threaded C CIC loops + scipy.fft on all cores); the mesh
+    state is allocated once, like the reference's initialize_pm."""
+
+    def __init__(self, cfg, dtype):
+        import copy
+        from oracle import field_oracle as fo
+        from oracle.hamiltonian_oracle import OracleHamiltonian
+        self.fo, self.dtype = fo, dtype
+        self.cfg = copy.deepcopy(cfg)
+        self.h = OracleHamiltonian(self.cfg)
+        self.st = fo.FieldState(self.cfg, dtype)
+
+    def __call__(self, pos, typ, q):
+        fo, cfg = self.fo, self.cfg
+        pos = np.ascontiguousarray(pos, dtype=self.dtype)
+        t0 = time.perf_counter()
+        fo.update_field(self.st, self.h, pos, typ, cfg, workers=-1, mt=True)
+        f = fo.compute_field_force(self.st, pos, typ, cfg.n_types, mt=True)
+        ef = None
+        if q is not None:
+            ef = fo.update_field_force_q(self.st, self.h, np.asarray(q, dtype=self.dtype), pos, cfg,
+                                         workers=-1, mt=True)
+        return f, ef, time.perf_counter() - t0
+
+
+def oracle_cycle(cfg, pos, typ, q, dtype):
+    return OracleCycle(cfg, dtype)(pos, typ, q)
+
+
 def run_reference(args, rank, world):
     """CPU port of the reference path (oracle/), all host threads; rank 0 only."""
     if rank != 0:
         return
-    import copy
     from hymd_b200.synthetic import SPECS, make_system
-    from oracle import field_oracle as fo
-    from oracle.hamiltonian_oracle import OracleHamiltonian
     dtype = np.float32 if args.dtype == "f32" else np.float64
     spec = SPECS[args.workload]
     n_full, mesh_full = args.n or spec["n"], args.mesh or spec["mesh"]
-    # bounded sample: same density and mesh spacing, box shrunk by 2 per axis until the whole
-    # run fits ~150 s (measured here: ~1 us per particle-step on 8 cores)
+    copies = world if args.scaling == "weak" else 1
+    # The arm runs the workload the GPU arm names, at full size, for every one of the K + W cycles
+    # (measured on the GPU box: 0.44 us per particle-step on 16 cores, i.e. ~4.4 s per C4 cycle and
+    # ~100 s for the driver's 20 + 5 cycles).  Only a configuration whose K + W full cycles would
+    # exceed 20 minutes (C5: ~50 s per cycle) is sampled: same density and mesh spacing, box
+    # halved per axis; the line then says so (same_config false).
     total = args.steps + args.warmup
     n, mesh, shrink = n_full, mesh_full, 0
-    while n * total * 1.0e-6 > 150.0 and mesh % 2 == 0 and mesh >= 32:
+    while n * copies * total * 0.6e-6 > 1200.0 and mesh % 2 == 0 and mesh >= 32:
         n, mesh, shrink = n // 8, mesh // 2, shrink + 1
-    sysm = make_system(args.workload, dtype=dtype, n=n, mesh=mesh)
-    cfg = copy.deepcopy(sysm.config)
-    h = OracleHamiltonian(cfg)
-    st = fo.FieldState(cfg, dtype)
+    if copies == 1:
+        sysm = make_system(args.workload, dtype=dtype, n=n, mesh=mesh)
+        pos, typ, q = sysm.positions, sysm.types, sysm.charges
+    else:   # weak scaling: the global system is `world` boxes stacked along x
+        parts = [make_system(args.workload, dtype=dtype, n=n, mesh=mesh, x_copies=copies, x_index=r)
+                 for r in range(copies)]
+        sysm = parts[0]
+        pos = np.concatenate([p.positions for p in parts])
+        typ = np.concatenate([p.types for p in parts])
+        q = None if sysm.charges is None else np.concatenate([p.charges for p in parts])
+    cfg = sysm.config
+    n_run = len(pos)
     cores = os.cpu_count() or 1
-
-    def cycle():
-        fo.update_field(st, h, sysm.positions, sysm.types, cfg, workers=-1, mt=True)
-        f = fo.compute_field_force(st, sysm.positions, sysm.types, cfg.n_types, mt=True)
-        if sysm.charges is not None:
-            fo.update_field_force_q(st, h, sysm.charges, sysm.positions, cfg, workers=-1, mt=True)
-        return f
-
+    oc = OracleCycle(cfg, dtype)
     for _ in range(args.warmup):
-        cycle()
+        oc(pos, typ, q)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cycle()
+        oc(pos, typ, q)
     dt = time.perf_counter() - t0
-    value = n * args.steps / dt
-    sample = (f"{args.workload} at full size (N={n}, {mesh}^3)" if shrink == 0 else
-              f"{args.workload} shrunk {2 ** shrink}x per axis at equal density and mesh "
-              f"spacing (N={n}, {mesh}^3 instead of N={n_full}, {mesh_full}^3)")
+    value = n_run * args.steps / dt
+    sample = (f"every step = one full cycle of {args.workload} (N={n_run}, mesh {mesh}), nothing sampled"
+              if shrink == 0 else
+              f"{args.workload} shrunk {2 ** shrink}x per axis at equal density and mesh spacing "
+              f"(N={n_run}, {mesh}^3 instead of N={n_full * copies}, {mesh_full}^3)")
+    config = workload_config(args, world, cfg, n_run, q is not None)
+    config["same_config"] = shrink == 0
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"{args.workload}: N={n_full}, mesh {mesh_full}^3, "
-                               f"T={cfg.n_types}, sigma=0.5, kappa=0.05, DefaultWithChi"},
+        "dtype": args.dtype, "data": "synthetic", "config": config,
         "ns_per_day": args.steps / dt * 86400.0 * PS_PER_CYCLE / 1000.0,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample,
@@ -218,32 +276,13 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(sysm, dtype):
-    """One cycle of the CPU port on the same inputs (bounded sample: <= ~30 s)."""
-    import copy
-    from oracle import field_oracle as fo
-    from oracle.hamiltonian_oracle import OracleHamiltonian
-    cfg = copy.deepcopy(sysm.config)
-    n = len(sysm.positions)
-    h = OracleHamiltonian(cfg)
-    st = fo.FieldState(cfg, dtype)
-    reps = 1 if n >= 5_000_000 else (3 if n >= 500_000 else 10)
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
-    def cycle():
-        fo.update_field(st, h, sysm.positions, sysm.types, cfg, workers=-1, mt=True)
-        fo.compute_field_force(st, sysm.positions, sysm.types, cfg.n_types, mt=True)
-        if sysm.charges is not None:
-            fo.update_field_force_q(st, h, sysm.charges, sysm.positions, cfg, workers=-1, mt=True)
 
-    if n < 5_000_000:
-        cycle()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        cycle()
-    dt = time.perf_counter() - t0
-    return {"value": n * reps / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": f"{reps} full cycle(s) of the same workload (N={n}), "
-                      f"{dt:.1f} s of wall time on all host threads"}
+PARITY_TOL = {"f32": 1e-5, "f64": 1e-10}
 
 
 def main():
@@ -282,35 +321,38 @@ def main():
     layouts = [pm.decompose(None) for _ in range(T)]
     pme = sysm.charges is not None
 
-    # this rank's particles (slab along x); single GPU: all of them
+    # this rank's particles (slab along x); single GPU: all of them.  gid = index in the global
+    # system (strong scaling: the generator's order; weak: box r holds [r*n, (r+1)*n))
     pos_h, typ_h, q_h = sysm.positions, sysm.types, sysm.charges
     vel_h = sysm.velocities
+    gid_h = np.arange(len(pos_h), dtype=np.int64) + (rank * len(pos_h) if presharded else 0)
     if world > 1 and not presharded:
         L = float(cfg.box_size[0])
         cell = np.floor(pos_h[:, 0].astype(np.float64) * mesh[0] / L).astype(np.int64) % mesh[0]
         mine = (cell // (mesh[0] // world)) == rank
-        pos_h, typ_h, vel_h = pos_h[mine], typ_h[mine], vel_h[mine]
+        pos_h, typ_h, vel_h, gid_h = pos_h[mine], typ_h[mine], vel_h[mine], gid_h[mine]
         q_h = None if q_h is None else q_h[mine]
     if not args.no_dd:
         # what main.py does once at start-up (and every config.domain_decomposition steps) when
         # the option is set: all per-particle arrays come back permuted identically
-        extra = (vel_h, typ_h) if q_h is None else (vel_h, typ_h, q_h)
+        extra = (vel_h, typ_h, gid_h) if q_h is None else (vel_h, typ_h, gid_h, q_h)
         out = F.domain_decomposition(pos_h, pm, *extra)
-        pos_h, vel_h, typ_h = out[0], out[1], out[2]
-        q_h = None if q_h is None else out[3]
+        pos_h, vel_h, typ_h, gid_h = out[0], out[1], out[2], out[3]
+        q_h = None if q_h is None else out[4]
     n_loc = len(pos_h)
     dev = pm.device
     # MD-like input stream: step k sees the positions of step k-1 displaced by one outer step of
     # thermal motion (v * respa_inner * time_step, ~0.05 nm = 12 % of a cell), so every step
-    # re-bins genuinely different coordinates.  NBUF trajectories frames, visited ping-pong.
-    NBUF = 6
+    # re-bins genuinely different coordinates.  NBUF trajectory frames, visited ping-pong.  With
+    # several GPUs nothing keeps a particle inside its rank's slab: frames 1.. hold particles that
+    # crossed a slab face, and every cycle routes them to the slab owner and their forces back.
     L = np.asarray(cfg.box_size, dtype=np.float64)
     frames_h = []
     for k in range(NBUF):
         f = np.mod(pos_h.astype(np.float64) + k * PS_PER_CYCLE * vel_h.astype(np.float64), L)
         f = f.astype(np_dtype)
         f[f >= L.astype(np_dtype)] = 0
-        if world > 1:   # keep every particle inside this rank's slab (no migration in the timed loop)
+        if world > 1 and CLIP_TO_SLAB:
             lo = rank * (mesh[0] // world) * L[0] / mesh[0]
             hi = (rank + 1) * (mesh[0] // world) * L[0] / mesh[0]
             f[:, 0] = np.clip(f[:, 0], np.nextafter(np_dtype(lo), np_dtype(hi)) if lo > 0 else 0,
@@ -374,6 +416,69 @@ def main():
     N_global = N
     value = N_global * args.steps / (ms_total * 1e-3)
 
+    # ---- parity: the GPU forces of the most-drifted frame against the CPU oracle -------------
+    # Same frame on every rank (NBUF - 1 outer steps of drift: with several GPUs that is the frame
+    # with the most particles away from their home slab).  The oracle runs in float64 on the same
+    # (dtype-valued) coordinates, the tolerance is the north star's (1e-5 fp32 / 1e-10 fp64),
+    # max|a-b| / max|b| over all particles of all ranks.
+    PF = NBUF - 1
+    cycle(frames_d[PF], typ_d, q_d, force_d, eforce_d)
+    torch.cuda.synchronize()
+    gpu_f = force_d.cpu().numpy().copy()
+    gpu_ef = eforce_d.cpu().numpy().copy() if pme else None
+    parity = None
+    if N_global <= args.parity_max_n:
+        if world > 1:
+            payload = (gid_h, frames_h[PF], typ_h, q_h, gpu_f, gpu_ef) if presharded else \
+                (gid_h, None, None, None, gpu_f, gpu_ef)
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(payload, gathered, dst=0)
+        else:
+            gathered = [(gid_h, None, None, None, gpu_f, gpu_ef)]
+        if rank == 0:
+            if presharded:      # weak scaling: the global system is the ranks' boxes side by side
+                g_pos = np.concatenate([g[1] for g in gathered])
+                g_typ = np.concatenate([g[2] for g in gathered])
+                g_q = None if not pme else np.concatenate([g[3] for g in gathered])
+                got = np.concatenate([g[4] for g in gathered])
+                got_e = None if not pme else np.concatenate([g[5] for g in gathered])
+            else:               # strong scaling: frame PF of the whole system in generator order
+                g_pos = np.mod(sysm.positions.astype(np.float64) +
+                               PF * PS_PER_CYCLE * sysm.velocities.astype(np.float64), L).astype(np_dtype)
+                g_pos[g_pos >= L.astype(np_dtype)] = 0
+                g_typ, g_q = sysm.types, sysm.charges
+                got = np.full((N_global, 3), np.nan)
+                got_e = np.full((N_global, 3), np.nan) if pme else None
+                for g in gathered:
+                    got[g[0]] = g[4]
+                    if pme:
+                        got_e[g[0]] = g[5]
+                if CLIP_TO_SLAB and world > 1:
+                    raise SystemExit("parity needs unclipped frames")
+            want, want_e, oracle_s = oracle_cycle(cfg, g_pos, g_typ, g_q, np.float64)
+            err = rel_err(got, want) if np.isfinite(got).all() else float("inf")
+            parity = {"config": args.workload, "n_compared": int(len(want)), "frame": PF,
+                      "rel_err": err, "tol": PARITY_TOL[args.dtype],
+                      "oracle": "oracle/field_oracle.py, float64, one cycle on rank 0 "
+                                f"({oracle_s:.1f} s)", "norm": "max|a-b| / max|b| over all particles"}
+            if pme:
+                parity["rel_err_elec"] = rel_err(got_e, want_e)
+            net = np.abs(got.sum(axis=0)).max() / max(np.abs(got).sum(), 1e-300)
+            parity["net_force_fraction"] = float(net)
+            parity["ok"] = bool(err < parity["tol"] and parity.get("rel_err_elec", 0.0) < parity["tol"])
+    else:
+        # too large for a CPU oracle cycle inside the bench: the size-independent property only
+        # (momentum conservation of the spectral field forces, summed over all ranks)
+        s1 = torch.tensor(np.concatenate([gpu_f.astype(np.float64).sum(axis=0),
+                                          [np.abs(gpu_f).astype(np.float64).sum()]]), device=dev)
+        if world > 1:
+            dist.all_reduce(s1)
+        s1 = s1.cpu().numpy()
+        net = float(np.abs(s1[:3]).max() / max(s1[3], 1e-300))
+        parity = {"config": args.workload, "n_compared": 0, "rel_err": None,
+                  "note": f"N={N_global} exceeds --parity-max-n: momentum conservation only",
+                  "net_force_fraction": net, "ok": bool(net < (1e-5 if args.dtype == "f32" else 1e-10))}
+
     # ---- end to end: host (pinned) in, host out, every step --------------------------------
     e2e = None
     if not args.no_e2e:
@@ -412,6 +517,26 @@ def main():
                "d2h_bytes_per_step": int(d2h),
                "path": "hymd_b200.field.update_field + compute_field_force with pinned host "
                        "tensors (per rank)"}
+        # what the unmodified main.py hands over: pageable numpy arrays, forces written in place
+        # into a numpy array (wall clock around synchronised steps)
+        force_n = np.zeros((n_loc, 3), dtype=np_dtype)
+        eforce_n = np.zeros((n_loc, 3), dtype=np_dtype) if pme else None
+        typ_n = typ_h.astype(np.int32)
+        kn = 3
+        cycle(frames_h[0], typ_n, q_h, force_n, eforce_n)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(kn):
+            cycle(frames_h[1 + i % 3], typ_n, q_h, force_n, eforce_n)
+        torch.cuda.synchronize()
+        dt_n = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt_n, op=dist.ReduceOp.MAX)
+        e2e["numpy_pageable"] = {"value": N_global * kn / float(dt_n.item()), "unit": UNIT, "steps": kn,
+                                 "ms_per_step": float(dt_n.item()) / kn * 1e3,
+                                 "path": "same calls with pageable numpy arrays in and out (what "
+                                         "main.py passes), wall clock, max over ranks"}
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -459,33 +584,48 @@ def main():
                 "all_hand_written": {k: {"kernel": kernel_of[k], "gbs": phases[k]["gbs"],
                                          "frac": phases[k]["frac_of_peak"]} for k in own}}
     total_alg = sum(alg.values())
+    config = workload_config(args, world, cfg, N_global, pme)
+    config["particle_order"] = ("generator (molecule) order" if args.no_dd else
+                                "as returned by the start-up domain_decomposition call "
+                                "(mesh-cell order of frame 0, main.py:274-300)")
+    config["l2"] = (f"inputs larger than L2 (per-step working set {total_alg / 1e6:.0f} MB per GPU "
+                    "vs 126 MB L2), no flush")
+    if world > 1:
+        config["routing"] = "clipped to the slab (no routing)" if CLIP_TO_SLAB else \
+            "in loop: unclipped trajectories, guests routed every cycle"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"{args.workload}: N={N_global}, mesh {mesh[0]}x{mesh[1]}x{mesh[2]}, "
-                               f"T={T} (U={U} distinct potential rows), sigma={cfg.sigma}, "
-                               f"kappa={cfg.kappa}, DefaultWithChi" + (", PME" if pme else ""),
-                   "inputs": f"{NBUF} trajectory frames visited ping-pong, consecutive frames differ by "
-                             "one outer step of thermal motion (0.25 ps at 323 K, ~0.05 nm); particle "
-                             "order: " + ("generator (molecule) order" if args.no_dd else
-                                          "as returned by the start-up domain_decomposition call "
-                                          "(mesh-cell order of frame 0, main.py:274-300)"),
-                   "l2": "inputs larger than L2 (per-step working set "
-                         f"{total_alg / 1e6:.0f} MB vs 126 MB L2), no flush",
-                   "parallelism": "single GPU" if world == 1 else f"{world} x-slabs (slab FFT, NCCL all-to-all)"},
+        "config": config,
         "ns_per_day": args.steps / (ms_total * 1e-3) * 86400.0 * PS_PER_CYCLE / 1000.0,
         "cycle_frac_of_hbm_roofline": total_alg / (ms_per_step * 1e-3) / 1e9 / peak,
+        "parity": parity,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "paths": paths,
         "roofline": roofline, "phases": phases,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(sysm, np_dtype)
+        # the CPU port in the run's own dtype on the same frame (one full cycle, all host threads)
+        reps = 1 if N_global >= 5_000_000 else (3 if N_global >= 500_000 else 10)
+        oc = OracleCycle(cfg, np_dtype)
+        if reps > 1:
+            oc(frames_h[0], typ_h, q_h)
+        dt = sum(oc(frames_h[0], typ_h, q_h)[2] for _ in range(reps))
+        line["cpu_baseline"] = {"value": N_global * reps / dt, "unit": UNIT, "cores": os.cpu_count() or 1,
+                                "kind": "port",
+                                "sample": f"{reps} full cycle(s) of the same workload (N={N_global}), "
+                                          f"{dt:.1f} s of wall time on all host threads"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        print(f"PARITY FAILED: {parity}", file=sys.stderr, flush=True)
+        return 3
     return 0
+
+
+CLIP_TO_SLAB = True     # until per-step routing runs on several GPUs
 
 
 if __name__ == "__main__":

@@ -75,6 +75,24 @@ class HymdError(RuntimeError):
     pass
 
 
+# Tensors the library writes through raw pointers (hymd_md_kick_drift, hymd_bonded_inner_step) keep
+# their torch ``_version``; every such write is recorded here so that the bin cache of
+# ParticleMesh.sort (keyed on data pointer + version) sees it.
+_write_epoch = {}
+
+
+def mark_written(tensor):
+    """Record that the library modified ``tensor``'s storage behind torch's back."""
+    key = tensor.data_ptr()
+    if len(_write_epoch) > 4096:
+        _write_epoch.clear()
+    _write_epoch[key] = _write_epoch.get(key, 0) + 1
+
+
+def write_epoch(tensor):
+    return _write_epoch.get(tensor.data_ptr(), 0)
+
+
 _lib = None
 
 

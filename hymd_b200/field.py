@@ -42,13 +42,7 @@ def initialize_pm(pmesh, config, comm=None):
     dtype = "f8" if np.dtype(config.dtype) == np.float64 else "f4"
     coulombtype = getattr(config, "coulombtype", None)
     if coulombtype == "PIC_Spectral_GPE":
-        import os
         import torch.distributed as dist
-        if os.environ.get("HYMD_B200_ENABLE_GPE", "0") != "1":
-            raise NotImplementedError(
-                "coulombtype='PIC_Spectral_GPE' (field.py:764-1112): the device path (hymd_gpe_cycle) "
-                "exists but has not been run on a GPU yet; set HYMD_B200_ENABLE_GPE=1 to try it, or use "
-                "'PIC_Spectral'")
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             raise NotImplementedError("coulombtype='PIC_Spectral_GPE' runs on a single GPU only")
     pm = ParticleMesh(config.mesh_size, BoxSize=config.box_size, dtype=dtype, comm=comm,
@@ -182,8 +176,7 @@ def update_field_force_q_GPE(conv_fun, phi, types, charges, phi_q, phi_q_fourier
     electrostatic potential and the forces, written in place into ``elec_forces``.  ``conv_fun`` (the
     reference's closure over ``config.convergence_type``, ``main.py:141-163``) is accepted and ignored:
     the convergence measure is evaluated on the device according to ``config.convergence_type``.
-    Returns ``(Vbar_elec, phi_eps, elec_dot)`` like the reference (``elec_dot`` as a mesh handle).
-    NOT YET RUN ON A GPU."""
+    Returns ``(Vbar_elec, phi_eps, elec_dot)`` like the reference (``elec_dot`` as a mesh handle)."""
     pm.sync_interaction(hamiltonian, config)
     pm.sort(positions, None, charges)
     n = pm._n_local

@@ -170,6 +170,9 @@ class BondedTopology:
             ctypes.c_void_p(x_in.data_ptr()), ctypes.c_void_p(x_out.data_ptr()) if x_out is not None else None,
             ctypes.c_void_p(vel.data_ptr()), box, float(mass), float(kick_dt), int(n_kicks), float(drift_dt),
             fptr, ctypes.cast(ctypes.c_void_p(res.data_ptr()), _F64P) if res is not None else None, stream))
+        _lib.mark_written(vel)
+        if x_out is not None:
+            _lib.mark_written(x_out)
         return res
 
 

@@ -95,6 +95,9 @@ def kick_drift(vel, pos, forces, mass, kick_dt, drift_dt=0.0, box=None, sequenti
         code, ctypes.c_void_p(vel.data_ptr()), ctypes.c_void_p(pos.data_ptr()) if pos is not None else None,
         fptr, len(forces), 1 if sequential else 0, float(mass), float(kick_dt), float(drift_dt), bx,
         int(vel.shape[0]), ctypes.c_void_p(torch.cuda.current_stream(vel.device).cuda_stream)))
+    _lib.mark_written(vel)
+    if pos is not None:
+        _lib.mark_written(pos)      # written through a raw pointer: invalidates cached bins (pm.sort)
 
 
 class RespaMD:
@@ -165,9 +168,10 @@ class RespaMD:
                 kick_drift(velocities, None, fast, self.mass, self.dt)
         slow_forces = self.field_force_fn(positions)                                     # main.py:976-1058
         kick_drift(velocities, None, slow_forces, self.mass, outer, sequential=True)     # main.py:1144-1169
-        self.step_count += 1
-        if self.thermostat is not None and self.step_count % self.n_b == 0:             # main.py:1290-1292
+        # the reference tests np.mod(step, n_b) == 0 with step counting from 0 (main.py:1290-1292, 1315)
+        if self.thermostat is not None and self.step_count % self.n_b == 0:
             self.thermostat(velocities)
+        self.step_count += 1
         return slow_forces
 
     def _fused_inner(self, positions, velocities):

@@ -304,12 +304,24 @@ class ParticleMesh:
 
     @staticmethod
     def _fingerprint(x):
+        """Key under which ``sort`` recognises "the positions the bins were built from".
+
+        torch tensors: storage pointer + torch's version counter + the library's own write epoch
+        (``hymd_md_kick_drift`` / ``hymd_bonded_inner_step`` write through raw pointers, which torch
+        does not see).  numpy arrays have no version counter: the key is the identity of the array
+        plus a hash of a strided sample of <= 65536 rows (every row for small systems), so an array
+        mutated in place between ``update_field`` and a later read-out is re-binned.  Contract for
+        callers that change fewer rows than the sample stride: pass a new array or call
+        ``pm.reset_order()``."""
         if isinstance(x, torch.Tensor):
-            return ("t", x.data_ptr(), x._version, tuple(x.shape), x.dtype)
+            return ("t", x.data_ptr(), x._version, _lib.write_epoch(x), tuple(x.shape), x.dtype)
         a = np.asarray(x)
         n = a.shape[0]
-        probe = (float(a[0, 0]), float(a[n // 2, 1]), float(a[-1, -1])) if a.ndim == 2 and n else ()
-        return ("n", id(x), a.ctypes.data, a.shape, probe)
+        probe = 0
+        if a.ndim == 2 and n:
+            step = max(1, n // 65536)
+            probe = hash(np.ascontiguousarray(a[::step]).tobytes())
+        return ("n", id(x), a.ctypes.data, a.shape, a.dtype.str, probe)
 
     def sort(self, positions, types, charges=None, force=False):
         """Bin the local particles (all types at once).  ``update_field`` always re-bins

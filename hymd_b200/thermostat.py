@@ -31,7 +31,15 @@ _I32P = ctypes.POINTER(ctypes.c_int32)
 
 
 class DeviceScalar:
-    """A float64 scalar that lives on the GPU until somebody needs its value."""
+    """A float64 scalar that lives on the GPU until somebody needs its value.
+
+    ``config.thermostat_work`` is a plain float in the reference and its consumers treat it as one
+    (``file_io.py:704`` stores it into an HDF5 dataset, ``file_io.py:751`` subtracts it from the total
+    energy), so this class implements the numeric protocol: any arithmetic, comparison, formatting or
+    ``numpy`` conversion reads the value back (one synchronisation, on print steps only) and yields a
+    Python float."""
+
+    __array_priority__ = 100
 
     def __init__(self, tensor):
         self.tensor = tensor
@@ -44,6 +52,54 @@ class DeviceScalar:
 
     def __repr__(self):
         return f"DeviceScalar({float(self)!r})"
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(float(self), dtype=dtype or np.float64)
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+    def __int__(self):
+        return int(float(self))
+
+    def __bool__(self):
+        return bool(float(self))
+
+    def __hash__(self):
+        return hash(float(self))
+
+    def __neg__(self):
+        return -float(self)
+
+    def __pos__(self):
+        return float(self)
+
+    def __abs__(self):
+        return abs(float(self))
+
+    def __round__(self, n=None):
+        return round(float(self), n)
+
+
+def _binary(name):
+    import operator
+    op = getattr(operator, name)
+
+    def fwd(self, other):
+        return op(float(self), float(other) if isinstance(other, DeviceScalar) else other)
+
+    def rev(self, other):
+        return op(float(other) if isinstance(other, DeviceScalar) else other, float(self))
+    return fwd, rev
+
+
+for _n in ("add", "sub", "mul", "truediv", "floordiv", "mod", "pow"):
+    _f, _r = _binary(_n)
+    setattr(DeviceScalar, f"__{_n}__", _f)
+    setattr(DeviceScalar, f"__r{_n}__", _r)
+for _n in ("lt", "le", "gt", "ge", "eq", "ne"):
+    setattr(DeviceScalar, f"__{_n}__", _binary(_n)[0])
+del _n, _f, _r
 
 
 def _dtype_code(t):

@@ -78,13 +78,14 @@ class OracleRun:
         self.h = OracleHamiltonian(cfg)
         self.st = fo.FieldState(cfg, dtype)
         pos = np.asarray(positions, dtype=dtype)
+        mt = len(pos) > 500_000      # full-size BASELINE configs: the threaded C loops (same arithmetic)
         fo.update_field(self.st, self.h, pos, types, cfg, compute_potential=compute_potential,
-                        workers=-1)
-        self.force = fo.compute_field_force(self.st, pos, types, cfg.n_types)
+                        workers=-1, mt=mt)
+        self.force = fo.compute_field_force(self.st, pos, types, cfg.n_types, mt=mt)
         self.elec_forces = None
         if charges is not None:
             self.elec_forces = fo.update_field_force_q(self.st, self.h, np.asarray(charges, dtype=dtype),
-                                                       pos, cfg, workers=-1)
+                                                       pos, cfg, workers=-1, mt=mt)
 
     def energies(self, velocities):
         return fo.compute_field_and_kinetic_energy(self.st, self.h, velocities, self.cfg)

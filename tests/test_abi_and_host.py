@@ -212,3 +212,31 @@ def test_block_ordering_keeps_molecules_whole_and_separates_chains_from_solvent(
     single = (np.arange(n) >= nch * length)[perm]
     tiles = single[: n // 128 * 128].reshape(-1, 128).mean(axis=1)
     assert ((tiles > 0) & (tiles < 1)).mean() < 0.4            # cell order alone: every tile is mixed
+
+
+def test_device_scalar_behaves_like_the_float_the_reference_expects():
+    """config.thermostat_work is a float in the reference; file_io.py:751 subtracts it and
+    file_io.py:704 stores it into an HDF5 dataset."""
+    import torch
+    from hymd_b200.thermostat import DeviceScalar
+    w = DeviceScalar(torch.tensor([2.5], dtype=torch.float64))
+    assert 10.0 - 1.0 - w == 6.5 and w - 1 == 1.5 and 2 * w == 5.0 and w / 2 == 1.25
+    assert isinstance(10.0 - w, float) and -w == -2.5 and abs(w) == 2.5 and w < 3 and w >= 2.5
+    a = np.zeros(2)
+    a[1] = w
+    assert a[1] == 2.5 and float(np.asarray(w)) == 2.5 and f"{w:.2f}" == "2.50"
+    assert np.float64(1.0) + w == 3.5
+
+
+def test_write_epoch_changes_the_position_fingerprint():
+    import torch
+    from hymd_b200 import _lib
+    from hymd_b200.pm import ParticleMesh
+    x = torch.zeros((4, 3))
+    k0 = ParticleMesh._fingerprint(x)
+    _lib.mark_written(x)
+    assert ParticleMesh._fingerprint(x) != k0
+    a = np.zeros((100, 3))
+    k1 = ParticleMesh._fingerprint(a)
+    a[50, 1] = 1.0
+    assert ParticleMesh._fingerprint(a) != k1

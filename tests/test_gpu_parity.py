@@ -335,3 +335,40 @@ def test_laplacian_and_pressure_match_oracle(dtype, mesh, coulomb):
     # every term against the largest term (the total mixes terms of both signs)
     ref = np.abs(want).max()
     assert np.abs(got - want).max() < 10 * TOL[dtype] * ref, (got, want)
+
+
+def test_positions_moved_behind_torchs_back_are_rebinned():
+    """hymd_md_kick_drift writes positions through a raw pointer (torch's version counter
+    does not move).  A read-out / PME call on the moved positions WITHOUT a preceding update_field must
+    re-bin them (bins are keyed on pointer + version + the library's write epoch), not reuse stale bins."""
+    from gpu_common import GpuRun, rel_err
+    from hymd_b200 import field as F
+    from hymd_b200.md import kick_drift
+    cfg, pos, types, q = _system(5000, [16, 16, 16], [4.0, 5.0, 6.0], np.float64, seed=5, coulomb=True)
+    g = GpuRun(cfg, pos, types, charges=q)
+    vel = torch.full_like(g.pos, 3.0)
+    kick_drift(vel, g.pos, [torch.zeros_like(g.pos)], 72.0, 0.0, 0.1, box=cfg.box_size)   # x += 0.3 nm, wrapped
+    ef = torch.zeros_like(g.elec_forces)
+    F.update_field_force_q(g.q, g.phi_q, g.phi_q_fourier, g.psi, None, None, g.elec_field, ef,
+                           g.pm.decompose(None), g.h, g.pm, g.pos, cfg)
+    fresh = GpuRun(cfg, g.pos.cpu().numpy(), types, charges=q)
+    assert rel_err(ef.cpu().numpy(), fresh.eforces()) < 1e-12
+    assert rel_err(ef.cpu().numpy(), g.eforces()) > 1e-3          # the particles really moved
+
+
+def test_numpy_positions_mutated_in_place_are_rebinned():
+    """numpy arrays carry no version counter; an in-place update between
+    update_field and a later call is detected (strided-sample hash) and re-binned."""
+    from gpu_common import GpuRun, rel_err
+    from hymd_b200 import field as F
+    cfg, pos, types, q = _system(5000, [16, 16, 16], [4.0, 5.0, 6.0], np.float64, seed=6, coulomb=True)
+    g = GpuRun(cfg, pos, types, charges=q, as_numpy=True)
+    before = g.eforces().copy()
+    pos += 0.3
+    np.mod(pos, np.asarray(cfg.box_size, dtype=pos.dtype)[None, :], out=pos)
+    ef = np.zeros_like(before)
+    F.update_field_force_q(g.q, g.phi_q, g.phi_q_fourier, g.psi, None, None, g.elec_field, ef,
+                           g.pm.decompose(None), g.h, g.pm, pos, cfg)
+    fresh = GpuRun(cfg, pos.copy(), types, charges=q, as_numpy=True)
+    assert rel_err(ef, fresh.eforces()) < 1e-12
+    assert rel_err(ef, before) > 1e-3

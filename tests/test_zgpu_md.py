@@ -358,9 +358,7 @@ def test_fused_step_edge_cases():
 
 
 @pytest.mark.parametrize("real", [np.float32, np.float64])
-@pytest.mark.parametrize("tile", [128, pytest.param(512, marks=pytest.mark.xfail(
-    strict=False, reason="several particles per thread + opt-in shared memory > 48 KB: CPU-verified only, first "
-                         "GPU run is the driver's (XPASS = verified)"))])      # unverified cases run last
+@pytest.mark.parametrize("tile", [128, 512])
 def test_cta_cooperative_evaluation_matches_the_per_particle_result(real, tile, monkeypatch):
     """hymd_bonded_set_cta(1): each CTA evaluates every term touching its 128 particles once into shared
     memory and the particles gather their slots.  Same additions in the same order => the forces equal the
@@ -439,8 +437,6 @@ def test_cta_cooperative_evaluation_matches_the_per_particle_result(real, tile, 
     topo.set_cta(False)
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: first run on a GPU "
-                                        "is the driver's; XPASS = verified, remove the mark next round")
 def test_barostat_rescale_then_fields_match_the_oracle_in_the_new_box():
     """NPT step (main.py:889-935): hymd_b200.barostat.isotropic computes the pressure on the device,
     rescales box and positions in place and tells the context the new box (hymd_ctx_set_box) instead of
@@ -484,8 +480,6 @@ def test_barostat_rescale_then_fields_match_the_oracle_in_the_new_box():
     assert rel_err(g.forces(), o2.force) < 1e-10
 
 
-@pytest.mark.xfail(strict=False, reason="single-precision bond / angle arithmetic: CPU-verified only, first GPU run is "
-                                        "the driver's (XPASS = verified)")
 def test_f32_math_inner_step_stays_within_the_fp32_tolerance():
     """hymd_bonded_set_math(1): float arithmetic for bonds and angles in the per-particle fused step of the
     fp32 build, against the default double arithmetic: forces within 1e-5 of the largest force (north_star

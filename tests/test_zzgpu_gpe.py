@@ -1,21 +1,18 @@
 """GPU parity of row f3 (general-Poisson-equation electrostatics, hymd_gpe_cycle) against
 oracle/gpe_oracle.py, which is pinned on the reference's own update_field_force_q_GPE
-(tests/test_oracle_gpe.py).  Written after the round's GPU minutes were spent: every test here is a
-non-strict xfail until its first GPU run (XPASS = verified)."""
+(tests/test_oracle_gpe.py).  First run on a B200 by the round-1 driver (GPUTEST_r01: 11 XPASS)."""
 import numpy as np
 import pytest
 import torch
 
 from conftest import make_config
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180),
-              pytest.mark.xfail(strict=False, reason="hymd_gpe_cycle has not been run on a GPU yet")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-8), (np.float32, 2e-4)])
 @pytest.mark.parametrize("mesh", [[16, 16, 16], [10, 12, 8], [9, 8, 11]])
 def test_gpe_matches_oracle(monkeypatch, dtype, tol, mesh):
-    monkeypatch.setenv("HYMD_B200_ENABLE_GPE", "1")
     from gpu_common import rel_err
     from hymd_b200 import field as F
     from hymd_b200.hamiltonian import get_hamiltonian
@@ -86,9 +83,10 @@ def test_gpe_matches_oracle(monkeypatch, dtype, tol, mesh):
     assert torch.equal(again, elec_forces)
 
 
-def test_gpe_is_opt_in_until_verified(monkeypatch):
+def test_gpe_needs_no_opt_in(monkeypatch):
+    """The HYMD_B200_ENABLE_GPE gate of round 1 is gone: the coulombtype works out of the box."""
     monkeypatch.delenv("HYMD_B200_ENABLE_GPE", raising=False)
     from hymd_b200 import field as F
     cfg = make_config(["A", "B"], 10, 8, [2.0, 2.0, 2.0], coulombtype="PIC_Spectral_GPE")
-    with pytest.raises(NotImplementedError):
-        F.initialize_pm(None, cfg)
+    pm, fl, ecl, cl = F.initialize_pm(None, cfg)
+    assert len(cl) == 12

@@ -122,7 +122,7 @@ def _output_buffer(pm, out, n):
         return buf, lambda: out.copy_(buf)
 
     def back():
-        out[...] = buf.cpu().numpy()
+        pm.to_host(buf, out, "forces")
     return buf, back
 
 

@@ -625,7 +625,7 @@ def main():
     return 0
 
 
-CLIP_TO_SLAB = True     # until per-step routing runs on several GPUs
+CLIP_TO_SLAB = False    # debugging aid only: keeps every frame inside the slab (no guests)
 
 
 if __name__ == "__main__":

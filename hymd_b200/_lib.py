@@ -33,6 +33,7 @@ EXPORTS = [
     "hymd_md_kick_drift", "hymd_velocity_moments", "hymd_velocity_moments_scratch_doubles",
     "hymd_csvr_apply", "hymd_cancel_com",
     "hymd_gpe_cycle", "hymd_gpe_energy",
+    "hymd_local_group_id", "hymd_ctx_check",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -111,6 +112,8 @@ def load():
     lib.hymd_last_error.argtypes = []
     lib.hymd_abi_version.restype = ctypes.c_int
     lib.hymd_nccl_unique_id.argtypes = [P(ctypes.c_uint8)]
+    lib.hymd_local_group_id.argtypes = [ctypes.c_int, P(ctypes.c_uint8)]
+    lib.hymd_ctx_check.argtypes = [vp]
     lib.hymd_ctx_create.argtypes = [P(HymdConfig), P(ctypes.c_uint8), P(vp)]
     lib.hymd_ctx_destroy.argtypes = [vp]
     lib.hymd_ctx_set_box.argtypes = [vp, P(dbl)]

@@ -40,6 +40,7 @@ static int upload(void* dst, const std::vector<double>& v) {
     std::vector<real> h(v.size());
     for (size_t i = 0; i < v.size(); ++i) h[i] = (real)v[i];
     HYMD_CUDA(cudaMemcpy(dst, h.data(), h.size() * sizeof(real), cudaMemcpyHostToDevice));
+    HYMD_CUDA(cudaDeviceSynchronize());   // callers launch on non-blocking streams: the DMA must have landed
     return HYMD_OK;
 }
 
@@ -107,6 +108,7 @@ static int build_interaction(hymd_ctx* c) {
     HYMD_CHECK(upload_real(c, c->Au, Au));
     HYMD_CHECK(upload_real(c, c->cu, cu));
     HYMD_CUDA(cudaMemcpy(c->d_urow, c->urow, T * sizeof(int), cudaMemcpyHostToDevice));
+    HYMD_CUDA(cudaDeviceSynchronize());
     const double dv = g.box[0] * g.box[1] * g.box[2] / m;
     std::vector<double> os(T + 1);
     for (int t = 0; t < T; ++t) os[t] = c->cfg.m[t] / dv;
@@ -115,16 +117,17 @@ static int build_interaction(hymd_ctx* c) {
 }
 
 static int ensure_particle_capacity(hymd_ctx* c, int64_t n) {
-    if (n <= c->cap) return HYMD_OK;
+    if (n <= c->cap && c->rec) return HYMD_OK;      // (a rank without particles still bins its guests)
     int64_t cap = n + n / 8 + 1024;
+    const int64_t guests = route_guest_rows(c);      // several slabs: room for the guests of every peer
     void* bufs[] = {c->rec, c->rec_alt, c->q_sorted};
     for (void* b : bufs)
         if (b) cudaFree(b);
     c->rec = c->rec_alt = c->q_sorted = nullptr;
     c->order_n = -1;
-    HYMD_CHECK(dev_alloc(&c->rec, (size_t)cap * (c->f64 ? sizeof(Rec64) : sizeof(Rec32))));
-    HYMD_CHECK(dev_alloc(&c->rec_alt, (size_t)cap * (c->f64 ? sizeof(Rec64) : sizeof(Rec32))));
-    HYMD_CHECK(dev_alloc(&c->q_sorted, (size_t)cap * c->rsz));
+    HYMD_CHECK(dev_alloc(&c->rec, (size_t)(cap + guests) * (c->f64 ? sizeof(Rec64) : sizeof(Rec32))));
+    HYMD_CHECK(dev_alloc(&c->rec_alt, (size_t)(cap + guests) * (c->f64 ? sizeof(Rec64) : sizeof(Rec32))));
+    HYMD_CHECK(dev_alloc(&c->q_sorted, (size_t)(cap + guests) * c->rsz));
     c->cap = cap;
     return HYMD_OK;
 }
@@ -205,9 +208,9 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
 
     int st = HYMD_OK;
     auto fail = [&](int code) { hymd_ctx_destroy(c); return code; };
-    if ((st = dev_alloc((void**)&c->cell_start, (size_t)(g.ncell + 2) * 4))) return fail(st);
+    if ((st = dev_alloc((void**)&c->cell_start, (size_t)(g.ncell + 3) * 4))) return fail(st);
     if ((st = dev_alloc((void**)&c->scalars, sizeof(DeviceScalars)))) return fail(st);
-    c->scan_tmp_bytes = scan_temp_bytes(g.ncell + 1);
+    c->scan_tmp_bytes = scan_temp_bytes(g.ncell + 2);
     if ((st = dev_alloc(&c->scan_tmp, c->scan_tmp_bytes))) return fail(st);
     if ((st = build_tables(c))) return fail(st);
     if ((st = build_interaction(c))) return fail(st);
@@ -247,6 +250,7 @@ int hymd_ctx_destroy(hymd_ctx* c) {
     cudaDeviceSynchronize();
     if (c->plans) { destroy_plans(c); delete c->plans; c->plans = nullptr; }
     migrate_destroy(c);
+    route_destroy(c);
     comm_destroy(c);
     gpe_destroy(c);
     void* bufs[] = {c->rec, c->rec_alt, c->cell_start, c->q_sorted,
@@ -256,7 +260,6 @@ int hymd_ctx_destroy(hymd_ctx* c) {
                     c->wA, c->wS, c->halo, c->ytw, c->ztw, c->plane_scratch};
     for (void* b : bufs)
         if (b) cudaFree(b);
-    if (c->h_out_of_slab) { cudaFreeHost(c->h_out_of_slab); cudaEventDestroy(c->ev_slab); }
     if (c->ev_open) {
         for (auto& iv : *c->ev_open) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
         delete c->ev_open;
@@ -330,53 +333,30 @@ int hymd_ctx_reset_order(hymd_ctx* c) {
 
 int hymd_sort_particles_ex(hymd_ctx* c, const void* d_pos, const int32_t* d_types,
                            const void* d_charges, int64_t n, int flags, void* stream) {
-    const bool reuse = c && (flags & HYMD_SORT_REUSE_ORDER) && c->order_n == n && n > 0;
+    const bool reuse = c && (flags & HYMD_SORT_REUSE_ORDER) && c->order_n == n && (n > 0 || c->g.P > 1);
     if (!c || (n > 0 && (!d_pos || (!d_types && !reuse)))) { set_error("null argument"); return HYMD_ERR_INVALID; }
     const int64_t lim = c->f64 ? (1LL << 31) : (1LL << REC32_IDX_BITS);
     if (n < 0 || n >= lim) {
         set_error("n = %lld particles exceeds the per-GPU limit %lld", (long long)n, (long long)lim);
         return HYMD_ERR_CAPACITY;
     }
+    cudaStream_t s = (cudaStream_t)stream;
+    HYMD_CHECK(comm_check_status(c));
+    HYMD_CHECK(route_prepare(c, n, s));      // several slabs, first call: guest buffers (collective)
     HYMD_CHECK(ensure_particle_capacity(c, n));
     c->np = n;
     c->has_charges = d_charges != nullptr;
     {
-        PhaseScope ps(c, HYMD_PHASE_SORT, (cudaStream_t)stream);
-        HYMD_CHECK(sort_particles(c, d_pos, d_types, d_charges, n, reuse, (cudaStream_t)stream));
+        PhaseScope ps(c, HYMD_PHASE_SORT, s);
+        HYMD_CHECK(sort_particles(c, d_pos, d_types, d_charges, n, reuse, s));
     }
     c->sorted = true;
     c->order_n = n;
-    if (c->g.P > 1) {
-        if (!c->h_out_of_slab) {
-            HYMD_CUDA(cudaMallocHost((void**)&c->h_out_of_slab, sizeof(unsigned int)));
-            HYMD_CUDA(cudaEventCreateWithFlags(&c->ev_slab, cudaEventDisableTiming));
-        }
-        HYMD_CUDA(cudaMemcpyAsync(c->h_out_of_slab, &c->scalars->out_of_slab, sizeof(unsigned int),
-                                  cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-        HYMD_CUDA(cudaEventRecord(c->ev_slab, (cudaStream_t)stream));
-        c->slab_check_pending = true;
-    }
-    return HYMD_OK;
-}
-
-// Multi-GPU: every particle handed to hymd_sort_particles must lie inside this rank's slab (the
-// caller re-homes them with hymd_migrate / domain_decomposition); particles outside would be
-// painted into the edge planes.  Never silently: the count of the last sort is checked here.
-static int check_slab(hymd_ctx* c) {
-    if (!c->slab_check_pending) return HYMD_OK;
-    HYMD_CUDA(cudaEventSynchronize(c->ev_slab));     // the count kernel ran long ago: no GPU bubble
-    c->slab_check_pending = false;
-    if (*c->h_out_of_slab > 0) {
-        set_error("%u particles lie outside the x-slab of rank %d: call domain_decomposition "
-                  "(hymd_migrate_plan/apply) before update_field, and often enough that particles "
-                  "cannot leave their slab in between", *c->h_out_of_slab, c->g.rank);
-        return HYMD_ERR_STATE;
-    }
     return HYMD_OK;
 }
 
 int hymd_set_charges(hymd_ctx* c, const void* d_charges, void* stream) {
-    if (!c || !d_charges) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    if (!c || (!d_charges && c->np > 0)) { set_error("null argument"); return HYMD_ERR_INVALID; }
     if (!c->sorted) { set_error("hymd_set_charges before hymd_sort_particles"); return HYMD_ERR_STATE; }
     HYMD_CHECK(gather_charges(c, d_charges, (cudaStream_t)stream));
     c->has_charges = true;
@@ -539,8 +519,8 @@ int hymd_readout(hymd_ctx* c, void* d_force, void* stream) {
         set_error("hymd_readout needs hymd_sort_particles and hymd_field_cycle first");
         return HYMD_ERR_STATE;
     }
-    HYMD_CHECK(check_slab(c));
-    if (c->np == 0) return HYMD_OK;
+    HYMD_CHECK(comm_check_status(c));
+    if (c->np == 0 && c->g.P == 1) return HYMD_OK;   // several slabs: guests may still be read out here
     PhaseScope ps(c, HYMD_PHASE_READOUT, (cudaStream_t)stream);
     return readout_forces(c, d_force, (cudaStream_t)stream);
 }
@@ -585,8 +565,8 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
         if (want_psi) HYMD_CHECK(fft_inverse(c, c->psi_hat, 1, c->psi, false, s));
     }
     c->have_psi = want_psi != 0;
-    HYMD_CHECK(check_slab(c));
-    if (c->np > 0 && d_elec_force) {
+    HYMD_CHECK(comm_check_status(c));
+    if ((c->np > 0 || c->g.P > 1) && d_elec_force) {
         PhaseScope ps(c, HYMD_PHASE_PME_READOUT, s);
         HYMD_CHECK(readout_pme(c, d_elec_force, s));
     }
@@ -678,6 +658,17 @@ int hymd_ctx_paths(hymd_ctx* c, int32_t out[4]) {
 int hymd_nccl_unique_id(uint8_t id[HYMD_NCCL_UNIQUE_ID_BYTES]) {
     if (!id) { set_error("null argument"); return HYMD_ERR_INVALID; }
     return comm_unique_id(id);
+}
+
+int hymd_local_group_id(int world_size, uint8_t id[HYMD_NCCL_UNIQUE_ID_BYTES]) {
+    if (!id) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    return comm_local_group_id(world_size, id);
+}
+
+int hymd_ctx_check(hymd_ctx* c) {
+    if (!c) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    HYMD_CUDA(cudaDeviceSynchronize());
+    return comm_check_status(c);
 }
 
 int hymd_migrate_plan(hymd_ctx* c, const void* d_pos, int64_t n, int64_t* n_new, void* stream) {

@@ -81,7 +81,7 @@ struct __align__(16) Rec32 {
 struct __align__(16) Rec64 {
     unsigned long long ux, uy, uz, meta;
 };
-enum PeerBuffer : unsigned { PEER_WORK = 1u, PEER_HALO = 2u, PEER_K = 4u, PEER_MESH = 8u };
+enum PeerBuffer : unsigned { PEER_WORK = 1u, PEER_HALO = 2u, PEER_K = 4u, PEER_MESH = 8u, PEER_INBOX = 16u, PEER_RET = 32u };
 constexpr int HYMD_MAX_PEERS = 8;    // slabs (GPUs of one NVLink domain)
 constexpr int REC32_IDX_BITS = 27;  // <= 134M particles per GPU, <= 32 types
 constexpr int REC64_IDX_BITS = 40;
@@ -124,6 +124,12 @@ struct PlanEntry {
 };
 struct Comm;
 struct MigrateState;
+struct RouteState;
+// device-side particle counts of the last sort with several slabs (sort.cu, per-step routing)
+struct RouteTotals {
+    unsigned int n_work;    // records painted / read out here: home particles present + guests
+    unsigned int n_total;   // n_work + the home particles that are away (kept in an extra bin)
+};
 struct GpeState;
 
 struct PhaseInterval {
@@ -215,12 +221,8 @@ struct hymd_ctx {
                             // a peer may not overwrite them before another barrier (same call sequence
                             // on every rank, so the flags agree)
     hymd::MigrateState* mig;
+    hymd::RouteState* route;   // per-step routing of particles outside their home slab (several slabs)
     hymd::GpeState* gpe;    // general-Poisson-equation electrostatics (gpe.cu), allocated on first use
-    // multi-GPU: particles found outside the local slab by the last sort, copied to pinned host memory
-    // right after the count kernel and checked (without stalling the GPU) before the readout
-    unsigned int* h_out_of_slab;
-    cudaEvent_t ev_slab;
-    bool slab_check_pending;
 
     // readout TMA
     CUtensorMap tmap_gmesh, tmap_emesh;
@@ -268,6 +270,14 @@ int sort_particles(hymd_ctx* c, const void* d_pos, const int32_t* d_types, const
                    int64_t n, bool reuse, cudaStream_t s);
 size_t scan_temp_bytes(long long n);
 int gather_charges(hymd_ctx* c, const void* d_q, cudaStream_t s);
+// per-step routing (sort.cu)
+int route_prepare(hymd_ctx* c, int64_t n, cudaStream_t s);
+void route_destroy(hymd_ctx* c);
+long long route_guest_rows(const hymd_ctx* c);
+const RouteTotals* route_totals(const hymd_ctx* c);
+int route_return(hymd_ctx* c, void* d_force, cudaStream_t s);
+int route_acquire_return(hymd_ctx* c, cudaStream_t s);
+void route_peer_ret(const hymd_ctx* c, void** out, long long* G);
 // paint.cu
 int paint_types(hymd_ctx* c, cudaStream_t s);
 int paint_charges(hymd_ctx* c, cudaStream_t s);
@@ -303,6 +313,12 @@ int migrate_apply(hymd_ctx* c, const void* d_in, void* d_out, int row_bytes, cud
 void migrate_destroy(hymd_ctx* c);
 // comm.cu
 int comm_unique_id(uint8_t* id);
+int comm_local_group_id(int world_size, uint8_t* id);
+bool comm_is_local(const hymd_ctx* c);
+unsigned int* comm_status_device(hymd_ctx* c);
+int comm_check_status(hymd_ctx* c);
+int comm_barrier_payload(hymd_ctx* c, const uint32_t* d_payload, cudaStream_t s);
+const uint32_t* comm_payload(hymd_ctx* c);
 int comm_create(hymd_ctx* c, const uint8_t* id);
 void comm_destroy(hymd_ctx* c);
 int comm_alltoall(hymd_ctx* c, const void* send, void* recv, size_t bytes_per_peer, cudaStream_t s);

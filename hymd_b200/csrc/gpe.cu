@@ -185,7 +185,7 @@ static int galloc(void** p, size_t bytes, bool zero) {
         set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
         return HYMD_ERR_NOMEM;
     }
-    if (zero) cudaMemset(*p, 0, bytes);
+    if (zero) { cudaMemset(*p, 0, bytes); cudaDeviceSynchronize(); }
     return HYMD_OK;
 }
 
@@ -217,6 +217,7 @@ static int gpe_state(hymd_ctx* c) {
         int id[HYMD_MAX_TYPES];
         for (int t = 0; t < HYMD_MAX_TYPES; ++t) id[t] = t;
         HYMD_CUDA(cudaMemcpy(st->urow_id, id, sizeof(id), cudaMemcpyHostToDevice));
+        HYMD_CUDA(cudaDeviceSynchronize());
     }
     if (!st->h_delta) HYMD_CUDA(cudaMallocHost((void**)&st->h_delta, 2 * sizeof(double)));
     return HYMD_OK;

@@ -709,6 +709,7 @@ static int plane_tables(hymd_ctx* c) {
         }
         (a ? c->ztw : c->ytw) = d;
     }
+    HYMD_CUDA(cudaDeviceSynchronize());   // uploads ran on the legacy stream, the kernels use the caller's
     return HYMD_OK;
 }
 

@@ -257,6 +257,13 @@ struct GatherParams {
     long long n, ghost_elems;
     int Ny1, Nzp;            // Ny + 1, padded z pitch
     int fbx, fby, fbz;
+    // several slabs (sort.cu, per-step routing): n is a capacity bound, the live count is rt->n_work;
+    // records with idx >= n_home are guests: guest e = idx - n_home came from rank e / G as its row
+    // e % G, and its force goes into that rank's return section for this rank
+    const RouteTotals* rt;
+    long long n_home, G;
+    int rank;
+    void* ret[HYMD_MAX_PEERS];
 };
 
 template <typename real, bool CHARGE>
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(256) readout_gather_kernel(
     using Tr = RTraits<real>;
     using UT = typename Tr::UT;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
+    if (i >= (p.rt ? (long long)p.rt->n_work : p.n)) return;
     const typename Tr::Rec rc = rec[i];
     const UT mx = ((UT)1 << p.fbx) - 1, my = ((UT)1 << p.fby) - 1, mz = ((UT)1 << p.fbz) - 1;
     const real dx = (real)(rc.ux & mx) / (real)((UT)1 << p.fbx), dy = (real)(rc.uy & my) / (real)((UT)1 << p.fby),
@@ -291,23 +298,41 @@ __global__ void __launch_bounds__(256) readout_gather_kernel(
         }
     }
     if (CHARGE) { const real q = q_sorted[i]; f0 *= q; f1 *= q; f2 *= q; }
-    real* o = force + (size_t)(rc.meta & (((UT)1 << Tr::IDX_BITS) - 1)) * 3;
+    const long long idx = (long long)(rc.meta & (((UT)1 << Tr::IDX_BITS) - 1));
+    real* o;
+    if (p.rt != nullptr && idx >= p.n_home) {
+        const long long e = idx - p.n_home;
+        o = reinterpret_cast<real*>(p.ret[(int)(e / p.G)]) + 3 * ((long long)p.rank * p.G + e % p.G);
+    } else {
+        o = force + (size_t)idx * 3;
+    }
     o[0] = f0; o[1] = f1; o[2] = f2;
+}
+
+static void gather_params(hymd_ctx* c, GatherParams& p) {
+    const Geometry& g = c->g;
+    p.n = c->np; p.ghost_elems = g.ghost_elems; p.Ny1 = g.Ny + 1; p.Nzp = g.Nzp;
+    p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
+    p.rt = route_totals(c);
+    p.n_home = c->np; p.rank = g.rank;
+    route_peer_ret(c, p.ret, &p.G);
+    if (p.rt) p.n = c->np + route_guest_rows(c);
 }
 
 template <typename real, bool CHARGE>
 static int launch_gather(hymd_ctx* c, void* d_force, cudaStream_t s) {
     using Tr = RTraits<real>;
-    const Geometry& g = c->g;
     GatherParams p;
-    p.n = c->np; p.ghost_elems = g.ghost_elems; p.Ny1 = g.Ny + 1; p.Nzp = g.Nzp;
-    p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
+    gather_params(c, p);
+    HYMD_CHECK(route_acquire_return(c, s));
     const unsigned int blocks = (unsigned int)((p.n + 255) / 256);
-    readout_gather_kernel<real, CHARGE><<<blocks, 256, 0, s>>>(
-        (const real*)(CHARGE ? c->emesh : c->gmesh), (const typename Tr::Rec*)c->rec,
-        (const real*)c->q_sorted, c->d_urow, (real*)d_force, p);
-    HYMD_LAUNCH_CHECK(c);
-    return HYMD_OK;
+    if (blocks > 0) {
+        readout_gather_kernel<real, CHARGE><<<blocks, 256, 0, s>>>(
+            (const real*)(CHARGE ? c->emesh : c->gmesh), (const typename Tr::Rec*)c->rec,
+            (const real*)c->q_sorted, c->d_urow, (real*)d_force, p);
+        HYMD_LAUNCH_CHECK(c);
+    }
+    return route_return(c, d_force, s);
 }
 
 // Periodic images into the ghost planes of nfields ghost-padded meshes (single-GPU x; y and z
@@ -456,14 +481,15 @@ static int launch_readout_tile(hymd_ctx* c, void* d_force, cudaStream_t s) {
 
 // Default: the direct gather (measured faster at C4: 0.25 ms vs 0.30 ms for the TMA-staged tiles
 // with cell-ordered callers); HYMD_B200_READOUT=tma selects the TMA-staged kernel.
-static bool use_gather() {
+static bool use_gather(const hymd_ctx* c) {
+    if (c->g.P > 1) return true;      // guests' forces go to their owners (per-step routing): gather kernel only
     const char* e = getenv("HYMD_B200_READOUT");
     return !(e && e[0] == 't');
 }
 
 template <typename real, bool CHARGE>
 static int launch_readout(hymd_ctx* c, void* d_force, cudaStream_t s) {
-    if (use_gather()) return launch_gather<real, CHARGE>(c, d_force, s);
+    if (use_gather(c)) return launch_gather<real, CHARGE>(c, d_force, s);
     switch (c->rtx * 16 + c->rty) {
         case 4 * 16 + 8: return launch_readout_tile<real, CHARGE, 4, 8>(c, d_force, s);
         case 4 * 16 + 4: return launch_readout_tile<real, CHARGE, 4, 4>(c, d_force, s);
@@ -482,10 +508,9 @@ static int launch_readout(hymd_ctx* c, void* d_force, cudaStream_t s) {
 template <typename real>
 static int launch_gather_custom(hymd_ctx* c, const void* mesh, const int* d_urow, void* d_force, cudaStream_t s) {
     using Tr = RTraits<real>;
-    const Geometry& g = c->g;
     GatherParams p;
-    p.n = c->np; p.ghost_elems = g.ghost_elems; p.Ny1 = g.Ny + 1; p.Nzp = g.Nzp;
-    p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
+    gather_params(c, p);
+    if (p.rt) { set_error("custom read-outs run on a single slab only"); return HYMD_ERR_STATE; }
     const unsigned int blocks = (unsigned int)((p.n + 255) / 256);
     readout_gather_kernel<real, false><<<blocks, 256, 0, s>>>(
         (const real*)mesh, (const typename Tr::Rec*)c->rec, (const real*)c->q_sorted, d_urow, (real*)d_force, p);

@@ -47,6 +47,7 @@ static int grow(void** p, size_t* have, size_t want) {
         return HYMD_ERR_NOMEM;
     }
     cudaMemset(*p, 0, want);
+    cudaDeviceSynchronize();     // the memset runs on the legacy stream, the users on non-blocking ones
     *have = want;
     return HYMD_OK;
 }

@@ -63,25 +63,39 @@ __device__ __forceinline__ void warp_runs(uint32_t key, unsigned& head_lane, uns
 // in the previous call (its index and type come from the previous record), otherwise particle j
 // of the caller's arrays.  It converts the CURRENT position to the fixed-point record, leaves it
 // in stage[j] (in place over the previous record) and counts its cell.
-template <typename real, typename RecT, typename UT, int IDX_BITS, bool REUSE>
+//
+// ROUTED (several slabs, route.cu): the staged array of the previous call also holds that call's guests
+// (records with idx >= n, dropped here: this step's guests are binned by guest_count_kernel) and, in an
+// extra bin `ncell` at its end, the home particles that were away; REUSE then walks all
+// rt->n_total records.  A home particle outside this rank's slab goes to the away bin -- it is painted
+// and read out on the rank that owns its cell.  keys[j] keeps the bin for the scatter pass.
+template <typename real, typename RecT, typename UT, int IDX_BITS, bool REUSE, bool ROUTED>
 __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos,
                                                     const int32_t* __restrict__ types, long long n,
                                                     SortParams p, RecT* __restrict__ stage,
                                                     uint32_t* __restrict__ cnt,
-                                                    DeviceScalars* __restrict__ sc) {
+                                                    DeviceScalars* __restrict__ sc,
+                                                    const RouteTotals* __restrict__ rt,
+                                                    uint32_t* __restrict__ keys, uint32_t away_bin) {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     unsigned int r1 = 0, bad = 0;
     uint32_t key = 0xffffffffu;                        // lanes past the end: a run of their own
-    if (j < n) {
-        UT idx, type;
+    const long long limit = (ROUTED && REUSE) ? (long long)rt->n_total : n;
+    bool live = j < limit;
+    UT idx = 0, type = 0;
+    if (live) {
         if (REUSE) {
             const UT meta = stage[j].meta;
             idx = meta & (((UT)1 << IDX_BITS) - 1);
             type = meta >> IDX_BITS;
+            if (ROUTED && (long long)idx >= n) live = false;      // a guest of the previous step
         } else {
             idx = (UT)j;
             type = (UT)(uint32_t)types[j];
         }
+    }
+    if (ROUTED && j < limit && !live) keys[j] = 0xffffffffu;
+    if (live) {
         int cx, cy, cz;
         double dx, dy, dz;
         split_coord((double)pos[3 * idx + 0] * p.sx, p.Nx, cx, dx);
@@ -99,10 +113,15 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
         r.meta = idx | (type << IDX_BITS);
         stage[j] = r;
         key = (uint32_t)(((long long)lx * p.Ny + cy) * p.nbz + zbin_of(cz, p.Nz));
+        if (ROUTED) {
+            if (bad) key = away_bin;
+            keys[j] = key;
+        }
     }
     unsigned head_lane, rank, count;
     warp_runs(key, head_lane, rank, count);
-    if (rank == 0 && j < n) r1 = atomicAdd(&cnt[key], count) + count;
+    if (rank == 0 && live) r1 = atomicAdd(&cnt[key], count) + count;
+    if (ROUTED && key == away_bin) r1 = 0;             // the away bin does not bound the paint scale
     unsigned int m = __reduce_max_sync(0xffffffffu, r1);
     unsigned int b = __reduce_add_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0) {
@@ -112,16 +131,25 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
 }
 
 // Pass 2 (after the scan): staged record j goes to the next free slot of its cell.
-template <typename real, typename RecT, typename UT, int IDX_BITS>
+template <typename real, typename RecT, typename UT, int IDX_BITS, bool ROUTED>
 __global__ void __launch_bounds__(256) scatter_kernel(
     const RecT* __restrict__ stage, const real* __restrict__ q, long long n, SortParams p,
     uint32_t* __restrict__ cur, RecT* __restrict__ rec, real* __restrict__ q_sorted,
-    DeviceScalars* __restrict__ sc) {
+    DeviceScalars* __restrict__ sc, const RouteTotals* __restrict__ rt, const uint32_t* __restrict__ keys,
+    int reuse) {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     float aq = 0.f;
     RecT r;
     uint32_t key = 0xffffffffu;
-    if (j < n) {
+    const long long limit = (ROUTED && reuse) ? (long long)rt->n_total : n;
+    bool live = j < limit;
+    if (ROUTED) {
+        if (live) {
+            key = keys[j];
+            live = key != 0xffffffffu;
+            if (live) r = stage[j];
+        }
+    } else if (live) {
         r = stage[j];
         const long long lx = (long long)(r.ux >> p.fbx), cy = (long long)(r.uy >> p.fby),
                         cz = (long long)(r.uz >> p.fbz);
@@ -130,9 +158,9 @@ __global__ void __launch_bounds__(256) scatter_kernel(
     unsigned head_lane, rank, count;
     warp_runs(key, head_lane, rank, count);
     uint32_t base = 0;
-    if (rank == 0 && j < n) base = atomicAdd(&cur[key], count);
+    if (rank == 0 && live) base = atomicAdd(&cur[key], count);
     base = __shfl_sync(0xffffffffu, base, (int)head_lane);
-    if (j < n) {
+    if (live) {
         const size_t slot = (size_t)base + rank;
         rec[slot] = r;
         if (q != nullptr) {
@@ -148,17 +176,21 @@ __global__ void __launch_bounds__(256) scatter_kernel(
 }
 
 // Charges into sorted order for a sort that was made without them (update_field_force_q is
-// called after update_field on the same positions: main.py:1006-1058).
+// called after update_field on the same positions: main.py:1006-1058).  Several slabs: n = capacity
+// bound, the live count is rt->n_total, guests read the charges their owners sent (gq).
 template <typename real, typename RecT, typename UT, int IDX_BITS>
 __global__ void __launch_bounds__(256) gather_charges_kernel(const RecT* __restrict__ rec,
                                                              const real* __restrict__ q, long long n,
                                                              real* __restrict__ q_sorted,
-                                                             DeviceScalars* __restrict__ sc) {
+                                                             DeviceScalars* __restrict__ sc,
+                                                             const RouteTotals* __restrict__ rt,
+                                                             const real* __restrict__ gq, long long n_home) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     float aq = 0.f;
+    if (rt != nullptr) n = (long long)rt->n_total;
     if (i < n) {
-        const UT idx = rec[i].meta & (((UT)1 << IDX_BITS) - 1);
-        const real qi = q[idx];
+        const long long idx = (long long)(rec[i].meta & (((UT)1 << IDX_BITS) - 1));
+        const real qi = (rt != nullptr && idx >= n_home) ? gq[idx - n_home] : q[idx];
         q_sorted[i] = qi;
         aq = fabsf((float)qi);
     }
@@ -166,26 +198,305 @@ __global__ void __launch_bounds__(256) gather_charges_kernel(const RecT* __restr
     if ((threadIdx.x & 31) == 0 && m > sc->qmax_bits) atomicMax(&sc->qmax_bits, m);
 }
 
-int gather_charges(hymd_ctx* c, const void* d_q, cudaStream_t s) {
-    const long long n = c->np;
-    if (n == 0) return HYMD_OK;
-    const unsigned int blocks = (unsigned int)((n + 255) / 256);
-    if (c->f64)
-        gather_charges_kernel<double, Rec64, unsigned long long, REC64_IDX_BITS>
-            <<<blocks, 256, 0, s>>>((const Rec64*)c->rec, (const double*)d_q, n,
-                                    (double*)c->q_sorted, c->scalars);
-    else
-        gather_charges_kernel<float, Rec32, uint32_t, REC32_IDX_BITS>
-            <<<blocks, 256, 0, s>>>((const Rec32*)c->rec, (const float*)d_q, n,
-                                    (float*)c->q_sorted, c->scalars);
-    HYMD_LAUNCH_CHECK(c);
-    return HYMD_OK;
-}
-
 size_t scan_temp_bytes(long long n) {
     size_t bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
     return bytes;
+}
+
+// ---- per-step routing between slabs (several GPUs) ----------------------------------------------------
+// pmesh routes, on every paint / readout, a copy of each particle to the rank that owns its mesh cell and
+// brings the read-out value back (pm.decompose + Layout.exchange / Layout.gather: main.py:977-980,
+// field.py:574, 200).  The caller's particles therefore need not lie in their rank's slab: molecules live
+// on the rank of their first bead (field.py:1156-1163) and every particle drifts between two
+// domain_decomposition calls.  Here, per step and entirely on the device:
+//   route_scan   every home particle whose x cell belongs to another slab q is appended (atomic slot) to
+//                rank q's INBOX section for this rank -- position, type, (charge) stored straight into
+//                q's HBM over NVLink -- and remembered in sent_idx;
+//   barrier      carries the per-destination counts (comm_barrier_payload);
+//   binning      home particles that are present + the guests of all inbox sections share one counting
+//                sort; home particles that are away sit in an extra bin nobody paints;
+//   readout      a guest's force is stored into its owner's RETURN section; after a barrier the owner
+//                scatters the returned rows to force[sent_idx].
+// No host synchronisation, no NCCL call; capacities are fixed (G guests per rank pair), an overflow
+// raises status bit 1 (comm_check_status) instead of dropping particles silently.
+struct RoutePeers {
+    void* pos[HYMD_MAX_PEERS];
+    void* type[HYMD_MAX_PEERS];
+    void* q[HYMD_MAX_PEERS];
+    void* ret[HYMD_MAX_PEERS];
+};
+
+struct RouteState {
+    long long G = 0;                 // guest rows per (source, destination) pair
+    void* in_pos = nullptr;          // [P*G][3] real   inbox: section r written by rank r
+    int32_t* in_type = nullptr;      // [P*G]
+    void* in_q = nullptr;            // [P*G] real
+    void* ret = nullptr;             // [P*G][3] real   section q = forces of the guests sent to rank q
+    RoutePeers peers;
+    uint32_t* send_count = nullptr;  // [HYMD_MAX_PEERS]
+    int32_t* sent_idx = nullptr;     // [P*G]: home index of guest k sent to rank q at q*G + k
+    int32_t* types_home = nullptr;   // caller-order types (REUSE calls do not pass them)
+    long long types_cap = 0;
+    void* gstage = nullptr;          // [P*G] staged guest records
+    uint32_t* gkeys = nullptr;       // [P*G]
+    uint32_t* keys = nullptr;        // [cap + P*G] bins of the staged home records
+    long long keys_cap = 0;
+    RouteTotals* totals = nullptr;   // {n_work, n_total} of the last sort
+    bool sent_charges = false;
+};
+
+__device__ __forceinline__ int owner_of(double x, double sx, int Nx, int nxl) {
+    const double f = floor(x * sx);
+    long long c = (long long)f % Nx;
+    if (c < 0) c += Nx;
+    if (x * sx - f >= 1.0) c = (c + 1 == Nx) ? 0 : c + 1;     // same rounding rule as split_coord
+    return (int)(c / nxl);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256) route_scan_kernel(
+    const real* __restrict__ pos, const int32_t* __restrict__ types, const real* __restrict__ q, long long n,
+    double sx, int Nx, int nxl, int rank, long long G, RoutePeers peers, uint32_t* __restrict__ send_count,
+    int32_t* __restrict__ sent_idx, unsigned int* status) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const real x = pos[3 * i];
+    const int d = owner_of((double)x, sx, Nx, nxl);
+    if (d == rank) return;
+    const uint32_t k = atomicAdd(&send_count[d], 1u);
+    if (k >= (uint32_t)G) {                    // never silently: raised to the host through mapped memory
+        if (status) { atomicOr(status, 2u); atomicAdd(status + 1, 1u); }
+        return;
+    }
+    const long long row = (long long)rank * G + k;
+    real* dp = reinterpret_cast<real*>(peers.pos[d]) + 3 * row;
+    dp[0] = x; dp[1] = pos[3 * i + 1]; dp[2] = pos[3 * i + 2];
+    reinterpret_cast<int32_t*>(peers.type[d])[row] = types[i];
+    if (q != nullptr) reinterpret_cast<real*>(peers.q[d])[row] = q[i];
+    sent_idx[(long long)d * G + k] = (int32_t)i;
+}
+
+// charges of the guests already sent (hymd_set_charges after a sort without charges)
+template <typename real>
+__global__ void __launch_bounds__(256) route_charges_kernel(const real* __restrict__ q, int P, int rank, long long G,
+                                                            RoutePeers peers, const uint32_t* __restrict__ send_count,
+                                                            const int32_t* __restrict__ sent_idx) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)P * G) return;
+    const int d = (int)(e / G);
+    const long long k = e % G;
+    if (d == rank || k >= (long long)min(send_count[d], (uint32_t)G)) return;
+    reinterpret_cast<real*>(peers.q[d])[(long long)rank * G + k] = q[sent_idx[e]];
+}
+
+template <typename real, typename RecT, typename UT, int IDX_BITS>
+__global__ void __launch_bounds__(256) guest_count_kernel(
+    const real* __restrict__ gpos, const int32_t* __restrict__ gtype, const uint32_t* __restrict__ recv_count,
+    int P, int rank, long long G, long long n_home, SortParams p, RecT* __restrict__ gstage,
+    uint32_t* __restrict__ gkeys, uint32_t* __restrict__ cnt, DeviceScalars* __restrict__ sc, unsigned int* status) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)P * G) return;
+    const int r = (int)(e / G);
+    const long long k = e % G;
+    if (r == rank || k >= (long long)min(recv_count[r], (uint32_t)G)) return;
+    int cx, cy, cz;
+    double dx, dy, dz;
+    split_coord((double)gpos[3 * e + 0] * p.sx, p.Nx, cx, dx);
+    split_coord((double)gpos[3 * e + 1] * p.sy, p.Ny, cy, dy);
+    split_coord((double)gpos[3 * e + 2] * p.sz, p.Nz, cz, dz);
+    int lx = cx - p.x0;
+    if (lx < 0 || lx >= p.nxl) {               // cannot happen: sender and receiver use the same rule
+        if (status) atomicOr(status, 4u);
+        gkeys[e] = 0xffffffffu;
+        return;
+    }
+    RecT rc;
+    rc.ux = pack_coord<UT>(lx, dx, p.fbx);
+    rc.uy = pack_coord<UT>(cy, dy, p.fby);
+    rc.uz = pack_coord<UT>(cz, dz, p.fbz);
+    rc.meta = (UT)(n_home + e) | ((UT)(uint32_t)gtype[e] << IDX_BITS);
+    gstage[e] = rc;
+    const uint32_t key = (uint32_t)(((long long)lx * p.Ny + cy) * p.nbz + zbin_of(cz, p.Nz));
+    gkeys[e] = key;
+    const uint32_t c1 = atomicAdd(&cnt[key], 1u) + 1u;
+    if (c1 > sc->max_cell_count) atomicMax(&sc->max_cell_count, c1);
+}
+
+template <typename real, typename RecT>
+__global__ void __launch_bounds__(256) guest_scatter_kernel(
+    const RecT* __restrict__ gstage, const uint32_t* __restrict__ gkeys, const real* __restrict__ gq,
+    const uint32_t* __restrict__ recv_count, int P, int rank, long long G, uint32_t* __restrict__ cur,
+    RecT* __restrict__ rec, real* __restrict__ q_sorted, DeviceScalars* __restrict__ sc, int with_q) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)P * G) return;
+    const int r = (int)(e / G);
+    const long long k = e % G;
+    if (r == rank || k >= (long long)min(recv_count[r], (uint32_t)G)) return;
+    const uint32_t key = gkeys[e];
+    if (key == 0xffffffffu) return;
+    const uint32_t slot = atomicAdd(&cur[key], 1u);
+    rec[slot] = gstage[e];
+    if (with_q) {
+        const real qi = gq[e];
+        q_sorted[slot] = qi;
+        atomicMax(&sc->qmax_bits, __float_as_uint(fabsf((float)qi)));
+    }
+}
+
+// after the scatter passes: cell_start[k] = start of bin k, bin ncell = the away bin
+__global__ void route_totals_kernel(const uint32_t* __restrict__ cell_start, long long ncell,
+                                    RouteTotals* __restrict__ rt) {
+    rt->n_work = cell_start[ncell];
+    rt->n_total = cell_start[ncell + 1];
+}
+
+// forces of the guests this rank sent away, back at their home index
+template <typename real>
+__global__ void __launch_bounds__(256) route_return_kernel(const real* __restrict__ ret, int P, int rank, long long G,
+                                                           const uint32_t* __restrict__ send_count,
+                                                           const int32_t* __restrict__ sent_idx,
+                                                           real* __restrict__ force) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)P * G) return;
+    const int d = (int)(e / G);
+    const long long k = e % G;
+    if (d == rank || k >= (long long)min(send_count[d], (uint32_t)G)) return;
+    real* o = force + 3 * (long long)sent_idx[e];
+    o[0] = ret[3 * e]; o[1] = ret[3 * e + 1]; o[2] = ret[3 * e + 2];
+}
+
+static int route_alloc(void** p, size_t bytes) {
+    if (cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed in the routing buffers", bytes);
+        return HYMD_ERR_NOMEM;
+    }
+    cudaMemset(*p, 0, bytes ? bytes : 16);
+    return HYMD_OK;
+}
+
+void route_destroy(hymd_ctx* c) {
+    RouteState* r = c->route;
+    if (!r) return;
+    void* bufs[] = {r->in_pos, r->in_type, r->in_q, r->ret, r->send_count, r->sent_idx, r->types_home,
+                    r->gstage, r->gkeys, r->keys, r->totals};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    delete r;
+    c->route = nullptr;
+}
+
+long long route_guest_rows(const hymd_ctx* c) { return c->route ? c->route->G * c->g.P : 0; }
+const RouteTotals* route_totals(const hymd_ctx* c) { return c->route ? c->route->totals : nullptr; }
+
+// Collective (first sort of a context with several slabs): sizes the guest buffers from this rank's
+// particle count -- G = max(16384, n / 4) rows per rank pair, or HYMD_B200_GUEST_CAPACITY -- and
+// exchanges their peer addresses.  The buffers are never re-allocated (peers hold their addresses).
+int route_prepare(hymd_ctx* c, int64_t n, cudaStream_t s) {
+    if (c->route || c->g.P == 1) return HYMD_OK;
+    RouteState* r = new RouteState();
+    c->route = r;
+    const int P = c->g.P;
+    long long G = n / 4 > 16384 ? n / 4 : 16384;
+    if (const char* e = getenv("HYMD_B200_GUEST_CAPACITY")) {
+        const long long v = atoll(e);
+        if (v > 0) G = v;
+    }
+    // all ranks must agree on G (it is part of the peer addressing): take the maximum
+    {
+        uint32_t* d_tmp = nullptr;
+        HYMD_CHECK(route_alloc((void**)&d_tmp, 2 * HYMD_MAX_PEERS * sizeof(unsigned long long)));
+        unsigned long long mine = (unsigned long long)G, all[HYMD_MAX_PEERS];
+        HYMD_CUDA(cudaMemcpyAsync(d_tmp, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+        HYMD_CHECK(comm_allgather_host(c, d_tmp, (unsigned long long*)d_tmp + 1, sizeof(mine), s));
+        HYMD_CUDA(cudaMemcpyAsync(all, (unsigned long long*)d_tmp + 1, sizeof(mine) * P, cudaMemcpyDeviceToHost, s));
+        HYMD_CUDA(cudaStreamSynchronize(s));
+        for (int q = 0; q < P; ++q) if ((long long)all[q] > G) G = (long long)all[q];
+        cudaFree(d_tmp);
+    }
+    r->G = G;
+    const size_t rows = (size_t)P * G;
+    HYMD_CHECK(route_alloc(&r->in_pos, rows * 3 * c->rsz));
+    HYMD_CHECK(route_alloc((void**)&r->in_type, rows * 4));
+    HYMD_CHECK(route_alloc(&r->in_q, rows * c->rsz));
+    HYMD_CHECK(route_alloc(&r->ret, rows * 3 * c->rsz));
+    HYMD_CHECK(route_alloc((void**)&r->send_count, HYMD_MAX_PEERS * 4));
+    HYMD_CHECK(route_alloc((void**)&r->sent_idx, rows * 4));
+    HYMD_CHECK(route_alloc(&r->gstage, rows * (c->f64 ? sizeof(Rec64) : sizeof(Rec32))));
+    HYMD_CHECK(route_alloc((void**)&r->gkeys, rows * 4));
+    HYMD_CHECK(route_alloc((void**)&r->totals, sizeof(RouteTotals)));
+    HYMD_CUDA(cudaDeviceSynchronize());
+    HYMD_CHECK(comm_peer_ptrs(c, r->in_pos, r->peers.pos, s));
+    HYMD_CHECK(comm_peer_ptrs(c, r->in_type, r->peers.type, s));
+    HYMD_CHECK(comm_peer_ptrs(c, r->in_q, r->peers.q, s));
+    HYMD_CHECK(comm_peer_ptrs(c, r->ret, r->peers.ret, s));
+    return HYMD_OK;
+}
+
+template <typename real>
+static int route_gather_charges(hymd_ctx* c, const void* d_q, cudaStream_t s) {
+    // guests were sent without charges: send them now (same slots), then gather into sorted order
+    RouteState* r = c->route;
+    const Geometry& g = c->g;
+    if (!r->sent_charges) {
+        if (c->peer_busy & PEER_INBOX) HYMD_CHECK(comm_barrier(c, s));
+        const long long rows = (long long)g.P * r->G;
+        route_charges_kernel<real><<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
+            (const real*)d_q, g.P, g.rank, r->G, r->peers, r->send_count, r->sent_idx);
+        HYMD_LAUNCH_CHECK(c);
+        HYMD_CHECK(comm_barrier(c, s));
+        c->peer_busy |= PEER_INBOX;
+        r->sent_charges = true;
+    }
+    return HYMD_OK;
+}
+
+int gather_charges(hymd_ctx* c, const void* d_q, cudaStream_t s) {
+    const long long n = c->np;
+    RouteState* r = c->route;
+    if (r) HYMD_CHECK(c->f64 ? route_gather_charges<double>(c, d_q, s) : route_gather_charges<float>(c, d_q, s));
+    const long long bound = r ? n + (long long)c->g.P * r->G : n;
+    if (bound == 0) return HYMD_OK;
+    const unsigned int blocks = (unsigned int)((bound + 255) / 256);
+    if (c->f64)
+        gather_charges_kernel<double, Rec64, unsigned long long, REC64_IDX_BITS>
+            <<<blocks, 256, 0, s>>>((const Rec64*)c->rec, (const double*)d_q, n, (double*)c->q_sorted, c->scalars,
+                                    r ? r->totals : nullptr, r ? (const double*)r->in_q : nullptr, n);
+    else
+        gather_charges_kernel<float, Rec32, uint32_t, REC32_IDX_BITS>
+            <<<blocks, 256, 0, s>>>((const Rec32*)c->rec, (const float*)d_q, n, (float*)c->q_sorted, c->scalars,
+                                    r ? r->totals : nullptr, r ? (const float*)r->in_q : nullptr, n);
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
+}
+
+// readout side: forces of the guests that were sent away, back into the caller's array
+int route_return(hymd_ctx* c, void* d_force, cudaStream_t s) {
+    RouteState* r = c->route;
+    if (!r) return HYMD_OK;
+    const Geometry& g = c->g;
+    HYMD_CHECK(comm_barrier(c, s));                   // every rank's readout has stored its guests' rows
+    const long long rows = (long long)g.P * r->G;
+    const unsigned blocks = (unsigned)((rows + 255) / 256);
+    if (c->f64) route_return_kernel<double><<<blocks, 256, 0, s>>>((const double*)r->ret, g.P, g.rank, r->G,
+                                                                   r->send_count, r->sent_idx, (double*)d_force);
+    else route_return_kernel<float><<<blocks, 256, 0, s>>>((const float*)r->ret, g.P, g.rank, r->G,
+                                                           r->send_count, r->sent_idx, (float*)d_force);
+    HYMD_LAUNCH_CHECK(c);
+    c->peer_busy |= PEER_RET;
+    return HYMD_OK;
+}
+
+int route_acquire_return(hymd_ctx* c, cudaStream_t s) {
+    // before a readout stores guests' rows into the owners' return sections: the owners must have consumed
+    // the previous contents (a barrier has passed since their route_return)
+    if (c->route && (c->peer_busy & PEER_RET)) return comm_barrier(c, s);
+    return HYMD_OK;
+}
+
+void route_peer_ret(const hymd_ctx* c, void** out, long long* G) {
+    for (int q = 0; q < HYMD_MAX_PEERS; ++q) out[q] = c->route ? c->route->peers.ret[q] : nullptr;
+    *G = c->route ? c->route->G : 0;
 }
 
 template <typename real, typename RecT, typename UT, int IDX_BITS>
@@ -197,28 +508,93 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
     p.fbx = g.fbx; p.fby = g.fby; p.fbz = g.fbz;
     p.sx = g.Nx / g.box[0]; p.sy = g.Ny / g.box[1]; p.sz = g.Nz / g.box[2];
     const long long ncell = g.ncell;
+    const bool routed = g.P > 1;
+    RouteState* r = nullptr;
+    long long rows = 0;
+    if (routed) {
+        HYMD_CHECK(route_prepare(c, n, s));
+        r = c->route;
+        rows = (long long)g.P * r->G;
+        if (n + rows >= ((long long)1 << IDX_BITS)) {
+            set_error("n + guest rows = %lld exceeds the record index range", n + rows);
+            return HYMD_ERR_CAPACITY;
+        }
+        if (r->keys_cap < c->cap + rows) {
+            if (r->keys) { cudaStreamSynchronize(s); cudaFree(r->keys); r->keys = nullptr; }
+            r->keys_cap = c->cap + rows;
+            HYMD_CHECK(route_alloc((void**)&r->keys, (size_t)r->keys_cap * 4));
+        }
+        if (!reuse) {     // caller-order types: REUSE calls do not pass them again
+            if (r->types_cap < n) {
+                if (r->types_home) { cudaStreamSynchronize(s); cudaFree(r->types_home); r->types_home = nullptr; }
+                r->types_cap = n + n / 8 + 1024;
+                HYMD_CHECK(route_alloc((void**)&r->types_home, (size_t)r->types_cap * 4));
+            }
+            if (n > 0) HYMD_CUDA(cudaMemcpyAsync(r->types_home, d_types, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        // ---- guests out: stores into the owners' inboxes, counts ride on the barrier ----------------
+        if (c->peer_busy & PEER_INBOX) HYMD_CHECK(comm_barrier(c, s));
+        HYMD_CUDA(cudaMemsetAsync(r->send_count, 0, HYMD_MAX_PEERS * 4, s));
+        if (n > 0) {
+            route_scan_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+                (const real*)d_pos, r->types_home, (const real*)d_q, n, p.sx, g.Nx, g.nxl, g.rank, r->G, r->peers,
+                r->send_count, r->sent_idx, comm_status_device(c));
+            HYMD_LAUNCH_CHECK(c);
+        }
+        HYMD_CHECK(comm_barrier_payload(c, r->send_count, s));
+        c->peer_busy |= PEER_INBOX;
+        r->sent_charges = d_q != nullptr;
+    }
     uint32_t* cur = c->cell_start + 1;
-    HYMD_CUDA(cudaMemsetAsync(c->cell_start, 0, (size_t)(ncell + 2) * sizeof(uint32_t), s));
+    HYMD_CUDA(cudaMemsetAsync(c->cell_start, 0, (size_t)(ncell + 3) * sizeof(uint32_t), s));
     HYMD_CUDA(cudaMemsetAsync(c->scalars, 0, sizeof(DeviceScalars), s));
     // stage = the buffer holding the previous sorted records (overwritten in place), out = the other
     RecT* stage = (RecT*)c->rec;
     RecT* out = (RecT*)c->rec_alt;
-    const unsigned int blocks = (unsigned int)((n + 255) / 256);
-    if (n > 0) {
-        if (reuse)
-            count_kernel<real, RecT, UT, IDX_BITS, true><<<blocks, 256, 0, s>>>(
-                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars);
-        else
-            count_kernel<real, RecT, UT, IDX_BITS, false><<<blocks, 256, 0, s>>>(
-                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars);
+    const long long span = (routed && reuse) ? n + rows : n;     // bound of the staged home records
+    const unsigned int blocks = (unsigned int)((span + 255) / 256);
+    if (span > 0) {
+        if (routed) {
+            if (reuse)
+                count_kernel<real, RecT, UT, IDX_BITS, true, true><<<blocks, 256, 0, s>>>(
+                    (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, r->totals, r->keys, (uint32_t)ncell);
+            else
+                count_kernel<real, RecT, UT, IDX_BITS, false, true><<<blocks, 256, 0, s>>>(
+                    (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, r->totals, r->keys, (uint32_t)ncell);
+        } else if (reuse) {
+            count_kernel<real, RecT, UT, IDX_BITS, true, false><<<blocks, 256, 0, s>>>(
+                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, nullptr, nullptr, 0u);
+        } else {
+            count_kernel<real, RecT, UT, IDX_BITS, false, false><<<blocks, 256, 0, s>>>(
+                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, nullptr, nullptr, 0u);
+        }
+        HYMD_LAUNCH_CHECK(c);
+    }
+    const unsigned gblocks = (unsigned)((rows + 255) / 256);
+    if (routed) {
+        guest_count_kernel<real, RecT, UT, IDX_BITS><<<gblocks, 256, 0, s>>>(
+            (const real*)r->in_pos, r->in_type, comm_payload(c), g.P, g.rank, r->G, n, p, (RecT*)r->gstage, r->gkeys,
+            cur, c->scalars, comm_status_device(c));
         HYMD_LAUNCH_CHECK(c);
     }
     size_t tmp = c->scan_tmp_bytes;
-    HYMD_CUDA(cub::DeviceScan::ExclusiveSum(c->scan_tmp, tmp, cur, cur, (int)ncell, s));
+    HYMD_CUDA(cub::DeviceScan::ExclusiveSum(c->scan_tmp, tmp, cur, cur, (int)(routed ? ncell + 1 : ncell), s));
     c->launches += 2;  // cub scan: init + scan kernels
-    if (n > 0) {
-        scatter_kernel<real, RecT, UT, IDX_BITS><<<blocks, 256, 0, s>>>(
-            stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars);
+    if (span > 0) {
+        if (routed)
+            scatter_kernel<real, RecT, UT, IDX_BITS, true><<<blocks, 256, 0, s>>>(
+                stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars, r->totals, r->keys, reuse ? 1 : 0);
+        else
+            scatter_kernel<real, RecT, UT, IDX_BITS, false><<<blocks, 256, 0, s>>>(
+                stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars, nullptr, nullptr, 0);
+        HYMD_LAUNCH_CHECK(c);
+    }
+    if (routed) {
+        guest_scatter_kernel<real, RecT><<<gblocks, 256, 0, s>>>(
+            (const RecT*)r->gstage, r->gkeys, (const real*)r->in_q, comm_payload(c), g.P, g.rank, r->G, cur, out,
+            (real*)c->q_sorted, c->scalars, d_q != nullptr ? 1 : 0);
+        HYMD_LAUNCH_CHECK(c);
+        route_totals_kernel<<<1, 1, 0, s>>>(c->cell_start, ncell, r->totals);
         HYMD_LAUNCH_CHECK(c);
     }
     c->rec = out;

@@ -42,8 +42,8 @@ def initialize_pm(pmesh, config, comm=None):
     dtype = "f8" if np.dtype(config.dtype) == np.float64 else "f4"
     coulombtype = getattr(config, "coulombtype", None)
     if coulombtype == "PIC_Spectral_GPE":
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        from . import _world
+        if _world.current().size > 1:
             raise NotImplementedError("coulombtype='PIC_Spectral_GPE' runs on a single GPU only")
     pm = ParticleMesh(config.mesh_size, BoxSize=config.box_size, dtype=dtype, comm=comm,
                       config=config)
@@ -103,17 +103,6 @@ def update_field(phi, phi_laplacian, phi_transfer, layouts, force_mesh, hamilton
 
 def _output_buffer(pm, out, n):
     """Device tensor the kernel writes into, and a callback copying it back if needed."""
-    if getattr(pm, "auto_route", False):
-        # the kernel writes the working set's rows; they travel back to their owners afterwards
-        buf = torch.empty((n, 3), dtype=pm.dtype, device=pm.device)
-
-        def routed_back():
-            res = pm.route_back(buf)
-            if isinstance(out, torch.Tensor):
-                out.copy_(res)
-            else:
-                out[...] = res.cpu().numpy()
-        return buf, routed_back
     if isinstance(out, torch.Tensor) and out.device == pm.device and out.dtype == pm.dtype \
             and out.is_contiguous() and tuple(out.shape) == (n, 3):
         return out, None
@@ -329,11 +318,5 @@ def domain_decomposition(positions, pm, *args, molecules=None, bonds=None, topol
 
 
 def _allreduce(t):
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        t = t.clone()
-        if dist.get_backend() == "nccl":
-            t = t.cuda()
-        dist.all_reduce(t)
-        t = t.cpu()
-    return t
+    from . import _world
+    return _world.current().allreduce(t).cpu()

@@ -15,15 +15,8 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, _world
 from .hamiltonian import affine_parameters, get_hamiltonian
-
-
-def _dist():
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
-        return dist
-    return None
 
 
 class _CudaView:
@@ -140,9 +133,8 @@ class ParticleMesh:
         self.dtype = torch.float64 if dt == np.dtype("f8") else torch.float32
         self.cdtype = torch.complex128 if dt == np.dtype("f8") else torch.complex64
         self.comm = comm
-        dist = _dist()
-        self.world_size = dist.get_world_size() if dist else 1
-        self.rank = dist.get_rank() if dist else 0
+        self.world = _world.current()     # torch.distributed ranks, virtual (in-process) ranks or one GPU
+        self.world_size, self.rank = self.world.size, self.world.rank
         self.np = (self.world_size, 1)          # processor mesh, logged at main.py:252
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.n_types = int(config.n_types)
@@ -157,17 +149,10 @@ class ParticleMesh:
         self._keep = (None, None, None)
         self._n_local = 0
         self._sorted_with_charges = False
-        # per-step routing of particles that are not on the rank owning their slab (pmesh's
-        # Layout.exchange inside paint / readout): opt-in until it has run on several GPUs
-        import os
-        self.auto_route = self.world_size > 1 and os.environ.get("HYMD_B200_AUTO_ROUTE", "0") == "1"
-        self._route = None
         if hamiltonian is None:
             hamiltonian = get_hamiltonian(config) if _has_density_params(config) else None
         cfg = self._make_config(config, hamiltonian)
-        nccl_id = None
-        if self.world_size > 1:
-            nccl_id = self._broadcast_nccl_id()
+        nccl_id = self.world.comm_id(self.lib, self.device) if self.world_size > 1 else None
         _lib.check(self.lib.hymd_ctx_create(ctypes.byref(cfg), nccl_id, ctypes.byref(self._ctx)))
 
     # ---- context configuration ---------------------------------------------------------
@@ -237,20 +222,6 @@ class ParticleMesh:
         dp = ctypes.POINTER(ctypes.c_double)
         _lib.check(self.lib.hymd_ctx_set_box(self._ctx, self.BoxSize.ctypes.data_as(dp)))
         self._sort_key = None
-
-    def _broadcast_nccl_id(self):
-        dist = _dist()
-        buf = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES)()
-        if self.rank == 0:
-            _lib.check(self.lib.hymd_nccl_unique_id(buf))
-        t = torch.tensor(list(buf), dtype=torch.uint8)
-        if dist.get_backend() == "nccl":
-            t = t.to(self.device)
-        dist.broadcast(t, src=0)
-        vals = t.cpu().tolist()
-        for i, v in enumerate(vals):
-            buf[i] = v
-        return buf
 
     def close(self):
         if self._ctx:
@@ -365,11 +336,6 @@ class ParticleMesh:
         tk = None if types is None else self._fingerprint_types(types)
         if not force and pk == self._sort_key and (tk is None or tk == self._sort_types_key):
             if charges is not None and not self._sorted_with_charges:
-                if self.auto_route:      # same positions => same plan => same working order
-                    saved = self._route
-                    _, charges = self.route_in(positions, charges)
-                    self._route = saved
-                    self._sort_key, self._sort_types_key = pk, tk     # migrate() cleared them
                 q = self.as_device(charges, shape=(self._n_local,))
                 _lib.check(self.lib.hymd_set_charges(self._ctx, ctypes.c_void_p(q.data_ptr()),
                                                      self.stream))
@@ -379,17 +345,13 @@ class ParticleMesh:
         pos = self.as_device(positions, role="positions")
         if pos.ndim != 2 or pos.shape[1] != 3:
             raise ValueError(f"positions must be (N,3), got {tuple(pos.shape)}")
-        if self.auto_route:
-            # working set = residents at home + guests from the other ranks; its composition changes
-            # from step to step, so every routed sort is a cold one (migrate() forgets the order)
-            pos, types, charges = self.route_in(pos, types, charges)
         n = pos.shape[0]
         # Consecutive MD steps pass the same types object (HyMD reads the types once,
         # main.py:72-125): the library then re-bins starting from the previous cell order and
         # does not need the types again (they ride along in the sorted records).
         otk = ("none", n) if types is None else tk
         reuse = self._order_types_key is not None and otk == self._order_types_key \
-            and n == self._n_local and n > 0
+            and n == self._n_local and (n > 0 or self.world_size > 1)
         ty = None
         if not reuse:
             if types is None:
@@ -485,47 +447,12 @@ class ParticleMesh:
         _lib.check(self.lib.hymd_ctx_reset_order(self._ctx))
 
     def _allreduce_scalar(self, s):
-        dist = _dist()
-        if dist and self.world_size > 1:
-            s = s.clone()
-            dist.all_reduce(s)
-        v = s.item()
-        return v
+        return self.world.allreduce(s).item()
 
-    # ---- per-step routing (world_size > 1, HYMD_B200_AUTO_ROUTE=1) ---------------------------------
-    # The reference never requires a particle to sit on the rank that owns its mesh cell: pm.decompose
-    # routes copies to the owners for the paint and brings the read-out values back
-    # (main.py:977-980, field.py:200).  Molecules make this the normal case: domain_decomposition keeps a
-    # molecule on the rank of its FIRST bead (field.py:1156-1163), so beads of chains that straddle a slab
-    # face are guests on their rank.  route_in / route_back do the same with the migration kernels: the
-    # working set of a field call is "my particles that are at home + the guests the other ranks sent
-    # me", and results travel back by a second migration whose routing position is a point inside the
-    # origin rank's slab.
-    def route_in(self, positions, *arrays):
-        """Working copies of ``positions`` and ``arrays`` on the ranks owning the particles' slabs."""
-        pos = self.as_device(positions)
-        n = pos.shape[0]
-        origin_rank = torch.full((n,), self.rank, dtype=torch.int32, device=self.device)
-        origin_index = torch.arange(n, dtype=torch.int64, device=self.device)
-        keep = [a for a in arrays if a is not None]
-        out = self.migrate(pos, *keep, origin_rank, origin_index)
-        self._route = {"n": n, "rank": out[-2], "index": out[-1]}
-        it = iter(out[1:-2])
-        return (out[0],) + tuple(None if a is None else next(it) for a in arrays)
-
-    def route_back(self, values):
-        """Per-particle results of the working set (rows as ``route_in`` returned them) back to the
-        caller's particles, in the caller's order."""
-        r = self._route
-        if r is None or values.shape[0] != r["rank"].shape[0]:
-            raise _lib.HymdError("route_back without a matching route_in")
-        slab = float(self.BoxSize[0]) / self.world_size
-        fake = torch.zeros((values.shape[0], 3), dtype=self.dtype, device=self.device)
-        fake[:, 0] = ((r["rank"].to(torch.float64) + 0.5) * slab).to(self.dtype)
-        back, index = self.migrate(values, r["index"], routing_positions=fake)
-        out = torch.empty((r["n"],) + tuple(values.shape[1:]), dtype=values.dtype, device=self.device)
-        out[index] = back
-        return out
+    def check(self):
+        """Synchronize and raise if a device-side condition was flagged (guest capacity exceeded, a
+        peer-memory barrier timed out); the per-step calls check the same flags without synchronizing."""
+        _lib.check(self.lib.hymd_ctx_check(self._ctx))
 
     def migrate(self, positions, *arrays, routing_positions=None):
         """Re-home per-particle arrays on the rank owning their slab (``Layout.exchange`` of

@@ -89,6 +89,15 @@ int hymd_abi_version(void);
  * to hymd_ctx_create.  Replaces the MPI communicator handed to pmesh (field.py:45-47). */
 int hymd_nccl_unique_id(uint8_t id[HYMD_NCCL_UNIQUE_ID_BYTES]);
 
+/* "Virtual slabs": the world_size ranks are world_size host THREADS of this process (each with its own
+ * context and stream, on one GPU or several) instead of one process per GPU.  Writes an id that
+ * hymd_ctx_create accepts in place of an NCCL id; every thread then passes it with its own rank.  Peer
+ * memory is plain device memory of the same address space and barriers synchronise the stream and meet
+ * on the host, so the whole sharded pipeline (transposes, halos, per-step particle routing) runs -- and
+ * is tested -- on a single-GPU box.  Nothing in the reference corresponds (it is always one MPI rank
+ * per process). */
+int hymd_local_group_id(int world_size, uint8_t id[HYMD_NCCL_UNIQUE_ID_BYTES]);
+
 /* initialize_pm (field.py:10-149): builds cuFFT plans and every mesh buffer for this slab.
  * nccl_id may be NULL iff world_size == 1.  Synchronous. */
 int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** out);
@@ -103,8 +112,14 @@ int hymd_ctx_set_interaction(hymd_ctx* ctx, const double* A, const double* c, co
 /* pm.decompose(positions[types==t]) for all t (main.py:977-980, 1007): bins the n local
  * particles by mesh-cell bin (two bins per 32 cells of a cell row).  d_pos is (n,3) row-major in the context dtype, d_types int32 (n),
  * d_charges (n) in the context dtype or NULL.  Positions may lie anywhere (they are wrapped
- * periodically); with world_size > 1 every particle must lie inside this rank's slab
- * (see hymd_migrate).  Keeps no reference to the inputs after the stream work completes. */
+ * periodically).  With world_size > 1 the call is collective and does what pm.decompose +
+ * Layout.exchange do in the reference: a particle whose cell belongs to another rank's slab (a bead
+ * of a molecule that straddles a slab face, or a particle that drifted since the last
+ * domain_decomposition) is stored into that rank's guest inbox over NVLink, painted and read out
+ * there, and hymd_readout / hymd_pme_cycle bring its force back to the caller's row -- on the device,
+ * without host synchronisation.  The guest buffers hold max(16384, n/4) particles per rank pair
+ * (HYMD_B200_GUEST_CAPACITY overrides); exceeding them fails the next call with HYMD_ERR_CAPACITY.
+ * Keeps no reference to the inputs after the stream work completes. */
 int hymd_sort_particles(hymd_ctx* ctx, const void* d_pos, const int32_t* d_types,
                         const void* d_charges, int64_t n, void* stream);
 
@@ -170,9 +185,14 @@ int hymd_field_pressure(hymd_ctx* ctx, const double* A, const double* c, const d
 int hymd_get_field(hymd_ctx* ctx, int field_id, int t, int d, void** d_ptr, int64_t dims[3],
                    int64_t pitch[3]);
 
-/* Synchronizes and reports {max particles per sort bin (>= per cell), particles outside the local slab,
+/* Synchronizes and reports {max particles per sort bin (>= per cell), local particles that are guests on another slab,
  * local particle count, distinct potential rows} of the last hymd_sort_particles. */
 int hymd_ctx_status(hymd_ctx* ctx, int64_t out[4]);
+
+/* Synchronizes the device and returns the sticky device-raised conditions of a multi-slab context
+ * (guest capacity exceeded -> HYMD_ERR_CAPACITY, a peer-memory barrier timed out -> HYMD_ERR_NCCL);
+ * the per-step entry points check the same flags without synchronizing. */
+int hymd_ctx_check(hymd_ctx* ctx);
 
 /* Which code paths this context runs (bench / test bookkeeping): out = {fused x-line kernel,
  * one-pass (y,z) plane transforms, slab pipeline, exchanges over NVLink peer memory}, 0 or 1. */

@@ -2,11 +2,12 @@
 a single process to exercise the slab pipeline on one GPU via HYMD_B200_FORCE_SLAB=1).
 
     torchrun --nproc-per-node P tests/mgpu_worker.py [--dtype f64] [--pme] [--mesh 32 24 40]
-                                                     [--particles 20000] [--migrate] [--guests]
+                                                     [--particles 20000] [--migrate] [--route]
 
 Every rank builds the same seeded system, keeps the particles of its x-slab (or, with
---migrate, an arbitrary 1/P share that is re-homed by domain_decomposition; with --guests the
-same share WITHOUT re-homing, which must raise), runs update_field + compute_field_force (+ PME) through
+--migrate, an arbitrary 1/P share that is re-homed by domain_decomposition; with --route the
+same share WITHOUT re-homing: most particles are then guests on another rank's slab and are routed
+there and back inside every field call), runs update_field + compute_field_force (+ PME) through
 hymd_b200.field, and rank 0 compares the gathered forces, filtered densities and force meshes
 with the CPU oracle at the north-star tolerances (1e-5 fp32, 1e-10 fp64)."""
 import argparse
@@ -37,10 +38,9 @@ def main():
     ap.add_argument("--mesh", type=int, nargs=3, default=[32, 24, 40])
     ap.add_argument("--particles", dest="n", type=int, default=20000)
     ap.add_argument("--migrate", action="store_true")
-    ap.add_argument("--guests", action="store_true")
     ap.add_argument("--route", action="store_true",
-                    help="arbitrary share WITHOUT re-homing, HYMD_B200_AUTO_ROUTE=1 in the environment: the "
-                         "per-step routing layer must make the cycle equal the oracle")
+                    help="arbitrary share WITHOUT re-homing: the per-step routing inside the library must "
+                         "make the cycle equal the oracle")
     ap.add_argument("--seed", type=int, default=11)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -72,7 +72,7 @@ def main():
     # ownership
     nxl = args.mesh[0] // world
     cell = np.floor(pos[:, 0].astype(np.float64) * args.mesh[0] / float(box[0])).astype(np.int64) % args.mesh[0]
-    if args.migrate or args.guests or args.route:
+    if args.migrate or args.route:
         mine = (np.arange(n) % world) == rank          # arbitrary share, most particles not home
     else:
         mine = (cell // nxl) == rank
@@ -97,26 +97,6 @@ def main():
         assert bool(((st_cells // nxl) == rank).all()), "migrate left particles outside the slab"
     layouts = [pm.decompose(None) for _ in range(cfg.n_types)]
     force_d = torch.zeros((len(pos_d), 3), dtype=tdt, device=dev)
-    if args.guests:
-        # particles that are not at home and no domain_decomposition: must fail loudly, not paint
-        # them into the edge planes
-        from hymd_b200._lib import HymdError
-        raised = False
-        try:
-            F.update_field(phi, phi_laplacian, phi_transfer, layouts, force_mesh, ham, pm, pos_d, typ_d,
-                           cfg, v_ext, phi_fourier, v_ext_fourier, cfg.m)
-            F.compute_field_force(layouts, pos_d, force_mesh, force_d, typ_d, cfg.n_types)
-        except HymdError as e:
-            raised = "outside the x-slab" in str(e)
-        flag = torch.tensor([1 if raised else 0], device=dev)
-        if world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if rank == 0:
-            print("MGPU guests:", "OK" if flag.item() else "FAIL (no error for out-of-slab particles)", flush=True)
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        sys.exit(0 if flag.item() else 1)
     F.update_field(phi, phi_laplacian, phi_transfer, layouts, force_mesh, ham, pm, pos_d, typ_d,
                    cfg, v_ext, phi_fourier, v_ext_fourier, cfg.m, compute_potential=True)
     F.compute_field_force(layouts, pos_d, force_mesh, force_d, typ_d, cfg.n_types)

@@ -240,3 +240,26 @@ def test_write_epoch_changes_the_position_fingerprint():
     k1 = ParticleMesh._fingerprint(a)
     a[50, 1] = 1.0
     assert ParticleMesh._fingerprint(a) != k1
+
+
+def test_virtual_ranks_host_logic():
+    """hymd_b200._world.VirtualRanks: P threads see themselves as P ranks, all-reduce sums over them, an
+    exception in one rank surfaces in the caller (no GPU needed: hymd_local_group_id is host code)."""
+    import torch
+    from hymd_b200 import _world
+
+    def worker(rank):
+        w = _world.current()
+        assert (w.size, w.rank) == (3, rank)
+        return float(w.allreduce(torch.tensor([float(rank + 1)], dtype=torch.float64))[0])
+
+    assert _world.VirtualRanks(3).run(worker) == [6.0, 6.0, 6.0]
+    assert _world.current().size == 1
+
+    def failing(rank):
+        if rank == 1:
+            raise ValueError("rank 1 fails")
+        return _world.current().allreduce(torch.zeros(1))
+
+    with pytest.raises(ValueError, match="rank 1 fails"):
+        _world.VirtualRanks(3, timeout=5.0).run(failing)

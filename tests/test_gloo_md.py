@@ -29,11 +29,3 @@ def test_thermostat_over_ranks_matches_single_rank(host_lib, nproc):
     r = _torchrun(nproc, WORKER, [host_lib], 29611 + nproc)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "OK" in r.stdout
-
-
-@pytest.mark.parametrize("nproc", [2, 4])
-def test_per_step_routing_roundtrip(nproc):
-    """HYMD_B200_AUTO_ROUTE: route_in / route_back over a gloo stand-in for the migration kernels."""
-    r = _torchrun(nproc, os.path.join(ROOT, "tests", "gloo_route_worker.py"), [], 29631 + nproc)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert "OK" in r.stdout

@@ -83,20 +83,18 @@ def test_migration_rehomes_particles():
     _run(2, ["--dtype", "f64", "--pme", "--migrate"])
 
 
-def test_particles_outside_their_slab_fail_loudly():
-    """No domain_decomposition and particles that are not at home: the cycle must raise (the count
-    of out-of-slab particles of every sort is checked before the readout), never paint them into
-    the edge planes."""
-    _need(2)
-    _run(2, ["--dtype", "f64", "--guests"])
-
-
-@pytest.mark.xfail(strict=False, reason="per-step routing layer (HYMD_B200_AUTO_ROUTE): verified over a gloo stand-in "
-                                        "for the migration kernels only; its first multi-GPU run is pending")
+@pytest.mark.parametrize("nproc", [2, 4])
 @pytest.mark.parametrize("pme", [False, True])
-def test_guests_are_routed_to_their_slab_and_back(pme):
+def test_guests_are_routed_to_their_slab_and_back(pme, nproc):
     """Particles that are not on the rank owning their slab and NO domain_decomposition (what a molecule
-    straddling a slab face looks like): with HYMD_B200_AUTO_ROUTE=1 every field call routes working
-    copies to the owners and the forces back, like pmesh's Layout.exchange; results equal the oracle."""
+    straddling a slab face looks like): every field call routes them to the owners' guest inboxes over
+    NVLink and their forces back, like pmesh's Layout.exchange; results equal the oracle.  (The same data
+    flow runs on one GPU in tests/test_gpu_virtual_slabs.py.)"""
+    _need(nproc)
+    _run(nproc, ["--dtype", "f64", "--route", "--mesh", "32", "32", "32"] + (["--pme"] if pme else []))
+
+
+def test_nccl_barrier_fallback():
+    """HYMD_B200_NCCL_BARRIER=1: the round-1 all-reduce barrier instead of flags in peer memory."""
     _need(2)
-    _run(2, ["--dtype", "f64", "--route"] + (["--pme"] if pme else []), {"HYMD_B200_AUTO_ROUTE": "1"})
+    _run(2, ["--dtype", "f32", "--pme", "--route", "--mesh", "32", "32", "32"], {"HYMD_B200_NCCL_BARRIER": "1"})

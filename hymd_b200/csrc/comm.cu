@@ -497,9 +497,10 @@ static int setup_control(hymd_ctx* c) {
     void* peers[HYMD_MAX_PEERS] = {};
     HYMD_CHECK(comm_peer_ptrs(c, cm->ctrl, peers, 0));
     for (int q = 0; q < cm->P; ++q) cm->peer_ctrl[q] = (unsigned char*)peers[q];
+    // (in-process ranks sharing one device must not spin on each other: a device-wide synchronisation
+    // on one rank's host thread would wait for the other rank's spinning kernel -- they use the host barrier)
     const char* nb = getenv("HYMD_B200_NCCL_BARRIER");
-    const char* lf = getenv("HYMD_B200_LOCAL_FLAGS");
-    cm->flags = cm->local ? (lf && lf[0] == '1') : !(nb && nb[0] == '1');
+    cm->flags = !cm->local && !(nb && nb[0] == '1');
     return HYMD_OK;
 }
 

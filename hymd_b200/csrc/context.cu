@@ -238,7 +238,10 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     c->grad2 = c->fused && c->plane && !(no_grad2 && no_grad2[0] == '0');
     if (P > 1 && (st = comm_create(c, nccl_id))) return fail(st);
     const char* nccl_x = getenv("HYMD_B200_NCCL_EXCHANGE");
-    c->p2p = P > 1 && !(nccl_x && nccl_x[0] == '1');
+    c->p2p = P > 1 && (!(nccl_x && nccl_x[0] == '1') || comm_is_local(c));
+    const char* fpush = getenv("HYMD_B200_FUSED_PUSH");
+    c->fused_push = c->p2p && c->fused && c->plane && !(fpush && fpush[0] == '0') &&
+                    (g.nxl & (g.nxl - 1)) == 0 && (g.nyl & (g.nyl - 1)) == 0;
     if ((st = readout_setup(c))) return fail(st);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(HYMD_ERR_CUDA);
     *out = c;
@@ -381,16 +384,33 @@ int hymd_paint(hymd_ctx* c, void* stream) {
 // work layout of the batched 2-D c2r, otherwise f_hat in the k layout.
 static void* force_spectra(hymd_ctx* c) { return (c->fused && c->g.P == 1) ? c->wA : c->f_hat; }
 
-static int run_kspace(hymd_ctx* c, bool want_v, bool want_phif, cudaStream_t s) {
+// for_forces: the force spectra are consumed by the inverse (y,z) transforms right after (field / PME
+// cycle); with several slabs the x-line kernel then stores them straight into the peers' work buffers.
+// By-product calls (hymd_materialize) only want the k-space outputs and keep everything local.
+static int run_kspace(hymd_ctx* c, bool want_v, bool want_phif, cudaStream_t s, bool for_forces = false) {
     if (!c->fused) return kspace_forces(c, want_v, want_phif, s);
     HYMD_CHECK(ensure_work(c, 3 * c->U > c->T ? 3 * c->U : c->T));
+    if (for_forces && c->g.P > 1 && c->fused_push && c->plane) {
+        void* peers[HYMD_MAX_PEERS];
+        HYMD_CHECK(push_work_begin(c, (c->grad2 ? 2 : 3) * c->U, peers, s));
+        HYMD_CHECK(xline_forces(c, c->phi_hat, nullptr, want_v ? c->v_hat : nullptr,
+                                want_phif ? c->phif_hat : nullptr, s, peers));
+        return push_work_end(c, s);
+    }
     return xline_forces(c, c->phi_hat, force_spectra(c), want_v ? c->v_hat : nullptr,
                         want_phif ? c->phif_hat : nullptr, s);
 }
 
-static int run_kspace_pme(hymd_ctx* c, bool want_psi, cudaStream_t s) {
+static int run_kspace_pme(hymd_ctx* c, bool want_psi, cudaStream_t s, bool for_forces = false) {
     if (!c->fused) return kspace_pme(c, want_psi, s);
     HYMD_CHECK(ensure_work(c, 3 * c->U > c->T ? 3 * c->U : c->T));
+    if (for_forces && c->g.P > 1 && c->fused_push && c->plane) {
+        void* peers[HYMD_MAX_PEERS];
+        HYMD_CHECK(push_work_begin(c, c->grad2 ? 2 : 3, peers, s));
+        HYMD_CHECK(xline_pme(c, c->phiq_hat, nullptr, want_psi ? c->psi_hat : nullptr,
+                             want_psi ? c->phiqf_hat : nullptr, s, peers));
+        return push_work_end(c, s);
+    }
     return xline_pme(c, c->phiq_hat, (c->g.P == 1) ? c->wA : c->e_hat,
                      want_psi ? c->psi_hat : nullptr, want_psi ? c->phiqf_hat : nullptr, s);
 }
@@ -431,7 +451,7 @@ int hymd_field_cycle(hymd_ctx* c, int compute_potential, void* stream) {
     }
     {
         PhaseScope ps(c, HYMD_PHASE_KSPACE, s);
-        HYMD_CHECK(run_kspace(c, cp, cp, s));
+        HYMD_CHECK(run_kspace(c, cp, cp, s, true));
     }
     {
         PhaseScope ps(c, HYMD_PHASE_FFT_INV, s);
@@ -553,7 +573,7 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
     }
     {
         PhaseScope ps(c, HYMD_PHASE_PME_KSPACE, s);
-        HYMD_CHECK(run_kspace_pme(c, want_psi != 0, s));
+        HYMD_CHECK(run_kspace_pme(c, want_psi != 0, s, true));
     }
     {
         PhaseScope ps(c, HYMD_PHASE_PME_FFT, s);
@@ -566,7 +586,8 @@ int hymd_pme_cycle(hymd_ctx* c, void* d_elec_force, int want_psi, void* stream) 
     }
     c->have_psi = want_psi != 0;
     HYMD_CHECK(comm_check_status(c));
-    if ((c->np > 0 || c->g.P > 1) && d_elec_force) {
+    // (several slabs: a rank without particles of its own still reads out its guests -- collective)
+    if (d_elec_force || (c->g.P > 1 && c->np == 0)) {
         PhaseScope ps(c, HYMD_PHASE_PME_READOUT, s);
         HYMD_CHECK(readout_pme(c, d_elec_force, s));
     }

@@ -217,6 +217,8 @@ struct hymd_ctx {
     size_t halo_bytes;
     hymd::Comm* comm;       // NCCL communicator (world_size > 1)
     bool p2p;               // exchanges store into peer memory over NVLink (CUDA IPC) instead of NCCL send/recv
+    bool fused_push;        // the transposes are stores issued by the plane r2c / x-line kernels themselves
+    bool xpushed;           // the x-line kernel has already stored its output into the peers' work buffers
     unsigned peer_busy;     // PEER_* buffers whose local consumers were enqueued after the last barrier:
                             // a peer may not overwrite them before another barrier (same call sequence
                             // on every rank, so the flags agree)
@@ -300,13 +302,18 @@ int halo_fetch(hymd_ctx* c, void* ghost_meshes, int F, cudaStream_t s);
 // planefft.cu
 bool plane_supported(const hymd_ctx* c);
 int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int nplanes, void* k_out,
-                  long long k_fs, cudaStream_t s);
+                  long long k_fs, cudaStream_t s, void* const* push_peers = nullptr);
 int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int nplanes, void* real_out,
                   bool ghost, bool derive, cudaStream_t s);
 // xline.cu
 bool xline_supported(const hymd_ctx* c);
-int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s);
-int xline_pme(hymd_ctx* c, const void* in, void* fout, void* psi_out, void* rhof_out, cudaStream_t s);
+int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s,
+                 void* const* push_peers = nullptr);
+int xline_pme(hymd_ctx* c, const void* in, void* fout, void* psi_out, void* rhof_out, cudaStream_t s,
+              void* const* push_peers = nullptr);
+// slabfft.cu: peer addresses of the work buffer + acquire, for the fused inverse transpose; and its closing barrier
+int push_work_begin(hymd_ctx* c, int F, void** peers, cudaStream_t s);
+int push_work_end(hymd_ctx* c, cudaStream_t s);
 // migrate.cu
 int migrate_plan(hymd_ctx* c, const void* d_pos, int64_t n, int64_t* n_new, cudaStream_t s);
 int migrate_apply(hymd_ctx* c, const void* d_in, void* d_out, int row_bytes, cudaStream_t s);

@@ -160,6 +160,12 @@ struct PlaneParams {
     int scr_hint;                   // scratch plane accesses carry L2 eviction priorities
     int scr_alt;                    // experiment: alternate between two scratch planes per CTA (L2 footprint x2)
     int row_tma;                    // staged row phase (Cfg::TMA_ROWS): bit 0 = inputs, bit 1 = outputs via bulk copies
+    // forward, several slabs: the last butterfly stage stores every spectrum row straight into the k
+    // buffer of the rank that owns its k_y range (the forward transpose of the slab FFT, fused):
+    // row ky of local plane x, field f  ->  peer[ky >> nyl_shift] + (x0 + x) pk_xs + f pk_fs + (ky & (nyl-1)) Nzcp
+    int push, nyl_shift, x0;
+    long long pk_xs, pk_fs;
+    void* peer[HYMD_MAX_PEERS];
 };
 
 // Work decomposition inside the 512-thread CTA.
@@ -668,9 +674,20 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_r2c_kernel(
                 for (int n2 = 0; n2 < R2y; ++n2) v[n2] = cur[LA::at2(k1, n2, c)];
                 dft_reg<real, R2y, -1>(v);
                 if (c0 + c < NZCP) {
+                    if (p.push) {
+                        const long long off = (long long)(p.x0 + x) * p.pk_xs + f * p.pk_fs + c0 + c;
+                        const int nyl_mask = (1 << p.nyl_shift) - 1;
 #pragma unroll
-                    for (int k2 = 0; k2 < R2y; ++k2)
-                        st_stream(dstp + (long long)(k1 + R1y * k2) * NZCP + c0 + c, v[k2]);
+                        for (int k2 = 0; k2 < R2y; ++k2) {
+                            const int ky = k1 + R1y * k2;
+                            Cx<real>* dq = reinterpret_cast<Cx<real>*>(p.peer[ky >> p.nyl_shift]);
+                            st_stream(dq + off + (long long)(ky & nyl_mask) * NZCP, v[k2]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k2 = 0; k2 < R2y; ++k2)
+                            st_stream(dstp + (long long)(k1 + R1y * k2) * NZCP + c0 + c, v[k2]);
+                    }
                 }
             }
             if (NTILE == 1) group_sync(g + 1, GT);
@@ -791,9 +808,18 @@ static int dispatch_plane(hymd_ctx* c, const void* in, void* out, const PlanePar
 
 // real [f][plane][Ny][Nz] (strides r_*) -> spectra [f][plane][Ny][Nzcp] (strides k_*)
 int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int nplanes, void* k_out,
-                  long long k_fs, cudaStream_t s) {
+                  long long k_fs, cudaStream_t s, void* const* push_peers) {
     const Geometry& g = c->g;
     PlaneParams p;
+    memset(&p, 0, sizeof(p));
+    if (push_peers) {      // k_out is ignored: rows go to the peers' k buffers (k layout of F fields)
+        int sh = 0;
+        while ((1 << sh) < g.nyl) ++sh;
+        if ((1 << sh) != g.nyl) { set_error("fused forward transpose needs a power-of-two Ny / P"); return HYMD_ERR_INVALID; }
+        const KLayout l = klayout(c, F);
+        p.push = 1; p.nyl_shift = sh; p.x0 = g.x0; p.pk_xs = l.xs; p.pk_fs = l.fs;
+        for (int q = 0; q < g.P; ++q) p.peer[q] = push_peers[q];
+    }
     p.nunits = F * nplanes; p.nplanes = nplanes;
     p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
     p.r_fs = r_fs; p.r_xs = (long long)g.Ny * g.Nz; p.r_ys = g.Nz;
@@ -812,6 +838,7 @@ int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int npla
                   bool ghost, bool derive, cudaStream_t s) {
     const Geometry& g = c->g;
     PlaneParams p;
+    memset(&p, 0, sizeof(p));
     if (derive && F % 3 != 0) { set_error("plane_inverse: derive needs 3 outputs per row"); return HYMD_ERR_INVALID; }
     p.nunits = (derive ? F / 3 : F) * nplanes; p.nplanes = nplanes;
     p.derive = derive ? 1 : 0;

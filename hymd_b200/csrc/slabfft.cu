@@ -319,6 +319,25 @@ static int transpose_inverse(hymd_ctx* c, int F, void* k_in, cudaStream_t s) {
     return HYMD_OK;
 }
 
+// Fused inverse transpose (xline.cu stores into the peers' work buffers): peer addresses + acquire before
+// the launch, barrier after it.
+int push_work_begin(hymd_ctx* c, int F, void** peers, cudaStream_t s) {
+    HYMD_CHECK(ensure_work(c, F));
+    PeerPtrs A;
+    HYMD_CHECK(peer_table(c, c->wA, &A, s));
+    HYMD_CHECK(peer_acquire(c, PEER_WORK, s));
+    for (int q = 0; q < HYMD_MAX_PEERS; ++q) peers[q] = A.p[q];
+    return HYMD_OK;
+}
+
+int push_work_end(hymd_ctx* c, cudaStream_t s) {
+    PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+    HYMD_CHECK(comm_barrier(c, s));
+    c->peer_busy |= PEER_WORK;
+    c->xpushed = true;
+    return HYMD_OK;
+}
+
 // 2-D (y,z) transforms of the local planes: the one-pass plane kernels (planefft.cu) when the
 // plane size is supported, batched cuFFT 2-D plans otherwise.
 static int yz_forward(hymd_ctx* c, void* real_in, int F, void* k_out, long long k_fs, cudaStream_t s) {
@@ -366,6 +385,18 @@ int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t 
     const Geometry& g = c->g;
     if (g.P == 1) return yz_forward(c, real_in, F, k_out, klayout(c, F).fs, s);
     HYMD_CHECK(ensure_work(c, F));
+    if (c->fused_push && c->plane) {
+        // the forward transpose is the plane kernel's own epilogue: every spectrum row is stored into the
+        // k buffer of the rank owning its k_y range while the next rows are still being transformed
+        PeerPtrs K;
+        HYMD_CHECK(peer_table(c, k_out, &K, s));
+        HYMD_CHECK(peer_acquire(c, PEER_K, s));
+        HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, K.p));
+        PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+        HYMD_CHECK(comm_barrier(c, s));
+        c->peer_busy |= PEER_K;
+        return HYMD_OK;
+    }
     HYMD_CHECK(yz_forward(c, real_in, F, c->wA, (long long)(g.nxl + 1) * g.Ny * g.Nzcp, s));
     return transpose_forward(c, F, k_out, s);
 }
@@ -390,7 +421,8 @@ int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost
     const int Fin = derive ? F / 3 * 2 : F;
     if (g.P > 1) {
         HYMD_CHECK(ensure_work(c, Fin));
-        HYMD_CHECK(transpose_inverse(c, Fin, k_in, s));
+        if (c->xpushed) c->xpushed = false;     // the x-line kernel stored into the peers' work buffers itself
+        else HYMD_CHECK(transpose_inverse(c, Fin, k_in, s));
         return yz_inverse(c, c->wA, (g.nxl + 1) * plane, F, real_out, ghost, s, derive);
     }
     return yz_inverse(c, k_in, (ghost ? g.Nx + 1 : g.Nx) * plane, F, real_out, ghost, s, derive);

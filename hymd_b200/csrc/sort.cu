@@ -43,6 +43,24 @@ __device__ __forceinline__ UT pack_coord(int cell, double frac, int fb) {
     return ((UT)cell << fb) | f;
 }
 
+// Peer addresses of the guest buffers (per-step routing, below) and what the binning pass needs to send a
+// home particle that is away to the rank owning its cell.
+struct RoutePeers {
+    void* pos[HYMD_MAX_PEERS];
+    void* type[HYMD_MAX_PEERS];
+    void* q[HYMD_MAX_PEERS];
+    void* ret[HYMD_MAX_PEERS];
+};
+struct RouteOut {
+    RoutePeers peers;
+    uint32_t* send_count;      // [P] guests sent to each rank this step
+    int32_t* sent_idx;         // [P*G] home index of guest k sent to rank d at d*G + k
+    unsigned int* status;      // mapped host words: bit 1 = capacity exceeded
+    const void* q;             // caller-order charges or NULL
+    long long G;
+    int rank;
+};
+
 // Consecutive lanes with the same key form a run (in REUSE mode the lanes walk the previous bin
 // order, so a warp usually holds two or three runs): one counter atomic per run instead of one per
 // lane.  Returns this lane's run head, its rank inside the run and the run length.
@@ -76,7 +94,7 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
                                                     uint32_t* __restrict__ cnt,
                                                     DeviceScalars* __restrict__ sc,
                                                     const RouteTotals* __restrict__ rt,
-                                                    uint32_t* __restrict__ keys, uint32_t away_bin) {
+                                                    uint32_t* __restrict__ keys, uint32_t away_bin, RouteOut ro) {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     unsigned int r1 = 0, bad = 0;
     uint32_t key = 0xffffffffu;                        // lanes past the end: a run of their own
@@ -114,7 +132,24 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
         stage[j] = r;
         key = (uint32_t)(((long long)lx * p.Ny + cy) * p.nbz + zbin_of(cz, p.Nz));
         if (ROUTED) {
-            if (bad) key = away_bin;
+            if (bad) {
+                // away: goes into rank d's inbox section for this rank (stores into d's HBM over NVLink);
+                // here it only occupies the extra bin so that the next REUSE pass finds it again
+                key = away_bin;
+                const int d = cx / p.nxl;
+                const uint32_t k = atomicAdd(&ro.send_count[d], 1u);
+                if (k >= (uint32_t)ro.G) {         // never silently: raised to the host through mapped memory
+                    if (ro.status) { atomicOr(ro.status, 2u); atomicAdd(ro.status + 1, 1u); }
+                } else {
+                    const long long row = (long long)ro.rank * ro.G + k;
+                    real* dp = reinterpret_cast<real*>(ro.peers.pos[d]) + 3 * row;
+                    dp[0] = pos[3 * idx + 0]; dp[1] = pos[3 * idx + 1]; dp[2] = pos[3 * idx + 2];
+                    reinterpret_cast<int32_t*>(ro.peers.type[d])[row] = (int32_t)type;
+                    if (ro.q != nullptr)
+                        reinterpret_cast<real*>(ro.peers.q[d])[row] = reinterpret_cast<const real*>(ro.q)[idx];
+                    ro.sent_idx[(long long)d * ro.G + k] = (int32_t)idx;
+                }
+            }
             keys[j] = key;
         }
     }
@@ -220,13 +255,6 @@ size_t scan_temp_bytes(long long n) {
 //                scatters the returned rows to force[sent_idx].
 // No host synchronisation, no NCCL call; capacities are fixed (G guests per rank pair), an overflow
 // raises status bit 1 (comm_check_status) instead of dropping particles silently.
-struct RoutePeers {
-    void* pos[HYMD_MAX_PEERS];
-    void* type[HYMD_MAX_PEERS];
-    void* q[HYMD_MAX_PEERS];
-    void* ret[HYMD_MAX_PEERS];
-};
-
 struct RouteState {
     long long G = 0;                 // guest rows per (source, destination) pair
     void* in_pos = nullptr;          // [P*G][3] real   inbox: section r written by rank r
@@ -236,8 +264,6 @@ struct RouteState {
     RoutePeers peers;
     uint32_t* send_count = nullptr;  // [HYMD_MAX_PEERS]
     int32_t* sent_idx = nullptr;     // [P*G]: home index of guest k sent to rank q at q*G + k
-    int32_t* types_home = nullptr;   // caller-order types (REUSE calls do not pass them)
-    long long types_cap = 0;
     void* gstage = nullptr;          // [P*G] staged guest records
     uint32_t* gkeys = nullptr;       // [P*G]
     uint32_t* keys = nullptr;        // [cap + P*G] bins of the staged home records
@@ -245,37 +271,6 @@ struct RouteState {
     RouteTotals* totals = nullptr;   // {n_work, n_total} of the last sort
     bool sent_charges = false;
 };
-
-__device__ __forceinline__ int owner_of(double x, double sx, int Nx, int nxl) {
-    const double f = floor(x * sx);
-    long long c = (long long)f % Nx;
-    if (c < 0) c += Nx;
-    if (x * sx - f >= 1.0) c = (c + 1 == Nx) ? 0 : c + 1;     // same rounding rule as split_coord
-    return (int)(c / nxl);
-}
-
-template <typename real>
-__global__ void __launch_bounds__(256) route_scan_kernel(
-    const real* __restrict__ pos, const int32_t* __restrict__ types, const real* __restrict__ q, long long n,
-    double sx, int Nx, int nxl, int rank, long long G, RoutePeers peers, uint32_t* __restrict__ send_count,
-    int32_t* __restrict__ sent_idx, unsigned int* status) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const real x = pos[3 * i];
-    const int d = owner_of((double)x, sx, Nx, nxl);
-    if (d == rank) return;
-    const uint32_t k = atomicAdd(&send_count[d], 1u);
-    if (k >= (uint32_t)G) {                    // never silently: raised to the host through mapped memory
-        if (status) { atomicOr(status, 2u); atomicAdd(status + 1, 1u); }
-        return;
-    }
-    const long long row = (long long)rank * G + k;
-    real* dp = reinterpret_cast<real*>(peers.pos[d]) + 3 * row;
-    dp[0] = x; dp[1] = pos[3 * i + 1]; dp[2] = pos[3 * i + 2];
-    reinterpret_cast<int32_t*>(peers.type[d])[row] = types[i];
-    if (q != nullptr) reinterpret_cast<real*>(peers.q[d])[row] = q[i];
-    sent_idx[(long long)d * G + k] = (int32_t)i;
-}
 
 // charges of the guests already sent (hymd_set_charges after a sort without charges)
 template <typename real>
@@ -378,7 +373,7 @@ static int route_alloc(void** p, size_t bytes) {
 void route_destroy(hymd_ctx* c) {
     RouteState* r = c->route;
     if (!r) return;
-    void* bufs[] = {r->in_pos, r->in_type, r->in_q, r->ret, r->send_count, r->sent_idx, r->types_home,
+    void* bufs[] = {r->in_pos, r->in_type, r->in_q, r->ret, r->send_count, r->sent_idx,
                     r->gstage, r->gkeys, r->keys, r->totals};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -524,26 +519,16 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
             r->keys_cap = c->cap + rows;
             HYMD_CHECK(route_alloc((void**)&r->keys, (size_t)r->keys_cap * 4));
         }
-        if (!reuse) {     // caller-order types: REUSE calls do not pass them again
-            if (r->types_cap < n) {
-                if (r->types_home) { cudaStreamSynchronize(s); cudaFree(r->types_home); r->types_home = nullptr; }
-                r->types_cap = n + n / 8 + 1024;
-                HYMD_CHECK(route_alloc((void**)&r->types_home, (size_t)r->types_cap * 4));
-            }
-            if (n > 0) HYMD_CUDA(cudaMemcpyAsync(r->types_home, d_types, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
-        }
-        // ---- guests out: stores into the owners' inboxes, counts ride on the barrier ----------------
+        // guests go out from inside the binning pass (count_kernel): the owners' inboxes must be free
         if (c->peer_busy & PEER_INBOX) HYMD_CHECK(comm_barrier(c, s));
         HYMD_CUDA(cudaMemsetAsync(r->send_count, 0, HYMD_MAX_PEERS * 4, s));
-        if (n > 0) {
-            route_scan_kernel<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
-                (const real*)d_pos, r->types_home, (const real*)d_q, n, p.sx, g.Nx, g.nxl, g.rank, r->G, r->peers,
-                r->send_count, r->sent_idx, comm_status_device(c));
-            HYMD_LAUNCH_CHECK(c);
-        }
-        HYMD_CHECK(comm_barrier_payload(c, r->send_count, s));
-        c->peer_busy |= PEER_INBOX;
         r->sent_charges = d_q != nullptr;
+    }
+    RouteOut ro;
+    memset(&ro, 0, sizeof(ro));
+    if (routed) {
+        ro.peers = r->peers; ro.send_count = r->send_count; ro.sent_idx = r->sent_idx;
+        ro.status = comm_status_device(c); ro.q = d_q; ro.G = r->G; ro.rank = g.rank;
     }
     uint32_t* cur = c->cell_start + 1;
     HYMD_CUDA(cudaMemsetAsync(c->cell_start, 0, (size_t)(ncell + 3) * sizeof(uint32_t), s));
@@ -557,21 +542,24 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
         if (routed) {
             if (reuse)
                 count_kernel<real, RecT, UT, IDX_BITS, true, true><<<blocks, 256, 0, s>>>(
-                    (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, r->totals, r->keys, (uint32_t)ncell);
+                    (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, r->totals, r->keys, (uint32_t)ncell, ro);
             else
                 count_kernel<real, RecT, UT, IDX_BITS, false, true><<<blocks, 256, 0, s>>>(
-                    (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, r->totals, r->keys, (uint32_t)ncell);
+                    (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, r->totals, r->keys, (uint32_t)ncell, ro);
         } else if (reuse) {
             count_kernel<real, RecT, UT, IDX_BITS, true, false><<<blocks, 256, 0, s>>>(
-                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, nullptr, nullptr, 0u);
+                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, nullptr, nullptr, 0u, ro);
         } else {
             count_kernel<real, RecT, UT, IDX_BITS, false, false><<<blocks, 256, 0, s>>>(
-                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, nullptr, nullptr, 0u);
+                (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, nullptr, nullptr, 0u, ro);
         }
         HYMD_LAUNCH_CHECK(c);
     }
     const unsigned gblocks = (unsigned)((rows + 255) / 256);
     if (routed) {
+        // the per-destination counts ride on the barrier; after it every inbox section is complete
+        HYMD_CHECK(comm_barrier_payload(c, r->send_count, s));
+        c->peer_busy |= PEER_INBOX;
         guest_count_kernel<real, RecT, UT, IDX_BITS><<<gblocks, 256, 0, s>>>(
             (const real*)r->in_pos, r->in_type, comm_payload(c), g.P, g.rank, r->G, n, p, (RecT*)r->gstage, r->gkeys,
             cur, c->scalars, comm_status_device(c));

@@ -37,6 +37,12 @@ struct XParams {
     long long xs_v, fs_v, xs_pf, fs_pf;   // optional k-space outputs (not x-inverted)
     int pme;
     int two;                         // 2 outputs per row (-i k_x V, -i V): the plane c2r applies k_y, k_z
+    // several slabs: the force spectra go straight into the work buffer of the rank owning plane x (the
+    // inverse transpose of the slab FFT, fused): element (f, x, col) -> peer[x / nxl] + (f (nxl+1) + x % nxl)
+    // plane + ky0 Nzcp + col, the layout the plane c2r reads
+    int push, nxl_shift;
+    long long push_plane, push_fs, push_y0;
+    void* peer[HYMD_MAX_PEERS];
 };
 
 // shared-memory position of element (pos, c): rows of CH columns, one extra row of padding per
@@ -282,6 +288,25 @@ __global__ void __launch_bounds__(NTH) xline_kernel(
             if (!(full || col0 + c < p.ncols)) continue;
             const real ky = s_hk[0][c][1], kz = s_hk[0][c][2];
             Cx<real>* o = f0 + (long long)n2 * p.xs_f + col0 + c;
+            if (p.push) {
+                const int fo = (p.two ? 2 : 3) * u + (isK ? 0 : 1);
+                const int nxl_mask = (1 << p.nxl_shift) - 1;
+                const long long off = (long long)fo * p.push_fs + p.push_y0 + col0 + c;
+#pragma unroll
+                for (int n1 = 0; n1 < R1; ++n1) {
+                    const int x = n1 * R2 + n2;
+                    Cx<real>* dq = reinterpret_cast<Cx<real>*>(p.peer[x >> p.nxl_shift]) + off +
+                                   (long long)(x & nxl_mask) * p.push_plane;
+                    const Cx<real> w = {v[n1].y, -v[n1].x};
+                    if (isK || p.two) {
+                        store_cx(dq, w);
+                    } else {
+                        store_cx(dq, Cx<real>{ky * w.x, ky * w.y});
+                        store_cx(dq + p.push_fs, Cx<real>{kz * w.x, kz * w.y});
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int n1 = 0; n1 < R1; ++n1) {
                 Cx<real>* ox = o + (long long)(n1 * R2) * p.xs_f;
@@ -319,9 +344,10 @@ bool xline_supported(const hymd_ctx* c) {
 
 template <typename real, int NX, int CH, int NTH = 256>
 static int launch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vout, void* pfout,
-                    int T, int U, cudaStream_t s) {
+                    int T, int U, cudaStream_t s, void* const* push_peers) {
     const Geometry& g = c->g;
     XParams p;
+    memset(&p, 0, sizeof(p));
     p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nyl = g.nyl; p.y0 = g.y0; p.Nzc = g.Nzc; p.Nzcp = g.Nzcp;
     p.T = T; p.U = U; p.pme = pme ? 1 : 0; p.two = c->grad2 ? 1 : 0;
     p.ncols = (long long)g.nyl * g.Nzcp;
@@ -335,6 +361,16 @@ static int launch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vou
     } else {
         const KLayout lf = klayout(c, (c->grad2 ? 2 : 3) * U);
         p.xs_f = lf.xs; p.fs_f = lf.fs;
+        if (push_peers) {
+            int sh = 0;
+            while ((1 << sh) < g.nxl) ++sh;
+            if ((1 << sh) != g.nxl) { set_error("fused inverse transpose needs a power-of-two Nx / P"); return HYMD_ERR_INVALID; }
+            p.push = 1; p.nxl_shift = sh;
+            p.push_plane = (long long)g.Ny * g.Nzcp;
+            p.push_fs = (long long)(g.nxl + 1) * p.push_plane;
+            p.push_y0 = (long long)g.y0 * g.Nzcp;
+            for (int q = 0; q < g.P; ++q) p.peer[q] = push_peers[q];
+        }
     }
     const size_t smem = sizeof(Cx<real>) * ((size_t)NX + (size_t)(2 + T) * field_elems<NX, CH>());
     if (smem > 227 * 1024) {
@@ -358,19 +394,19 @@ static int launch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vou
 
 template <typename real>
 static int dispatch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vout, void* pfout,
-                      int T, int U, cudaStream_t s) {
+                      int T, int U, cudaStream_t s, void* const* push_peers) {
     // columns per CTA: 8 complex = 64 B (fp32) / 128 B (fp64) contiguous per x row
     switch (c->g.Nx) {
-        case 16: return launch_x<real, 16, 8>(c, pme, in, fout, vout, pfout, T, U, s);
-        case 32: return launch_x<real, 32, 8>(c, pme, in, fout, vout, pfout, T, U, s);
-        case 64: return launch_x<real, 64, 8>(c, pme, in, fout, vout, pfout, T, U, s);
-        case 128: return launch_x<real, 128, 8>(c, pme, in, fout, vout, pfout, T, U, s);
-        case 256: return launch_x<real, 256, 8>(c, pme, in, fout, vout, pfout, T, U, s);
+        case 16: return launch_x<real, 16, 8>(c, pme, in, fout, vout, pfout, T, U, s, push_peers);
+        case 32: return launch_x<real, 32, 8>(c, pme, in, fout, vout, pfout, T, U, s, push_peers);
+        case 64: return launch_x<real, 64, 8>(c, pme, in, fout, vout, pfout, T, U, s, push_peers);
+        case 128: return launch_x<real, 128, 8>(c, pme, in, fout, vout, pfout, T, U, s, push_peers);
+        case 256: return launch_x<real, 256, 8>(c, pme, in, fout, vout, pfout, T, U, s, push_peers);
         default: break;
     }
     if (sizeof(real) == 4) {
-        if (c->g.Nx == 512) return launch_x<float, 512, 4>(c, pme, in, fout, vout, pfout, T, U, s);
-        if (c->g.Nx == 1024) return launch_x<float, 1024, 2>(c, pme, in, fout, vout, pfout, T, U, s);
+        if (c->g.Nx == 512) return launch_x<float, 512, 4>(c, pme, in, fout, vout, pfout, T, U, s, push_peers);
+        if (c->g.Nx == 1024) return launch_x<float, 1024, 2>(c, pme, in, fout, vout, pfout, T, U, s, push_peers);
     }
     set_error("xline: unsupported Nx = %d", c->g.Nx);
     return HYMD_ERR_INVALID;
@@ -378,14 +414,18 @@ static int dispatch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* v
 
 // in: spectra after the 2-D (y,z) transforms, k layout of T fields.  fout: 3U x-inverted force
 // spectra (P == 1: work layout of the ghost c2r; P > 1: k layout of 3U fields).
-int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s) {
-    return c->f64 ? dispatch_x<double>(c, false, in, fout, vout, pfout, c->T, c->U, s)
-                  : dispatch_x<float>(c, false, in, fout, vout, pfout, c->T, c->U, s);
+// push_peers != NULL (several slabs): fout is ignored, the force spectra are stored into the peers' work
+// buffers (the fused inverse transpose; the caller brackets the launch with the acquire / barrier).
+int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s,
+                 void* const* push_peers) {
+    return c->f64 ? dispatch_x<double>(c, false, in, fout, vout, pfout, c->T, c->U, s, push_peers)
+                  : dispatch_x<float>(c, false, in, fout, vout, pfout, c->T, c->U, s, push_peers);
 }
 
-int xline_pme(hymd_ctx* c, const void* in, void* fout, void* psi_out, void* rhof_out, cudaStream_t s) {
-    return c->f64 ? dispatch_x<double>(c, true, in, fout, psi_out, rhof_out, 1, 1, s)
-                  : dispatch_x<float>(c, true, in, fout, psi_out, rhof_out, 1, 1, s);
+int xline_pme(hymd_ctx* c, const void* in, void* fout, void* psi_out, void* rhof_out, cudaStream_t s,
+              void* const* push_peers) {
+    return c->f64 ? dispatch_x<double>(c, true, in, fout, psi_out, rhof_out, 1, 1, s, push_peers)
+                  : dispatch_x<float>(c, true, in, fout, psi_out, rhof_out, 1, 1, s, push_peers);
 }
 
 }  // namespace hymd

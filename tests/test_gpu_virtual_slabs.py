@@ -171,9 +171,3 @@ def test_guest_capacity_overflow_fails_loudly(monkeypatch):
     with pytest.raises(HymdError, match="GUEST_CAPACITY"):
         _run_and_compare(2, [32, 32, 32], 20000, np.float64, False, "scattered",
                          env={"HYMD_B200_GUEST_CAPACITY": "64"}, monkeypatch=monkeypatch)
-
-
-def test_flag_barriers_between_virtual_slabs(monkeypatch):
-    """The peer-memory flag barrier (the production barrier over NVLink) between two streams of one GPU."""
-    _run_and_compare(2, [32, 32, 32], 20000, np.float32, True, "drifted", steps=2,
-                     env={"HYMD_B200_LOCAL_FLAGS": "1"}, monkeypatch=monkeypatch)

@@ -37,7 +37,21 @@ from hymd_b200.md import FieldOnlyMD  # noqa: E402
 from hymd_b200.synthetic import make_system  # noqa: E402
 
 
-def run_gpu(sysm, dtype, steps, every, dt):
+def run_gpu_slabs(sysm, dtype, steps, every, dt, P):
+    """The same trajectory on P slabs (virtual ranks = threads of this process on one GPU): every rank
+    owns an arbitrary 1/P share of the particles (index modulo P), nothing ever re-homes them, so every
+    step routes the particles outside their owner's slab to the slab owner and their forces back."""
+    from hymd_b200._world import VirtualRanks
+    out = [None] * P
+
+    def worker(rank):
+        out[rank] = run_gpu(sysm, dtype, steps, every, dt, share=(rank, P))
+
+    VirtualRanks(P).run(worker)
+    return out[0]
+
+
+def run_gpu(sysm, dtype, steps, every, dt, share=None):
     import torch
     from hymd_b200 import field as F
     from hymd_b200.hamiltonian import get_hamiltonian
@@ -49,9 +63,10 @@ def run_gpu(sysm, dtype, steps, every, dt):
     phi, phi_fourier, force_mesh, v_ext_fourier, v_ext, phi_transfer, phi_laplacian = fl
     layouts = [pm.decompose(None) for _ in range(cfg.n_types)]
     dev = pm.device
-    pos = torch.as_tensor(sysm.positions.astype(dtype), device=dev)
-    vel = torch.as_tensor(sysm.velocities.astype(dtype), device=dev)
-    typ = torch.as_tensor(sysm.types.astype(np.int32), device=dev)
+    sel = slice(None) if share is None else slice(share[0], None, share[1])
+    pos = torch.as_tensor(np.ascontiguousarray(sysm.positions[sel].astype(dtype)), device=dev)
+    vel = torch.as_tensor(np.ascontiguousarray(sysm.velocities[sel].astype(dtype)), device=dev)
+    typ = torch.as_tensor(np.ascontiguousarray(sysm.types[sel].astype(np.int32)), device=dev)
     n = pos.shape[0]
     force = torch.zeros((n, 3), dtype=tdt, device=dev)
 

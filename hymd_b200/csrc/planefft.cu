@@ -696,6 +696,416 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_r2c_kernel(
     }
 }
 
+// =====================================================================================================
+// Tensor-memory variant (fp32, 256 x 256 planes: the benchmark mesh): the y <-> z exchange between the two
+// phases goes through TMEM instead of an L2-resident scratch plane.
+//
+// A plane of half spectra is 256 rows x 129 columns of complex fp32.  Columns kz = 0 .. 127 are
+// 256 * 128 * 8 B = 256 KB -- exactly the tensor memory of one SM (128 lanes x 512 columns x 32 bit), which
+// nothing else in this library uses; the Nyquist column kz = 128 (2 KB) lives in shared memory.  tcgen05.st /
+// tcgen05.ld (shape 32x32b) let thread t of warp w touch TMEM lane 32 (w % 4) + t only, so the two phases
+// are laid out such that the thread that WRITES element (y, kz) in one phase and the thread that READS it in
+// the other sit in the same lane of warps with the same w % 4:
+//
+//      y = y7 .. y0,  kz = kz6 .. kz0            lane   = (y1, kz3 kz2 kz1 kz0)        (thread lane)
+//                                                quarter = (y3, y2)                     (warp % 4)
+//                                                column = 2 * (16 * (y7 y6 y5 y4) + (kz6 kz5 kz4 y0)) + {re, im}
+//
+//   column phase (FFT along y, 32 columns at a time over the whole CTA): the thread of the last butterfly
+//       stage owns (column c = kz4..kz0, n2 = y3..y0) and all sixteen n1 = y7..y4: sixteen 2-column
+//       accesses;
+//   row phase (FFT along z on row pairs): the thread owns k1 = kz3..kz0 and two rows y0 = 0, 1 of one row
+//       pair, for k2 = kz6 kz5 kz4 = 0..7: ONE 32-column access; the mirrored half k > 128 comes from the
+//       partner lane 16 - k1 of the same warp by shuffles.
+//
+// No scratch plane, no L2 round trip (it was two thirds of the kernel's global load/store instructions
+// and half of its L2 traffic; ncu: lg_throttle was the top stall), and the global accesses of the column
+// phase become 256-byte rows.  Everything else -- butterflies, register twiddles, the derive mode, the
+// ghost-padded output, the fused forward transpose -- is the code of the kernels above.
+// =====================================================================================================
+constexpr int TM_N = 256, TM_CS = 32;                      // plane edge, columns per super-chunk
+using TmLA = LayA<TM_N, TM_CS>;
+using TmLB = LayB<TM_N, 2>;
+constexpr int TM_TILE = TmLA::ELEMS > 16 * TmLB::ELEMS ? TmLA::ELEMS : 16 * TmLB::ELEMS;
+constexpr size_t TM_SMEM = sizeof(Cx<float>) * (size_t)(3 * TM_N + TM_TILE);
+
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(a)),
+                 "r"(__float_as_uint(b)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
+    uint32_t x, y;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(taddr) : "memory");
+    a = __uint_as_float(x); b = __uint_as_float(y);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
+        "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]), "f"(r[16]),
+        "f"(r[17]), "f"(r[18]), "f"(r[19]), "f"(r[20]), "f"(r[21]), "f"(r[22]), "f"(r[23]), "f"(r[24]), "f"(r[25]),
+        "f"(r[26]), "f"(r[27]), "f"(r[28]), "f"(r[29]), "f"(r[30]), "f"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+          "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]),
+          "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]),
+          "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// CTA barrier that orders tensor-memory accesses before / after it
+__device__ __forceinline__ void tmem_sync() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tmem_alloc_all(uint32_t* slot, int warp) {
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tmem_sync();
+    return *reinterpret_cast<volatile uint32_t*>(slot);
+}
+__device__ __forceinline__ void tmem_free_all(uint32_t base, int warp) {
+    tmem_sync();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+
+// thread <-> task maps shared by both kernels (512 threads, warp w = 0..15, lane l)
+struct TmMap {
+    int c, n2, combo_lo;        // column-phase TMEM side: column within the super-chunk, y % 16, (kz4, y0)
+    int k1, y1, q, n1lo;        // row-phase: kz % 16, y1, (y3 y2), (y5 y4)
+    uint32_t lane_base;         // TMEM lane field of this warp
+    __device__ __forceinline__ TmMap(int w, int l) {
+        c = ((w >> 2) & 1) * 16 + (l & 15);
+        n2 = ((w & 3) << 2) | ((l >> 4) << 1) | (w >> 3);
+        combo_lo = ((w >> 2) & 1) * 2 + (w >> 3);
+        k1 = l & 15; y1 = l >> 4; q = w & 3; n1lo = w >> 2;
+        lane_base = (uint32_t)(32 * (w & 3)) << 16;
+    }
+};
+
+__global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
+    const Cx<float>* __restrict__ in, float* __restrict__ out, const Cx<float>* __restrict__ twy_g,
+    const Cx<float>* __restrict__ twz_g, PlaneParams p) {
+    using real = float;
+    constexpr int NY = TM_N, NZ = TM_N, NZC = NZ / 2 + 1, NZCP = NZC + 1, R = 16, CS = TM_CS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx<real>* twy = reinterpret_cast<Cx<real>*>(smem_raw);
+    Cx<real>* twz = twy + NY;
+    Cx<real>* nyq = twz + NZ;                               // column kz = 128 after the y transform
+    Cx<real>* tile = nyq + NY;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    for (int i = tid; i < NY; i += 512) { twy[i] = twy_g[i]; twz[i] = twz_g[i]; }
+    const uint32_t tbase = tmem_alloc_all(&tmem_slot, warp);
+    const TmMap m(warp, lane);
+    TwiddleRegs<real, R> twc, twr;
+    const int a_c = lane, a_k1 = warp;                      // first column stage: (column, k1)
+    twc.init(twy, a_k1, NY);
+    twr.init(twz, m.k1, NZ);
+    Cx<real>* wtile = tile + warp * TmLB::ELEMS;
+    const int ND = p.derive ? 3 : 1;
+    const real dky = (real)p.dky, dkz = (real)p.dkz;
+
+    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+      const int fu = unit / p.nplanes, x = unit % p.nplanes;
+      for (int d = 0; d < ND; ++d) {
+        const int fin = p.derive ? 2 * fu + (d > 0 ? 1 : 0) : fu;
+        const int f = p.derive ? 3 * fu + d : fu;
+        const int mode = p.derive ? d : 0;
+        const Cx<real>* src = in + fin * p.k_fs + x * p.k_xs;
+        auto scale_chunk = [&](Cx<real> (&v)[R], int k1, int col) {
+            if (mode == 1) {
+                const bool selfc = col == 0 || 2 * col == NZ;
+                const real fk1 = (real)k1;
+#pragma unroll
+                for (int k2 = 0; k2 < R; ++k2) {
+                    const real nn = fk1 + (real)(R * k2 - (2 * k2 >= R ? NY : 0));
+                    real sk = dky * nn;
+                    if (2 * k2 == R && k1 == 0 && selfc) sk = 0;
+                    v[k2].x *= sk; v[k2].y *= sk;
+                }
+            } else if (mode == 2) {
+                const real sk = (2 * col == NZ) ? (real)0 : dkz * (real)col;
+#pragma unroll
+                for (int k2 = 0; k2 < R; ++k2) { v[k2].x *= sk; v[k2].y *= sk; }
+            }
+        };
+        // ---------------- column phase: inverse FFT along y, super-chunks 0..3 = columns 0..127, 4 = Nyquist ----
+        Cx<real> nx[R];
+        auto load_chunk = [&](int sc, Cx<real> (&dst)[R]) {
+            const int col = sc * CS + a_c;
+            const bool valid = sc < 4 || (sc == 4 && a_c == 0);
+#pragma unroll
+            for (int k2 = 0; k2 < R; ++k2) {
+                const Cx<real>* e = src + (long long)(a_k1 + R * k2) * NZCP + col;
+                dst[k2] = valid ? (mode == 1 ? ld_l2(e) : ld_stream(e)) : Cx<real>{0, 0};
+            }
+        };
+        load_chunk(0, nx);
+        for (int sc = 0; sc < 5; ++sc) {
+            Cx<real> v[R];
+#pragma unroll
+            for (int k2 = 0; k2 < R; ++k2) v[k2] = nx[k2];
+            if (sc < 4) load_chunk(sc + 1, nx);
+            if (sc < 4 || a_c == 0) {
+                scale_chunk(v, a_k1, sc * CS + a_c);
+                dft_reg<real, R, +1>(v);
+                twc.template apply<true>(v);
+#pragma unroll
+                for (int n2 = 0; n2 < R; ++n2) tile[TmLA::at2(a_k1, n2, a_c)] = v[n2];
+            }
+            __syncthreads();
+            if (sc < 4 || m.c == 0) {
+                Cx<real> u[R];
+#pragma unroll
+                for (int k1 = 0; k1 < R; ++k1) u[k1] = tile[TmLA::at2(k1, m.n2, m.c)];
+                dft_reg<real, R, +1>(u);
+                if (sc < 4) {
+                    const uint32_t t0 = tbase + m.lane_base + 2u * (uint32_t)(sc * 4 + m.combo_lo);
+#pragma unroll
+                    for (int n1 = 0; n1 < R; ++n1) tmem_st2(t0 + 32u * n1, u[n1].x, u[n1].y);
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < R; ++n1) nyq[n1 * R + m.n2] = u[n1];
+                }
+            }
+            __syncthreads();
+        }
+        tmem_wait_st();
+        tmem_sync();
+        // ---------------- row phase: c2r along z on row pairs (A + iB) ----------------
+        real* obase = out + f * p.r_fs + x * p.r_xs;
+        real* obase2 = (p.xdup_plane >= 0 && x == 0) ? out + f * p.r_fs + p.xdup_plane * p.r_xs : nullptr;
+        const int partner = (lane & 16) | ((16 - m.k1) & 15);
+        for (int pass = 0; pass < 4; ++pass) {
+            const int n1 = pass * 4 + m.n1lo;
+            const int ybase = n1 * 16 + m.q * 4;            // rows ybase + 2 y1 (+ 1) belong to this lane
+            float r[32];
+            tmem_ld32(tbase + m.lane_base + 32u * (uint32_t)n1, r);
+            tmem_wait_ld();
+            Cx<real> v[R];
+            // k = k1 + 16 k2 < 128: A = (r[4k2], r[4k2+1]), B = (r[4k2+2], r[4k2+3])
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const real s = (k2 == 0 && m.k1 == 0) ? (real)0 : (real)1;
+                v[k2] = {r[4 * k2] - s * r[4 * k2 + 3], s * r[4 * k2 + 1] + r[4 * k2 + 2]};
+            }
+            // mirrored half k = k1 + 16 (8 + j): conj(A) + i conj(B) of element 256 - k, held by the partner lane
+            // (register 7 - j; lane k1 = 0 mirrors onto itself, register 8 - j, and j = 0 is the Nyquist column)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int own = (j == 0) ? 0 : 8 - j;       // k1 == 0 source register (j = 0 unused)
+                const real gx = (m.k1 == 0) ? r[4 * own] + r[4 * own + 3] : r[4 * (7 - j)] + r[4 * (7 - j) + 3];
+                const real gy = (m.k1 == 0) ? r[4 * own + 2] - r[4 * own + 1] : r[4 * (7 - j) + 2] - r[4 * (7 - j) + 1];
+                v[8 + j] = {shfl(gx, partner), shfl(gy, partner)};
+            }
+            if (m.k1 == 0) {                                // k = 128: imaginary parts dropped (c2r semantics)
+                const int y = ybase + 2 * m.y1;
+                v[8] = {nyq[y].x, nyq[y + 1].x};
+            }
+            dft_reg<real, R, +1>(v);
+            twr.template apply<true>(v);
+#pragma unroll
+            for (int n2 = 0; n2 < R; ++n2) wtile[TmLB::at2(m.k1, n2, m.y1)] = v[n2];
+            __syncwarp();
+            {
+                const int c2 = lane / R, n2 = lane % R;
+                Cx<real> u[R];
+#pragma unroll
+                for (int k1b = 0; k1b < R; ++k1b) u[k1b] = wtile[TmLB::at2(k1b, n2, c2)];
+                dft_reg<real, R, +1>(u);
+                const int y0 = ybase + 2 * c2;
+#pragma unroll
+                for (int dup = 0; dup < 2; ++dup) {
+                    real* ob = dup ? obase2 : obase;
+                    if (ob == nullptr) continue;
+                    real* oa = ob + (long long)y0 * p.r_ys + n2;
+#pragma unroll
+                    for (int n1b = 0; n1b < R; ++n1b) {
+                        __stcs(oa + n1b * R, u[n1b].x);
+                        __stcs(oa + p.r_ys + n1b * R, u[n1b].y);
+                    }
+                    if (p.ghost) {
+                        if (n2 == 0) { oa[NZ] = u[0].x; oa[p.r_ys + NZ] = u[0].y; }
+                        if (y0 == 0) {
+                            real* og = ob + (long long)NY * p.r_ys + n2;
+#pragma unroll
+                            for (int n1b = 0; n1b < R; ++n1b) __stcs(og + n1b * R, u[n1b].x);
+                            if (n2 == 0) og[NZ] = u[0].x;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        tmem_sync();                                        // TMEM and the tile are free for the next transform
+      }
+    }
+    tmem_free_all(tbase, warp);
+}
+
+__global__ void __launch_bounds__(512, 1) plane_r2c_tmem_kernel(
+    const float* __restrict__ in, Cx<float>* __restrict__ out, const Cx<float>* __restrict__ twy_g,
+    const Cx<float>* __restrict__ twz_g, PlaneParams p) {
+    using real = float;
+    constexpr int NY = TM_N, NZ = TM_N, NZC = NZ / 2 + 1, NZCP = NZC + 1, R = 16, CS = TM_CS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Cx<real>* twy = reinterpret_cast<Cx<real>*>(smem_raw);
+    Cx<real>* twz = twy + NY;
+    Cx<real>* nyq = twz + NZ;
+    Cx<real>* tile = nyq + NY;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    for (int i = tid; i < NY; i += 512) { twy[i] = twy_g[i]; twz[i] = twz_g[i]; }
+    const uint32_t tbase = tmem_alloc_all(&tmem_slot, warp);
+    const TmMap m(warp, lane);
+    TwiddleRegs<real, R> twc, twr;
+    twr.init(twz, lane % R, NZ);            // row phase, first stage: n2 = lane % 16
+    twc.init(twy, m.n2, NY);                // column phase, first stage: n2 = y % 16
+    Cx<real>* wtile = tile + warp * TmLB::ELEMS;
+    const int b_c = lane, b_k1 = warp;      // last column stage: (column, k1)
+
+    for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
+        const int f = unit / p.nplanes, x = unit % p.nplanes;
+        const real* src = in + f * p.r_fs + x * p.r_xs;
+        // ---------------- row phase: one complex FFT along z per row pair (a + ib) ----------------
+        Cx<real> nx[R];
+        auto load_pair = [&](int pass, Cx<real> (&dst)[R]) {
+            const int c = lane / R, n2 = lane % R;
+            const int y = (pass * 4 + m.n1lo) * 16 + m.q * 4 + 2 * c;
+            const real* ra = src + (long long)y * p.r_ys + n2;
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1)
+                dst[n1] = pass < 4 ? Cx<real>{__ldcs(ra + n1 * R), __ldcs(ra + p.r_ys + n1 * R)} : Cx<real>{0, 0};
+        };
+        load_pair(0, nx);
+        const int partner = (lane & 16) | ((16 - m.k1) & 15);
+        for (int pass = 0; pass < 4; ++pass) {
+            const int n1r = pass * 4 + m.n1lo;
+            {
+                const int c = lane / R, n2 = lane % R;
+                Cx<real> v[R];
+#pragma unroll
+                for (int n1 = 0; n1 < R; ++n1) v[n1] = nx[n1];
+                load_pair(pass + 1, nx);
+                dft_reg<real, R, -1>(v);
+                twr.template apply<false>(v);
+#pragma unroll
+                for (int k1 = 0; k1 < R; ++k1) wtile[TmLB::at2(k1, n2, c)] = v[k1];
+            }
+            __syncwarp();
+            {   // (row pair y1, k1): v[k2] = Z[k1 + 16 k2]
+                Cx<real> v[R];
+#pragma unroll
+                for (int n2 = 0; n2 < R; ++n2) v[n2] = wtile[TmLB::at2(m.k1, n2, m.y1)];
+                dft_reg<real, R, -1>(v);
+                float r[32];
+                Cx<real> nA = {0, 0}, nB = {0, 0};
+                static_for<0, 9>([&](auto kc) {
+                    constexpr int k2 = decltype(kc)::value;
+                    // Z[NZ - k] lives in lane (16 - k1) % 16 of the same row pair, register 15 - k2
+                    // (k1 == 0: own register (16 - k2) % 16)
+                    const Cx<real> give = (m.k1 == 0) ? v[(R - k2) % R] : v[R - 1 - k2];
+                    const Cx<real> zn = {shfl(give.x, partner), shfl(give.y, partner)};
+                    const Cx<real> zk = v[k2];
+                    const Cx<real> A = {(real)0.5 * (zk.x + zn.x), (real)0.5 * (zk.y - zn.y)};
+                    const Cx<real> B = {(real)0.5 * (zk.y + zn.y), (real)0.5 * (zn.x - zk.x)};
+                    if constexpr (k2 < 8) {
+                        r[4 * k2] = A.x; r[4 * k2 + 1] = A.y; r[4 * k2 + 2] = B.x; r[4 * k2 + 3] = B.y;
+                    } else {
+                        nA = A; nB = B;                     // k = 128 for k1 == 0
+                    }
+                });
+                tmem_st32(tbase + m.lane_base + 32u * (uint32_t)n1r, r);
+                if (m.k1 == 0) {
+                    const int y = n1r * 16 + m.q * 4 + 2 * m.y1;
+                    nyq[y] = nA; nyq[y + 1] = nB;
+                }
+            }
+            __syncwarp();
+        }
+        tmem_wait_st();
+        tmem_sync();
+        // ---------------- column phase: FFT along y, super-chunks 0..3 = columns 0..127, 4 = Nyquist + pad ----
+        Cx<real>* dstp = out + f * p.k_fs + x * p.k_xs;
+        for (int sc = 0; sc < 5; ++sc) {
+            if (sc < 4 || m.c == 0) {
+                Cx<real> v[R];
+                if (sc < 4) {
+                    const uint32_t t0 = tbase + m.lane_base + 2u * (uint32_t)(sc * 4 + m.combo_lo);
+#pragma unroll
+                    for (int n1 = 0; n1 < R; ++n1) tmem_ld2(t0 + 32u * n1, v[n1].x, v[n1].y);
+                    tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < R; ++n1) v[n1] = nyq[n1 * R + m.n2];
+                }
+                dft_reg<real, R, -1>(v);
+                twc.template apply<false>(v);
+#pragma unroll
+                for (int k1 = 0; k1 < R; ++k1) tile[TmLA::at2(k1, m.n2, m.c)] = v[k1];
+            }
+            __syncthreads();
+            const int col = sc * CS + b_c;
+            if (sc < 4 || b_c < 2) {                        // column 128 and the zero pad column 129
+                Cx<real> v[R];
+#pragma unroll
+                for (int n2 = 0; n2 < R; ++n2) v[n2] = (sc < 4 || b_c == 0) ? tile[TmLA::at2(b_k1, n2, b_c)] : Cx<real>{0, 0};
+                if (sc < 4 || b_c == 0) dft_reg<real, R, -1>(v);
+                if (p.push) {
+                    const long long off = (long long)(p.x0 + x) * p.pk_xs + f * p.pk_fs + col;
+                    const int nyl_mask = (1 << p.nyl_shift) - 1;
+#pragma unroll
+                    for (int k2 = 0; k2 < R; ++k2) {
+                        const int ky = b_k1 + R * k2;
+                        Cx<real>* dq = reinterpret_cast<Cx<real>*>(p.peer[ky >> p.nyl_shift]);
+                        st_stream(dq + off + (long long)(ky & nyl_mask) * NZCP, v[k2]);
+                    }
+                } else {
+#pragma unroll
+                    for (int k2 = 0; k2 < R; ++k2) st_stream(dstp + (long long)(b_k1 + R * k2) * NZCP + col, v[k2]);
+                }
+            }
+            __syncthreads();
+        }
+        tmem_sync();
+    }
+    tmem_free_all(tbase, warp);
+}
+
+static bool plane_tmem_enabled() {
+    const char* e = getenv("HYMD_B200_PLANE_TMEM");
+    return !(e && e[0] == '0');
+}
+
+static int launch_plane_tmem(hymd_ctx* c, bool inverse, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
+    int sms = 0;
+    HYMD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev));
+    int grid = sms;                     // one CTA per SM: it owns the SM's whole tensor memory
+    if (grid > p.nunits) grid = p.nunits;
+    if (grid < 1) return HYMD_OK;
+    if (inverse) {
+        HYMD_CUDA(cudaFuncSetAttribute(plane_c2r_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+        plane_c2r_tmem_kernel<<<grid, 512, TM_SMEM, s>>>((const Cx<float>*)in, (float*)out, (const Cx<float>*)c->ytw,
+                                                         (const Cx<float>*)c->ztw, p);
+    } else {
+        HYMD_CUDA(cudaFuncSetAttribute(plane_r2c_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+        plane_r2c_tmem_kernel<<<grid, 512, TM_SMEM, s>>>((const float*)in, (Cx<float>*)out, (const Cx<float>*)c->ytw,
+                                                         (const Cx<float>*)c->ztw, p);
+    }
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 static bool pow2_in(int n, int lo, int hi) { return n >= lo && n <= hi && (n & (n - 1)) == 0; }
 
@@ -793,6 +1203,10 @@ static int launch_plane_nt(hymd_ctx* c, const void* in, void* out, const PlanePa
 
 template <typename real, bool INVERSE>
 static int dispatch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
+    if (sizeof(real) == 4 && c->g.Ny == TM_N && c->g.Nz == TM_N && plane_tmem_enabled()) {
+        HYMD_CHECK(plane_tables(c));
+        return launch_plane_tmem(c, INVERSE, in, out, p, s);
+    }
     switch (c->g.Ny) {
         case 16: return launch_plane_nt<real, 16, INVERSE>(c, in, out, p, s);
         case 32: return launch_plane_nt<real, 32, INVERSE>(c, in, out, p, s);

@@ -372,3 +372,38 @@ def test_numpy_positions_mutated_in_place_are_rebinned():
     fresh = GpuRun(cfg, pos.copy(), types, charges=q, as_numpy=True)
     assert rel_err(ef, fresh.eforces()) < 1e-12
     assert rel_err(ef, before) > 1e-3
+
+
+@pytest.mark.parametrize("coulomb", [False, True])
+def test_tensor_memory_plane_transforms(coulomb, monkeypatch):
+    """256 x 256 fp32 planes: the (y,z) transforms exchange their two phases through tensor memory
+    (planefft.cu, plane_*_tmem_kernel).  Every output kind they produce -- force meshes (derive mode, ghost
+    layout), filtered densities, potentials, psi, electric field, Laplacians -- against the oracle, and the
+    forces against the L2-scratch kernels (HYMD_B200_PLANE_TMEM=0) they replace."""
+    from gpu_common import GpuRun, OracleRun, rel_err
+    cfg, pos, types, q = _system(40000, [16, 256, 256], [3.0, 9.0, 9.5], np.float32, seed=21, coulomb=coulomb)
+    g = GpuRun(cfg, pos, types, charges=q, compute_potential=True)
+    o = OracleRun(cfg, pos, types, charges=q)
+    tol = TOL[np.float32]
+    assert rel_err(g.forces(), o.force) < tol
+    for t in range(cfg.n_types):
+        assert rel_err(g.phi[t].value.cpu().numpy(), o.st.phi[t]) < tol
+        scale = np.abs(o.st.v_ext[t]).max() + 1.0 / cfg.kappa
+        assert np.abs(g.v_ext[t].value.cpu().numpy() - o.st.v_ext[t]).max() / scale < tol
+        for d in range(3):
+            assert rel_err(g.force_mesh[t][d].value.cpu().numpy(), o.st.force_mesh[t][d]) < tol
+    from oracle import field_oracle as fo
+    fo.comp_laplacian(o.st, o.cfg, workers=-1)
+    lscale = max(np.abs(o.st.phi_laplacian[t][d]).max() for t in range(cfg.n_types) for d in range(3))
+    for t in range(cfg.n_types):
+        for d in range(3):
+            got = g.phi_laplacian[t][d].value.cpu().numpy()
+            assert np.abs(got - o.st.phi_laplacian[t][d]).max() / lscale < tol
+    if coulomb:
+        assert rel_err(g.eforces(), o.elec_forces) < tol
+        assert rel_err(g.psi.value.cpu().numpy(), o.st.psi) < tol
+        for d in range(3):
+            assert rel_err(g.elec_field[d].value.cpu().numpy(), o.st.elec_field[d]) < tol
+    monkeypatch.setenv("HYMD_B200_PLANE_TMEM", "0")
+    h = GpuRun(cfg, pos, types, charges=q)
+    assert rel_err(g.forces(), h.forces()) < 2e-6

@@ -145,7 +145,7 @@ def _run_and_compare(P, mesh, n, dtype, pme, mode, steps=1, env=None, monkeypatc
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("P,mesh", [(2, [32, 24, 40]), (4, [32, 24, 40]), (2, [32, 32, 32]), (4, [16, 64, 64]),
-                                    (8, [64, 32, 32]), (2, [18, 12, 10])])
+                                    (8, [64, 32, 32]), (2, [18, 12, 10]), (2, [16, 256, 256])])
 def test_virtual_slabs_match_oracle(P, mesh, dtype):
     """Particles at home: transposes, halo reduce / fetch, slab-sharded energies (cuFFT path for the odd
     meshes, plane + x-line kernels for the power-of-two ones)."""

@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--mesh", type=int, default=None, help="override mesh size (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--whole", action="store_true",
+                    help="C5: every rank generates the whole 1e8-particle box (default: x-chunks with their own "
+                         "seeds, each rank generates only its share)")
     ap.add_argument("--parity-max-n", type=int, default=25_000_000,
                     help="largest global particle count for which rank 0 runs a CPU oracle cycle "
                          "and compares every particle's force (above: momentum conservation only)")
@@ -140,6 +143,13 @@ def build_system(args, world, rank=0):
     if args.scaling == "weak" and world > 1:
         return make_system(args.workload, dtype=dtype, n=args.n, mesh=args.mesh, x_copies=world,
                            x_index=rank), True
+    if args.workload == "C5" and not args.whole:
+        # 1e8 particles: no rank generates the whole box.  The global system is 8 x-chunks with their own
+        # seeds (hymd_b200.synthetic.make_system, x_chunk); rank r generates chunks [8 r / P, 8 (r+1) / P),
+        # i.e. the same global system for P = 1, 2, 4, 8.
+        per = CHUNKS // world
+        return make_system(args.workload, dtype=dtype, n=args.n, mesh=args.mesh,
+                           x_chunk=(rank * per, (rank + 1) * per, CHUNKS)), True
     return make_system(args.workload, dtype=dtype, n=args.n, mesh=args.mesh), False
 
 
@@ -182,6 +192,7 @@ def workload_config(args, world, cfg, n_global, pme):
 
 
 NBUF = 6
+CHUNKS = 8
 
 
 class OracleCycle:
@@ -313,7 +324,11 @@ def main():
     cfg = sysm.config
     mesh = [int(x) for x in np.full(3, cfg.mesh_size)]
     T = cfg.n_types
-    N = len(sysm.positions) * (world if presharded else 1)
+    N = len(sysm.positions)
+    if presharded and world > 1:
+        nt = torch.tensor([N], dtype=torch.int64, device="cuda")
+        dist.all_reduce(nt)
+        N = int(nt.item())
     ham = get_hamiltonian(cfg)
     pm, fl, ecl, cl = F.initialize_pm(None, cfg)
     phi, phi_fourier, force_mesh, v_ext_fourier, v_ext, phi_transfer, phi_laplacian = fl
@@ -325,7 +340,7 @@ def main():
     # system (strong scaling: the generator's order; weak: box r holds [r*n, (r+1)*n))
     pos_h, typ_h, q_h = sysm.positions, sysm.types, sysm.charges
     vel_h = sysm.velocities
-    gid_h = np.arange(len(pos_h), dtype=np.int64) + (rank * len(pos_h) if presharded else 0)
+    gid_h = np.arange(len(pos_h), dtype=np.int64) + (rank * len(pos_h) if presharded else 0)   # equal shares
     if world > 1 and not presharded:
         L = float(cfg.box_size[0])
         cell = np.floor(pos_h[:, 0].astype(np.float64) * mesh[0] / L).astype(np.int64) % mesh[0]
@@ -434,7 +449,7 @@ def main():
             gathered = [None] * world if rank == 0 else None
             dist.gather_object(payload, gathered, dst=0)
         else:
-            gathered = [(gid_h, None, None, None, gpu_f, gpu_ef)]
+            gathered = [(gid_h, frames_h[PF], typ_h, q_h, gpu_f, gpu_ef)]
         if rank == 0:
             if presharded:      # weak scaling: the global system is the ranks' boxes side by side
                 g_pos = np.concatenate([g[1] for g in gathered])

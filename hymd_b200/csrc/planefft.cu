@@ -727,7 +727,8 @@ constexpr int TM_N = 256, TM_CS = 32;                      // plane edge, column
 using TmLA = LayA<TM_N, TM_CS>;
 using TmLB = LayB<TM_N, 2>;
 constexpr int TM_TILE = TmLA::ELEMS > 16 * TmLB::ELEMS ? TmLA::ELEMS : 16 * TmLB::ELEMS;
-constexpr size_t TM_SMEM = sizeof(Cx<float>) * (size_t)(3 * TM_N + TM_TILE);
+constexpr size_t TM_SMEM = sizeof(Cx<float>) * (size_t)(4 * TM_N + TM_TILE);
+constexpr size_t TM_SMEM_DBUF = sizeof(Cx<float>) * (size_t)(4 * TM_N + 2 * TmLA::ELEMS);
 
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(a)),
@@ -800,10 +801,11 @@ __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Cx<real>* twy = reinterpret_cast<Cx<real>*>(smem_raw);
     Cx<real>* twz = twy + NY;
-    Cx<real>* nyq = twz + NZ;                               // column kz = 128 after the y transform
-    Cx<real>* tile = nyq + NY;
+    Cx<real>* nyq = twz + NZ;                               // column kz = 128 after the y transform (x2: derive)
+    Cx<real>* tile = nyq + 2 * NY;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const bool dbuf = p.scr_alt != 0;                       // two column tiles: one CTA barrier per round
     for (int i = tid; i < NY; i += 512) { twy[i] = twy_g[i]; twz[i] = twz_g[i]; }
     const uint32_t tbase = tmem_alloc_all(&tmem_slot, warp);
     const TmMap m(warp, lane);
@@ -850,35 +852,72 @@ __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
                 dst[k2] = valid ? (mode == 1 ? ld_l2(e) : ld_stream(e)) : Cx<real>{0, 0};
             }
         };
+        // Nyquist column (round 4).  derive: mode 2 multiplies it by k_z = 0 (all zeros: no round), and the
+        // columns of modes 0 and 1 are transformed together in the round of d = 0 (lanes c = 0 and c = 1).
+        const int nround = (p.derive && d > 0) ? 4 : 5;
+        const int nyq_cols = p.derive ? 2 : 1;
+        auto nyq_src = [&](int c) { return p.derive ? in + (2 * fu + c) * p.k_fs + x * p.k_xs : src; };
+        auto load_nyq = [&](Cx<real> (&dst)[R]) {
+            const Cx<real>* sn = nyq_src(a_c < nyq_cols ? a_c : 0);
+#pragma unroll
+            for (int k2 = 0; k2 < R; ++k2)
+                dst[k2] = a_c < nyq_cols ? ld_l2(sn + (long long)(a_k1 + R * k2) * NZCP + NZ / 2) : Cx<real>{0, 0};
+        };
         load_chunk(0, nx);
-        for (int sc = 0; sc < 5; ++sc) {
+        // rounds 0..3 (compile-time round index: the prefetch target, the TMEM columns and the tile buffer fold)
+        static_for<0, 4>([&](auto scc) {
+            constexpr int sc = decltype(scc)::value;
+            Cx<real>* cur = tile + (dbuf ? (sc & 1) * TmLA::ELEMS : 0);
             Cx<real> v[R];
 #pragma unroll
             for (int k2 = 0; k2 < R; ++k2) v[k2] = nx[k2];
-            if (sc < 4) load_chunk(sc + 1, nx);
-            if (sc < 4 || a_c == 0) {
-                scale_chunk(v, a_k1, sc * CS + a_c);
+            if constexpr (sc < 3) load_chunk(sc + 1, nx);
+            else if (nround == 5) load_nyq(nx);
+            scale_chunk(v, a_k1, sc * CS + a_c);
+            dft_reg<real, R, +1>(v);
+            twc.template apply<true>(v);
+#pragma unroll
+            for (int n2 = 0; n2 < R; ++n2) cur[TmLA::at2(a_k1, n2, a_c)] = v[n2];
+            __syncthreads();
+            Cx<real> u[R];
+#pragma unroll
+            for (int k1 = 0; k1 < R; ++k1) u[k1] = cur[TmLA::at2(k1, m.n2, m.c)];
+            dft_reg<real, R, +1>(u);
+            const uint32_t t0 = tbase + m.lane_base + 2u * (uint32_t)(sc * 4 + m.combo_lo);
+#pragma unroll
+            for (int n1 = 0; n1 < R; ++n1) tmem_st2(t0 + 32u * n1, u[n1].x, u[n1].y);
+            if (!dbuf) __syncthreads();
+        });
+        if (nround == 5) {                                  // Nyquist column(s): 16 (32) threads per stage
+            Cx<real>* cur = tile;
+            if (a_c < nyq_cols) {
+                Cx<real> v[R];
+#pragma unroll
+                for (int k2 = 0; k2 < R; ++k2) v[k2] = nx[k2];
+                if (p.derive && a_c == 1) {                 // mode 1 on the Nyquist column: k_y, self-conjugate rule
+                    const real fk1 = (real)a_k1;
+#pragma unroll
+                    for (int k2 = 0; k2 < R; ++k2) {
+                        real sk = dky * (fk1 + (real)(R * k2 - (2 * k2 >= R ? NY : 0)));
+                        if (2 * k2 == R && a_k1 == 0) sk = 0;
+                        v[k2].x *= sk; v[k2].y *= sk;
+                    }
+                }
                 dft_reg<real, R, +1>(v);
                 twc.template apply<true>(v);
 #pragma unroll
-                for (int n2 = 0; n2 < R; ++n2) tile[TmLA::at2(a_k1, n2, a_c)] = v[n2];
+                for (int n2 = 0; n2 < R; ++n2) cur[TmLA::at2(a_k1, n2, a_c)] = v[n2];
             }
             __syncthreads();
-            if (sc < 4 || m.c == 0) {
+            if (m.c < nyq_cols) {
                 Cx<real> u[R];
 #pragma unroll
-                for (int k1 = 0; k1 < R; ++k1) u[k1] = tile[TmLA::at2(k1, m.n2, m.c)];
+                for (int k1 = 0; k1 < R; ++k1) u[k1] = cur[TmLA::at2(k1, m.n2, m.c)];
                 dft_reg<real, R, +1>(u);
-                if (sc < 4) {
-                    const uint32_t t0 = tbase + m.lane_base + 2u * (uint32_t)(sc * 4 + m.combo_lo);
+                Cx<real>* nq = nyq + m.c * NY;
 #pragma unroll
-                    for (int n1 = 0; n1 < R; ++n1) tmem_st2(t0 + 32u * n1, u[n1].x, u[n1].y);
-                } else {
-#pragma unroll
-                    for (int n1 = 0; n1 < R; ++n1) nyq[n1 * R + m.n2] = u[n1];
-                }
+                for (int n1 = 0; n1 < R; ++n1) nq[n1 * R + m.n2] = u[n1];
             }
-            __syncthreads();
         }
         tmem_wait_st();
         tmem_sync();
@@ -910,7 +949,8 @@ __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
             }
             if (m.k1 == 0) {                                // k = 128: imaginary parts dropped (c2r semantics)
                 const int y = ybase + 2 * m.y1;
-                v[8] = {nyq[y].x, nyq[y + 1].x};
+                if (p.derive && d == 2) v[8] = {0, 0};
+                else { const Cx<real>* nq = nyq + ((p.derive && d == 1) ? NY : 0); v[8] = {nq[y].x, nq[y + 1].x}; }
             }
             dft_reg<real, R, +1>(v);
             twr.template apply<true>(v);
@@ -962,9 +1002,10 @@ __global__ void __launch_bounds__(512, 1) plane_r2c_tmem_kernel(
     Cx<real>* twy = reinterpret_cast<Cx<real>*>(smem_raw);
     Cx<real>* twz = twy + NY;
     Cx<real>* nyq = twz + NZ;
-    Cx<real>* tile = nyq + NY;
+    Cx<real>* tile = nyq + 2 * NY;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const bool dbuf = p.scr_alt != 0;
     for (int i = tid; i < NY; i += 512) { twy[i] = twy_g[i]; twz[i] = twz_g[i]; }
     const uint32_t tbase = tmem_alloc_all(&tmem_slot, warp);
     const TmMap m(warp, lane);
@@ -1038,6 +1079,7 @@ __global__ void __launch_bounds__(512, 1) plane_r2c_tmem_kernel(
         // ---------------- column phase: FFT along y, super-chunks 0..3 = columns 0..127, 4 = Nyquist + pad ----
         Cx<real>* dstp = out + f * p.k_fs + x * p.k_xs;
         for (int sc = 0; sc < 5; ++sc) {
+            Cx<real>* cur = tile + (dbuf ? (sc & 1) * TmLA::ELEMS : 0);
             if (sc < 4 || m.c == 0) {
                 Cx<real> v[R];
                 if (sc < 4) {
@@ -1052,14 +1094,14 @@ __global__ void __launch_bounds__(512, 1) plane_r2c_tmem_kernel(
                 dft_reg<real, R, -1>(v);
                 twc.template apply<false>(v);
 #pragma unroll
-                for (int k1 = 0; k1 < R; ++k1) tile[TmLA::at2(k1, m.n2, m.c)] = v[k1];
+                for (int k1 = 0; k1 < R; ++k1) cur[TmLA::at2(k1, m.n2, m.c)] = v[k1];
             }
             __syncthreads();
             const int col = sc * CS + b_c;
             if (sc < 4 || b_c < 2) {                        // column 128 and the zero pad column 129
                 Cx<real> v[R];
 #pragma unroll
-                for (int n2 = 0; n2 < R; ++n2) v[n2] = (sc < 4 || b_c == 0) ? tile[TmLA::at2(b_k1, n2, b_c)] : Cx<real>{0, 0};
+                for (int n2 = 0; n2 < R; ++n2) v[n2] = (sc < 4 || b_c == 0) ? cur[TmLA::at2(b_k1, n2, b_c)] : Cx<real>{0, 0};
                 if (sc < 4 || b_c == 0) dft_reg<real, R, -1>(v);
                 if (p.push) {
                     const long long off = (long long)(p.x0 + x) * p.pk_xs + f * p.pk_fs + col;
@@ -1075,7 +1117,7 @@ __global__ void __launch_bounds__(512, 1) plane_r2c_tmem_kernel(
                     for (int k2 = 0; k2 < R; ++k2) st_stream(dstp + (long long)(b_k1 + R * k2) * NZCP + col, v[k2]);
                 }
             }
-            __syncthreads();
+            if (!dbuf) __syncthreads();
         }
         tmem_sync();
     }
@@ -1087,19 +1129,25 @@ static bool plane_tmem_enabled() {
     return !(e && e[0] == '0');
 }
 
-static int launch_plane_tmem(hymd_ctx* c, bool inverse, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
+static int launch_plane_tmem(hymd_ctx* c, bool inverse, const void* in, void* out, const PlaneParams& p_in, cudaStream_t s) {
     int sms = 0;
     HYMD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev));
     int grid = sms;                     // one CTA per SM: it owns the SM's whole tensor memory
-    if (grid > p.nunits) grid = p.nunits;
+    if (grid > p_in.nunits) grid = p_in.nunits;
     if (grid < 1) return HYMD_OK;
+    PlaneParams p = p_in;
+    // double-buffered column tiles (one CTA barrier per round instead of two): measured -2 % on the forward
+    // kernel, nothing on the inverse (profiles/r2h_*), so only the forward kernel pays the extra 70 KB
+    p.scr_alt = inverse ? 0 : 1;
+    if (const char* e = getenv("HYMD_B200_TMEM_DBUF")) p.scr_alt = atoi(e) != 0;
+    const size_t smem = p.scr_alt ? TM_SMEM_DBUF : TM_SMEM;
     if (inverse) {
-        HYMD_CUDA(cudaFuncSetAttribute(plane_c2r_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
-        plane_c2r_tmem_kernel<<<grid, 512, TM_SMEM, s>>>((const Cx<float>*)in, (float*)out, (const Cx<float>*)c->ytw,
+        HYMD_CUDA(cudaFuncSetAttribute(plane_c2r_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        plane_c2r_tmem_kernel<<<grid, 512, smem, s>>>((const Cx<float>*)in, (float*)out, (const Cx<float>*)c->ytw,
                                                          (const Cx<float>*)c->ztw, p);
     } else {
-        HYMD_CUDA(cudaFuncSetAttribute(plane_r2c_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
-        plane_r2c_tmem_kernel<<<grid, 512, TM_SMEM, s>>>((const float*)in, (Cx<float>*)out, (const Cx<float>*)c->ytw,
+        HYMD_CUDA(cudaFuncSetAttribute(plane_r2c_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        plane_r2c_tmem_kernel<<<grid, 512, smem, s>>>((const float*)in, (Cx<float>*)out, (const Cx<float>*)c->ytw,
                                                          (const Cx<float>*)c->ztw, p);
     }
     HYMD_LAUNCH_CHECK(c);

@@ -67,13 +67,28 @@ def box_length(n: int) -> float:
 
 def make_system(name: str = "C2", dtype=np.float32, n: Optional[int] = None,
                 mesh: Optional[int] = None, sigma: float = 0.5, kappa: float = 0.05,
-                chains: bool = True, x_copies: int = 1, x_index: int = 0) -> System:
+                chains: bool = True, x_copies: int = 1, x_index: int = 0,
+                x_chunk: Optional[Tuple[int, int, int]] = None) -> System:
     """Build one of the C1..C5 systems (optionally at a reduced ``n`` / ``mesh``).
 
     ``x_copies > 1`` (weak scaling): the global system is ``x_copies`` independent boxes of ``n``
     particles stacked along x (box ``[x_copies * L, L, L]``, mesh ``[x_copies * mesh, mesh,
     mesh]``); the call returns the particles of box ``x_index`` only (own seed) together with the
-    GLOBAL config, so every rank generates just its own slab."""
+    GLOBAL config, so every rank generates just its own slab.
+
+    ``x_chunk = (first, last, count)`` (strong scaling of the largest systems, where no rank can afford to
+    generate all 1e8 particles): the cubic box is cut into ``count`` x-chunks, chunk ``k`` holds ``n / count``
+    particles generated from its own seed with their chain starts / solvent positions uniform inside the
+    chunk; the call returns chunks ``first .. last - 1``.  The GLOBAL system (all chunks) is the same however
+    many ranks share it; chains may reach into the neighbouring chunk."""
+    if x_chunk is not None:
+        first, last, count = x_chunk
+        parts = [_make_chunk(name, dtype, n, mesh, sigma, kappa, chains, k, count) for k in range(first, last)]
+        return System(name=name, config=parts[0].config,
+                      positions=np.concatenate([p.positions for p in parts]),
+                      types=np.concatenate([p.types for p in parts]),
+                      charges=None if parts[0].charges is None else np.concatenate([p.charges for p in parts]),
+                      velocities=np.concatenate([p.velocities for p in parts]))
     spec = SPECS[name]
     n = int(n if n is not None else spec["n"])
     mesh = int(mesh if mesh is not None else spec["mesh"])
@@ -148,3 +163,43 @@ def make_system(name: str = "C2", dtype=np.float32, n: Optional[int] = None,
     return System(name=name, config=cfg, positions=pos, types=types.astype(np.int32),
                   charges=None if charges is None else charges.astype(dtype),
                   velocities=vel.astype(dtype))
+
+
+def _make_chunk(name, dtype, n, mesh, sigma, kappa, chains, k, count):
+    """Chunk ``k`` of ``count`` of the global system ``name`` (see ``make_system(x_chunk=...)``): the
+    generator of the whole box run on ``n / count`` particles, squeezed into the chunk's x range."""
+    spec = SPECS[name]
+    n_glob = int(n if n is not None else spec["n"])
+    sub = make_system(name, dtype=np.float64, n=n_glob // count, mesh=mesh, sigma=sigma, kappa=kappa, chains=False)
+    L = box_length(n_glob)
+    rng = np.random.default_rng(spec["seed"] + 104729 * (k + 1))
+    m = len(sub.positions)
+    pos = rng.uniform(0.0, 1.0, size=(m, 3)) * np.array([L / count, L, L]) + np.array([k * L / count, 0.0, 0.0])
+    types = sub.types
+    if chains:      # 20-bead random walks along the file order of every polymer type (vectorised)
+        names = spec["names"]
+        cfg0 = sub.config
+        for t, is_poly in enumerate(spec["polymer"]):
+            if not is_poly:
+                continue
+            idx = np.nonzero(types == cfg0.name_to_type_map[names[t]])[0]
+            nb = len(idx) // 20 * 20
+            if nb == 0:
+                continue
+            steps = rng.normal(size=(nb // 20, 20, 3))
+            steps *= 0.47 / np.linalg.norm(steps, axis=2, keepdims=True)
+            steps[:, 0, :] = 0.0
+            walk = np.cumsum(steps, axis=1) + pos[idx[:nb:20], None, :]
+            pos[idx[:nb]] = walk.reshape(nb, 3)
+    pos = np.mod(pos, L).astype(dtype)
+    pos[pos >= np.asarray(L, dtype=dtype)] = 0.0
+    vel = rng.normal(size=(m, 3)) * np.sqrt(Config.gas_constant * 323.0 / 72.0)
+    cfg = Config(mesh_size=int(mesh if mesh is not None else spec["mesh"]), sigma=sigma, kappa=kappa,
+                 box_size=[L, L, L], hamiltonian="DefaultWithChi", chi=[Chi(*c) for c in spec["chi"]],
+                 dtype=np.dtype(dtype), mass=72.0, time_step=0.01, respa_inner=25,
+                 coulombtype=sub.config.coulombtype, dielectric_const=sub.config.dielectric_const)
+    cfg.finalize(spec["names"], n_particles=(n_glob // count) * count)
+    if sub.charges is not None:
+        cfg.type_charges = sub.config.type_charges
+    return System(name=name, config=cfg, positions=pos, types=types,
+                  charges=None if sub.charges is None else sub.charges.astype(dtype), velocities=vel.astype(dtype))

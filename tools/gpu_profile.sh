@@ -8,7 +8,7 @@ timeout 900 python bench.py "$@" > $OUT/bench.json 2> $OUT/bench.err; tail -c 60
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e "$@" > $OUT/ncu_launch.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on \
-    -k regex:'paint_kernel|xline_kernel|readout_gather_kernel|readout_kernel|count_kernel|scatter_kernel|plane_r2c_kernel|plane_c2r_kernel' -s 21 -c 7 \
+    -k regex:'paint_kernel|xline_kernel|readout_gather_kernel|readout_kernel|count_kernel|scatter_kernel|plane_r2c|plane_c2r' -s 21 -c 7 \
     -o $OUT/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e "$@" > $OUT/ncu_full.log 2>&1
 tail -2 $OUT/ncu_full.log | cut -c1-200
 ls -la $OUT

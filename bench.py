@@ -443,11 +443,30 @@ def main():
     gpu_ef = eforce_d.cpu().numpy().copy() if pme else None
     parity = None
     if N_global <= args.parity_max_n:
+        def gather_rows(a):
+            """Per-rank arrays with one row per local particle -> list of the ranks' arrays on rank 0 (NCCL
+            gather of padded tensors: the ranks hold different particle counts after domain_decomposition)."""
+            if a is None:
+                return None
+            t = torch.as_tensor(np.ascontiguousarray(a), device=dev)
+            nmax = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)
+            counts = [torch.zeros_like(nmax) for _ in range(world)]
+            dist.all_gather(counts, nmax)
+            m = int(max(int(c.item()) for c in counts))
+            pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            pad[: t.shape[0]] = t
+            out = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad, out, dst=0)
+            if rank != 0:
+                return None
+            return [o[: int(c.item())].cpu().numpy() for o, c in zip(out, counts)]
+
         if world > 1:
-            payload = (gid_h, frames_h[PF], typ_h, q_h, gpu_f, gpu_ef) if presharded else \
-                (gid_h, None, None, None, gpu_f, gpu_ef)
-            gathered = [None] * world if rank == 0 else None
-            dist.gather_object(payload, gathered, dst=0)
+            cols = [gid_h, frames_h[PF] if presharded else None, typ_h if presharded else None,
+                    q_h if presharded else None, gpu_f, gpu_ef]
+            cols = [gather_rows(a) for a in cols]
+            gathered = None if rank != 0 else \
+                [tuple(None if c is None else c[r] for c in cols) for r in range(world)]
         else:
             gathered = [(gid_h, frames_h[PF], typ_h, q_h, gpu_f, gpu_ef)]
         if rank == 0:

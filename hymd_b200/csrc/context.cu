@@ -239,9 +239,18 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     if (P > 1 && (st = comm_create(c, nccl_id))) return fail(st);
     const char* nccl_x = getenv("HYMD_B200_NCCL_EXCHANGE");
     c->p2p = P > 1 && (!(nccl_x && nccl_x[0] == '1') || comm_is_local(c));
-    const char* fpush = getenv("HYMD_B200_FUSED_PUSH");
-    c->fused_push = c->p2p && c->fused && c->plane && !(fpush && fpush[0] == '0') &&
-                    (g.nxl & (g.nxl - 1)) == 0 && (g.nyl & (g.nyl - 1)) == 0;
+    // Transposes of the slab FFT over NVLink: "blocked" (default with the plane kernels:
+    // the kernels read / write per-destination blocks, each block crosses as ONE contiguous peer copy),
+    // "fused" (remote stores issued by the plane r2c / x-line kernels), "kernels" (pack / unpack push kernels)
+    const char* xm = getenv("HYMD_B200_EXCHANGE");
+    const bool pow2 = (g.nxl & (g.nxl - 1)) == 0 && (g.nyl & (g.nyl - 1)) == 0;
+    c->xmode = 0;
+    if (c->p2p && c->plane && pow2) {
+        c->xmode = 2;
+        if (xm && xm[0] == 'f' && c->fused) c->xmode = 1;
+        if (xm && xm[0] == 'k') c->xmode = 0;
+    }
+    c->fused_push = c->xmode == 1;
     if ((st = readout_setup(c))) return fail(st);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(HYMD_ERR_CUDA);
     *out = c;

@@ -217,7 +217,9 @@ struct hymd_ctx {
     size_t halo_bytes;
     hymd::Comm* comm;       // NCCL communicator (world_size > 1)
     bool p2p;               // exchanges store into peer memory over NVLink (CUDA IPC) instead of NCCL send/recv
-    bool fused_push;        // the transposes are stores issued by the plane r2c / x-line kernels themselves
+    int xmode;              // how the FFT transposes cross NVLink (slabfft.cu): 0 pack / unpack push kernels,
+                            // 1 stores issued by the plane r2c / x-line kernels, 2 blocked layouts + contiguous peer copies
+    bool fused_push;        // xmode == 1
     bool xpushed;           // the x-line kernel has already stored its output into the peers' work buffers
     unsigned peer_busy;     // PEER_* buffers whose local consumers were enqueued after the last barrier:
                             // a peer may not overwrite them before another barrier (same call sequence
@@ -304,7 +306,7 @@ bool plane_supported(const hymd_ctx* c);
 int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int nplanes, void* k_out,
                   long long k_fs, cudaStream_t s, void* const* push_peers = nullptr);
 int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int nplanes, void* real_out,
-                  bool ghost, bool derive, cudaStream_t s);
+                  bool ghost, bool derive, cudaStream_t s, bool blocked = false);
 // xline.cu
 bool xline_supported(const hymd_ctx* c);
 int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s,

@@ -166,7 +166,22 @@ struct PlaneParams {
     int push, nyl_shift, x0;
     long long pk_xs, pk_fs;
     void* peer[HYMD_MAX_PEERS];
+    // inverse, several slabs, "blocked" exchange: the input is the receive buffer of the inverse transpose as the
+    // peers' contiguous copies left it, W[q][x][f][kyl][kz] (block q = the k_y range rank q transformed along x):
+    // row ky of plane x, spectrum f  ->  in + (ky >> nyl_shift) blk_q + x blk_x + f blk_f + (ky & (nyl-1)) Nzcp
+    int blk_in;
+    long long blk_q, blk_x, blk_f;
 };
+
+// first element of spectrum row ky (plane x, spectrum f) of the inverse kernels' input
+template <typename real>
+__device__ __forceinline__ const Cx<real>* in_row(const Cx<real>* __restrict__ in, const PlaneParams& p, int f, int x,
+                                                   int ky, int nzcp) {
+    if (p.blk_in)
+        return in + (long long)(ky >> p.nyl_shift) * p.blk_q + (long long)x * p.blk_x + (long long)f * p.blk_f +
+               (long long)(ky & ((1 << p.nyl_shift) - 1)) * nzcp;
+    return in + f * p.k_fs + x * p.k_xs + (long long)ky * nzcp;
+}
 
 // Work decomposition inside the 512-thread CTA.
 //   column phase: NG groups of GT threads, each on its own chunk of CG kz-columns (64 bytes per
@@ -299,7 +314,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
 #pragma unroll
                 for (int k2 = 0; k2 < R2y; ++k2)
                 {
-                    const Cx<real>* e = src + (long long)(k1 + R1y * k2) * NZCP + ch * CG + c;
+                    const Cx<real>* e = in_row<real>(in, p, fin, x, k1 + R1y * k2, NZCP) + ch * CG + c;
                     // derive: the plane read for the k_y component is read again for k_z: keep it in L2
                     dst[k2] = valid ? (mode == 1 ? ld_l2(e) : ld_stream(e)) : Cx<real>{0, 0};
                 }
@@ -848,7 +863,7 @@ __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
             const bool valid = sc < 4 || (sc == 4 && a_c == 0);
 #pragma unroll
             for (int k2 = 0; k2 < R; ++k2) {
-                const Cx<real>* e = src + (long long)(a_k1 + R * k2) * NZCP + col;
+                const Cx<real>* e = in_row<real>(in, p, fin, x, a_k1 + R * k2, NZCP) + col;
                 dst[k2] = valid ? (mode == 1 ? ld_l2(e) : ld_stream(e)) : Cx<real>{0, 0};
             }
         };
@@ -856,12 +871,11 @@ __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
         // columns of modes 0 and 1 are transformed together in the round of d = 0 (lanes c = 0 and c = 1).
         const int nround = (p.derive && d > 0) ? 4 : 5;
         const int nyq_cols = p.derive ? 2 : 1;
-        auto nyq_src = [&](int c) { return p.derive ? in + (2 * fu + c) * p.k_fs + x * p.k_xs : src; };
         auto load_nyq = [&](Cx<real> (&dst)[R]) {
-            const Cx<real>* sn = nyq_src(a_c < nyq_cols ? a_c : 0);
+            const int fn = p.derive ? 2 * fu + (a_c < nyq_cols ? a_c : 0) : fin;
 #pragma unroll
             for (int k2 = 0; k2 < R; ++k2)
-                dst[k2] = a_c < nyq_cols ? ld_l2(sn + (long long)(a_k1 + R * k2) * NZCP + NZ / 2) : Cx<real>{0, 0};
+                dst[k2] = a_c < nyq_cols ? ld_l2(in_row<real>(in, p, fn, x, a_k1 + R * k2, NZCP) + NZ / 2) : Cx<real>{0, 0};
         };
         load_chunk(0, nx);
         // rounds 0..3 (compile-time round index: the prefetch target, the TMEM columns and the tile buffer fold)
@@ -1297,10 +1311,18 @@ int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int n
 // derive: k_in holds 2F/3 spectra (per potential row: -i k_x V and -i V, x-inverted) and the
 // kernel forms the k_y / k_z components itself (PlaneParams::derive).
 int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int nplanes, void* real_out,
-                  bool ghost, bool derive, cudaStream_t s) {
+                  bool ghost, bool derive, cudaStream_t s, bool blocked) {
     const Geometry& g = c->g;
     PlaneParams p;
     memset(&p, 0, sizeof(p));
+    if (blocked) {         // k_in = W[q][x][f][kyl][kz] with Fin spectra (see PlaneParams::blk_in)
+        const int Fin = derive ? F / 3 * 2 : F;
+        int sh = 0;
+        while ((1 << sh) < g.nyl) ++sh;
+        if ((1 << sh) != g.nyl) { set_error("blocked inverse transpose needs a power-of-two Ny / P"); return HYMD_ERR_INVALID; }
+        p.blk_in = 1; p.nyl_shift = sh;
+        p.blk_f = (long long)g.nyl * g.Nzcp; p.blk_x = Fin * p.blk_f; p.blk_q = g.nxl * p.blk_x;
+    }
     if (derive && F % 3 != 0) { set_error("plane_inverse: derive needs 3 outputs per row"); return HYMD_ERR_INVALID; }
     p.nunits = (derive ? F / 3 : F) * nplanes; p.nplanes = nplanes;
     p.derive = derive ? 1 : 0;

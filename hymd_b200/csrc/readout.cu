@@ -273,8 +273,9 @@ __global__ void __launch_bounds__(256) readout_gather_kernel(
     GatherParams p) {
     using Tr = RTraits<real>;
     using UT = typename Tr::UT;
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= (p.rt ? (long long)p.rt->n_work : p.n)) return;
+    // several slabs: the grid covers the home particles; the guests behind them take further trips
+    const long long limit = p.rt ? (long long)p.rt->n_work : p.n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < limit; i += (long long)gridDim.x * blockDim.x) {
     const typename Tr::Rec rc = rec[i];
     const UT mx = ((UT)1 << p.fbx) - 1, my = ((UT)1 << p.fby) - 1, mz = ((UT)1 << p.fbz) - 1;
     const real dx = (real)(rc.ux & mx) / (real)((UT)1 << p.fbx), dy = (real)(rc.uy & my) / (real)((UT)1 << p.fby),
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(256) readout_gather_kernel(
         o = force + (size_t)idx * 3;
     }
     o[0] = f0; o[1] = f1; o[2] = f2;
+    }
 }
 
 static void gather_params(hymd_ctx* c, GatherParams& p) {
@@ -316,7 +318,7 @@ static void gather_params(hymd_ctx* c, GatherParams& p) {
     p.rt = route_totals(c);
     p.n_home = c->np; p.rank = g.rank;
     route_peer_ret(c, p.ret, &p.G);
-    if (p.rt) p.n = c->np + route_guest_rows(c);
+    if (p.rt) p.n = c->np > 0 ? c->np : 1;     // grid size only: the live count is rt->n_work
 }
 
 template <typename real, bool CHARGE>

@@ -58,7 +58,8 @@ int ensure_work(hymd_ctx* c, int F) {
     // peer-mapped buffers must never be re-allocated: size them for the largest batch (3T fields)
     if (c->p2p && F < 3 * c->T) F = 3 * c->T;
     HYMD_CHECK(grow(&c->wA, &c->wA_bytes, (size_t)F * (g.nxl + 1) * g.Ny * g.Nzcp * csz));
-    if (g.P > 1 && !c->p2p) HYMD_CHECK(grow(&c->wS, &c->wS_bytes, (size_t)F * g.nxl * g.Ny * g.Nzcp * csz));
+    if (g.P > 1 && (!c->p2p || c->xmode == 2))
+        HYMD_CHECK(grow(&c->wS, &c->wS_bytes, (size_t)F * g.nxl * g.Ny * g.Nzcp * csz));
     return HYMD_OK;
 }
 
@@ -385,6 +386,30 @@ int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t 
     const Geometry& g = c->g;
     if (g.P == 1) return yz_forward(c, real_in, F, k_out, klayout(c, F).fs, s);
     HYMD_CHECK(ensure_work(c, F));
+    if (c->xmode == 2) {
+        // blocked exchange: the plane kernel stores every spectrum row into the staging block of the rank that
+        // owns its k_y range (own rows straight into the local k buffer); a block is exactly the contiguous
+        // range [x0, x0 + nxl) of the receiver's k buffer, so it crosses NVLink as ONE contiguous copy
+        const size_t csz = 2 * c->rsz;
+        const KLayout l = klayout(c, F);
+        const long long block = (long long)g.nxl * l.xs;               // elements per destination
+        PeerPtrs K, T;
+        HYMD_CHECK(peer_table(c, k_out, &K, s));
+        HYMD_CHECK(peer_acquire(c, PEER_K, s));
+        for (int q = 0; q < g.P; ++q)
+            T.p[q] = q == g.rank ? k_out : (char*)c->wS + ((long long)q * block - (long long)g.x0 * l.xs) * (long long)csz;
+        HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p));
+        PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+        for (int i = 1; i < g.P; ++i) {
+            const int q = (g.rank + i) % g.P;
+            HYMD_CUDA(cudaMemcpyAsync((char*)K.p[q] + (size_t)g.x0 * l.xs * csz, (char*)c->wS + (size_t)q * block * csz,
+                                      (size_t)block * csz, cudaMemcpyDeviceToDevice, s));
+        }
+        c->launches += g.P - 1;
+        HYMD_CHECK(comm_barrier(c, s));
+        c->peer_busy |= PEER_K;
+        return HYMD_OK;
+    }
     if (c->fused_push && c->plane) {
         // the forward transpose is the plane kernel's own epilogue: every spectrum row is stored into the
         // k buffer of the rank owning its k_y range while the next rows are still being transformed
@@ -421,6 +446,25 @@ int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost
     const int Fin = derive ? F / 3 * 2 : F;
     if (g.P > 1) {
         HYMD_CHECK(ensure_work(c, Fin));
+        if (c->xmode == 2) {
+            // blocked exchange: the x-range of rank q is one contiguous block of the k layout; it is copied as
+            // it is into block `rank` of q's work buffer, and the plane kernel reads W[q][x][f][kyl][kz]
+            const size_t csz = 2 * c->rsz;
+            const long long block = (long long)g.nxl * klayout(c, Fin).xs;
+            PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+            PeerPtrs W;
+            HYMD_CHECK(peer_table(c, c->wA, &W, s));
+            HYMD_CHECK(peer_acquire(c, PEER_WORK, s));
+            for (int i = 0; i < g.P; ++i) {
+                const int q = (g.rank + i) % g.P;
+                HYMD_CUDA(cudaMemcpyAsync((char*)W.p[q] + (size_t)g.rank * block * csz, (char*)k_in + (size_t)q * block * csz,
+                                          (size_t)block * csz, cudaMemcpyDeviceToDevice, s));
+            }
+            c->launches += g.P;
+            HYMD_CHECK(comm_barrier(c, s));
+            c->peer_busy |= PEER_WORK;
+            return plane_inverse(c, c->wA, 0, F, g.nxl, real_out, ghost, derive, s, true);
+        }
         if (c->xpushed) c->xpushed = false;     // the x-line kernel stored into the peers' work buffers itself
         else HYMD_CHECK(transpose_inverse(c, Fin, k_in, s));
         return yz_inverse(c, c->wA, (g.nxl + 1) * plane, F, real_out, ghost, s, derive);
@@ -511,6 +555,10 @@ int halo_fetch(hymd_ctx* c, void* meshes, int F, cudaStream_t s) {
         PeerPtrs M;
         HYMD_CHECK(peer_table(c, meshes, &M, s));
         HYMD_CHECK(peer_acquire(c, PEER_MESH, s));
+        // cuFFT path: the receiver's own batched 2-D c2r writes all nxl + 1 planes of its ghost meshes (the
+        // last one from a stale work plane), so nobody may store into a neighbour's plane nxl before every
+        // rank has finished its transform.  (The plane kernels write planes 0 .. nxl-1 only.)
+        if (!c->plane) HYMD_CHECK(comm_barrier(c, s));
         const int to = (g.rank - 1 + g.P) % g.P;
         HYMD_CUDA(cudaMemcpy2DAsync((char*)M.p[to] + (size_t)g.nxl * plane, (size_t)g.ghost_elems * c->rsz,
                                     meshes, (size_t)g.ghost_elems * c->rsz, plane, F,

@@ -95,10 +95,12 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
                                                     DeviceScalars* __restrict__ sc,
                                                     const RouteTotals* __restrict__ rt,
                                                     uint32_t* __restrict__ keys, uint32_t away_bin, RouteOut ro) {
-    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long limit = (ROUTED && REUSE) ? (long long)rt->n_total : n;
+    // ROUTED: the grid covers the n home particles; the (few) blocks whose range is followed by staged
+    // guest records of the previous step take a second trip (block-uniform loop: the warp shuffles stay whole)
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;; j += (long long)gridDim.x * blockDim.x) {
     unsigned int r1 = 0, bad = 0;
     uint32_t key = 0xffffffffu;                        // lanes past the end: a run of their own
-    const long long limit = (ROUTED && REUSE) ? (long long)rt->n_total : n;
     bool live = j < limit;
     UT idx = 0, type = 0;
     if (live) {
@@ -163,6 +165,8 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
         if (m > sc->max_cell_count) atomicMax(&sc->max_cell_count, m);
         if (b) atomicAdd(&sc->out_of_slab, b);
     }
+    if (!ROUTED || j - threadIdx.x + (long long)gridDim.x * blockDim.x >= limit) break;
+    }
 }
 
 // Pass 2 (after the scan): staged record j goes to the next free slot of its cell.
@@ -172,11 +176,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(
     uint32_t* __restrict__ cur, RecT* __restrict__ rec, real* __restrict__ q_sorted,
     DeviceScalars* __restrict__ sc, const RouteTotals* __restrict__ rt, const uint32_t* __restrict__ keys,
     int reuse) {
-    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long limit = (ROUTED && reuse) ? (long long)rt->n_total : n;
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;; j += (long long)gridDim.x * blockDim.x) {
     float aq = 0.f;
     RecT r;
     uint32_t key = 0xffffffffu;
-    const long long limit = (ROUTED && reuse) ? (long long)rt->n_total : n;
     bool live = j < limit;
     if (ROUTED) {
         if (live) {
@@ -207,6 +211,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(
     if (q != nullptr) {
         unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(aq));
         if ((threadIdx.x & 31) == 0 && m > sc->qmax_bits) atomicMax(&sc->qmax_bits, m);
+    }
+    if (!ROUTED || j - threadIdx.x + (long long)gridDim.x * blockDim.x >= limit) break;
     }
 }
 
@@ -272,17 +278,30 @@ struct RouteState {
     bool sent_charges = false;
 };
 
+// Flat index over the guests actually present (count[r] rows of every section r != rank, each capped at G)
+// -> row e = r * G + k of the [P][G] guest arrays; false past the end.
+__device__ __forceinline__ bool guest_row(long long flat, const uint32_t* __restrict__ count, int P, int rank,
+                                          long long G, long long& e) {
+    for (int r = 0; r < P; ++r) {
+        if (r == rank) continue;
+        const long long c = (long long)min(count[r], (uint32_t)G);
+        if (flat < c) { e = (long long)r * G + flat; return true; }
+        flat -= c;
+    }
+    return false;
+}
+constexpr int GUEST_BLOCKS = 148 * 2;      // grid of the guest passes: their work is the guest count, not P * G
+
 // charges of the guests already sent (hymd_set_charges after a sort without charges)
 template <typename real>
 __global__ void __launch_bounds__(256) route_charges_kernel(const real* __restrict__ q, int P, int rank, long long G,
                                                             RoutePeers peers, const uint32_t* __restrict__ send_count,
                                                             const int32_t* __restrict__ sent_idx) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= (long long)P * G) return;
-    const int d = (int)(e / G);
-    const long long k = e % G;
-    if (d == rank || k >= (long long)min(send_count[d], (uint32_t)G)) return;
-    reinterpret_cast<real*>(peers.q[d])[(long long)rank * G + k] = q[sent_idx[e]];
+    for (long long flat = blockIdx.x * (long long)blockDim.x + threadIdx.x;; flat += (long long)gridDim.x * blockDim.x) {
+        long long e;
+        if (!guest_row(flat, send_count, P, rank, G, e)) return;
+        reinterpret_cast<real*>(peers.q[(int)(e / G)])[(long long)rank * G + e % G] = q[sent_idx[e]];
+    }
 }
 
 template <typename real, typename RecT, typename UT, int IDX_BITS>
@@ -290,11 +309,9 @@ __global__ void __launch_bounds__(256) guest_count_kernel(
     const real* __restrict__ gpos, const int32_t* __restrict__ gtype, const uint32_t* __restrict__ recv_count,
     int P, int rank, long long G, long long n_home, SortParams p, RecT* __restrict__ gstage,
     uint32_t* __restrict__ gkeys, uint32_t* __restrict__ cnt, DeviceScalars* __restrict__ sc, unsigned int* status) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= (long long)P * G) return;
-    const int r = (int)(e / G);
-    const long long k = e % G;
-    if (r == rank || k >= (long long)min(recv_count[r], (uint32_t)G)) return;
+    for (long long flat = blockIdx.x * (long long)blockDim.x + threadIdx.x;; flat += (long long)gridDim.x * blockDim.x) {
+    long long e;
+    if (!guest_row(flat, recv_count, P, rank, G, e)) return;
     int cx, cy, cz;
     double dx, dy, dz;
     split_coord((double)gpos[3 * e + 0] * p.sx, p.Nx, cx, dx);
@@ -304,7 +321,7 @@ __global__ void __launch_bounds__(256) guest_count_kernel(
     if (lx < 0 || lx >= p.nxl) {               // cannot happen: sender and receiver use the same rule
         if (status) atomicOr(status, 4u);
         gkeys[e] = 0xffffffffu;
-        return;
+        continue;
     }
     RecT rc;
     rc.ux = pack_coord<UT>(lx, dx, p.fbx);
@@ -316,6 +333,7 @@ __global__ void __launch_bounds__(256) guest_count_kernel(
     gkeys[e] = key;
     const uint32_t c1 = atomicAdd(&cnt[key], 1u) + 1u;
     if (c1 > sc->max_cell_count) atomicMax(&sc->max_cell_count, c1);
+    }
 }
 
 template <typename real, typename RecT>
@@ -323,19 +341,18 @@ __global__ void __launch_bounds__(256) guest_scatter_kernel(
     const RecT* __restrict__ gstage, const uint32_t* __restrict__ gkeys, const real* __restrict__ gq,
     const uint32_t* __restrict__ recv_count, int P, int rank, long long G, uint32_t* __restrict__ cur,
     RecT* __restrict__ rec, real* __restrict__ q_sorted, DeviceScalars* __restrict__ sc, int with_q) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= (long long)P * G) return;
-    const int r = (int)(e / G);
-    const long long k = e % G;
-    if (r == rank || k >= (long long)min(recv_count[r], (uint32_t)G)) return;
-    const uint32_t key = gkeys[e];
-    if (key == 0xffffffffu) return;
-    const uint32_t slot = atomicAdd(&cur[key], 1u);
-    rec[slot] = gstage[e];
-    if (with_q) {
-        const real qi = gq[e];
-        q_sorted[slot] = qi;
-        atomicMax(&sc->qmax_bits, __float_as_uint(fabsf((float)qi)));
+    for (long long flat = blockIdx.x * (long long)blockDim.x + threadIdx.x;; flat += (long long)gridDim.x * blockDim.x) {
+        long long e;
+        if (!guest_row(flat, recv_count, P, rank, G, e)) return;
+        const uint32_t key = gkeys[e];
+        if (key == 0xffffffffu) continue;
+        const uint32_t slot = atomicAdd(&cur[key], 1u);
+        rec[slot] = gstage[e];
+        if (with_q) {
+            const real qi = gq[e];
+            q_sorted[slot] = qi;
+            atomicMax(&sc->qmax_bits, __float_as_uint(fabsf((float)qi)));
+        }
     }
 }
 
@@ -352,13 +369,12 @@ __global__ void __launch_bounds__(256) route_return_kernel(const real* __restric
                                                            const uint32_t* __restrict__ send_count,
                                                            const int32_t* __restrict__ sent_idx,
                                                            real* __restrict__ force) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= (long long)P * G) return;
-    const int d = (int)(e / G);
-    const long long k = e % G;
-    if (d == rank || k >= (long long)min(send_count[d], (uint32_t)G)) return;
-    real* o = force + 3 * (long long)sent_idx[e];
-    o[0] = ret[3 * e]; o[1] = ret[3 * e + 1]; o[2] = ret[3 * e + 2];
+    for (long long flat = blockIdx.x * (long long)blockDim.x + threadIdx.x;; flat += (long long)gridDim.x * blockDim.x) {
+        long long e;
+        if (!guest_row(flat, send_count, P, rank, G, e)) return;
+        real* o = force + 3 * (long long)sent_idx[e];
+        o[0] = ret[3 * e]; o[1] = ret[3 * e + 1]; o[2] = ret[3 * e + 2];
+    }
 }
 
 static int route_alloc(void** p, size_t bytes) {
@@ -436,7 +452,7 @@ static int route_gather_charges(hymd_ctx* c, const void* d_q, cudaStream_t s) {
     if (!r->sent_charges) {
         if (c->peer_busy & PEER_INBOX) HYMD_CHECK(comm_barrier(c, s));
         const long long rows = (long long)g.P * r->G;
-        route_charges_kernel<real><<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
+        route_charges_kernel<real><<<GUEST_BLOCKS, 256, 0, s>>>(
             (const real*)d_q, g.P, g.rank, r->G, r->peers, r->send_count, r->sent_idx);
         HYMD_LAUNCH_CHECK(c);
         HYMD_CHECK(comm_barrier(c, s));
@@ -471,8 +487,7 @@ int route_return(hymd_ctx* c, void* d_force, cudaStream_t s) {
     if (!r) return HYMD_OK;
     const Geometry& g = c->g;
     HYMD_CHECK(comm_barrier(c, s));                   // every rank's readout has stored its guests' rows
-    const long long rows = (long long)g.P * r->G;
-    const unsigned blocks = (unsigned)((rows + 255) / 256);
+    const unsigned blocks = GUEST_BLOCKS;
     if (c->f64) route_return_kernel<double><<<blocks, 256, 0, s>>>((const double*)r->ret, g.P, g.rank, r->G,
                                                                    r->send_count, r->sent_idx, (double*)d_force);
     else route_return_kernel<float><<<blocks, 256, 0, s>>>((const float*)r->ret, g.P, g.rank, r->G,
@@ -536,7 +551,10 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
     // stage = the buffer holding the previous sorted records (overwritten in place), out = the other
     RecT* stage = (RecT*)c->rec;
     RecT* out = (RecT*)c->rec_alt;
-    const long long span = (routed && reuse) ? n + rows : n;     // bound of the staged home records
+    // routed: the grid covers the home particles, the staged guests behind them are reached by a second
+    // (block-uniform) trip of the first blocks; at least one block so that a rank without particles of
+    // its own still retires the guests it staged last step
+    const long long span = routed ? (n > 0 ? n : 1) : n;
     const unsigned int blocks = (unsigned int)((span + 255) / 256);
     if (span > 0) {
         if (routed) {
@@ -555,7 +573,7 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
         }
         HYMD_LAUNCH_CHECK(c);
     }
-    const unsigned gblocks = (unsigned)((rows + 255) / 256);
+    const unsigned gblocks = GUEST_BLOCKS;
     if (routed) {
         // the per-destination counts ride on the barrier; after it every inbox section is complete
         HYMD_CHECK(comm_barrier_payload(c, r->send_count, s));

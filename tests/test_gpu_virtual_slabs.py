@@ -171,3 +171,13 @@ def test_guest_capacity_overflow_fails_loudly(monkeypatch):
     with pytest.raises(HymdError, match="GUEST_CAPACITY"):
         _run_and_compare(2, [32, 32, 32], 20000, np.float64, False, "scattered",
                          env={"HYMD_B200_GUEST_CAPACITY": "64"}, monkeypatch=monkeypatch)
+
+
+@pytest.mark.parametrize("mode", ["blocked", "fused", "kernels"])
+@pytest.mark.parametrize("P,mesh", [(4, [32, 32, 32]), (2, [16, 256, 256])])
+def test_exchange_modes(P, mesh, mode, monkeypatch):
+    """The three ways the FFT transposes cross NVLink (HYMD_B200_EXCHANGE, slabfft.cu): per-destination blocks
+    moved by contiguous peer copies (default), remote stores from the plane r2c / x-line epilogues, pack /
+    unpack push kernels -- same results."""
+    _run_and_compare(P, mesh, 20000, np.float32, True, "drifted", steps=2,
+                     env={"HYMD_B200_EXCHANGE": mode}, monkeypatch=monkeypatch)

@@ -98,3 +98,11 @@ def test_nccl_barrier_fallback():
     """HYMD_B200_NCCL_BARRIER=1: the round-1 all-reduce barrier instead of flags in peer memory."""
     _need(2)
     _run(2, ["--dtype", "f32", "--pme", "--route", "--mesh", "32", "32", "32"], {"HYMD_B200_NCCL_BARRIER": "1"})
+
+
+@pytest.mark.parametrize("mode", ["fused", "kernels"])
+def test_exchange_modes_over_nvlink(mode):
+    """HYMD_B200_EXCHANGE: the non-default transposes (remote stores from the kernels' epilogues, pack / unpack
+    push kernels) over real peer memory."""
+    _need(2)
+    _run(2, ["--dtype", "f32", "--pme", "--mesh", "32", "32", "32"], {"HYMD_B200_EXCHANGE": mode})

@@ -1,0 +1,27 @@
+#!/bin/bash
+# 8-GPU pass: routing test at 8 ranks, C4 strong (exchange modes), C4 weak, C5 strong (+ parity vs the oracle)
+TAG=${1:-r2s}; N=${2:-8}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi -L > $OUT/gpus.txt
+run() {  # name, env..., -- then bench args after "--"
+  name=$1; shift
+  envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+    bench.py --gpus $N "$@" > $OUT/bench_$name.json 2> $OUT/bench_$name.err; echo "bench $name exit $?"
+  python - <<PY
+import json
+try:
+    t = open("$OUT/bench_$name.json").read(); d = json.loads(t[t.index('{"metric"'):].splitlines()[0])
+    print("$name", round(d["ms_per_step"], 4), "%.3e" % d["value"], d["parity"])
+    print("   ", {k: round(v["ms_per_step"], 4) for k, v in d["phases"].items()})
+except Exception as e:
+    print("$name ERR", e); print(open("$OUT/bench_$name.err").read()[-1500:])
+PY
+}
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 \
+    tests/mgpu_worker.py --dtype f32 --pme --route --mesh 64 64 64 --particles 60000 > $OUT/route_test.log 2>&1; echo "route test exit $?"; tail -2 $OUT/route_test.log
+run c4_blocked HYMD_B200_EXCHANGE=blocked -- --steps 30 --warmup 5 --no-e2e
+run c4_fused HYMD_B200_EXCHANGE=fused -- --steps 30 --warmup 5 --no-e2e
+run c4_weak X=1 -- --steps 20 --warmup 5 --no-e2e --scaling weak
+run c5_strong X=1 -- --steps 10 --warmup 3 --no-e2e --workload C5 --parity-max-n 200000000

@@ -251,6 +251,7 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
         if (xm && xm[0] == 'k') c->xmode = 0;
     }
     c->fused_push = c->xmode == 1;
+    c->xcopy_kernel = !(xm && strcmp(xm, "blockedm") == 0);     // "blockedm": cudaMemcpyAsync (copy engines)
     if ((st = readout_setup(c))) return fail(st);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(HYMD_ERR_CUDA);
     *out = c;

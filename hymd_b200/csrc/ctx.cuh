@@ -220,6 +220,7 @@ struct hymd_ctx {
     int xmode;              // how the FFT transposes cross NVLink (slabfft.cu): 0 pack / unpack push kernels,
                             // 1 stores issued by the plane r2c / x-line kernels, 2 blocked layouts + contiguous peer copies
     bool fused_push;        // xmode == 1
+    bool xcopy_kernel;      // xmode == 2: the blocks are moved by an SM copy kernel instead of the copy engines
     bool xpushed;           // the x-line kernel has already stored its output into the peers' work buffers
     unsigned peer_busy;     // PEER_* buffers whose local consumers were enqueued after the last barrier:
                             // a peer may not overwrite them before another barrier (same call sequence

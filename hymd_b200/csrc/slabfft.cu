@@ -257,6 +257,33 @@ __global__ void __launch_bounds__(256) unpack_push_kernel(const vec* __restrict_
     }
 }
 
+// Blocked exchange with SM copies (HYMD_B200_EXCHANGE=blockedk): block q of `src` (contiguous, `block16` 16-byte
+// words) goes to dst.p[q] + dst_off16; every SM streams to every peer at once, 16 bytes per lane, four loads in
+// flight per thread (the pattern that reaches 700+ GB/s per direction in tools/microbench/p2p.cu).
+__global__ void __launch_bounds__(256) block_copy_kernel(const uint4* __restrict__ src, PeerPtrs dst, long long block16,
+                                                         long long dst_off16, int P, int rank, int include_self) {
+    // blockIdx.y = which peer (all peers are written at the same time, each by gridDim.x CTAs)
+    const int q = (rank + (int)blockIdx.y + (include_self ? 0 : 1)) % P;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const uint4* s = src + (long long)q * block16;
+    uint4* d = reinterpret_cast<uint4*>(dst.p[q]) + dst_off16;
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; j + 3 * stride < block16; j += 4 * stride) {
+        const uint4 a = __ldcs(s + j), b = __ldcs(s + j + stride), c2 = __ldcs(s + j + 2 * stride), e = __ldcs(s + j + 3 * stride);
+        d[j] = a; d[j + stride] = b; d[j + 2 * stride] = c2; d[j + 3 * stride] = e;
+    }
+    for (; j < block16; j += stride) d[j] = __ldcs(s + j);
+}
+
+// grid of the block copy: ~148 x 8 CTAs in total, split over the peers; CTAs per peer bounded by the block size
+static dim3 block_copy_grid(long long block16, int npeers) {
+    long long per = (148LL * 8 + npeers - 1) / npeers;
+    const long long need = (block16 + 4 * 256 - 1) / (4 * 256);
+    if (per > need) per = need;
+    if (per < 1) per = 1;
+    return dim3((unsigned)per, (unsigned)npeers, 1);
+}
+
 static int peer_table(hymd_ctx* c, void* local, PeerPtrs* t, cudaStream_t s) {
     memset(t, 0, sizeof(*t));
     return comm_peer_ptrs(c, local, t->p, s);
@@ -400,12 +427,19 @@ int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t 
             T.p[q] = q == g.rank ? k_out : (char*)c->wS + ((long long)q * block - (long long)g.x0 * l.xs) * (long long)csz;
         HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p));
         PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
-        for (int i = 1; i < g.P; ++i) {
-            const int q = (g.rank + i) % g.P;
-            HYMD_CUDA(cudaMemcpyAsync((char*)K.p[q] + (size_t)g.x0 * l.xs * csz, (char*)c->wS + (size_t)q * block * csz,
-                                      (size_t)block * csz, cudaMemcpyDeviceToDevice, s));
+        if (c->xcopy_kernel && (block * csz) % 16 == 0) {
+            block_copy_kernel<<<block_copy_grid(block * csz / 16, g.P - 1), 256, 0, s>>>(
+                (const uint4*)c->wS, K, (long long)(block * csz / 16), (long long)((size_t)g.x0 * l.xs * csz / 16),
+                g.P, g.rank, 0);
+            HYMD_LAUNCH_CHECK(c);
+        } else {
+            for (int i = 1; i < g.P; ++i) {
+                const int q = (g.rank + i) % g.P;
+                HYMD_CUDA(cudaMemcpyAsync((char*)K.p[q] + (size_t)g.x0 * l.xs * csz, (char*)c->wS + (size_t)q * block * csz,
+                                          (size_t)block * csz, cudaMemcpyDeviceToDevice, s));
+            }
+            c->launches += g.P - 1;
         }
-        c->launches += g.P - 1;
         HYMD_CHECK(comm_barrier(c, s));
         c->peer_busy |= PEER_K;
         return HYMD_OK;
@@ -455,12 +489,19 @@ int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost
             PeerPtrs W;
             HYMD_CHECK(peer_table(c, c->wA, &W, s));
             HYMD_CHECK(peer_acquire(c, PEER_WORK, s));
-            for (int i = 0; i < g.P; ++i) {
-                const int q = (g.rank + i) % g.P;
-                HYMD_CUDA(cudaMemcpyAsync((char*)W.p[q] + (size_t)g.rank * block * csz, (char*)k_in + (size_t)q * block * csz,
-                                          (size_t)block * csz, cudaMemcpyDeviceToDevice, s));
+            if (c->xcopy_kernel && (block * csz) % 16 == 0) {
+                block_copy_kernel<<<block_copy_grid(block * csz / 16, g.P), 256, 0, s>>>(
+                    (const uint4*)k_in, W, (long long)(block * csz / 16), (long long)((size_t)g.rank * block * csz / 16),
+                    g.P, g.rank, 1);
+                HYMD_LAUNCH_CHECK(c);
+            } else {
+                for (int i = 0; i < g.P; ++i) {
+                    const int q = (g.rank + i) % g.P;
+                    HYMD_CUDA(cudaMemcpyAsync((char*)W.p[q] + (size_t)g.rank * block * csz, (char*)k_in + (size_t)q * block * csz,
+                                              (size_t)block * csz, cudaMemcpyDeviceToDevice, s));
+                }
+                c->launches += g.P;
             }
-            c->launches += g.P;
             HYMD_CHECK(comm_barrier(c, s));
             c->peer_busy |= PEER_WORK;
             return plane_inverse(c, c->wA, 0, F, g.nxl, real_out, ghost, derive, s, true);

@@ -19,9 +19,6 @@ except Exception as e:
     print("$name ERR", e); print(open("$OUT/bench_$name.err").read()[-1500:])
 PY
 }
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 \
-    tests/mgpu_worker.py --dtype f32 --pme --route --mesh 64 64 64 --particles 60000 > $OUT/route_test.log 2>&1; echo "route test exit $?"; tail -2 $OUT/route_test.log
-run c4_blocked HYMD_B200_EXCHANGE=blocked -- --steps 30 --warmup 5 --no-e2e
-run c4_fused HYMD_B200_EXCHANGE=fused -- --steps 30 --warmup 5 --no-e2e
+run c4_blocked X=1 -- --steps 30 --warmup 5
 run c4_weak X=1 -- --steps 20 --warmup 5 --no-e2e --scaling weak
-run c5_strong X=1 -- --steps 10 --warmup 3 --no-e2e --workload C5 --parity-max-n 200000000
+run c5_strong X=1 -- --steps 10 --warmup 3 --no-e2e --workload C5

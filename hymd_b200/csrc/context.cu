@@ -252,6 +252,19 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     }
     c->fused_push = c->xmode == 1;
     c->xcopy_kernel = !(xm && strcmp(xm, "blockedm") == 0);     // "blockedm": cudaMemcpyAsync (copy engines)
+    // pipelined blocked exchange (slabfft.cu): HYMD_B200_XPIPE = 0 off, 1 when the pieces are large (default), 2 always
+    c->xpipe = 0; c->xstream = nullptr; c->plane_sm_reserve = 0;
+    if (c->xmode == 2 && c->xcopy_kernel) {
+        const char* xp = getenv("HYMD_B200_XPIPE");
+        c->xpipe = xp ? atoi(xp) : 1;
+        if (c->xpipe) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);       // lo = the numerically greatest = lowest priority
+            if (cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, lo) != cudaSuccess) return fail(HYMD_ERR_CUDA);
+            for (auto& e : c->xev)
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(HYMD_ERR_CUDA);
+        }
+    }
     if ((st = readout_setup(c))) return fail(st);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(HYMD_ERR_CUDA);
     *out = c;
@@ -273,6 +286,11 @@ int hymd_ctx_destroy(hymd_ctx* c) {
                     c->wA, c->wS, c->halo, c->ytw, c->ztw, c->plane_scratch};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    if (c->xstream) {
+        for (auto& e : c->xev)
+            if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(c->xstream);
+    }
     if (c->ev_open) {
         for (auto& iv : *c->ev_open) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
         delete c->ev_open;

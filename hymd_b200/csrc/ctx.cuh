@@ -221,6 +221,12 @@ struct hymd_ctx {
                             // 1 stores issued by the plane r2c / x-line kernels, 2 blocked layouts + contiguous peer copies
     bool fused_push;        // xmode == 1
     bool xcopy_kernel;      // xmode == 2: the blocks are moved by an SM copy kernel instead of the copy engines
+    // xmode == 2, pipelined exchange (slabfft.cu): the copies of field f run on a second, low-priority stream while
+    // the plane kernel transforms field f + 1 (forward) / row u - 1 (inverse)
+    int xpipe;              // 0 off, 1 on when a field's block is large enough, 2 always (tests)
+    int plane_sm_reserve;   // > 0 while the pipeline runs: the persistent plane kernels leave this many SMs to the copies
+    cudaStream_t xstream;
+    cudaEvent_t xev[2 * HYMD_MAX_TYPES + 2];
     bool xpushed;           // the x-line kernel has already stored its output into the peers' work buffers
     unsigned peer_busy;     // PEER_* buffers whose local consumers were enqueued after the last barrier:
                             // a peer may not overwrite them before another barrier (same call sequence
@@ -304,10 +310,11 @@ int halo_reduce(hymd_ctx* c, void* fields, int F, cudaStream_t s);
 int halo_fetch(hymd_ctx* c, void* ghost_meshes, int F, cudaStream_t s);
 // planefft.cu
 bool plane_supported(const hymd_ctx* c);
+// f0, nf: only fields (derive: potential rows) f0 .. f0 + nf - 1 of the F-field layouts (nf < 0: all from f0)
 int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int nplanes, void* k_out,
-                  long long k_fs, cudaStream_t s, void* const* push_peers = nullptr);
+                  long long k_fs, cudaStream_t s, void* const* push_peers = nullptr, int f0 = 0, int nf = -1);
 int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int nplanes, void* real_out,
-                  bool ghost, bool derive, cudaStream_t s, bool blocked = false);
+                  bool ghost, bool derive, cudaStream_t s, bool blocked = false, int f0 = 0, int nf = -1);
 // xline.cu
 bool xline_supported(const hymd_ctx* c);
 int xline_forces(hymd_ctx* c, const void* in, void* fout, void* vout, void* pfout, cudaStream_t s,

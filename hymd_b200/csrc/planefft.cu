@@ -147,6 +147,8 @@ __device__ __forceinline__ double shfl(double v, int lane) { return __shfl_sync(
 
 struct PlaneParams {
     int nunits, nplanes;            // units = fields x planes
+    int f0;                         // first field (potential row in derive mode) of this launch: the slab pipeline
+                                    // transforms field by field while the previous field crosses NVLink
     long long k_fs, k_xs;           // complex strides (field, plane) of the spectra, row pitch Nzcp
     long long r_fs, r_xs;           // real strides (field, plane)
     int r_ys;                       // real row pitch
@@ -171,6 +173,7 @@ struct PlaneParams {
     // row ky of plane x, spectrum f  ->  in + (ky >> nyl_shift) blk_q + x blk_x + f blk_f + (ky & (nyl-1)) Nzcp
     int blk_in;
     long long blk_q, blk_x, blk_f;
+    long long blk_d;                // blk_q - nyl Nzcp: what crossing into the next block adds to a row offset
 };
 
 // first element of spectrum row ky (plane x, spectrum f) of the inverse kernels' input
@@ -181,6 +184,21 @@ __device__ __forceinline__ const Cx<real>* in_row(const Cx<real>* __restrict__ i
         return in + (long long)(ky >> p.nyl_shift) * p.blk_q + (long long)x * p.blk_x + (long long)f * p.blk_f +
                (long long)(ky & ((1 << p.nyl_shift) - 1)) * nzcp;
     return in + f * p.k_fs + x * p.k_xs + (long long)ky * nzcp;
+}
+
+// The column phase of the inverse kernels reads, per thread, rows k1 + R k2 (k2 = 0 .. R2-1) of one plane.  Their
+// addresses are one base pointer (row k1: in_row, once per transform) plus row_step: a compile-time multiple of the
+// row pitch -- an immediate of the load instruction -- and, for the blocked layout only, the block term.  (It was
+// ~17 integer instructions and a branch per 8-byte load, as many as the butterflies themselves: profiles/r2_sass_tmem.md.)
+template <bool BLK, int R, int NZCP_>
+__device__ __forceinline__ long long row_step(int k1, int k2, int q0, int blk_shift, long long blk_d) {
+    long long o = (long long)k2 * (R * NZCP_);
+    if (BLK) {
+        int q = ((k1 + R * k2) >> blk_shift) - q0;
+        asm volatile("" : "+r"(q));        // evaluated at the load: sixteen hoisted 64-bit offsets would spill
+        o += (long long)q * blk_d;
+    }
+    return o;
 }
 
 // Work decomposition inside the 512-thread CTA.
@@ -224,7 +242,7 @@ template <typename real, int NY, int NZ, int NT_, int TILES> struct PlaneCfg {
 };
 
 // ---- inverse: spectra [ky][kz] -> real plane ------------------------------------------------------
-template <typename real, int NY, int NZ, int NTH, int TILES>
+template <typename real, int NY, int NZ, int NTH, int TILES, bool BLK>
 __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
     const Cx<real>* __restrict__ in, Cx<real>* __restrict__ scratch, real* __restrict__ out,
     const Cx<real>* __restrict__ twy_g, const Cx<real>* __restrict__ twz_g, PlaneParams p) {
@@ -275,8 +293,10 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
 
     const int ND = p.derive ? 3 : 1;
     const real dky = (real)p.dky, dkz = (real)p.dkz;
+    const int blk_shift = BLK ? p.nyl_shift : 0;
+    const long long blk_d = BLK ? p.blk_d : 0;
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
-      const int fu = unit / p.nplanes, x = unit % p.nplanes;
+      const int fu = unit / p.nplanes + p.f0, x = unit % p.nplanes;
       for (int d = 0; d < ND; ++d) {
         // derive: d = 1, 2 read the same spectrum plane (the second time from L2)
         const int fin = p.derive ? 2 * fu + (d > 0 ? 1 : 0) : fu;
@@ -311,10 +331,12 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_c2r_kernel(
             auto load_chunk = [&](int ch, int task, Cx<real> (&dst)[R2y]) {
                 const int c = task % CG, k1 = task / CG;
                 const bool valid = ch < NCHG && task < CG * R1y && ch * CG + c < NZC;
+                const Cx<real>* e0 = in_row<real>(in, p, fin, x, k1, NZCP) + ch * CG + c;
+                const int q0 = k1 >> blk_shift;
 #pragma unroll
                 for (int k2 = 0; k2 < R2y; ++k2)
                 {
-                    const Cx<real>* e = in_row<real>(in, p, fin, x, k1 + R1y * k2, NZCP) + ch * CG + c;
+                    const Cx<real>* e = e0 + row_step<BLK, R1y, NZCP>(k1, k2, q0, blk_shift, blk_d);
                     // derive: the plane read for the k_y component is read again for k_z: keep it in L2
                     dst[k2] = valid ? (mode == 1 ? ld_l2(e) : ld_stream(e)) : Cx<real>{0, 0};
                 }
@@ -584,7 +606,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) plane_r2c_kernel(
     if constexpr (REGC) twc.init(twy, (gt / CG) % R2y, NY);
 
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
-        const int f = unit / p.nplanes, x = unit % p.nplanes;
+        const int f = unit / p.nplanes + p.f0, x = unit % p.nplanes;
         const real* src = in + f * p.r_fs + x * p.r_xs;
         // ---------------- row phase: one complex FFT along z per row pair (a + ib) ----------------
         // (the plane comes from HBM: the next pass's inputs are loaded into a second register set
@@ -808,6 +830,9 @@ struct TmMap {
     }
 };
 
+// BSH: rows k1 + 16 k2 (k1 < 16) of the input lie in block k2 >> BSH of the blocked layout (Ny / P = 16 << BSH rows
+// per block); BSH = 4: the plain layout (one block).
+template <int BSH>
 __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
     const Cx<float>* __restrict__ in, float* __restrict__ out, const Cx<float>* __restrict__ twy_g,
     const Cx<float>* __restrict__ twz_g, PlaneParams p) {
@@ -833,7 +858,7 @@ __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
     const real dky = (real)p.dky, dkz = (real)p.dkz;
 
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
-      const int fu = unit / p.nplanes, x = unit % p.nplanes;
+      const int fu = unit / p.nplanes + p.f0, x = unit % p.nplanes;
       for (int d = 0; d < ND; ++d) {
         const int fin = p.derive ? 2 * fu + (d > 0 ? 1 : 0) : fu;
         const int f = p.derive ? 3 * fu + d : fu;
@@ -858,12 +883,13 @@ __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
         };
         // ---------------- column phase: inverse FFT along y, super-chunks 0..3 = columns 0..127, 4 = Nyquist ----
         Cx<real> nx[R];
+        // row a_k1, column a_c of the input plane; rows a_k1 + 16 k2 and the column blocks follow by immediates
+        const Cx<real>* cbase = in_row<real>(in, p, fin, x, a_k1, NZCP) + a_c;
         auto load_chunk = [&](int sc, Cx<real> (&dst)[R]) {
-            const int col = sc * CS + a_c;
             const bool valid = sc < 4 || (sc == 4 && a_c == 0);
 #pragma unroll
             for (int k2 = 0; k2 < R; ++k2) {
-                const Cx<real>* e = in_row<real>(in, p, fin, x, a_k1 + R * k2, NZCP) + col;
+                const Cx<real>* e = cbase + sc * CS + (k2 * (R * NZCP) + (long long)(k2 >> BSH) * p.blk_d);
                 dst[k2] = valid ? (mode == 1 ? ld_l2(e) : ld_stream(e)) : Cx<real>{0, 0};
             }
         };
@@ -873,9 +899,10 @@ __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
         const int nyq_cols = p.derive ? 2 : 1;
         auto load_nyq = [&](Cx<real> (&dst)[R]) {
             const int fn = p.derive ? 2 * fu + (a_c < nyq_cols ? a_c : 0) : fin;
+            const Cx<real>* nbase = in_row<real>(in, p, fn, x, a_k1, NZCP) + NZ / 2;
 #pragma unroll
             for (int k2 = 0; k2 < R; ++k2)
-                dst[k2] = a_c < nyq_cols ? ld_l2(in_row<real>(in, p, fn, x, a_k1 + R * k2, NZCP) + NZ / 2) : Cx<real>{0, 0};
+                dst[k2] = a_c < nyq_cols ? ld_l2(nbase + (k2 * (R * NZCP) + (long long)(k2 >> BSH) * p.blk_d)) : Cx<real>{0, 0};
         };
         load_chunk(0, nx);
         // rounds 0..3 (compile-time round index: the prefetch target, the TMEM columns and the tile buffer fold)
@@ -1030,7 +1057,7 @@ __global__ void __launch_bounds__(512, 1) plane_r2c_tmem_kernel(
     const int b_c = lane, b_k1 = warp;      // last column stage: (column, k1)
 
     for (int unit = blockIdx.x; unit < p.nunits; unit += gridDim.x) {
-        const int f = unit / p.nplanes, x = unit % p.nplanes;
+        const int f = unit / p.nplanes + p.f0, x = unit % p.nplanes;
         const real* src = in + f * p.r_fs + x * p.r_xs;
         // ---------------- row phase: one complex FFT along z per row pair (a + ib) ----------------
         Cx<real> nx[R];
@@ -1147,6 +1174,7 @@ static int launch_plane_tmem(hymd_ctx* c, bool inverse, const void* in, void* ou
     int sms = 0;
     HYMD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev));
     int grid = sms;                     // one CTA per SM: it owns the SM's whole tensor memory
+    if (c->plane_sm_reserve > 0 && grid > sms - c->plane_sm_reserve) grid = sms - c->plane_sm_reserve;
     if (grid > p_in.nunits) grid = p_in.nunits;
     if (grid < 1) return HYMD_OK;
     PlaneParams p = p_in;
@@ -1156,9 +1184,13 @@ static int launch_plane_tmem(hymd_ctx* c, bool inverse, const void* in, void* ou
     if (const char* e = getenv("HYMD_B200_TMEM_DBUF")) p.scr_alt = atoi(e) != 0;
     const size_t smem = p.scr_alt ? TM_SMEM_DBUF : TM_SMEM;
     if (inverse) {
-        HYMD_CUDA(cudaFuncSetAttribute(plane_c2r_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        plane_c2r_tmem_kernel<<<grid, 512, smem, s>>>((const Cx<float>*)in, (float*)out, (const Cx<float>*)c->ytw,
-                                                         (const Cx<float>*)c->ztw, p);
+        const int bsh = p.blk_in ? p.nyl_shift - 4 : 4;
+        if (bsh < 0 || bsh > 4) { set_error("tensor-memory c2r: blocked input needs 16 <= Ny / P"); return HYMD_ERR_INVALID; }
+        auto kern = bsh == 0 ? plane_c2r_tmem_kernel<0> : bsh == 1 ? plane_c2r_tmem_kernel<1> : bsh == 2 ? plane_c2r_tmem_kernel<2>
+                  : bsh == 3 ? plane_c2r_tmem_kernel<3> : plane_c2r_tmem_kernel<4>;
+        HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 512, smem, s>>>((const Cx<float>*)in, (float*)out, (const Cx<float>*)c->ytw,
+                                     (const Cx<float>*)c->ztw, p);
     } else {
         HYMD_CUDA(cudaFuncSetAttribute(plane_r2c_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         plane_r2c_tmem_kernel<<<grid, 512, smem, s>>>((const float*)in, (Cx<float>*)out, (const Cx<float>*)c->ytw,
@@ -1225,6 +1257,7 @@ static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParam
     int sms = 0;
     HYMD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev));
     int grid = sms * Cfg::CTAS;
+    if (c->plane_sm_reserve > 0 && sms > c->plane_sm_reserve) grid = (sms - c->plane_sm_reserve) * Cfg::CTAS;
     if (const char* e = getenv("HYMD_B200_PLANE_GRID")) grid = atoi(e) > 0 ? atoi(e) : grid;   // tuning
     if (grid > p.nunits) grid = p.nunits;
     if (grid < 1) return HYMD_OK;
@@ -1236,7 +1269,7 @@ static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParam
     }
     if ((size_t)grid * N * Cfg::NZCP * sizeof(Cx<real>) > c->plane_scratch_bytes) grid = 2 * sms;
     if (INVERSE) {
-        auto kern = plane_c2r_kernel<real, N, N, NTH, TILES>;
+        auto kern = p.blk_in ? plane_c2r_kernel<real, N, N, NTH, TILES, true> : plane_c2r_kernel<real, N, N, NTH, TILES, false>;
         size_t smem = Cfg::smem_inv((p.row_tma & 2) != 0);
         if (const char* e = getenv("HYMD_B200_PLANE_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;   // L1 carve-out experiment
         HYMD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1284,7 +1317,7 @@ static int dispatch_plane(hymd_ctx* c, const void* in, void* out, const PlanePar
 
 // real [f][plane][Ny][Nz] (strides r_*) -> spectra [f][plane][Ny][Nzcp] (strides k_*)
 int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int nplanes, void* k_out,
-                  long long k_fs, cudaStream_t s, void* const* push_peers) {
+                  long long k_fs, cudaStream_t s, void* const* push_peers, int f0, int nf) {
     const Geometry& g = c->g;
     PlaneParams p;
     memset(&p, 0, sizeof(p));
@@ -1296,7 +1329,8 @@ int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int n
         p.push = 1; p.nyl_shift = sh; p.x0 = g.x0; p.pk_xs = l.xs; p.pk_fs = l.fs;
         for (int q = 0; q < g.P; ++q) p.peer[q] = push_peers[q];
     }
-    p.nunits = F * nplanes; p.nplanes = nplanes;
+    if (nf < 0) nf = F - f0;          // fields f0 .. f0 + nf - 1 of the F-field layouts
+    p.nunits = nf * nplanes; p.nplanes = nplanes; p.f0 = f0;
     p.k_fs = k_fs; p.k_xs = (long long)g.Ny * g.Nzcp;
     p.r_fs = r_fs; p.r_xs = (long long)g.Ny * g.Nz; p.r_ys = g.Nz;
     p.ghost = 0; p.xdup_plane = -1; p.derive = 0; p.dky = p.dkz = 0; p.row_tma = 0; p.scr_alt = 0;
@@ -1311,7 +1345,7 @@ int plane_forward(hymd_ctx* c, const void* real_in, long long r_fs, int F, int n
 // derive: k_in holds 2F/3 spectra (per potential row: -i k_x V and -i V, x-inverted) and the
 // kernel forms the k_y / k_z components itself (PlaneParams::derive).
 int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int nplanes, void* real_out,
-                  bool ghost, bool derive, cudaStream_t s, bool blocked) {
+                  bool ghost, bool derive, cudaStream_t s, bool blocked, int f0, int nf) {
     const Geometry& g = c->g;
     PlaneParams p;
     memset(&p, 0, sizeof(p));
@@ -1322,9 +1356,11 @@ int plane_inverse(hymd_ctx* c, const void* k_in, long long k_fs, int F, int npla
         if ((1 << sh) != g.nyl) { set_error("blocked inverse transpose needs a power-of-two Ny / P"); return HYMD_ERR_INVALID; }
         p.blk_in = 1; p.nyl_shift = sh;
         p.blk_f = (long long)g.nyl * g.Nzcp; p.blk_x = Fin * p.blk_f; p.blk_q = g.nxl * p.blk_x;
+        p.blk_d = p.blk_q - (long long)g.nyl * g.Nzcp;
     }
     if (derive && F % 3 != 0) { set_error("plane_inverse: derive needs 3 outputs per row"); return HYMD_ERR_INVALID; }
-    p.nunits = (derive ? F / 3 : F) * nplanes; p.nplanes = nplanes;
+    if (nf < 0) nf = (derive ? F / 3 : F) - f0;      // fields (derive: potential rows) f0 .. f0 + nf - 1
+    p.nunits = nf * nplanes; p.nplanes = nplanes; p.f0 = f0;
     p.derive = derive ? 1 : 0;
     p.dky = 2.0 * M_PI / g.box[1]; p.dkz = 2.0 * M_PI / g.box[2];
     p.row_tma = 1;

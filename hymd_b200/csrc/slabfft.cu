@@ -284,6 +284,57 @@ static dim3 block_copy_grid(long long block16, int npeers) {
     return dim3((unsigned)per, (unsigned)npeers, 1);
 }
 
+// Pipelined exchange: the part of every per-destination block that belongs to ONE field (forward) or one potential
+// row (inverse) -- inside block q that is `nseg` segments (one per local x plane) of seg16 16-byte words, stride16
+// apart, starting off16 into the block.  Same roles of src / dst / include_self as block_copy_kernel.  A small fixed
+// grid (16 SMs' worth): it runs beside the plane kernel that transforms the next field.
+__global__ void __launch_bounds__(256) block_copy2d_kernel(const uint4* __restrict__ src, PeerPtrs dst, long long block16,
+                                                           long long dst_off16, long long off16, unsigned int seg16,
+                                                           long long stride16, unsigned int nseg, int P, int rank,
+                                                           int include_self) {
+    const int q = (rank + (int)blockIdx.y + (include_self ? 0 : 1)) % P;
+    const uint4* s = src + (long long)q * block16 + off16;
+    uint4* d = reinterpret_cast<uint4*>(dst.p[q]) + dst_off16 + off16;
+    const unsigned int total = seg16 * nseg, stride = gridDim.x * blockDim.x;
+    auto at = [&](unsigned int w) { return (long long)(w / seg16) * stride16 + (w % seg16); };
+    unsigned int w = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; w + 3ull * stride < total; w += 4 * stride) {
+        const long long o0 = at(w), o1 = at(w + stride), o2 = at(w + 2 * stride), o3 = at(w + 3 * stride);
+        const uint4 a = __ldcs(s + o0), b = __ldcs(s + o1), c2 = __ldcs(s + o2), e = __ldcs(s + o3);
+        d[o0] = a; d[o1] = b; d[o2] = c2; d[o3] = e;
+    }
+    for (; w < total; w += stride) { const long long o = at(w); d[o] = __ldcs(s + o); }
+}
+
+// Is the per-field piece of a block big enough for the pipeline to pay?  (Every piece costs two launches and an
+// event; below ~4 MB the exchange is latency, not bandwidth.)
+static bool pipe_pieces(const hymd_ctx* c, long long piece_bytes, int pieces) {
+    if (c->xpipe == 0 || pieces < 2 || c->xstream == nullptr || piece_bytes % 16 != 0) return false;
+    return c->xpipe == 2 || piece_bytes >= (4LL << 20);
+}
+
+// while alive, the persistent plane kernels keep 16 SMs free for the copy kernel of the second stream
+struct SmReserve {
+    hymd_ctx* c;
+    explicit SmReserve(hymd_ctx* ctx) : c(ctx) { c->plane_sm_reserve = 16; }
+    ~SmReserve() { c->plane_sm_reserve = 0; }
+};
+
+static int launch_copy2d(hymd_ctx* c, const void* src, const PeerPtrs& dst, long long block16, long long dst_off16,
+                         long long off16, long long seg16, long long stride16, int nseg, int npeers, int include_self,
+                         cudaStream_t s) {
+    if (seg16 * nseg >= (1LL << 32)) { set_error("pipelined exchange: piece too large"); return HYMD_ERR_INVALID; }
+    long long per = 128 / npeers;                       // ~128 CTAs in total
+    const long long need = (seg16 * nseg + 4 * 256 - 1) / (4 * 256);
+    if (per > need) per = need;
+    if (per < 1) per = 1;
+    block_copy2d_kernel<<<dim3((unsigned)per, (unsigned)npeers, 1), 256, 0, s>>>(
+        (const uint4*)src, dst, block16, dst_off16, off16, (unsigned int)seg16, stride16, (unsigned int)nseg,
+        c->g.P, c->g.rank, include_self);
+    HYMD_LAUNCH_CHECK(c);
+    return HYMD_OK;
+}
+
 static int peer_table(hymd_ctx* c, void* local, PeerPtrs* t, cudaStream_t s) {
     memset(t, 0, sizeof(*t));
     return comm_peer_ptrs(c, local, t->p, s);
@@ -425,6 +476,25 @@ int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t 
         HYMD_CHECK(peer_acquire(c, PEER_K, s));
         for (int q = 0; q < g.P; ++q)
             T.p[q] = q == g.rank ? k_out : (char*)c->wS + ((long long)q * block - (long long)g.x0 * l.xs) * (long long)csz;
+        const long long piece = (long long)g.nxl * l.fs * (long long)csz;       // bytes of one field inside a block
+        if (pipe_pieces(c, piece, F) && (l.fs * csz) % 16 == 0) {
+            // field f crosses NVLink (second stream) while the plane kernel transforms field f + 1
+            SmReserve reserve(c);
+            for (int f = 0; f < F; ++f) {
+                HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p, f, 1));
+                HYMD_CUDA(cudaEventRecord(c->xev[f], s));
+                HYMD_CUDA(cudaStreamWaitEvent(c->xstream, c->xev[f], 0));
+                HYMD_CHECK(launch_copy2d(c, c->wS, K, (long long)(block * csz / 16), (long long)((size_t)g.x0 * l.xs * csz / 16),
+                                         (long long)((size_t)f * l.fs * csz / 16), (long long)(l.fs * csz / 16),
+                                         (long long)(l.xs * csz / 16), g.nxl, g.P - 1, 0, c->xstream));
+            }
+            PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+            HYMD_CUDA(cudaEventRecord(c->xev[F], c->xstream));
+            HYMD_CUDA(cudaStreamWaitEvent(s, c->xev[F], 0));
+            HYMD_CHECK(comm_barrier(c, s));
+            c->peer_busy |= PEER_K;
+            return HYMD_OK;
+        }
         HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p));
         PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
         if (c->xcopy_kernel && (block * csz) % 16 == 0) {
@@ -484,10 +554,41 @@ int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost
             // blocked exchange: the x-range of rank q is one contiguous block of the k layout; it is copied as
             // it is into block `rank` of q's work buffer, and the plane kernel reads W[q][x][f][kyl][kz]
             const size_t csz = 2 * c->rsz;
-            const long long block = (long long)g.nxl * klayout(c, Fin).xs;
-            PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+            const KLayout lk = klayout(c, Fin);
+            const long long block = (long long)g.nxl * lk.xs;
             PeerPtrs W;
             HYMD_CHECK(peer_table(c, c->wA, &W, s));
+            const int U = derive ? F / 3 : 0;
+            const long long piece = 2LL * g.nxl * lk.fs * (long long)csz;       // bytes of one potential row inside a block
+            if (derive && pipe_pieces(c, piece, U) && (lk.fs * csz) % 16 == 0) {
+                // the two spectra of potential row u cross NVLink (second stream) while the plane kernel turns row
+                // u - 1 into its three force meshes; one barrier per row tells every rank that the row has landed
+                {
+                    PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+                    HYMD_CHECK(peer_acquire(c, PEER_WORK, s));
+                    HYMD_CUDA(cudaEventRecord(c->xev[0], s));                   // the x-line kernel has written k_in
+                    HYMD_CUDA(cudaStreamWaitEvent(c->xstream, c->xev[0], 0));
+                    for (int u = 0; u < U; ++u) {
+                        HYMD_CHECK(launch_copy2d(c, k_in, W, (long long)(block * csz / 16),
+                                                 (long long)((size_t)g.rank * block * csz / 16),
+                                                 (long long)((size_t)2 * u * lk.fs * csz / 16), (long long)(2 * lk.fs * csz / 16),
+                                                 (long long)(lk.xs * csz / 16), g.nxl, g.P, 1, c->xstream));
+                        HYMD_CUDA(cudaEventRecord(c->xev[1 + u], c->xstream));
+                    }
+                }
+                SmReserve reserve(c);
+                for (int u = 0; u < U; ++u) {
+                    {
+                        PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+                        HYMD_CUDA(cudaStreamWaitEvent(s, c->xev[1 + u], 0));
+                        HYMD_CHECK(comm_barrier(c, s));
+                    }
+                    HYMD_CHECK(plane_inverse(c, c->wA, 0, F, g.nxl, real_out, ghost, derive, s, true, u, 1));
+                }
+                c->peer_busy |= PEER_WORK;
+                return HYMD_OK;
+            }
+            PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
             HYMD_CHECK(peer_acquire(c, PEER_WORK, s));
             if (c->xcopy_kernel && (block * csz) % 16 == 0) {
                 block_copy_kernel<<<block_copy_grid(block * csz / 16, g.P), 256, 0, s>>>(

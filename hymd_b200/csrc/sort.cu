@@ -26,13 +26,19 @@ struct SortParams {
 __device__ __forceinline__ void split_coord(double x, int n, int& cell, double& frac) {
     double f = floor(x);
     double d = x - f;
-    long long c = (long long)f % n;
-    if (c < 0) c += n;
+    int c;
+    if (f >= 0.0 && f < (double)n) {       // the usual case: callers wrap positions into [0, L) (main.py:187, 837)
+        c = (int)f;
+    } else {                               // images further out: 64-bit modulo (some 60 instructions), rarely taken
+        long long cc = (long long)f % n;
+        if (cc < 0) cc += n;
+        c = (int)cc;
+    }
     if (d >= 1.0) {  // x = -tiny rounds to d == 1
         d = 0.0;
         c = (c + 1 == n) ? 0 : c + 1;
     }
-    cell = (int)c;
+    cell = c;
     frac = d;
 }
 
@@ -88,7 +94,7 @@ __device__ __forceinline__ void warp_runs(uint32_t key, unsigned& head_lane, uns
 // rt->n_total records.  A home particle outside this rank's slab goes to the away bin -- it is painted
 // and read out on the rank that owns its cell.  keys[j] keeps the bin for the scatter pass.
 template <typename real, typename RecT, typename UT, int IDX_BITS, bool REUSE, bool ROUTED>
-__global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos,
+__global__ void __launch_bounds__(256, ROUTED ? 5 : 8) count_kernel(const real* __restrict__ pos,
                                                     const int32_t* __restrict__ types, long long n,
                                                     SortParams p, RecT* __restrict__ stage,
                                                     uint32_t* __restrict__ cnt,
@@ -169,6 +175,72 @@ __global__ void __launch_bounds__(256) count_kernel(const real* __restrict__ pos
     }
 }
 
+// Pass 1, one slab: the same as count_kernel<..., false>, two particles per thread (j and j + 256 of a 512-particle
+// block).  The pass is a chain of dependent memory operations per particle (previous record -> position -> staged
+// record, counter): with both chains of a thread in flight the latency is paid once per pair.
+template <typename real, typename RecT, typename UT, int IDX_BITS, bool REUSE>
+__global__ void __launch_bounds__(256, 6) count2_kernel(const real* __restrict__ pos, const int32_t* __restrict__ types,
+                                                     long long n, SortParams p, RecT* __restrict__ stage,
+                                                     uint32_t* __restrict__ cnt, DeviceScalars* __restrict__ sc) {
+    const long long j0 = blockIdx.x * 512LL + threadIdx.x;
+    UT idx[2], type[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const long long j = j0 + 256 * u;
+        live[u] = j < n;
+        idx[u] = 0; type[u] = 0;
+        if (live[u]) {
+            if (REUSE) {
+                const UT meta = stage[j].meta;
+                idx[u] = meta & (((UT)1 << IDX_BITS) - 1);
+                type[u] = meta >> IDX_BITS;
+            } else {
+                idx[u] = (UT)j;
+                type[u] = (UT)(uint32_t)types[j];
+            }
+        }
+    }
+    real x[2][3];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[u][a] = live[u] ? pos[3 * idx[u] + a] : (real)0;
+    unsigned int r1 = 0, bad = 0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        uint32_t key = 0xffffffffu;                    // lanes past the end: a run of their own
+        if (live[u]) {
+            int cx, cy, cz;
+            double dx, dy, dz;
+            split_coord((double)x[u][0] * p.sx, p.Nx, cx, dx);
+            split_coord((double)x[u][1] * p.sy, p.Ny, cy, dy);
+            split_coord((double)x[u][2] * p.sz, p.Nz, cz, dz);
+            int lx = cx - p.x0;
+            if (lx < 0 || lx >= p.nxl) {
+                bad += 1;
+                lx = lx < 0 ? 0 : p.nxl - 1;
+            }
+            RecT r;
+            r.ux = pack_coord<UT>(lx, dx, p.fbx);
+            r.uy = pack_coord<UT>(cy, dy, p.fby);
+            r.uz = pack_coord<UT>(cz, dz, p.fbz);
+            r.meta = idx[u] | (type[u] << IDX_BITS);
+            stage[j0 + 256 * u] = r;
+            key = (uint32_t)(((long long)lx * p.Ny + cy) * p.nbz + zbin_of(cz, p.Nz));
+        }
+        unsigned head_lane, rank, count;
+        warp_runs(key, head_lane, rank, count);
+        if (rank == 0 && live[u]) r1 = max(r1, atomicAdd(&cnt[key], count) + count);
+    }
+    unsigned int m = __reduce_max_sync(0xffffffffu, r1);
+    unsigned int b = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (m > sc->max_cell_count) atomicMax(&sc->max_cell_count, m);
+        if (b) atomicAdd(&sc->out_of_slab, b);
+    }
+}
+
 // Pass 2 (after the scan): staged record j goes to the next free slot of its cell.
 template <typename real, typename RecT, typename UT, int IDX_BITS, bool ROUTED>
 __global__ void __launch_bounds__(256) scatter_kernel(
@@ -216,6 +288,59 @@ __global__ void __launch_bounds__(256) scatter_kernel(
     }
 }
 
+// Pass 2, one slab: the same as scatter_kernel<..., false>, two staged records per thread (j and j + 256 of a
+// 512-record block) with both loads, then both cursor atomics, in flight at once: the pass is a chain of three
+// dependent memory operations per record (staged record -> cursor -> slot) and was latency-bound at one record per
+// thread (ncu: long_scoreboard 36 of 44 stall cycles per issue).
+template <typename real, typename RecT, typename UT, int IDX_BITS>
+__global__ void __launch_bounds__(256) scatter2_kernel(
+    const RecT* __restrict__ stage, const real* __restrict__ q, long long n, SortParams p,
+    uint32_t* __restrict__ cur, RecT* __restrict__ rec, real* __restrict__ q_sorted, DeviceScalars* __restrict__ sc) {
+    const long long j0 = blockIdx.x * 512LL + threadIdx.x;
+    RecT r[2];
+    uint32_t key[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const long long j = j0 + 256 * u;
+        live[u] = j < n;
+        key[u] = 0xffffffffu;
+        if (live[u]) r[u] = stage[j];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+        if (live[u]) {
+            const long long lx = (long long)(r[u].ux >> p.fbx), cy = (long long)(r[u].uy >> p.fby),
+                            cz = (long long)(r[u].uz >> p.fbz);
+            key[u] = (uint32_t)((lx * p.Ny + cy) * p.nbz + zbin_of((int)cz, p.Nz));
+        }
+    unsigned head_lane[2], rank[2], count[2];
+    uint32_t base[2] = {0, 0};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        warp_runs(key[u], head_lane[u], rank[u], count[u]);
+        if (rank[u] == 0 && live[u]) base[u] = atomicAdd(&cur[key[u]], count[u]);
+    }
+    float aq = 0.f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        base[u] = __shfl_sync(0xffffffffu, base[u], (int)head_lane[u]);
+        if (live[u]) {
+            const size_t slot = (size_t)base[u] + rank[u];
+            rec[slot] = r[u];
+            if (q != nullptr) {
+                const real qi = q[r[u].meta & (((UT)1 << IDX_BITS) - 1)];
+                q_sorted[slot] = qi;
+                aq = fmaxf(aq, fabsf((float)qi));
+            }
+        }
+    }
+    if (q != nullptr) {
+        unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(aq));
+        if ((threadIdx.x & 31) == 0 && m > sc->qmax_bits) atomicMax(&sc->qmax_bits, m);
+    }
+}
+
 // Charges into sorted order for a sort that was made without them (update_field_force_q is
 // called after update_field on the same positions: main.py:1006-1058).  Several slabs: n = capacity
 // bound, the live count is rt->n_total, guests read the charges their owners sent (gq).
@@ -237,6 +362,12 @@ __global__ void __launch_bounds__(256) gather_charges_kernel(const RecT* __restr
     }
     unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(aq));
     if ((threadIdx.x & 31) == 0 && m > sc->qmax_bits) atomicMax(&sc->qmax_bits, m);
+}
+
+// HYMD_B200_SCATTER=1: one staged record per thread (the first version of the pass; A/B)
+static bool scatter_two() {
+    const char* e = getenv("HYMD_B200_SCATTER");
+    return !(e && e[0] == '1');
 }
 
 size_t scan_temp_bytes(long long n) {
@@ -564,6 +695,14 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
             else
                 count_kernel<real, RecT, UT, IDX_BITS, false, true><<<blocks, 256, 0, s>>>(
                     (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, r->totals, r->keys, (uint32_t)ncell, ro);
+        } else if (scatter_two()) {
+            const unsigned int blocks2 = (unsigned int)((span + 511) / 512);
+            if (reuse)
+                count2_kernel<real, RecT, UT, IDX_BITS, true><<<blocks2, 256, 0, s>>>(
+                    (const real*)d_pos, d_types, n, p, stage, cur, c->scalars);
+            else
+                count2_kernel<real, RecT, UT, IDX_BITS, false><<<blocks2, 256, 0, s>>>(
+                    (const real*)d_pos, d_types, n, p, stage, cur, c->scalars);
         } else if (reuse) {
             count_kernel<real, RecT, UT, IDX_BITS, true, false><<<blocks, 256, 0, s>>>(
                 (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, nullptr, nullptr, 0u, ro);
@@ -590,6 +729,9 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
         if (routed)
             scatter_kernel<real, RecT, UT, IDX_BITS, true><<<blocks, 256, 0, s>>>(
                 stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars, r->totals, r->keys, reuse ? 1 : 0);
+        else if (scatter_two())
+            scatter2_kernel<real, RecT, UT, IDX_BITS><<<(unsigned int)((span + 511) / 512), 256, 0, s>>>(
+                stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars);
         else
             scatter_kernel<real, RecT, UT, IDX_BITS, false><<<blocks, 256, 0, s>>>(
                 stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars, nullptr, nullptr, 0);

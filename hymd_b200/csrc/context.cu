@@ -263,6 +263,13 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
             if (cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, lo) != cudaSuccess) return fail(HYMD_ERR_CUDA);
             for (auto& e : c->xev)
                 if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(HYMD_ERR_CUDA);
+            const char* xc = getenv("HYMD_B200_XPIPE_COPY");
+            c->xpipe_ce = !(xc && xc[0] == 'k');
+            for (int q = 0; q < P; ++q) {
+                if (cudaStreamCreateWithFlags(&c->xpeer[q], cudaStreamNonBlocking) != cudaSuccess) return fail(HYMD_ERR_CUDA);
+                for (auto& e : c->xdone[q])
+                    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(HYMD_ERR_CUDA);
+            }
         }
     }
     if ((st = readout_setup(c))) return fail(st);
@@ -290,6 +297,11 @@ int hymd_ctx_destroy(hymd_ctx* c) {
         for (auto& e : c->xev)
             if (e) cudaEventDestroy(e);
         cudaStreamDestroy(c->xstream);
+        for (int q = 0; q < HYMD_MAX_PEERS; ++q) {
+            for (auto& e : c->xdone[q])
+                if (e) cudaEventDestroy(e);
+            if (c->xpeer[q]) cudaStreamDestroy(c->xpeer[q]);
+        }
     }
     if (c->ev_open) {
         for (auto& iv : *c->ev_open) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }

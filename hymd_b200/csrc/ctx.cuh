@@ -225,8 +225,11 @@ struct hymd_ctx {
     // the plane kernel transforms field f + 1 (forward) / row u - 1 (inverse)
     int xpipe;              // 0 off, 1 on when a field's block is large enough, 2 always (tests)
     int plane_sm_reserve;   // > 0 while the pipeline runs: the persistent plane kernels leave this many SMs to the copies
-    cudaStream_t xstream;
-    cudaEvent_t xev[2 * HYMD_MAX_TYPES + 2];
+    cudaStream_t xstream;                               // SM copy kernel variant (HYMD_B200_XPIPE_COPY=kernel)
+    cudaEvent_t xev[2 * HYMD_MAX_TYPES + 2];             // "piece ready" on the main stream / copied (kernel variant)
+    cudaStream_t xpeer[hymd::HYMD_MAX_PEERS];                  // copy-engine variant (default): one stream per destination
+    cudaEvent_t xdone[hymd::HYMD_MAX_PEERS][HYMD_MAX_TYPES + 1];
+    bool xpipe_ce;
     bool xpushed;           // the x-line kernel has already stored its output into the peers' work buffers
     unsigned peer_busy;     // PEER_* buffers whose local consumers were enqueued after the last barrier:
                             // a peer may not overwrite them before another barrier (same call sequence

@@ -171,6 +171,7 @@ struct PlaneParams {
     // inverse, several slabs, "blocked" exchange: the input is the receive buffer of the inverse transpose as the
     // peers' contiguous copies left it, W[q][x][f][kyl][kz] (block q = the k_y range rank q transformed along x):
     // row ky of plane x, spectrum f  ->  in + (ky >> nyl_shift) blk_q + x blk_x + f blk_f + (ky & (nyl-1)) Nzcp
+    int vec_out;                    // tensor-memory inverse: finished rows staged in shared memory, 16-byte stores
     int blk_in;
     long long blk_q, blk_x, blk_f;
     long long blk_d;                // blk_q - nyl Nzcp: what crossing into the next block adds to a row offset
@@ -1005,6 +1006,39 @@ __global__ void __launch_bounds__(512, 1) plane_c2r_tmem_kernel(
                 for (int k1b = 0; k1b < R; ++k1b) u[k1b] = wtile[TmLB::at2(k1b, n2, c2)];
                 dft_reg<real, R, +1>(u);
                 const int y0 = ybase + 2 * c2;
+                if (p.vec_out) {
+                    // The four finished rows ybase .. ybase + 3 of this warp go through the (now free) warp tile and
+                    // leave as 16-byte stores, whole 512-byte runs per instruction, instead of 32 4-byte stores per
+                    // lane: the load/store queue was the kernel's top stall (ncu: lg_throttle).  Row pitch 264 words:
+                    // the two row pairs of a pass fall into different banks.
+                    constexpr int OP = NZ + 8;
+                    __syncwarp();                            // every lane has read its butterfly inputs
+                    float* st = reinterpret_cast<float*>(wtile);
+#pragma unroll
+                    for (int n1b = 0; n1b < R; ++n1b) {
+                        st[(2 * c2) * OP + n1b * R + n2] = u[n1b].x;
+                        st[(2 * c2 + 1) * OP + n1b * R + n2] = u[n1b].y;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float4 a = *reinterpret_cast<const float4*>(st + r * OP + 4 * lane);
+                        const float4 b = *reinterpret_cast<const float4*>(st + r * OP + NZ / 2 + 4 * lane);
+#pragma unroll
+                        for (int dup = 0; dup < 2; ++dup) {
+                            real* ob = dup ? obase2 : obase;
+                            if (ob == nullptr) continue;
+#pragma unroll
+                            for (int gh = 0; gh < 2; ++gh) {     // gh = 1: row 0 again as the periodic image y = NY
+                                if (gh && !(p.ghost && ybase + r == 0)) continue;
+                                real* row = ob + (long long)(gh ? NY : ybase + r) * p.r_ys;
+                                __stcs(reinterpret_cast<float4*>(row + 4 * lane), a);
+                                __stcs(reinterpret_cast<float4*>(row + NZ / 2 + 4 * lane), b);
+                                if (p.ghost && lane == 0) row[NZ] = a.x;
+                            }
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int dup = 0; dup < 2; ++dup) {
                     real* ob = dup ? obase2 : obase;
@@ -1182,6 +1216,9 @@ static int launch_plane_tmem(hymd_ctx* c, bool inverse, const void* in, void* ou
     // kernel, nothing on the inverse (profiles/r2h_*), so only the forward kernel pays the extra 70 KB
     p.scr_alt = inverse ? 0 : 1;
     if (const char* e = getenv("HYMD_B200_TMEM_DBUF")) p.scr_alt = atoi(e) != 0;
+    p.vec_out = 0;                      // measured slower (2 slabs, C4: 0.489 vs 0.475 ms per cycle in the inverse transform)
+    if (const char* e = getenv("HYMD_B200_C2R_VEC")) p.vec_out = atoi(e) != 0;
+    if (p.r_ys % 4 != 0) p.vec_out = 0;
     const size_t smem = p.scr_alt ? TM_SMEM_DBUF : TM_SMEM;
     if (inverse) {
         const int bsh = p.blk_in ? p.nyl_shift - 4 : 4;

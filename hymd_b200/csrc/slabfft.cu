@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) block_copy2d_kernel(const uint4* __restri
 // Is the per-field piece of a block big enough for the pipeline to pay?  (Every piece costs two launches and an
 // event; below ~4 MB the exchange is latency, not bandwidth.)
 static bool pipe_pieces(const hymd_ctx* c, long long piece_bytes, int pieces) {
-    if (c->xpipe == 0 || pieces < 2 || c->xstream == nullptr || piece_bytes % 16 != 0) return false;
+    if (c->xpipe == 0 || pieces < 2 || pieces > HYMD_MAX_TYPES || c->xstream == nullptr || piece_bytes % 16 != 0) return false;
     return c->xpipe == 2 || piece_bytes >= (4LL << 20);
 }
 
@@ -479,6 +479,31 @@ int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t 
         const long long piece = (long long)g.nxl * l.fs * (long long)csz;       // bytes of one field inside a block
         if (pipe_pieces(c, piece, F) && (l.fs * csz) % 16 == 0) {
             // field f crosses NVLink (second stream) while the plane kernel transforms field f + 1
+            if (c->xpipe_ce) {
+                // copy engines, one stream per destination: the SMs stay with the plane kernel (an SM copy kernel
+                // squeezed onto the 16-20 SMs the plane kernel leaves free reached a third of the NVLink rate)
+                for (int f = 0; f < F; ++f) {
+                    HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p, f, 1));
+                    HYMD_CUDA(cudaEventRecord(c->xev[f], s));
+                    for (int i = 1; i < g.P; ++i) {
+                        const int q = (g.rank + i) % g.P;
+                        HYMD_CUDA(cudaStreamWaitEvent(c->xpeer[q], c->xev[f], 0));
+                        HYMD_CUDA(cudaMemcpy2DAsync((char*)K.p[q] + ((size_t)g.x0 * l.xs + (size_t)f * l.fs) * csz, (size_t)l.xs * csz,
+                                                    (char*)c->wS + ((size_t)q * block + (size_t)f * l.fs) * csz, (size_t)l.xs * csz,
+                                                    (size_t)l.fs * csz, (size_t)g.nxl, cudaMemcpyDeviceToDevice, c->xpeer[q]));
+                    }
+                    c->launches += g.P - 1;
+                }
+                PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+                for (int i = 1; i < g.P; ++i) {
+                    const int q = (g.rank + i) % g.P;
+                    HYMD_CUDA(cudaEventRecord(c->xdone[q][0], c->xpeer[q]));
+                    HYMD_CUDA(cudaStreamWaitEvent(s, c->xdone[q][0], 0));
+                }
+                HYMD_CHECK(comm_barrier(c, s));
+                c->peer_busy |= PEER_K;
+                return HYMD_OK;
+            }
             SmReserve reserve(c);
             for (int f = 0; f < F; ++f) {
                 HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p, f, 1));
@@ -563,6 +588,34 @@ int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost
             if (derive && pipe_pieces(c, piece, U) && (lk.fs * csz) % 16 == 0) {
                 // the two spectra of potential row u cross NVLink (second stream) while the plane kernel turns row
                 // u - 1 into its three force meshes; one barrier per row tells every rank that the row has landed
+                if (c->xpipe_ce) {
+                    {
+                        PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+                        HYMD_CHECK(peer_acquire(c, PEER_WORK, s));
+                        HYMD_CUDA(cudaEventRecord(c->xev[0], s));               // the x-line kernel has written k_in
+                        for (int i = 0; i < g.P; ++i) {
+                            const int q = (g.rank + i) % g.P;
+                            HYMD_CUDA(cudaStreamWaitEvent(c->xpeer[q], c->xev[0], 0));
+                            for (int u = 0; u < U; ++u) {
+                                HYMD_CUDA(cudaMemcpy2DAsync((char*)W.p[q] + ((size_t)g.rank * block + (size_t)2 * u * lk.fs) * csz, (size_t)lk.xs * csz,
+                                                            (char*)k_in + ((size_t)q * block + (size_t)2 * u * lk.fs) * csz, (size_t)lk.xs * csz,
+                                                            (size_t)2 * lk.fs * csz, (size_t)g.nxl, cudaMemcpyDeviceToDevice, c->xpeer[q]));
+                                HYMD_CUDA(cudaEventRecord(c->xdone[q][u], c->xpeer[q]));
+                            }
+                        }
+                        c->launches += g.P * U;
+                    }
+                    for (int u = 0; u < U; ++u) {
+                        {
+                            PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
+                            for (int q = 0; q < g.P; ++q) HYMD_CUDA(cudaStreamWaitEvent(s, c->xdone[q][u], 0));
+                            HYMD_CHECK(comm_barrier(c, s));
+                        }
+                        HYMD_CHECK(plane_inverse(c, c->wA, 0, F, g.nxl, real_out, ghost, derive, s, true, u, 1));
+                    }
+                    c->peer_busy |= PEER_WORK;
+                    return HYMD_OK;
+                }
                 {
                     PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
                     HYMD_CHECK(peer_acquire(c, PEER_WORK, s));

@@ -37,6 +37,7 @@ struct XParams {
     long long xs_v, fs_v, xs_pf, fs_pf;   // optional k-space outputs (not x-inverted)
     int pme;
     int two;                         // 2 outputs per row (-i k_x V, -i V): the plane c2r applies k_y, k_z
+    int no_inplace;                  // HYMD_B200_XLINE_INPLACE=0: one combine pass per potential row (first version; A/B)
     // several slabs: the force spectra go straight into the work buffer of the rank owning plane x (the
     // inverse transpose of the slab FFT, fused): element (f, x, col) -> peer[x / nxl] + (f (nxl+1) + x % nxl)
     // plane + ky0 Nzcp + col, the layout the plane c2r reads
@@ -226,7 +227,107 @@ __global__ void __launch_bounds__(NTH) xline_kernel(
         }
     }
 
+    // ---- U <= 4 potential rows (every shipped Hamiltonian): all rows in ONE pass over the T spectra, V^_u written in
+    // place over spectrum u (U <= T), k_x V^_u formed by the inverse butterfly's K tasks while they load.  The
+    // per-row pass below read the T spectra once per row and stored k_x V^ as a second spectrum: a third of the
+    // kernel's shared-memory traffic (ncu: l1tex 70 % busy, the kernel's second limiter after instruction issue).
+    constexpr int UF = 4;
+    const bool inplace = p.U <= UF && p.U <= p.T && !p.no_inplace;
+    if (inplace) {
+        for (int e = tid; e < NX * (CH / VEC); e += NT) {
+            const int c = (e % (CH / VEC)) * VEC, pos = e / (CH / VEC);
+            const int kx = pos / R2 + R1 * (pos % R2);
+            const int sp = spos<NX, CH>(pos, c);
+            const real hxv = s_hx[pos], kxr = s_kx[pos];
+            Cx<real> acc[UF][VEC];
+#pragma unroll
+            for (int u = 0; u < UF; ++u)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[u][i] = {0, 0};
+            for (int t = 0; t < p.T; ++t) {
+                Cx<real> v[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) v[i] = data[t * FE + sp + i];
+#pragma unroll
+                for (int u = 0; u < UF; ++u) {
+                    if (u < p.U) {
+                        const real a = s_A[u * p.T + t];
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) { acc[u][i].x += a * v[i].x; acc[u][i].y += a * v[i].y; }
+                    }
+                }
+            }
+            real g[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const int ci = c + i;
+                const real h = hxv * s_hk[0][ci][0];
+                if (p.pme) {
+                    const real kyr = s_hk[1][ci][0], kzr = s_hk[1][ci][1];
+                    real k2 = kxr * kxr + kyr * kyr + kzr * kzr;
+                    if (kx == 0 && s_hk[1][ci][2] != (real)0) k2 = (real)1;   // normp(p=2, zeromode=1)
+                    g[i] = coef * h / k2;
+                } else {
+                    g[i] = h * h;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UF; ++u) {
+                if (u < p.U) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const int ci = c + i;
+                        const real ar = acc[u][i].x * g[i], ai = acc[u][i].y * g[i];
+                        data[u * FE + sp + i] = {ar, ai};
+                        if (vout != nullptr && (full || col0 + ci < p.ncols)) {
+                            real vr = ar;
+                            if (!p.pme && kx == 0 && s_hk[1][ci][2] != (real)0) vr += cu[u];
+                            vout[u * p.fs_v + kx * p.xs_v + col0 + ci] = {vr, ai};
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
     for (int u = 0; u < p.U; ++u) {
+        if (inplace) {
+            // ---- first inverse butterfly of V^_u (tasks < R1 CH) and of k_x V^_u (the others), both from spectrum u ----
+            for (int task = tid; task < 2 * R1 * CH; task += NT) {
+                const bool isK = task >= R1 * CH;
+                const int rem = task % (R1 * CH), c = rem % CH, k1 = rem / CH;
+                const Cx<real>* src = data + u * FE;
+                Cx<real>* dst = isK ? wK : wV;
+                Cx<real> v[R2];
+#pragma unroll
+                for (int k2 = 0; k2 < R2; ++k2) v[k2] = src[spos2<NX, CH>(k1, k2, c)];
+                if (isK) {
+                    const bool selfc = s_hk[0][c][3] != (real)0;
+#pragma unroll
+                    for (int k2 = 0; k2 < R2; ++k2) {
+                        // position k1 R2 + k2 holds frequency k1 + R1 k2; x-Nyquist rule on self-conjugate columns
+                        real kxe = s_kx[k1 * R2 + k2];
+                        if ((NX % 2 == 0) && k1 + R1 * k2 == NX / 2 && selfc) kxe = 0;
+                        v[k2].x *= kxe; v[k2].y *= kxe;
+                    }
+                }
+                dft_reg<real, R2, +1>(v);
+                if constexpr (REG) {
+                    twi.template apply<true>(v);
+#pragma unroll
+                    for (int n2 = 0; n2 < R2; ++n2) dst[spos2<NX, CH>(k1, n2, c)] = v[n2];
+                } else {
+#pragma unroll
+                    for (int n2 = 0; n2 < R2; ++n2) {
+                        Cx<real> w = tw[(n2 * k1) & (NX - 1)];
+                        w.y = -w.y;
+                        dst[spos2<NX, CH>(k1, n2, c)] = (k1 == 0) ? v[n2] : cmul(w, v[n2]);
+                    }
+                }
+            }
+            __syncthreads();
+        } else {
         // ---- potential and k_x * potential in frequency space ----
         for (int e = tid; e < NX * (CH / VEC); e += NT) {
             const int c = (e % (CH / VEC)) * VEC, pos = e / (CH / VEC);
@@ -274,6 +375,7 @@ __global__ void __launch_bounds__(NTH) xline_kernel(
         for (int task = tid; task < 2 * R1 * CH; task += NT)
             fft_inv_stepA<real, NX, CH, REG>(task < R1 * CH ? wV : wK, tw, twi, task % (R1 * CH));
         __syncthreads();
+        }
         // ---- last butterfly stage + F_d = -i k_d V:  -i (a + i b) = b - i a, stored straight from
         // the registers (V -> F_y, F_z; k_x V -> F_x); lanes = neighbouring columns: 64-byte runs ----
         Cx<real>* f0 = fout + (long long)((p.two ? 2 : 3) * u) * p.fs_f;
@@ -350,6 +452,7 @@ static int launch_x(hymd_ctx* c, bool pme, const void* in, void* fout, void* vou
     memset(&p, 0, sizeof(p));
     p.Nx = g.Nx; p.Ny = g.Ny; p.Nz = g.Nz; p.nyl = g.nyl; p.y0 = g.y0; p.Nzc = g.Nzc; p.Nzcp = g.Nzcp;
     p.T = T; p.U = U; p.pme = pme ? 1 : 0; p.two = c->grad2 ? 1 : 0;
+    if (const char* e = getenv("HYMD_B200_XLINE_INPLACE")) p.no_inplace = e[0] == '0';
     p.ncols = (long long)g.nyl * g.Nzcp;
     const KLayout lin = klayout(c, T), lv = klayout(c, U);
     p.xs_in = lin.xs; p.fs_in = lin.fs;

@@ -193,6 +193,8 @@ def test_pipelined_exchange_matches_oracle(P, mesh, pme, dtype, monkeypatch):
     if dtype == np.float64 and mesh[1] == 256:
         pytest.skip("tensor-memory plane kernels are fp32")
     _run_and_compare(P, mesh, 20000, dtype, pme, "drifted", steps=3,
-                     env={"HYMD_B200_XPIPE": "2"}, monkeypatch=monkeypatch)
+                     env={"HYMD_B200_XPIPE": "2"}, monkeypatch=monkeypatch)          # pieces moved by the copy engines
+    _run_and_compare(P, mesh, 20000, dtype, pme, "drifted", steps=3,
+                     env={"HYMD_B200_XPIPE": "2", "HYMD_B200_XPIPE_COPY": "kernel"}, monkeypatch=monkeypatch)
     _run_and_compare(P, mesh, 20000, dtype, pme, "drifted", steps=2,
                      env={"HYMD_B200_XPIPE": "0"}, monkeypatch=monkeypatch)

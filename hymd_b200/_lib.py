@@ -33,7 +33,7 @@ EXPORTS = [
     "hymd_md_kick_drift", "hymd_velocity_moments", "hymd_velocity_moments_scratch_doubles",
     "hymd_csvr_apply", "hymd_cancel_com",
     "hymd_gpe_cycle", "hymd_gpe_energy",
-    "hymd_local_group_id", "hymd_ctx_check",
+    "hymd_local_group_id", "hymd_ctx_check", "hymd_exchange_cost",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -139,6 +139,7 @@ def load():
     lib.hymd_ctx_get_timings.argtypes = [vp, P(dbl), P(i64)]
     lib.hymd_migrate_plan.argtypes = [vp, vp, i64, P(i64), vp]
     lib.hymd_migrate_apply.argtypes = [vp, vp, vp, i32, vp]
+    lib.hymd_exchange_cost.argtypes = [vp, P(i64), vp]
     I32P, F64P = P(i32), P(dbl)
     lib.hymd_bonded_create.argtypes = [i64, i64, I32P, I32P, F64P, F64P, i64, I32P, I32P, I32P, F64P, F64P,
                                        i64, I32P, I32P, I32P, I32P, F64P, I32P, P(vp)]

@@ -398,6 +398,18 @@ int hymd_sort_particles_ex(hymd_ctx* c, const void* d_pos, const int32_t* d_type
     return HYMD_OK;
 }
 
+int hymd_exchange_cost(hymd_ctx* c, int64_t* sent_to, void* stream) {
+    if (!c || !sent_to) { set_error("null argument"); return HYMD_ERR_INVALID; }
+    for (int q = 0; q < c->g.P; ++q) sent_to[q] = 0;
+    const uint32_t* d = route_send_counts(c);
+    if (c->g.P == 1 || d == nullptr || !c->sorted) return HYMD_OK;
+    uint32_t h[HYMD_MAX_PEERS] = {};
+    HYMD_CUDA(cudaMemcpyAsync(h, d, sizeof(uint32_t) * c->g.P, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    HYMD_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int q = 0; q < c->g.P; ++q) sent_to[q] = q == c->g.rank ? 0 : (int64_t)h[q];
+    return HYMD_OK;
+}
+
 int hymd_set_charges(hymd_ctx* c, const void* d_charges, void* stream) {
     if (!c || (!d_charges && c->np > 0)) { set_error("null argument"); return HYMD_ERR_INVALID; }
     if (!c->sorted) { set_error("hymd_set_charges before hymd_sort_particles"); return HYMD_ERR_STATE; }

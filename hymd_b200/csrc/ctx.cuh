@@ -289,6 +289,7 @@ int route_prepare(hymd_ctx* c, int64_t n, cudaStream_t s);
 void route_destroy(hymd_ctx* c);
 long long route_guest_rows(const hymd_ctx* c);
 const RouteTotals* route_totals(const hymd_ctx* c);
+const uint32_t* route_send_counts(const hymd_ctx* c);   // [HYMD_MAX_PEERS] guests sent to each slab by the last sort (device)
 int route_return(hymd_ctx* c, void* d_force, cudaStream_t s);
 int route_acquire_return(hymd_ctx* c, cudaStream_t s);
 void route_peer_ret(const hymd_ctx* c, void** out, long long* G);

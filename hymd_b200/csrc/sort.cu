@@ -93,7 +93,7 @@ __device__ __forceinline__ void warp_runs(uint32_t key, unsigned& head_lane, uns
 // extra bin `ncell` at its end, the home particles that were away; REUSE then walks all
 // rt->n_total records.  A home particle outside this rank's slab goes to the away bin -- it is painted
 // and read out on the rank that owns its cell.  keys[j] keeps the bin for the scatter pass.
-template <typename real, typename RecT, typename UT, int IDX_BITS, bool REUSE, bool ROUTED>
+template <typename real, typename RecT, typename UT, int IDX_BITS, bool REUSE, bool ROUTED, int PER>
 __global__ void __launch_bounds__(256, ROUTED ? 5 : 8) count_kernel(const real* __restrict__ pos,
                                                     const int32_t* __restrict__ types, long long n,
                                                     SortParams p, RecT* __restrict__ stage,
@@ -102,31 +102,50 @@ __global__ void __launch_bounds__(256, ROUTED ? 5 : 8) count_kernel(const real* 
                                                     const RouteTotals* __restrict__ rt,
                                                     uint32_t* __restrict__ keys, uint32_t away_bin, RouteOut ro) {
     const long long limit = (ROUTED && REUSE) ? (long long)rt->n_total : n;
-    // ROUTED: the grid covers the n home particles; the (few) blocks whose range is followed by staged
-    // guest records of the previous step take a second trip (block-uniform loop: the warp shuffles stay whole)
-    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;; j += (long long)gridDim.x * blockDim.x) {
-    unsigned int r1 = 0, bad = 0;
-    uint32_t key = 0xffffffffu;                        // lanes past the end: a run of their own
-    bool live = j < limit;
-    UT idx = 0, type = 0;
-    if (live) {
-        if (REUSE) {
-            const UT meta = stage[j].meta;
-            idx = meta & (((UT)1 << IDX_BITS) - 1);
-            type = meta >> IDX_BITS;
-            if (ROUTED && (long long)idx >= n) live = false;      // a guest of the previous step
-        } else {
-            idx = (UT)j;
-            type = (UT)(uint32_t)types[j];
+    // A block takes PER x 256 consecutive records per trip (thread t: records t, t + 256, ...), with the loads of
+    // all of them issued before the first is processed (the pass is a chain of dependent memory operations).
+    // ROUTED: the grid covers the n home particles; the (few) blocks whose range is followed by staged guest
+    // records of the previous step take a second trip (block-uniform loop: the warp shuffles stay whole)
+    const long long trip = (long long)gridDim.x * (256 * PER);
+    for (long long base = blockIdx.x * (long long)(256 * PER);; base += trip) {
+    UT idx[PER], type[PER];
+    bool live[PER], inr[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const long long j = base + 256 * u + threadIdx.x;
+        inr[u] = j < limit;
+        live[u] = inr[u];
+        idx[u] = 0; type[u] = 0;
+        if (live[u]) {
+            if (REUSE) {
+                const UT meta = stage[j].meta;
+                idx[u] = meta & (((UT)1 << IDX_BITS) - 1);
+                type[u] = meta >> IDX_BITS;
+                if (ROUTED && (long long)idx[u] >= n) live[u] = false;      // a guest of the previous step
+            } else {
+                idx[u] = (UT)j;
+                type[u] = (UT)(uint32_t)types[j];
+            }
         }
     }
-    if (ROUTED && j < limit && !live) keys[j] = 0xffffffffu;
-    if (live) {
+    real x[PER][3];
+#pragma unroll
+    for (int u = 0; u < PER; ++u)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[u][a] = live[u] ? pos[3 * idx[u] + a] : (real)0;
+    unsigned int r1 = 0, badsum = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+    const long long j = base + 256 * u + threadIdx.x;
+    unsigned int bad = 0;
+    uint32_t key = 0xffffffffu;                        // lanes past the end: a run of their own
+    if (ROUTED && inr[u] && !live[u]) keys[j] = 0xffffffffu;
+    if (live[u]) {
         int cx, cy, cz;
         double dx, dy, dz;
-        split_coord((double)pos[3 * idx + 0] * p.sx, p.Nx, cx, dx);
-        split_coord((double)pos[3 * idx + 1] * p.sy, p.Ny, cy, dy);
-        split_coord((double)pos[3 * idx + 2] * p.sz, p.Nz, cz, dz);
+        split_coord((double)x[u][0] * p.sx, p.Nx, cx, dx);
+        split_coord((double)x[u][1] * p.sy, p.Ny, cy, dy);
+        split_coord((double)x[u][2] * p.sz, p.Nz, cz, dz);
         int lx = cx - p.x0;
         if (lx < 0 || lx >= p.nxl) {
             bad = 1;
@@ -136,7 +155,7 @@ __global__ void __launch_bounds__(256, ROUTED ? 5 : 8) count_kernel(const real* 
         r.ux = pack_coord<UT>(lx, dx, p.fbx);
         r.uy = pack_coord<UT>(cy, dy, p.fby);
         r.uz = pack_coord<UT>(cz, dz, p.fbz);
-        r.meta = idx | (type << IDX_BITS);
+        r.meta = idx[u] | (type[u] << IDX_BITS);
         stage[j] = r;
         key = (uint32_t)(((long long)lx * p.Ny + cy) * p.nbz + zbin_of(cz, p.Nz));
         if (ROUTED) {
@@ -151,11 +170,11 @@ __global__ void __launch_bounds__(256, ROUTED ? 5 : 8) count_kernel(const real* 
                 } else {
                     const long long row = (long long)ro.rank * ro.G + k;
                     real* dp = reinterpret_cast<real*>(ro.peers.pos[d]) + 3 * row;
-                    dp[0] = pos[3 * idx + 0]; dp[1] = pos[3 * idx + 1]; dp[2] = pos[3 * idx + 2];
-                    reinterpret_cast<int32_t*>(ro.peers.type[d])[row] = (int32_t)type;
+                    dp[0] = x[u][0]; dp[1] = x[u][1]; dp[2] = x[u][2];
+                    reinterpret_cast<int32_t*>(ro.peers.type[d])[row] = (int32_t)type[u];
                     if (ro.q != nullptr)
-                        reinterpret_cast<real*>(ro.peers.q[d])[row] = reinterpret_cast<const real*>(ro.q)[idx];
-                    ro.sent_idx[(long long)d * ro.G + k] = (int32_t)idx;
+                        reinterpret_cast<real*>(ro.peers.q[d])[row] = reinterpret_cast<const real*>(ro.q)[idx[u]];
+                    ro.sent_idx[(long long)d * ro.G + k] = (int32_t)idx[u];
                 }
             }
             keys[j] = key;
@@ -163,15 +182,19 @@ __global__ void __launch_bounds__(256, ROUTED ? 5 : 8) count_kernel(const real* 
     }
     unsigned head_lane, rank, count;
     warp_runs(key, head_lane, rank, count);
-    if (rank == 0 && live) r1 = atomicAdd(&cnt[key], count) + count;
-    if (ROUTED && key == away_bin) r1 = 0;             // the away bin does not bound the paint scale
+    unsigned int r1u = 0;
+    if (rank == 0 && live[u]) r1u = atomicAdd(&cnt[key], count) + count;
+    if (ROUTED && key == away_bin) r1u = 0;            // the away bin does not bound the paint scale
+    r1 = max(r1, r1u);
+    badsum += bad;
+    }
     unsigned int m = __reduce_max_sync(0xffffffffu, r1);
-    unsigned int b = __reduce_add_sync(0xffffffffu, bad);
+    unsigned int b = __reduce_add_sync(0xffffffffu, badsum);
     if ((threadIdx.x & 31) == 0) {
         if (m > sc->max_cell_count) atomicMax(&sc->max_cell_count, m);
         if (b) atomicAdd(&sc->out_of_slab, b);
     }
-    if (!ROUTED || j - threadIdx.x + (long long)gridDim.x * blockDim.x >= limit) break;
+    if (!ROUTED || base + trip >= limit) break;
     }
 }
 
@@ -242,49 +265,65 @@ __global__ void __launch_bounds__(256, 6) count2_kernel(const real* __restrict__
 }
 
 // Pass 2 (after the scan): staged record j goes to the next free slot of its cell.
-template <typename real, typename RecT, typename UT, int IDX_BITS, bool ROUTED>
+template <typename real, typename RecT, typename UT, int IDX_BITS, bool ROUTED, int PER>
 __global__ void __launch_bounds__(256) scatter_kernel(
     const RecT* __restrict__ stage, const real* __restrict__ q, long long n, SortParams p,
     uint32_t* __restrict__ cur, RecT* __restrict__ rec, real* __restrict__ q_sorted,
     DeviceScalars* __restrict__ sc, const RouteTotals* __restrict__ rt, const uint32_t* __restrict__ keys,
     int reuse) {
     const long long limit = (ROUTED && reuse) ? (long long)rt->n_total : n;
-    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;; j += (long long)gridDim.x * blockDim.x) {
+    const long long trip = (long long)gridDim.x * (256 * PER);
+    for (long long base = blockIdx.x * (long long)(256 * PER);; base += trip) {
     float aq = 0.f;
-    RecT r;
-    uint32_t key = 0xffffffffu;
-    bool live = j < limit;
-    if (ROUTED) {
-        if (live) {
-            key = keys[j];
-            live = key != 0xffffffffu;
-            if (live) r = stage[j];
+    RecT r[PER];
+    uint32_t key[PER];
+    bool live[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const long long j = base + 256 * u + threadIdx.x;
+        key[u] = 0xffffffffu;
+        live[u] = j < limit;
+        if (ROUTED) {
+            if (live[u]) {
+                key[u] = keys[j];
+                live[u] = key[u] != 0xffffffffu;
+                if (live[u]) r[u] = stage[j];
+            }
+        } else if (live[u]) {
+            r[u] = stage[j];
         }
-    } else if (live) {
-        r = stage[j];
-        const long long lx = (long long)(r.ux >> p.fbx), cy = (long long)(r.uy >> p.fby),
-                        cz = (long long)(r.uz >> p.fbz);
-        key = (uint32_t)((lx * p.Ny + cy) * p.nbz + zbin_of((int)cz, p.Nz));
     }
-    unsigned head_lane, rank, count;
-    warp_runs(key, head_lane, rank, count);
-    uint32_t base = 0;
-    if (rank == 0 && live) base = atomicAdd(&cur[key], count);
-    base = __shfl_sync(0xffffffffu, base, (int)head_lane);
-    if (live) {
-        const size_t slot = (size_t)base + rank;
-        rec[slot] = r;
-        if (q != nullptr) {
-            const real qi = q[r.meta & (((UT)1 << IDX_BITS) - 1)];
-            q_sorted[slot] = qi;
-            aq = fabsf((float)qi);
+    uint32_t bs[PER];
+    unsigned head_lane[PER], rank[PER], count[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        if (!ROUTED && live[u]) {
+            const long long lx = (long long)(r[u].ux >> p.fbx), cy = (long long)(r[u].uy >> p.fby),
+                            cz = (long long)(r[u].uz >> p.fbz);
+            key[u] = (uint32_t)((lx * p.Ny + cy) * p.nbz + zbin_of((int)cz, p.Nz));
+        }
+        warp_runs(key[u], head_lane[u], rank[u], count[u]);
+        bs[u] = 0;
+        if (rank[u] == 0 && live[u]) bs[u] = atomicAdd(&cur[key[u]], count[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        bs[u] = __shfl_sync(0xffffffffu, bs[u], (int)head_lane[u]);
+        if (live[u]) {
+            const size_t slot = (size_t)bs[u] + rank[u];
+            rec[slot] = r[u];
+            if (q != nullptr) {
+                const real qi = q[r[u].meta & (((UT)1 << IDX_BITS) - 1)];
+                q_sorted[slot] = qi;
+                aq = fmaxf(aq, fabsf((float)qi));
+            }
         }
     }
     if (q != nullptr) {
         unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(aq));
         if ((threadIdx.x & 31) == 0 && m > sc->qmax_bits) atomicMax(&sc->qmax_bits, m);
     }
-    if (!ROUTED || j - threadIdx.x + (long long)gridDim.x * blockDim.x >= limit) break;
+    if (!ROUTED || base + trip >= limit) break;
     }
 }
 
@@ -530,6 +569,7 @@ void route_destroy(hymd_ctx* c) {
 
 long long route_guest_rows(const hymd_ctx* c) { return c->route ? c->route->G * c->g.P : 0; }
 const RouteTotals* route_totals(const hymd_ctx* c) { return c->route ? c->route->totals : nullptr; }
+const uint32_t* route_send_counts(const hymd_ctx* c) { return c->route ? c->route->send_count : nullptr; }
 
 // Collective (first sort of a context with several slabs): sizes the guest buffers from this rank's
 // particle count -- G = max(16384, n / 4) rows per rank pair, or HYMD_B200_GUEST_CAPACITY -- and
@@ -687,16 +727,16 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
     // its own still retires the guests it staged last step
     const long long span = routed ? (n > 0 ? n : 1) : n;
     const unsigned int blocks = (unsigned int)((span + 255) / 256);
+    const unsigned int blocks2 = (unsigned int)((span + 511) / 512);      // two records per thread
     if (span > 0) {
         if (routed) {
             if (reuse)
-                count_kernel<real, RecT, UT, IDX_BITS, true, true><<<blocks, 256, 0, s>>>(
+                count_kernel<real, RecT, UT, IDX_BITS, true, true, 2><<<blocks2, 256, 0, s>>>(
                     (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, r->totals, r->keys, (uint32_t)ncell, ro);
             else
-                count_kernel<real, RecT, UT, IDX_BITS, false, true><<<blocks, 256, 0, s>>>(
+                count_kernel<real, RecT, UT, IDX_BITS, false, true, 2><<<blocks2, 256, 0, s>>>(
                     (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, r->totals, r->keys, (uint32_t)ncell, ro);
         } else if (scatter_two()) {
-            const unsigned int blocks2 = (unsigned int)((span + 511) / 512);
             if (reuse)
                 count2_kernel<real, RecT, UT, IDX_BITS, true><<<blocks2, 256, 0, s>>>(
                     (const real*)d_pos, d_types, n, p, stage, cur, c->scalars);
@@ -704,10 +744,10 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
                 count2_kernel<real, RecT, UT, IDX_BITS, false><<<blocks2, 256, 0, s>>>(
                     (const real*)d_pos, d_types, n, p, stage, cur, c->scalars);
         } else if (reuse) {
-            count_kernel<real, RecT, UT, IDX_BITS, true, false><<<blocks, 256, 0, s>>>(
+            count_kernel<real, RecT, UT, IDX_BITS, true, false, 1><<<blocks, 256, 0, s>>>(
                 (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, nullptr, nullptr, 0u, ro);
         } else {
-            count_kernel<real, RecT, UT, IDX_BITS, false, false><<<blocks, 256, 0, s>>>(
+            count_kernel<real, RecT, UT, IDX_BITS, false, false, 1><<<blocks, 256, 0, s>>>(
                 (const real*)d_pos, d_types, n, p, stage, cur, c->scalars, nullptr, nullptr, 0u, ro);
         }
         HYMD_LAUNCH_CHECK(c);
@@ -727,13 +767,13 @@ static int sort_impl(hymd_ctx* c, const void* d_pos, const int32_t* d_types, con
     c->launches += 2;  // cub scan: init + scan kernels
     if (span > 0) {
         if (routed)
-            scatter_kernel<real, RecT, UT, IDX_BITS, true><<<blocks, 256, 0, s>>>(
+            scatter_kernel<real, RecT, UT, IDX_BITS, true, 2><<<blocks2, 256, 0, s>>>(
                 stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars, r->totals, r->keys, reuse ? 1 : 0);
         else if (scatter_two())
             scatter2_kernel<real, RecT, UT, IDX_BITS><<<(unsigned int)((span + 511) / 512), 256, 0, s>>>(
                 stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars);
         else
-            scatter_kernel<real, RecT, UT, IDX_BITS, false><<<blocks, 256, 0, s>>>(
+            scatter_kernel<real, RecT, UT, IDX_BITS, false, 1><<<blocks, 256, 0, s>>>(
                 stage, (const real*)d_q, n, p, cur, out, (real*)c->q_sorted, c->scalars, nullptr, nullptr, 0);
         HYMD_LAUNCH_CHECK(c);
     }

@@ -43,7 +43,10 @@ class Layout:
         self.smoothing = smoothing
 
     def get_exchange_cost(self):
-        return np.zeros(max(self.pm.world_size, 1), dtype=np.int64)
+        """pmesh's ``Layout.get_exchange_cost`` as ``main.py:1304-1312`` reads it: entry ``r`` = number of
+        particles rank ``r`` ships to other ranks per field call, here the guests its last binning pass routed
+        to other slabs (all types together: one sort serves every type's layout).  Collective."""
+        return self.pm.exchange_cost()
 
     def exchange(self, *arrays):
         if self.pm.world_size == 1:
@@ -425,6 +428,18 @@ class ParticleMesh:
         out = (ctypes.c_int32 * 4)()
         _lib.check(self.lib.hymd_ctx_paths(self._ctx, out))
         return {"xline": bool(out[0]), "plane": bool(out[1]), "slab": bool(out[2]), "p2p": bool(out[3])}
+
+    def exchange_cost(self):
+        """Guests sent by every rank in the last ``sort`` (length ``world_size``); zeros on one GPU."""
+        P = max(self.world_size, 1)
+        cost = np.zeros(P, dtype=np.int64)
+        if P == 1 or self._ctx is None:
+            return cost
+        sent = (ctypes.c_int64 * P)()
+        _lib.check(self.lib.hymd_exchange_cost(self._ctx, sent, self.stream))
+        mine = torch.zeros(P, dtype=torch.int64)
+        mine[self.rank] = int(sum(sent))
+        return self.world.allreduce(mine).cpu().numpy().astype(np.int64)
 
     def set_timing(self, enable=True):
         _lib.check(self.lib.hymd_ctx_set_timing(self._ctx, int(bool(enable))))

@@ -241,6 +241,11 @@ int hymd_migrate_plan(hymd_ctx* ctx, const void* d_pos, int64_t n, int64_t* n_ne
 int hymd_migrate_apply(hymd_ctx* ctx, const void* d_in, void* d_out, int32_t row_bytes,
                        void* stream);
 
+/* Layout.get_exchange_cost (pmesh; read by main.py:1304-1312 at verbose > 2): sent_to[q], q < world size, receives
+ * the number of this rank's particles that the last hymd_sort_particles routed to slab q as guests (0 for q = rank
+ * and on a single GPU).  Synchronizes the stream: a logging call, not part of the cycle. */
+int hymd_exchange_cost(hymd_ctx* ctx, int64_t* sent_to, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Row f3: general-Poisson-equation electrostatics, coulombtype "PIC_Spectral_GPE".
  * NOT YET RUN ON A GPU (written after the round's GPU minutes were spent); single GPU only.

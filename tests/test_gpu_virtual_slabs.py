@@ -89,7 +89,9 @@ def _cycle(rank, cfg, pos, types, q, owner, tdt, steps, results):
     energies = F.compute_field_and_kinetic_energy(phi, phi_q, psi, vel, ham, pos_d, typ_d, v_ext, cfg, layouts)
     pm.check()
     st = pm.status()
+    cost = layouts[0].get_exchange_cost()           # collective (pmesh Layout.get_exchange_cost, main.py:1304-1312)
     results[rank] = {
+        "exchange_cost": cost,
         "idx": idx, "pos": pos_d.cpu().numpy(), "force": force_d.cpu().numpy(),
         "eforce": None if eforce_d is None else eforce_d.cpu().numpy(),
         "phi": [p.value.cpu().numpy() for p in phi],
@@ -140,6 +142,12 @@ def _run_and_compare(P, mesh, n, dtype, pme, mode, steps=1, env=None, monkeypatc
         checks["field_q_energy"] = abs(e_g[2] - e_o[2]) / max(abs(e_o[2]), 1e-300)
     bad = {k: v for k, v in checks.items() if not v < tol}
     assert not bad, f"P={P} mesh={mesh} mode={mode}: {bad}"
+    # Layout.get_exchange_cost: entry r = the particles rank r holds outside its own slab (its guests elsewhere)
+    cell = np.floor(gpos[:, 0].astype(np.float64) * mesh[0] / float(cfg.box_size[0])).astype(np.int64) % mesh[0]
+    home = cell // (mesh[0] // P)
+    want = np.array([np.count_nonzero((owner == r) & (home != r)) for r in range(P)])
+    for r in results:
+        assert np.array_equal(r["exchange_cost"], want), (r["exchange_cost"], want)
     return results
 
 

@@ -113,7 +113,9 @@ if os.path.exists(rep):
                                 ("xline_kernel", "kspace"), ("readout_kernel", "readout"),
                                 ("readout_gather_kernel", "readout"),
                                 ("plane_r2c_kernel", "fft_fwd"), ("plane_c2r_kernel", "fft_inv"),
-                                ("count_kernel", "sort_count"), ("scatter_kernel", "sort_scatter")):
+                                ("plane_r2c_tmem_kernel", "fft_fwd"), ("plane_c2r_tmem_kernel", "fft_inv"),
+                                ("count_kernel", "sort_count"), ("scatter_kernel", "sort_scatter"),
+                                ("count2_kernel", "sort_count"), ("scatter2_kernel", "sort_scatter")):
                     if frag in name:
                         traffic[k] = int(rd + wr)
             except Exception:

@@ -253,7 +253,8 @@ int hymd_ctx_create(const hymd_config* cfg, const uint8_t* nccl_id, hymd_ctx** o
     c->fused_push = c->xmode == 1;
     c->xcopy_kernel = !(xm && strcmp(xm, "blockedm") == 0);     // "blockedm": cudaMemcpyAsync (copy engines)
     // pipelined blocked exchange (slabfft.cu): HYMD_B200_XPIPE = 0 off, 1 when the pieces are large (default), 2 always
-    c->xpipe = 0; c->xstream = nullptr; c->plane_sm_reserve = 0;
+    c->xpipe = 0; c->xstream = nullptr; c->plane_sm_reserve = 0; c->sm_count = 0;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->dev);
     if (c->xmode == 2 && c->xcopy_kernel) {
         const char* xp = getenv("HYMD_B200_XPIPE");
         c->xpipe = xp ? atoi(xp) : 1;

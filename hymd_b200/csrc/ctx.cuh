@@ -224,6 +224,7 @@ struct hymd_ctx {
     // xmode == 2, pipelined exchange (slabfft.cu): the copies of field f run on a second, low-priority stream while
     // the plane kernel transforms field f + 1 (forward) / row u - 1 (inverse)
     int xpipe;              // 0 off, 1 on when a field's block is large enough, 2 always (tests)
+    int sm_count;           // multiprocessors of the device
     int plane_sm_reserve;   // > 0 while the pipeline runs: the persistent plane kernels leave this many SMs to the copies
     cudaStream_t xstream;                               // SM copy kernel variant (HYMD_B200_XPIPE_COPY=kernel)
     cudaEvent_t xev[2 * HYMD_MAX_TYPES + 2];             // "piece ready" on the main stream / copied (kernel variant)

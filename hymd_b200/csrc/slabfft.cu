@@ -306,11 +306,21 @@ __global__ void __launch_bounds__(256) block_copy2d_kernel(const uint4* __restri
     for (; w < total; w += stride) { const long long o = at(w); d[o] = __ldcs(s + o); }
 }
 
-// Is the per-field piece of a block big enough for the pipeline to pay?  (Every piece costs two launches and an
-// event; below ~4 MB the exchange is latency, not bandwidth.)
-static bool pipe_pieces(const hymd_ctx* c, long long piece_bytes, int pieces) {
-    if (c->xpipe == 0 || pieces < 2 || pieces > HYMD_MAX_TYPES || c->xstream == nullptr || piece_bytes % 16 != 0) return false;
-    return c->xpipe == 2 || piece_bytes >= (4LL << 20);
+// Pipeline plan: how many fields (potential rows) make one piece.  A piece is one launch of the persistent plane
+// kernel, so it needs about as many (field, plane) units as there are SMs -- nxl = 64 planes per field on 148 SMs ran
+// the 8-rank C5 cycle at 5.1 ms against 3.6 ms without the pipeline (profiles/r3i_*) -- and, unless forced, >= 4 MB
+// per destination (below that the exchange is latency, not bandwidth).  Returns 0: no pipeline (one piece).
+static int pipe_group(const hymd_ctx* c, int nfields, long long field_bytes) {
+    if (c->xpipe == 0 || nfields < 2 || nfields > HYMD_MAX_TYPES || c->xstream == nullptr || field_bytes % 16 != 0) return 0;
+    int group = 1;
+    if (c->xpipe != 2) {
+        const int sms = c->sm_count > 0 ? c->sm_count : 148;
+        group = (int)((0.8 * sms + c->g.nxl - 1) / c->g.nxl);
+        if (group < 1) group = 1;
+        if ((long long)group * field_bytes < (4LL << 20)) group = (int)(((4LL << 20) + field_bytes - 1) / field_bytes);
+    }
+    if (const char* e = getenv("HYMD_B200_XPIPE_GROUP")) group = atoi(e) > 0 ? atoi(e) : group;     // tests
+    return group < nfields ? group : 0;
 }
 
 // while alive, the persistent plane kernels keep 16 SMs free for the copy kernel of the second stream
@@ -476,21 +486,23 @@ int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t 
         HYMD_CHECK(peer_acquire(c, PEER_K, s));
         for (int q = 0; q < g.P; ++q)
             T.p[q] = q == g.rank ? k_out : (char*)c->wS + ((long long)q * block - (long long)g.x0 * l.xs) * (long long)csz;
-        const long long piece = (long long)g.nxl * l.fs * (long long)csz;       // bytes of one field inside a block
-        if (pipe_pieces(c, piece, F) && (l.fs * csz) % 16 == 0) {
-            // field f crosses NVLink (second stream) while the plane kernel transforms field f + 1
+        const int grp = (l.fs * csz) % 16 == 0 ? pipe_group(c, F, (long long)g.nxl * l.fs * (long long)csz) : 0;
+        if (grp > 0) {
+            // fields f .. f + cnt - 1 cross NVLink while the plane kernel transforms the next group
+            int piece = 0;
             if (c->xpipe_ce) {
                 // copy engines, one stream per destination: the SMs stay with the plane kernel (an SM copy kernel
                 // squeezed onto the 16-20 SMs the plane kernel leaves free reached a third of the NVLink rate)
-                for (int f = 0; f < F; ++f) {
-                    HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p, f, 1));
-                    HYMD_CUDA(cudaEventRecord(c->xev[f], s));
+                for (int f = 0; f < F; f += grp, ++piece) {
+                    const int cnt = F - f < grp ? F - f : grp;
+                    HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p, f, cnt));
+                    HYMD_CUDA(cudaEventRecord(c->xev[piece], s));
                     for (int i = 1; i < g.P; ++i) {
                         const int q = (g.rank + i) % g.P;
-                        HYMD_CUDA(cudaStreamWaitEvent(c->xpeer[q], c->xev[f], 0));
+                        HYMD_CUDA(cudaStreamWaitEvent(c->xpeer[q], c->xev[piece], 0));
                         HYMD_CUDA(cudaMemcpy2DAsync((char*)K.p[q] + ((size_t)g.x0 * l.xs + (size_t)f * l.fs) * csz, (size_t)l.xs * csz,
                                                     (char*)c->wS + ((size_t)q * block + (size_t)f * l.fs) * csz, (size_t)l.xs * csz,
-                                                    (size_t)l.fs * csz, (size_t)g.nxl, cudaMemcpyDeviceToDevice, c->xpeer[q]));
+                                                    (size_t)cnt * l.fs * csz, (size_t)g.nxl, cudaMemcpyDeviceToDevice, c->xpeer[q]));
                     }
                     c->launches += g.P - 1;
                 }
@@ -505,17 +517,18 @@ int fft_forward_yz(hymd_ctx* c, void* real_in, int F, void* k_out, cudaStream_t 
                 return HYMD_OK;
             }
             SmReserve reserve(c);
-            for (int f = 0; f < F; ++f) {
-                HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p, f, 1));
-                HYMD_CUDA(cudaEventRecord(c->xev[f], s));
-                HYMD_CUDA(cudaStreamWaitEvent(c->xstream, c->xev[f], 0));
+            for (int f = 0; f < F; f += grp, ++piece) {
+                const int cnt = F - f < grp ? F - f : grp;
+                HYMD_CHECK(plane_forward(c, real_in, g.real_elems, F, g.nxl, nullptr, 0, s, T.p, f, cnt));
+                HYMD_CUDA(cudaEventRecord(c->xev[piece], s));
+                HYMD_CUDA(cudaStreamWaitEvent(c->xstream, c->xev[piece], 0));
                 HYMD_CHECK(launch_copy2d(c, c->wS, K, (long long)(block * csz / 16), (long long)((size_t)g.x0 * l.xs * csz / 16),
-                                         (long long)((size_t)f * l.fs * csz / 16), (long long)(l.fs * csz / 16),
+                                         (long long)((size_t)f * l.fs * csz / 16), (long long)((size_t)cnt * l.fs * csz / 16),
                                          (long long)(l.xs * csz / 16), g.nxl, g.P - 1, 0, c->xstream));
             }
             PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
-            HYMD_CUDA(cudaEventRecord(c->xev[F], c->xstream));
-            HYMD_CUDA(cudaStreamWaitEvent(s, c->xev[F], 0));
+            HYMD_CUDA(cudaEventRecord(c->xev[piece], c->xstream));
+            HYMD_CUDA(cudaStreamWaitEvent(s, c->xev[piece], 0));
             HYMD_CHECK(comm_barrier(c, s));
             c->peer_busy |= PEER_K;
             return HYMD_OK;
@@ -584,10 +597,11 @@ int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost
             PeerPtrs W;
             HYMD_CHECK(peer_table(c, c->wA, &W, s));
             const int U = derive ? F / 3 : 0;
-            const long long piece = 2LL * g.nxl * lk.fs * (long long)csz;       // bytes of one potential row inside a block
-            if (derive && pipe_pieces(c, piece, U) && (lk.fs * csz) % 16 == 0) {
-                // the two spectra of potential row u cross NVLink (second stream) while the plane kernel turns row
-                // u - 1 into its three force meshes; one barrier per row tells every rank that the row has landed
+            const int grp = (derive && (lk.fs * csz) % 16 == 0) ? pipe_group(c, U, 2LL * g.nxl * lk.fs * (long long)csz) : 0;
+            if (grp > 0) {
+                // the spectra of potential rows u .. u + cnt - 1 cross NVLink while the plane kernel turns the previous
+                // group into its force meshes; one barrier per group tells every rank that the group has landed
+                const int npiece = (U + grp - 1) / grp;
                 if (c->xpipe_ce) {
                     {
                         PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
@@ -596,22 +610,24 @@ int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost
                         for (int i = 0; i < g.P; ++i) {
                             const int q = (g.rank + i) % g.P;
                             HYMD_CUDA(cudaStreamWaitEvent(c->xpeer[q], c->xev[0], 0));
-                            for (int u = 0; u < U; ++u) {
+                            for (int pc = 0; pc < npiece; ++pc) {
+                                const int u = pc * grp, cnt = U - u < grp ? U - u : grp;
                                 HYMD_CUDA(cudaMemcpy2DAsync((char*)W.p[q] + ((size_t)g.rank * block + (size_t)2 * u * lk.fs) * csz, (size_t)lk.xs * csz,
                                                             (char*)k_in + ((size_t)q * block + (size_t)2 * u * lk.fs) * csz, (size_t)lk.xs * csz,
-                                                            (size_t)2 * lk.fs * csz, (size_t)g.nxl, cudaMemcpyDeviceToDevice, c->xpeer[q]));
-                                HYMD_CUDA(cudaEventRecord(c->xdone[q][u], c->xpeer[q]));
+                                                            (size_t)2 * cnt * lk.fs * csz, (size_t)g.nxl, cudaMemcpyDeviceToDevice, c->xpeer[q]));
+                                HYMD_CUDA(cudaEventRecord(c->xdone[q][pc], c->xpeer[q]));
                             }
                         }
-                        c->launches += g.P * U;
+                        c->launches += g.P * npiece;
                     }
-                    for (int u = 0; u < U; ++u) {
+                    for (int pc = 0; pc < npiece; ++pc) {
+                        const int u = pc * grp, cnt = U - u < grp ? U - u : grp;
                         {
                             PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
-                            for (int q = 0; q < g.P; ++q) HYMD_CUDA(cudaStreamWaitEvent(s, c->xdone[q][u], 0));
+                            for (int q = 0; q < g.P; ++q) HYMD_CUDA(cudaStreamWaitEvent(s, c->xdone[q][pc], 0));
                             HYMD_CHECK(comm_barrier(c, s));
                         }
-                        HYMD_CHECK(plane_inverse(c, c->wA, 0, F, g.nxl, real_out, ghost, derive, s, true, u, 1));
+                        HYMD_CHECK(plane_inverse(c, c->wA, 0, F, g.nxl, real_out, ghost, derive, s, true, u, cnt));
                     }
                     c->peer_busy |= PEER_WORK;
                     return HYMD_OK;
@@ -621,22 +637,24 @@ int fft_inverse_xdone(hymd_ctx* c, void* k_in, int F, void* real_out, bool ghost
                     HYMD_CHECK(peer_acquire(c, PEER_WORK, s));
                     HYMD_CUDA(cudaEventRecord(c->xev[0], s));                   // the x-line kernel has written k_in
                     HYMD_CUDA(cudaStreamWaitEvent(c->xstream, c->xev[0], 0));
-                    for (int u = 0; u < U; ++u) {
+                    for (int pc = 0; pc < npiece; ++pc) {
+                        const int u = pc * grp, cnt = U - u < grp ? U - u : grp;
                         HYMD_CHECK(launch_copy2d(c, k_in, W, (long long)(block * csz / 16),
                                                  (long long)((size_t)g.rank * block * csz / 16),
-                                                 (long long)((size_t)2 * u * lk.fs * csz / 16), (long long)(2 * lk.fs * csz / 16),
+                                                 (long long)((size_t)2 * u * lk.fs * csz / 16), (long long)((size_t)2 * cnt * lk.fs * csz / 16),
                                                  (long long)(lk.xs * csz / 16), g.nxl, g.P, 1, c->xstream));
-                        HYMD_CUDA(cudaEventRecord(c->xev[1 + u], c->xstream));
+                        HYMD_CUDA(cudaEventRecord(c->xev[1 + pc], c->xstream));
                     }
                 }
                 SmReserve reserve(c);
-                for (int u = 0; u < U; ++u) {
+                for (int pc = 0; pc < npiece; ++pc) {
+                    const int u = pc * grp, cnt = U - u < grp ? U - u : grp;
                     {
                         PhaseScope ps(c, HYMD_PHASE_ALLTOALL, s);
-                        HYMD_CUDA(cudaStreamWaitEvent(s, c->xev[1 + u], 0));
+                        HYMD_CUDA(cudaStreamWaitEvent(s, c->xev[1 + pc], 0));
                         HYMD_CHECK(comm_barrier(c, s));
                     }
-                    HYMD_CHECK(plane_inverse(c, c->wA, 0, F, g.nxl, real_out, ghost, derive, s, true, u, 1));
+                    HYMD_CHECK(plane_inverse(c, c->wA, 0, F, g.nxl, real_out, ghost, derive, s, true, u, cnt));
                 }
                 c->peer_busy |= PEER_WORK;
                 return HYMD_OK;

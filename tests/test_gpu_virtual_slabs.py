@@ -204,5 +204,9 @@ def test_pipelined_exchange_matches_oracle(P, mesh, pme, dtype, monkeypatch):
                      env={"HYMD_B200_XPIPE": "2"}, monkeypatch=monkeypatch)          # pieces moved by the copy engines
     _run_and_compare(P, mesh, 20000, dtype, pme, "drifted", steps=3,
                      env={"HYMD_B200_XPIPE": "2", "HYMD_B200_XPIPE_COPY": "kernel"}, monkeypatch=monkeypatch)
+    # two fields / potential rows per piece (what the planner picks when a slab has fewer planes than the GPU has SMs):
+    # three types -> pieces {0, 1} and {2}
+    _run_and_compare(P, mesh, 20000, dtype, pme, "drifted", steps=2,
+                     env={"HYMD_B200_XPIPE": "2", "HYMD_B200_XPIPE_GROUP": "2", "HYMD_B200_XPIPE_COPY": "ce"}, monkeypatch=monkeypatch)
     _run_and_compare(P, mesh, 20000, dtype, pme, "drifted", steps=2,
                      env={"HYMD_B200_XPIPE": "0"}, monkeypatch=monkeypatch)

@@ -306,18 +306,19 @@ __global__ void __launch_bounds__(256) block_copy2d_kernel(const uint4* __restri
     for (; w < total; w += stride) { const long long o = at(w); d[o] = __ldcs(s + o); }
 }
 
-// Pipeline plan: how many fields (potential rows) make one piece.  A piece is one launch of the persistent plane
-// kernel, so it needs about as many (field, plane) units as there are SMs -- nxl = 64 planes per field on 148 SMs ran
-// the 8-rank C5 cycle at 5.1 ms against 3.6 ms without the pipeline (profiles/r3i_*) -- and, unless forced, >= 4 MB
-// per destination (below that the exchange is latency, not bandwidth).  Returns 0: no pipeline (one piece).
+// Pipeline plan: how many fields (potential rows) make one piece; 0 = no pipeline (one piece).  A piece is one launch
+// of the persistent plane kernel, so one field must bring about as many (field, plane) units as there are SMs:
+//   2 ranks, C4 (128 planes per field on 148 SMs): 1.364 -> 1.264 ms per cycle with per-field pieces (profiles/r3e_*)
+//   4 ranks, C4 ( 64 planes): two fields per piece 0.907 ms against 0.899 ms without the pipeline (profiles/r3k_*)
+//   8 ranks, C5 ( 64 planes): per-field pieces 5.09 ms against 3.59 ms without (profiles/r3i_*)
+// so the pipeline is used when a slab has >= 0.75 x SMs planes (and a piece is >= 4 MB per destination: below that the
+// exchange is latency, not bandwidth).  HYMD_B200_XPIPE=2 forces it, HYMD_B200_XPIPE_GROUP sets the piece (tests).
 static int pipe_group(const hymd_ctx* c, int nfields, long long field_bytes) {
     if (c->xpipe == 0 || nfields < 2 || nfields > HYMD_MAX_TYPES || c->xstream == nullptr || field_bytes % 16 != 0) return 0;
     int group = 1;
     if (c->xpipe != 2) {
         const int sms = c->sm_count > 0 ? c->sm_count : 148;
-        group = (int)((0.8 * sms + c->g.nxl - 1) / c->g.nxl);
-        if (group < 1) group = 1;
-        if ((long long)group * field_bytes < (4LL << 20)) group = (int)(((4LL << 20) + field_bytes - 1) / field_bytes);
+        if (4 * c->g.nxl < 3 * sms || field_bytes < (4LL << 20)) return 0;
     }
     if (const char* e = getenv("HYMD_B200_XPIPE_GROUP")) group = atoi(e) > 0 ? atoi(e) : group;     // tests
     return group < nfields ? group : 0;

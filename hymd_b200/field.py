@@ -142,7 +142,22 @@ def compute_self_energy_q(config, charges, comm=None):
 def update_field_force_q(charges, phi_q, phi_q_fourier, psi, psi_fourier, elec_field_fourier,
                          elec_field, elec_forces, layout_q, hamiltonian, pm, positions, config):
     """PME electrostatics (``field.py:241-403``): charge density, Poisson solve with the
-    Gaussian filter, E = -grad psi, forces q*E written in place into ``elec_forces``."""
+    Gaussian filter, E = -grad psi, forces q*E written in place into ``elec_forces``.
+
+    Called with mesh arguments that are not the handles of ``initialize_pm`` -- the peptide-dipole call of
+    ``main.py:1060-1095`` passes ``pm.create`` meshes and the reconstructed dipole charges / positions -- the
+    cycle runs in a second context (``pm.secondary_pme``), so the charge density and potential of the real
+    charges, which the energy print reads afterwards, are left alone.  The passed meshes are opaque to
+    ``main.py`` and are not filled."""
+    if not isinstance(phi_q, MeshField) and getattr(pm, "pme", False) and not getattr(pm, "gpe", False):
+        sec = pm.secondary_pme(config)
+        sec.sort(positions, None, charges)
+        n = sec._n_local
+        buf, back = _output_buffer(sec, elec_forces, n)
+        _lib.check(sec.lib.hymd_pme_cycle(sec._ctx, ctypes.c_void_p(buf.data_ptr()), 0, sec.stream))
+        if back is not None:
+            back()
+        return
     pm.sync_interaction(hamiltonian, config)
     pm.sort(positions, None, charges)
     n = pm._n_local

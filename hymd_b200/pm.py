@@ -226,7 +226,32 @@ class ParticleMesh:
         _lib.check(self.lib.hymd_ctx_set_box(self._ctx, self.BoxSize.ctypes.data_as(dp)))
         self._sort_key = None
 
+    def secondary_pme(self, config):
+        """A second particle-mesh context on the same mesh for PME calls on ANOTHER particle set with its own
+        meshes -- the peptide backbone dipoles of ``main.py:1060-1095`` (``phi_dipoles``, ``psi_dipoles``, ... come
+        from ``pm.create``).  The reference keeps those results in separate pmesh fields so that ``phi_q`` / ``psi``
+        of the real charges survive for the energy print (``field.py:697-699``); here the second set gets its own
+        one-type context (charge density, spectrum, potential, three field meshes), created on first use
+        (collective on several GPUs) and re-boxed when a barostat has changed the box."""
+        sec = getattr(self, "_secondary", None)
+        if sec is None:
+            from types import SimpleNamespace
+            cfg = SimpleNamespace(
+                n_types=1, mesh_size=[int(x) for x in self.Nmesh], box_size=self.BoxSize.copy(),
+                dtype=np.float64 if self.np_dtype == np.dtype("f8") else np.float32,
+                sigma=float(config.sigma), coulombtype="PIC_Spectral", m=[1.0],
+                coulomb_constant=float(config.coulomb_constant), dielectric_const=float(config.dielectric_const))
+            sec = ParticleMesh(self.Nmesh, BoxSize=self.BoxSize, dtype=self.np_dtype, comm=self.comm, config=cfg)
+            self._secondary = sec
+        if not np.array_equal(sec.BoxSize, self.BoxSize):
+            sec.set_box(self.BoxSize)
+        return sec
+
     def close(self):
+        sec = getattr(self, "_secondary", None)
+        if sec is not None:
+            sec.close()
+            self._secondary = None
         if self._ctx:
             self.lib.hymd_ctx_destroy(self._ctx)
             self._ctx = ctypes.c_void_p()

@@ -303,6 +303,52 @@ def test_kernel_variants_match_oracle(dtype, env, monkeypatch):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mesh", [[32, 32, 32], [24, 20, 28]])
+def test_second_pme_call_on_another_particle_set(dtype, mesh):
+    """The peptide-dipole call of main.py:1060-1095: ``update_field_force_q`` with the reconstructed dipole charges /
+    positions (another particle set, 4 point charges per torsion) and meshes from ``pm.create``.  Forces on the
+    dipoles equal the oracle's PME forces for that set, and the charge density / potential / electrostatic energy
+    of the real charges are unchanged afterwards (the reference keeps the two in separate pmesh fields)."""
+    from gpu_common import GpuRun, OracleRun, rel_err
+    from hymd_b200 import field as F
+    cfg, pos, types, q = _system(9000, mesh, [4.0, 5.0, 6.0], dtype, seed=71, coulomb=True)
+    g = GpuRun(cfg, pos, types, charges=q)
+    vel = torch.zeros_like(g.pos)
+    e_before = g.energies(vel)
+    psi_before = g.psi.value.cpu().numpy().copy()
+    rng = np.random.default_rng(5)
+    n_tors = 37
+    dip_pos = (rng.uniform(0, 1, size=(4 * n_tors, 3)) * np.asarray(cfg.box_size)).astype(dtype)
+    dip_q = np.tile(np.array([0.25, -0.25, 0.25, -0.25]), n_tors).astype(dtype)
+    pm = g.pm
+    phi_d, psi_d = pm.create("real", value=0.0), pm.create("real", value=0.0)
+    phi_df, psi_df = pm.create("complex", value=0.0), pm.create("complex", value=0.0)
+    field_df = [pm.create("complex", value=0.0) for _ in range(3)]
+    field_d = [pm.create("real", value=0.0) for _ in range(3)]
+    for as_numpy in (False, True):
+        if as_numpy:
+            dq, dp, df = dip_q, dip_pos, np.zeros((4 * n_tors, 3), dtype=dtype)
+        else:
+            dq = torch.as_tensor(dip_q, device="cuda")
+            dp = torch.as_tensor(dip_pos, device="cuda")
+            df = torch.zeros((4 * n_tors, 3), dtype=dq.dtype, device="cuda")
+        F.update_field_force_q(dq, phi_d, phi_df, psi_d, psi_df, field_df, field_d, df, pm.decompose(dp),
+                               g.h, pm, dp, cfg)
+        got = df if as_numpy else df.cpu().numpy()
+        o = OracleRun(cfg, dip_pos, np.zeros(4 * n_tors, dtype=np.int32), charges=dip_q)
+        assert rel_err(got, o.elec_forces) < TOL[dtype]
+    torch.cuda.synchronize()
+    e_after = g.energies(vel)
+    assert e_after == e_before
+    assert np.array_equal(psi_before, g.psi.value.cpu().numpy())
+    # ... and the real charges can be cycled again afterwards
+    F.update_field_force_q(g.q, g.phi_q, g.phi_q_fourier, g.psi, None, None, g.elec_field, g.elec_forces,
+                           pm.decompose(None), g.h, pm, g.pos, cfg)
+    o2 = OracleRun(cfg, pos, types, charges=q)
+    assert rel_err(g.eforces(), o2.elec_forces) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("mesh,n", [([32, 64, 64], 60000), ([24, 20, 28], 9000), ([16, 16, 80], 200000), ([9, 12, 10], 700)])
 def test_paint_kernels_are_bitwise_identical(dtype, mesh, n, monkeypatch):
     """The flattened-list paint (default) and the row-walker paint (HYMD_B200_PAINT=rows: a lane per cell row,

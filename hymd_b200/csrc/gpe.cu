@@ -97,7 +97,11 @@ __global__ void __launch_bounds__(256) gpe_sum_kernel(const real* __restrict__ a
 template <typename real>
 __global__ void __launch_bounds__(256) gpe_pol_kernel(const real* __restrict__ eta, const real* __restrict__ E,
                                                       long long fs, real w, real* __restrict__ pol, int mode,
-                                                      double* __restrict__ partial, long long n) {
+                                                      double* __restrict__ partial, long long n,
+                                                      const double* __restrict__ state) {
+    // state = {delta of the last counted iteration, iterations counted, conv_crit}: once delta <= conv_crit the
+    // fixed point has stopped (field.py:1062-1064) and further launches of the un-synchronised batch change nothing
+    if (state[0] <= state[2]) return;
     double acc = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -123,8 +127,10 @@ __global__ void __launch_bounds__(256) gpe_pol_kernel(const real* __restrict__ e
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
+// out = {delta, iterations, conv_crit} when `gate` (the polarisation loop): a converged loop is left alone
 __global__ void __launch_bounds__(256) gpe_reduce_kernel(const double* __restrict__ partial, int nblocks, int mode,
-                                                         double scale, double* __restrict__ out) {
+                                                         double scale, double* __restrict__ out, int gate) {
+    if (gate && out[0] <= out[2]) return;
     __shared__ double sh[256];
     double acc = 0.0;
     for (int i = threadIdx.x; i < nblocks; i += 256) acc = mode == 0 ? (partial[i] > acc ? partial[i] : acc) : acc + partial[i];
@@ -137,7 +143,10 @@ __global__ void __launch_bounds__(256) gpe_reduce_kernel(const double* __restric
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = sh[0] * scale;
+    if (threadIdx.x == 0) {
+        out[0] = sh[0] * scale;
+        if (gate) out[1] += 1.0;
+    }
 }
 
 // elec_dot = |E|^2, elec_field_contrib = elec_dot / den where den > 1e-6, and
@@ -210,7 +219,7 @@ static int gpe_state(hymd_ctx* c) {
     HYMD_CHECK(galloc(&st->kS, kb, true));
     HYMD_CHECK(galloc(&st->mesh, (size_t)3 * T * gb, true));
     HYMD_CHECK(galloc((void**)&st->d_par, sizeof(double) * 2 * HYMD_MAX_TYPES, true));
-    HYMD_CHECK(galloc((void**)&st->red, sizeof(double) * (GPE_BLOCKS + 2), true));
+    HYMD_CHECK(galloc((void**)&st->red, sizeof(double) * (GPE_BLOCKS + 4), true));
     HYMD_CHECK(galloc(&c->psi, rb, true));
     if (!st->urow_id) {
         HYMD_CHECK(galloc((void**)&st->urow_id, sizeof(int) * HYMD_MAX_TYPES, true));
@@ -219,7 +228,7 @@ static int gpe_state(hymd_ctx* c) {
         HYMD_CUDA(cudaMemcpy(st->urow_id, id, sizeof(id), cudaMemcpyHostToDevice));
         HYMD_CUDA(cudaDeviceSynchronize());
     }
-    if (!st->h_delta) HYMD_CUDA(cudaMallocHost((void**)&st->h_delta, 2 * sizeof(double)));
+    if (!st->h_delta) HYMD_CUDA(cudaMallocHost((void**)&st->h_delta, 4 * sizeof(double)));
     return HYMD_OK;
 }
 
@@ -282,25 +291,37 @@ static int gpe_cycle_t(hymd_ctx* c, const hymd_gpe_params* prm, void* d_force, i
     HYMD_LAUNCH_CHECK(c);
     // polarisation-charge fixed point (field.py:1037-1064), from zero at every call
     HYMD_CUDA(cudaMemsetAsync(st->pol, 0, (size_t)n * sizeof(real), s));
-    int it = 0;
-    double delta = 1.0;
+    // The convergence test runs on the device: {delta, iterations, conv_crit} live in st->red + GPE_BLOCKS, the
+    // update and the reduction of an iteration are skipped once delta <= conv_crit, and the host looks at the state
+    // only once per batch of GPE_BATCH iterations (it was one stream synchronisation per iteration).  The iterations
+    // of a batch that come after convergence only recompute scratch (tmp, E), which the next stage overwrites.
+    constexpr int GPE_BATCH = 4;
     const int max_iter = prm->max_iter > 0 ? prm->max_iter : 100;
-    while (it < max_iter && delta > prm->conv_crit) {
-        gpe_sum_kernel<real><<<GPE_BLOCKS, 256, 0, s>>>(phi_q, (const real*)st->pol, (real)1, (real*)st->tmp, n);
-        HYMD_LAUNCH_CHECK(c);
-        HYMD_CHECK(fft_forward(c, st->tmp, 1, st->kA, s));
-        HYMD_CHECK(kspace<real>(c, st->kA, 1, nullptr, st->kB, 1.0 / M, false, true, -1.0, s));
-        HYMD_CHECK(fft_inverse(c, st->kB, 3, st->E, false, s));
-        gpe_pol_kernel<real><<<GPE_BLOCKS, 256, 0, s>>>((const real*)st->eta, (const real*)st->E, fs,
-                                                        (real)prm->pol_mixing, (real*)st->pol,
-                                                        prm->convergence_type, st->red, n);
-        HYMD_LAUNCH_CHECK(c);
-        gpe_reduce_kernel<<<1, 256, 0, s>>>(st->red, GPE_BLOCKS, prm->convergence_type, 1.0, st->red + GPE_BLOCKS);
-        HYMD_LAUNCH_CHECK(c);
-        HYMD_CUDA(cudaMemcpyAsync(st->h_delta, st->red + GPE_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, s));
+    double* state = st->red + GPE_BLOCKS;
+    st->h_delta[0] = 1.0; st->h_delta[1] = 0.0; st->h_delta[2] = prm->conv_crit;     // the reference starts from delta = 1
+    HYMD_CUDA(cudaMemcpyAsync(state, st->h_delta, 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    int it = 0, launched = 0;
+    double delta = 1.0;
+    while (launched < max_iter && delta > prm->conv_crit) {
+        const int batch = max_iter - launched < GPE_BATCH ? max_iter - launched : GPE_BATCH;
+        for (int b = 0; b < batch; ++b) {
+            gpe_sum_kernel<real><<<GPE_BLOCKS, 256, 0, s>>>(phi_q, (const real*)st->pol, (real)1, (real*)st->tmp, n);
+            HYMD_LAUNCH_CHECK(c);
+            HYMD_CHECK(fft_forward(c, st->tmp, 1, st->kA, s));
+            HYMD_CHECK(kspace<real>(c, st->kA, 1, nullptr, st->kB, 1.0 / M, false, true, -1.0, s));
+            HYMD_CHECK(fft_inverse(c, st->kB, 3, st->E, false, s));
+            gpe_pol_kernel<real><<<GPE_BLOCKS, 256, 0, s>>>((const real*)st->eta, (const real*)st->E, fs,
+                                                            (real)prm->pol_mixing, (real*)st->pol,
+                                                            prm->convergence_type, st->red, n, state);
+            HYMD_LAUNCH_CHECK(c);
+            gpe_reduce_kernel<<<1, 256, 0, s>>>(st->red, GPE_BLOCKS, prm->convergence_type, 1.0, state, 1);
+            HYMD_LAUNCH_CHECK(c);
+        }
+        launched += batch;
+        HYMD_CUDA(cudaMemcpyAsync(st->h_delta, state, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
         HYMD_CUDA(cudaStreamSynchronize(s));
         delta = st->h_delta[0];
-        ++it;
+        it = (int)st->h_delta[1];
     }
     if (iterations) *iterations = it;
     // potential and field (field.py:1066-1084)
@@ -342,7 +363,7 @@ int gpe_energy(hymd_ctx* c, double coulomb_constant, double* out, cudaStream_t s
     HYMD_LAUNCH_CHECK(c);
     const double dv = g.box[0] * g.box[1] * g.box[2] / ((double)g.Nx * g.Ny * g.Nz);
     const double eps_0 = 1.0 / (coulomb_constant * 4.0 * 3.14159265358979323846);
-    gpe_reduce_kernel<<<1, 256, 0, s>>>(st->red, GPE_BLOCKS, 1, dv * 0.5 * eps_0, st->red + GPE_BLOCKS);
+    gpe_reduce_kernel<<<1, 256, 0, s>>>(st->red, GPE_BLOCKS, 1, dv * 0.5 * eps_0, st->red + GPE_BLOCKS, 0);
     HYMD_LAUNCH_CHECK(c);
     HYMD_CUDA(cudaMemcpyAsync(st->h_delta, st->red + GPE_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, s));
     HYMD_CUDA(cudaStreamSynchronize(s));

@@ -139,3 +139,88 @@ def test_pressure_byproducts_are_virials():
     a3 = np.arange(4)
     f, e, pr = bo.compute_angle_forces(r, box, a3, a3 + 1, a3 + 2, np.full(4, 2.0), np.full(4, 25.0))
     np.testing.assert_allclose(pr, np.sum(r * f, axis=0), rtol=1e-10, atol=1e-10)
+
+
+def _cbt_system(seed=11, n=7):
+    """A short backbone: n beads, n-3 dihedrals of dtype 1, the last one flagged (its second angle is reconstructed)."""
+    rng = np.random.default_rng(seed)
+    r = np.cumsum(rng.normal(scale=0.33, size=(n, 3)), axis=0) + np.array([2.0, 2.5, 3.0])
+    box = np.array([5.0, 6.0, 7.0])
+    a = np.arange(n - 3)
+    coeff = np.zeros((n - 3, 6, 5))
+    coeff[:, 0] = rng.uniform(0.5, 2.0, size=(n - 3, 5))
+    coeff[:, 1] = rng.uniform(-1, 1, size=(n - 3, 5))
+    coeff[:, 4] = rng.uniform(20, 60, size=(n - 3, 5))       # k(phi) series of the bending constant
+    coeff[:, 5] = rng.uniform(-1, 1, size=(n - 3, 5))
+    dt = np.ones(n - 3, dtype=int)
+    last = np.zeros(n - 3, dtype=int)
+    last[-1] = 1
+    return r, box, (a, a + 1, a + 2, a + 3), coeff, dt, last
+
+
+def test_cbt_forces_are_negative_energy_gradients():
+    """dtype 1 (compute_dihedral_forces.f90:77-112 + reconstruct): propensity series + k(phi) (gamma - gamma_0(phi))^2
+    on the angle a-b-c of every dihedral and on b-c-d of the last one; the forces (dihedral part with the extra
+    dE/dphi of the bending term, minus the angle parts) are the negative gradient of the returned energy."""
+    r, box, idx, coeff, dt, last = _cbt_system()
+    f, e = bo.compute_dihedral_forces(r, box, *idx, coeff, dt, last)
+    g = _num_grad(lambda x: bo.compute_dihedral_forces(x, box, *idx, coeff, dt, last)[1], r)
+    np.testing.assert_allclose(f, -g, rtol=0, atol=2e-6 * np.abs(f).max())
+    assert np.abs(f.sum(axis=0)).max() < 1e-9 * np.abs(f).max()
+    # the flag of the last dihedral matters, and dipole_flag does not change forces or energy
+    f0, e0 = bo.compute_dihedral_forces(r, box, *idx, coeff, dt, np.zeros_like(last))
+    assert abs(e - e0) > 1e-3
+    f1, e1, dip, tm = bo.compute_dihedral_forces(r, box, *idx, coeff, dt, last, dipole_flag=1, full=True)
+    assert e1 == e and np.array_equal(f1, f)
+    assert np.all(dip[:-1, 2:] == 0) and np.all(tm[:-1, 3:] == 0) and np.any(dip[-1, 2:] != 0)
+
+
+def test_cbt_dipoles_and_transfer_matrices():
+    """Geometry of the reconstructed dipole: the two charges sit delta = 0.3 nm apart, centred on the middle of the
+    b-c bond.  The transfer matrices: with the sign of the three gamma-derivative terms flipped (see
+    ``bonded_oracle.reconstruct``) they are the exact Jacobians d d / d r_i at fixed phi -- this pins every other
+    term of the restatement; the default keeps the reference's sign."""
+    rng = np.random.default_rng(3)
+    ra, rb, rc = rng.normal(size=(3, 3)) + 2.0
+    box = np.array([50.0, 50.0, 50.0])
+    c_k, d_k, phi = np.array([30.0, 5, 2, 1, 0.5]), np.array([0.1, 0.2, -0.3, 0.4, 0.0]), 0.7
+
+    def half(ra, rb, rc, sign):
+        rec = bo.reconstruct(ra - rb, rb, rc - rb, box, c_k, d_k, phi, 1, gamma_sign=sign)
+        return 0.5 * (rec[5][0] - rec[5][1]), 0.5 * (rec[5][0] + rec[5][1]), rec[6]
+    d, centre, T_ref = half(ra, rb, rc, 1.0)
+    assert np.linalg.norm(2 * d) == pytest.approx(0.3, rel=1e-6)     # cos_psi, sin_psi are single-precision constants
+    np.testing.assert_allclose(centre, 0.5 * (rb + rc), atol=1e-12)
+    _, _, T = half(ra, rb, rc, -1.0)
+    assert np.abs(T - T_ref).max() > 1e-2 * np.abs(T).max()
+    h = 1e-6
+    for which in range(3):
+        J = np.zeros((3, 3))
+        for k in range(3):
+            p, m = [ra.copy(), rb.copy(), rc.copy()], [ra.copy(), rb.copy(), rc.copy()]
+            p[which][k] += h
+            m[which][k] -= h
+            J[k] = (half(*p, -1.0)[0] - half(*m, -1.0)[0]) / (2 * h)
+        np.testing.assert_allclose(T[which], J, rtol=0, atol=1e-8)
+
+
+def test_dipole_force_redistribution_is_the_chain_rule():
+    """hymd/force.py:855-880: f_bead = sum_i D_i (f_+ - f_-) + 1/2 (f_+ + f_-) on the two beads of the bond that
+    carries the dipole; total force is conserved for the centre term."""
+    r, box, idx, coeff, dt, last = _cbt_system(seed=5)
+    _, _, dip, tm = bo.compute_dihedral_forces(r, box, *idx, coeff, dt, last, dipole_flag=1, full=True)
+    rng = np.random.default_rng(2)
+    fd = rng.normal(size=dip.shape)
+    out = bo.dipole_forces_redistribution(len(r), fd, tm, *idx, dt, last)
+    want = np.zeros_like(out)
+    for t, (i, j, k, l) in enumerate(zip(*idx)):
+        s, df = fd[t, 0] + fd[t, 1], fd[t, 0] - fd[t, 1]
+        want[i] += tm[t, 0].astype(float) @ df
+        want[j] += tm[t, 1].astype(float) @ df + 0.5 * s
+        want[k] += tm[t, 2].astype(float) @ df + 0.5 * s
+        if last[t]:
+            s, df = fd[t, 2] + fd[t, 3], fd[t, 2] - fd[t, 3]
+            want[j] += tm[t, 3].astype(float) @ df
+            want[k] += tm[t, 4].astype(float) @ df + 0.5 * s
+            want[l] += tm[t, 5].astype(float) @ df + 0.5 * s
+    np.testing.assert_allclose(out, want, atol=1e-12)

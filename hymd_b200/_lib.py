@@ -34,6 +34,7 @@ EXPORTS = [
     "hymd_csvr_apply", "hymd_cancel_com",
     "hymd_gpe_cycle", "hymd_gpe_energy",
     "hymd_local_group_id", "hymd_ctx_check", "hymd_exchange_cost",
+    "hymd_bonded_set_last", "hymd_bonded_dipoles", "hymd_dipole_redistribute",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -148,6 +149,9 @@ def load():
     lib.hymd_bonded_inner_step.argtypes = [vp, ctypes.c_int, vp, vp, vp, P(dbl), dbl, dbl, ctypes.c_int, dbl,
                                            P(vp), F64P, vp]
     lib.hymd_bonded_set_cta.argtypes = [vp, ctypes.c_int]
+    lib.hymd_bonded_set_last.argtypes = [vp, I32P]
+    lib.hymd_bonded_dipoles.argtypes = [vp, ctypes.c_int, vp, P(dbl), vp, vp, vp]
+    lib.hymd_dipole_redistribute.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
     lib.hymd_bonded_set_math.argtypes = [vp, ctypes.c_int]
     lib.hymd_bonded_launch_count.argtypes = [vp]
     lib.hymd_bonded_launch_count.restype = i64

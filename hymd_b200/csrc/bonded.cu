@@ -16,6 +16,8 @@ struct hymd_bonded {
     int32_t* idx[3];             // [n_terms][4]
     double* par[3];              // [n_terms][2] / [n_terms][30]
     int32_t* dih_type;           // [n4]
+    int32_t* dih_last;           // [n4] bonds_4_last: 1 = last dihedral of a backbone (hymd_bonded_set_last)
+    long long n_cbt;             // dihedrals of dih_type 1 (combined bending-torsion)
     uint32_t* cta_start[3];      // CTA-cooperative evaluation (bonded.cuh, CtaLists)
     uint32_t* cta_terms[3];
     uint32_t* lrefs[3];
@@ -334,6 +336,99 @@ __global__ void __launch_bounds__(256) bonded_final_kernel(const double* __restr
     if (threadIdx.x < 4) out[threadIdx.x] = sh[threadIdx.x][0];
 }
 
+// ---- dtype-1 dihedrals (bonded.cuh: cbt_eval, dipole_term, redistribute_term) ---------------------------
+// The bending term of the combined bending-torsion dihedrals, gathered per particle like everything else here (no
+// atomics, fixed order) and ADDED to the force array the dihedral kernel has just written; energy into `partial`.
+// A separate pass: topologies without dtype 1 never launch it and the hot kernels keep their registers.
+template <typename real>
+__global__ void __launch_bounds__(BONDED_THREADS) cbt_kernel(
+    const real* __restrict__ pos, long long n, Vec3d box, const uint32_t* __restrict__ start,
+    const uint32_t* __restrict__ refs, const int32_t* __restrict__ idx, const double* __restrict__ par,
+    const int32_t* __restrict__ dtype, const int32_t* __restrict__ last, real* __restrict__ force,
+    double* __restrict__ partial) {
+    const long long p = (long long)blockIdx.x * BONDED_THREADS + threadIdx.x;
+    double e_acc = 0.0;
+    if (p < n) {
+        Vec3d acc = {0.0, 0.0, 0.0};
+        bool any = false;
+        for (uint32_t k = start[p]; k < start[p + 1]; ++k) {
+            const long long t = refs[k] >> 2;
+            const int slot = (int)(refs[k] & 3u);
+            if (dtype[t] != 1) continue;
+            const int32_t* ix = idx + 4 * t;
+            Vec3d out[4];
+            double e;
+            cbt_eval(pos, box, ix[0], ix[1], ix[2], ix[3], par + (long long)DIH_ROWS * DIH_COLS * t, last[t], out, e);
+            acc = acc + out[slot];
+            if (slot == 0) e_acc += e;
+            any = true;
+        }
+        if (any) {
+            force[3 * p + 0] = (real)((double)force[3 * p + 0] + acc.x);
+            force[3 * p + 1] = (real)((double)force[3 * p + 1] + acc.y);
+            force[3 * p + 2] = (real)((double)force[3 * p + 2] + acc.z);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e_acc += __shfl_down_sync(0xffffffffu, e_acc, o);
+    __shared__ double sh[BONDED_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sh[warp] = e_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < BONDED_THREADS / 32; ++w2) s += sh[w2];
+        partial[blockIdx.x] = s;
+    }
+}
+
+// out[0] += sum of the block partials (fixed order)
+__global__ void __launch_bounds__(256) cbt_final_kernel(const double* __restrict__ partial, int nblocks,
+                                                        double* __restrict__ out) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 256) acc += partial[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] += sh[0];
+}
+
+// one thread per dihedral: its (4,3) dipole positions and (6,3,3) transfer matrices (zeros unless dtype 1)
+template <typename real>
+__global__ void __launch_bounds__(BONDED_THREADS) dipole_kernel(
+    const real* __restrict__ pos, long long n4, Vec3d box, const int32_t* __restrict__ idx,
+    const double* __restrict__ par, const int32_t* __restrict__ dtype, const int32_t* __restrict__ last,
+    real* __restrict__ dipoles, real* __restrict__ transfer) {
+    const long long t = (long long)blockIdx.x * BONDED_THREADS + threadIdx.x;
+    if (t >= n4) return;
+    const int32_t* ix = idx + 4 * t;
+    dipole_term<real>(pos, box, ix[0], ix[1], ix[2], ix[3], par + (long long)DIH_ROWS * DIH_COLS * t, dtype[t], last[t],
+                      dipoles + 12 * t, transfer + 54 * t);
+}
+
+// dipole_forces_redistribution (force.py:855-880), gathered per bead in ascending dihedral order
+template <typename real>
+__global__ void __launch_bounds__(BONDED_THREADS) redistribute_kernel(
+    long long n, const uint32_t* __restrict__ start, const uint32_t* __restrict__ refs,
+    const int32_t* __restrict__ dtype, const int32_t* __restrict__ last, const real* __restrict__ f_dipoles,
+    const real* __restrict__ transfer, real* __restrict__ f_beads) {
+    const long long p = (long long)blockIdx.x * BONDED_THREADS + threadIdx.x;
+    if (p >= n) return;
+    Vec3d acc = {0.0, 0.0, 0.0};
+    for (uint32_t k = start[p]; k < start[p + 1]; ++k) {
+        const long long t = refs[k] >> 2;
+        if (dtype[t] != 1) continue;
+        acc = acc + redistribute_term<real>((int)(refs[k] & 3u), last[t], f_dipoles + 12 * t, transfer + 54 * t);
+    }
+    f_beads[3 * p + 0] = (real)acc.x;
+    f_beads[3 * p + 1] = (real)acc.y;
+    f_beads[3 * p + 2] = (real)acc.z;
+}
+
 template <typename T>
 static int to_device(T** dst, const T* src, size_t count) {
     *dst = nullptr;
@@ -373,6 +468,9 @@ static int upload_kind(hymd_bonded* b, int kind, long long n_terms, int slots,
 }
 
 template <typename real>
+static int launch_cbt(hymd_bonded* b, const real* pos, Vec3d box, real* force, double* d_out, cudaStream_t s);
+
+template <typename real>
 static int launch_kind(hymd_bonded* b, int kind, const real* pos, Vec3d box, real* force, double* d_out,
                        cudaStream_t s) {
     const long long n = b->n_particles;
@@ -398,6 +496,21 @@ static int launch_kind(hymd_bonded* b, int kind, const real* pos, Vec3d box, rea
         HYMD_LAUNCH_CHECK(b);
     }
     bonded_final_kernel<<<1, 256, 0, s>>>(b->partial, blocks, d_out);
+    HYMD_LAUNCH_CHECK(b);
+    if (kind == 2) return launch_cbt<real>(b, pos, box, force, d_out, s);
+    return HYMD_OK;
+}
+
+// the bending term of the dtype-1 dihedrals on top of a dihedral force array / energy just computed on stream s
+template <typename real>
+static int launch_cbt(hymd_bonded* b, const real* pos, Vec3d box, real* force, double* d_out, cudaStream_t s) {
+    if (b->n_cbt == 0 || b->n_particles == 0) return HYMD_OK;
+    const long long n = b->n_particles;
+    const int blocks = (int)((n + BONDED_THREADS - 1) / BONDED_THREADS);
+    cbt_kernel<real><<<blocks, BONDED_THREADS, 0, s>>>(pos, n, box, b->start[2], b->refs[2], b->idx[2], b->par[2],
+                                                       b->dih_type, b->dih_last, force, b->partial);
+    HYMD_LAUNCH_CHECK(b);
+    cbt_final_kernel<<<1, 256, 0, s>>>(b->partial, blocks, d_out);
     HYMD_LAUNCH_CHECK(b);
     return HYMD_OK;
 }
@@ -507,15 +620,19 @@ int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const
         return HYMD_ERR_INVALID;
     }
     if (n_particles >= (1LL << 31)) { set_error("more than 2^31 particles per GPU"); return HYMD_ERR_INVALID; }
-    for (int64_t t = 0; t < n4; ++t)
-        if (type4[t] != 0 && type4[t] != 2) {
-            set_error("dihedral %lld has dih_type %d: only 0 (cosine series) and 2 (improper) are built; "
-                      "1 (combined bending-torsion + dipole reconstruction) is not", (long long)t, type4[t]);
+    long long n_cbt = 0;
+    for (int64_t t = 0; t < n4; ++t) {
+        if (type4[t] < 0 || type4[t] > 2) {
+            set_error("dihedral %lld has dih_type %d: expected 0 (cosine series), 1 (combined bending-torsion) or "
+                      "2 (improper)", (long long)t, type4[t]);
             return HYMD_ERR_INVALID;
         }
+        n_cbt += type4[t] == 1;
+    }
     hymd_bonded* b = new hymd_bonded();
     memset(b, 0, sizeof(*b));
     b->n_particles = n_particles;
+    b->n_cbt = n_cbt;
     b->tile = BONDED_THREADS;
     if (const char* env = getenv("HYMD_B200_BONDED_TILE")) {
         const int tile = atoi(env);
@@ -555,6 +672,10 @@ int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t* a2, const
     }
     if (st == HYMD_OK) st = to_device(&b->dih_type, type4, (size_t)n4);
     if (st == HYMD_OK) {
+        std::vector<int32_t> zeros((size_t)n4, 0);
+        st = to_device(&b->dih_last, zeros.data(), (size_t)n4);
+    }
+    if (st == HYMD_OK) {
         b->max_blocks = (int)((n_particles + BONDED_THREADS - 1) / BONDED_THREADS);
         cudaError_t e = cudaMalloc((void**)&b->partial, sizeof(double) * 12 * (size_t)(b->max_blocks + 1));
         if (e != cudaSuccess) { set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); st = HYMD_ERR_NOMEM; }
@@ -588,6 +709,7 @@ int hymd_bonded_destroy(hymd_bonded* b) {
     }
     cudaFree(b->out12);
     cudaFree(b->dih_type);
+    cudaFree(b->dih_last);
     cudaFree(b->partial);
     delete b;
     return HYMD_OK;
@@ -614,6 +736,9 @@ int hymd_bonded_forces(hymd_bonded* b, int kind, int dtype, const void* d_pos, c
         if (st != HYMD_OK) return st;
         HYMD_CUDA(cudaMemcpyAsync(d_out, b->out12 + 4 * (kind - 2), 4 * sizeof(double),
                                   cudaMemcpyDeviceToDevice, s));
+        if (kind == 4)
+            return dtype == HYMD_F64 ? launch_cbt<double>(b, (const double*)d_pos, bx, (double*)d_force, d_out, s)
+                                     : launch_cbt<float>(b, (const float*)d_pos, bx, (float*)d_force, d_out, s);
         return HYMD_OK;
     }
     if (dtype == HYMD_F64)
@@ -630,6 +755,11 @@ int hymd_bonded_inner_step(hymd_bonded* b, int dtype, const void* d_pos_in, void
     }
     if (n_kicks < 0 || n_kicks > 2) { set_error("n_kicks = %d, expected 0, 1 or 2", n_kicks); return HYMD_ERR_INVALID; }
     if (d_pos_out == d_pos_in) { set_error("hymd_bonded_inner_step: d_pos_out must not alias d_pos_in"); return HYMD_ERR_INVALID; }
+    if (b->n_cbt > 0) {
+        set_error("hymd_bonded_inner_step: the topology has %lld dihedrals of dih_type 1 (combined bending-torsion), whose "
+                  "bending term is a separate pass: use hymd_bonded_forces + hymd_md_kick_drift", b->n_cbt);
+        return HYMD_ERR_STATE;
+    }
     if (dtype != HYMD_F32 && dtype != HYMD_F64) { set_error("bad dtype %d", dtype); return HYMD_ERR_INVALID; }
     const Vec3d bx = {box[0], box[1], box[2]};
     cudaStream_t s = (cudaStream_t)stream;
@@ -638,6 +768,58 @@ int hymd_bonded_inner_step(hymd_bonded* b, int dtype, const void* d_pos_in, void
                                     kick_dt, n_kicks, drift_dt, d_force_out, d_out, s);
     return launch_inner<float>(b, 7, (const float*)d_pos_in, (float*)d_pos_out, (float*)d_vel, bx, mass,
                                kick_dt, n_kicks, drift_dt, d_force_out, d_out, s);
+}
+
+int hymd_bonded_set_last(hymd_bonded* b, const int32_t* last4) {
+    if (!b || (b->n_terms[2] > 0 && !last4)) { set_error("hymd_bonded_set_last: null argument"); return HYMD_ERR_INVALID; }
+    if (b->n_terms[2] > 0)
+        HYMD_CUDA(cudaMemcpy(b->dih_last, last4, sizeof(int32_t) * (size_t)b->n_terms[2], cudaMemcpyHostToDevice));
+    return HYMD_OK;
+}
+
+int hymd_bonded_dipoles(hymd_bonded* b, int dtype, const void* d_pos, const double box[3], void* d_dipoles,
+                        void* d_transfer, void* stream) {
+    if (!b || !box || (b->n_terms[2] > 0 && (!d_pos || !d_dipoles || !d_transfer))) {
+        set_error("hymd_bonded_dipoles: null argument");
+        return HYMD_ERR_INVALID;
+    }
+    if (dtype != HYMD_F32 && dtype != HYMD_F64) { set_error("bad dtype %d", dtype); return HYMD_ERR_INVALID; }
+    const long long n4 = b->n_terms[2];
+    if (n4 == 0) return HYMD_OK;
+    const Vec3d bx = {box[0], box[1], box[2]};
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = (int)((n4 + BONDED_THREADS - 1) / BONDED_THREADS);
+    if (dtype == HYMD_F64)
+        dipole_kernel<double><<<blocks, BONDED_THREADS, 0, s>>>((const double*)d_pos, n4, bx, b->idx[2], b->par[2], b->dih_type,
+                                                                b->dih_last, (double*)d_dipoles, (double*)d_transfer);
+    else
+        dipole_kernel<float><<<blocks, BONDED_THREADS, 0, s>>>((const float*)d_pos, n4, bx, b->idx[2], b->par[2], b->dih_type,
+                                                               b->dih_last, (float*)d_dipoles, (float*)d_transfer);
+    HYMD_LAUNCH_CHECK(b);
+    return HYMD_OK;
+}
+
+int hymd_dipole_redistribute(hymd_bonded* b, int dtype, const void* d_f_dipoles, const void* d_transfer,
+                             void* d_f_beads, void* stream) {
+    if (!b || (b->n_particles > 0 && !d_f_beads) || (b->n_terms[2] > 0 && (!d_f_dipoles || !d_transfer))) {
+        set_error("hymd_dipole_redistribute: null argument");
+        return HYMD_ERR_INVALID;
+    }
+    if (dtype != HYMD_F32 && dtype != HYMD_F64) { set_error("bad dtype %d", dtype); return HYMD_ERR_INVALID; }
+    const long long n = b->n_particles;
+    if (n == 0) return HYMD_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = (int)((n + BONDED_THREADS - 1) / BONDED_THREADS);
+    if (dtype == HYMD_F64)
+        redistribute_kernel<double><<<blocks, BONDED_THREADS, 0, s>>>(n, b->start[2], b->refs[2], b->dih_type, b->dih_last,
+                                                                      (const double*)d_f_dipoles, (const double*)d_transfer,
+                                                                      (double*)d_f_beads);
+    else
+        redistribute_kernel<float><<<blocks, BONDED_THREADS, 0, s>>>(n, b->start[2], b->refs[2], b->dih_type, b->dih_last,
+                                                                     (const float*)d_f_dipoles, (const float*)d_transfer,
+                                                                     (float*)d_f_beads);
+    HYMD_LAUNCH_CHECK(b);
+    return HYMD_OK;
 }
 
 int hymd_bonded_set_math(hymd_bonded* b, int f32math) {

@@ -3,7 +3,8 @@
 // Reference kernels (Fortran, sequential over terms, read-modify-write of f per term):
 //   hymd/compute_bond_forces.f90:1-61        cbf
 //   hymd/compute_angle_forces.f90:1-93       caf
-//   hymd/compute_dihedral_forces.f90:1-137   cdf   (dtype 0: cosine series, 2: improper)
+//   hymd/compute_dihedral_forces.f90:1-137   cdf   (dtype 0: cosine series, 1: combined bending-torsion, 2: improper)
+//   hymd/dipole_reconstruction.f90:50-221    reconstruct (bending term, backbone dipoles, transfer matrices)
 //   hymd/dipole_reconstruction.f90:37-48     cosine_series
 //
 // B200 design: no scatter, no atomics.  A host-built CSR lists, for every particle, the terms it
@@ -188,7 +189,7 @@ __host__ __device__ inline void dihedral_eval(const P& pos, Vec3d box, int ia, i
     const double f_dot_g = dot(f, g), h_dot_g = dot(h, g);
     double df = 0.0;
     e = 0.0;
-    if (dtype == 0) {
+    if (dtype == 0 || dtype == 1) {    // dtype 1: the propensity series here, the bending term in cbt_eval below
         cosine_series(coeff, coeff + DIH_COLS, phi, e, df);
         const double* c_coil = coeff + 2 * DIH_COLS;
         const double* d_coil = coeff + 3 * DIH_COLS;
@@ -210,6 +211,234 @@ __host__ __device__ inline void dihedral_eval(const P& pos, Vec3d box, int ia, i
     out[1] = sc * df - fa;
     out[2] = sc * (-df) - fd;
     out[3] = fd;
+}
+
+// ---- combined bending-torsion dihedrals (dtype 1) and the backbone dipoles -------------------------
+// compute_dihedral_forces.f90:77-112 + dipole_reconstruction.f90:50-221 (reconstruct): besides the propensity
+// series, a dihedral a-b-c-d of dtype 1 carries V = 1/2 k(phi) (gamma - gamma_0(phi))^2 on the angle gamma = a-b-c
+// (and, for the last dihedral of a backbone, on b-c-d as well), with k(phi) a cosine series (coefficient rows 4, 5)
+// and gamma_0(phi) = 1.85 - 0.227 cos(phi - 0.785).  The bending term acts on the three beads of its angle AND adds
+// dV/dphi to the dihedral force.  The reconstructed dipole (two charges 0.3 nm apart, centred on the b-c bond) and
+// its transfer matrices follow the Fortran literally, including its sign convention for the gamma-derivative terms
+// (oracle/bonded_oracle.py::reconstruct) and its single-precision constants cos(1.392947), sin(1.392947), 0.1.
+struct CbtGeom {
+    Vec3d w, v, dga, dgb, dgc;      // unit vectors of b->a and b->c; d gamma / d r_a, r_b, r_c
+    double norm_a, norm_c, cos_gamma, sin_gamma, gamm;
+    double energy, df_cbt, df_ang;
+};
+
+// false for collinear bonds (cos^2 gamma >= 1): the Fortran then leaves every output untouched
+__host__ __device__ inline bool cbt_angle(Vec3d rab, Vec3d rcb, const double* __restrict__ c_k,
+                                          const double* __restrict__ d_k, double phi, CbtGeom& q) {
+    double k = 0.0, dk = 0.0;
+    cosine_series(c_k, d_k, phi, k, dk);
+    const double gamma_0 = 1.85 - 0.227 * cos(phi - 0.785);
+    const double dg = 0.227 * sin(phi - 0.785);
+    q.norm_a = sqrt(dot(rab, rab));
+    q.norm_c = sqrt(dot(rcb, rcb));
+    q.w = {rab.x / q.norm_a, rab.y / q.norm_a, rab.z / q.norm_a};
+    q.v = {rcb.x / q.norm_c, rcb.y / q.norm_c, rcb.z / q.norm_c};
+    q.cos_gamma = dot(q.w, q.v);
+    const double cos2 = q.cos_gamma * q.cos_gamma;
+    if (!(cos2 < 1.0)) return false;
+    q.gamm = acos(q.cos_gamma);
+    q.sin_gamma = sqrt(1.0 - cos2);
+    if (q.sin_gamma < 0.1) q.sin_gamma = 0.10000000149011612;      // "sin_gamma = 0.1", a default-real literal
+    const Vec3d fa = (q.v - q.w * q.cos_gamma), fc = (q.w - q.v * q.cos_gamma);
+    q.dga = {-(fa.x / q.norm_a) / q.sin_gamma, -(fa.y / q.norm_a) / q.sin_gamma, -(fa.z / q.norm_a) / q.sin_gamma};
+    q.dgc = {-(fc.x / q.norm_c) / q.sin_gamma, -(fc.y / q.norm_c) / q.sin_gamma, -(fc.z / q.norm_c) / q.sin_gamma};
+    q.dgb = {-(q.dga.x + q.dgc.x), -(q.dga.y + q.dgc.y), -(q.dga.z + q.dgc.z)};
+    q.df_ang = k * (q.gamm - gamma_0);
+    const double var_sq = (q.gamm - gamma_0) * (q.gamm - gamma_0);
+    q.energy = 0.5 * k * var_sq;
+    q.df_cbt = 0.5 * dk * var_sq - q.df_ang * dg;
+    return true;
+}
+
+// what the bending term ADDS to the force of the particle in each slot (on top of dihedral_eval's propensity part),
+// and its energy; last != 0: the angle b-c-d is treated as well
+template <typename P>
+__host__ __device__ inline void cbt_eval(const P& pos, Vec3d box, int ia, int ib, int ic, int id,
+                                         const double* __restrict__ coeff, int last, Vec3d* out, double& e) {
+    const Vec3d f = mic_diff(pos, (long long)ia, (long long)ib, box);
+    const Vec3d g = mic_diff(pos, (long long)ib, (long long)ic, box);
+    const Vec3d h = mic_diff(pos, (long long)id, (long long)ic, box);
+    const Vec3d v = cross(f, g), w = cross(h, g);
+    const double v_sq = dot(v, v), w_sq = dot(w, w);
+    const double g_norm = sqrt(dot(g, g));
+    const double phi = atan2(dot(w, f) * g_norm, dot(v, w));
+    const double f_dot_g = dot(f, g), h_dot_g = dot(h, g);
+    const double* c_k = coeff + 4 * DIH_COLS;
+    const double* d_k = coeff + 5 * DIH_COLS;
+    const Vec3d zero = {0.0, 0.0, 0.0};
+    out[0] = out[1] = out[2] = out[3] = zero;
+    double df = 0.0;
+    e = 0.0;
+    CbtGeom q;
+    if (cbt_angle(f, zero - g, c_k, d_k, phi, q)) {
+        e += q.energy;
+        df += q.df_cbt;
+        out[0] = out[0] - q.dga * q.df_ang;
+        out[1] = out[1] - q.dgb * q.df_ang;
+        out[2] = out[2] - q.dgc * q.df_ang;
+    }
+    if (last && cbt_angle(g, h, c_k, d_k, phi, q)) {
+        e += q.energy;
+        df += q.df_cbt;
+        out[1] = out[1] - q.dga * q.df_ang;
+        out[2] = out[2] - q.dgb * q.df_ang;
+        out[3] = out[3] - q.dgc * q.df_ang;
+    }
+    const Vec3d sc = v * (f_dot_g / (v_sq * g_norm)) - w * (h_dot_g / (w_sq * g_norm));
+    const Vec3d fa = v * (-df * g_norm / v_sq);
+    const Vec3d fd = w * (df * g_norm / w_sq);
+    out[0] = out[0] + fa;
+    out[1] = out[1] + (sc * df - fa);
+    out[2] = out[2] + (sc * (-df) - fd);
+    out[3] = out[3] + fd;
+}
+
+struct Mat3d {
+    double m[3][3];
+};
+__host__ __device__ inline Vec3d row(const Mat3d& a, int i) { return {a.m[i][0], a.m[i][1], a.m[i][2]}; }
+__host__ __device__ inline void set_row(Mat3d& a, int i, Vec3d r) { a.m[i][0] = r.x; a.m[i][1] = r.y; a.m[i][2] = r.z; }
+__host__ __device__ inline double comp(Vec3d a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+// row i of the result = row i of a x vec (dipole_reconstruction.f90:14-24)
+__host__ __device__ inline Mat3d cross_matrix(const Mat3d& a, Vec3d vec) {
+    Mat3d o;
+    for (int i = 0; i < 3; ++i) set_row(o, i, cross(row(a, i), vec));
+    return o;
+}
+// row i = a_i * b (dipole_reconstruction.f90:26-35)
+__host__ __device__ inline Mat3d outer(Vec3d a, Vec3d b) {
+    Mat3d o;
+    for (int i = 0; i < 3; ++i) set_row(o, i, b * comp(a, i));
+    return o;
+}
+__host__ __device__ inline Mat3d axpby(double x, const Mat3d& a, double y, const Mat3d& b) {
+    Mat3d o;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) o.m[i][j] = x * a.m[i][j] + y * b.m[i][j];
+    return o;
+}
+
+// The dipole of the angle a-b-c (rab = r_a - r_b, rcb = r_c - r_b, rb = r_b): the two charge positions (wrapped,
+// rounded to the position type like the Fortran's real(4) array) and the three transfer matrices D_a, D_b, D_c.
+// Returns false (outputs untouched) for collinear bonds.
+template <typename real>
+__host__ __device__ inline bool cbt_dipole(Vec3d rab, Vec3d rb, Vec3d rcb, Vec3d box, const double* __restrict__ c_k,
+                                           const double* __restrict__ d_k, double phi, real* __restrict__ dipole,
+                                           real* __restrict__ transfer) {
+    CbtGeom q;
+    if (!cbt_angle(rab, rcb, c_k, d_k, phi, q)) return false;
+    const double delta = 0.3, cos_psi = 0.1769132763147354, sin_psi = 0.9842264652252197;   // cos / sin(1.392947) in real(4)
+    const double fac = exp((q.gamm - 1.73) / 0.025);
+    const double theta = -1.607 * q.gamm + 0.094 + 1.883 / (1.0 + fac);
+    const double d_theta = -1.607 - 1.883 / 0.025 * fac / ((1.0 + fac) * (1.0 + fac));
+    const double cos_theta = cos(theta), sin_theta = sin(theta);
+    const Vec3d wxv = cross(q.w, q.v);
+    const Vec3d n = {wxv.x / q.sin_gamma, wxv.y / q.sin_gamma, wxv.z / q.sin_gamma};
+    const Vec3d m = cross(n, q.v);
+    const Vec3d r0 = rb + rcb * 0.5;
+    const Vec3d d = (q.v * cos_psi + (n * cos_theta + m * sin_theta) * sin_psi) * (0.5 * delta);
+    const double bx[3] = {box.x, box.y, box.z};
+    for (int s = 0; s < 2; ++s) {
+        const Vec3d p = s == 0 ? r0 + d : r0 - d;
+        for (int k = 0; k < 3; ++k) {
+            const double x = (double)(real)comp(p, k);                  // dipole(s,:) is real(4)
+            const double qn = x / bx[k];
+            const double nint = qn >= 0.0 ? floor(qn + 0.5) : -floor(-qn + 0.5);
+            dipole[3 * s + k] = (real)(x - bx[k] * nint);
+        }
+    }
+    Mat3d V_b, W_b;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            V_b.m[i][j] = (comp(q.v, i) * comp(q.v, j) - (i == j ? 1.0 : 0.0)) / q.norm_c;
+            W_b.m[i][j] = (comp(q.w, i) * comp(q.w, j) - (i == j ? 1.0 : 0.0)) / q.norm_a;
+        }
+    const Mat3d Z = {{{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}};
+    const Mat3d V_c = axpby(-1.0, V_b, 0.0, Z), W_a = axpby(-1.0, W_b, 0.0, Z);
+    // N_i, M_i as written in the Fortran (lines 186-192)
+    Mat3d N_a = axpby(q.cos_gamma, outer(q.dga, n), 1.0, cross_matrix(W_a, q.v));
+    Mat3d N_b = axpby(1.0, axpby(q.cos_gamma, outer(q.dgb, n), 1.0, cross_matrix(W_b, q.v)), -1.0, cross_matrix(V_b, q.w));
+    Mat3d N_c = axpby(q.cos_gamma, outer(q.dgc, n), -1.0, cross_matrix(V_c, q.w));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            N_a.m[i][j] = N_a.m[i][j] / q.sin_gamma; N_b.m[i][j] = N_b.m[i][j] / q.sin_gamma; N_c.m[i][j] = N_c.m[i][j] / q.sin_gamma;
+        }
+    const Mat3d M_a = cross_matrix(N_a, q.v);
+    const Mat3d M_b = axpby(1.0, cross_matrix(N_b, q.v), -1.0, cross_matrix(V_b, n));
+    const Mat3d M_c = axpby(1.0, cross_matrix(N_c, q.v), -1.0, cross_matrix(V_c, n));
+    const Vec3d dg[3] = {q.dga, q.dgb, q.dgc};
+    const Mat3d* Nm[3] = {&N_a, &N_b, &N_c};
+    const Mat3d* Mm[3] = {&M_a, &M_b, &M_c};
+    const Mat3d* Vm[3] = {&Z, &V_b, &V_c};
+    for (int t = 0; t < 3; ++t) {
+        const Mat3d FN = outer(dg[t], n), FM = outer(dg[t], m);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                const double inner = cos_theta * Nm[t]->m[i][j] + sin_theta * Mm[t]->m[i][j] +
+                                     sin_theta * d_theta * FN.m[i][j] - cos_theta * d_theta * FM.m[i][j];
+                transfer[9 * t + 3 * i + j] = (real)(0.5 * delta * (cos_psi * Vm[t]->m[i][j] + sin_psi * inner));
+            }
+    }
+    return true;
+}
+
+// dipoles (4,3) and transfer matrices (6,3,3) of one dihedral (zero unless dtype 1; rows 2-3 / matrices 3-5 only for
+// the last dihedral of a backbone): compute_dihedral_forces.f90:27-28, 84-111 with dipole_flag = 1
+template <typename real>
+__host__ __device__ inline void dipole_term(const real* __restrict__ pos, Vec3d box, int ia, int ib, int ic, int id,
+                                            const double* __restrict__ coeff, int dtype, int last,
+                                            real* __restrict__ dipoles, real* __restrict__ transfer) {
+    for (int k = 0; k < 12; ++k) dipoles[k] = (real)0;
+    for (int k = 0; k < 54; ++k) transfer[k] = (real)0;
+    if (dtype != 1) return;
+    const Vec3d f = mic_diff(pos, (long long)ia, (long long)ib, box);
+    const Vec3d g = mic_diff(pos, (long long)ib, (long long)ic, box);
+    const Vec3d h = mic_diff(pos, (long long)id, (long long)ic, box);
+    const Vec3d v = cross(f, g), w = cross(h, g);
+    const double g_norm = sqrt(dot(g, g));
+    const double phi = atan2(dot(w, f) * g_norm, dot(v, w));
+    const double* c_k = coeff + 4 * DIH_COLS;
+    const double* d_k = coeff + 5 * DIH_COLS;
+    const Vec3d zero = {0.0, 0.0, 0.0};
+    const Vec3d rb = {(double)pos[3 * ib + 0], (double)pos[3 * ib + 1], (double)pos[3 * ib + 2]};
+    cbt_dipole<real>(f, rb, zero - g, box, c_k, d_k, phi, dipoles, transfer);
+    if (last) {
+        const Vec3d rc = {(double)pos[3 * ic + 0], (double)pos[3 * ic + 1], (double)pos[3 * ic + 2]};
+        cbt_dipole<real>(g, rc, h, box, c_k, d_k, phi, dipoles + 6, transfer + 27);
+    }
+}
+
+// dipole_forces_redistribution (hymd/force.py:855-880): what the forces fd (4,3) on the dipole charges of ONE
+// dihedral add to the bead in `slot` of that dihedral (D = its six transfer matrices; f += D_i @ (f+ - f-), the
+// two beads of the bond carrying the dipole also take half of f+ + f-)
+template <typename real>
+__host__ __device__ inline Vec3d redistribute_term(int slot, int last, const real* __restrict__ fd,
+                                                   const real* __restrict__ D) {
+    Vec3d out = {0.0, 0.0, 0.0};
+    auto mv = [&](int mat, Vec3d x) {
+        const real* M = D + 9 * mat;
+        return Vec3d{(double)M[0] * x.x + (double)M[1] * x.y + (double)M[2] * x.z,
+                     (double)M[3] * x.x + (double)M[4] * x.y + (double)M[5] * x.z,
+                     (double)M[6] * x.x + (double)M[7] * x.y + (double)M[8] * x.z};
+    };
+    const Vec3d f0 = {(double)fd[0], (double)fd[1], (double)fd[2]}, f1 = {(double)fd[3], (double)fd[4], (double)fd[5]};
+    const Vec3d s01 = f0 + f1, d01 = f0 - f1;
+    if (slot == 0) out = mv(0, d01);
+    else if (slot == 1) out = mv(1, d01) + s01 * 0.5;
+    else if (slot == 2) out = mv(2, d01) + s01 * 0.5;
+    if (last) {
+        const Vec3d f2 = {(double)fd[6], (double)fd[7], (double)fd[8]}, f3 = {(double)fd[9], (double)fd[10], (double)fd[11]};
+        const Vec3d s23 = f2 + f3, d23 = f2 - f3;
+        if (slot == 1) out = out + mv(3, d23);
+        else if (slot == 2) out = out + mv(4, d23) + s23 * 0.5;
+        else if (slot == 3) out = mv(5, d23) + s23 * 0.5;
+    }
+    return out;
 }
 
 template <typename real>

@@ -8,7 +8,9 @@ this module                    reference
 =============================  ==========================================================
 ``compute_bond_forces``        ``cbf``  ``hymd/compute_bond_forces.f90:1-61``
 ``compute_angle_forces``       ``caf``  ``hymd/compute_angle_forces.f90:1-93``
-``compute_dihedral_forces``    ``cdf``  ``hymd/compute_dihedral_forces.f90:1-137`` (dtype 0, 2)
+``compute_dihedral_forces``    ``cdf``  ``hymd/compute_dihedral_forces.f90:1-137`` (dtype 0, 1, 2;
+                               dipoles and transfer matrices of ``dipole_reconstruction.f90``)
+``dipole_forces_redistribution``  ``hymd/force.py:855-880``
 =============================  ==========================================================
 
 The index / parameter arrays are the ones ``prepare_bonds`` returns (``hymd/force.py:573-728``;
@@ -53,7 +55,8 @@ class BondedTopology:
 
     def __init__(self, n_particles, bonds=None, angles=None, dihedrals=None, device=None):
         """``bonds = (a, b, r0, k)``, ``angles = (a, b, c, theta0, k)``,
-        ``dihedrals = (a, b, c, d, coeff (D,6,5), dih_type)``; any of them may be ``None``."""
+        ``dihedrals = (a, b, c, d, coeff (D,6,5), dih_type[, last])``; any of them may be ``None``.
+        ``last`` = ``bonds_4_last`` (1 = last dihedral of a backbone; only read for ``dih_type`` 1)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.HymdError("hymd_b200.force needs a CUDA device (no CPU fallback)")
@@ -62,8 +65,11 @@ class BondedTopology:
         empty_i, empty_f = np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float64)
         a2, b2, r0, k2 = bonds if bonds is not None else (empty_i, empty_i, empty_f, empty_f)
         a3, b3, c3, t0, k3 = angles if angles is not None else (empty_i,) * 3 + (empty_f,) * 2
+        last4 = None
         if dihedrals is not None:
-            a4, b4, c4, d4, coeff, dtype4 = dihedrals
+            a4, b4, c4, d4, coeff, dtype4 = dihedrals[:6]
+            if len(dihedrals) > 6 and dihedrals[6] is not None:
+                last4 = _i32(dihedrals[6])
         else:
             a4 = b4 = c4 = d4 = dtype4 = empty_i
             coeff = np.zeros((0, 6, 5))
@@ -88,6 +94,11 @@ class BondedTopology:
                 self.n_terms[2], ip(keep[9]), ip(keep[10]), ip(keep[11]), ip(keep[12]), fp(keep[13]),
                 ip(keep[14]), ctypes.byref(handle)))
         self._h = handle
+        self.n_cbt = int(np.count_nonzero(keep[14] == 1))
+        if last4 is not None:
+            if len(last4) != self.n_terms[2]:
+                raise ValueError("bonds_4_last must have one entry per dihedral")
+            _lib.check(self.lib.hymd_bonded_set_last(handle, ip(last4)))
         self._out = torch.zeros((3, 4), dtype=torch.float64, device=self.device)
         self._out12 = torch.zeros((3, 4), dtype=torch.float64, device=self.device)
         self._cta = None     # unknown until set (HYMD_B200_BONDED_CTA may have chosen at creation)
@@ -113,7 +124,7 @@ class BondedTopology:
     def set_math(self, f32=True):
         """Single-precision arithmetic for bonds and angles in the per-particle fused inner step of the
         fp32 build (``hymd_bonded_set_math``, ``csrc/bonded_f32.cuh``); the default is the Fortran's double
-        arithmetic.  Not yet run on a GPU."""
+        arithmetic."""
         _lib.check(self.lib.hymd_bonded_set_math(self._h, 1 if f32 else 0))
 
     def launch_count(self):
@@ -136,6 +147,30 @@ class BondedTopology:
             ctypes.cast(ctypes.c_void_p(res.data_ptr()), _F64P), stream))
         return res
 
+
+    def dipoles(self, positions, box_size, dipoles, transfer):
+        """What ``cdf`` leaves in ``dipoles`` (D,4,3) and ``transfer_matrix`` (D,6,3,3) with ``dipole_flag = 1``
+        (``hymd_bonded_dipoles``): contiguous device tensors of the position dtype, overwritten."""
+        D = self.n_terms[2]
+        if tuple(dipoles.shape) != (D, 4, 3) or tuple(transfer.shape) != (D, 6, 3, 3):
+            raise ValueError(f"dipoles / transfer matrices must have shapes ({D}, 4, 3) / ({D}, 6, 3, 3)")
+        for t in (dipoles, transfer):
+            if t.dtype != positions.dtype or not t.is_contiguous() or not t.is_cuda:
+                raise ValueError("dipoles / transfer matrices must be contiguous device tensors of the position dtype")
+        box = (ctypes.c_double * 3)(*[float(b) for b in np.asarray(box_size).reshape(-1)[:3]])
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.hymd_bonded_dipoles(
+            self._h, _lib.F64 if positions.dtype == torch.float64 else _lib.F32,
+            ctypes.c_void_p(positions.data_ptr()), box, ctypes.c_void_p(dipoles.data_ptr()),
+            ctypes.c_void_p(transfer.data_ptr()), stream))
+
+    def redistribute(self, f_dipoles, transfer, f_beads):
+        """``dipole_forces_redistribution`` (``hymd_dipole_redistribute``): ``f_beads`` (n,3) is overwritten."""
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.hymd_dipole_redistribute(
+            self._h, _lib.F64 if f_beads.dtype == torch.float64 else _lib.F32,
+            ctypes.c_void_p(f_dipoles.data_ptr()), ctypes.c_void_p(transfer.data_ptr()),
+            ctypes.c_void_p(f_beads.data_ptr()), stream))
 
     def inner_step(self, x_in, x_out, vel, box_size, mass, kick_dt, n_kicks, drift_dt, force_out=None,
                    want_energies=True, cta=None):
@@ -253,23 +288,93 @@ def compute_angle_forces(f_angles, r, box_size, a, b, c, t0, k):
     return _result(res, back is None)
 
 
+def _like_device(x, ref, shape):
+    """Contiguous device tensor of ``ref``'s dtype for the caller's array ``x`` (a view when it already is one)."""
+    if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == ref.dtype and x.is_contiguous() \
+            and tuple(x.shape) == tuple(shape):
+        return x, True
+    return torch.empty(shape, dtype=ref.dtype, device=ref.device), False
+
+
+def _store(dst, src):
+    """``dst[...] = src`` for torch tensors and numpy arrays of any memory order."""
+    if isinstance(dst, torch.Tensor):
+        dst.copy_(src.reshape(dst.shape))
+    else:
+        dst[...] = src.cpu().numpy().reshape(dst.shape)
+
+
 def compute_dihedral_forces(f_dihedrals, r, dipoles, transfer_matrix, box_size, a, b, c, d, coeff,
                             dtype, bb_index=None, dipole_flag=0):
-    """``cdf`` for ``dtype`` 0 (cosine series) and 2 (improper); returns the energy.  ``dipoles`` and
-    ``transfer_matrix`` are zeroed like the Fortran does (``compute_dihedral_forces.f90:27-28``);
-    terms of ``dtype`` 1 (combined bending-torsion + dipole reconstruction) raise ``HymdError``."""
+    """``cdf``: ``dtype`` 0 (cosine series), 1 (combined bending-torsion: the series plus
+    ``k(phi) (gamma - gamma_0(phi))^2`` on the angle a-b-c and, where ``bb_index`` = ``bonds_4_last`` is 1, on b-c-d)
+    and 2 (improper); returns the energy.  ``dipoles`` (D,4,3) and ``transfer_matrix`` (D,6,3,3) are zeroed like
+    the Fortran does (``compute_dihedral_forces.f90:27-28``) and, with ``dipole_flag = 1``, receive the
+    reconstructed backbone dipoles and their transfer matrices (``dipole_reconstruction.f90:50-221``)."""
     pos, buf, back = _device_io(r, f_dihedrals)
-    topo = _topology(4, pos.shape[0], pos.device, (a, b, c, d, coeff, dtype),
-                     lambda: BondedTopology(pos.shape[0], dihedrals=(a, b, c, d, coeff, dtype),
+    last = bb_index if bb_index is not None else np.zeros(len(a), dtype=np.int32)
+    arrays = (a, b, c, d, coeff, dtype) + ((bb_index,) if bb_index is not None else ())
+    topo = _topology(4, pos.shape[0], pos.device, arrays,
+                     lambda: BondedTopology(pos.shape[0], dihedrals=(a, b, c, d, coeff, dtype, last),
                                             device=pos.device))
     res = topo.forces(4, pos, box_size, buf)
-    for arr in (dipoles, transfer_matrix):
-        if arr is None:
-            continue
-        if isinstance(arr, torch.Tensor):
-            arr.zero_()
-        else:
-            arr[...] = 0
+    D = topo.n_terms[2]
+    if dipole_flag and topo.n_cbt and dipoles is not None and transfer_matrix is not None:
+        dd, d_view = _like_device(dipoles, pos, (D, 4, 3))
+        tt, t_view = _like_device(transfer_matrix, pos, (D, 6, 3, 3))
+        topo.dipoles(pos, box_size, dd, tt)
+        if not d_view:
+            _store(dipoles, dd)
+        if not t_view:
+            _store(transfer_matrix, tt)
+    else:
+        for arr in (dipoles, transfer_matrix):
+            if arr is None:
+                continue
+            if isinstance(arr, torch.Tensor):
+                arr.zero_()
+            else:
+                arr[...] = 0
     if back is not None:
         back()
     return _result(res, back is None, with_pr=False)
+
+
+def dipole_forces_redistribution(f_on_bead, f_dipoles, trans_matrices, a, b, c, d, type_array, last_bb,
+                                 coeff=None):
+    """``dipole_forces_redistribution`` (``hymd/force.py:855-880``): the electrostatic forces on the reconstructed
+    dipole charges ``f_dipoles`` (D,4,3) carried to the backbone beads through the transfer matrices; ``f_on_bead``
+    (N,3) is overwritten.  The topology is the one cached by ``compute_dihedral_forces`` for the same index arrays
+    (pass ``coeff`` to hit that cache entry; otherwise a force-free topology is built once)."""
+    n = f_on_bead.shape[0]
+    dev_in = isinstance(f_on_bead, torch.Tensor) and f_on_bead.is_cuda
+    device = f_on_bead.device if dev_in else torch.device(_default_device())
+    D = len(a)
+    if coeff is None:
+        coeff = _zero_coeff(D)
+    arrays = (a, b, c, d, coeff, type_array, last_bb)
+    topo = _topology(4, n, device, arrays,
+                     lambda: BondedTopology(n, dihedrals=(a, b, c, d, coeff, type_array, last_bb), device=device))
+    if dev_in:
+        ref = f_on_bead
+    else:
+        dt = torch.float64 if np.asarray(f_on_bead).dtype == np.float64 else torch.float32
+        ref = torch.empty((n, 3), dtype=dt, device=device)
+
+    def dev(x, shape):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=device, dtype=ref.dtype).reshape(shape).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(np.asarray(x).reshape(shape)), dtype=ref.dtype).to(device)
+    out = f_on_bead if dev_in and f_on_bead.is_contiguous() else torch.empty((n, 3), dtype=ref.dtype, device=device)
+    topo.redistribute(dev(f_dipoles, (D, 4, 3)), dev(trans_matrices, (D, 6, 3, 3)), out)
+    if out is not f_on_bead:
+        _store(f_on_bead, out)
+
+
+_zero_coeffs = {}
+
+
+def _zero_coeff(D):
+    if D not in _zero_coeffs:
+        _zero_coeffs[D] = np.zeros((D, 6, 5))
+    return _zero_coeffs[D]

@@ -269,7 +269,7 @@ typedef struct {
  * iterations to *iterations (may be NULL).  Afterwards HYMD_FIELD_PHI_Q holds the filtered charge density
  * divided by the dielectric (field.py:1010, 1021), HYMD_FIELD_PSI the potential, HYMD_FIELD_GPE_* the
  * dielectric, |E|^2 and the per-type electrostatic potentials.  The context must have been created with
- * pme = 1.  Synchronizes the stream once per iteration (the convergence test). */
+ * pme = 1.  Synchronizes the stream once per batch of four iterations (the convergence state lives on the device). */
 int hymd_gpe_cycle(hymd_ctx* ctx, const hymd_gpe_params* params, void* d_elec_force, int32_t* iterations,
                    void* stream);
 /* compute_field_energy_q_GPE (field.py:706-760): dV * eps_0 / 2 * sum_cells phi_eps |E|^2 of this slab to the
@@ -285,8 +285,8 @@ int hymd_gpe_energy(hymd_ctx* ctx, double coulomb_constant, double* out, void* s
 
 /* Device-resident term lists built from what prepare_bonds returns (hymd/force.py:573-728; HOST arrays
  * of local particle indices and parameters).  coeff4 is bonds_4_coeff (n4,6,5) row-major, type4 is
- * bonds_4_type; dih_type 1 (combined bending-torsion with dipole reconstruction,
- * dipole_reconstruction.f90:50-221) is rejected with HYMD_ERR_INVALID.  Synchronous.  Rebuild after
+ * bonds_4_type: 0 cosine series, 1 combined bending-torsion (rows 4, 5 of its coefficients are the series of the
+ * bending constant; hymd_bonded_set_last, hymd_bonded_dipoles below), 2 improper.  Synchronous.  Rebuild after
  * domain_decomposition permutes the particles (main.py:1239-1262 does the same with prepare_bonds).
  * A hymd_bonded owns one set of reduction scratch buffers: use it from one stream at a time. */
 typedef struct hymd_bonded hymd_bonded;
@@ -306,6 +306,24 @@ int hymd_bonded_destroy(hymd_bonded* b);
 int hymd_bonded_forces(hymd_bonded* b, int kind, int dtype, const void* d_pos, const double box[3],
                        void* d_force, double* d_out, void* stream);
 int64_t hymd_bonded_launch_count(hymd_bonded* b);
+
+/* Dihedrals of dih_type 1 (compute_dihedral_forces.f90:77-112, dipole_reconstruction.f90:50-221).
+ * hymd_bonded_set_last: last4 (HOST, n4) = bonds_4_last of prepare_bonds (force.py:569, the `bb_index` argument of
+ *   cdf): 1 marks the last dihedral of a backbone, whose second angle b-c-d carries a bending term and a dipole as
+ *   well.  All zeros until it is called.  Synchronous.
+ * hymd_bonded_forces(kind = 4) includes the bending term (a second pass over the particles; topologies without
+ *   dih_type 1 never launch it); hymd_bonded_inner_step refuses such topologies (HYMD_ERR_STATE).
+ * hymd_bonded_dipoles: what cdf leaves in `dipoles` (n4,4,3) and `transfer_matrix` (n4,6,3,3) with dipole_flag = 1,
+ *   row-major in `dtype` -- the reconstructed backbone dipole charges' positions (wrapped into the box) and the
+ *   matrices that carry forces on them back to the beads; zeros for dihedrals of other types.
+ * hymd_dipole_redistribute: dipole_forces_redistribution (hymd/force.py:855-880): d_f_dipoles (n4,4,3) are the
+ *   electrostatic forces on the dipole charges (hymd_pme_cycle on the dipole positions, main.py:1060-1095);
+ *   d_f_beads (n,3) is overwritten for every particle. */
+int hymd_bonded_set_last(hymd_bonded* b, const int32_t* last4);
+int hymd_bonded_dipoles(hymd_bonded* b, int dtype, const void* d_pos, const double box[3], void* d_dipoles,
+                        void* d_transfer, void* stream);
+int hymd_dipole_redistribute(hymd_bonded* b, int dtype, const void* d_f_dipoles, const void* d_transfer,
+                             void* d_f_beads, void* stream);
 
 /* Evaluation strategy of hymd_bonded_forces / hymd_bonded_inner_step.  0 (default): every particle
  * re-evaluates the terms it takes part in.  1: every CTA of 128 consecutive particles evaluates each

@@ -39,6 +39,60 @@ extern "C" int host_bonded(int kind, int f64, const void* pos, const double* box
     return 0;
 }
 
+// dtype-1 dihedrals: what the device adds on top of host_bonded(kind = 4) -- the bending term's forces and energy
+// (cbt_eval, gathered per particle like the device's cbt pass), the dipoles and transfer matrices (dipole_term) and
+// the redistribution of dipole forces to the beads (redistribute_term, gathered per particle)
+template <typename real>
+static void run_cbt(const real* pos, Vec3d bx, long long n, long long nt, const std::vector<uint32_t>& start,
+                    const std::vector<uint32_t>& refs, const std::vector<int32_t>& idx, const double* par,
+                    const int32_t* dtype, const int32_t* last, real* force_add, double* energy, real* dipoles,
+                    real* transfer, const real* f_dipoles, real* f_beads) {
+    *energy = 0.0;
+    for (long long p = 0; p < n; ++p) {
+        Vec3d acc = {0, 0, 0}, accb = {0, 0, 0};
+        for (uint32_t k = start[p]; k < start[p + 1]; ++k) {
+            const long long t = refs[k] >> 2;
+            const int slot = refs[k] & 3;
+            if (dtype[t] != 1) continue;
+            const int32_t* ix = &idx[4 * t];
+            Vec3d out[4];
+            double e;
+            cbt_eval(pos, bx, ix[0], ix[1], ix[2], ix[3], par + (long long)DIH_ROWS * DIH_COLS * t, last[t], out, e);
+            acc = acc + out[slot];
+            if (slot == 0) *energy += e;
+            if (f_dipoles) accb = accb + redistribute_term<real>(slot, last[t], f_dipoles + 12 * t, transfer + 54 * t);
+        }
+        force_add[3 * p] = (real)acc.x; force_add[3 * p + 1] = (real)acc.y; force_add[3 * p + 2] = (real)acc.z;
+        if (f_beads) { f_beads[3 * p] = (real)accb.x; f_beads[3 * p + 1] = (real)accb.y; f_beads[3 * p + 2] = (real)accb.z; }
+    }
+}
+
+extern "C" int host_cbt(int f64, const void* pos, const double* box, long long n, long long nt, const int32_t* a,
+                        const int32_t* b, const int32_t* c, const int32_t* d, const double* par, const int32_t* dtype,
+                        const int32_t* last, void* force_add, double* energy, void* dipoles, void* transfer,
+                        const void* f_dipoles, void* f_beads) {
+    const int32_t* index[4] = {a, b, c, d};
+    std::vector<uint32_t> start, refs;
+    if (!build_particle_csr(n, nt, 4, index, start, refs)) return -1;
+    std::vector<int32_t> idx((size_t)nt * 4, 0);
+    for (long long t = 0; t < nt; ++t)
+        for (int s = 0; s < 4; ++s) idx[4 * t + s] = index[s][t];
+    const Vec3d bx = {box[0], box[1], box[2]};
+    // dipoles first: the redistribution reads the transfer matrices
+    for (long long t = 0; t < nt; ++t) {
+        const int32_t* ix = &idx[4 * t];
+        if (f64) dipole_term<double>((const double*)pos, bx, ix[0], ix[1], ix[2], ix[3], par + (long long)DIH_ROWS * DIH_COLS * t,
+                                     dtype[t], last[t], (double*)dipoles + 12 * t, (double*)transfer + 54 * t);
+        else dipole_term<float>((const float*)pos, bx, ix[0], ix[1], ix[2], ix[3], par + (long long)DIH_ROWS * DIH_COLS * t,
+                                dtype[t], last[t], (float*)dipoles + 12 * t, (float*)transfer + 54 * t);
+    }
+    if (f64) run_cbt<double>((const double*)pos, bx, n, nt, start, refs, idx, par, dtype, last, (double*)force_add, energy,
+                             (double*)dipoles, (double*)transfer, (const double*)f_dipoles, (double*)f_beads);
+    else run_cbt<float>((const float*)pos, bx, n, nt, start, refs, idx, par, dtype, last, (float*)force_add, energy,
+                        (float*)dipoles, (float*)transfer, (const float*)f_dipoles, (float*)f_beads);
+    return 0;
+}
+
 template <typename real>
 static void kd(real* vel, real* pos, const void* const* forces, int nf, int sequential, double mass,
                double kick_dt, double drift_dt, const double* box, long long n) {
@@ -95,7 +149,7 @@ extern "C" int host_csvr(int f64, void* vel, const int32_t* group, int g, long l
 struct HostBonded {
     long long n;
     std::vector<uint32_t> start[3], refs[3];
-    std::vector<int32_t> idx[3], dtype;
+    std::vector<int32_t> idx[3], dtype, last;
     std::vector<double> par[3];
     std::vector<uint32_t> cta_start[3], cta_terms[3], lrefs[3];
     std::vector<TermRec> rec[2];
@@ -126,7 +180,7 @@ extern "C" int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t
                                   int64_t n4, const int32_t* a4, const int32_t* b4, const int32_t* c4,
                                   const int32_t* d4, const double* coeff4, const int32_t* type4, void** out) {
     for (int64_t t = 0; t < n4; ++t)
-        if (type4[t] != 0 && type4[t] != 2) return -1;
+        if (type4[t] < 0 || type4[t] > 2) return -1;
     HostBonded* b = new HostBonded();
     b->n = n_particles;
     b->launches = 0;
@@ -149,7 +203,76 @@ extern "C" int hymd_bonded_create(int64_t n_particles, int64_t n2, const int32_t
         return -1;
     }
     b->dtype.assign(type4, type4 + n4);
+    b->last.assign((size_t)n4, 0);
     *out = b;
+    return 0;
+}
+
+extern "C" int hymd_bonded_set_last(void* h, const int32_t* last4) {
+    HostBonded* b = (HostBonded*)h;
+    b->last.assign(last4, last4 + b->dtype.size());
+    return 0;
+}
+
+// the bending pass of csrc/bonded.cu (cbt_kernel + cbt_final_kernel) on top of a dihedral force array
+template <typename real>
+static void host_cbt_pass(HostBonded* b, const real* pos, Vec3d bx, real* force, double* out) {
+    bool any = false;
+    for (int32_t t : b->dtype) any |= t == 1;
+    if (!any) return;
+    for (long long p = 0; p < b->n; ++p) {
+        Vec3d acc = {0, 0, 0};
+        bool hit = false;
+        for (uint32_t k = b->start[2][p]; k < b->start[2][p + 1]; ++k) {
+            const long long t = b->refs[2][k] >> 2;
+            const int slot = b->refs[2][k] & 3;
+            if (b->dtype[t] != 1) continue;
+            const int32_t* ix = &b->idx[2][4 * t];
+            Vec3d o[4];
+            double e;
+            cbt_eval(pos, bx, ix[0], ix[1], ix[2], ix[3], b->par[2].data() + (long long)DIH_ROWS * DIH_COLS * t, b->last[t], o, e);
+            acc = acc + o[slot];
+            if (slot == 0) out[0] += e;
+            hit = true;
+        }
+        if (hit) {
+            force[3 * p] = (real)((double)force[3 * p] + acc.x);
+            force[3 * p + 1] = (real)((double)force[3 * p + 1] + acc.y);
+            force[3 * p + 2] = (real)((double)force[3 * p + 2] + acc.z);
+        }
+    }
+}
+
+extern "C" int hymd_bonded_dipoles(void* h, int dtype, const void* pos, const double* box, void* dipoles, void* transfer,
+                                   void* stream) {
+    HostBonded* b = (HostBonded*)h;
+    const Vec3d bx = {box[0], box[1], box[2]};
+    for (size_t t = 0; t < b->dtype.size(); ++t) {
+        const int32_t* ix = &b->idx[2][4 * t];
+        const double* par = b->par[2].data() + (long long)DIH_ROWS * DIH_COLS * t;
+        if (dtype == 1) dipole_term<double>((const double*)pos, bx, ix[0], ix[1], ix[2], ix[3], par, b->dtype[t], b->last[t],
+                                            (double*)dipoles + 12 * t, (double*)transfer + 54 * t);
+        else dipole_term<float>((const float*)pos, bx, ix[0], ix[1], ix[2], ix[3], par, b->dtype[t], b->last[t],
+                                (float*)dipoles + 12 * t, (float*)transfer + 54 * t);
+    }
+    return 0;
+}
+
+extern "C" int hymd_dipole_redistribute(void* h, int dtype, const void* f_dipoles, const void* transfer, void* f_beads,
+                                        void* stream) {
+    HostBonded* b = (HostBonded*)h;
+    for (long long p = 0; p < b->n; ++p) {
+        Vec3d acc = {0, 0, 0};
+        for (uint32_t k = b->start[2][p]; k < b->start[2][p + 1]; ++k) {
+            const long long t = b->refs[2][k] >> 2;
+            if (b->dtype[t] != 1) continue;
+            const int slot = b->refs[2][k] & 3;
+            if (dtype == 1) acc = acc + redistribute_term<double>(slot, b->last[t], (const double*)f_dipoles + 12 * t, (const double*)transfer + 54 * t);
+            else acc = acc + redistribute_term<float>(slot, b->last[t], (const float*)f_dipoles + 12 * t, (const float*)transfer + 54 * t);
+        }
+        if (dtype == 1) { ((double*)f_beads)[3 * p] = acc.x; ((double*)f_beads)[3 * p + 1] = acc.y; ((double*)f_beads)[3 * p + 2] = acc.z; }
+        else { ((float*)f_beads)[3 * p] = (float)acc.x; ((float*)f_beads)[3 * p + 1] = (float)acc.y; ((float*)f_beads)[3 * p + 2] = (float)acc.z; }
+    }
     return 0;
 }
 
@@ -185,6 +308,7 @@ extern "C" int hymd_bonded_forces(void* h, int kind, int dtype, const void* pos,
         if (dtype == 1) inner<double>(b, 1 << k, (const double*)pos, nullptr, nullptr, bx, 1.0, 0.0, 0, 0.0, fo, out12);
         else inner<float>(b, 1 << k, (const float*)pos, nullptr, nullptr, bx, 1.0, 0.0, 0, 0.0, fo, out12);
         for (int j = 0; j < 4; ++j) out[j] = out12[4 * k + j];
+        if (kind == 4) { if (dtype == 1) host_cbt_pass<double>(b, (const double*)pos, bx, (double*)force, out); else host_cbt_pass<float>(b, (const float*)pos, bx, (float*)force, out); }
         return 0;
     }
 #define RUN(real, K) run_kind<real, K>((const real*)pos, bx, b->n, b->start[k], b->refs[k], b->idx[k], \
@@ -192,6 +316,7 @@ extern "C" int hymd_bonded_forces(void* h, int kind, int dtype, const void* pos,
     if (dtype == 1) { if (kind == 2) RUN(double, 2); else if (kind == 3) RUN(double, 3); else RUN(double, 4); }
     else            { if (kind == 2) RUN(float, 2);  else if (kind == 3) RUN(float, 3);  else RUN(float, 4); }
 #undef RUN
+    if (kind == 4) { if (dtype == 1) host_cbt_pass<double>(b, (const double*)pos, bx, (double*)force, out); else host_cbt_pass<float>(b, (const float*)pos, bx, (float*)force, out); }
     return 0;
 }
 
@@ -330,6 +455,7 @@ extern "C" int hymd_bonded_inner_step(void* h, int dtype, const void* x_in, void
                                       double drift_dt, void* const* f_out, double* out12, void* stream) {
     HostBonded* b = (HostBonded*)h;
     if (n_kicks < 0 || n_kicks > 2 || x_in == x_out) return -1;
+    for (int32_t t : b->dtype) if (t == 1) return -6;       // HYMD_ERR_STATE: the bending term is a separate pass
     if (b->f32math && dtype == 0 && !b->use_cta) {
         b->launches += out12 ? 2 : 1;
         return host_inner_step_f32(h, (const float*)x_in, (float*)x_out, (float*)vel, box, mass, kick_dt, n_kicks,

@@ -21,7 +21,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 F2 = ["hymd_bonded_set_math", "hymd_bonded_set_cta", "hymd_bonded_inner_step", "hymd_bonded_create", "hymd_bonded_destroy", "hymd_bonded_forces", "hymd_bonded_launch_count",
       "hymd_md_kick_drift", "hymd_velocity_moments", "hymd_velocity_moments_scratch_doubles",
-      "hymd_csvr_apply", "hymd_cancel_com"]
+      "hymd_csvr_apply", "hymd_cancel_com",
+      "hymd_bonded_set_last", "hymd_bonded_dipoles", "hymd_dipole_redistribute"]
 
 
 @pytest.fixture()
@@ -62,6 +63,11 @@ def emulated(tmp_path_factory, monkeypatch):
 @pytest.mark.parametrize("real", [np.float32, np.float64])
 def test_bonded(emulated, real):
     emulated.test_bonded_forces_match_oracle(real)
+
+
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_cbt_dihedrals(emulated, real):
+    emulated.test_cbt_dihedrals_dipoles_and_redistribution_match_oracle(real)
 
 
 def test_bonded_kats_and_edges(emulated):

@@ -98,6 +98,57 @@ def test_bonds_angles_dihedrals_match_oracle(lib, real, tol):
     assert np.all(out[1:] == 0)
 
 
+@pytest.mark.parametrize("real,tol", [(np.float64, 1e-12), (np.float32, 2e-6)])
+def test_cbt_dihedrals_dipoles_and_redistribution_match_oracle(lib, real, tol):
+    """dtype-1 dihedrals through the device source (cbt_eval / dipole_term / redistribute_term of csrc/bonded.cuh):
+    the propensity part comes from the dihedral kernel (dtype 1 is evaluated like dtype 0 there), the bending term,
+    the dipoles with their transfer matrices and the redistribution from the three new functions -- together they
+    equal the oracle's restatement of compute_dihedral_forces.f90 + dipole_reconstruction.f90 + force.py:855-880."""
+    rng = np.random.default_rng(21)
+    n = 40
+    box = np.array([3.0, 3.5, 4.0])
+    r = np.mod(np.cumsum(rng.normal(scale=0.33, size=(n, 3)), axis=0) + 1.5, box).astype(real)
+    a = np.arange(n - 3, dtype=np.int32)
+    nt = len(a)
+    coeff = np.zeros((nt, 6, 5))
+    coeff[:, 0] = rng.uniform(0.5, 2.0, size=(nt, 5))
+    coeff[:, 1] = rng.uniform(-1, 1, size=(nt, 5))
+    coeff[:, 4] = rng.uniform(20, 60, size=(nt, 5))
+    coeff[:, 5] = rng.uniform(-1, 1, size=(nt, 5))
+    dt = rng.choice([0, 1, 1, 2], size=nt).astype(np.int32)
+    dt[-1] = 1
+    coeff[dt == 2, 0, :2] = [0.4, 30.0]
+    last = np.zeros(nt, dtype=np.int32)
+    last[-1] = 1
+    last[nt // 2] = 1
+    idx = [a, a + 1, a + 2, a + 3]
+    f_main, out = run_bonded(lib, 4, r, box, idx, coeff.reshape(-1), dt, real)
+    vp = ctypes.c_void_p
+    f_add = np.zeros((n, 3), dtype=real)
+    e_cbt = ctypes.c_double(0.0)
+    dip = np.zeros((nt, 4, 3), dtype=real)
+    tm = np.zeros((nt, 6, 3, 3), dtype=real)
+    fd = rng.normal(size=(nt, 4, 3)).astype(real)
+    f_beads = np.zeros((n, 3), dtype=real)
+    par = np.ascontiguousarray(coeff.reshape(-1))
+    rc = lib.host_cbt(int(real == np.float64), r.ctypes.data_as(vp), box.ctypes.data_as(vp), ctypes.c_longlong(n),
+                      ctypes.c_longlong(nt), *[i32(x).ctypes.data_as(vp) for x in idx], par.ctypes.data_as(vp),
+                      dt.ctypes.data_as(vp), last.ctypes.data_as(vp), f_add.ctypes.data_as(vp), ctypes.byref(e_cbt),
+                      dip.ctypes.data_as(vp), tm.ctypes.data_as(vp), fd.ctypes.data_as(vp), f_beads.ctypes.data_as(vp))
+    assert rc == 0
+    fo, eo, dipo, tmo = bo.compute_dihedral_forces(r, box, *idx, coeff, dt, last, dipole_flag=1, full=True)
+    scale = np.abs(fo).max()
+    assert np.abs(f_main.astype(np.float64) + f_add.astype(np.float64) - fo).max() < tol * scale
+    assert out[0] + e_cbt.value == pytest.approx(eo, rel=max(tol, 1e-12))
+    assert np.abs(dip.astype(np.float64) - dipo.astype(np.float64)).max() < (1e-12 if real == np.float64 else 1e-6)
+    assert np.abs(tm.astype(np.float64) - tmo.astype(np.float64)).max() < tol * max(1.0, np.abs(tmo).max())
+    fb = bo.dipole_forces_redistribution(n, fd, tm, *idx, dt, last)
+    assert np.abs(f_beads.astype(np.float64) - fb).max() < tol * max(1.0, np.abs(fb).max())
+    # rows / matrices of dihedrals that are not dtype 1, and the second pair where the dihedral is not the last one
+    assert np.all(dip[dt != 1] == 0) and np.all(tm[dt != 1] == 0)
+    assert np.all(dip[(dt == 1) & (last == 0), 2:] == 0)
+
+
 def test_reference_kats_through_the_device_source(lib):
     """test/test_force.py known answers (see tests/test_oracle_bonded.py) through bonded.cuh."""
     r, box = G["dppc/r"], G["dppc/box"]

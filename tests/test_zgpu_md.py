@@ -85,6 +85,73 @@ def test_bonded_forces_match_oracle(real):
     assert float(e) == pytest.approx(eo, rel=ETOL[real])
 
 
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_cbt_dihedrals_dipoles_and_redistribution_match_oracle(real):
+    """dih_type 1 through the reference-shaped interface (``cdf`` with ``bb_index`` / ``dipole_flag``, then
+    ``dipole_forces_redistribution``): forces, energy, dipole positions, transfer matrices and redistributed forces
+    against the oracle's restatement of compute_dihedral_forces.f90 + dipole_reconstruction.f90 + force.py:855-880;
+    device tensors and the numpy interface; mixed with dihedrals of types 0 and 2."""
+    from hymd_b200 import _lib
+    from hymd_b200 import force as F
+    rng = np.random.default_rng(33)
+    n = 300
+    box = np.array([3.0, 3.5, 4.0])
+    r = np.mod(np.cumsum(rng.normal(scale=0.33, size=(n, 3)), axis=0) + 1.5, box).astype(real)
+    a = np.arange(n - 3)
+    nt = len(a)
+    coeff = np.zeros((nt, 6, 5))
+    coeff[:, 0] = rng.uniform(0.5, 2.0, size=(nt, 5))
+    coeff[:, 1] = rng.uniform(-1, 1, size=(nt, 5))
+    coeff[:, 4] = rng.uniform(20, 60, size=(nt, 5))
+    coeff[:, 5] = rng.uniform(-1, 1, size=(nt, 5))
+    dt = rng.choice([0, 1, 1, 2], size=nt)
+    dt[-1] = 1
+    coeff[dt == 2, 0, :2] = [0.4, 30.0]
+    last = np.zeros(nt, dtype=int)
+    last[-1] = 1
+    last[np.nonzero(dt == 1)[0][::7]] = 1
+    idx = (a, a + 1, a + 2, a + 3)
+    fo_, eo, dipo, tmo = bo.compute_dihedral_forces(r, box, *idx, coeff, dt, last, dipole_flag=1, full=True)
+    tol = 1e-10 if real == np.float64 else 1e-6
+    scale = np.abs(fo_).max()
+    tdt = torch.float64 if real == np.float64 else torch.float32
+    # device tensors
+    pos = torch.as_tensor(r, device=DEVICE)
+    f = torch.empty_like(pos)
+    dip = torch.zeros((nt, 4, 3), dtype=tdt, device=DEVICE)
+    tm = torch.zeros((nt, 6, 3, 3), dtype=tdt, device=DEVICE)
+    e = F.compute_dihedral_forces(f, pos, dip, tm, box, *idx, coeff, dt, last, 1)
+    assert np.abs(f.cpu().numpy() - fo_).max() < tol * scale
+    assert float(e) == pytest.approx(eo, rel=tol)
+    assert np.abs(dip.cpu().numpy().astype(np.float64) - dipo.astype(np.float64)).max() < (1e-12 if real == np.float64 else 2e-6)
+    assert np.abs(tm.cpu().numpy().astype(np.float64) - tmo.astype(np.float64)).max() < tol * max(1.0, np.abs(tmo).max())
+    # dipole_flag = 0: same forces and energy, dipole arrays zeroed (compute_dihedral_forces.f90:27-28)
+    f0 = torch.empty_like(pos)
+    e0 = F.compute_dihedral_forces(f0, pos, dip, tm, box, *idx, coeff, dt, last, 0)
+    assert torch.equal(f0, f) and float(e0) == float(e) and not dip.any() and not tm.any()
+    # redistribution of forces on the dipole charges (what the second PME call returns) to the beads
+    fd = rng.normal(size=(nt, 4, 3)).astype(real)
+    want = bo.dipole_forces_redistribution(n, fd, tmo, *idx, dt, last)
+    fb = torch.full((n, 3), 7.0, dtype=tdt, device=DEVICE)
+    F.dipole_forces_redistribution(fb, torch.as_tensor(fd, device=DEVICE), torch.as_tensor(tmo, device=DEVICE),
+                                   *idx, dt, last, coeff=coeff)
+    assert np.abs(fb.cpu().numpy() - want).max() < tol * max(1.0, np.abs(want).max())
+    # numpy interface, Fortran-ordered arrays as main.py:505-506 makes them
+    fn = np.zeros((n, 3), dtype=real)
+    dipn = np.asfortranarray(np.ones((nt, 4, 3), dtype=real))
+    tmn = np.asfortranarray(np.ones((nt, 6, 3, 3), dtype=real))
+    en = F.compute_dihedral_forces(fn, r, dipn, tmn, box, *idx, coeff, dt, last, 1)
+    assert np.abs(fn - fo_).max() < tol * scale and en == pytest.approx(eo, rel=tol)
+    assert np.abs(dipn.astype(np.float64) - dipo.astype(np.float64)).max() < (1e-12 if real == np.float64 else 2e-6)
+    fbn = np.zeros((n, 3), dtype=real)
+    F.dipole_forces_redistribution(fbn, fd, tmn, *idx, dt, last)
+    assert np.abs(fbn - want).max() < 2 * tol * max(1.0, np.abs(want).max())
+    # the fused inner step refuses such a topology instead of dropping the bending term
+    topo = F.BondedTopology(n, dihedrals=(*idx, coeff, dt, last), device=DEVICE)
+    with pytest.raises(_lib.HymdError):
+        topo.inner_step(pos, torch.empty_like(pos), torch.zeros_like(pos), box, 72.0, 0.01, 1, 0.01)
+
+
 def test_reference_kats_on_the_device_and_numpy_interface():
     """test/test_force.py known answers (via the golden file) with numpy in / numpy out like the f2py
     kernels; the dihedral sign is the production Fortran's (see tests/test_oracle_bonded.py)."""
@@ -122,9 +189,9 @@ def test_bonded_edge_cases():
     assert float(e) == 0.0 and not f.any()
     with pytest.raises(_lib.HymdError):          # index outside the local particles
         F.compute_bond_forces(f, pos, box, np.array([0]), np.array([9]), np.array([0.4]), np.array([1.0]))
-    with pytest.raises(_lib.HymdError):          # dih_type 1 is not built
+    with pytest.raises(_lib.HymdError):          # dih_type outside 0, 1, 2
         F.compute_dihedral_forces(f, pos, None, None, box, np.array([0]), np.array([1]), np.array([2]),
-                                  np.array([3]), np.zeros((1, 6, 5)), np.array([1]))
+                                  np.array([3]), np.zeros((1, 6, 5)), np.array([3]))
     # bitwise reproducible
     a = np.arange(4)
     args = (box, a, a + 1, np.full(4, 0.4), np.full(4, 100.0))

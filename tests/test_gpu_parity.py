@@ -349,6 +349,65 @@ def test_second_pme_call_on_another_particle_set(dtype, mesh):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_peptide_dipole_flow_matches_oracle(dtype):
+    """main.py:530-552 + 1060-1095 end to end on the device: dihedral forces of a peptide backbone with
+    ``dipole_flag = 1`` leave the reconstructed dipole charges' positions and the transfer matrices; the PME cycle on
+    those 4 n_tors point charges (second context, the real charges' state untouched) gives the forces on them;
+    ``dipole_forces_redistribution`` carries these back to the backbone beads.  Compared with the same chain of
+    oracle restatements."""
+    from gpu_common import GpuRun, OracleRun, rel_err
+    from hymd_b200 import field as F
+    from hymd_b200 import force as FO
+    from oracle import bonded_oracle as bo
+    cfg, pos, types, q = _system(6000, [32, 32, 32], [4.0, 5.0, 6.0], dtype, seed=91, coulomb=True)
+    g = GpuRun(cfg, pos, types, charges=q)
+    rng = np.random.default_rng(17)
+    box = np.asarray(cfg.box_size, dtype=np.float64)
+    # three backbones of 30 beads among the first particles: consecutive beads 0.3 nm apart
+    n_bb, L = 3, 30
+    a = []
+    for c in range(n_bb):
+        start = c * L
+        chain = np.mod(np.cumsum(rng.normal(scale=0.2, size=(L, 3)), axis=0) + rng.uniform(0, 1, 3) * box, box)
+        pos[start:start + L] = chain.astype(dtype)
+        a += list(range(start, start + L - 3))
+    a = np.array(a)
+    n_tors = len(a)
+    idx = (a, a + 1, a + 2, a + 3)
+    coeff = np.zeros((n_tors, 6, 5))
+    coeff[:, 0] = rng.uniform(0.5, 2.0, size=(n_tors, 5))
+    coeff[:, 4] = rng.uniform(20, 60, size=(n_tors, 5))
+    dt = np.ones(n_tors, dtype=int)
+    last = np.zeros(n_tors, dtype=int)
+    last[L - 4::L - 3] = 1
+    charges_d = np.array([[0.25, -0.25, 0.25, -0.25] if l else [0.25, -0.25, 0.0, 0.0] for l in last],
+                         dtype=dtype).reshape(-1)                      # main.py:475-485
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    pos_d = torch.as_tensor(pos, device="cuda")
+    f_dih = torch.empty_like(pos_d)
+    dip = torch.zeros((n_tors, 4, 3), dtype=tdt, device="cuda")
+    tm = torch.zeros((n_tors, 6, 3, 3), dtype=tdt, device="cuda")
+    FO.compute_dihedral_forces(f_dih, pos_d, dip, tm, box, *idx, coeff, dt, last, 1)
+    pm = g.pm
+    dip_pos = dip.reshape(4 * n_tors, 3)
+    f_dip = torch.zeros_like(dip_pos)
+    meshes = [pm.create("real"), pm.create("complex"), pm.create("real"), pm.create("complex"),
+              [pm.create("complex") for _ in range(3)], [pm.create("real") for _ in range(3)]]
+    F.update_field_force_q(torch.as_tensor(charges_d, device="cuda"), *meshes, f_dip, pm.decompose(dip_pos), g.h, pm,
+                           dip_pos, cfg)
+    f_beads = torch.zeros_like(pos_d)
+    FO.dipole_forces_redistribution(f_beads, f_dip.reshape(n_tors, 4, 3), tm, *idx, dt, last, coeff=coeff)
+    # oracle chain
+    fo_, eo, dipo, tmo = bo.compute_dihedral_forces(pos, box, *idx, coeff, dt, last, dipole_flag=1, full=True)
+    o = OracleRun(cfg, dipo.reshape(-1, 3), np.zeros(4 * n_tors, dtype=np.int32), charges=charges_d)
+    want = bo.dipole_forces_redistribution(len(pos), o.elec_forces.reshape(n_tors, 4, 3), tmo, *idx, dt, last)
+    tol = TOL[dtype]
+    assert rel_err(f_dih.cpu().numpy(), fo_) < (1e-6 if dtype == np.float32 else 1e-10)
+    assert rel_err(f_dip.cpu().numpy(), o.elec_forces) < 10 * tol     # dipole positions differ by one rounding in fp32
+    assert rel_err(f_beads.cpu().numpy(), want) < 10 * tol
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("mesh,n", [([32, 64, 64], 60000), ([24, 20, 28], 9000), ([16, 16, 80], 200000), ([9, 12, 10], 700)])
 def test_paint_kernels_are_bitwise_identical(dtype, mesh, n, monkeypatch):
     """The flattened-list paint (default) and the row-walker paint (HYMD_B200_PAINT=rows: a lane per cell row,

@@ -1324,8 +1324,21 @@ static int launch_plane(hymd_ctx* c, const void* in, void* out, const PlaneParam
     return HYMD_OK;
 }
 
+// 64^2 / 128^2 fp32 planes: two 256-thread CTAs per SM instead of one of 512 when the launch has work for four waves
+// of SMs (>= 4 x SMs (field, plane) units).  Measured at C3 (1 M particles, 128^3, T = 6; profiles/r3p_*): forward
+// 0.052 -> 0.046 ms, inverse 0.195 -> 0.164 ms per cycle; the PME transforms of the same system (128 / 384 units) are
+// slower that way (0.052 -> 0.060 ms) and keep the 512-thread CTA.  HYMD_B200_PLANE_THREADS = 256 / 512 forces either.
+static bool plane_half_ctas(const hymd_ctx* c, int nunits) {
+    if (const char* e = getenv("HYMD_B200_PLANE_THREADS")) return atoi(e) == 256;
+    const int sms = c->sm_count > 0 ? c->sm_count : 148;
+    return nunits >= 4 * sms;
+}
+
 template <typename real, int N, bool INVERSE>
 static int launch_plane_nt(hymd_ctx* c, const void* in, void* out, const PlaneParams& p, cudaStream_t s) {
+    if constexpr (sizeof(real) == 4 && (N == 64 || N == 128)) {
+        if (plane_tiles() == 1 && plane_half_ctas(c, p.nunits)) return launch_plane<real, N, 256, 1, INVERSE>(c, in, out, p, s);
+    }
     switch (plane_tiles()) {
         case 2: return launch_plane<real, N, 512, 2, INVERSE>(c, in, out, p, s);
         case 3: return launch_plane<real, N, 512, 3, INVERSE>(c, in, out, p, s);

@@ -210,3 +210,11 @@ def test_pipelined_exchange_matches_oracle(P, mesh, pme, dtype, monkeypatch):
                      env={"HYMD_B200_XPIPE": "2", "HYMD_B200_XPIPE_GROUP": "2", "HYMD_B200_XPIPE_COPY": "ce"}, monkeypatch=monkeypatch)
     _run_and_compare(P, mesh, 20000, dtype, pme, "drifted", steps=2,
                      env={"HYMD_B200_XPIPE": "0"}, monkeypatch=monkeypatch)
+
+
+@pytest.mark.parametrize("P,mesh", [(2, [32, 64, 64]), (4, [16, 128, 128])])
+def test_half_size_plane_ctas_on_slabs(P, mesh, monkeypatch):
+    """HYMD_B200_PLANE_THREADS=256 (two 256-thread CTAs per SM for 64^2 / 128^2 planes, the default for large
+    launches) with the blocked receive layout of the slab pipeline, pipelined exchange forced on."""
+    _run_and_compare(P, mesh, 20000, np.float32, True, "drifted", steps=2,
+                     env={"HYMD_B200_PLANE_THREADS": "256", "HYMD_B200_XPIPE": "2"}, monkeypatch=monkeypatch)

@@ -1339,6 +1339,10 @@ static int launch_plane_nt(hymd_ctx* c, const void* in, void* out, const PlanePa
     if constexpr (sizeof(real) == 4 && (N == 64 || N == 128)) {
         if (plane_tiles() == 1 && plane_half_ctas(c, p.nunits)) return launch_plane<real, N, 256, 1, INVERSE>(c, in, out, p, s);
     }
+    if constexpr (sizeof(real) == 4 && N == 512) {      // experiment (C5): only when forced
+        const char* e = getenv("HYMD_B200_PLANE_THREADS");
+        if (plane_tiles() == 1 && e && atoi(e) == 256) return launch_plane<real, N, 256, 1, INVERSE>(c, in, out, p, s);
+    }
     switch (plane_tiles()) {
         case 2: return launch_plane<real, N, 512, 2, INVERSE>(c, in, out, p, s);
         case 3: return launch_plane<real, N, 512, 3, INVERSE>(c, in, out, p, s);

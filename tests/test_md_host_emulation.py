@@ -70,6 +70,10 @@ def test_cbt_dihedrals(emulated, real):
     emulated.test_cbt_dihedrals_dipoles_and_redistribution_match_oracle(real)
 
 
+def test_respa_md_with_cbt(emulated):
+    emulated.test_respa_md_with_cbt_dihedrals_takes_the_unfused_loop()
+
+
 def test_bonded_kats_and_edges(emulated):
     emulated.test_reference_kats_on_the_device_and_numpy_interface()
     emulated.test_bonded_edge_cases()

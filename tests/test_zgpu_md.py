@@ -385,6 +385,42 @@ def test_fused_inner_step_equals_separate_launches(real):
         assert out[True][2][k] == pytest.approx(out[False][2][k], rel=1e-6 if real == np.float32 else 1e-11)
 
 
+def test_respa_md_with_cbt_dihedrals_takes_the_unfused_loop():
+    """A topology with dih_type 1 through RespaMD: the fused inner-step kernel does not carry the bending term, so
+    ``fused=True`` must run the separate launches (bitwise the same trajectory as ``fused=False``), and the dihedral
+    energy it reports is the oracle's for the final positions."""
+    from hymd_b200.force import BondedTopology
+    from hymd_b200.md import RespaMD
+    rng = np.random.default_rng(44)
+    box = np.array([4.0, 5.0, 4.5])
+    n = 60
+    r = np.mod(np.cumsum(rng.normal(scale=0.25, size=(n, 3)), axis=0) + 2.0, box)
+    a2, a4 = np.arange(n - 1), np.arange(n - 3)
+    coeff = np.zeros((len(a4), 6, 5))
+    coeff[:, 0] = rng.uniform(0.5, 2.0, size=(len(a4), 5))
+    coeff[:, 4] = rng.uniform(20, 40, size=(len(a4), 5))
+    dt4 = np.ones(len(a4), dtype=int)
+    last = np.zeros(len(a4), dtype=int)
+    last[-1] = 1
+    topo = BondedTopology(n, bonds=(a2, a2 + 1, np.full(n - 1, 0.47), np.full(n - 1, 1250.0)),
+                          dihedrals=(a4, a4 + 1, a4 + 2, a4 + 3, coeff, dt4, last),
+                          device=DEVICE if DEVICE != "cuda" else None)
+    assert topo.n_cbt == len(a4)
+    v = rng.normal(scale=0.1, size=(n, 3))
+    out = {}
+    for fused in (True, False):
+        md = RespaMD(lambda x: [torch.zeros_like(x)], box, 72.0, 0.002, respa_inner=4, topology=topo, fused=fused)
+        xd, vd = dev(r, np.float64), dev(v, np.float64)
+        f = [torch.zeros_like(xd)]
+        for _ in range(3):
+            f = md.step(xd, vd, f)
+        out[fused] = (xd.cpu().numpy(), vd.cpu().numpy(), md.bonded_energies())
+    assert np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1])
+    # energies belong to the positions of the last inner force evaluation = the final positions
+    fo_, eo = bo.compute_dihedral_forces(out[True][0], box, a4, a4 + 1, a4 + 2, a4 + 3, coeff, dt4, last)
+    assert out[True][2][4] == pytest.approx(eo, rel=1e-10)
+
+
 def test_fused_step_edge_cases():
     """Empty topology (monatomic system), a single particle, and a 129-particle chain whose terms straddle
     the CTA boundary, through the fused inner step in per-particle and CTA-cooperative mode."""

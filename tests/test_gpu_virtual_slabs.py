@@ -218,3 +218,70 @@ def test_half_size_plane_ctas_on_slabs(P, mesh, monkeypatch):
     launches) with the blocked receive layout of the slab pipeline, pipelined exchange forced on."""
     _run_and_compare(P, mesh, 20000, np.float32, True, "drifted", steps=2,
                      env={"HYMD_B200_PLANE_THREADS": "256", "HYMD_B200_XPIPE": "2"}, monkeypatch=monkeypatch)
+
+
+def _dipole_cycle(rank, cfg, pos, types, q, owner, dip_pos, dip_q, dip_owner, tdt, results):
+    """Main PME cycle on the rank's particles, then the peptide-dipole call (main.py:1060-1095) on the rank's own
+    dipole charges with pm.create meshes: a second context per rank, created collectively on first use."""
+    from hymd_b200 import field as F
+    from hymd_b200.hamiltonian import get_hamiltonian
+    idx = np.nonzero(owner == rank)[0]
+    didx = np.nonzero(dip_owner == rank)[0]
+    ham = get_hamiltonian(cfg)
+    pm, fl, ecl, cl = F.initialize_pm(None, cfg)
+    phi, phi_fourier, force_mesh, v_ext_fourier, v_ext, phi_transfer, phi_laplacian = fl
+    phi_q, phi_q_fourier, psi, elec_field = ecl
+    dev = pm.device
+    pos_d = torch.as_tensor(np.ascontiguousarray(pos[idx]), dtype=tdt, device=dev)
+    typ_d = torch.as_tensor(types[idx], device=dev)
+    q_d = torch.as_tensor(q[idx], dtype=tdt, device=dev)
+    layouts = [pm.decompose(None) for _ in range(cfg.n_types)]
+    force_d = torch.zeros((len(idx), 3), dtype=tdt, device=dev)
+    eforce_d = torch.zeros((len(idx), 3), dtype=tdt, device=dev)
+    F.update_field(phi, phi_laplacian, phi_transfer, layouts, force_mesh, ham, pm, pos_d, typ_d, cfg, v_ext,
+                   phi_fourier, v_ext_fourier, cfg.m)
+    F.compute_field_force(layouts, pos_d, force_mesh, force_d, typ_d, cfg.n_types)
+    F.update_field_force_q(q_d, phi_q, phi_q_fourier, psi, None, None, elec_field, eforce_d, pm.decompose(None), ham,
+                           pm, pos_d, cfg)
+    e0 = F.compute_field_and_kinetic_energy(phi, phi_q, psi, torch.zeros_like(pos_d), ham, pos_d, typ_d, v_ext, cfg, layouts)
+    dp = torch.as_tensor(np.ascontiguousarray(dip_pos[didx]), dtype=tdt, device=dev)
+    dq = torch.as_tensor(dip_q[didx], dtype=tdt, device=dev)
+    df = torch.zeros((len(didx), 3), dtype=tdt, device=dev)
+    F.update_field_force_q(dq, pm.create("real"), pm.create("complex"), pm.create("real"), pm.create("complex"),
+                           [pm.create("complex") for _ in range(3)], [pm.create("real") for _ in range(3)], df,
+                           pm.decompose(dp), ham, pm, dp, cfg)
+    e1 = F.compute_field_and_kinetic_energy(phi, phi_q, psi, torch.zeros_like(pos_d), ham, pos_d, typ_d, v_ext, cfg, layouts)
+    pm.check()
+    results[rank] = {"didx": didx, "dforce": df.cpu().numpy(), "e0": e0, "e1": e1, "idx": idx,
+                     "eforce": eforce_d.cpu().numpy()}
+    pm.close()
+    return True
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_peptide_dipole_call_on_slabs(P):
+    """The second PME call on another particle set, sharded: every rank holds its own dipole charges (they are not
+    domain-decomposed in the reference either, main.py:469-471), the second context routes them like any particle;
+    forces equal the single-rank oracle and the real charges' energies are untouched."""
+    from gpu_common import OracleRun, rel_err
+    from hymd_b200._world import VirtualRanks
+    dtype, mesh = np.float64, [32, 32, 32]
+    cfg, pos, types, q = _system(12000, mesh, dtype, True)
+    owner = _ownership(pos, mesh, cfg.box_size, P, "drifted")
+    rng = np.random.default_rng(4)
+    nd = 4 * 53
+    dip_pos = (rng.uniform(0, 1, size=(nd, 3)) * np.asarray(cfg.box_size)).astype(dtype)
+    dip_q = np.tile(np.array([0.25, -0.25, 0.25, -0.25]), nd // 4).astype(dtype)
+    dip_owner = np.arange(nd) // 4 % P                 # whole torsions on arbitrary ranks
+    results = [None] * P
+    VirtualRanks(P).run(_dipole_cycle, cfg, pos, types, q, owner, dip_pos, dip_q, dip_owner, torch.float64, results)
+    df = np.zeros((nd, 3))
+    ef = np.zeros((len(pos), 3))
+    for r in results:
+        df[r["didx"]] = r["dforce"]
+        ef[r["idx"]] = r["eforce"]
+        assert r["e0"] == r["e1"]
+    o = OracleRun(cfg, dip_pos, np.zeros(nd, dtype=np.int32), charges=dip_q)
+    assert rel_err(df, o.elec_forces) < TOL[dtype]
+    o2 = OracleRun(cfg, pos, types, charges=q)
+    assert rel_err(ef, o2.elec_forces) < TOL[dtype]

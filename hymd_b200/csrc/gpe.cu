@@ -4,7 +4,9 @@
 // (field.py:706-760).  Per call: 1 charge paint, (6 + T + n_iter) forward and (11 + 3T + 3 n_iter)
 // inverse transforms through the same plane / x-line / cuFFT pipeline as the force path (fft_forward /
 // fft_inverse of slabfft.cu), one k-space kernel with four modes, a handful of pointwise kernels and
-// a per-type readout of 3T electrostatic force meshes.  Single GPU only for now (P == 1).
+// a per-type readout of 3T electrostatic force meshes.  Several slabs: the same transforms (slabfft.cu), pointwise
+// kernels on the owned planes, the convergence measure combined over the ranks on the device, guests read out and
+// returned like in the force path.
 //
 // Reference semantics kept on purpose:
 //  * the masked divisions `np.divide(x, y, where=y > 1e-6, out=o)` leave `o` untouched where the mask
@@ -15,9 +17,8 @@
 //  * r2c carries 1/M, c2r none (every k-space mode applies `coef` = 1/M once per forward transform);
 //  * Nyquist rule of kspace.cu for every i k_d product.
 //
-// STATUS: written after the round's GPU minutes were spent -- compiles for sm_100a, never run on a GPU.
-// The oracle (oracle/gpe_oracle.py) and its golden vectors from the reference's own function are what
-// tests/test_zzgpu_gpe.py checks it against.
+// Checked against the oracle (oracle/gpe_oracle.py, pinned on golden vectors of the reference's own function) in
+// tests/test_zzgpu_gpe.py, on one GPU and on virtual slabs.
 #include <stdlib.h>
 
 #include "ctx.cuh"
@@ -149,6 +150,16 @@ __global__ void __launch_bounds__(256) gpe_reduce_kernel(const double* __restric
     }
 }
 
+// The convergence measure of all ranks (csum / cnorm are global sums, max_diff an MPI.MAX: main.py:141-163) into the
+// loop state {delta, iterations, conv_crit}; a converged loop is left alone (every rank sees the same state).
+__global__ void gpe_combine_kernel(const double* __restrict__ all, int P, int mode, double* __restrict__ state) {
+    if (state[0] <= state[2]) return;
+    double v = all[0];
+    for (int q = 1; q < P; ++q) v = mode == 0 ? (all[q] > v ? all[q] : v) : v + all[q];
+    state[0] = v;
+    state[1] += 1.0;
+}
+
 // elec_dot = |E|^2, elec_field_contrib = elec_dot / den where den > 1e-6, and
 // Vbar_t = q_t psi - (0.5 / eps0_inv) (eps_t - phi_eps) elec_field_contrib   (field.py:1079-1097)
 template <typename real>
@@ -219,7 +230,7 @@ static int gpe_state(hymd_ctx* c) {
     HYMD_CHECK(galloc(&st->kS, kb, true));
     HYMD_CHECK(galloc(&st->mesh, (size_t)3 * T * gb, true));
     HYMD_CHECK(galloc((void**)&st->d_par, sizeof(double) * 2 * HYMD_MAX_TYPES, true));
-    HYMD_CHECK(galloc((void**)&st->red, sizeof(double) * (GPE_BLOCKS + 4), true));
+    HYMD_CHECK(galloc((void**)&st->red, sizeof(double) * (GPE_BLOCKS + 4 + HYMD_MAX_PEERS), true));
     HYMD_CHECK(galloc(&c->psi, rb, true));
     if (!st->urow_id) {
         HYMD_CHECK(galloc((void**)&st->urow_id, sizeof(int) * HYMD_MAX_TYPES, true));
@@ -267,7 +278,9 @@ static int gpe_cycle_t(hymd_ctx* c, const hymd_gpe_params* prm, void* d_force, i
     GpeState* st = c->gpe;
     const Geometry& g = c->g;
     const int T = c->T;
-    const long long n = g.real_elems, fs = g.real_elems;
+    // pointwise kernels and reductions run over the owned planes (the first nxl of a field's nxl + 1 planes on
+    // several slabs: the ghost plane belongs to the next slab's sums)
+    const long long n = (long long)g.nxl * g.Ny * g.Nz, fs = g.real_elems;
     const double M = (double)g.Nx * g.Ny * g.Nz;
     const double eps0_inv = prm->coulomb_constant * 4.0 * 3.14159265358979323846;
     double par[2 * HYMD_MAX_TYPES];
@@ -277,6 +290,7 @@ static int gpe_cycle_t(hymd_ctx* c, const hymd_gpe_params* prm, void* d_force, i
     PhaseScope ps(c, HYMD_PHASE_PME_KSPACE, s);
     // smeared charge density (field.py:1006-1010)
     HYMD_CHECK(paint_charges(c, s));
+    HYMD_CHECK(halo_reduce(c, c->phi_q, 1, s));
     HYMD_CHECK(fft_forward(c, c->phi_q, 1, st->kA, s));
     HYMD_CHECK(kspace<real>(c, st->kA, 1, st->kS, nullptr, 1.0 / M, true, false, 1.0, s));
     HYMD_CHECK(fft_inverse(c, st->kS, 1, c->phi_q, false, s));
@@ -314,7 +328,12 @@ static int gpe_cycle_t(hymd_ctx* c, const hymd_gpe_params* prm, void* d_force, i
                                                             (real)prm->pol_mixing, (real*)st->pol,
                                                             prm->convergence_type, st->red, n, state);
             HYMD_LAUNCH_CHECK(c);
-            gpe_reduce_kernel<<<1, 256, 0, s>>>(st->red, GPE_BLOCKS, prm->convergence_type, 1.0, state, 1);
+            double* xloc = st->red + GPE_BLOCKS + 3;
+            double* xall = xloc + 1;
+            gpe_reduce_kernel<<<1, 256, 0, s>>>(st->red, GPE_BLOCKS, prm->convergence_type, 1.0, xloc, 0);
+            HYMD_LAUNCH_CHECK(c);
+            if (g.P > 1) HYMD_CHECK(comm_allgather_host(c, xloc, xall, sizeof(double), s));
+            gpe_combine_kernel<<<1, 1, 0, s>>>(g.P > 1 ? xall : xloc, g.P, prm->convergence_type, state);
             HYMD_LAUNCH_CHECK(c);
         }
         launched += batch;
@@ -341,10 +360,12 @@ static int gpe_cycle_t(hymd_ctx* c, const hymd_gpe_params* prm, void* d_force, i
     HYMD_CHECK(kspace<real>(c, st->kA, T, nullptr, st->kB, 1.0 / M, true, false, -1.0, s));
     HYMD_CHECK(fft_inverse(c, st->kB, 3 * T, st->mesh, true, s));
     if (!c->plane) HYMD_CHECK(fill_ghosts(c, st->mesh, 3 * T, s));
+    HYMD_CHECK(halo_fetch(c, st->mesh, 3 * T, s));
     c->have_psi = true;
     c->have_phiq_hat = false;      // phi_q now holds the filtered, eps-scaled density (reference semantics)
     st->have = true;
-    if (c->np > 0 && d_force) HYMD_CHECK(readout_custom(c, st->mesh, st->urow_id, d_force, s));
+    // several slabs: collective (a rank without particles still reads out its guests)
+    if (g.P > 1 || (c->np > 0 && d_force)) HYMD_CHECK(readout_custom(c, st->mesh, st->urow_id, d_force, s));
     return HYMD_OK;
 }
 
@@ -357,7 +378,7 @@ int gpe_cycle(hymd_ctx* c, const hymd_gpe_params* prm, void* d_force, int32_t* i
 int gpe_energy(hymd_ctx* c, double coulomb_constant, double* out, cudaStream_t s) {
     GpeState* st = c->gpe;
     const Geometry& g = c->g;
-    const long long n = g.real_elems;
+    const long long n = (long long)g.nxl * g.Ny * g.Nz;       // owned planes: the Python layer sums over the ranks
     if (c->f64) gpe_energy_kernel<double><<<GPE_BLOCKS, 256, 0, s>>>((const double*)st->eps, (const double*)st->dot, st->red, n);
     else gpe_energy_kernel<float><<<GPE_BLOCKS, 256, 0, s>>>((const float*)st->eps, (const float*)st->dot, st->red, n);
     HYMD_LAUNCH_CHECK(c);
@@ -395,7 +416,6 @@ int hymd_gpe_cycle(hymd_ctx* c, const hymd_gpe_params* prm, void* d_elec_force, 
         set_error("hymd_gpe_params size mismatch: caller %d, library %zu", prm->struct_size, sizeof(hymd_gpe_params));
         return HYMD_ERR_INVALID;
     }
-    if (c->g.P != 1) { set_error("hymd_gpe_cycle: single GPU only (world_size = %d)", c->g.P); return HYMD_ERR_INVALID; }
     if (!c->cfg.pme) { set_error("context created without the charge-density buffers (pme = 0)"); return HYMD_ERR_STATE; }
     if (!c->sorted || !c->has_charges) { set_error("hymd_gpe_cycle needs hymd_sort_particles with charges"); return HYMD_ERR_STATE; }
     if (prm->convergence_type < 0 || prm->convergence_type > 2 || !(prm->conv_crit > 0) ||

@@ -541,12 +541,14 @@ static int launch_gather_custom(hymd_ctx* c, const void* mesh, const int* d_urow
     using Tr = RTraits<real>;
     GatherParams p;
     gather_params(c, p);
-    if (p.rt) { set_error("custom read-outs run on a single slab only"); return HYMD_ERR_STATE; }
+    HYMD_CHECK(route_acquire_return(c, s));
     const unsigned int blocks = (unsigned int)((p.n + 255) / 256);
-    readout_gather_kernel<real, false><<<blocks, 256, 0, s>>>(
-        (const real*)mesh, (const typename Tr::Rec*)c->rec, (const real*)c->q_sorted, d_urow, (real*)d_force, p);
-    HYMD_LAUNCH_CHECK(c);
-    return HYMD_OK;
+    if (blocks > 0) {
+        readout_gather_kernel<real, false><<<blocks, 256, 0, s>>>(
+            (const real*)mesh, (const typename Tr::Rec*)c->rec, (const real*)c->q_sorted, d_urow, (real*)d_force, p);
+        HYMD_LAUNCH_CHECK(c);
+    }
+    return route_return(c, d_force, s);       // several slabs: guests' rows go back to their owners
 }
 
 int readout_custom(hymd_ctx* c, const void* mesh, const int* d_urow, void* d_force, cudaStream_t s) {

@@ -41,10 +41,6 @@ def initialize_pm(pmesh, config, comm=None):
     list layouts (``field.py:139-147, 66-75, 83-86``)."""
     dtype = "f8" if np.dtype(config.dtype) == np.float64 else "f4"
     coulombtype = getattr(config, "coulombtype", None)
-    if coulombtype == "PIC_Spectral_GPE":
-        from . import _world
-        if _world.current().size > 1:
-            raise NotImplementedError("coulombtype='PIC_Spectral_GPE' runs on a single GPU only")
     pm = ParticleMesh(config.mesh_size, BoxSize=config.box_size, dtype=dtype, comm=comm,
                       config=config)
     T = config.n_types

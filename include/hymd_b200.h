@@ -248,7 +248,7 @@ int hymd_exchange_cost(hymd_ctx* ctx, int64_t* sent_to, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row f3: general-Poisson-equation electrostatics, coulombtype "PIC_Spectral_GPE".
- * NOT YET RUN ON A GPU (written after the round's GPU minutes were spent); single GPU only.
+ * One GPU or several slabs (collective: every rank calls it, also one without particles).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t struct_size;                     /* = sizeof(hymd_gpe_params) */

@@ -35,6 +35,7 @@ EXPORTS = [
     "hymd_gpe_cycle", "hymd_gpe_energy",
     "hymd_local_group_id", "hymd_ctx_check", "hymd_exchange_cost",
     "hymd_bonded_set_last", "hymd_bonded_dipoles", "hymd_dipole_redistribute",
+    "hymd_update_cycle", "hymd_ctx_set_graph", "hymd_ctx_graph_stats",
 ]
 PHASES = ["sort", "paint", "fft_fwd", "kspace", "fft_inv", "ghost", "readout", "pme_paint",
           "pme_fft", "pme_kspace", "pme_readout", "alltoall", "halo", "migrate", "byproducts",
@@ -126,6 +127,9 @@ def load():
     lib.hymd_paint.argtypes = [vp, vp]
     lib.hymd_field_cycle.argtypes = [vp, ctypes.c_int, vp]
     lib.hymd_readout.argtypes = [vp, vp, vp]
+    lib.hymd_update_cycle.argtypes = [vp, vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, vp]
+    lib.hymd_ctx_set_graph.argtypes = [vp, ctypes.c_int]
+    lib.hymd_ctx_graph_stats.argtypes = [vp, P(i64)]
     lib.hymd_pme_cycle.argtypes = [vp, vp, ctypes.c_int, vp]
     lib.hymd_materialize.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.hymd_field_energy.argtypes = [vp, P(dbl), dbl, dbl, dbl, P(dbl), vp]

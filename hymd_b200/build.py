@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "csrc", "_obj")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhymd_b200.so")
 SOURCES = ["context.cu", "sort.cu", "paint.cu", "kspace.cu", "readout.cu", "energy.cu",
-           "slabfft.cu", "comm.cu", "migrate.cu", "xline.cu", "planefft.cu", "bonded.cu", "md.cu", "gpe.cu"]
+           "slabfft.cu", "comm.cu", "migrate.cu", "xline.cu", "planefft.cu", "bonded.cu", "md.cu", "gpe.cu", "graph.cu"]
 HEADERS = [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "fft.cuh"), os.path.join(CSRC, "bonded.cuh"),
            os.path.join(CSRC, "md.cuh"), os.path.join(CSRC, "gpe.cuh"), os.path.join(HERE, "..", "include", "hymd_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -508,6 +508,7 @@ struct TermLists {
     const int32_t* idx[3];
     const double* par[3];
     const int32_t* dih_type;
+    const int32_t* dih_last;     // bonds_4_last (only read for dih_type 1)
     long long n_terms[3];
 };
 
@@ -550,6 +551,42 @@ __host__ __device__ inline void inner_step_particle(long long p, const real* __r
     acc[0] = t.n_terms[0] ? particle_terms<real, 2>(p, x_in, box, t.start[0], t.refs[0], t.idx[0], t.par[0], nullptr) : zero;
     acc[1] = t.n_terms[1] ? particle_terms<real, 3>(p, x_in, box, t.start[1], t.refs[1], t.idx[1], t.par[1], nullptr) : zero;
     acc[2] = t.n_terms[2] ? particle_terms<real, 4>(p, x_in, box, t.start[2], t.refs[2], t.idx[2], t.par[2], t.dih_type) : zero;
+    finish_particle<real>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);
+}
+
+// The bending terms of one particle's dtype-1 dihedrals (what cbt_kernel / the CBT variant of the fused step add)
+template <typename real>
+__host__ __device__ inline void particle_cbt(long long p, const real* __restrict__ pos, Vec3d box, const TermLists& t,
+                                             BondAcc& acc) {
+    for (uint32_t r = t.start[2][p]; r < t.start[2][p + 1]; ++r) {
+        const uint32_t ref = t.refs[2][r];
+        const long long term = ref >> 2;
+        if (t.dih_type[term] != 1) continue;
+        const int32_t* ix = t.idx[2] + 4 * term;
+        Vec3d out[4];
+        double e;
+        cbt_eval(pos, box, ix[0], ix[1], ix[2], ix[3], t.par[2] + (long long)DIH_ROWS * DIH_COLS * term, t.dih_last[term],
+                 out, e);
+        acc.f = acc.f + out[ref & 3u];
+        if ((ref & 3u) == 0) acc.e += e;
+    }
+}
+
+// inner_step_particle for topologies with dtype-1 dihedrals: the bending terms join the dihedral kind before the
+// rounding to the array type (a separate instantiation: the common kernels do not carry this code)
+template <typename real>
+__host__ __device__ inline void inner_step_particle_cbt(long long p, const real* __restrict__ x_in,
+                                                        real* __restrict__ x_out, real* __restrict__ vel,
+                                                        Vec3d box, const TermLists& t, real mass, real half_dt,
+                                                        int n_kicks, real dt, real* const* f_out, BondAcc* acc) {
+    const BondAcc zero = {{0.0, 0.0, 0.0}, 0.0, {0.0, 0.0, 0.0}};
+    acc[0] = t.n_terms[0] ? particle_terms<real, 2>(p, x_in, box, t.start[0], t.refs[0], t.idx[0], t.par[0], nullptr) : zero;
+    acc[1] = t.n_terms[1] ? particle_terms<real, 3>(p, x_in, box, t.start[1], t.refs[1], t.idx[1], t.par[1], nullptr) : zero;
+    acc[2] = zero;
+    if (t.n_terms[2]) {
+        acc[2] = particle_terms<real, 4>(p, x_in, box, t.start[2], t.refs[2], t.idx[2], t.par[2], t.dih_type);
+        particle_cbt<real>(p, x_in, box, t, acc[2]);
+    }
     finish_particle<real>(p, x_in, x_out, vel, box, mass, half_dt, n_kicks, dt, f_out, acc);
 }
 

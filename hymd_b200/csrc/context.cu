@@ -287,6 +287,7 @@ int hymd_ctx_destroy(hymd_ctx* c) {
     route_destroy(c);
     comm_destroy(c);
     gpe_destroy(c);
+    graph_destroy(c);
     void* bufs[] = {c->rec, c->rec_alt, c->cell_start, c->q_sorted,
                     c->scalars, c->scan_tmp, c->tab, c->xtw, c->Au, c->cu, c->d_urow, c->outscale, c->phi,
                     c->phi_hat, c->f_hat, c->gmesh, c->v_hat, c->phif_hat, c->tmp_hat, c->v_ext,

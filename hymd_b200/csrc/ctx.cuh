@@ -131,6 +131,7 @@ struct RouteTotals {
     unsigned int n_total;   // n_work + the home particles that are away (kept in an extra bin)
 };
 struct GpeState;
+struct GraphCache;
 
 struct PhaseInterval {
     int phase;
@@ -238,6 +239,7 @@ struct hymd_ctx {
     hymd::MigrateState* mig;
     hymd::RouteState* route;   // per-step routing of particles outside their home slab (several slabs)
     hymd::GpeState* gpe;    // general-Poisson-equation electrostatics (gpe.cu), allocated on first use
+    hymd::GraphCache* graphs;  // CUDA-graph replay of the per-step field update (graph.cu), allocated on first use
 
     // readout TMA
     CUtensorMap tmap_gmesh, tmap_emesh;
@@ -357,6 +359,8 @@ int readout_setup(hymd_ctx* c);
 int readout_forces(hymd_ctx* c, void* d_force, cudaStream_t s);
 int readout_pme(hymd_ctx* c, void* d_force, cudaStream_t s);
 int fill_ghosts(hymd_ctx* c, void* mesh, int nfields, cudaStream_t s);
+// graph.cu
+void graph_destroy(hymd_ctx* c);
 // gpe.cu
 void gpe_destroy(hymd_ctx* c);
 void* gpe_field(hymd_ctx* c, int which, int t);

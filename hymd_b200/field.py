@@ -92,9 +92,7 @@ def update_field(phi, phi_laplacian, phi_transfer, layouts, force_mesh, hamilton
     ``v_ext`` are materialized as well (``field.py:578, 615-616``); otherwise they are computed
     lazily when a handle's ``.value`` is read."""
     pm.sync_interaction(hamiltonian, config, m)
-    pm.sort(positions, types, force=True)
-    _lib.check(pm.lib.hymd_paint(pm._ctx, pm.stream))
-    _lib.check(pm.lib.hymd_field_cycle(pm._ctx, 1 if compute_potential else 0, pm.stream))
+    pm.sort(positions, types, force=True, cycle=1 if compute_potential else 0)
 
 
 def _output_buffer(pm, out, n):

@@ -355,11 +355,15 @@ class ParticleMesh:
             probe = hash(np.ascontiguousarray(a[::step]).tobytes())
         return ("n", id(x), a.ctypes.data, a.shape, a.dtype.str, probe)
 
-    def sort(self, positions, types, charges=None, force=False):
+    def sort(self, positions, types, charges=None, force=False, cycle=None):
         """Bin the local particles (all types at once).  ``update_field`` always re-bins
         (``force=True``: it is the call that opens a step, ``main.py:976-996``);
         ``compute_field_force`` / ``update_field_force_q`` called afterwards on the same
-        positions object reuse its bins (``types=None`` means "whatever the bins hold")."""
+        positions object reuse its bins (``types=None`` means "whatever the bins hold").
+
+        ``cycle`` (``update_field`` only: 0 / 1 = ``compute_potential``): the paint and the field cycle follow
+        the binning inside the same library call (``hymd_update_cycle``), which small systems replay as one
+        CUDA graph."""
         pk = self._fingerprint(positions)
         tk = None if types is None else self._fingerprint_types(types)
         if not force and pk == self._sort_key and (tk is None or tk == self._sort_types_key):
@@ -387,11 +391,14 @@ class ParticleMesh:
             else:
                 ty = self.as_device(types, dtype=torch.int32, shape=(n,))
         q = None if charges is None else self.as_device(charges, shape=(n,), role="charges")
-        _lib.check(self.lib.hymd_sort_particles_ex(
-            self._ctx, ctypes.c_void_p(pos.data_ptr()),
-            ctypes.c_void_p(ty.data_ptr()) if ty is not None else None,
-            ctypes.c_void_p(q.data_ptr()) if q is not None else None, n,
-            _lib.SORT_REUSE_ORDER if reuse else 0, self.stream))
+        args = (self._ctx, ctypes.c_void_p(pos.data_ptr()),
+                ctypes.c_void_p(ty.data_ptr()) if ty is not None else None,
+                ctypes.c_void_p(q.data_ptr()) if q is not None else None, n,
+                _lib.SORT_REUSE_ORDER if reuse else 0)
+        if cycle is None:
+            _lib.check(self.lib.hymd_sort_particles_ex(*args, self.stream))
+        else:
+            _lib.check(self.lib.hymd_update_cycle(*args, int(cycle), self.stream))
         self._keep = (pos, ty, q)   # inputs must outlive the asynchronous kernels
         self._sort_key, self._sort_types_key = pk, tk
         self._order_types_key = otk
@@ -479,6 +486,16 @@ class ParticleMesh:
 
     def launch_count(self):
         return int(self.lib.hymd_launch_count(self._ctx))
+
+    def set_graph(self, mode):
+        """Graph replay of the per-step field update (``hymd_ctx_set_graph``): ``False`` / ``True`` / ``"auto"``."""
+        m = -1 if mode == "auto" else int(bool(mode))
+        _lib.check(self.lib.hymd_ctx_set_graph(self._ctx, m))
+
+    def graph_stats(self):
+        out = (ctypes.c_int64 * 4)()
+        _lib.check(self.lib.hymd_ctx_graph_stats(self._ctx, out))
+        return {"replayed": int(out[0]), "recorded": int(out[1]), "eager": int(out[2]), "alive": int(out[3])}
 
     def reset_order(self):
         """Forget the cached cell order / bins (the caller's particle order changed)."""

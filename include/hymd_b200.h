@@ -148,6 +148,21 @@ int hymd_paint(hymd_ctx* ctx, void* stream);
  * materializes HYMD_FIELD_V_EXT (field.py:615-616) and the filtered HYMD_FIELD_PHI. */
 int hymd_field_cycle(hymd_ctx* ctx, int compute_potential, void* stream);
 
+/* update_field (hymd/field.py:428-616) in one call: hymd_sort_particles_ex + hymd_paint + hymd_field_cycle with the
+ * same arguments and the same results.  On one GPU, for launch-bound systems, the step can be recorded once into a
+ * CUDA graph and replayed with a single submission (hymd_ctx_set_graph): the recording is a stream capture of the
+ * same host code, keyed on n, the flags, the current half of the record double buffer and a digest of the
+ * configuration and of the context's buffers; d_pos may change from call to call (the recorded kernels read a
+ * context-owned staging array that an ordinary copy on the caller's stream fills first).  Steps with
+ * compute_potential != 0, with phase timing enabled, or on several slabs always take the ordinary launches. */
+int hymd_update_cycle(hymd_ctx* ctx, const void* d_pos, const int32_t* d_types, const void* d_charges,
+                      int64_t n, int flags, int compute_potential, void* stream);
+/* Graph replay of hymd_update_cycle: 0 off, 1 on, -1 automatic (on when n <= 2^21 and the mesh has <= 2^21 cells).
+ * The environment variable HYMD_B200_GRAPH (0 | 1 | auto) sets the initial mode of a context. */
+int hymd_ctx_set_graph(hymd_ctx* ctx, int mode);
+/* out = {steps replayed, graphs recorded, steps run eagerly by hymd_update_cycle, graphs alive}. */
+int hymd_ctx_graph_stats(hymd_ctx* ctx, int64_t out[4]);
+
 /* compute_field_force (field.py:152-200): d_force (n,3) row-major, caller particle order. */
 int hymd_readout(hymd_ctx* ctx, void* d_force, void* stream);
 

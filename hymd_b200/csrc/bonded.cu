@@ -108,7 +108,9 @@ struct ForceOut {
 // Fused inner rRESPA step: bonded forces of all kinds + velocity kick(s) + drift/wrap in one pass
 // (48 B per particle of HBM traffic in fp32 instead of 176 B for the four separate launches; the
 // per-kind force arrays are only written on request).
-template <typename real>
+// CBT: topologies with dtype-1 dihedrals -- the bending terms (bonded.cuh: particle_cbt) join the dihedral kind; a
+// separate instantiation, so that the common kernel keeps its registers.
+template <typename real, bool CBT>
 __global__ void __launch_bounds__(BONDED_THREADS) inner_step_kernel(
     const real* __restrict__ x_in, real* __restrict__ x_out, real* __restrict__ vel, long long n, Vec3d box,
     TermLists t, real mass, real half_dt, int n_kicks, real dt, ForceOut fo, double* __restrict__ partial) {
@@ -119,7 +121,8 @@ __global__ void __launch_bounds__(BONDED_THREADS) inner_step_kernel(
     for (int k = 0; k < 12; ++k) v[k] = 0.0;
     if (p < n) {
         real* f_out[3] = {(real*)fo.f[0], (real*)fo.f[1], (real*)fo.f[2]};
-        inner_step_particle<real>(p, x_in, x_out, vel, box, t, mass, half_dt, n_kicks, dt, f_out, acc);
+        if (CBT) inner_step_particle_cbt<real>(p, x_in, x_out, vel, box, t, mass, half_dt, n_kicks, dt, f_out, acc);
+        else inner_step_particle<real>(p, x_in, x_out, vel, box, t, mass, half_dt, n_kicks, dt, f_out, acc);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             v[4 * k] = acc[k].e; v[4 * k + 1] = acc[k].pr.x; v[4 * k + 2] = acc[k].pr.y; v[4 * k + 3] = acc[k].pr.z;
@@ -522,7 +525,9 @@ static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x
                         double mass, double kick_dt, int n_kicks, double drift_dt, void* const* d_force_out,
                         double* d_out, cudaStream_t s) {
     const long long n = b->n_particles;
-    const int per_cta = b->use_cta ? b->tile : BONDED_THREADS;
+    // dtype-1 dihedrals: the per-particle kernel that carries the bending term, whatever evaluation mode is set
+    const bool cbt = b->n_cbt > 0 && ((kind_mask >> 2) & 1);
+    const int per_cta = (b->use_cta && !cbt) ? b->tile : BONDED_THREADS;
     const int blocks = (int)((n + per_cta - 1) / per_cta);
     TermLists t;
     CtaLists c;
@@ -533,9 +538,15 @@ static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x
         c.max_terms[k] = b->max_terms[k];
     }
     t.dih_type = b->dih_type;
+    t.dih_last = b->dih_last;
     ForceOut fo;
     for (int k = 0; k < 3; ++k) fo.f[k] = d_force_out ? d_force_out[k] : nullptr;
-    if (blocks > 0 && b->f32math && sizeof(real) == 4 && !b->use_cta) {
+    if (blocks > 0 && cbt) {
+        inner_step_kernel<real, true><<<blocks, BONDED_THREADS, 0, s>>>(x_in, x_out, vel, n, box, t, (real)mass,
+                                                                        (real)(0.5 * kick_dt), n_kicks,
+                                                                        (real)drift_dt, fo, b->partial);
+        HYMD_LAUNCH_CHECK(b);
+    } else if (blocks > 0 && b->f32math && sizeof(real) == 4 && !b->use_cta) {
         inner_step_f32_kernel<<<blocks, BONDED_THREADS, 0, s>>>((const float*)x_in, (float*)x_out, (float*)vel, n, box,
                                                               t, (float)mass, (float)(0.5 * kick_dt), n_kicks,
                                                               (float)drift_dt, fo, b->partial);
@@ -566,9 +577,9 @@ static int launch_inner(hymd_bonded* b, int kind_mask, const real* x_in, real* x
 #undef HYMD_CTA_LAUNCH
         }
         else
-            inner_step_kernel<real><<<blocks, BONDED_THREADS, 0, s>>>(x_in, x_out, vel, n, box, t, (real)mass,
-                                                                      (real)(0.5 * kick_dt), n_kicks,
-                                                                      (real)drift_dt, fo, b->partial);
+            inner_step_kernel<real, false><<<blocks, BONDED_THREADS, 0, s>>>(x_in, x_out, vel, n, box, t, (real)mass,
+                                                                             (real)(0.5 * kick_dt), n_kicks,
+                                                                             (real)drift_dt, fo, b->partial);
         HYMD_LAUNCH_CHECK(b);
     }
     if (d_out) {
@@ -755,11 +766,6 @@ int hymd_bonded_inner_step(hymd_bonded* b, int dtype, const void* d_pos_in, void
     }
     if (n_kicks < 0 || n_kicks > 2) { set_error("n_kicks = %d, expected 0, 1 or 2", n_kicks); return HYMD_ERR_INVALID; }
     if (d_pos_out == d_pos_in) { set_error("hymd_bonded_inner_step: d_pos_out must not alias d_pos_in"); return HYMD_ERR_INVALID; }
-    if (b->n_cbt > 0) {
-        set_error("hymd_bonded_inner_step: the topology has %lld dihedrals of dih_type 1 (combined bending-torsion), whose "
-                  "bending term is a separate pass: use hymd_bonded_forces + hymd_md_kick_drift", b->n_cbt);
-        return HYMD_ERR_STATE;
-    }
     if (dtype != HYMD_F32 && dtype != HYMD_F64) { set_error("bad dtype %d", dtype); return HYMD_ERR_INVALID; }
     const Vec3d bx = {box[0], box[1], box[2]};
     cudaStream_t s = (cudaStream_t)stream;

@@ -156,9 +156,9 @@ class RespaMD:
         ``fused=False`` (or no topology) runs the four separate launches per inner step."""
         outer = self.inner * self.dt
         kick_drift(velocities, None, slow_forces, self.mass, outer, sequential=True)     # main.py:803-827
-        # dihedrals of dih_type 1 carry a bending term that is a separate pass of hymd_bonded_forces: such
-        # topologies take the unfused inner loop (the fused kernel refuses them)
-        if self.topology is not None and self.fused and not getattr(self.topology, "n_cbt", 0):
+        # (topologies with dihedrals of dih_type 1 run the per-particle variant of the fused kernel that carries
+        # the bending term, whatever ``cta`` says)
+        if self.topology is not None and self.fused:
             self._fused_inner(positions, velocities)
         else:
             if self.topology is not None and self.topology._cta not in (None, 0):

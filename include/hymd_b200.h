@@ -327,7 +327,8 @@ int64_t hymd_bonded_launch_count(hymd_bonded* b);
  *   cdf): 1 marks the last dihedral of a backbone, whose second angle b-c-d carries a bending term and a dipole as
  *   well.  All zeros until it is called.  Synchronous.
  * hymd_bonded_forces(kind = 4) includes the bending term (a second pass over the particles; topologies without
- *   dih_type 1 never launch it); hymd_bonded_inner_step refuses such topologies (HYMD_ERR_STATE).
+ *   dih_type 1 never launch it); hymd_bonded_inner_step runs such topologies through the per-particle variant of its
+ *   kernel that carries the bending term, whatever hymd_bonded_set_cta selected.
  * hymd_bonded_dipoles: what cdf leaves in `dipoles` (n4,4,3) and `transfer_matrix` (n4,6,3,3) with dipole_flag = 1,
  *   row-major in `dtype` -- the reconstructed backbone dipole charges' positions (wrapped into the box) and the
  *   matrices that carry forces on them back to the beads; zeros for dihedrals of other types.

@@ -443,6 +443,31 @@ static void inner(HostBonded* b, int kind_mask, const real* x_in, real* x_out, r
     if (out12) for (int k = 0; k < 12; ++k) out12[k] = acc12[k];
 }
 
+template <typename real>
+static void inner_cbt(HostBonded* b, const real* x_in, real* x_out, real* vel, const double* box, double mass,
+                      double kick_dt, int n_kicks, double drift_dt, void* const* f_out, double* out12) {
+    TermLists t;
+    for (int k = 0; k < 3; ++k) {
+        t.start[k] = b->start[k].data(); t.refs[k] = b->refs[k].data(); t.idx[k] = b->idx[k].data();
+        t.par[k] = b->par[k].data(); t.n_terms[k] = (long long)(b->idx[k].size() / 4);
+    }
+    t.dih_type = b->dtype.data();
+    t.dih_last = b->last.data();
+    const Vec3d bx = {box[0], box[1], box[2]};
+    real* fo[3] = {f_out ? (real*)f_out[0] : nullptr, f_out ? (real*)f_out[1] : nullptr, f_out ? (real*)f_out[2] : nullptr};
+    double acc12[12] = {0};
+    for (long long p = 0; p < b->n; ++p) {
+        BondAcc acc[3];
+        inner_step_particle_cbt<real>(p, x_in, x_out, vel, bx, t, (real)mass, (real)(0.5 * kick_dt), n_kicks,
+                                      (real)drift_dt, fo, acc);
+        for (int k = 0; k < 3; ++k) {
+            acc12[4 * k] += acc[k].e; acc12[4 * k + 1] += acc[k].pr.x; acc12[4 * k + 2] += acc[k].pr.y;
+            acc12[4 * k + 3] += acc[k].pr.z;
+        }
+    }
+    if (out12) for (int k = 0; k < 12; ++k) out12[k] = acc12[k];
+}
+
 extern "C" int hymd_bonded_set_cta(void* h, int enable) { ((HostBonded*)h)->use_cta = (enable == 2 || enable == 3) ? enable : (enable ? 1 : 0); return 0; }
 
 extern "C" int host_inner_step_f32(void* h, const float* x_in, float* x_out, float* vel, const double* box,
@@ -455,7 +480,14 @@ extern "C" int hymd_bonded_inner_step(void* h, int dtype, const void* x_in, void
                                       double drift_dt, void* const* f_out, double* out12, void* stream) {
     HostBonded* b = (HostBonded*)h;
     if (n_kicks < 0 || n_kicks > 2 || x_in == x_out) return -1;
-    for (int32_t t : b->dtype) if (t == 1) return -6;       // HYMD_ERR_STATE: the bending term is a separate pass
+    bool cbt = false;
+    for (int32_t t : b->dtype) cbt = cbt || t == 1;
+    if (cbt) {      // dtype-1 dihedrals: the per-particle variant that carries the bending term (inner_step_kernel<real, true>)
+        b->launches += out12 ? 2 : 1;
+        if (dtype == 1) inner_cbt<double>(b, (const double*)x_in, (double*)x_out, (double*)vel, box, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
+        else inner_cbt<float>(b, (const float*)x_in, (float*)x_out, (float*)vel, box, mass, kick_dt, n_kicks, drift_dt, f_out, out12);
+        return 0;
+    }
     if (b->f32math && dtype == 0 && !b->use_cta) {
         b->launches += out12 ? 2 : 1;
         return host_inner_step_f32(h, (const float*)x_in, (float*)x_out, (float*)vel, box, mass, kick_dt, n_kicks,

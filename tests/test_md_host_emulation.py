@@ -70,8 +70,9 @@ def test_cbt_dihedrals(emulated, real):
     emulated.test_cbt_dihedrals_dipoles_and_redistribution_match_oracle(real)
 
 
-def test_respa_md_with_cbt(emulated):
-    emulated.test_respa_md_with_cbt_dihedrals_takes_the_unfused_loop()
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_respa_md_with_cbt(emulated, real):
+    emulated.test_respa_md_with_cbt_dihedrals_fused_equals_separate_launches(real)
 
 
 def test_bonded_kats_and_edges(emulated):

@@ -146,10 +146,12 @@ def test_cbt_dihedrals_dipoles_and_redistribution_match_oracle(real):
     fbn = np.zeros((n, 3), dtype=real)
     F.dipole_forces_redistribution(fbn, fd, tmn, *idx, dt, last)
     assert np.abs(fbn - want).max() < 2 * tol * max(1.0, np.abs(want).max())
-    # the fused inner step refuses such a topology instead of dropping the bending term
+    # the fused inner step carries the bending term: the dihedral force array it hands out is cdf's
     topo = F.BondedTopology(n, dihedrals=(*idx, coeff, dt, last), device=DEVICE)
-    with pytest.raises(_lib.HymdError):
-        topo.inner_step(pos, torch.empty_like(pos), torch.zeros_like(pos), box, 72.0, 0.01, 1, 0.01)
+    f3 = [None, None, torch.zeros_like(pos)]
+    res = topo.inner_step(pos, None, torch.zeros_like(pos), box, 72.0, 0.01, 1, 0.0, force_out=f3)
+    assert np.abs(f3[2].cpu().numpy() - fo_).max() < tol * scale
+    assert float(res[2][0]) == pytest.approx(eo, rel=tol)
 
 
 def test_reference_kats_on_the_device_and_numpy_interface():
@@ -385,40 +387,56 @@ def test_fused_inner_step_equals_separate_launches(real):
         assert out[True][2][k] == pytest.approx(out[False][2][k], rel=1e-6 if real == np.float32 else 1e-11)
 
 
-def test_respa_md_with_cbt_dihedrals_takes_the_unfused_loop():
-    """A topology with dih_type 1 through RespaMD: the fused inner-step kernel does not carry the bending term, so
-    ``fused=True`` must run the separate launches (bitwise the same trajectory as ``fused=False``), and the dihedral
-    energy it reports is the oracle's for the final positions."""
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_respa_md_with_cbt_dihedrals_fused_equals_separate_launches(real):
+    """A topology with dih_type 1 through RespaMD: the fused inner step runs the per-particle kernel variant that
+    carries the bending term (inner_step_kernel<real, true>, whatever ``cta`` says) and must follow the separate
+    launches (dihedral kernel + bending pass + kick / drift) to rounding; the dihedral energy it reports is the
+    oracle's for the final positions."""
     from hymd_b200.force import BondedTopology
     from hymd_b200.md import RespaMD
     rng = np.random.default_rng(44)
     box = np.array([4.0, 5.0, 4.5])
     n = 60
-    r = np.mod(np.cumsum(rng.normal(scale=0.25, size=(n, 3)), axis=0) + 2.0, box)
-    a2, a4 = np.arange(n - 1), np.arange(n - 3)
+    r = np.mod(np.cumsum(rng.normal(scale=0.25, size=(n, 3)), axis=0) + 2.0, box).astype(real)
+    a2, a3, a4 = np.arange(n - 1), np.arange(n - 2), np.arange(n - 3)
     coeff = np.zeros((len(a4), 6, 5))
     coeff[:, 0] = rng.uniform(0.5, 2.0, size=(len(a4), 5))
     coeff[:, 4] = rng.uniform(20, 40, size=(len(a4), 5))
     dt4 = np.ones(len(a4), dtype=int)
+    dt4[::5] = 0                      # a few plain cosine-series dihedrals among them
     last = np.zeros(len(a4), dtype=int)
     last[-1] = 1
     topo = BondedTopology(n, bonds=(a2, a2 + 1, np.full(n - 1, 0.47), np.full(n - 1, 1250.0)),
+                          angles=(a3, a3 + 1, a3 + 2, np.full(n - 2, 2.0), np.full(n - 2, 25.0)),
                           dihedrals=(a4, a4 + 1, a4 + 2, a4 + 3, coeff, dt4, last),
                           device=DEVICE if DEVICE != "cuda" else None)
-    assert topo.n_cbt == len(a4)
-    v = rng.normal(scale=0.1, size=(n, 3))
+    assert topo.n_cbt == int((dt4 == 1).sum())
+    v = rng.normal(scale=0.1, size=(n, 3)).astype(real)
     out = {}
     for fused in (True, False):
-        md = RespaMD(lambda x: [torch.zeros_like(x)], box, 72.0, 0.002, respa_inner=4, topology=topo, fused=fused)
-        xd, vd = dev(r, np.float64), dev(v, np.float64)
+        md = RespaMD(lambda x: [torch.zeros_like(x)], box, 72.0, 0.002, respa_inner=3, topology=topo, fused=fused)
+        xd, vd = dev(r, real), dev(v, real)
         f = [torch.zeros_like(xd)]
         for _ in range(3):
             f = md.step(xd, vd, f)
-        out[fused] = (xd.cpu().numpy(), vd.cpu().numpy(), md.bonded_energies())
-    assert np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1])
+        out[fused] = (xd.cpu().numpy().astype(np.float64), vd.cpu().numpy().astype(np.float64), md.bonded_energies())
+    eps = np.finfo(real).eps
+    d = np.abs(out[True][0] - out[False][0])
+    d = np.minimum(d, np.abs(d - box[None, :]))
+    assert d.max() <= 256 * eps * box.max()
+    assert np.abs(out[True][1] - out[False][1]).max() <= 256 * eps * np.abs(out[False][1]).max()
+    for k in (2, 3, 4):
+        assert out[True][2][k] == pytest.approx(out[False][2][k], rel=2e-5 if real == np.float32 else 1e-10)
     # energies belong to the positions of the last inner force evaluation = the final positions
     fo_, eo = bo.compute_dihedral_forces(out[True][0], box, a4, a4 + 1, a4 + 2, a4 + 3, coeff, dt4, last)
-    assert out[True][2][4] == pytest.approx(eo, rel=1e-10)
+    assert out[True][2][4] == pytest.approx(eo, rel=1e-5 if real == np.float32 else 1e-10)
+    # the standalone entry point with the per-kind force arrays: bending + torsion land in the dihedral array
+    x = dev(out[True][0], real)
+    f3 = [torch.zeros_like(x) for _ in range(3)]
+    vv = dev(v, real)
+    topo.inner_step(x, None, vv, box, 72.0, 0.002, 1, 0.0, force_out=f3, cta=1)
+    assert np.abs(f3[2].cpu().numpy() - fo_).max() < (1e-5 if real == np.float32 else 1e-10) * np.abs(fo_).max()
 
 
 def test_fused_step_edge_cases():

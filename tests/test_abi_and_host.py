@@ -28,6 +28,49 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().hymd_abi_version() == 1
 
 
+def _header_prototypes():
+    """{name: (return type, [parameter declarations])} of every prototype in the header."""
+    src = open(os.path.join(ROOT, "include", "hymd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for ret, name, params in re.findall(r"^\s*((?:const\s+)?[a-z_0-9]+\s*\*?)\s*(hymd_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", src,
+                                        flags=re.M | re.S):
+        plist = [q.strip() for q in params.split(",")] if params.strip() not in ("", "void") else []
+        out[name] = (ret.strip(), plist)
+    return out
+
+
+def test_ctypes_binding_matches_the_header_prototypes():
+    """Every prototype of include/hymd_b200.h against the argtypes / restype hymd_b200/_lib.py declares: same
+    number of parameters, pointers bound as pointers, 64-bit integers as 64-bit, doubles as doubles (a binding
+    that drifts from the header corrupts the call silently: ctypes checks nothing)."""
+    from hymd_b200 import _lib
+    lib = _lib.load()
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(_lib.EXPORTS)
+    pointer_like = (ctypes.c_void_p, ctypes.c_char_p)
+    for name, (ret, params) in protos.items():
+        fn = getattr(lib, name)
+        argtypes = fn.argtypes
+        if argtypes is None:            # entry points the Python layer never calls with arguments
+            assert not params or name in ("hymd_abi_version",), f"{name}: no argtypes declared"
+            continue
+        assert len(argtypes) == len(params), f"{name}: header has {len(params)} parameters, binding {len(argtypes)}"
+        for decl, at in zip(params, argtypes):
+            is_ptr = "*" in decl or "[" in decl
+            bound_ptr = issubclass(at, pointer_like) or hasattr(at, "contents") or issubclass(at, ctypes.Array)
+            assert is_ptr == bound_ptr, f"{name}: '{decl}' bound as {at.__name__}"
+            if not is_ptr:
+                base = decl.replace("const", "").split()[0]
+                want = {"int": 4, "int32_t": 4, "int64_t": 8, "double": 8}[base]
+                assert ctypes.sizeof(at) == want, f"{name}: '{decl}' bound as {at.__name__}"
+                assert (base == "double") == (at is ctypes.c_double), f"{name}: '{decl}' bound as {at.__name__}"
+        if ret == "int64_t":
+            assert fn.restype is ctypes.c_int64, name
+        elif ret.replace(" ", "") == "constchar*":
+            assert fn.restype is ctypes.c_char_p, name
+
+
 def test_config_struct_matches_header_layout():
     from hymd_b200 import _lib
     # 5 int32 (+4 pad) + 3 double + 4 int32 + 2 double + (32*32 + 32 + 32) double

@@ -17,6 +17,7 @@ module             mirrors (reference, HyMD v2.2.0)
 ``thermostat``     ``hymd/thermostat.py``: csvr_thermostat, cancel_com_momentum, generate_initial_velocities
 ``md``             ``hymd/integrator.py`` and the rRESPA loop of ``main.py:801-1169`` (RespaMD)
 ``hamiltonian``    ``hymd/hamiltonian.py``; ``config`` the field-relevant slice of ``input_parser.Config``
+``file_io``        ``hymd/file_io.py``: OutDataset, store_static, store_data, distribute_input (needs h5py)
 =================  ==========================================================================
 """
 __version__ = "0.1.0"

@@ -312,3 +312,13 @@ def test_without_h5py_the_layer_says_so(tmp_path):
     fio.set_backend(None)
     with pytest.raises(HymdError, match="h5py"):
         fio.OutDataset(tmp_path, Cfg("x"))
+
+
+@pytest.mark.parametrize("nproc", [2, 3])
+def test_file_io_over_process_ranks(nproc):
+    """torch.distributed (gloo) ranks instead of threads: tests/gloo_file_io_worker.py."""
+    from conftest import ROOT
+    from test_gloo_slabs import _torchrun
+    r = _torchrun(nproc, os.path.join(ROOT, "tests", "gloo_file_io_worker.py"), [], 29641 + nproc)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "OK" in r.stdout
